@@ -1,0 +1,205 @@
+/* ttam.h — C ABI of libttam.so: the B200 (sm_100a) hot path of the two-tower recommender.
+ *
+ * The reference (alperkartkaya2-afk/two-tower-augmented-with-adaptive-mimic-mechanism) is pure
+ * Python/PyTorch and has no FFI layer, so there is no existing binding to mirror; each entry point
+ * below replaces one chain of ATen calls on the reference's hot path and cites it (file:line relative
+ * to the reference root).  INTEGRATION.md shows the ctypes stub a maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; row-major, contiguous rows
+ *   - indices are int64 (reference: datasets.py:34-39, adaptive_mimic.py:101-102); floats are fp32
+ *     unless the name says bf16 (uint16_t storage)
+ *   - no allocation, no host synchronisation inside; work is enqueued on `stream` (a cudaStream_t
+ *     passed as void*); callers provide outputs and workspaces (ttam_*_workspace_bytes tells how much)
+ *   - return 0 on success, a negative TTAM_E* code otherwise; ttam_last_error() returns a
+ *     thread-local message for the last failing call
+ */
+#ifndef TTAM_H_
+#define TTAM_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TTAM_OK 0
+#define TTAM_EINVAL -1      /* bad argument (shape, alignment, unsupported option) */
+#define TTAM_ECUDA -2       /* a CUDA runtime call failed (launch error is sticky: see message) */
+#define TTAM_EWORKSPACE -3  /* workspace too small */
+#define TTAM_EUNSUPPORTED -4
+
+/* activations of build_feature_encoder (encoders.py:68-78) */
+#define TTAM_ACT_NONE 0
+#define TTAM_ACT_RELU 1
+#define TTAM_ACT_GELU 2
+#define TTAM_ACT_TANH 3
+#define TTAM_ACT_SELU 4
+
+/* arithmetic of the GEMM-shaped ops */
+#define TTAM_PREC_FP32 0 /* SIMT FFMA, fp32 in / fp32 accumulate (bit-faithful to the fp32 reference up to summation order) */
+#define TTAM_PREC_TF32 1 /* tcgen05 kind::tf32, fp32 accumulate in TMEM */
+#define TTAM_PREC_BF16 2 /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate in TMEM */
+
+/* dense optimiser kinds (training.py:1315-1333) */
+#define TTAM_OPT_ADAMW 0
+#define TTAM_OPT_ADAM 1
+#define TTAM_OPT_SGD 2
+
+/* Device-resident per-step state.  Kernels that depend on the step number (bias corrections, dropout
+ * counters) read it from here when given a non-null pointer, so that one captured CUDA graph can be
+ * replayed for every step; ttam_advance_step bumps it at the head of the step. */
+typedef struct {
+  int32_t step;        /* 1-based optimiser step of the step in flight */
+  int32_t pad_;
+  uint64_t rng_offset; /* added to every dropout counter */
+} ttam_step_state;
+int ttam_advance_step(ttam_step_state* state_dev, uint64_t rng_stride, void* stream);
+
+const char* ttam_last_error(void);
+int ttam_version(void);
+/* number of kernel launches this library has issued in this process (bench.py's gpu_launches) */
+int64_t ttam_launch_count(void);
+/* 1 if the library was built with sm_100a SASS and the current device can run it */
+int ttam_device_ok(void);
+
+/* ---- row gather ------------------------------------------------------------------------------
+ * out[r, 0:ncols] = table[idx[r], 0:ncols].  Replaces nn.Embedding.forward for the ID tables
+ * (encoders.py:223), the augmentation tables (adaptive_mimic.py:97-105) and index_select on the
+ * feature matrices (training.py:743,747,775). */
+int ttam_gather_rows_f32(const float* table, int64_t ld_table, int64_t num_rows, const int64_t* idx,
+                         float* out, int64_t ld_out, int64_t R, int64_t ncols, void* stream);
+/* fp32 -> bf16 (round-to-nearest-even) row cast, used to build the retrieval corpus */
+int ttam_cast_f32_to_bf16(const float* src, int64_t ld_src, uint16_t* dst, int64_t ld_dst, int64_t R,
+                          int64_t ncols, void* stream);
+
+/* ---- linear layers (encoders.py:121-144, 157-162) ------------------------------------------------
+ * fwd  : y[M,N] = dropout_p(act(x[gather?][M,K] . w[N,K]^T + bias[N]))      nn.Linear + activation + nn.Dropout
+ *        if `gather` is non-null the rows of x are x[gather[m]] (fused index_select, training.py:743-775)
+ *        dropout: Philox4x32-10 keyed by (seed, offset + state_dev->rng_offset + m*N + n); kept value
+ *        scaled by 1/(1-p).  state_dev (nullable) is the device-resident step state below, so that a
+ *        captured CUDA graph draws a fresh mask on every replay.
+ * dgrad: dx[M,K] (+)= (dy[M,N] . w[N,K]) * act'(...) optional
+ *        mask_mode 0: none; 1: multiply by (aux[m,k] > 0)  (ReLU/dropout backward through the saved output)
+ *        accumulate != 0 adds into dx
+ * wgrad: dw[N,K] = dy[M,N]^T . x[gather?][M,K] ; db[N] = colsum(dy)   (deterministic split-M reduction) */
+int ttam_linear_fwd(const float* x, int64_t ldx, const int64_t* gather, const float* w, const float* bias,
+                    float* y, int64_t ldy, int64_t M, int64_t N, int64_t K, int act, float dropout_p,
+                    uint64_t seed, uint64_t offset, const ttam_step_state* state_dev, int precision,
+                    void* stream);
+int ttam_linear_dgrad(const float* dy, int64_t lddy, const float* w, float* dx, int64_t lddx,
+                      const float* aux, int64_t ldaux, int mask_mode, float scale, int accumulate,
+                      int64_t M, int64_t N, int64_t K, int precision, void* stream);
+int64_t ttam_linear_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int ttam_linear_wgrad(const float* dy, int64_t lddy, const float* x, int64_t ldx, const int64_t* gather,
+                      float* dw, float* db, int64_t M, int64_t N, int64_t K, int accumulate,
+                      void* workspace, int64_t workspace_bytes, int precision, void* stream);
+
+/* elementwise activation + dropout for the non-ReLU feature encoders (encoders.py:68-78,136-137):
+ * fwd: y = dropout_p(act(pre));  bwd: dpre = dy * keep/(1-p) * act'(pre)   (mask regenerated from Philox) */
+int ttam_act_fwd(const float* pre, float* y, int64_t n, int64_t row_len, int act, float dropout_p, uint64_t seed,
+                 uint64_t offset, const ttam_step_state* state_dev, void* stream);
+int ttam_act_bwd(const float* dy, const float* pre, float* dpre, int64_t n, int64_t row_len, int act,
+                 float dropout_p, uint64_t seed, uint64_t offset, const ttam_step_state* state_dev, void* stream);
+
+/* ---- gated fusion + augmentation (encoders.py:149-168, adaptive_mimic.py:88-105) -----------------
+ * z[R,2D] = [e ; f];  pre2[R,D] = G2.relu(G1.z+c1)+c2 (computed by two ttam_linear_fwd calls)
+ * fwd: g = sigmoid(pre2); t = g*e + (1-g)*f; o = t + aug[idx]        (aug may be null: o = t)
+ * bwd: dpre2 = dt*(e-f)*g*(1-g);  dz = [dt*g ; dt*(1-g)]               */
+int ttam_gate_fwd(const float* z, const float* pre2, const float* aug_table, int64_t aug_rows,
+                  const int64_t* idx, float* g, float* t, float* o, float* q_out, int64_t R, int64_t D,
+                  void* stream);
+int ttam_gate_bwd(const float* dt, const float* z, const float* g, float* dpre2, float* dz, int64_t R,
+                  int64_t D, void* stream);
+/* o[r] = t[r] + aug[idx[r]]   (AdaptiveMimicMechanism._apply_aug, adaptive_mimic.py:88-95) */
+int ttam_augment_fwd(const float* t, const float* aug_table, int64_t aug_rows, const int64_t* idx, float* o,
+                     float* q_out, int64_t R, int64_t D, void* stream);
+
+/* ---- fused loss forward+backward (training.py:770-803, adaptive_mimic.py:59-68) -------------------
+ * o_u[B,D], o_i[(1+N)B,D] (positives first, then negatives row-major [B,N]); t_u,t_p[B,D] base tower
+ * outputs, q_u,q_p[B,D] augmentation rows of the positive pairs (all four null when mimic is off).
+ * loss_out[4] = {total, bce, mimic_user, mimic_item}.  Gradients (null pointers skip the backward):
+ *   do_u[B,D], do_i[(1+N)B,D]  = dL/do = dL/dt ;  dq_u[B,D], dq_p[B,D] = dL/dq of the positive pairs
+ *   (dL/dq of a negative row equals its do_i row). */
+int64_t ttam_loss_workspace_bytes(int64_t B);
+int ttam_loss_fwd_bwd(const float* o_u, const float* o_i, const float* t_u, const float* t_p,
+                      const float* q_u, const float* q_p, float lambda_u, float lambda_i, float* loss_out,
+                      float* do_u, float* do_i, float* dq_u, float* dq_p, int64_t B, int64_t N, int64_t D,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- sparse backward + row-wise optimisers ---------------------------------------------------------
+ * Step 1  ttam_sort_rows: stable radix sort of the R touched row ids; sorted_idx[R], perm[R] (int32:
+ *         original positions).  Replaces coalesce() of the uncoalesced COO gradient
+ *         (torch/optim/_functional.py:44, training.py:822).
+ * Step 2  one of the row-wise updates; each (unique row) sums its duplicate gradient rows in sorted
+ *         (= original) order and applies the optimiser in one pass over p, m, v.  Gradient rows come
+ *         from two sources so that no concatenation is materialised: positions < n_a read
+ *         grad_a[pos*ld_a], the others grad_b[(pos-n_a)*ld_b].
+ *   Hyper-parameters are doubles (Python floats); each is rounded to fp32 where torch rounds it.
+ *   ttam_sparse_adam_rows : torch.optim.SparseAdam (torch/optim/_functional.py:24-84); `step` is the
+ *                           per-table step count (1-based)
+ *   ttam_lazy_rows        : dense AdamW / Adam / SGD(momentum) semantics (torch/optim/adam.py:347-547)
+ *                           on a table whose untouched rows are brought up to date lazily:
+ *                           last_step[row] records the last step applied; the zero-gradient steps in
+ *                           between are replayed in registers before the real one.  scalars[4*t+0] =
+ *                           lr/(1-beta1^t), [4*t+1] = sqrt(1-beta2^t), [4*t+2] = lr*sqrt(1-beta2^t)/(1-beta1^t)
+ *                           (SparseAdam step size), [4*t+3] unused; t = 0..step, computed in double, stored fp32.
+ *   Every row-wise update takes `step` by value and, optionally, `state_dev`: when non-null the step is
+ *   read from the device (state_dev->step) and the scalars from the table, which makes the launch
+ *   replayable inside a CUDA graph.
+ *   ttam_lazy_flush       : bring rows [0,num_rows) up to `step` (before any full-table read).
+ * ttam_unique_rows: the sorted set of touched rows (what SparseAdam updates), n_unique on the device. */
+int64_t ttam_sort_workspace_bytes(int64_t R);
+int ttam_sort_rows(const int64_t* idx, int64_t R, int64_t num_rows, int64_t* sorted_idx, int32_t* perm,
+                   void* workspace, int64_t workspace_bytes, void* stream);
+int ttam_unique_rows(const int64_t* sorted_idx, int64_t R, int64_t* unique_out, int64_t* n_unique_out,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+int ttam_sparse_adam_rows(float* p, float* m, float* v, int64_t D, const int64_t* sorted_idx,
+                          const int32_t* perm, int64_t R, const float* grad_a, int64_t ld_a, int64_t n_a,
+                          const float* grad_b, int64_t ld_b, const float* scalars, double lr, double beta1,
+                          double beta2, double eps, int64_t step, const ttam_step_state* state_dev, void* stream);
+int ttam_lazy_rows(int kind, float* p, float* m, float* v, int32_t* last_step, int64_t D,
+                   const int64_t* sorted_idx, const int32_t* perm, int64_t R, const float* grad_a,
+                   int64_t ld_a, int64_t n_a, const float* grad_b, int64_t ld_b, const float* scalars,
+                   double lr, double weight_decay, double beta1, double beta2, double eps, double momentum,
+                   int64_t step, const ttam_step_state* state_dev, void* stream);
+int ttam_lazy_flush(int kind, float* p, float* m, float* v, int32_t* last_step, int64_t num_rows, int64_t D,
+                    const float* scalars, double lr, double weight_decay, double beta1, double beta2, double eps,
+                    double momentum, int64_t step, const ttam_step_state* state_dev, void* stream);
+/* dense AdamW / Adam / SGD over up to TTAM_MAX_TENSORS small tensors in ONE launch
+ * (the MLP / gate weights and biases; torch/optim/adam.py:347-547) */
+#define TTAM_MAX_TENSORS 48
+typedef struct {
+  int32_t count;
+  int32_t pad_;
+  float* p[TTAM_MAX_TENSORS];
+  const float* g[TTAM_MAX_TENSORS];
+  float* m[TTAM_MAX_TENSORS];
+  float* v[TTAM_MAX_TENSORS];
+  int64_t numel[TTAM_MAX_TENSORS];
+} ttam_tensor_list;
+int ttam_dense_step(int kind, const ttam_tensor_list* list_host, const float* scalars, double lr,
+                    double weight_decay, double beta1, double beta2, double eps, double momentum, int64_t step,
+                    const ttam_step_state* state_dev, void* stream);
+
+/* ---- retrieval (training.py:330-384, 613-679, 944-972; faiss.IndexFlatIP) --------------------------
+ * Exact inner-product top-K of every query against the whole corpus, result in canonical order
+ * (descending score, ascending id on ties).  Scores returned are the canonical fp32 scores
+ * (sequential accumulation over d).  id_offset is added to every returned id (item-sharded corpora).
+ *   ttam_topk_f32 : fp32 operands, SIMT                       (drop-in for the fp32 FAISS path)
+ *   ttam_topk_bf16: bf16 operands, TMA-fed tcgen05 GEMM with an in-kernel threshold top-K epilogue,
+ *                   followed by an exact re-score + (-score,+id) sort of the survivors
+ *   ttam_topk_merge: merge `parts` partial lists per query (item shards) under the same order */
+int64_t ttam_topk_f32_workspace_bytes(int64_t Q, int64_t N, int64_t D, int64_t K);
+int ttam_topk_f32(const float* q, const float* items, int64_t Q, int64_t N, int64_t D, int64_t K,
+                  int64_t id_offset, int64_t* out_ids, float* out_scores, void* workspace,
+                  int64_t workspace_bytes, void* stream);
+int64_t ttam_topk_bf16_workspace_bytes(int64_t Q, int64_t N, int64_t D, int64_t K);
+int ttam_topk_bf16(const uint16_t* q, const uint16_t* items, int64_t Q, int64_t N, int64_t D, int64_t K,
+                   int64_t id_offset, int64_t* out_ids, float* out_scores, void* workspace,
+                   int64_t workspace_bytes, void* stream);
+int ttam_topk_merge(const int64_t* ids, const float* scores, int64_t Q, int64_t parts, int64_t K_in,
+                    int64_t K_out, int64_t* out_ids, float* out_scores, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TTAM_H_ */

@@ -33,3 +33,43 @@ def load_case(name):
 def state_after(d, step):
     pre = f"after{step}/"
     return {k[len(pre):]: v for k, v in d.items() if k.startswith(pre)}
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU-side helpers (import torch lazily so that the CPU-only oracle tests stay light)
+# ---------------------------------------------------------------------------------------------
+def tower_cfg(meta, kw, state, side):
+    D, H, Hg = meta["D"], meta["H"], meta["Hg"]
+    sparse = kw.get("sparse", True)
+    pre = f"{side}_encoder."
+    if not any(k.startswith(pre + "feature_encoder") for k in state):
+        return {"type": "embedding", "params": {"embedding_dim": D, "sparse": sparse}}
+    fe_type = "linear" if pre + "feature_encoder.network.weight" in state else "mlp"
+    cfg = {"type": "tower",
+           "id_embedding": {"params": {"embedding_dim": D, "sparse": sparse}},
+           "feature_encoder": {"type": fe_type, "hidden_dims": [H] if fe_type == "mlp" else None,
+                               "activation": "relu", "output_dim": D, "dropout": 0.0},
+           "fusion": kw.get("fusion", "gated"), "output_dim": D}
+    if Hg:
+        cfg["adaptive_mimic"] = {"hidden_dim": Hg}
+    return cfg
+
+
+def build_model(meta, kw, state, device, pkg=None):
+    """Our TwoTowerModel with the golden case's structure and `state` loaded (state: name -> np.ndarray)."""
+    import torch
+    if pkg is None:
+        import two_tower_augmented_with_adaptive_mimic_mechanism_b200 as pkg
+    ue = pkg.build_tower_encoder(tower_cfg(meta, kw, state, "user"), num_embeddings=meta["NU"], feature_dim=meta["F"])
+    ie = pkg.build_tower_encoder(tower_cfg(meta, kw, state, "item"), num_embeddings=meta["NI"], feature_dim=meta["F"])
+    mm = None
+    if "adaptive_mimic.user_augmented.weight" in state:
+        mm = pkg.AdaptiveMimicMechanism(num_users=meta["NU"], num_items=meta["NI"], embedding_dim=meta["D"])
+    model = pkg.TwoTowerModel(ue, ie, adaptive_mimic=mm)
+    missing = model.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in state.items()}, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return model.to(device)
+
+
+def model_state_np(model):
+    return {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}

@@ -1,0 +1,56 @@
+"""The C-ABI shared library loads and exports every symbol include/ttam.h declares (no compute here)."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.fixture(scope="module")
+def built():
+    from two_tower_augmented_with_adaptive_mimic_mechanism_b200 import _lib
+    _lib.build()
+    return _lib
+
+
+def _declared():
+    text = (ROOT / "include" / "ttam.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ttam_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(built):
+    names = _declared()
+    assert len(names) >= 25
+    handle = ctypes.CDLL(str(built.LIB_PATH))
+    missing = [n for n in names if not hasattr(handle, n)]
+    assert not missing, f"declared in ttam.h but not exported: {missing}"
+
+
+def test_bindings_cover_the_header(built):
+    assert sorted(built.SIGNATURES) == _declared()
+    lib = built.lib()
+    assert lib.ttam_version() >= 100
+    assert isinstance(lib.ttam_last_error(), bytes)
+
+
+def test_missing_library_fails_loudly(built, monkeypatch, tmp_path):
+    monkeypatch.setattr(built, "LIB_PATH", tmp_path / "nope.so")
+    monkeypatch.setattr(built, "_LIB", None)
+    with pytest.raises(built.TtamError, match="no CPU fallback"):
+        built.lib()
+
+
+def test_library_is_sm100a_only(built):
+    import subprocess
+    out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-lelf", str(built.LIB_PATH)], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_product_never_imports_oracle():
+    pkg = ROOT / "two_tower_augmented_with_adaptive_mimic_mechanism_b200"
+    for f in pkg.glob("*.py"):
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", f.read_text(), flags=re.M), f

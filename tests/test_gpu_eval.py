@@ -1,0 +1,112 @@
+"""Retrieval / evaluation parity: corpus encoding, eval loss, exact top-K (canonical order), the batched
+`_evaluate_model` replacement with the reference's host filter, and ranking metrics."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from helpers import TRAIN_CASES, build_model, load_case, state_after
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tt():
+    import two_tower_augmented_with_adaptive_mimic_mechanism_b200 as pkg
+    return pkg
+
+
+@pytest.mark.parametrize("Q,N,D,K", [(1, 64, 16, 10), (300, 5000, 96, 100), (17, 4097, 128, 100), (5, 50, 8, 100),
+                                     (64, 20000, 96, 128)])
+def test_topk_f32_bit_exact_ids(tt, Q, N, D, K):
+    rng = np.random.default_rng(N)
+    q = rng.standard_normal((Q, D)).astype(np.float32)
+    items = rng.standard_normal((N, D)).astype(np.float32)
+    items[N // 2] = items[N // 3]                      # exact duplicates -> ties broken by id
+    items[N - 1] = items[0]
+    ids, scores = tt.functional.topk(torch.from_numpy(q).cuda(), torch.from_numpy(items).cuda(), K, id_offset=1000)
+    ref_s = oracle.canonical_scores(q, items)
+    ref_i, ref_v = oracle.topk_canonical(ref_s, K)
+    assert np.array_equal(ids.cpu().numpy(), ref_i + 1000)
+    assert np.array_equal(scores.cpu().numpy(), ref_v)          # canonical sequential-fp32 scores, bit for bit
+
+
+def test_topk_all_ties(tt):
+    q = torch.ones(3, 8, device="cuda")
+    items = torch.ones(500, 8, device="cuda")
+    ids, _ = tt.functional.topk(q, items, 20)
+    assert ids.cpu().tolist() == [list(range(20))] * 3
+
+
+def test_topk_merge_equals_unsharded(tt):
+    rng = np.random.default_rng(1)
+    Q, N, D, K, parts = 50, 8000, 32, 100, 8
+    q = rng.standard_normal((Q, D)).astype(np.float32)
+    items = np.round(rng.standard_normal((N, D)) * 4).astype(np.float32) / 4      # coarse values -> many exact ties
+    dq, di = torch.from_numpy(q).cuda(), torch.from_numpy(items).cuda()
+    full_i, full_s = tt.functional.topk(dq, di, K)
+    shard = N // parts
+    pi, ps = [], []
+    for r in range(parts):
+        i_, s_ = tt.functional.topk(dq, di[r * shard:(r + 1) * shard].contiguous(), K, id_offset=r * shard)
+        pi.append(i_); ps.append(s_)
+    mi, ms = tt.functional.topk_merge(torch.stack(pi, 1), torch.stack(ps, 1), K)
+    assert torch.equal(mi, full_i) and torch.equal(ms, full_s)
+    ref_i, _ = oracle.topk_canonical(oracle.canonical_scores(q, items), K)
+    assert np.array_equal(mi.cpu().numpy(), ref_i)
+
+
+@pytest.mark.parametrize("name,cosine", [("train_gated_mlp", False), ("train_gated_mlp_cosine", True)])
+def test_eval_path_matches_reference_golden(tt, name, cosine):
+    d, meta, _ = load_case(name)
+    state = state_after(d, meta["steps"] - 1)
+    model = build_model(meta, TRAIN_CASES[name], state, "cuda")
+    if not cosine:
+        model.similarity = torch.nn.Identity()      # anything that is not CosineSimilarity == dot product
+    model.eval()
+    eng = tt.FusedEngine(model, max_steps=4)
+    ux, ix = torch.from_numpy(d["user_x"]).cuda(), torch.from_numpy(d["item_x"]).cuda()
+    # _compute_loss
+    ev = eng.eval_loss(*(torch.from_numpy(d[f"eval/{k}"]).cuda() for k in ("users", "pos", "neg")), ux, ix)
+    assert float(ev[1]) == pytest.approx(float(d["eval/loss"]), rel=5e-6)
+    # _encode_item_embeddings (through the hook, CPU result like the reference)
+    emb = tt.hooks._encode_item_embeddings(model, num_items=meta["NI"], item_features=ix, device=torch.device("cuda"), batch_size=17)
+    assert emb.device.type == "cpu"
+    np.testing.assert_allclose(emb.numpy(), d["eval/item_embeddings"], rtol=2e-5, atol=2e-6)
+    uemb = eng.encode("user", torch.arange(meta["NU"], device="cuda"), ux)
+    np.testing.assert_allclose(uemb.cpu().numpy(), d["eval/user_embeddings"], rtol=2e-5, atol=2e-6)
+    # _score_all_items_for_user
+    for u in range(4):
+        ids = tt.hooks._score_all_items_for_user(model, user_idx=u, top_k=10, num_items=meta["NI"], user_features=ux,
+                                                 item_features=ix, device=torch.device("cuda"))
+        assert ids == d["eval/score_all_topk"][u].tolist()
+    # _evaluate_model + metrics
+    import pandas as pd
+    keys, ptr, vals = d["eval/pos_keys"], d["eval/pos_ptr"], d["eval/pos_vals"]
+    train_pos = {int(k): set(vals[ptr[i]:ptr[i + 1]].tolist()) for i, k in enumerate(keys)}
+    val = pd.DataFrame({"user_idx": d["eval/val_users"], "item_idx": d["eval/val_items"]})
+    k_values = [5, 10, 20]
+    preds, gts = tt.hooks._evaluate_model(model, train_positive_map=train_pos, val_interactions=val, item_feature_tensor=ix,
+                                          user_feature_tensor=ux, device=torch.device("cuda"), num_items=meta["NI"],
+                                          candidate_samples=50, k_values=k_values, rng=np.random.default_rng(0),
+                                          faiss_resources={"normalize": cosine}, faiss_search_k=4 * max(k_values))
+    assert sorted(preds) == d["eval/pred_users"].tolist()
+    for r, u in enumerate(d["eval/pred_users"].tolist()):
+        row = d["eval/pred_items"][r]
+        assert preds[u] == row[row >= 0].tolist(), f"user {u}"
+    met = oracle.ranking_metrics(preds, gts, k_values)
+    for r, k in enumerate(k_values):
+        got = [met["recall"][k], met["precision"][k], met["ndcg"][k], met["hit_rate"][k], met["map"][k]]
+        np.testing.assert_allclose(got, d["eval/metrics"][r], rtol=1e-12)
+
+
+def test_device_sampler_excludes_positives(tt):
+    """reference tests/test_samplers.py:6-19 semantics, on the device."""
+    from two_tower_augmented_with_adaptive_mimic_mechanism_b200.sampler import sample_negative_items
+    users = torch.tensor([0, 1, 0, 2], device="cuda")
+    positives = {0: {0, 1, 2, 3, 4, 5, 6}, 1: {9}, 2: set()}
+    neg = sample_negative_items(users, num_items=10, positives=positives, num_negatives=6, device=torch.device("cuda"))
+    assert neg.shape == (4, 6) and neg.dtype == torch.long
+    for r, u in enumerate(users.cpu().tolist()):
+        assert not (set(neg[r].cpu().tolist()) & positives[u])
+    assert int(neg.min()) >= 0 and int(neg.max()) < 10

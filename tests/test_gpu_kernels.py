@@ -1,0 +1,284 @@
+"""Kernel-level parity through the C ABI (functional.py is a 1:1 ctypes wrapper) against the numpy oracle."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle.optim import dense_step as o_dense_step, sparse_adam_step as o_sparse_adam
+from helpers import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+# fp32 SIMT kernels vs numpy fp32: same arithmetic, different summation order
+RTOL, ATOL = 2e-5, 2e-6
+
+
+@pytest.fixture(scope="module")
+def F():
+    from two_tower_augmented_with_adaptive_mimic_mechanism_b200 import functional
+    assert functional.lib().ttam_device_ok() == 1
+    return functional
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("R,ncols", [(0, 96), (1, 96), (1000, 96), (333, 21), (4097, 608), (77, 605)])
+def test_gather_rows_bit_exact(F, R, ncols):
+    rng = np.random.default_rng(R + ncols)
+    table = rng.standard_normal((5000, ncols)).astype(np.float32)
+    idx = rng.integers(0, 5000, size=R).astype(np.int64)
+    out = F.gather_rows(dev(table), dev(idx))
+    assert np.array_equal(out.cpu().numpy(), table[idx])
+
+
+def test_gather_into_strided_view(F):
+    rng = np.random.default_rng(0)
+    table = rng.standard_normal((100, 16)).astype(np.float32)
+    idx = rng.integers(0, 100, size=50).astype(np.int64)
+    z = torch.zeros((50, 32), device="cuda")
+    F.gather_rows(dev(table), dev(idx), out=z[:, :16])
+    assert np.array_equal(z[:, :16].cpu().numpy(), table[idx]) and float(z[:, 16:].abs().sum()) == 0.0
+
+
+def test_cast_bf16_rne(F):
+    x = torch.randn(513, 96, device="cuda")
+    x[0, 0], x[0, 1], x[0, 2] = float("inf"), -0.0, 1.0 + 2 ** -8     # tie -> even
+    got = F.cast_bf16(x)
+    assert torch.equal(got.view(torch.int16), x.to(torch.bfloat16).view(torch.int16))
+
+
+@pytest.mark.parametrize("M,N,K,act,gather", [(257, 32, 21, "relu", True), (64, 16, 32, "none", False),
+                                              (1000, 192, 605, "relu", True), (130, 96, 192, "tanh", False),
+                                              (65, 24, 32, "gelu", False), (65, 24, 32, "selu", False)])
+def test_linear_fwd(F, M, N, K, act, gather):
+    rng = np.random.default_rng(M)
+    X = rng.standard_normal((2000, K)).astype(np.float32)
+    W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32) * 0.1
+    idx = rng.integers(0, 2000, size=M).astype(np.int64)
+    x = X[idx] if gather else X[:M]
+    ref = x @ W.T + b
+    if act != "none":
+        ref = oracle.model._act(act, ref.astype(np.float32))
+    got = F.linear_fwd(dev(X) if gather else dev(x), dev(W), dev(b), gather=dev(idx) if gather else None, act=act)
+    np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=RTOL, atol=ATOL)
+
+
+def test_linear_dgrad_and_wgrad(F):
+    rng = np.random.default_rng(5)
+    M, N, K = 999, 48, 37
+    X = rng.standard_normal((300, K)).astype(np.float32)
+    idx = rng.integers(0, 300, size=M).astype(np.int64)
+    dy = rng.standard_normal((M, N)).astype(np.float32)
+    W = rng.standard_normal((N, K)).astype(np.float32)
+    aux = rng.standard_normal((M, K)).astype(np.float32)
+    got = F.linear_dgrad(dev(dy), dev(W), aux=dev(aux), relu_mask=True, scale=1.25)
+    np.testing.assert_allclose(got.cpu().numpy(), (dy @ W) * (aux > 0) * 1.25, rtol=RTOL, atol=1e-5)
+    base = rng.standard_normal((M, K)).astype(np.float32)
+    out = dev(base)
+    F.linear_dgrad(dev(dy), dev(W), out=out, accumulate=True)
+    np.testing.assert_allclose(out.cpu().numpy(), base + dy @ W, rtol=RTOL, atol=1e-5)
+    dw, db = F.linear_wgrad(dev(dy), dev(X), gather=dev(idx))
+    np.testing.assert_allclose(dw.cpu().numpy(), dy.T @ X[idx], rtol=1e-4, atol=2e-4)
+    np.testing.assert_allclose(db.cpu().numpy(), dy.sum(0), rtol=1e-4, atol=2e-4)
+    # deterministic: same launch twice gives the same bits
+    dw2, db2 = F.linear_wgrad(dev(dy), dev(X), gather=dev(idx))
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)
+
+
+def test_dropout_mask_is_reproducible_and_scaled(F):
+    M, N, K, p = 512, 64, 16, 0.25
+    x = torch.ones(M, K, device="cuda")
+    W = torch.ones(N, K, device="cuda") / K
+    y1 = F.linear_fwd(x, W, None, act="relu", dropout_p=p, seed=7, offset=123)
+    y2 = F.linear_fwd(x, W, None, act="relu", dropout_p=p, seed=7, offset=123)
+    y3 = F.linear_fwd(x, W, None, act="relu", dropout_p=p, seed=8, offset=123)
+    assert torch.equal(y1, y2) and not torch.equal(y1, y3)
+    vals = torch.unique(y1).cpu().tolist()
+    assert len(vals) == 2 and vals[0] == 0.0 and abs(vals[1] - 1.0 / (1 - p)) < 1e-6
+    keep = float((y1 > 0).float().mean())
+    assert abs(keep - (1 - p)) < 0.02
+    # the stand-alone activation kernel draws the same mask as the fused epilogue
+    pre = F.linear_fwd(x, W, None)
+    y4 = F.act_fwd(pre, act="relu", dropout_p=p, seed=7, offset=123)
+    assert torch.equal(y1, y4)
+    # device step state shifts the counters
+    st = F.new_step_state("cuda", 0, 0)
+    F.advance_step(st, rng_stride=1 << 20)
+    y5 = F.linear_fwd(x, W, None, act="relu", dropout_p=p, seed=7, offset=123, state=st)
+    y6 = F.linear_fwd(x, W, None, act="relu", dropout_p=p, seed=7, offset=123 + (1 << 20))
+    assert torch.equal(y5, y6) and int(st[0].item()) == 1
+
+
+@pytest.mark.parametrize("act", ["relu", "gelu", "tanh", "selu"])
+def test_act_bwd(F, act):
+    rng = np.random.default_rng(3)
+    pre = rng.standard_normal((50, 24)).astype(np.float32)
+    dy = rng.standard_normal((50, 24)).astype(np.float32)
+    out = oracle.model._act(act, pre)
+    ref = dy * oracle.model._dact(act, pre, out)
+    got = F.act_bwd(dev(dy), dev(pre), act=act)
+    np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=1e-5, atol=1e-6)
+
+
+def test_gate_and_augment(F):
+    rng = np.random.default_rng(9)
+    R, D = 300, 96
+    z = rng.standard_normal((R, 2 * D)).astype(np.float32)
+    pre2 = rng.standard_normal((R, D)).astype(np.float32)
+    A = rng.standard_normal((50, D)).astype(np.float32)
+    idx = rng.integers(0, 50, size=R).astype(np.int64)
+    e, f = z[:, :D], z[:, D:]
+    g_ref = oracle.model._sigmoid(pre2)
+    t_ref = g_ref * e + (1 - g_ref) * f
+    g, t, o, q = (torch.empty(R, D, device="cuda") for _ in range(4))
+    F.gate_fwd(dev(z), dev(pre2), g=g, t=t, o=o, q=q, aug_table=dev(A), idx=dev(idx))
+    np.testing.assert_allclose(g.cpu().numpy(), g_ref, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(t.cpu().numpy(), t_ref, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(o.cpu().numpy(), t_ref + A[idx], rtol=1e-5, atol=1e-6)
+    assert np.array_equal(q.cpu().numpy(), A[idx])
+    dt = rng.standard_normal((R, D)).astype(np.float32)
+    dpre2, dz = torch.empty(R, D, device="cuda"), torch.empty(R, 2 * D, device="cuda")
+    F.gate_bwd(dev(dt), dev(z), g, dpre2=dpre2, dz=dz)
+    np.testing.assert_allclose(dpre2.cpu().numpy(), dt * (e - f) * g_ref * (1 - g_ref), rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(dz.cpu().numpy(), np.concatenate([dt * g_ref, dt * (1 - g_ref)], 1), rtol=1e-5, atol=1e-6)
+    o2, q2 = torch.empty(R, D, device="cuda"), torch.empty(R, D, device="cuda")
+    F.augment_fwd(dev(t_ref), dev(A), dev(idx), out=o2, q_out=q2)
+    np.testing.assert_allclose(o2.cpu().numpy(), t_ref + A[idx], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("B,N,D,mimic", [(24, 3, 16, True), (1, 1, 96, False), (8192, 5, 96, True), (100, 16, 128, True)])
+def test_loss_fwd_bwd(F, B, N, D, mimic):
+    rng = np.random.default_rng(B)
+    o_u = rng.standard_normal((B, D)).astype(np.float32) * 0.3
+    o_i = rng.standard_normal((B * (1 + N), D)).astype(np.float32) * 0.3
+    kw = {}
+    okw = {}
+    if mimic:
+        t_u, t_p, q_u, q_p = (rng.standard_normal((B, D)).astype(np.float32) * 0.1 for _ in range(4))
+        kw = dict(t_u=dev(t_u), t_p=dev(t_p), q_u=dev(q_u), q_p=dev(q_p), lambda_u=0.15, lambda_i=0.2)
+        okw = dict(t_u=t_u, t_p=t_p, q_u=q_u, q_p=q_p, lambda_u=0.15, lambda_i=0.2)
+    ref = oracle.loss_forward_backward(o_u, o_i[:B], o_i[B:].reshape(B, N, D), **okw)
+    loss, do_u, do_i, dq_u, dq_p = F.loss_fwd_bwd(dev(o_u), dev(o_i), **kw)
+    loss = loss.cpu().numpy()
+    assert loss[0] == pytest.approx(float(ref["loss"]), rel=2e-6)
+    assert loss[1] == pytest.approx(float(ref["bce"]), rel=2e-6)
+    np.testing.assert_allclose(do_u.cpu().numpy(), ref["do_u"], rtol=1e-4, atol=1e-9)
+    np.testing.assert_allclose(do_i[:B].cpu().numpy(), ref["do_p"], rtol=1e-4, atol=1e-9)
+    np.testing.assert_allclose(do_i[B:].cpu().numpy(), ref["do_n"].reshape(B * N, D), rtol=1e-4, atol=1e-9)
+    if mimic:
+        assert loss[2] == pytest.approx(float(ref["mimic_user"]), rel=2e-6)
+        assert loss[3] == pytest.approx(float(ref["mimic_item"]), rel=2e-6)
+        np.testing.assert_allclose(dq_u.cpu().numpy(), ref["do_u"] + ref["dq_u_extra"], rtol=1e-4, atol=1e-9)
+        np.testing.assert_allclose(dq_p.cpu().numpy(), ref["do_p"] + ref["dq_p_extra"], rtol=1e-4, atol=1e-9)
+    # forward only (the _compute_loss path)
+    l2, *_ = F.loss_fwd_bwd(dev(o_u), dev(o_i), backward=False)
+    assert float(l2[1]) == pytest.approx(float(ref["bce"]), rel=2e-6)
+
+
+def test_sort_and_unique_rows_bit_exact(F):
+    rng = np.random.default_rng(2)
+    idx = rng.integers(0, 2_000_000, size=57344).astype(np.int64)
+    idx[:5000] = rng.integers(0, 50, size=5000)          # heavy duplicates
+    s, perm = F.sort_rows(dev(idx), 2_000_000)
+    order = np.argsort(idx, kind="stable")
+    assert np.array_equal(s.cpu().numpy(), idx[order])
+    assert np.array_equal(perm.cpu().numpy(), order.astype(np.int32))   # stable: duplicates keep original order
+    assert np.array_equal(F.unique_rows(s).cpu().numpy(), np.unique(idx))
+    one = dev(np.array([7], dtype=np.int64))
+    s1, p1 = F.sort_rows(one, 10)
+    assert s1.cpu().tolist() == [7] and p1.cpu().tolist() == [0]
+
+
+def _run_sparse_adam(F, p0, idx_steps, val_steps, lr, betas, split=False, use_state=False):
+    p = dev(p0.copy())
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    scal = F.adam_scalar_table(len(idx_steps) + 1, lr, betas, "cuda")
+    st = F.new_step_state("cuda") if use_state else None
+    touched = []
+    for s, (ix, val) in enumerate(zip(idx_steps, val_steps)):
+        if st is not None:
+            F.advance_step(st)
+        sidx, perm = F.sort_rows(dev(ix), p0.shape[0])
+        touched.append(F.unique_rows(sidx).cpu().numpy())
+        if split and len(ix) > 2:
+            h = len(ix) // 2
+            F.sparse_adam_rows(p, m, v, sidx, perm, dev(val[:h]), dev(val[h:]), lr=lr, betas=betas, step=s + 1, scalars=scal, state=st)
+        else:
+            F.sparse_adam_rows(p, m, v, sidx, perm, dev(val), lr=lr, betas=betas, step=s + 1, scalars=scal, state=st)
+    return p.cpu().numpy(), m.cpu().numpy(), v.cpu().numpy(), touched
+
+
+@pytest.mark.parametrize("split,use_state", [(False, False), (True, False), (False, True)])
+def test_sparse_adam_matches_torch_golden(F, split, use_state):
+    z = np.load(GOLDEN / "optim.npz")
+    steps = 6
+    p, m, v, touched = _run_sparse_adam(F, z["p0"], [z[f"idx{s}"] for s in range(steps)], [z[f"val{s}"] for s in range(steps)],
+                                        1e-3, (0.9, 0.999), split, use_state)
+    np.testing.assert_allclose(p, z[f"sparse_adam/p{steps - 1}"], rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(m, z["sparse_adam/exp_avg"], rtol=1e-6, atol=1e-10)
+    np.testing.assert_allclose(v, z["sparse_adam/exp_avg_sq"], rtol=1e-6, atol=1e-12)
+    for s in range(steps):
+        assert np.array_equal(touched[s], np.unique(z[f"idx{s}"]))
+
+
+def test_sparse_adam_wide_rows_bit_exact_vs_oracle(F):
+    """D=96/128/256 rows, many duplicates: the segment sum runs in original order like coalesce, so the result
+    is bit-identical to the sequential-fp32 oracle."""
+    for D in (96, 128, 256, 20):
+        rng = np.random.default_rng(D)
+        N, R = 500, 3000
+        p0 = (rng.standard_normal((N, D)) * 0.02).astype(np.float32)
+        idxs = [rng.integers(0, N, size=R).astype(np.int64) for _ in range(3)]
+        vals = [(rng.standard_normal((R, D)) * 0.01).astype(np.float32) for _ in range(3)]
+        p, m, v, _ = _run_sparse_adam(F, p0, idxs, vals, 1e-3, (0.9, 0.999))
+        po, st = p0.copy(), {"step": 0}
+        for ix, val in zip(idxs, vals):
+            o_sparse_adam(po, st, ix, val, lr=1e-3)
+        np.testing.assert_allclose(m, st["exp_avg"], rtol=0, atol=0)
+        np.testing.assert_allclose(v, st["exp_avg_sq"], rtol=0, atol=0)
+        np.testing.assert_allclose(p, po, rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize("kind", ["adamw", "adam", "sgd"])
+def test_lazy_rows_equal_dense_optimizer(F, kind):
+    """Lazy-exact replay: touching a few rows per step + a final flush == the dense optimiser stepping every row
+    every step (torch golden, rows with zero gradient for several steps included)."""
+    z = np.load(GOLDEN / "optim.npz")
+    steps, lr, wd, mom = 6, 1e-3, 0.01, 0.9
+    p = dev(z["p0"].copy())
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    last = torch.zeros(p.shape[0], dtype=torch.int32, device="cuda")
+    scal = F.adam_scalar_table(steps + 1, lr, (0.9, 0.999), "cuda")
+    for s in range(steps):
+        sidx, perm = F.sort_rows(dev(z[f"idx{s}"]), p.shape[0])
+        F.lazy_rows(kind, p, m, v, last, sidx, perm, dev(z[f"val{s}"]), scalars=scal, lr=lr, weight_decay=wd,
+                    momentum=mom, step=s + 1)
+        if s in (2, steps - 1):      # a mid-run flush must not change the end result
+            F.lazy_flush(kind, p, m, v, last, scalars=scal, lr=lr, weight_decay=wd, momentum=mom, step=s + 1)
+            np.testing.assert_allclose(p.cpu().numpy(), z[f"{kind}/p{s}"], rtol=1e-6, atol=1e-8, err_msg=f"{kind} step {s}")
+    assert int(last.min()) == steps
+    if kind != "sgd":
+        np.testing.assert_allclose(m.cpu().numpy(), z[f"{kind}/exp_avg"], rtol=1e-5, atol=1e-10)
+        np.testing.assert_allclose(v.cpu().numpy(), z[f"{kind}/exp_avg_sq"], rtol=1e-5, atol=1e-12)
+
+
+def test_dense_step_matches_oracle(F):
+    rng = np.random.default_rng(4)
+    shapes = [(32, 21), (32,), (16, 32), (16,), (192, 605)]
+    for kind in ("adamw", "adam", "sgd"):
+        ps = [rng.standard_normal(s).astype(np.float32) * 0.1 for s in shapes]
+        ref = [p.copy() for p in ps]
+        sts = [{"step": 0} for _ in shapes]
+        dp = [dev(p) for p in ps]
+        dm = [torch.zeros_like(p) for p in dp]
+        dv = [torch.zeros_like(p) for p in dp]
+        for step in range(1, 4):
+            gs = [rng.standard_normal(s).astype(np.float32) * 0.01 for s in shapes]
+            F.dense_step(kind, dp, [dev(g) for g in gs], dm, dv, lr=1e-3, weight_decay=0.01, momentum=0.9, step=step)
+            for r, g, st in zip(ref, gs, sts):
+                o_dense_step(kind, r, g, st, lr=1e-3, weight_decay=0.01, momentum=0.9)
+        for a, r in zip(dp, ref):
+            np.testing.assert_allclose(a.cpu().numpy(), r, rtol=1e-6, atol=1e-8, err_msg=kind)

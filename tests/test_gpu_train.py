@@ -1,0 +1,173 @@
+"""End-to-end parity of the fused training step against (1) the golden fixtures produced by the unmodified
+reference and (2) the numpy oracle on larger seeded inputs.
+
+Tolerances (fp32 everywhere; only the summation order differs from the reference's CPU BLAS):
+  losses            rel 5e-6
+  updated tensors   rtol 5e-5, atol 2e-6   (Adam normalises the gradient, so elements whose gradient is ~0
+                                            can move by up to ~lr with either sign: atol = 2e-3 * lr)
+  SparseAdam touched-row sets: bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from helpers import TRAIN_CASES, build_model, load_case, model_state_np, state_after
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 5e-5, 2e-6
+
+
+def _engine(model, meta, kw, **extra):
+    from two_tower_augmented_with_adaptive_mimic_mechanism_b200 import FusedEngine
+    lu, li, lc = meta["lambdas"]
+    return FusedEngine(model, optimizer=kw["optimizer"], lr=meta["lr"], weight_decay=meta["wd"], momentum=meta["momentum"],
+                       sparse_betas=meta["betas"], loss_weights={"mimic_user": lu, "mimic_item": li, "category_alignment": lc},
+                       max_steps=64, **extra)
+
+
+@pytest.mark.parametrize("name", sorted(TRAIN_CASES))
+def test_fused_step_matches_reference_golden(name):
+    from two_tower_augmented_with_adaptive_mimic_mechanism_b200 import functional as F
+    d, meta, init = load_case(name)
+    kw = TRAIN_CASES[name]
+    model = build_model(meta, kw, init, "cuda")
+    eng = _engine(model, meta, kw, item_category_tensor=torch.from_numpy(d["cat_tensor"]).cuda(), major_category_id=int(d["major"]))
+    ux, ix = torch.from_numpy(d["user_x"]).cuda(), torch.from_numpy(d["item_x"]).cuda()
+    for s in range(meta["steps"]):
+        u, p, n = (torch.from_numpy(d[f"step{s}/{k}"]).cuda() for k in ("users", "pos", "neg"))
+        loss = eng.train_step(u, p, n, ux, ix)
+        assert float(loss[0]) == pytest.approx(float(d["losses"][s]), rel=5e-6, abs=1e-7)
+        # bit-exact: the row sets the sparse optimiser touches
+        su, _ = F.sort_rows(u, meta["NU"])
+        si, _ = F.sort_rows(torch.cat([p, n.reshape(-1)]), meta["NI"])
+        assert np.array_equal(F.unique_rows(su).cpu().numpy(), np.unique(d[f"step{s}/users"]))
+        assert np.array_equal(F.unique_rows(si).cpu().numpy(), np.unique(np.concatenate([d[f"step{s}/pos"], d[f"step{s}/neg"].reshape(-1)])))
+        if s in (0, meta["steps"] - 1):
+            eng.flush()
+            got, ref = model_state_np(model), state_after(d, s)
+            assert set(got) == set(ref)
+            for k in ref:
+                np.testing.assert_allclose(got[k], ref[k], rtol=RTOL, atol=ATOL, err_msg=f"{name} step {s} {k}")
+    st = eng.optimizer_state()
+    for k, v in d.items():
+        if k.startswith("opt/"):
+            _, pname, slot = k.split("/")
+            key = "exp_avg" if slot == "momentum_buffer" else slot
+            np.testing.assert_allclose(st[pname][key].cpu().numpy(), v, rtol=2e-4, atol=1e-9, err_msg=k)
+
+
+def _synthetic(seed, NU, NI, D, H, Hg, F, B, N):
+    rng = np.random.default_rng(seed)
+    st = {}
+    for side, n in (("user", NU), ("item", NI)):
+        pre = f"{side}_encoder."
+        st[pre + "embedding.weight"] = (rng.standard_normal((n, D)) * 0.02).astype(np.float32)
+        st[pre + "feature_encoder.network.0.weight"] = (rng.standard_normal((H, F)) * np.sqrt(2.0 / (H + F))).astype(np.float32)
+        st[pre + "feature_encoder.network.0.bias"] = (rng.standard_normal(H) * 0.05).astype(np.float32)
+        st[pre + "feature_encoder.network.2.weight"] = (rng.standard_normal((D, H)) * np.sqrt(2.0 / (H + D))).astype(np.float32)
+        st[pre + "feature_encoder.network.2.bias"] = (rng.standard_normal(D) * 0.05).astype(np.float32)
+        st[pre + "adaptive_mimic.gate_network.0.weight"] = (rng.standard_normal((Hg, 2 * D)) * np.sqrt(2.0 / (Hg + 2 * D))).astype(np.float32)
+        st[pre + "adaptive_mimic.gate_network.0.bias"] = (rng.standard_normal(Hg) * 0.05).astype(np.float32)
+        st[pre + "adaptive_mimic.gate_network.2.weight"] = (rng.standard_normal((D, Hg)) * np.sqrt(2.0 / (Hg + D))).astype(np.float32)
+        st[pre + "adaptive_mimic.gate_network.2.bias"] = (rng.standard_normal(D) * 0.05).astype(np.float32)
+        st[f"adaptive_mimic.{side}_augmented.weight"] = (rng.standard_normal((n, D)) * 0.02).astype(np.float32)
+    item_x = np.zeros((NI, F), dtype=np.float32)
+    for r in range(NI):
+        item_x[r, rng.choice(F - 5, size=3, replace=False)] = (1.0, 0.5, 1.0)
+    item_x[:, F - 5:] = rng.standard_normal((NI, 5)).astype(np.float32)
+    user_x = np.stack([item_x[rng.integers(0, NI, size=4)].mean(0) for _ in range(NU)]).astype(np.float32)
+    pop = 1.0 / np.arange(1, NI + 1) ** 1.05
+    pop /= pop.sum()
+    batches = [(rng.integers(0, NU, size=B).astype(np.int64), rng.choice(NI, size=B, p=pop).astype(np.int64),
+                rng.integers(0, NI, size=(B, N)).astype(np.int64)) for _ in range(3)]
+    return st, user_x, item_x, batches
+
+
+@pytest.mark.parametrize("D,H,Hg,F,B,graph", [(96, 192, 96, 605, 512, False), (128, 256, 128, 64, 256, False),
+                                              (96, 192, 96, 608, 512, True)])
+def test_fused_step_matches_oracle_at_tower_shapes(D, H, Hg, F, B, graph):
+    """North-star tower shapes (96-dim, 192->96 MLP, F=605), duplicate-heavy Zipf positives, 3 steps, and the same
+    steps replayed from a captured CUDA graph."""
+    NU, NI, N = 3000, 5000, 5
+    st, user_x, item_x, batches = _synthetic(7, NU, NI, D, H, Hg, F, B, N)
+    meta = dict(NU=NU, NI=NI, D=D, H=H, Hg=Hg, F=F, lr=1e-3, wd=0.01, momentum=0.0, betas=(0.9, 0.999), lambdas=(0.15, 0.15, 0.0))
+    kw = dict(optimizer="adamw")
+    model = build_model(meta, kw, st, "cuda")
+    eng = _engine(model, meta, kw)
+    ref_state = {k: v.copy() for k, v in st.items()}
+    spec = oracle.spec_from_state(ref_state)
+    opt = oracle.OptState()
+    ux, ix = torch.from_numpy(user_x).cuda(), torch.from_numpy(item_x).cuda()
+    for u, p, n in batches:
+        ref = oracle.train_step(ref_state, opt, spec, u, p, n, user_x, item_x, lr=1e-3, weight_decay=0.01, lambdas=(0.15, 0.15, 0.0))
+        loss = eng.train_step(torch.from_numpy(u).cuda(), torch.from_numpy(p).cuda(), torch.from_numpy(n).cuda(), ux, ix, graph=graph)
+        got = loss.cpu().numpy()
+        assert got[0] == pytest.approx(ref["loss"], rel=5e-6)
+        assert got[1] == pytest.approx(ref["bce"], rel=5e-6)
+        assert got[2] == pytest.approx(ref["mimic_user"], rel=5e-6)
+        assert got[3] == pytest.approx(ref["mimic_item"], rel=5e-6)
+    eng.flush()
+    got = model_state_np(model)
+    for k in ref_state:
+        np.testing.assert_allclose(got[k], ref_state[k], rtol=RTOL, atol=ATOL, err_msg=k)
+    # rows never touched keep their bits in the sparse tables; in the aug tables they decay (AdamW on every row)
+    untouched = np.setdiff1d(np.arange(NU), np.unique(np.concatenate([b[0] for b in batches])))
+    assert np.array_equal(got["user_encoder.embedding.weight"][untouched], st["user_encoder.embedding.weight"][untouched])
+    a0, a1 = st["adaptive_mimic.user_augmented.weight"][untouched], got["adaptive_mimic.user_augmented.weight"][untouched]
+    np.testing.assert_allclose(a1, a0 * np.float32(1 - 1e-3 * 0.01) ** 3, rtol=1e-6)
+
+
+def test_dropout_training_step_runs_and_differs_per_step():
+    NU, NI, D, H, Hg, F, B, N = 500, 800, 32, 64, 32, 24, 128, 3
+    st, user_x, item_x, batches = _synthetic(3, NU, NI, D, H, Hg, F, B, N)
+    import two_tower_augmented_with_adaptive_mimic_mechanism_b200 as tt
+    cfg = {"type": "tower", "id_embedding": {"params": {"embedding_dim": D, "sparse": True}},
+           "feature_encoder": {"type": "mlp", "hidden_dims": [H], "output_dim": D, "dropout": 0.15}, "fusion": "gated",
+           "adaptive_mimic": {"hidden_dim": Hg}}
+    ue = tt.build_tower_encoder(cfg, num_embeddings=NU, feature_dim=F)
+    ie = tt.build_tower_encoder(cfg, num_embeddings=NI, feature_dim=F)
+    model = tt.TwoTowerModel(ue, ie, adaptive_mimic=tt.AdaptiveMimicMechanism(num_users=NU, num_items=NI, embedding_dim=D)).cuda()
+    eng = tt.FusedEngine(model, lr=1e-3, weight_decay=0.01, loss_weights={"mimic_user": 0.15, "mimic_item": 0.15}, max_steps=16)
+    ux, ix = torch.from_numpy(user_x).cuda(), torch.from_numpy(item_x).cuda()
+    u, p, n = (torch.from_numpy(a).cuda() for a in batches[0])
+    l1 = eng.train_step(u, p, n, ux, ix).clone()
+    h1 = eng.bufs_u["hd0"][:B].clone()
+    l2 = eng.train_step(u, p, n, ux, ix).clone()
+    h2 = eng.bufs_u["hd0"][:B].clone()
+    assert torch.isfinite(l1).all() and torch.isfinite(l2).all()
+    z1, z2 = (h1 == 0), (h2 == 0)
+    assert 0.1 < float(z1.float().mean()) < 0.9          # relu zeros + ~15% dropped
+    assert not torch.equal(z1, z2)                       # a fresh mask every step
+
+
+def test_module_api_forward_backward_matches_oracle():
+    """The nn.Module path (autograd.Function wrappers) that `scripts/train.py` would use without the fused hook."""
+    d, meta, init = load_case("train_gated_mlp")
+    model = build_model(meta, TRAIN_CASES["train_gated_mlp"], init, "cuda")
+    model.train()
+    u = torch.from_numpy(d["step0/users"]).cuda()
+    p = torch.from_numpy(d["step0/pos"]).cuda()
+    ux, ix = torch.from_numpy(d["user_x"]).cuda(), torch.from_numpy(d["item_x"]).cuda()
+    t_u = model.user_encoder({"indices": u, "features": ux.index_select(0, u)})
+    t_p = model.item_encoder({"indices": p, "features": ix.index_select(0, p)})
+    o_u, o_p, lu, li = model.adaptive_mimic(user_indices=u, item_indices=p, user_embedding=t_u, item_embedding=t_p)
+    spec = oracle.spec_from_state(init)
+    cu = oracle.tower_forward(init, "user", spec.user, d["step0/users"], d["user_x"][d["step0/users"]])
+    cp = oracle.tower_forward(init, "item", spec.item, d["step0/pos"], d["item_x"][d["step0/pos"]])
+    np.testing.assert_allclose(t_u.detach().cpu().numpy(), cu["t"], rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(t_p.detach().cpu().numpy(), cp["t"], rtol=2e-5, atol=2e-6)
+    qu = init["adaptive_mimic.user_augmented.weight"][d["step0/users"]]
+    assert float(lu) == pytest.approx(float(((qu - cp["t"]) ** 2).mean()), rel=1e-5)
+    loss = (o_u * o_p).sum(-1).mean() + 0.15 * lu + 0.15 * li
+    loss.backward()
+    g = model.user_encoder.embedding.weight.grad
+    assert g.is_sparse and g._nnz() == u.numel()
+    assert model.adaptive_mimic.user_augmented.weight.grad.shape == (meta["NU"], meta["D"])
+    w = model.user_encoder.feature_encoder.network[0].weight
+    assert w.grad is not None and torch.isfinite(w.grad).all() and float(w.grad.abs().sum()) > 0
+    # reference shape tests (reference tests/test_encoders.py:6-26, tests/test_adaptive_mimic.py:6-33)
+    assert t_u.shape == (u.numel(), meta["D"]) and o_p.shape == t_p.shape and lu.ndim == 0 and float(li) >= 0
+    n = torch.from_numpy(d["step0/neg"]).cuda()
+    t_n = model.item_encoder({"indices": n.reshape(-1), "features": ix.index_select(0, n.reshape(-1))})
+    assert model.adaptive_mimic.augment_items(n.reshape(-1), t_n).shape == t_n.shape

@@ -115,3 +115,25 @@ def test_canonical_topk_ties_break_by_id():
     s = np.array([[1.0, 3.0, 3.0, 2.0, 3.0]], dtype=np.float32)
     ids, sc = oracle.topk_canonical(s, 4)
     assert ids.tolist() == [[1, 2, 4, 3]]
+
+
+@pytest.mark.parametrize("name", ["train_gated_mlp", "train_gated_mlp_cosine"])
+def test_torch_port_matches_reference_golden(name):
+    """The torch CPU port timed by bench.py as the CPU baseline reproduces the reference's numbers."""
+    import torch
+    from oracle import torch_port
+    torch.set_num_threads(1)
+    d, meta, init = load_case(name)
+    model = torch_port.Model(meta["NU"], meta["NI"], meta["D"], meta["F"], meta["H"], meta["Hg"] or meta["D"])
+    model.load_reference_state(init)
+    opts = torch_port.build_optimizers(model, lr=meta["lr"], weight_decay=meta["wd"], betas=meta["betas"])
+    ux, ix = torch.from_numpy(d["user_x"]), torch.from_numpy(d["item_x"])
+    for s in range(meta["steps"]):
+        loss = torch_port.train_step(model, opts, torch.from_numpy(d[f"step{s}/users"]), torch.from_numpy(d[f"step{s}/pos"]),
+                                     torch.from_numpy(d[f"step{s}/neg"]), ux, ix, lambdas=meta["lambdas"][:2])
+        assert loss == pytest.approx(float(d["losses"][s]), rel=1e-6)
+    got, ref = model.reference_state(), state_after(d, meta["steps"] - 1)
+    assert set(got) == set(ref)
+    for k in ref:
+        np.testing.assert_allclose(got[k], ref[k], rtol=1e-5, atol=1e-7, err_msg=k)
+    np.testing.assert_allclose(torch_port.encode_items(model, ix).numpy(), d["eval/item_embeddings"], rtol=1e-5, atol=1e-7)

@@ -1,0 +1,146 @@
+// fp32 SIMT GEMMs with fused gather / bias / activation / dropout / mask epilogues (TTAM_PREC_FP32).
+// These keep the reference's fp32 arithmetic (encoders.py:121-144,157-162 -> ATen addmm); the tcgen05
+// versions in gemm_tc.cu trade that for tensor-core throughput.
+//
+//   fwd   (NT): y[M,N]  = act(x[g(m),:K] . w[n,:K] + b[n])
+//   dgrad (NN): dx[M,K] = (dy[M,:N] . w[:N,k]) * mask * scale   (+ dx)
+//   wgrad (TN): dw[N,K] = sum_m dy[m,n] * x[g(m),k]              (split over m, deterministic reduce)
+#include "gemm_simt.cuh"
+
+namespace ttam {
+
+// out[i] (+)= sum_s partial[s][i], fixed order
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ partial, int splits,
+                                                            int64_t numel, float* __restrict__ out, int accumulate) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < numel; i += (int64_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += partial[(int64_t)k * numel + i];
+    out[i] = accumulate ? out[i] + s : s;
+  }
+}
+
+// partial[s][n] = sum_{m in chunk s} dy[m][n]
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ dy, int64_t lddy, int M, int N,
+                                                             int chunk, float* __restrict__ partial) {
+  const int s = blockIdx.y;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int lo = s * chunk, hi = min(M, lo + chunk);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int m = lo;
+  for (; m + 3 < hi; m += 4) {
+    a0 += dy[(int64_t)m * lddy + n];
+    a1 += dy[(int64_t)(m + 1) * lddy + n];
+    a2 += dy[(int64_t)(m + 2) * lddy + n];
+    a3 += dy[(int64_t)(m + 3) * lddy + n];
+  }
+  for (; m < hi; ++m) a0 += dy[(int64_t)m * lddy + n];
+  partial[(int64_t)s * N + n] = (a0 + a1) + (a2 + a3);
+}
+
+static int wgrad_splits(int64_t M, int64_t N, int64_t K) {
+  int64_t tiles = ceil_div(N, BM) * ceil_div(K, BN);
+  int64_t want = ceil_div((int64_t)num_sms() * 4, tiles);
+  int64_t max_by_rows = ceil_div(M, 256);
+  int64_t s = want < max_by_rows ? want : max_by_rows;
+  if (s < 1) s = 1;
+  if (s > 1024) s = 1024;
+  return (int)s;
+}
+
+}  // namespace ttam
+
+using namespace ttam;
+
+extern "C" int ttam_linear_fwd(const float* x, int64_t ldx, const int64_t* gather, const float* w, const float* bias,
+                               float* y, int64_t ldy, int64_t M, int64_t N, int64_t K, int act, float dropout_p,
+                               uint64_t seed, uint64_t offset, const ttam_step_state* state_dev, int precision,
+                               void* stream) {
+  TTAM_CHECK_ARG(x && w && y, "linear_fwd: null pointer");
+  TTAM_CHECK_ARG(M >= 0 && N > 0 && K > 0 && ldx >= K && ldy >= N, "linear_fwd: bad shape");
+  TTAM_CHECK_ARG(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "linear_fwd: dimension too large");
+  TTAM_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "linear_fwd: dropout must be in [0,1)");
+  TTAM_CHECK_ARG(act >= TTAM_ACT_NONE && act <= TTAM_ACT_SELU, "linear_fwd: unknown activation %d", act);
+  if (M == 0) return TTAM_OK;
+  if (precision != TTAM_PREC_FP32) {
+    set_error("linear_fwd: precision %d is not built into this library yet", precision);
+    return TTAM_EUNSUPPORTED;
+  }
+  GemmP p{};
+  p.A = x; p.B = w; p.C = y; p.lda = ldx; p.ldb = K; p.ldc = ldy; p.gatherA = gather;
+  p.M = (int)M; p.N = (int)N; p.K = (int)K; p.bias = bias; p.act = act; p.dropout_p = dropout_p;
+  p.seed = seed; p.offset = offset; p.st = state_dev; p.scale = 1.f;
+  dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, BM), 1);
+  gemm_f32_kernel<true, true, false><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  TTAM_LAUNCH_CHECK();
+  return TTAM_OK;
+}
+
+extern "C" int ttam_linear_dgrad(const float* dy, int64_t lddy, const float* w, float* dx, int64_t lddx,
+                                 const float* aux, int64_t ldaux, int mask_mode, float scale, int accumulate,
+                                 int64_t M, int64_t N, int64_t K, int precision, void* stream) {
+  TTAM_CHECK_ARG(dy && w && dx, "linear_dgrad: null pointer");
+  TTAM_CHECK_ARG(M >= 0 && N > 0 && K > 0 && lddy >= N && lddx >= K, "linear_dgrad: bad shape");
+  TTAM_CHECK_ARG(mask_mode == 0 || (mask_mode == 1 && aux && ldaux >= K), "linear_dgrad: bad mask arguments");
+  if (M == 0) return TTAM_OK;
+  if (precision != TTAM_PREC_FP32) {
+    set_error("linear_dgrad: precision %d is not built into this library yet", precision);
+    return TTAM_EUNSUPPORTED;
+  }
+  // C[M,K] = A[M,N] . B where B(row=k, kk=n) = w[n*K + k]  (MN-contiguous)
+  GemmP p{};
+  p.A = dy; p.B = w; p.C = dx; p.lda = lddy; p.ldb = K; p.ldc = lddx;
+  p.M = (int)M; p.N = (int)K; p.K = (int)N; p.aux = aux; p.ldaux = ldaux; p.mask_mode = mask_mode;
+  p.scale = scale; p.accumulate = accumulate;
+  dim3 grid((unsigned)ceil_div(K, BN), (unsigned)ceil_div(M, BM), 1);
+  gemm_f32_kernel<true, false, false><<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  TTAM_LAUNCH_CHECK();
+  return TTAM_OK;
+}
+
+extern "C" int64_t ttam_linear_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+  int s = wgrad_splits(M, N, K);
+  return (int64_t)s * (N * K + N) * (int64_t)sizeof(float);
+}
+
+extern "C" int ttam_linear_wgrad(const float* dy, int64_t lddy, const float* x, int64_t ldx, const int64_t* gather,
+                                 float* dw, float* db, int64_t M, int64_t N, int64_t K, int accumulate,
+                                 void* workspace, int64_t workspace_bytes, int precision, void* stream) {
+  TTAM_CHECK_ARG(dy && x && dw && workspace, "linear_wgrad: null pointer");
+  TTAM_CHECK_ARG(M > 0 && N > 0 && K > 0 && lddy >= N && ldx >= K, "linear_wgrad: bad shape");
+  if (precision != TTAM_PREC_FP32) {
+    set_error("linear_wgrad: precision %d is not built into this library yet", precision);
+    return TTAM_EUNSUPPORTED;
+  }
+  if (workspace_bytes < ttam_linear_wgrad_workspace_bytes(M, N, K)) {
+    set_error("linear_wgrad: workspace too small");
+    return TTAM_EWORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int splits = wgrad_splits(M, N, K);
+  const int chunk = (int)align_up(ceil_div(M, splits), BK);
+  float* partial_w = (float*)workspace;
+  float* partial_b = partial_w + (int64_t)splits * N * K;
+  // C[N,K] = sum_m A(row=n, k=m) * B(row=k, k=m);  A = dy (MN-contiguous), B = x rows (MN-contiguous, gathered on m)
+  GemmP p{};
+  p.A = dy; p.B = x; p.C = partial_w; p.lda = lddy; p.ldb = ldx; p.ldc = K; p.gatherK = gather;
+  p.M = (int)N; p.N = (int)K; p.K = (int)M; p.k_begin_stride = chunk; p.scale = 1.f;
+  const int real_splits = (int)ceil_div(M, chunk);
+  dim3 grid((unsigned)ceil_div(K, BN), (unsigned)ceil_div(N, BM), (unsigned)real_splits);
+  gemm_f32_kernel<false, false, false><<<grid, 256, 0, s>>>(p);
+  TTAM_LAUNCH_CHECK();
+  {
+    int64_t numel = N * K;
+    int blocks = (int)std::min<int64_t>(ceil_div(numel, 256), (int64_t)num_sms() * 8);
+    splitk_reduce_kernel<<<blocks, 256, 0, s>>>(partial_w, real_splits, numel, dw, accumulate);
+    TTAM_LAUNCH_CHECK();
+  }
+  if (db) {
+    dim3 g2((unsigned)ceil_div(N, 256), (unsigned)real_splits, 1);
+    colsum_partial_kernel<<<g2, 256, 0, s>>>(dy, lddy, (int)M, (int)N, chunk, partial_b);
+    TTAM_LAUNCH_CHECK();
+    splitk_reduce_kernel<<<(int)ceil_div(N, 256), 256, 0, s>>>(partial_b, real_splits, N, db, accumulate);
+    TTAM_LAUNCH_CHECK();
+  }
+  return TTAM_OK;
+}

@@ -1,0 +1,433 @@
+// Row gather / cast / gate / augmentation / fused loss kernels (HBM-bound, SIMT by design).
+//   ttam_gather_rows_f32 : nn.Embedding.forward / index_select     (reference encoders.py:223,
+//                          adaptive_mimic.py:97-105, training.py:743-775)
+//   ttam_gate_fwd/bwd    : FeatureFusionGate tail + _apply_aug      (encoders.py:160-168, adaptive_mimic.py:88-95)
+//   ttam_loss_fwd_bwd    : dot products + BCEWithLogits + 2x MSE    (training.py:770-803, adaptive_mimic.py:66-67)
+#include "common.cuh"
+
+namespace ttam {
+
+// ------------------------------------------------------------------------------------------------
+// gather: one 16-byte chunk per thread-iteration, 4 independent loads in flight per thread
+// ------------------------------------------------------------------------------------------------
+template <bool VEC>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ table, int64_t ld_t,
+                                                          int64_t num_rows, const int64_t* __restrict__ idx,
+                                                          float* __restrict__ out, int64_t ld_o, int64_t R,
+                                                          int64_t ncols) {
+  if (VEC) {
+    const int64_t cpr = ncols >> 2;  // chunks per row
+    const int64_t total = R * cpr;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < total; i += 4 * stride) {
+      float4 v[4];
+      int64_t r[4], c[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        int64_t j = i + u * stride;
+        r[u] = j / cpr;
+        c[u] = j - r[u] * cpr;
+        int64_t src = idx[r[u]];
+        v[u] = (src >= 0 && src < num_rows) ? ld_f4(table + src * ld_t + c[u] * 4) : make_float4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) st_f4(out + r[u] * ld_o + c[u] * 4, v[u]);
+    }
+    for (; i < total; i += stride) {
+      int64_t r = i / cpr, c = i - r * cpr;
+      int64_t src = idx[r];
+      float4 v = (src >= 0 && src < num_rows) ? ld_f4(table + src * ld_t + c * 4) : make_float4(0, 0, 0, 0);
+      st_f4(out + r * ld_o + c * 4, v);
+    }
+  } else {
+    const int64_t total = R * ncols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+      int64_t r = i / ncols, c = i - r * ncols;
+      int64_t src = idx[r];
+      out[r * ld_o + c] = (src >= 0 && src < num_rows) ? table[src * ld_t + c] : 0.f;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src, int64_t ld_s,
+                                                        uint16_t* __restrict__ dst, int64_t ld_d, int64_t R,
+                                                        int64_t ncols) {
+  const int64_t total = R * ncols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / ncols, c = i - r * ncols;
+    uint32_t u = __float_as_uint(src[r * ld_s + c]);
+    // round to nearest even; NaN stays NaN
+    uint32_t lsb = (u >> 16) & 1u;
+    uint32_t rounded = u + 0x7FFFu + lsb;
+    uint16_t h = ((u & 0x7F800000u) == 0x7F800000u) ? (uint16_t)((u >> 16) | ((u & 0xFFFFu) ? 0x40u : 0u))
+                                                    : (uint16_t)(rounded >> 16);
+    dst[r * ld_d + c] = h;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// gate forward / backward, augmentation
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void __launch_bounds__(256) gate_fwd_kernel(const float* __restrict__ z, const float* __restrict__ pre2,
+                                                       const float* __restrict__ aug, int64_t aug_rows,
+                                                       const int64_t* __restrict__ idx, float* __restrict__ g,
+                                                       float* __restrict__ t, float* __restrict__ o,
+                                                       float* __restrict__ q_out, int64_t R, int64_t D) {
+  const int64_t total = R * D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / D, d = i - r * D;
+    float e = z[r * 2 * D + d], f = z[r * 2 * D + D + d];
+    float gg = sigmoidf_(pre2[i]);
+    float tt = gg * e + (1.f - gg) * f;
+    g[i] = gg;
+    if (t) t[i] = tt;
+    float q = 0.f;
+    if (aug) {
+      int64_t src = idx[r];
+      q = (src >= 0 && src < aug_rows) ? aug[src * D + d] : 0.f;
+      if (q_out) q_out[i] = q;
+    }
+    if (o) o[i] = tt + q;
+  }
+}
+
+__global__ void __launch_bounds__(256) gate_bwd_kernel(const float* __restrict__ dt, const float* __restrict__ z,
+                                                       const float* __restrict__ g, float* __restrict__ dpre2,
+                                                       float* __restrict__ dz, int64_t R, int64_t D) {
+  const int64_t total = R * D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / D, d = i - r * D;
+    float e = z[r * 2 * D + d], f = z[r * 2 * D + D + d];
+    float gg = g[i], d_t = dt[i];
+    dpre2[i] = d_t * (e - f) * gg * (1.f - gg);
+    dz[r * 2 * D + d] = d_t * gg;
+    dz[r * 2 * D + D + d] = d_t * (1.f - gg);
+  }
+}
+
+__global__ void __launch_bounds__(256) augment_fwd_kernel(const float* __restrict__ t, const float* __restrict__ aug,
+                                                          int64_t aug_rows, const int64_t* __restrict__ idx,
+                                                          float* __restrict__ o, float* __restrict__ q_out, int64_t R,
+                                                          int64_t D) {
+  const int64_t total = R * D;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / D, d = i - r * D;
+    int64_t src = idx[r];
+    float q = (src >= 0 && src < aug_rows) ? aug[src * D + d] : 0.f;
+    if (q_out) q_out[i] = q;
+    o[i] = t[i] + q;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused loss: one warp per positive pair
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxNeg = 16;
+
+__device__ __forceinline__ float softplusf_(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
+
+__global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ o_u, const float* __restrict__ o_i,
+                                                   const float* __restrict__ t_u, const float* __restrict__ t_p,
+                                                   const float* __restrict__ q_u, const float* __restrict__ q_p,
+                                                   float cu, float ci, float* __restrict__ partial,
+                                                   float* __restrict__ do_u, float* __restrict__ do_i,
+                                                   float* __restrict__ dq_u, float* __restrict__ dq_p, int B, int N,
+                                                   int D, float inv_M) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B) return;
+  const int b = warp;
+  const float* u = o_u + (int64_t)b * D;
+  const float* p = o_i + (int64_t)b * D;
+  const float* n0 = o_i + ((int64_t)B + (int64_t)b * N) * D;
+  float sp = 0.f;
+  float sn[kMaxNeg];
+#pragma unroll
+  for (int n = 0; n < kMaxNeg; ++n) sn[n] = 0.f;
+  for (int d = lane; d < D; d += 32) {
+    float uu = u[d];
+    sp = fmaf(uu, p[d], sp);
+#pragma unroll
+    for (int n = 0; n < kMaxNeg; ++n)
+      if (n < N) sn[n] = fmaf(uu, n0[(int64_t)n * D + d], sn[n]);
+  }
+  sp = warp_sum(sp);
+  float bce = softplusf_(-sp);
+  float dsp = (sigmoidf_(sp) - 1.f) * inv_M;
+#pragma unroll
+  for (int n = 0; n < kMaxNeg; ++n)
+    if (n < N) {
+      float s = warp_sum(sn[n]);
+      bce += softplusf_(s);
+      sn[n] = sigmoidf_(s) * inv_M;  // reuse as ds_neg
+    }
+  float mu = 0.f, mi = 0.f;
+  const bool mimic = (q_u != nullptr);
+  const bool bwd = (do_u != nullptr);
+  if (bwd || mimic) {
+    for (int d = lane; d < D; d += 32) {
+      float uu = u[d], pp = p[d];
+      float gu = dsp * pp;
+      if (bwd) {
+#pragma unroll
+        for (int n = 0; n < kMaxNeg; ++n)
+          if (n < N) {
+            float nn = n0[(int64_t)n * D + d];
+            gu = fmaf(sn[n], nn, gu);
+            do_i[((int64_t)B + (int64_t)b * N + n) * D + d] = sn[n] * uu;
+          }
+        do_u[(int64_t)b * D + d] = gu;
+        do_i[(int64_t)b * D + d] = dsp * uu;
+      }
+      if (mimic) {
+        float du = q_u[(int64_t)b * D + d] - t_p[(int64_t)b * D + d];
+        float di = q_p[(int64_t)b * D + d] - t_u[(int64_t)b * D + d];
+        mu = fmaf(du, du, mu);
+        mi = fmaf(di, di, mi);
+        if (bwd) {
+          dq_u[(int64_t)b * D + d] = fmaf(cu, du, gu);
+          dq_p[(int64_t)b * D + d] = fmaf(ci, di, dsp * uu);
+        }
+      }
+    }
+    mu = warp_sum(mu);
+    mi = warp_sum(mi);
+  }
+  if (lane == 0) {
+    partial[(int64_t)b * 3 + 0] = bce;
+    partial[(int64_t)b * 3 + 1] = mu;
+    partial[(int64_t)b * 3 + 2] = mi;
+  }
+}
+
+// deterministic final reduction: one block, fixed-order strided partial sums + tree
+__global__ void __launch_bounds__(1024) loss_reduce_kernel(const float* __restrict__ partial, int B, float inv_M,
+                                                           float inv_BD, float lambda_u, float lambda_i, int mimic,
+                                                           float* __restrict__ loss_out) {
+  __shared__ double sh[3][1024];
+  double a0 = 0, a1 = 0, a2 = 0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    a0 += partial[(int64_t)b * 3 + 0];
+    a1 += partial[(int64_t)b * 3 + 1];
+    a2 += partial[(int64_t)b * 3 + 2];
+  }
+  sh[0][threadIdx.x] = a0;
+  sh[1][threadIdx.x] = a1;
+  sh[2][threadIdx.x] = a2;
+  __syncthreads();
+  for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + s];
+      sh[1][threadIdx.x] += sh[1][threadIdx.x + s];
+      sh[2][threadIdx.x] += sh[2][threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    float bce = (float)(sh[0][0] * (double)inv_M);
+    float mu = (float)(sh[1][0] * (double)inv_BD);
+    float mi = (float)(sh[2][0] * (double)inv_BD);
+    float total = bce;
+    if (mimic && lambda_u > 0.f) total += lambda_u * mu;
+    if (mimic && lambda_i > 0.f) total += lambda_i * mi;
+    loss_out[0] = total;
+    loss_out[1] = bce;
+    loss_out[2] = mu;
+    loss_out[3] = mi;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// step state, elementwise activation (+dropout) for the non-ReLU feature encoders
+// ------------------------------------------------------------------------------------------------
+__global__ void advance_step_kernel(ttam_step_state* st, uint64_t rng_stride) {
+  st->step += 1;
+  st->rng_offset += rng_stride;
+}
+
+__device__ __forceinline__ float act_fwd_(int act, float x) {
+  switch (act) {
+    case TTAM_ACT_RELU: return fmaxf(x, 0.f);
+    case TTAM_ACT_TANH: return tanhf(x);
+    case TTAM_ACT_GELU: return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+    case TTAM_ACT_SELU: {
+      const float alpha = 1.6732632423543772848170429916717f, scale = 1.0507009873554804934193349852946f;
+      return scale * (x > 0.f ? x : alpha * (expf(x) - 1.f));
+    }
+    default: return x;
+  }
+}
+__device__ __forceinline__ float act_bwd_(int act, float x) {
+  switch (act) {
+    case TTAM_ACT_RELU: return x > 0.f ? 1.f : 0.f;
+    case TTAM_ACT_TANH: { float t = tanhf(x); return 1.f - t * t; }
+    case TTAM_ACT_GELU: {
+      const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+      const float pdf = expf(-0.5f * x * x) * 0.39894228040143267794f;
+      return cdf + x * pdf;
+    }
+    case TTAM_ACT_SELU: {
+      const float alpha = 1.6732632423543772848170429916717f, scale = 1.0507009873554804934193349852946f;
+      return x > 0.f ? scale : scale * alpha * expf(x);
+    }
+    default: return 1.f;
+  }
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(256) act_kernel(const float* __restrict__ dy, const float* __restrict__ pre,
+                                                  float* __restrict__ out, int64_t n, int act, float p, uint64_t seed,
+                                                  uint64_t offset, const ttam_step_state* __restrict__ st) {
+  const float keep_scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  const uint64_t base = offset + ((p > 0.f && st) ? st->rng_offset : 0ull);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = pre[i];
+    float v = BWD ? dy[i] * act_bwd_(act, x) : act_fwd_(act, x);
+    if (p > 0.f) v = dropout_keep(seed, base + (uint64_t)i, p) ? v * keep_scale : 0.f;
+    out[i] = v;
+  }
+}
+
+static inline int grid_for(int64_t total, int threads, int per_thread = 4) {
+  int64_t blocks = ceil_div(total, (int64_t)threads * per_thread);
+  int64_t cap = (int64_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace ttam
+
+using namespace ttam;
+
+extern "C" int ttam_gather_rows_f32(const float* table, int64_t ld_table, int64_t num_rows, const int64_t* idx,
+                                    float* out, int64_t ld_out, int64_t R, int64_t ncols, void* stream) {
+  TTAM_CHECK_ARG(table && idx && out, "gather_rows: null pointer");
+  TTAM_CHECK_ARG(R >= 0 && ncols > 0 && ld_table >= ncols && ld_out >= ncols, "gather_rows: bad shape");
+  if (R == 0) return TTAM_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  bool vec = (ncols % 4 == 0) && (ld_table % 4 == 0) && (ld_out % 4 == 0) && (((uintptr_t)table & 15) == 0) &&
+             (((uintptr_t)out & 15) == 0);
+  if (vec)
+    gather_rows_kernel<true><<<grid_for(R * (ncols / 4), 256), 256, 0, s>>>(table, ld_table, num_rows, idx, out,
+                                                                           ld_out, R, ncols);
+  else
+    gather_rows_kernel<false><<<grid_for(R * ncols, 256), 256, 0, s>>>(table, ld_table, num_rows, idx, out, ld_out,
+                                                                      R, ncols);
+  TTAM_LAUNCH_CHECK();
+  return TTAM_OK;
+}
+
+extern "C" int ttam_cast_f32_to_bf16(const float* src, int64_t ld_src, uint16_t* dst, int64_t ld_dst, int64_t R,
+                                     int64_t ncols, void* stream) {
+  TTAM_CHECK_ARG(src && dst && R >= 0 && ncols > 0, "cast: bad argument");
+  if (R == 0) return TTAM_OK;
+  cast_bf16_kernel<<<grid_for(R * ncols, 256), 256, 0, (cudaStream_t)stream>>>(src, ld_src, dst, ld_dst, R, ncols);
+  TTAM_LAUNCH_CHECK();
+  return TTAM_OK;
+}
+
+extern "C" int ttam_gate_fwd(const float* z, const float* pre2, const float* aug_table, int64_t aug_rows,
+                             const int64_t* idx, float* g, float* t, float* o, float* q_out, int64_t R, int64_t D,
+                             void* stream) {
+  TTAM_CHECK_ARG(z && pre2 && g, "gate_fwd: null pointer");
+  TTAM_CHECK_ARG(!aug_table || idx, "gate_fwd: augmentation needs indices");
+  if (R == 0) return TTAM_OK;
+  gate_fwd_kernel<<<grid_for(R * D, 256, 2), 256, 0, (cudaStream_t)stream>>>(z, pre2, aug_table, aug_rows, idx, g, t,
+                                                                             o, q_out, R, D);
+  TTAM_LAUNCH_CHECK();
+  return TTAM_OK;
+}
+
+extern "C" int ttam_gate_bwd(const float* dt, const float* z, const float* g, float* dpre2, float* dz, int64_t R,
+                             int64_t D, void* stream) {
+  TTAM_CHECK_ARG(dt && z && g && dpre2 && dz, "gate_bwd: null pointer");
+  if (R == 0) return TTAM_OK;
+  gate_bwd_kernel<<<grid_for(R * D, 256, 2), 256, 0, (cudaStream_t)stream>>>(dt, z, g, dpre2, dz, R, D);
+  TTAM_LAUNCH_CHECK();
+  return TTAM_OK;
+}
+
+extern "C" int ttam_augment_fwd(const float* t, const float* aug_table, int64_t aug_rows, const int64_t* idx,
+                                float* o, float* q_out, int64_t R, int64_t D, void* stream) {
+  TTAM_CHECK_ARG(t && aug_table && idx && o, "augment_fwd: null pointer");
+  if (R == 0) return TTAM_OK;
+  augment_fwd_kernel<<<grid_for(R * D, 256, 2), 256, 0, (cudaStream_t)stream>>>(t, aug_table, aug_rows, idx, o, q_out,
+                                                                                R, D);
+  TTAM_LAUNCH_CHECK();
+  return TTAM_OK;
+}
+
+extern "C" int64_t ttam_loss_workspace_bytes(int64_t B) { return B * 3 * (int64_t)sizeof(float); }
+
+extern "C" int ttam_loss_fwd_bwd(const float* o_u, const float* o_i, const float* t_u, const float* t_p,
+                                 const float* q_u, const float* q_p, float lambda_u, float lambda_i, float* loss_out,
+                                 float* do_u, float* do_i, float* dq_u, float* dq_p, int64_t B, int64_t N, int64_t D,
+                                 void* workspace, int64_t workspace_bytes, void* stream) {
+  TTAM_CHECK_ARG(o_u && o_i && loss_out && workspace, "loss: null pointer");
+  TTAM_CHECK_ARG(B > 0 && N > 0 && N <= kMaxNeg && D > 0, "loss: need B>0, 0<N<=%d, D>0", kMaxNeg);
+  TTAM_CHECK_ARG((q_u == nullptr) == (q_p == nullptr) && (q_u == nullptr) == (t_u == nullptr) &&
+                     (q_u == nullptr) == (t_p == nullptr),
+                 "loss: mimic inputs must be all set or all null");
+  TTAM_CHECK_ARG((do_u == nullptr) == (do_i == nullptr), "loss: do_u/do_i must both be set or both null");
+  TTAM_CHECK_ARG(!(do_u && q_u) || (dq_u && dq_p), "loss: dq_u/dq_p required with mimic backward");
+  if (workspace_bytes < ttam_loss_workspace_bytes(B)) {
+    set_error("loss: workspace too small");
+    return TTAM_EWORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const double M = (double)B * (double)(1 + N);
+  const float inv_M = (float)(1.0 / M);
+  const float inv_BD = (float)(1.0 / ((double)B * (double)D));
+  // dL/dq extra term: lambda * 2 (q - t) / (B*D)   (only when lambda > 0: training.py:800-803)
+  const float cu = lambda_u > 0.f ? (float)(2.0 * (double)lambda_u / ((double)B * (double)D)) : 0.f;
+  const float ci = lambda_i > 0.f ? (float)(2.0 * (double)lambda_i / ((double)B * (double)D)) : 0.f;
+  const int threads = 256;
+  const int blocks = (int)ceil_div(B * 32, threads);
+  loss_kernel<<<blocks, threads, 0, s>>>(o_u, o_i, t_u, t_p, q_u, q_p, cu, ci, (float*)workspace, do_u, do_i, dq_u,
+                                         dq_p, (int)B, (int)N, (int)D, inv_M);
+  TTAM_LAUNCH_CHECK();
+  loss_reduce_kernel<<<1, 1024, 0, s>>>((const float*)workspace, (int)B, inv_M, inv_BD, lambda_u, lambda_i,
+                                        q_u != nullptr, loss_out);
+  TTAM_LAUNCH_CHECK();
+  return TTAM_OK;
+}
+
+extern "C" int ttam_advance_step(ttam_step_state* state_dev, uint64_t rng_stride, void* stream) {
+  TTAM_CHECK_ARG(state_dev, "advance_step: null state");
+  advance_step_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state_dev, rng_stride);
+  TTAM_LAUNCH_CHECK();
+  return TTAM_OK;
+}
+
+// NOTE: the dropout counter of element (m, n) is offset + m*row_len + n, the same indexing the fused
+// epilogue of ttam_linear_fwd uses, so `n` must cover whole contiguous rows of length row_len.
+extern "C" int ttam_act_fwd(const float* pre, float* y, int64_t n, int64_t row_len, int act, float dropout_p,
+                            uint64_t seed, uint64_t offset, const ttam_step_state* state_dev, void* stream) {
+  TTAM_CHECK_ARG(pre && y && n >= 0 && row_len > 0, "act_fwd: bad argument");
+  TTAM_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "act_fwd: dropout must be in [0,1)");
+  if (n == 0) return TTAM_OK;
+  act_kernel<false><<<grid_for(n, 256, 2), 256, 0, (cudaStream_t)stream>>>(nullptr, pre, y, n, act, dropout_p, seed,
+                                                                          offset, state_dev);
+  TTAM_LAUNCH_CHECK();
+  return TTAM_OK;
+}
+
+extern "C" int ttam_act_bwd(const float* dy, const float* pre, float* dpre, int64_t n, int64_t row_len, int act,
+                            float dropout_p, uint64_t seed, uint64_t offset, const ttam_step_state* state_dev,
+                            void* stream) {
+  TTAM_CHECK_ARG(dy && pre && dpre && n >= 0 && row_len > 0, "act_bwd: bad argument");
+  if (n == 0) return TTAM_OK;
+  act_kernel<true><<<grid_for(n, 256, 2), 256, 0, (cudaStream_t)stream>>>(dy, pre, dpre, n, act, dropout_p, seed, offset,
+                                                                         state_dev);
+  TTAM_LAUNCH_CHECK();
+  return TTAM_OK;
+}

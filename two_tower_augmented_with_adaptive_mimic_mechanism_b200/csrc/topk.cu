@@ -1,0 +1,190 @@
+// Exact inner-product top-K (fp32 SIMT path), candidate re-scoring and shard merge.
+// Replaces faiss.IndexFlatIP.search + host filtering input (reference training.py:672-675,955-958) and the
+// chunked torch.topk of _score_all_items_for_user (training.py:354-382).
+// Result order is canonical: descending score, ascending id on ties.
+#include "gemm_simt.cuh"
+#include <cub/cub.cuh>
+
+namespace ttam {
+
+// ---- order-preserving key: ascending uint64 == (descending score, ascending id) -----------------------------
+__host__ __device__ __forceinline__ uint64_t make_key(float score, uint32_t id) {
+  if (score == 0.f) score = 0.f;  // -0.0 -> +0.0 so that it ties with +0.0
+  uint32_t u;
+#ifdef __CUDA_ARCH__
+  u = __float_as_uint(score);
+#else
+  memcpy(&u, &score, 4);
+#endif
+  uint32_t ordered = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending with the float order
+  return ((uint64_t)(~ordered) << 32) | (uint64_t)id;
+}
+__device__ __forceinline__ float key_score(uint64_t key) {
+  uint32_t ordered = ~(uint32_t)(key >> 32);
+  uint32_t u = (ordered & 0x80000000u) ? (ordered & 0x7FFFFFFFu) : ~ordered;
+  return __uint_as_float(u);
+}
+constexpr uint64_t kWorstKey = ~0ull;  // sorts last; decodes to id 0xFFFFFFFF
+
+constexpr int kSelThreads = 256;
+constexpr int kSelItems = 20;                       // 5120 keys per block
+constexpr int kSelCap = kSelThreads * kSelItems;
+
+// One block per query: new running top-K = best K of (running K keys  U  chunk scores).
+// scores: [Q, ld] fp32 for ids id0 .. id0+n-1.  running: [Q, K] keys (sorted ascending).
+__global__ void __launch_bounds__(kSelThreads) select_topk_kernel(const float* __restrict__ scores, int64_t ld, int n,
+                                                                  uint32_t id0, uint64_t* __restrict__ running, int K) {
+  using Sort = cub::BlockRadixSort<uint64_t, kSelThreads, kSelItems>;
+  __shared__ typename Sort::TempStorage temp;
+  const int q = blockIdx.x;
+  uint64_t keys[kSelItems];
+  // blocked arrangement: thread t owns slots t*kSelItems .. +kSelItems-1
+#pragma unroll
+  for (int i = 0; i < kSelItems; ++i) {
+    const int slot = threadIdx.x * kSelItems + i;
+    uint64_t k = kWorstKey;
+    if (slot < K) k = running[(int64_t)q * K + slot];
+    else if (slot - K < n) k = make_key(scores[(int64_t)q * ld + (slot - K)], id0 + (uint32_t)(slot - K));
+    keys[i] = k;
+  }
+  Sort(temp).Sort(keys);
+#pragma unroll
+  for (int i = 0; i < kSelItems; ++i) {
+    const int slot = threadIdx.x * kSelItems + i;
+    if (slot < K) running[(int64_t)q * K + slot] = keys[i];
+  }
+}
+
+__global__ void fill_keys_kernel(uint64_t* keys, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    keys[i] = kWorstKey;
+}
+
+__global__ void decode_keys_kernel(const uint64_t* __restrict__ keys, int64_t n, int64_t id_offset,
+                                   int64_t* __restrict__ ids, float* __restrict__ scores) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t k = keys[i];
+    if (k == kWorstKey) {
+      ids[i] = -1;
+      if (scores) scores[i] = -INFINITY;
+    } else {
+      ids[i] = (int64_t)(uint32_t)k + id_offset;
+      if (scores) scores[i] = key_score(k);
+    }
+  }
+}
+
+// merge `parts` sorted/unsorted lists of K_in (score,id) pairs per query into the best K_out (ids are global int64,
+// so the key carries the position and the id is looked up afterwards; ties broken by the int64 id).
+constexpr int kMergeThreads = 128;
+constexpr int kMergeItems = 8;  // 1024 candidates per query
+struct MergeKey {
+  float score;
+  int64_t id;
+};
+__global__ void __launch_bounds__(kMergeThreads) merge_kernel(const int64_t* __restrict__ ids,
+                                                              const float* __restrict__ scores, int total, int K_out,
+                                                              int64_t* __restrict__ out_ids,
+                                                              float* __restrict__ out_scores) {
+  // two-pass radix sort: stable sort by id ascending, then stable sort by score descending
+  using SortId = cub::BlockRadixSort<int64_t, kMergeThreads, kMergeItems, float>;
+  using SortSc = cub::BlockRadixSort<uint32_t, kMergeThreads, kMergeItems, int64_t>;
+  __shared__ union {
+    typename SortId::TempStorage a;
+    typename SortSc::TempStorage b;
+  } temp;
+  const int q = blockIdx.x;
+  int64_t kid[kMergeItems];
+  float ksc[kMergeItems];
+#pragma unroll
+  for (int i = 0; i < kMergeItems; ++i) {
+    const int slot = threadIdx.x * kMergeItems + i;
+    if (slot < total && ids[(int64_t)q * total + slot] >= 0) {
+      kid[i] = ids[(int64_t)q * total + slot];
+      ksc[i] = scores[(int64_t)q * total + slot];
+    } else {
+      kid[i] = INT64_MAX;
+      ksc[i] = -INFINITY;
+    }
+  }
+  SortId(temp.a).Sort(kid, ksc);
+  __syncthreads();
+  uint32_t skey[kMergeItems];
+#pragma unroll
+  for (int i = 0; i < kMergeItems; ++i) skey[i] = (uint32_t)(make_key(ksc[i], 0) >> 32);
+  SortSc(temp.b).Sort(skey, kid);  // LSD radix sort is stable: equal scores keep ascending id order
+#pragma unroll
+  for (int i = 0; i < kMergeItems; ++i) {
+    const int slot = threadIdx.x * kMergeItems + i;
+    if (slot < K_out) {
+      const bool valid = kid[i] != INT64_MAX;
+      out_ids[(int64_t)q * K_out + slot] = valid ? kid[i] : -1;
+      out_scores[(int64_t)q * K_out + slot] = valid ? key_score((uint64_t)skey[i] << 32) : -INFINITY;
+    }
+  }
+}
+
+constexpr int kQBlock = 2048;   // queries per scoring pass
+constexpr int kChunk = 4096;    // items per scoring pass (+K <= kSelCap)
+
+}  // namespace ttam
+
+using namespace ttam;
+
+extern "C" int64_t ttam_topk_f32_workspace_bytes(int64_t Q, int64_t N, int64_t D, int64_t K) {
+  (void)N; (void)D;
+  int64_t qb = Q < kQBlock ? Q : kQBlock;
+  return align_up(qb * kChunk * 4, 256) + align_up(Q * K * 8, 256) + 256;
+}
+
+extern "C" int ttam_topk_f32(const float* q, const float* items, int64_t Q, int64_t N, int64_t D, int64_t K,
+                             int64_t id_offset, int64_t* out_ids, float* out_scores, void* workspace,
+                             int64_t workspace_bytes, void* stream) {
+  TTAM_CHECK_ARG(q && items && out_ids && workspace, "topk_f32: null pointer");
+  TTAM_CHECK_ARG(Q >= 0 && N > 0 && D > 0 && K > 0, "topk_f32: bad shape");
+  TTAM_CHECK_ARG(K + kChunk <= kSelCap, "topk_f32: K must be <= %d", kSelCap - kChunk);
+  TTAM_CHECK_ARG(N < (1ll << 32) - 1, "topk_f32: corpus too large for 32-bit local ids");
+  if (workspace_bytes < ttam_topk_f32_workspace_bytes(Q, N, D, K)) {
+    set_error("topk_f32: workspace too small");
+    return TTAM_EWORKSPACE;
+  }
+  if (Q == 0) return TTAM_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t qb = Q < kQBlock ? Q : kQBlock;
+  float* scores = (float*)workspace;
+  uint64_t* running = (uint64_t*)((char*)workspace + align_up(qb * kChunk * 4, 256));
+  fill_keys_kernel<<<(int)std::min<int64_t>(ceil_div(Q * K, 256), 4096), 256, 0, s>>>(running, Q * K);
+  TTAM_LAUNCH_CHECK();
+  for (int64_t q0 = 0; q0 < Q; q0 += qb) {
+    const int64_t nq = std::min<int64_t>(qb, Q - q0);
+    for (int64_t c0 = 0; c0 < N; c0 += kChunk) {
+      const int64_t nc = std::min<int64_t>(kChunk, N - c0);
+      GemmP p{};
+      p.A = q + q0 * D; p.B = items + c0 * D; p.C = scores; p.lda = D; p.ldb = D; p.ldc = kChunk;
+      p.M = (int)nq; p.N = (int)nc; p.K = (int)D; p.scale = 1.f;
+      dim3 grid((unsigned)ceil_div(nc, BN), (unsigned)ceil_div(nq, BM), 1);
+      gemm_f32_kernel<true, true, true><<<grid, 256, 0, s>>>(p);
+      TTAM_LAUNCH_CHECK();
+      select_topk_kernel<<<(unsigned)nq, kSelThreads, 0, s>>>(scores, kChunk, (int)nc, (uint32_t)c0,
+                                                              running + q0 * K, (int)K);
+      TTAM_LAUNCH_CHECK();
+    }
+  }
+  decode_keys_kernel<<<(int)std::min<int64_t>(ceil_div(Q * K, 256), 4096), 256, 0, s>>>(running, Q * K, id_offset,
+                                                                                        out_ids, out_scores);
+  TTAM_LAUNCH_CHECK();
+  return TTAM_OK;
+}
+
+extern "C" int ttam_topk_merge(const int64_t* ids, const float* scores, int64_t Q, int64_t parts, int64_t K_in,
+                               int64_t K_out, int64_t* out_ids, float* out_scores, void* stream) {
+  TTAM_CHECK_ARG(ids && scores && out_ids && out_scores, "topk_merge: null pointer");
+  TTAM_CHECK_ARG(parts > 0 && K_in > 0 && K_out > 0 && parts * K_in <= kMergeThreads * kMergeItems &&
+                     K_out <= parts * K_in,
+                 "topk_merge: parts*K_in must be <= %d and K_out <= parts*K_in", kMergeThreads * kMergeItems);
+  if (Q == 0) return TTAM_OK;
+  merge_kernel<<<(unsigned)Q, kMergeThreads, 0, (cudaStream_t)stream>>>(ids, scores, (int)(parts * K_in), (int)K_out,
+                                                                        out_ids, out_scores);
+  TTAM_LAUNCH_CHECK();
+  return TTAM_OK;
+}

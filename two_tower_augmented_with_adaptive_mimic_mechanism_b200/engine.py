@@ -1,0 +1,327 @@
+"""Fused training step, evaluation loss, corpus encoder and retrieval for a `TwoTowerModel`.
+
+This is the B200 replacement of the loop body of `_train_one_epoch` (reference training.py:726-831):
+towers -> mimic -> sampled-negative BCE -> backward -> optimiser step, as a fixed sequence of libttam launches
+on pre-allocated buffers.  No autograd, no dense table gradient: the duplicate gradient rows of the ID and
+augmentation tables are segment-reduced and applied row-wise (SparseAdam for `sparse=True` tables,
+lazy-exact AdamW/Adam/SGD for everything the reference hands to its dense optimiser).
+
+The engine updates the model's own parameter storage in place, so `state_dict()` / checkpoints keep working.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import functional as F
+from .tower_ops import TowerPlan, plan_from_module, tower_backward, tower_forward
+
+
+@dataclass
+class _Table:
+    """Optimiser state of one row-addressed table."""
+    name: str
+    weight: torch.Tensor
+    mode: str                      # "sparse_adam" | "lazy"
+    m: Optional[torch.Tensor] = None
+    v: Optional[torch.Tensor] = None
+    last_step: Optional[torch.Tensor] = None   # int32 [N], lazy tables only
+
+
+class FusedEngine:
+    def __init__(self, model, *, optimizer: str = "adamw", lr: float = 1e-3, weight_decay: float = 0.0,
+                 momentum: float = 0.0, dense_betas=(0.9, 0.999), sparse_betas=(0.9, 0.999), eps: float = 1e-8,
+                 loss_weights: Optional[dict] = None, precision: str = "fp32", seed: int = 1234,
+                 max_steps: int = 1 << 16, item_category_tensor=None, major_category_id=None) -> None:
+        self.model = model
+        mimic = getattr(model, "adaptive_mimic", None)
+        self.user: TowerPlan = plan_from_module(model.user_encoder, mimic.user_augmented if mimic is not None else None)
+        self.item: TowerPlan = plan_from_module(model.item_encoder, mimic.item_augmented if mimic is not None else None)
+        self.mimic = mimic is not None
+        dev = self.user.table.device
+        if dev.type != "cuda":
+            raise F._lib.TtamError(f"model is on {dev}: the fused engine needs CUDA (sm_100a) parameters; there is no CPU path")
+        F.lib()  # fail loudly now if libttam.so is missing
+        self.device = dev
+        self.kind = optimizer.lower()
+        if self.kind not in ("adamw", "adam", "sgd"):
+            raise ValueError(f"Unsupported optimizer: {optimizer}")
+        self.lr, self.wd, self.momentum, self.eps = float(lr), float(weight_decay), float(momentum), float(eps)
+        self.dense_betas, self.sparse_betas = tuple(dense_betas), tuple(sparse_betas)
+        w = loss_weights or {}
+        self.lambda_u = float(w.get("mimic_user", 0.0))
+        self.lambda_i = float(w.get("mimic_item", 0.0))
+        self.lambda_c = float(w.get("category_alignment", 0.0))
+        self.cat_tensor, self.major = item_category_tensor, major_category_id
+        self.precision = precision
+        self.seed = int(seed)
+        self.max_steps = int(max_steps)
+        self.t = 0                         # optimiser steps taken
+        self.dirty = False                 # lazy tables hold rows that are behind `t`
+        # ---- dense (small) parameters: one fused launch
+        seen, self.dense = set(), []
+        for p in self.user.dense_params() + self.item.dense_params():
+            if id(p) not in seen:
+                seen.add(id(p))
+                self.dense.append(p)
+        need_m = self.kind != "sgd" or self.momentum != 0.0
+        self.dense_m = [torch.zeros_like(p) for p in self.dense] if need_m else None
+        self.dense_v = [torch.zeros_like(p) for p in self.dense] if self.kind != "sgd" else None
+        # ---- tables
+        self.tables: dict[str, _Table] = {}
+        for side, plan in (("user", self.user), ("item", self.item)):
+            self._add_table(f"{side}_encoder.embedding.weight", plan.table, "sparse_adam" if plan.sparse else "lazy")
+            if plan.aug is not None:
+                self._add_table(f"adaptive_mimic.{side}_augmented.weight", plan.aug, "lazy")
+        # ---- step state + bias-correction tables (device resident: the step is CUDA-graph replayable)
+        self.state = F.new_step_state(dev, 0, 0)
+        self.scal_dense = F.adam_scalar_table(self.max_steps, self.lr, self.dense_betas, dev)
+        self.scal_sparse = F.adam_scalar_table(self.max_steps, self.lr, self.sparse_betas, dev)
+        self.bufs_u: dict = {}
+        self.bufs_i: dict = {}
+        self.misc: dict = {}
+        self._graphs: dict = {}
+
+    # --------------------------------------------------------------------------------------------
+    def _add_table(self, name, weight, mode):
+        t = _Table(name=name, weight=weight, mode=mode)
+        if mode == "sparse_adam" or self.kind != "sgd":
+            t.m, t.v = torch.zeros_like(weight), torch.zeros_like(weight)
+        elif self.momentum != 0.0:
+            t.m = torch.zeros_like(weight)
+        if mode == "lazy":
+            t.last_step = torch.zeros(weight.shape[0], dtype=torch.int32, device=weight.device)
+        self.tables[name] = t
+
+    def _misc(self, name, shape, dtype):
+        t = self.misc.get(name)
+        if t is None or t.shape[0] < shape[0] or t.shape[1:] != tuple(shape[1:]) or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self.misc[name] = t
+        return t[: shape[0]]
+
+    # --------------------------------------------------------------------------------------------
+    def _update_table(self, tab: _Table, idx, tag, grad_a, grad_b=None):
+        R = idx.numel()
+        sorted_idx = self._misc(f"sorted_{tag}", (R,), torch.int64)
+        perm = self._misc(f"perm_{tag}", (R,), torch.int32)
+        key = f"sorted_done_{tag}"
+        if not self._step_flags.get(key):
+            F.sort_rows(idx, tab.weight.shape[0], sorted_idx=sorted_idx, perm=perm)
+            self._step_flags[key] = True
+        if tab.mode == "sparse_adam":
+            F.sparse_adam_rows(tab.weight, tab.m, tab.v, sorted_idx, perm, grad_a, grad_b, lr=self.lr,
+                               betas=self.sparse_betas, eps=self.eps, step=self.t, scalars=self.scal_sparse,
+                               state=self.state)
+        else:
+            F.lazy_rows(self.kind, tab.weight, tab.m, tab.v, tab.last_step, sorted_idx, perm, grad_a, grad_b,
+                        scalars=self.scal_dense, lr=self.lr, weight_decay=self.wd, betas=self.dense_betas, eps=self.eps,
+                        momentum=self.momentum, step=self.t, state=self.state)
+
+    def _step_body(self, users, items, B, N, Xu, Xi):
+        self._step_flags = {}
+        launches0 = F.lib().ttam_launch_count()
+        F.advance_step(self.state, rng_stride=1 << 36)
+        cu = tower_forward(self.user, users, Xu, gather=True, train=True, bufs=self.bufs_u, seed=self.seed,
+                           rng_base=0, state=self.state, precision=self.precision, want_q=self.mimic)
+        ci = tower_forward(self.item, items, Xi, gather=True, train=True, bufs=self.bufs_i, seed=self.seed,
+                           rng_base=1 << 35, state=self.state, precision=self.precision, want_q=self.mimic)
+        D = cu.o.shape[1]
+        loss = self._misc("loss", (4,), torch.float32)
+        do_u = self._misc("do_u", (B, D), torch.float32)
+        do_i = self._misc("do_i", (B * (1 + N), D), torch.float32)
+        dq_u = self._misc("dq_u", (B, D), torch.float32) if self.mimic else None
+        dq_p = self._misc("dq_p", (B, D), torch.float32) if self.mimic else None
+        if self.mimic:
+            F.loss_fwd_bwd(cu.o, ci.o, t_u=cu.t, t_p=ci.t[:B], q_u=cu.q, q_p=ci.q[:B], lambda_u=self.lambda_u,
+                           lambda_i=self.lambda_i, out=(loss, do_u, do_i, dq_u, dq_p))
+        else:
+            F.loss_fwd_bwd(cu.o, ci.o, out=(loss, do_u, do_i, None, None))
+        if self.lambda_c > 0 and self.cat_tensor is not None and self.major is not None:
+            cal, gcal = category_alignment(items, ci.o, self.cat_tensor, self.major)
+            loss[0] += self.lambda_c * cal
+            if gcal is not None:
+                do_i.add_(gcal, alpha=self.lambda_c)
+                if self.mimic:
+                    dq_p.add_(gcal[:B], alpha=self.lambda_c)
+        grads: dict = {}
+        de_i = tower_backward(self.item, ci, do_i, grads, bufs=self.bufs_i, state=self.state, precision=self.precision)
+        de_u = tower_backward(self.user, cu, do_u, grads, bufs=self.bufs_u, state=self.state, precision=self.precision)
+        # ---- row-wise optimisers (no dense table gradient)
+        self._update_table(self.tables["user_encoder.embedding.weight"], users, "u", de_u)
+        self._update_table(self.tables["item_encoder.embedding.weight"], items, "i", de_i)
+        if self.mimic:
+            self._update_table(self.tables["adaptive_mimic.user_augmented.weight"], users, "u", dq_u)
+            self._update_table(self.tables["adaptive_mimic.item_augmented.weight"], items, "i", dq_p, do_i[B:])
+        # ---- dense optimiser on the MLP / gate / projection tensors that received a gradient
+        ps, gs, ms, vs = [], [], [], []
+        for j, p in enumerate(self.dense):
+            g = grads.get(id(p))
+            if g is None:
+                continue
+            ps.append(p.data); gs.append(g.view(p.shape))
+            if self.dense_m is not None:
+                ms.append(self.dense_m[j])
+            if self.dense_v is not None:
+                vs.append(self.dense_v[j])
+        if ps:
+            F.dense_step(self.kind, ps, gs, ms if self.dense_m is not None else None,
+                         vs if self.dense_v is not None else None, lr=self.lr, weight_decay=self.wd,
+                         betas=self.dense_betas, eps=self.eps, momentum=self.momentum, step=self.t,
+                         scalars=self.scal_dense, state=self.state)
+        self.launches_per_step = F.lib().ttam_launch_count() - launches0
+        return loss
+
+    @torch.no_grad()
+    def train_step(self, users: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor, user_x, item_x, *,
+                   graph: bool = False) -> torch.Tensor:
+        """One optimisation step on a batch (users [B], pos [B], neg [B,N], all int64 on the device).
+        Returns a device tensor loss[4] = {total, bce, mimic_user, mimic_item} (valid until the next step)."""
+        B, N = neg.shape
+        if self.t + 1 > self.max_steps:
+            raise RuntimeError(f"max_steps={self.max_steps} exhausted; build the engine with a larger max_steps")
+        if graph:
+            return self._graph_step(users, pos, neg, user_x, item_x)
+        items = self._misc("items", (B * (1 + N),), torch.int64)
+        items[:B].copy_(pos)
+        items[B:].copy_(neg.reshape(-1))
+        users = users.contiguous()
+        self.t += 1
+        self.dirty = True
+        return self._step_body(users, items, B, N, user_x, item_x)
+
+    def _graph_step(self, users, pos, neg, user_x, item_x):
+        B, N = neg.shape
+        key = (B, N, None if user_x is None else user_x.data_ptr(), None if item_x is None else item_x.data_ptr())
+        entry = self._graphs.get(key)
+        if entry is None:
+            su = torch.empty(B, dtype=torch.int64, device=self.device)
+            si = torch.empty(B * (1 + N), dtype=torch.int64, device=self.device)
+            su.copy_(users); si[:B].copy_(pos); si[B:].copy_(neg.reshape(-1))
+            # warm-up outside capture sizes every buffer; run it on copies of nothing: it IS a real step
+            self.t += 1
+            loss = self._step_body(su, si, B, N, user_x, item_x)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            # capture advances the device step once without executing: compensate afterwards
+            with torch.cuda.graph(g):
+                loss = self._step_body(su, si, B, N, user_x, item_x)
+            entry = (g, su, si, loss)
+            self._graphs[key] = entry
+            self.dirty = True
+            return loss
+        g, su, si, loss = entry
+        su.copy_(users); si[:B].copy_(pos); si[B:].copy_(neg.reshape(-1))
+        self.t += 1
+        self.dirty = True
+        g.replay()
+        return loss
+
+    # --------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def flush(self) -> None:
+        """Bring every lazily-updated table row up to the current step (before any full-table read)."""
+        if not self.dirty or self.t == 0:
+            return
+        for tab in self.tables.values():
+            if tab.mode == "lazy":
+                F.lazy_flush(self.kind, tab.weight, tab.m, tab.v, tab.last_step, scalars=self.scal_dense, lr=self.lr,
+                             weight_decay=self.wd, betas=self.dense_betas, eps=self.eps, momentum=self.momentum,
+                             step=self.t)
+        self.dirty = False
+
+    @torch.no_grad()
+    def encode(self, side: str, idx: torch.Tensor, X, *, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Eval-mode tower + augmentation for rows `idx` (reference training.py:613-643, 1019-1026)."""
+        self.flush()
+        plan = self.user if side == "user" else self.item
+        bufs = self.misc.setdefault(f"enc_{side}", {})
+        c = tower_forward(plan, idx.contiguous(), X, gather=True, train=False, bufs=bufs, precision=self.precision)
+        if out is None:
+            return c.o.clone()
+        out.copy_(c.o)
+        return out
+
+    @torch.no_grad()
+    def encode_all(self, side: str, X, chunk: int = 65536) -> torch.Tensor:
+        plan = self.user if side == "user" else self.item
+        n = plan.table.shape[0]
+        out = torch.empty((n, plan.out_dim), dtype=torch.float32, device=self.device)
+        for s in range(0, n, chunk):
+            e = min(n, s + chunk)
+            self.encode(side, torch.arange(s, e, device=self.device, dtype=torch.int64), X, out=out[s:e])
+        return out
+
+    @torch.no_grad()
+    def eval_loss(self, users, pos, neg, user_x, item_x) -> torch.Tensor:
+        """`_compute_loss` batch body (reference training.py:862-911): BCE on eval-mode augmented embeddings."""
+        B, N = neg.shape
+        items = torch.cat([pos.reshape(-1), neg.reshape(-1)])
+        o_u = self.encode("user", users, user_x)
+        o_i = self.encode("item", items, item_x)
+        loss, *_ = F.loss_fwd_bwd(o_u, o_i, backward=False)
+        return loss
+
+    # --------------------------------------------------------------------------------------------
+    def optimizer_state(self) -> dict:
+        """Per-parameter optimiser state in torch.optim layout ({name: {step, exp_avg, exp_avg_sq}})."""
+        self.flush()
+        out = {}
+        for name, tab in self.tables.items():
+            out[name] = {"step": self.t, "exp_avg": tab.m, "exp_avg_sq": tab.v}
+        names = {id(p): n for n, p in self.model.named_parameters()}
+        for j, p in enumerate(self.dense):
+            out[names.get(id(p), f"dense{j}")] = {
+                "step": self.t,
+                "exp_avg": None if self.dense_m is None else self.dense_m[j],
+                "exp_avg_sq": None if self.dense_v is None else self.dense_v[j]}
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# category-alignment loss (reference training.py:530-579).  Data-dependent control flow over the categories
+# present in the batch; kept as vectorised torch ops on the device for now.
+# ------------------------------------------------------------------------------------------------
+def category_alignment(item_idx: torch.Tensor, emb: torch.Tensor, cat_tensor: torch.Tensor, major: int):
+    """Returns (loss scalar tensor, d loss / d emb or None)."""
+    zero = emb.new_zeros(())
+    if item_idx.numel() == 0:
+        return zero, None
+    cats = cat_tensor.to(emb.device)[item_idx]
+    uniq, inv, counts = torch.unique(cats, return_inverse=True, return_counts=True)
+    if uniq.numel() <= 1:
+        return zero, None
+    is_major = uniq == int(major)
+    if not bool(is_major.any()) or int(counts[is_major][0]) < 2:
+        return zero, None
+    C, D = uniq.numel(), emb.shape[1]
+    cnt = counts.to(emb.dtype)
+    sums = emb.new_zeros((C, D)).index_add_(0, inv, emb)
+    mean = sums / cnt[:, None]
+    cen = emb - mean[inv]                                       # centred rows
+    # per-category covariance: sort rows by category and use one batched matmul over padded segments
+    order = torch.argsort(inv, stable=True)
+    cen_s = cen[order]
+    starts = torch.cumsum(counts, 0) - counts
+    maxn = int(counts.max())
+    pos_in_seg = torch.arange(cen_s.shape[0], device=emb.device) - starts[inv[order]]
+    padded = emb.new_zeros((C, maxn, D))
+    padded[inv[order], pos_in_seg] = cen_s
+    cov = padded.transpose(1, 2) @ padded / (cnt - 1).clamp_min(1)[:, None, None]
+    mj = int(torch.nonzero(is_major)[0])
+    use = (~is_major) & (counts >= 2)
+    n_c = int(use.sum())
+    if n_c == 0:
+        return zero, None
+    diff = (cov - cov[mj]) * use[:, None, None].to(emb.dtype)
+    loss = (diff * diff).sum() / n_c
+    # gradient: dL/dCov_c = 2 diff_c / n_c ; dL/dCov_major = -sum_c 2 diff_c / n_c ; dCov/dx = 2/(n-1) cen @ G (G symmetric)
+    G = 2.0 * diff / n_c
+    G[mj] = -G.sum(0)
+    scale = 2.0 / (cnt - 1).clamp_min(1)
+    gp = (padded @ G) * scale[:, None, None]                    # [C, maxn, D], same padded-segment layout
+    grad = torch.empty_like(emb)
+    grad[order] = gp[inv[order], pos_in_seg]
+    return loss, grad

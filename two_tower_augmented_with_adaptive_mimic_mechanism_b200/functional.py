@@ -1,0 +1,340 @@
+"""Tensor-level wrappers over the C ABI (include/ttam.h).  torch is used for device memory and
+streams only; every op below is one or two launches of our own sm_100a kernels."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ACT, OPT, PREC, TensorList, check, lib
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk(t: torch.Tensor, dtype, name: str) -> None:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a tensor")
+    if not t.is_cuda:
+        raise _lib.TtamError(f"{name} is on {t.device}; this package has no CPU path (CUDA tensors only)")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+
+
+def _rows2d(t: torch.Tensor, name: str):
+    """2-D tensor with unit inner stride -> (ptr, ld)."""
+    if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise ValueError(f"{name} must be 2-D with contiguous rows")
+    return t.data_ptr(), (t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1]))
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+_ws_cache: dict = {}
+
+
+def workspace(nbytes: int, device, tag: str = "default") -> torch.Tensor:
+    """Grow-only scratch buffer per (device, tag) so that hot loops never allocate."""
+    key = (str(device), tag)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+# ---------------------------------------------------------------------------------------------
+def gather_rows(table: torch.Tensor, idx: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    _chk(table, torch.float32, "table")
+    _chk(idx, torch.int64, "idx")
+    idx = idx.contiguous().view(-1)
+    tp, ldt = _rows2d(table, "table")
+    R, ncols = idx.numel(), table.shape[1]
+    if out is None:
+        out = torch.empty((R, ncols), dtype=torch.float32, device=table.device)
+    op, ldo = _rows2d(out, "out")
+    check(lib().ttam_gather_rows_f32(tp, ldt, table.shape[0], idx.data_ptr(), op, ldo, R, ncols, _stream()), "gather_rows")
+    return out
+
+
+def cast_bf16(src: torch.Tensor) -> torch.Tensor:
+    _chk(src, torch.float32, "src")
+    sp, lds = _rows2d(src, "src")
+    dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    check(lib().ttam_cast_f32_to_bf16(sp, lds, dst.data_ptr(), dst.stride(0), src.shape[0], src.shape[1], _stream()), "cast_bf16")
+    return dst
+
+
+def linear_fwd(x, w, bias=None, *, gather=None, act="none", out=None, dropout_p=0.0, seed=0, offset=0,
+               state=None, precision="fp32"):
+    _chk(x, torch.float32, "x"); _chk(w, torch.float32, "w")
+    xp, ldx = _rows2d(x, "x")
+    if not w.is_contiguous():
+        raise ValueError("w must be contiguous [N,K]")
+    N, K = w.shape
+    if x.shape[1] != K:
+        raise ValueError(f"x has {x.shape[1]} columns, weight expects {K}")
+    if gather is not None:
+        _chk(gather, torch.int64, "gather")
+        M = gather.numel()
+    else:
+        M = x.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    yp, ldy = _rows2d(out, "out")
+    check(lib().ttam_linear_fwd(xp, ldx, _ptr(gather), w.data_ptr(), _ptr(bias), yp, ldy, M, N, K, ACT[act],
+                                float(dropout_p), int(seed), int(offset), _ptr(state), PREC[precision], _stream()), "linear_fwd")
+    return out
+
+
+def linear_dgrad(dy, w, *, out=None, aux=None, relu_mask=False, scale=1.0, accumulate=False, precision="fp32"):
+    _chk(dy, torch.float32, "dy"); _chk(w, torch.float32, "w")
+    dyp, lddy = _rows2d(dy, "dy")
+    N, K = w.shape
+    M = dy.shape[0]
+    if out is None:
+        if accumulate:
+            raise ValueError("accumulate needs an output buffer")
+        out = torch.empty((M, K), dtype=torch.float32, device=dy.device)
+    dxp, lddx = _rows2d(out, "out")
+    auxp, ldaux = (None, 0)
+    if relu_mask:
+        auxp, ldaux = _rows2d(aux, "aux")
+    check(lib().ttam_linear_dgrad(dyp, lddy, w.data_ptr(), dxp, lddx, auxp, ldaux, 1 if relu_mask else 0, float(scale),
+                                  1 if accumulate else 0, M, N, K, PREC[precision], _stream()), "linear_dgrad")
+    return out
+
+
+def linear_wgrad(dy, x, *, gather=None, dw=None, db=None, accumulate=False, precision="fp32", want_bias=True):
+    _chk(dy, torch.float32, "dy"); _chk(x, torch.float32, "x")
+    dyp, lddy = _rows2d(dy, "dy")
+    xp, ldx = _rows2d(x, "x")
+    M, N = dy.shape
+    K = x.shape[1]
+    if dw is None:
+        dw = torch.empty((N, K), dtype=torch.float32, device=dy.device)
+        accumulate = False
+    if db is None and want_bias:
+        db = torch.empty((N,), dtype=torch.float32, device=dy.device)
+    nbytes = lib().ttam_linear_wgrad_workspace_bytes(M, N, K)
+    ws = workspace(nbytes, dy.device, "wgrad")
+    check(lib().ttam_linear_wgrad(dyp, lddy, xp, ldx, _ptr(gather), dw.data_ptr(), _ptr(db), M, N, K,
+                                  1 if accumulate else 0, ws.data_ptr(), ws.numel(), PREC[precision], _stream()), "linear_wgrad")
+    return dw, db
+
+
+def new_step_state(device, step: int = 0, rng_offset: int = 0) -> torch.Tensor:
+    """Device-resident ttam_step_state {int32 step; int32 pad; uint64 rng_offset} as an int64[2] tensor."""
+    return torch.tensor([int(step) & 0xFFFFFFFF, int(rng_offset)], dtype=torch.int64, device=device)
+
+
+def advance_step(state: torch.Tensor, rng_stride: int = 1 << 32) -> None:
+    check(lib().ttam_advance_step(state.data_ptr(), int(rng_stride), _stream()), "advance_step")
+
+
+def act_fwd(pre, *, act, out=None, dropout_p=0.0, seed=0, offset=0, state=None):
+    _chk(pre, torch.float32, "pre")
+    if out is None:
+        out = torch.empty_like(pre)
+    check(lib().ttam_act_fwd(pre.data_ptr(), out.data_ptr(), pre.numel(), pre.shape[-1], ACT[act], float(dropout_p),
+                             int(seed), int(offset), _ptr(state), _stream()), "act_fwd")
+    return out
+
+
+def act_bwd(dy, pre, *, act, out=None, dropout_p=0.0, seed=0, offset=0, state=None):
+    _chk(dy, torch.float32, "dy")
+    if out is None:
+        out = torch.empty_like(pre)
+    check(lib().ttam_act_bwd(dy.data_ptr(), pre.data_ptr(), out.data_ptr(), pre.numel(), pre.shape[-1], ACT[act],
+                             float(dropout_p), int(seed), int(offset), _ptr(state), _stream()), "act_bwd")
+    return out
+
+
+def gate_fwd(z, pre2, *, g, t=None, o=None, q=None, aug_table=None, idx=None):
+    """g = sigmoid(pre2); t = g*e + (1-g)*f with [e;f] = z; o = t + aug[idx]; q = aug[idx].  Outputs are caller-provided."""
+    _chk(z, torch.float32, "z"); _chk(pre2, torch.float32, "pre2")
+    R, D = pre2.shape
+    for name, ten in (("z", z), ("pre2", pre2), ("g", g), ("t", t), ("o", o), ("q", q)):
+        if ten is not None and not ten.is_contiguous():
+            raise ValueError(f"gate_fwd: {name} must be contiguous")
+    check(lib().ttam_gate_fwd(z.data_ptr(), pre2.data_ptr(), _ptr(aug_table), 0 if aug_table is None else aug_table.shape[0],
+                              _ptr(idx), g.data_ptr(), _ptr(t), _ptr(o), _ptr(q), R, D, _stream()), "gate_fwd")
+    return g, t, o, q
+
+
+def gate_bwd(dt, z, g, *, dpre2, dz):
+    R, D = g.shape
+    for name, ten in (("dt", dt), ("z", z), ("g", g), ("dpre2", dpre2), ("dz", dz)):
+        if not ten.is_contiguous():
+            raise ValueError(f"gate_bwd: {name} must be contiguous")
+    check(lib().ttam_gate_bwd(dt.data_ptr(), z.data_ptr(), g.data_ptr(), dpre2.data_ptr(), dz.data_ptr(), R, D, _stream()), "gate_bwd")
+    return dpre2, dz
+
+
+def augment_fwd(t, aug_table, idx, *, out, q_out=None):
+    """out = t + aug_table[idx]; q_out = aug_table[idx]."""
+    _chk(t, torch.float32, "t"); _chk(aug_table, torch.float32, "aug_table"); _chk(idx, torch.int64, "idx")
+    R, D = t.shape
+    for name, ten in (("t", t), ("out", out), ("q_out", q_out), ("idx", idx)):
+        if ten is not None and not ten.is_contiguous():
+            raise ValueError(f"augment_fwd: {name} must be contiguous")
+    if aug_table.shape[1] != D or not aug_table.is_contiguous():
+        raise ValueError("augment_fwd: table must be contiguous [N, D]")
+    check(lib().ttam_augment_fwd(t.data_ptr(), aug_table.data_ptr(), aug_table.shape[0], idx.data_ptr(),
+                                 out.data_ptr(), _ptr(q_out), R, D, _stream()), "augment_fwd")
+    return out, q_out
+
+
+def loss_fwd_bwd(o_u, o_i, *, t_u=None, t_p=None, q_u=None, q_p=None, lambda_u=0.0, lambda_i=0.0, backward=True,
+                 out=None):
+    """o_i = [positives (B rows); negatives (B*N rows, [B,N] row-major)].  Returns (loss[4], do_u, do_i, dq_u, dq_p)."""
+    _chk(o_u, torch.float32, "o_u"); _chk(o_i, torch.float32, "o_i")
+    B, D = o_u.shape
+    N = o_i.shape[0] // B - 1
+    dev = o_u.device
+    mimic = q_u is not None
+    if out is not None:      # (loss[4], do_u, do_i, dq_u, dq_p) provided by the caller
+        loss, do_u, do_i, dq_u, dq_p = out
+    else:
+        loss = torch.empty(4, dtype=torch.float32, device=dev)
+        do_u = torch.empty_like(o_u) if backward else None
+        do_i = torch.empty_like(o_i) if backward else None
+        dq_u = torch.empty_like(o_u) if (backward and mimic) else None
+        dq_p = torch.empty_like(o_u) if (backward and mimic) else None
+    ws = workspace(lib().ttam_loss_workspace_bytes(B), dev, "loss")
+    check(lib().ttam_loss_fwd_bwd(o_u.data_ptr(), o_i.data_ptr(), _ptr(t_u), _ptr(t_p), _ptr(q_u), _ptr(q_p),
+                                  float(lambda_u), float(lambda_i), loss.data_ptr(), _ptr(do_u), _ptr(do_i), _ptr(dq_u),
+                                  _ptr(dq_p), B, N, D, ws.data_ptr(), ws.numel(), _stream()), "loss_fwd_bwd")
+    return loss, do_u, do_i, dq_u, dq_p
+
+
+# ---------------------------------------------------------------------------------------------
+def sort_rows(idx: torch.Tensor, num_rows: int, *, sorted_idx=None, perm=None):
+    """Stable sort of the touched row ids -> (sorted ids, original positions int32)."""
+    _chk(idx, torch.int64, "idx")
+    idx = idx.contiguous().view(-1)
+    R = idx.numel()
+    if sorted_idx is None:
+        sorted_idx = torch.empty_like(idx)
+    if perm is None:
+        perm = torch.empty(R, dtype=torch.int32, device=idx.device)
+    ws = workspace(lib().ttam_sort_workspace_bytes(R), idx.device, "sort")
+    check(lib().ttam_sort_rows(idx.data_ptr(), R, num_rows, sorted_idx.data_ptr(), perm.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "sort_rows")
+    return sorted_idx, perm
+
+
+def unique_rows(sorted_idx: torch.Tensor) -> torch.Tensor:
+    R = sorted_idx.numel()
+    out = torch.empty_like(sorted_idx)
+    n = torch.zeros(1, dtype=torch.int64, device=sorted_idx.device)
+    ws = workspace(lib().ttam_sort_workspace_bytes(R), sorted_idx.device, "sort")
+    check(lib().ttam_unique_rows(sorted_idx.data_ptr(), R, out.data_ptr(), n.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "unique_rows")
+    return out[: int(n.item())]
+
+
+def _grad_src(grad_a, grad_b):
+    ap, lda = _rows2d(grad_a, "grad_a")
+    n_a = grad_a.shape[0]
+    if grad_b is None:
+        return ap, lda, n_a, None, 0
+    bp, ldb = _rows2d(grad_b, "grad_b")
+    return ap, lda, n_a, bp, ldb
+
+
+def sparse_adam_rows(p, m, v, sorted_idx, perm, grad_a, grad_b=None, *, lr, betas=(0.9, 0.999), eps=1e-8, step=1,
+                     scalars=None, state=None):
+    ap, lda, n_a, bp, ldb = _grad_src(grad_a, grad_b)
+    R = sorted_idx.numel()
+    check(lib().ttam_sparse_adam_rows(p.data_ptr(), m.data_ptr(), v.data_ptr(), p.shape[1], sorted_idx.data_ptr(),
+                                      perm.data_ptr(), R, ap, lda, n_a, bp, ldb, _ptr(scalars), float(lr), float(betas[0]),
+                                      float(betas[1]), float(eps), int(step), _ptr(state), _stream()), "sparse_adam_rows")
+
+
+def lazy_rows(kind, p, m, v, last_step, sorted_idx, perm, grad_a, grad_b=None, *, scalars, lr, weight_decay=0.0,
+              betas=(0.9, 0.999), eps=1e-8, momentum=0.0, step=1, state=None):
+    ap, lda, n_a, bp, ldb = _grad_src(grad_a, grad_b)
+    R = sorted_idx.numel()
+    check(lib().ttam_lazy_rows(OPT[kind], p.data_ptr(), _ptr(m), _ptr(v), last_step.data_ptr(), p.shape[1],
+                               sorted_idx.data_ptr(), perm.data_ptr(), R, ap, lda, n_a, bp, ldb, _ptr(scalars),
+                               float(lr), float(weight_decay), float(betas[0]), float(betas[1]), float(eps),
+                               float(momentum), int(step), _ptr(state), _stream()), "lazy_rows")
+
+
+def lazy_flush(kind, p, m, v, last_step, *, scalars, lr, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8,
+               momentum=0.0, step=1, state=None):
+    check(lib().ttam_lazy_flush(OPT[kind], p.data_ptr(), _ptr(m), _ptr(v), last_step.data_ptr(), p.shape[0], p.shape[1],
+                                _ptr(scalars), float(lr), float(weight_decay), float(betas[0]), float(betas[1]),
+                                float(eps), float(momentum), int(step), _ptr(state), _stream()), "lazy_flush")
+
+
+def dense_step(kind, params, grads, ms, vs, *, lr, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8, momentum=0.0, step=1,
+               scalars=None, state=None):
+    """AdamW / Adam / SGD over lists of small contiguous fp32 tensors, MAX_TENSORS per launch."""
+    n = len(params)
+    for s in range(0, n, _lib.MAX_TENSORS):
+        tl = TensorList()
+        cnt = min(_lib.MAX_TENSORS, n - s)
+        tl.count = cnt
+        for j in range(cnt):
+            p, g = params[s + j], grads[s + j]
+            if not (p.is_contiguous() and g.is_contiguous()):
+                raise ValueError("dense_step needs contiguous tensors")
+            tl.p[j] = p.data_ptr(); tl.g[j] = g.data_ptr()
+            tl.m[j] = _ptr(ms[s + j]) if ms is not None else None
+            tl.v[j] = _ptr(vs[s + j]) if vs is not None else None
+            tl.numel[j] = p.numel()
+        check(lib().ttam_dense_step(OPT[kind], C.byref(tl), _ptr(scalars), float(lr), float(weight_decay), float(betas[0]),
+                                    float(betas[1]), float(eps), float(momentum), int(step), _ptr(state), _stream()), "dense_step")
+
+
+def adam_scalar_table(max_step: int, lr: float, betas=(0.9, 0.999), device="cuda") -> torch.Tensor:
+    """scalars[4t] = lr/(1-b1^t), [4t+1] = sqrt(1-b2^t), [4t+2] = lr*sqrt(1-b2^t)/(1-b1^t) (SparseAdam), [4t+3] = 0;
+    computed in float64 like torch does (Python doubles), stored fp32."""
+    t = torch.arange(0, max_step + 1, dtype=torch.float64)
+    b1, b2 = betas
+    bc1 = 1.0 - torch.pow(torch.tensor(b1, dtype=torch.float64), t)
+    bc2 = 1.0 - torch.pow(torch.tensor(b2, dtype=torch.float64), t)
+    bc1[0] = 1.0
+    tab = torch.stack([lr / bc1, torch.sqrt(bc2), lr * torch.sqrt(bc2) / bc1, torch.zeros_like(bc1)], dim=1).to(torch.float32).contiguous()
+    return tab.view(-1).to(device)
+
+
+# ---------------------------------------------------------------------------------------------
+def topk(q: torch.Tensor, items: torch.Tensor, k: int, *, id_offset: int = 0):
+    """Exact inner-product top-k in canonical (-score,+id) order.  fp32 -> SIMT path; bf16 -> tcgen05 path."""
+    if q.dtype != items.dtype:
+        raise ValueError("q and items must have the same dtype")
+    if not (q.is_cuda and items.is_cuda):
+        raise _lib.TtamError("topk needs CUDA tensors; there is no CPU path")
+    q = q.contiguous(); items = items.contiguous()
+    Q, D = q.shape
+    N = items.shape[0]
+    k_eff = min(k, N)
+    ids = torch.empty((Q, k_eff), dtype=torch.int64, device=q.device)
+    scores = torch.empty((Q, k_eff), dtype=torch.float32, device=q.device)
+    L = lib()
+    if q.dtype == torch.float32:
+        ws = workspace(L.ttam_topk_f32_workspace_bytes(Q, N, D, k_eff), q.device, "topk")
+        check(L.ttam_topk_f32(q.data_ptr(), items.data_ptr(), Q, N, D, k_eff, id_offset, ids.data_ptr(), scores.data_ptr(),
+                              ws.data_ptr(), ws.numel(), _stream()), "topk_f32")
+    elif q.dtype == torch.bfloat16:
+        ws = workspace(L.ttam_topk_bf16_workspace_bytes(Q, N, D, k_eff), q.device, "topk")
+        check(L.ttam_topk_bf16(q.data_ptr(), items.data_ptr(), Q, N, D, k_eff, id_offset, ids.data_ptr(), scores.data_ptr(),
+                               ws.data_ptr(), ws.numel(), _stream()), "topk_bf16")
+    else:
+        raise ValueError(f"unsupported dtype {q.dtype}")
+    return ids, scores
+
+
+def topk_merge(ids: torch.Tensor, scores: torch.Tensor, k_out: int):
+    """ids/scores [Q, parts, K_in] -> best k_out per query under (-score,+id)."""
+    Q, parts, k_in = ids.shape
+    out_i = torch.empty((Q, k_out), dtype=torch.int64, device=ids.device)
+    out_s = torch.empty((Q, k_out), dtype=torch.float32, device=ids.device)
+    check(lib().ttam_topk_merge(ids.contiguous().data_ptr(), scores.contiguous().data_ptr(), Q, parts, k_in, k_out,
+                                out_i.data_ptr(), out_s.data_ptr(), _stream()), "topk_merge")
+    return out_i, out_s

@@ -1,0 +1,66 @@
+"""Device-side uniform negative sampler with rejection of known positives (reference samplers.py:11-85).
+
+Same contract as the reference's per-row Python loop — `num_negatives` uniform draws per user from
+[0, num_items), members of `positives[user]` redrawn for at most `max_rounds` rounds — but vectorised
+over the batch: the positives are a sorted int64 key array (user * num_items + item) searched with
+`torch.searchsorted`.  Statistical (not bit) parity: the draws come from the device generator.
+"""
+from __future__ import annotations
+
+from typing import Mapping
+
+import torch
+
+
+class PositiveSet:
+    """Sorted (user, item) keys resident on the device."""
+
+    def __init__(self, positives: Mapping[int, set[int]] | None, num_items: int, device) -> None:
+        self.num_items = int(num_items)
+        if positives:
+            keys = [int(u) * self.num_items + int(i) for u, items in positives.items() for i in items]
+            self.keys = torch.tensor(sorted(keys), dtype=torch.int64, device=device)
+        else:
+            self.keys = torch.empty(0, dtype=torch.int64, device=device)
+
+    def contains(self, users: torch.Tensor, items: torch.Tensor) -> torch.Tensor:
+        if self.keys.numel() == 0:
+            return torch.zeros_like(items, dtype=torch.bool)
+        q = users * self.num_items + items
+        pos = torch.searchsorted(self.keys, q).clamp_max(self.keys.numel() - 1)
+        return self.keys[pos] == q
+
+
+_cache: dict = {}
+
+
+def sample_negative_items(users: torch.Tensor, *, num_items: int, positives, num_negatives: int, device,
+                          max_rounds: int = 10, generator=None) -> torch.Tensor:
+    if num_negatives <= 0:
+        raise ValueError("num_negatives must be greater than zero.")
+    if num_items <= 1:
+        raise ValueError("num_items must be greater than one.")
+    pset = positives if isinstance(positives, PositiveSet) else None
+    if pset is None:
+        key = (id(positives), int(num_items), str(device))
+        pset = _cache.get(key)
+        if pset is None:
+            pset = PositiveSet(positives, num_items, device)
+            _cache.clear()
+            _cache[key] = pset
+    users = users.to(device)
+    B = users.shape[0]
+    neg = torch.randint(0, num_items, (B, num_negatives), device=device, generator=generator)
+    if pset.keys.numel() == 0:
+        return neg
+    u2 = users.view(-1, 1).expand(B, num_negatives)
+    bad = pset.contains(u2, neg)
+    attempts = 0
+    while bool(bad.any()):               # one host sync per round; the common case leaves after the first check
+        redraw = torch.randint(0, num_items, (B, num_negatives), device=device, generator=generator)
+        neg = torch.where(bad, redraw, neg)
+        bad = pset.contains(u2, neg)
+        attempts += 1
+        if attempts > max_rounds:
+            raise RuntimeError("Exceeded resampling attempts while drawing negatives.")
+    return neg
