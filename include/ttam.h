@@ -145,6 +145,8 @@ int ttam_loss_fwd_bwd(const float* o_u, const float* o_i, const float* t_u, cons
  *   Every row-wise update takes `step` by value and, optionally, `state_dev`: when non-null the step is
  *   read from the device (state_dev->step) and the scalars from the table, which makes the launch
  *   replayable inside a CUDA graph.
+ *   ttam_lazy_catchup     : replay the touched rows up to step-1 at the HEAD of step `step`, so that the forward
+ *                           gather of that step reads what the dense optimiser would have left there.
  *   ttam_lazy_flush       : bring rows [0,num_rows) up to `step` (before any full-table read).
  * ttam_unique_rows: the sorted set of touched rows (what SparseAdam updates), n_unique on the device. */
 int64_t ttam_sort_workspace_bytes(int64_t R);
@@ -161,6 +163,11 @@ int ttam_lazy_rows(int kind, float* p, float* m, float* v, int32_t* last_step, i
                    int64_t ld_a, int64_t n_a, const float* grad_b, int64_t ld_b, const float* scalars,
                    double lr, double weight_decay, double beta1, double beta2, double eps, double momentum,
                    int64_t step, const ttam_step_state* state_dev, void* stream);
+/* bring the unique rows of sorted_idx up to step-1 BEFORE the forward pass of step `step` reads them */
+int ttam_lazy_catchup(int kind, float* p, float* m, float* v, int32_t* last_step, int64_t D,
+                      const int64_t* sorted_idx, int64_t R, const float* scalars, double lr, double weight_decay,
+                      double beta1, double beta2, double eps, double momentum, int64_t step,
+                      const ttam_step_state* state_dev, void* stream);
 int ttam_lazy_flush(int kind, float* p, float* m, float* v, int32_t* last_step, int64_t num_rows, int64_t D,
                     const float* scalars, double lr, double weight_decay, double beta1, double beta2, double eps,
                     double momentum, int64_t step, const ttam_step_state* state_dev, void* stream);

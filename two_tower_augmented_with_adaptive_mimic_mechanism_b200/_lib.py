@@ -69,7 +69,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, _sources()))
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(LIB_PATH), *map(str, objs), "-lcuda"]
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(LIB_PATH), *map(str, objs)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
@@ -106,6 +106,7 @@ SIGNATURES = {
     "ttam_sparse_adam_rows": (C.c_int, [_p, _p, _p, _i64, _p, _p, _i64, _p, _i64, _i64, _p, _i64, _p, _d, _d, _d, _d, _i64, _p, _p]),
     "ttam_lazy_rows": (C.c_int, [_i32, _p, _p, _p, _p, _i64, _p, _p, _i64, _p, _i64, _i64, _p, _i64, _p,
                                  _d, _d, _d, _d, _d, _d, _i64, _p, _p]),
+    "ttam_lazy_catchup": (C.c_int, [_i32, _p, _p, _p, _p, _i64, _p, _i64, _p, _d, _d, _d, _d, _d, _d, _i64, _p, _p]),
     "ttam_lazy_flush": (C.c_int, [_i32, _p, _p, _p, _p, _i64, _i64, _p, _d, _d, _d, _d, _d, _d, _i64, _p, _p]),
     "ttam_dense_step": (C.c_int, [_i32, C.POINTER(TensorList), _p, _d, _d, _d, _d, _d, _d, _i64, _p, _p]),
     "ttam_topk_f32_workspace_bytes": (C.c_int64, [_i64, _i64, _i64, _i64]),

@@ -243,6 +243,61 @@ __global__ void __launch_bounds__(256) lazy_rows_kernel(float* __restrict__ P, f
   if (lane == 0) last_step[row] = step;
 }
 
+// Bring the unique rows of `sorted` up to step-1 (zero-gradient replay) so that the forward pass of step `step`
+// reads current values; the row-wise update at the end of the step then finds nothing left to replay.
+template <int KIND, bool VEC>
+__global__ void __launch_bounds__(256) lazy_catchup_kernel(float* __restrict__ P, float* __restrict__ Mo,
+                                                           float* __restrict__ Vo, int32_t* __restrict__ last_step, int D,
+                                                           const int64_t* __restrict__ sorted, int64_t R,
+                                                           const float* __restrict__ scalars, AdamScalars s, int step,
+                                                           const ttam_step_state* __restrict__ st) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= R) return;
+  const int64_t row = sorted[i];
+  if (i > 0 && sorted[i - 1] == row) return;
+  if (st) step = st->step;
+  const int t_prev = last_step[row];
+  if (t_prev >= step - 1) return;
+  const bool has_v = KIND != TTAM_OPT_SGD;
+  const bool has_m = KIND != TTAM_OPT_SGD || s.momentum != 0.f;
+  constexpr int W = VEC ? 128 : 32;
+  constexpr int NE = VEC ? 4 : 1;
+  for (int c0 = 0; c0 < D; c0 += W) {
+    const int col = c0 + (VEC ? lane * 4 : lane);
+    if (col >= D) continue;
+    const int64_t off = row * (int64_t)D + col;
+    float pp[NE], mm[NE], vv[NE];
+    if (VEC) {
+      float4 p4 = ld_f4(P + off);
+      float4 m4 = has_m ? ld_f4(Mo + off) : make_float4(0, 0, 0, 0);
+      float4 v4 = has_v ? ld_f4(Vo + off) : make_float4(0, 0, 0, 0);
+      pp[0] = p4.x; mm[0] = m4.x; vv[0] = v4.x;
+      if (NE == 4) {
+        pp[1 % NE] = p4.y; pp[2 % NE] = p4.z; pp[3 % NE] = p4.w;
+        mm[1 % NE] = m4.y; mm[2 % NE] = m4.z; mm[3 % NE] = m4.w;
+        vv[1 % NE] = v4.y; vv[2 % NE] = v4.z; vv[3 % NE] = v4.w;
+      }
+    } else {
+      pp[0] = P[off];
+      mm[0] = has_m ? Mo[off] : 0.f;
+      vv[0] = has_v ? Vo[off] : 0.f;
+    }
+    replay<KIND, NE>(pp, mm, vv, t_prev, step - 1, scalars, s);
+    if (VEC) {
+      st_f4(P + off, make_float4(pp[0], pp[1 % NE], pp[2 % NE], pp[3 % NE]));
+      if (has_m) st_f4(Mo + off, make_float4(mm[0], mm[1 % NE], mm[2 % NE], mm[3 % NE]));
+      if (has_v) st_f4(Vo + off, make_float4(vv[0], vv[1 % NE], vv[2 % NE], vv[3 % NE]));
+    } else {
+      P[off] = pp[0];
+      if (has_m) Mo[off] = mm[0];
+      if (has_v) Vo[off] = vv[0];
+    }
+  }
+  __syncwarp();
+  if (lane == 0) last_step[row] = step - 1;
+}
+
 template <int KIND, bool VEC>
 __global__ void __launch_bounds__(256) lazy_flush_kernel(float* __restrict__ P, float* __restrict__ Mo,
                                                          float* __restrict__ Vo, int32_t* __restrict__ last_step,
@@ -426,6 +481,27 @@ extern "C" int ttam_lazy_rows(int kind, float* p, float* m, float* v, int32_t* l
   cudaStream_t st = (cudaStream_t)stream;
 #define CALL(K, V) lazy_rows_kernel<K, V><<<blocks, 256, 0, st>>>(p, m, v, last_step, (int)D, sorted_idx, perm, R, gs, scalars, s, (int)step, state_dev)
   if (vec_ok(D, p, m, v, grad_a, ld_a, grad_b, ld_b)) TTAM_DISPATCH_KIND(kind, true, CALL);
+  else TTAM_DISPATCH_KIND(kind, false, CALL);
+#undef CALL
+  TTAM_LAUNCH_CHECK();
+  return TTAM_OK;
+}
+
+extern "C" int ttam_lazy_catchup(int kind, float* p, float* m, float* v, int32_t* last_step, int64_t D,
+                                 const int64_t* sorted_idx, int64_t R, const float* scalars, double lr,
+                                 double weight_decay, double beta1, double beta2, double eps, double momentum,
+                                 int64_t step, const ttam_step_state* state_dev, void* stream) {
+  TTAM_CHECK_ARG(kind >= TTAM_OPT_ADAMW && kind <= TTAM_OPT_SGD, "lazy_catchup: unknown optimiser kind %d", kind);
+  if (R == 0) return TTAM_OK;
+  TTAM_CHECK_ARG(p && last_step && sorted_idx, "lazy_catchup: null pointer");
+  TTAM_CHECK_ARG(kind == TTAM_OPT_SGD || (m && v && scalars), "lazy_catchup: Adam needs m, v and the scalar table");
+  TTAM_CHECK_ARG(kind != TTAM_OPT_SGD || momentum == 0.0 || m, "lazy_catchup: SGD momentum needs the buffer m");
+  TTAM_CHECK_ARG(D > 0 && step >= 1 && step < (1ll << 30), "lazy_catchup: bad argument");
+  AdamScalars s = make_scalars(lr, weight_decay, beta1, beta2, eps, momentum);
+  const int blocks = (int)ceil_div(R * 32, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+#define CALL(K, V) lazy_catchup_kernel<K, V><<<blocks, 256, 0, st>>>(p, m, v, last_step, (int)D, sorted_idx, R, scalars, s, (int)step, state_dev)
+  if (vec_ok(D, p, m, v, nullptr, 0, nullptr, 0)) TTAM_DISPATCH_KIND(kind, true, CALL);
   else TTAM_DISPATCH_KIND(kind, false, CALL);
 #undef CALL
   TTAM_LAUNCH_CHECK();

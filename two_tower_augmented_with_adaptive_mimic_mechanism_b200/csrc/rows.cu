@@ -310,9 +310,9 @@ using namespace ttam;
 
 extern "C" int ttam_gather_rows_f32(const float* table, int64_t ld_table, int64_t num_rows, const int64_t* idx,
                                     float* out, int64_t ld_out, int64_t R, int64_t ncols, void* stream) {
-  TTAM_CHECK_ARG(table && idx && out, "gather_rows: null pointer");
   TTAM_CHECK_ARG(R >= 0 && ncols > 0 && ld_table >= ncols && ld_out >= ncols, "gather_rows: bad shape");
-  if (R == 0) return TTAM_OK;
+  if (R == 0) return TTAM_OK;  // an empty batch has no rows to address (its pointers may be null)
+  TTAM_CHECK_ARG(table && idx && out, "gather_rows: null pointer");
   cudaStream_t s = (cudaStream_t)stream;
   bool vec = (ncols % 4 == 0) && (ld_table % 4 == 0) && (ld_out % 4 == 0) && (((uintptr_t)table & 15) == 0) &&
              (((uintptr_t)out & 15) == 0);

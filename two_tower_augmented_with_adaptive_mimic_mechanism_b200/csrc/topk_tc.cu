@@ -1,9 +1,632 @@
-// placeholder until the tcgen05 scoring kernel lands (next commit)
+// Full-corpus inner-product top-K on the 5th-gen tensor cores (sm_100a): TMA-fed tcgen05.mma with the score tile
+// kept in TMEM and a warp-level running-threshold top-K epilogue; the scores never touch HBM.
+// Replaces faiss.IndexFlatIP.search / the chunked torch.topk of the reference evaluation path
+// (reference training.py:330-384, 646-679, 944-972) for bf16 corpora (BASELINE.json configs[2]).
+//
+// Pipeline of ttam_topk_bf16 (all on `stream`, no host synchronisation):
+//   1. max_norm_kernel      max ||item||_2 (for the rounding-error bound used in step 3)
+//   2. score_topk_kernel    persistent, warp-specialised: 1 TMA warp, 1 MMA warp, 8 epilogue warps per CTA.
+//                           Work unit = (block of 256 queries, one of S item ranges).  Per 256-item tile the MMA warp
+//                           issues 2 x (D/16) tcgen05.mma (M=128, N=256, K=16, bf16 -> fp32) into two TMEM
+//                           accumulators; the epilogue warps drain them with tcgen05.ld (thread = query row, two
+//                           warps per row split the columns), compare against the row's running threshold and append
+//                           the rare survivors to a per-(row, column-half) list in global memory, which a
+//                           warp-cooperative bitonic sort compacts to its best 128 whenever it fills up.
+//   3. finalize_kernel      one CTA per query: merge the 2S lists, take everything within 2*delta of the K-th best
+//                           tensor-core score, re-score those candidates in the canonical order (fp32, sequential over
+//                           d, the order oracle/retrieval.py defines), sort by (-score, +id), emit K results.  A query
+//                           whose candidate set cannot be proven complete is put on the `flagged` list.
+//   4. exact_rows_kernel    brute-force canonical scoring for flagged queries only (normally none).
+// delta bounds |tensor-core score - canonical score|: both are fp32 accumulations of exact bf16 products.
 #include "common.cuh"
+#include "sm100.cuh"
+#include <cub/cub.cuh>
+#include <cuda_bf16.h>
+
+namespace ttam {
+namespace tc {
+
+using namespace ttam::sm100;
+
+constexpr int kBM = 128;       // queries per A tile (UMMA M)
+constexpr int kATiles = 2;     // A tiles resident per CTA: 256 queries per work unit
+constexpr int kQBlock = kBM * kATiles;
+constexpr int kBN = 256;       // items per B tile (UMMA N)
+constexpr int kBoxK = 64;      // bf16 per 128-byte swizzled smem row
+constexpr int kCap = 256;      // working list capacity per (query row, column half)
+constexpr int kKeep = 128;     // entries kept by a compaction (>= K)
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 32 * (2 + kEpiWarps);
+constexpr int kMaxSplits = 16;
+constexpr int kMaxCand = 512;  // candidates re-scored per query in the finalize kernel
+
+constexpr uint32_t kABoxBytes = kBM * 128;   // 16 KB: 128 rows x 128 B
+constexpr uint32_t kBBoxBytes = kBN * 128;   // 32 KB
+
+template <int KBOX>
+struct Cfg {
+  static constexpr int kStages = KBOX == 1 ? 4 : 2;
+  static constexpr uint32_t kABytes = kATiles * KBOX * kABoxBytes;
+  static constexpr uint32_t kBStage = KBOX * kBBoxBytes;
+  static constexpr uint32_t kSmem = kABytes + kStages * kBStage + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+// larger key == better candidate: (score descending, id ascending)
+__device__ __forceinline__ uint32_t ordered_bits(float s) {
+  if (s == 0.f) s = 0.f;  // -0.0 ties with +0.0
+  const uint32_t u = __float_as_uint(s);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(uint32_t o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
+}
+__device__ __forceinline__ uint64_t cand_key(float s, uint32_t id) {
+  return ((uint64_t)ordered_bits(s) << 32) | (uint64_t)(0xFFFFFFFFu - id);
+}
+__device__ __forceinline__ float key_score(uint64_t k) { return ordered_to_float((uint32_t)(k >> 32)); }
+__device__ __forceinline__ uint32_t key_id(uint64_t k) { return 0xFFFFFFFFu - (uint32_t)k; }
+
+// ---- warp-cooperative bitonic sort of 256 keys, descending; element e = lane*8 + j --------------------------------
+__device__ __forceinline__ void warp_sort256_desc(uint64_t (&k)[8], int lane) {
+#pragma unroll
+  for (int size = 2; size <= 256; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride >= 8) {
+        const int lstride = stride >> 3;
+        const bool lower = (lane & lstride) == 0;
+        const bool desc = ((lane * 8) & size) == 0;
+        const bool take_max = lower == desc;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint64_t o = __shfl_xor_sync(0xffffffffu, k[j], lstride);
+          const uint64_t mx = k[j] > o ? k[j] : o, mn = k[j] > o ? o : k[j];
+          k[j] = take_max ? mx : mn;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int pj = j ^ stride;
+          if (pj > j) {
+            const bool desc = ((lane * 8 + j) & size) == 0;
+            const uint64_t a = k[j], b = k[pj];
+            const uint64_t mx = a > b ? a : b, mn = a > b ? b : a;
+            k[j] = desc ? mx : mn;
+            k[pj] = desc ? mn : mx;
+          }
+        }
+      }
+    }
+  }
+}
+
+// Compact the list of the row owned by lane `r` to its best kKeep entries (all 32 lanes cooperate).
+// Returns, to lane r only, the new count and threshold through the references.
+__device__ __forceinline__ void compact_row(int r, int lane, uint64_t* my_buf, int& my_cnt, float& my_tau) {
+  const unsigned long long base = __shfl_sync(0xffffffffu, (unsigned long long)my_buf, r);
+  const int n = __shfl_sync(0xffffffffu, my_cnt, r);
+  uint64_t* buf = reinterpret_cast<uint64_t*>(base);
+  __syncwarp();  // lane r's appends are visible to the whole warp
+  uint64_t k[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int e = j * 32 + lane;  // coalesced read; the order of the input does not matter
+    k[j] = e < n ? buf[e] : 0ull;
+  }
+  warp_sort256_desc(k, lane);
+  __syncwarp();
+  if (lane < kKeep / 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) buf[lane * 8 + j] = k[j];
+  }
+  const uint64_t kth = __shfl_sync(0xffffffffu, k[7], kKeep / 8 - 1);  // element kKeep-1
+  __syncwarp();
+  if (lane == r && n >= kKeep) {
+    my_cnt = kKeep;
+    my_tau = key_score(kth);  // everything dropped scored <= this; later entries must beat it strictly
+  }
+}
+
+struct MainParams {
+  int64_t Q, N;
+  int D, S;
+  int qblocks, tiles_total, tiles_per_split;
+  uint64_t* lists;  // [Q][S][2][kCap]
+  int32_t* cnts;    // [Q][S][2]
+  float* taus;      // [Q][S][2]
+};
+
+template <int KBOX>
+__global__ void __launch_bounds__(kThreads, 1)
+score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_items, MainParams p) {
+  using C = Cfg<KBOX>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + C::kStages * C::kBStage);
+  uint64_t* a_full = bars + 0;
+  uint64_t* a_empty = bars + 1;
+  uint64_t* acc_full = bars + 2;    // [2]
+  uint64_t* acc_empty = bars + 4;   // [2]
+  uint64_t* b_full = bars + 6;      // [kStages]
+  uint64_t* b_empty = bars + 6 + C::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 2 * C::kStages);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q);
+    tma_prefetch_desc(&tmap_items);
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(acc_full + i, 1);
+      mbar_init(acc_empty + i, kEpiWarps);
+    }
+    for (int i = 0; i < C::kStages; ++i) {
+      mbar_init(b_full + i, 1);
+      mbar_init(b_empty + i, 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int units = p.qblocks * p.S;
+  const int ksteps = p.D / 16;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0, un = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x, ++un) {
+        const int qb = u % p.qblocks, s = u / p.qblocks;
+        mbar_wait(a_empty, (un & 1) ^ 1);
+        mbar_expect_tx(a_full, C::kABytes);
+        for (int a = 0; a < kATiles; ++a)
+          for (int kb = 0; kb < KBOX; ++kb)
+            tma_load_2d(smem_a + (a * KBOX + kb) * kABoxBytes, &tmap_q, a_full, kb * kBoxK, qb * kQBlock + a * kBM);
+        const int t0 = s * p.tiles_per_split;
+        const int t1 = min(p.tiles_total, t0 + p.tiles_per_split);
+        for (int t = t0; t < t1; ++t, ++it) {
+          const int stage = it % C::kStages;
+          mbar_wait(b_empty + stage, ((it / C::kStages) & 1) ^ 1);
+          mbar_expect_tx(b_full + stage, C::kBStage);
+          for (int kb = 0; kb < KBOX; ++kb)
+            tma_load_2d(smem_b + stage * C::kBStage + kb * kBBoxBytes, &tmap_items, b_full + stage, kb * kBoxK, t * kBN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(1 /*bf16*/, kBM, kBN);
+      uint32_t it = 0, un = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x, ++un) {
+        const int s = u / p.qblocks;
+        const int t0 = s * p.tiles_per_split;
+        const int t1 = min(p.tiles_total, t0 + p.tiles_per_split);
+        mbar_wait(a_full, un & 1);
+        for (int t = t0; t < t1; ++t, ++it) {
+          const int stage = it % C::kStages;
+          mbar_wait(b_full + stage, (it / C::kStages) & 1);
+          for (int a = 0; a < kATiles; ++a) {
+            mbar_wait(acc_empty + a, (it & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(a * kBN);
+            for (int k = 0; k < ksteps; ++k) {
+              const uint32_t a_addr = smem_u32(smem_a + (a * KBOX + (k >> 2)) * kABoxBytes) + (uint32_t)(k & 3) * 32u;
+              const uint32_t b_addr = smem_u32(smem_b + stage * C::kBStage + (k >> 2) * kBBoxBytes) + (uint32_t)(k & 3) * 32u;
+              umma_f16(d_tmem, make_kmajor_desc<128>(a_addr), make_kmajor_desc<128>(b_addr), idesc, k > 0 ? 1u : 0u);
+            }
+            umma_commit(acc_full + a);
+          }
+          umma_commit(b_empty + stage);
+        }
+        umma_commit(a_empty);  // all MMAs of this unit have read the query tiles
+      }
+    }
+  } else {
+    // ===================== epilogue: 8 warps, thread = query row, two warps per row split the columns ==========
+    const int ew = warp - 2;
+    const int quad = warp & 3;   // TMEM lanes 32*quad .. +31 are the only ones this warp may read
+    const int half = ew >> 2;    // which 128 of the 256 columns
+    const int row_in_tile = quad * 32 + lane;
+    uint32_t it = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const int qb = u % p.qblocks, s = u / p.qblocks;
+      const int t0 = s * p.tiles_per_split;
+      const int t1 = min(p.tiles_total, t0 + p.tiles_per_split);
+      float tau[kATiles];
+      int cnt[kATiles];
+      uint64_t* buf[kATiles];
+      int64_t qrow[kATiles];
+#pragma unroll
+      for (int a = 0; a < kATiles; ++a) {
+        qrow[a] = (int64_t)qb * kQBlock + a * kBM + row_in_tile;
+        const bool valid = qrow[a] < p.Q;
+        tau[a] = valid ? -INFINITY : INFINITY;  // rows past the end never collect anything
+        cnt[a] = 0;
+        const int64_t slot = ((valid ? qrow[a] : 0) * p.S + s) * 2 + half;
+        buf[a] = p.lists + slot * kCap;
+      }
+      for (int t = t0; t < t1; ++t, ++it) {
+#pragma unroll
+        for (int a = 0; a < kATiles; ++a) {
+          mbar_wait(acc_full + a, it & 1);
+          tc_fence_after();
+#pragma unroll 1
+          for (int ch = 0; ch < 4; ++ch) {
+            unsigned need = __ballot_sync(0xffffffffu, cnt[a] > kCap - 32);
+            while (need) {
+              const int r = __ffs(need) - 1;
+              need &= need - 1;
+              compact_row(r, lane, buf[a], cnt[a], tau[a]);
+            }
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * kBN + half * 128 + ch * 32);
+            tmem_ld_32x32(taddr, v);
+            float m = __uint_as_float(v[0]);
+#pragma unroll
+            for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
+            if (m > tau[a]) {
+              const uint32_t id0 = (uint32_t)t * kBN + (uint32_t)(half * 128 + ch * 32);
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const float sc = __uint_as_float(v[i]);
+                if (sc > tau[a] && (int64_t)(id0 + i) < p.N) {
+                  buf[a][cnt[a]] = cand_key(sc, id0 + i);
+                  ++cnt[a];
+                }
+              }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty + a);
+        }
+      }
+      // ---- end of unit: leave at most kKeep entries per list, publish count and threshold
+#pragma unroll
+      for (int a = 0; a < kATiles; ++a) {
+        unsigned need = __ballot_sync(0xffffffffu, cnt[a] > kKeep);
+        while (need) {
+          const int r = __ffs(need) - 1;
+          need &= need - 1;
+          compact_row(r, lane, buf[a], cnt[a], tau[a]);
+        }
+        if (qrow[a] < p.Q) {
+          const int64_t slot = (qrow[a] * p.S + s) * 2 + half;
+          p.cnts[slot] = cnt[a];
+          p.taus[slot] = tau[a];
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- max row norm of the corpus -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) max_norm_kernel(const __nv_bfloat16* __restrict__ items, int64_t N, int D,
+                                                       uint32_t* __restrict__ out_bits) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float best = 0.f;
+  for (int64_t r = warp0; r < N; r += nwarps) {
+    float s = 0.f;
+    for (int d = lane; d < D; d += 32) {
+      const float x = __bfloat162float(items[r * D + d]);
+      s = fmaf(x, x, s);
+    }
+    s = warp_sum(s);
+    best = fmaxf(best, s);
+  }
+  if (lane == 0) atomicMax(out_bits, __float_as_uint(sqrtf(best)));  // non-negative floats order like their bits
+}
+
+// ---- canonical score: fp32, products rounded to fp32 (exact for bf16 inputs), accumulated sequentially over d -------
+__device__ __forceinline__ float canonical_dot(const float* __restrict__ qf, const __nv_bfloat16* __restrict__ row, int D) {
+  float acc = 0.f;
+  for (int d0 = 0; d0 < D; d0 += 8) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(row + d0);
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float lo = __uint_as_float(w[j] << 16), hi = __uint_as_float(w[j] & 0xFFFF0000u);
+      acc = __fadd_rn(acc, __fmul_rn(qf[d0 + 2 * j], lo));
+      acc = __fadd_rn(acc, __fmul_rn(qf[d0 + 2 * j + 1], hi));
+    }
+  }
+  return acc;
+}
+
+// ascending radix-sort key == (descending score, ascending id)
+__device__ __forceinline__ uint64_t final_key(float score, uint32_t id) {
+  return ((uint64_t)(~ordered_bits(score)) << 32) | (uint64_t)id;
+}
+constexpr uint64_t kWorst = ~0ull;
+
+struct FinalParams {
+  const __nv_bfloat16* q;
+  const __nv_bfloat16* items;
+  int64_t Q, N, id_offset;
+  int D, S, K;
+  const uint64_t* lists;
+  const int32_t* cnts;
+  const float* taus;
+  const uint32_t* max_norm_bits;
+  int64_t* out_ids;
+  float* out_scores;
+  int32_t* flagged;      // [Q]
+  int32_t* n_flagged;    // [1]
+};
+
+__global__ void __launch_bounds__(256) finalize_kernel(FinalParams p) {
+  using SortA = cub::BlockRadixSort<uint64_t, 256, 16>;
+  using SortB = cub::BlockRadixSort<uint64_t, 256, 2>;
+  __shared__ union {
+    typename SortA::TempStorage a;
+    typename SortB::TempStorage b;
+  } temp;
+  __shared__ float qf[128];
+  __shared__ uint32_t cand[kMaxCand];
+  __shared__ float s_tk, s_qnorm2, s_tq;
+  __shared__ int s_total, s_P;
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int L = 2 * p.S;
+  if (tid < p.D) qf[tid] = __bfloat162float(p.q[(int64_t)q * p.D + tid]);
+  if (tid == 0) {
+    int tot = 0;
+    float tq = -INFINITY;
+    for (int l = 0; l < L; ++l) {
+      tot += p.cnts[(int64_t)q * L + l];
+      tq = fmaxf(tq, p.taus[(int64_t)q * L + l]);
+    }
+    s_total = tot;
+    s_tq = tq;
+    s_P = 0;
+    s_tk = -INFINITY;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float n2 = 0.f;
+    for (int d = 0; d < p.D; ++d) n2 = fmaf(qf[d], qf[d], n2);
+    s_qnorm2 = n2;
+  }
+  uint64_t keys[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int slot = tid * 16 + i;
+    const int l = slot / kKeep, pos = slot % kKeep;
+    uint64_t k = kWorst;
+    if (l < L && pos < p.cnts[(int64_t)q * L + l]) k = ~p.lists[((int64_t)q * L + l) * kCap + pos];
+    keys[i] = k;
+  }
+  SortA(temp.a).Sort(keys);  // ascending in ~key: best tensor-core score first
+  __syncthreads();
+  const int total = s_total;
+  const int kth = min(p.K, total) - 1;
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    if (tid * 16 + i == kth) s_tk = key_score(~keys[i]);
+  __syncthreads();
+  // |tc - canonical| <= delta: both are fp32 accumulations of D exact products bounded by |q||item|
+  const float max_norm = __uint_as_float(*p.max_norm_bits);
+  const float delta = 4.f * (float)p.D * 5.9604645e-8f * sqrtf(s_qnorm2) * max_norm;
+  const float thr = s_tk - 2.f * delta;
+  int mine = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    if (keys[i] != kWorst && key_score(~keys[i]) >= thr) ++mine;
+  if (mine) atomicAdd(&s_P, mine);
+  __syncthreads();
+  int P = s_P;
+  bool flag = false;
+  if (P > kMaxCand) {
+    P = kMaxCand;
+    flag = true;  // too many near-ties to re-score here
+  }
+  if (s_tq >= thr) flag = true;  // something a list dropped (score <= s_tq) could still belong to the top K
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int rank = tid * 16 + i;
+    if (rank < P) cand[rank] = key_id(~keys[i]);
+  }
+  __syncthreads();
+  uint64_t fk[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = tid * 2 + i;
+    fk[i] = kWorst;
+    if (c < P) {
+      const uint32_t id = cand[c];
+      fk[i] = final_key(canonical_dot(qf, p.items + (int64_t)id * p.D, p.D), id);
+    }
+  }
+  SortB(temp.b).Sort(fk);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int rank = tid * 2 + i;
+    if (rank < p.K) {
+      const bool valid = fk[i] != kWorst;
+      p.out_ids[(int64_t)q * p.K + rank] = valid ? (int64_t)(uint32_t)fk[i] + p.id_offset : -1;
+      p.out_scores[(int64_t)q * p.K + rank] = valid ? ordered_to_float(~(uint32_t)(fk[i] >> 32)) : -INFINITY;
+    }
+  }
+  if (flag && tid == 0) p.flagged[atomicAdd(p.n_flagged, 1)] = q;
+}
+
+// ---- exact brute force for flagged queries (normally zero of them) ---------------------------------------------------
+constexpr int kExactItems = 20;
+constexpr int kExactChunk = 4096;
+
+__global__ void __launch_bounds__(256) exact_rows_kernel(FinalParams p) {
+  using Sort = cub::BlockRadixSort<uint64_t, 256, kExactItems>;
+  __shared__ typename Sort::TempStorage temp;
+  __shared__ float qf[128];
+  const int tid = threadIdx.x;
+  const int nf = *p.n_flagged;
+  for (int f = blockIdx.x; f < nf; f += gridDim.x) {
+    const int q = p.flagged[f];
+    __syncthreads();
+    if (tid < p.D) qf[tid] = __bfloat162float(p.q[(int64_t)q * p.D + tid]);
+    __syncthreads();
+    uint64_t keys[kExactItems];
+#pragma unroll
+    for (int i = 0; i < kExactItems; ++i) keys[i] = kWorst;
+    // blocked arrangement after each sort: the running top K lives in slots [0, K) = threads 0 .. ceil(K/20)
+    for (int64_t c0 = 0; c0 < p.N; c0 += kExactChunk) {
+#pragma unroll
+      for (int i = 0; i < kExactItems; ++i) {
+        const int slot = tid * kExactItems + i;
+        if (slot >= p.K) {
+          const int64_t id = c0 + (slot - p.K);
+          keys[i] = (slot - p.K < kExactChunk && id < p.N) ? final_key(canonical_dot(qf, p.items + id * p.D, p.D), (uint32_t)id) : kWorst;
+        }
+      }
+      __syncthreads();
+      Sort(temp).Sort(keys);
+    }
+#pragma unroll
+    for (int i = 0; i < kExactItems; ++i) {
+      const int slot = tid * kExactItems + i;
+      if (slot < p.K) {
+        const bool valid = keys[i] != kWorst;
+        p.out_ids[(int64_t)q * p.K + slot] = valid ? (int64_t)(uint32_t)keys[i] + p.id_offset : -1;
+        p.out_scores[(int64_t)q * p.K + slot] = valid ? ordered_to_float(~(uint32_t)(keys[i] >> 32)) : -INFINITY;
+      }
+    }
+  }
+}
+
+// ---- host ---------------------------------------------------------------------------------------------------------------
+static int choose_splits(int64_t Q, int64_t N) {
+  const int64_t qblocks = ceil_div(Q, kQBlock), tiles = ceil_div(N, kBN);
+  const int64_t sms = num_sms();
+  int best = 1;
+  double best_cost = 1e300;
+  for (int s = 1; s <= kMaxSplits; ++s) {
+    if (s > tiles) break;
+    const int64_t units = qblocks * s;
+    const int64_t waves = ceil_div(units, sms);
+    // fixed cost per unit ~ 48 tiles: query-tile load, threshold warm-up and the final list compaction
+    const double cost = (double)waves * ((double)ceil_div(tiles, s) + 48.0);
+    if (cost < best_cost * 0.98) {
+      best_cost = cost;
+      best = s;
+    }
+  }
+  return best;
+}
+
+struct Workspace {
+  uint64_t* lists;
+  int32_t* cnts;
+  float* taus;
+  uint32_t* max_norm_bits;
+  int32_t* n_flagged;
+  int32_t* flagged;
+  int64_t bytes;
+};
+static Workspace carve(void* base, int64_t Q, int S) {
+  Workspace w{};
+  int64_t off = 0;
+  auto take = [&](int64_t n) {
+    void* ptr = base ? (char*)base + off : nullptr;
+    off += align_up(n, 256);
+    return ptr;
+  };
+  const int64_t L = Q * S * 2;
+  w.lists = (uint64_t*)take(L * kCap * 8);
+  w.cnts = (int32_t*)take(L * 4);
+  w.taus = (float*)take(L * 4);
+  w.max_norm_bits = (uint32_t*)take(256);
+  w.n_flagged = (int32_t*)((char*)w.max_norm_bits + (base ? 128 : 0));
+  w.flagged = (int32_t*)take(Q * 4 + 4);
+  w.bytes = off + 256;
+  return w;
+}
+
+}  // namespace tc
+}  // namespace ttam
+
 using namespace ttam;
-extern "C" int64_t ttam_topk_bf16_workspace_bytes(int64_t, int64_t, int64_t, int64_t) { return 256; }
-extern "C" int ttam_topk_bf16(const uint16_t*, const uint16_t*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t*,
-                              float*, void*, int64_t, void*) {
-  set_error("topk_bf16: not built yet");
-  return TTAM_EUNSUPPORTED;
+using namespace ttam::tc;
+
+extern "C" int64_t ttam_topk_bf16_workspace_bytes(int64_t Q, int64_t N, int64_t D, int64_t K) {
+  (void)D; (void)K;
+  if (Q <= 0 || N <= 0) return 256;
+  return carve(nullptr, Q, choose_splits(Q, N)).bytes;
+}
+
+extern "C" int ttam_topk_bf16(const uint16_t* q, const uint16_t* items, int64_t Q, int64_t N, int64_t D, int64_t K,
+                              int64_t id_offset, int64_t* out_ids, float* out_scores, void* workspace,
+                              int64_t workspace_bytes, void* stream) {
+  TTAM_CHECK_ARG(Q >= 0 && N > 0 && D > 0 && K > 0, "topk_bf16: bad shape");
+  if (Q == 0) return TTAM_OK;
+  TTAM_CHECK_ARG(q && items && out_ids && out_scores && workspace, "topk_bf16: null pointer");
+  if (D % 16 != 0 || D > 128 || K > kKeep) {
+    set_error("topk_bf16: the tcgen05 path needs D %% 16 == 0, D <= 128 and K <= %d (got D=%lld, K=%lld)", kKeep,
+              (long long)D, (long long)K);
+    return TTAM_EUNSUPPORTED;
+  }
+  TTAM_CHECK_ARG(N < (1ll << 32) - 1 && Q < (1ll << 31), "topk_bf16: corpus too large for 32-bit local ids");
+  TTAM_CHECK_ARG(((uintptr_t)q & 15) == 0 && ((uintptr_t)items & 15) == 0, "topk_bf16: operands must be 16-byte aligned");
+  const int S = choose_splits(Q, N);
+  Workspace w = carve(workspace, Q, S);
+  if (workspace_bytes < w.bytes) {
+    set_error("topk_bf16: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)w.bytes);
+    return TTAM_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int KBOX = D <= 64 ? 1 : 2;
+  CUtensorMap tq, ti;
+  int rc = make_tmap_2d(&tq, q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)Q, (uint64_t)D, (uint64_t)D * 2, kBoxK, kBM,
+                        CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != TTAM_OK) return rc;
+  rc = make_tmap_2d(&ti, items, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)N, (uint64_t)D, (uint64_t)D * 2, kBoxK, kBN,
+                    CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != TTAM_OK) return rc;
+
+  TTAM_CUDA(cudaMemsetAsync(w.max_norm_bits, 0, 256, st));  // max norm and the flagged counter
+  max_norm_kernel<<<num_sms() * 4, 256, 0, st>>>((const __nv_bfloat16*)items, N, (int)D, w.max_norm_bits);
+  TTAM_LAUNCH_CHECK();
+
+  MainParams mp{};
+  mp.Q = Q; mp.N = N; mp.D = (int)D; mp.S = S;
+  mp.qblocks = (int)ceil_div(Q, kQBlock);
+  mp.tiles_total = (int)ceil_div(N, kBN);
+  mp.tiles_per_split = (int)ceil_div(mp.tiles_total, S);
+  mp.lists = w.lists; mp.cnts = w.cnts; mp.taus = w.taus;
+  const int units = mp.qblocks * S;
+  const int grid = units < num_sms() ? units : num_sms();
+  if (KBOX == 1) {
+    TTAM_CUDA(cudaFuncSetAttribute(score_topk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<1>::kSmem));
+    score_topk_kernel<1><<<grid, kThreads, Cfg<1>::kSmem, st>>>(tq, ti, mp);
+  } else {
+    TTAM_CUDA(cudaFuncSetAttribute(score_topk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<2>::kSmem));
+    score_topk_kernel<2><<<grid, kThreads, Cfg<2>::kSmem, st>>>(tq, ti, mp);
+  }
+  TTAM_LAUNCH_CHECK();
+
+  FinalParams fp{};
+  fp.q = (const __nv_bfloat16*)q; fp.items = (const __nv_bfloat16*)items;
+  fp.Q = Q; fp.N = N; fp.id_offset = id_offset; fp.D = (int)D; fp.S = S; fp.K = (int)K;
+  fp.lists = w.lists; fp.cnts = w.cnts; fp.taus = w.taus; fp.max_norm_bits = w.max_norm_bits;
+  fp.out_ids = out_ids; fp.out_scores = out_scores; fp.flagged = w.flagged; fp.n_flagged = w.n_flagged;
+  finalize_kernel<<<(unsigned)Q, 256, 0, st>>>(fp);
+  TTAM_LAUNCH_CHECK();
+  exact_rows_kernel<<<num_sms(), 256, 0, st>>>(fp);
+  TTAM_LAUNCH_CHECK();
+  return TTAM_OK;
 }

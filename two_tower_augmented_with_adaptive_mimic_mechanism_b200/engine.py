@@ -103,27 +103,43 @@ class FusedEngine:
         return t[: shape[0]]
 
     # --------------------------------------------------------------------------------------------
-    def _update_table(self, tab: _Table, idx, tag, grad_a, grad_b=None):
+    def _sort(self, idx, tag, num_rows):
+        """Stable sort of the touched rows of one index set (once per step; shared by every table it addresses)."""
         R = idx.numel()
         sorted_idx = self._misc(f"sorted_{tag}", (R,), torch.int64)
         perm = self._misc(f"perm_{tag}", (R,), torch.int32)
-        key = f"sorted_done_{tag}"
-        if not self._step_flags.get(key):
-            F.sort_rows(idx, tab.weight.shape[0], sorted_idx=sorted_idx, perm=perm)
-            self._step_flags[key] = True
+        F.sort_rows(idx, num_rows, sorted_idx=sorted_idx, perm=perm)
+        return sorted_idx, perm
+
+    def _lazy_kw(self):
+        return dict(scalars=self.scal_dense, lr=self.lr, weight_decay=self.wd, betas=self.dense_betas, eps=self.eps,
+                    momentum=self.momentum, step=self.t, state=self.state)
+
+    def _catchup(self, tab: _Table, sorted_idx):
+        """Lazy tables: replay the zero-gradient steps of the rows this step reads, before the forward reads them."""
+        if tab.mode == "lazy":
+            F.lazy_catchup(self.kind, tab.weight, tab.m, tab.v, tab.last_step, sorted_idx, **self._lazy_kw())
+
+    def _update_table(self, tab: _Table, sort, grad_a, grad_b=None):
+        sorted_idx, perm = sort
         if tab.mode == "sparse_adam":
             F.sparse_adam_rows(tab.weight, tab.m, tab.v, sorted_idx, perm, grad_a, grad_b, lr=self.lr,
                                betas=self.sparse_betas, eps=self.eps, step=self.t, scalars=self.scal_sparse,
                                state=self.state)
         else:
             F.lazy_rows(self.kind, tab.weight, tab.m, tab.v, tab.last_step, sorted_idx, perm, grad_a, grad_b,
-                        scalars=self.scal_dense, lr=self.lr, weight_decay=self.wd, betas=self.dense_betas, eps=self.eps,
-                        momentum=self.momentum, step=self.t, state=self.state)
+                        **self._lazy_kw())
 
     def _step_body(self, users, items, B, N, Xu, Xi):
-        self._step_flags = {}
         launches0 = F.lib().ttam_launch_count()
         F.advance_step(self.state, rng_stride=1 << 36)
+        T = self.tables
+        sort_u = self._sort(users, "u", self.user.table.shape[0])
+        sort_i = self._sort(items, "i", self.item.table.shape[0])
+        for name, srt in (("user_encoder.embedding.weight", sort_u), ("item_encoder.embedding.weight", sort_i),
+                          ("adaptive_mimic.user_augmented.weight", sort_u), ("adaptive_mimic.item_augmented.weight", sort_i)):
+            if name in T:
+                self._catchup(T[name], srt[0])
         cu = tower_forward(self.user, users, Xu, gather=True, train=True, bufs=self.bufs_u, seed=self.seed,
                            rng_base=0, state=self.state, precision=self.precision, want_q=self.mimic)
         ci = tower_forward(self.item, items, Xi, gather=True, train=True, bufs=self.bufs_i, seed=self.seed,
@@ -150,11 +166,11 @@ class FusedEngine:
         de_i = tower_backward(self.item, ci, do_i, grads, bufs=self.bufs_i, state=self.state, precision=self.precision)
         de_u = tower_backward(self.user, cu, do_u, grads, bufs=self.bufs_u, state=self.state, precision=self.precision)
         # ---- row-wise optimisers (no dense table gradient)
-        self._update_table(self.tables["user_encoder.embedding.weight"], users, "u", de_u)
-        self._update_table(self.tables["item_encoder.embedding.weight"], items, "i", de_i)
+        self._update_table(T["user_encoder.embedding.weight"], sort_u, de_u)
+        self._update_table(T["item_encoder.embedding.weight"], sort_i, de_i)
         if self.mimic:
-            self._update_table(self.tables["adaptive_mimic.user_augmented.weight"], users, "u", dq_u)
-            self._update_table(self.tables["adaptive_mimic.item_augmented.weight"], items, "i", dq_p, do_i[B:])
+            self._update_table(T["adaptive_mimic.user_augmented.weight"], sort_u, dq_u)
+            self._update_table(T["adaptive_mimic.item_augmented.weight"], sort_i, dq_p, do_i[B:])
         # ---- dense optimiser on the MLP / gate / projection tensors that received a gradient
         ps, gs, ms, vs = [], [], [], []
         for j, p in enumerate(self.dense):

@@ -264,6 +264,15 @@ def lazy_rows(kind, p, m, v, last_step, sorted_idx, perm, grad_a, grad_b=None, *
                                float(momentum), int(step), _ptr(state), _stream()), "lazy_rows")
 
 
+def lazy_catchup(kind, p, m, v, last_step, sorted_idx, *, scalars, lr, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8,
+                 momentum=0.0, step=1, state=None):
+    """Replay the zero-gradient steps of the rows in sorted_idx up to step-1 (call before the forward of `step`)."""
+    check(lib().ttam_lazy_catchup(OPT[kind], p.data_ptr(), _ptr(m), _ptr(v), last_step.data_ptr(), p.shape[1],
+                                  sorted_idx.data_ptr(), sorted_idx.numel(), _ptr(scalars), float(lr), float(weight_decay),
+                                  float(betas[0]), float(betas[1]), float(eps), float(momentum), int(step), _ptr(state),
+                                  _stream()), "lazy_catchup")
+
+
 def lazy_flush(kind, p, m, v, last_step, *, scalars, lr, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8,
                momentum=0.0, step=1, state=None):
     check(lib().ttam_lazy_flush(OPT[kind], p.data_ptr(), _ptr(m), _ptr(v), last_step.data_ptr(), p.shape[0], p.shape[1],
