@@ -110,3 +110,64 @@ def test_device_sampler_excludes_positives(tt):
     for r, u in enumerate(users.cpu().tolist()):
         assert not (set(neg[r].cpu().tolist()) & positives[u])
     assert int(neg.min()) >= 0 and int(neg.max()) < 10
+
+
+# ---------------------------------------------------------------------------------------------
+# tcgen05 path (bf16 operands): ids AND canonical scores bit-exact against the oracle on the same bf16 values
+# ---------------------------------------------------------------------------------------------
+def _bf16_case(Q, N, D, seed):
+    g = torch.Generator().manual_seed(seed)
+    q = (torch.randn((Q, D), generator=g) * 0.3).bfloat16()
+    items = (torch.randn((N, D), generator=g) * 0.3).bfloat16()
+    return q, items
+
+
+@pytest.mark.parametrize("Q,N,D,K", [(300, 5000, 96, 100), (1, 300, 96, 100), (257, 70001, 96, 100), (64, 4096, 64, 10),
+                                     (130, 9000, 128, 128), (40, 3000, 32, 50), (33, 2000, 16, 100), (512, 200000, 96, 100)])
+def test_topk_bf16_tensor_core_bit_exact(tt, Q, N, D, K):
+    q, items = _bf16_case(Q, N, D, N + D)
+    items[N // 2] = items[N // 3]                     # exact duplicate rows -> exact score ties, broken by id
+    items[N - 1] = items[0]
+    ids, scores = tt.functional.topk(q.cuda(), items.cuda(), K, id_offset=7)
+    ref_s = oracle.canonical_scores(q.float().numpy(), items.float().numpy())
+    ref_i, ref_v = oracle.topk_canonical(ref_s, K)
+    assert np.array_equal(ids.cpu().numpy(), ref_i + 7)
+    assert np.array_equal(scores.cpu().numpy(), ref_v)
+
+
+def test_topk_bf16_degenerate_inputs_take_the_exact_fallback(tt):
+    """All scores tie: the candidate set cannot be proven complete from tensor-core scores, so every query is
+    re-done by the brute-force kernel; the answer is still canonical (ids 0..K-1)."""
+    q = torch.ones(5, 96).bfloat16().cuda()
+    items = torch.ones(3000, 96).bfloat16().cuda()
+    ids, scores = tt.functional.topk(q, items, 20)
+    assert ids.cpu().tolist() == [list(range(20))] * 5
+    assert torch.all(scores == 96.0)
+    # two distinct score levels, many ties inside each
+    items2 = torch.ones(3000, 96)
+    items2[1000:1010] = 2.0
+    ids2, _ = tt.functional.topk(q, items2.bfloat16().cuda(), 20)
+    assert ids2.cpu().tolist() == [list(range(1000, 1010)) + list(range(10))] * 5
+
+
+def test_topk_bf16_full_corpus_agrees_with_fp32_path(tt):
+    """BASELINE config 3 corpus size (2M x 96 bf16): the tensor-core result equals the fp32 SIMT kernel's
+    (canonical arithmetic on the same bf16 values) for a sample of the queries."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    items = (torch.randn((2_000_000, 96), device="cuda", generator=g) * 0.3).bfloat16()
+    q = (torch.randn((4096, 96), device="cuda", generator=g) * 0.3).bfloat16()
+    ids, scores = tt.functional.topk(q, items, 100)
+    sel = torch.arange(0, 4096, 32, device="cuda")
+    ref_i, ref_s = tt.functional.topk(q[sel].float(), items.float(), 100)
+    assert torch.equal(ids[sel], ref_i) and torch.equal(scores[sel], ref_s)
+    assert bool((scores[:, :-1] >= scores[:, 1:]).all())           # sortedness over all 4096 queries
+    assert int(ids.min()) >= 0 and int(ids.max()) < 2_000_000
+
+
+def test_flat_ip_index_bf16(tt):
+    emb = torch.randn(5000, 96, device="cuda")
+    q = torch.randn(10, 96, device="cuda")
+    idx = tt.retrieval.FlatIPIndex(emb, dtype=torch.bfloat16)
+    ids, sc = idx.search(q, 10)
+    ref = oracle.topk_canonical(oracle.canonical_scores(q.bfloat16().float().cpu().numpy(), emb.bfloat16().float().cpu().numpy()), 10)[0]
+    assert np.array_equal(ids.cpu().numpy(), ref)
