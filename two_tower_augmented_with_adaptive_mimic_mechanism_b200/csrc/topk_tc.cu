@@ -7,12 +7,14 @@
 //   1. max_norm_kernel      max ||item||_2 (for the rounding-error bound used in step 3)
 //   2. score_topk_kernel    persistent, warp-specialised: 1 TMA warp, 1 MMA warp, 8 epilogue warps per CTA.
 //                           Work unit = (block of 256 queries, one of S item ranges).  Per 256-item tile the MMA warp
-//                           issues 2 x (D/16) tcgen05.mma (M=128, N=256, K=16, bf16 -> fp32) into two TMEM
-//                           accumulators; the epilogue warps drain them with tcgen05.ld (thread = query row, two
-//                           warps per row split the columns), compare against the row's running threshold and append
-//                           the rare survivors to a per-(row, column-half) list in global memory, which a
-//                           warp-cooperative bitonic sort compacts to its best 128 whenever it fills up.
-//   3. finalize_kernel      one CTA per query: merge the 2S lists, take everything within 2*delta of the K-th best
+//                           issues 4 x (D/16) tcgen05.mma (M=128, N=128, K=16, bf16 -> fp32) into four TMEM
+//                           accumulators [query tile a][item half h] (all 512 TMEM columns); epilogue warpgroup a
+//                           drains accumulators (a, 0) and (a, 1) with tcgen05.ld while the tensor core fills the
+//                           others: thread = query row, it owns that row's running threshold and candidate list.
+//                           A 32-column chunk costs a 3-input-max tree and one compare; the rare survivors are
+//                           appended to the row's list in global memory, which a warp-cooperative bitonic sort
+//                           compacts to its best 128 whenever it fills up (raising the threshold).
+//   3. finalize_kernel      one CTA per query: merge the S lists, take everything within 2*delta of the K-th best
 //                           tensor-core score, re-score those candidates in the canonical order (fp32, sequential over
 //                           d, the order oracle/retrieval.py defines), sort by (-score, +id), emit K results.  A query
 //                           whose candidate set cannot be proven complete is put on the `flagged` list.
@@ -22,6 +24,7 @@
 #include "sm100.cuh"
 #include <cub/cub.cuh>
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 namespace ttam {
 namespace tc {
@@ -31,14 +34,17 @@ using namespace ttam::sm100;
 constexpr int kBM = 128;       // queries per A tile (UMMA M)
 constexpr int kATiles = 2;     // A tiles resident per CTA: 256 queries per work unit
 constexpr int kQBlock = kBM * kATiles;
-constexpr int kBN = 256;       // items per B tile (UMMA N)
+constexpr int kBN = 256;       // items per B tile (one TMA stage)
+constexpr int kHN = 128;       // items per MMA (UMMA N): two halves per B tile, one TMEM accumulator each
 constexpr int kBoxK = 64;      // bf16 per 128-byte swizzled smem row
-constexpr int kCap = 256;      // working list capacity per (query row, column half)
-constexpr int kKeep = 128;     // entries kept by a compaction (>= K)
+constexpr int kCap = 512;      // working list capacity per (query row, item split)
+constexpr int kPerLane = kCap / 32;
+constexpr int kKeep = 128;     // entries a compaction keeps at least (>= K); exactly this many after the final one
+constexpr int kSlack = 32;     // a mid-stream compaction may keep up to kKeep + kSlack (cheaper threshold search)
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 32 * (2 + kEpiWarps);
 constexpr int kMaxSplits = 16;
-constexpr int kMaxCand = 512;  // candidates re-scored per query in the finalize kernel
+constexpr int kMaxCand = 256;  // candidates re-scored per query in the finalize kernel
 
 constexpr uint32_t kABoxBytes = kBM * 128;   // 16 KB: 128 rows x 128 B
 constexpr uint32_t kBBoxBytes = kBN * 128;   // 32 KB
@@ -66,64 +72,89 @@ __device__ __forceinline__ uint64_t cand_key(float s, uint32_t id) {
 __device__ __forceinline__ float key_score(uint64_t k) { return ordered_to_float((uint32_t)(k >> 32)); }
 __device__ __forceinline__ uint32_t key_id(uint64_t k) { return 0xFFFFFFFFu - (uint32_t)k; }
 
-// ---- warp-cooperative bitonic sort of 256 keys, descending; element e = lane*8 + j --------------------------------
-__device__ __forceinline__ void warp_sort256_desc(uint64_t (&k)[8], int lane) {
-#pragma unroll
-  for (int size = 2; size <= 256; size <<= 1) {
-#pragma unroll
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      if (stride >= 8) {
-        const int lstride = stride >> 3;
-        const bool lower = (lane & lstride) == 0;
-        const bool desc = ((lane * 8) & size) == 0;
-        const bool take_max = lower == desc;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint64_t o = __shfl_xor_sync(0xffffffffu, k[j], lstride);
-          const uint64_t mx = k[j] > o ? k[j] : o, mn = k[j] > o ? o : k[j];
-          k[j] = take_max ? mx : mn;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int pj = j ^ stride;
-          if (pj > j) {
-            const bool desc = ((lane * 8 + j) & size) == 0;
-            const uint64_t a = k[j], b = k[pj];
-            const uint64_t mx = a > b ? a : b, mn = a > b ? b : a;
-            k[j] = desc ? mx : mn;
-            k[pj] = desc ? mn : mx;
-          }
-        }
-      }
-    }
-  }
-}
-
-// Compact the list of the row owned by lane `r` to its best kKeep entries (all 32 lanes cooperate).
-// Returns, to lane r only, the new count and threshold through the references.
-__device__ __forceinline__ void compact_row(int r, int lane, uint64_t* my_buf, int& my_cnt, float& my_tau) {
+// ---- list compaction: warp-cooperative threshold selection + in-place filter ------------------------------------------
+// List entries are stored raw, {score bits, item id}, so that an append is one 8-byte store.
+// compact_row finds t* with  kKeep <= #{score >= t*}  by a bitwise binary search over the order-preserving integer image
+// of the scores (one warp reduction per bit, starting below the bits all entries share), keeps the entries >= t*
+// (unordered), and raises the row's threshold so that only scores >= t* are appended from now on.  `exact` (the final
+// compaction of a work unit) searches down to the last bit and truncates ties so that exactly kKeep entries remain.
+// Invariant kept for the finalize kernel: every item of the stream that is NOT in the list scored <= tau.
+__device__ __noinline__ void compact_row(int r, int lane, bool exact, uint2* my_buf, int& my_cnt, float& my_tau) {
   const unsigned long long base = __shfl_sync(0xffffffffu, (unsigned long long)my_buf, r);
   const int n = __shfl_sync(0xffffffffu, my_cnt, r);
-  uint64_t* buf = reinterpret_cast<uint64_t*>(base);
+  uint2* buf = reinterpret_cast<uint2*>(base);
   __syncwarp();  // lane r's appends are visible to the whole warp
-  uint64_t k[8];
+  uint32_t o[kPerLane], id[kPerLane];
+  uint32_t lmax = 0u, lmin = 0xFFFFFFFFu;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int e = j * 32 + lane;  // coalesced read; the order of the input does not matter
-    k[j] = e < n ? buf[e] : 0ull;
+  for (int j = 0; j < kPerLane; ++j) {
+    const int e = j * 32 + lane;
+    o[j] = 0u;  // below every real entry
+    id[j] = 0u;
+    if (e < n) {
+      const uint2 raw = buf[e];
+      o[j] = ordered_bits(__uint_as_float(raw.x));
+      id[j] = raw.y;
+      lmax = max(lmax, o[j]);
+      lmin = min(lmin, o[j]);
+    }
   }
-  warp_sort256_desc(k, lane);
-  __syncwarp();
-  if (lane < kKeep / 8) {
+  const uint32_t omax = __reduce_max_sync(0xffffffffu, lmax);
+  const uint32_t omin = __reduce_min_sync(0xffffffffu, lmin);
+  uint32_t tstar = omin;  // #{o >= omin} = n >= kKeep
+  if (n > kKeep && omax != omin) {
+    const int hb = 31 - __clz(omax ^ omin);
+    uint32_t prefix = omax & ~((2u << hb) - 1u);  // bits shared by all entries
+    for (int bit = hb; bit >= 0; --bit) {
+      const uint32_t cand = prefix | (1u << bit);
+      int c = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) buf[lane * 8 + j] = k[j];
+      for (int j = 0; j < kPerLane; ++j) c += (o[j] >= cand) ? 1 : 0;
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (c >= kKeep) {
+        prefix = cand;
+        if (!exact && c <= kKeep + kSlack) break;
+      }
+    }
+    tstar = prefix;
   }
-  const uint64_t kth = __shfl_sync(0xffffffffu, k[7], kKeep / 8 - 1);  // element kKeep-1
+  // how many are strictly above / tied with t*
+  int c_gt = 0, c_eq = 0;
+#pragma unroll
+  for (int j = 0; j < kPerLane; ++j) {
+    c_gt += (o[j] > tstar) ? 1 : 0;
+    c_eq += (o[j] == tstar) ? 1 : 0;
+  }
+  c_gt = __reduce_add_sync(0xffffffffu, c_gt);
+  c_eq = __reduce_add_sync(0xffffffffu, c_eq);
+  // ties: keep them all when there is room (then scores == t* stay admissible), else only enough to reach kKeep
+  const bool keep_all_ties = !exact && (c_gt + c_eq <= kCap - 4 * 32);
+  const int tie_budget = keep_all_ties ? c_eq : max(0, min(c_eq, kKeep - c_gt));
   __syncwarp();
-  if (lane == r && n >= kKeep) {
-    my_cnt = kKeep;
-    my_tau = key_score(kth);  // everything dropped scored <= this; later entries must beat it strictly
+  const unsigned lt = (1u << lane) - 1u;
+  int total = 0;
+#pragma unroll
+  for (int j = 0; j < kPerLane; ++j) {
+    const bool keep = o[j] > tstar;
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (keep) buf[total + __popc(bal & lt)] = make_uint2(__float_as_uint(ordered_to_float(o[j])), id[j]);
+    total += __popc(bal);
+  }
+  int ties = 0;
+#pragma unroll
+  for (int j = 0; j < kPerLane; ++j) {
+    const bool tie = o[j] == tstar;
+    const unsigned bal = __ballot_sync(0xffffffffu, tie);
+    const int rank = ties + __popc(bal & lt);
+    if (tie && rank < tie_budget) buf[total + rank] = make_uint2(__float_as_uint(ordered_to_float(o[j])), id[j]);
+    ties += __popc(bal);
+  }
+  total += tie_budget;
+  __syncwarp();
+  if (lane == r && n > kKeep) {
+    my_cnt = total;
+    // appended from now on: keep_all_ties -> score >= t*  (tau = the float just below t*), else score > t*
+    my_tau = ordered_to_float(keep_all_ties ? tstar - 1u : tstar);
   }
 }
 
@@ -131,9 +162,10 @@ struct MainParams {
   int64_t Q, N;
   int D, S;
   int qblocks, tiles_total, tiles_per_split;
-  uint64_t* lists;  // [Q][S][2][kCap]
-  int32_t* cnts;    // [Q][S][2]
-  float* taus;      // [Q][S][2]
+  uint2* lists;     // [Q][S][kCap] raw {score bits, id}
+  int32_t* cnts;    // [Q][S]
+  float* taus;      // [Q][S]
+  int debug;        // timing experiments only (TTAM_TOPK_DEBUG): 1 = epilogue drains nothing, 2 = no compaction
 };
 
 template <int KBOX>
@@ -147,11 +179,11 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + C::kStages * C::kBStage);
   uint64_t* a_full = bars + 0;
   uint64_t* a_empty = bars + 1;
-  uint64_t* acc_full = bars + 2;    // [2]
-  uint64_t* acc_empty = bars + 4;   // [2]
-  uint64_t* b_full = bars + 6;      // [kStages]
-  uint64_t* b_empty = bars + 6 + C::kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6 + 2 * C::kStages);
+  uint64_t* acc_full = bars + 2;    // [4]: accumulator (a, h) at index a*2+h
+  uint64_t* acc_empty = bars + 6;   // [4]
+  uint64_t* b_full = bars + 10;     // [kStages]
+  uint64_t* b_empty = bars + 10 + C::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * C::kStages);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -161,9 +193,9 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     tma_prefetch_desc(&tmap_items);
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(acc_full + i, 1);
-      mbar_init(acc_empty + i, kEpiWarps);
+      mbar_init(acc_empty + i, kEpiWarps / 2);  // the 4 warps of the warpgroup that owns query tile a
     }
     for (int i = 0; i < C::kStages; ++i) {
       mbar_init(b_full + i, 1);
@@ -205,7 +237,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(1 /*bf16*/, kBM, kBN);
+      constexpr uint32_t idesc = make_idesc(1 /*bf16*/, kBM, kHN);
       uint32_t it = 0, un = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x, ++un) {
         const int s = u / p.qblocks;
@@ -215,16 +247,20 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         for (int t = t0; t < t1; ++t, ++it) {
           const int stage = it % C::kStages;
           mbar_wait(b_full + stage, (it / C::kStages) & 1);
-          for (int a = 0; a < kATiles; ++a) {
-            mbar_wait(acc_empty + a, (it & 1) ^ 1);
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(a * kBN);
-            for (int k = 0; k < ksteps; ++k) {
-              const uint32_t a_addr = smem_u32(smem_a + (a * KBOX + (k >> 2)) * kABoxBytes) + (uint32_t)(k & 3) * 32u;
-              const uint32_t b_addr = smem_u32(smem_b + stage * C::kBStage + (k >> 2) * kBBoxBytes) + (uint32_t)(k & 3) * 32u;
-              umma_f16(d_tmem, make_kmajor_desc<128>(a_addr), make_kmajor_desc<128>(b_addr), idesc, k > 0 ? 1u : 0u);
+          for (int h = 0; h < 2; ++h) {
+            for (int a = 0; a < kATiles; ++a) {
+              const int acc = a * 2 + h;
+              mbar_wait(acc_empty + acc, (it & 1) ^ 1);
+              tc_fence_after();
+              const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kHN);
+              for (int k = 0; k < ksteps; ++k) {
+                const uint32_t a_addr = smem_u32(smem_a + (a * KBOX + (k >> 2)) * kABoxBytes) + (uint32_t)(k & 3) * 32u;
+                const uint32_t b_addr = smem_u32(smem_b + stage * C::kBStage + (k >> 2) * kBBoxBytes + h * (kHN * 128)) +
+                                        (uint32_t)(k & 3) * 32u;
+                umma_f16(d_tmem, make_kmajor_desc<128>(a_addr), make_kmajor_desc<128>(b_addr), idesc, k > 0 ? 1u : 0u);
+              }
+              umma_commit(acc_full + acc);
             }
-            umma_commit(acc_full + a);
           }
           umma_commit(b_empty + stage);
         }
@@ -232,79 +268,84 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       }
     }
   } else {
-    // ===================== epilogue: 8 warps, thread = query row, two warps per row split the columns ==========
+    // ===================== epilogue: warpgroup a (4 warps) owns query tile a; thread = query row ===============
     const int ew = warp - 2;
     const int quad = warp & 3;   // TMEM lanes 32*quad .. +31 are the only ones this warp may read
-    const int half = ew >> 2;    // which 128 of the 256 columns
+    const int a = ew >> 2;       // which query tile / pair of accumulators
     const int row_in_tile = quad * 32 + lane;
     uint32_t it = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       const int qb = u % p.qblocks, s = u / p.qblocks;
       const int t0 = s * p.tiles_per_split;
       const int t1 = min(p.tiles_total, t0 + p.tiles_per_split);
-      float tau[kATiles];
-      int cnt[kATiles];
-      uint64_t* buf[kATiles];
-      int64_t qrow[kATiles];
-#pragma unroll
-      for (int a = 0; a < kATiles; ++a) {
-        qrow[a] = (int64_t)qb * kQBlock + a * kBM + row_in_tile;
-        const bool valid = qrow[a] < p.Q;
-        tau[a] = valid ? -INFINITY : INFINITY;  // rows past the end never collect anything
-        cnt[a] = 0;
-        const int64_t slot = ((valid ? qrow[a] : 0) * p.S + s) * 2 + half;
-        buf[a] = p.lists + slot * kCap;
-      }
+      const int64_t qrow = (int64_t)qb * kQBlock + a * kBM + row_in_tile;
+      const bool valid = qrow < p.Q;
+      float tau = valid ? -INFINITY : INFINITY;  // rows past the end never collect anything
+      int cnt = 0;
+      const int64_t slot = (valid ? qrow : 0) * p.S + s;
+      uint2* buf = p.lists + slot * kCap;
       for (int t = t0; t < t1; ++t, ++it) {
-#pragma unroll
-        for (int a = 0; a < kATiles; ++a) {
-          mbar_wait(acc_full + a, it & 1);
+        const bool tail = (t == p.tiles_total - 1) && (p.N % kBN != 0);  // TMA zero-filled rows past the corpus end
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          const int acc = a * 2 + h;
+          mbar_wait(acc_full + acc, it & 1);
           tc_fence_after();
 #pragma unroll 1
           for (int ch = 0; ch < 4; ++ch) {
-            unsigned need = __ballot_sync(0xffffffffu, cnt[a] > kCap - 32);
+            if (p.debug & 1) continue;
+            unsigned need = __ballot_sync(0xffffffffu, cnt > kCap - 32);
             while (need) {
               const int r = __ffs(need) - 1;
               need &= need - 1;
-              compact_row(r, lane, buf[a], cnt[a], tau[a]);
+              compact_row(r, lane, false, buf, cnt, tau);
             }
             uint32_t v[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * kBN + half * 128 + ch * 32);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kHN + ch * 32);
             tmem_ld_32x32(taddr, v);
-            float m = __uint_as_float(v[0]);
+            const uint32_t id0 = (uint32_t)t * kBN + (uint32_t)(h * kHN + ch * 32);
+            if (tail) {
 #pragma unroll
-            for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
-            if (m > tau[a]) {
-              const uint32_t id0 = (uint32_t)t * kBN + (uint32_t)(half * 128 + ch * 32);
+              for (int i = 0; i < 32; ++i)
+                if ((int64_t)(id0 + i) >= p.N) v[i] = 0xFF800000u;  // -inf: never a candidate
+            }
+            float m[8];
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                const float sc = __uint_as_float(v[i]);
-                if (sc > tau[a] && (int64_t)(id0 + i) < p.N) {
-                  buf[a][cnt[a]] = cand_key(sc, id0 + i);
-                  ++cnt[a];
+            for (int g = 0; g < 8; ++g)
+              m[g] = fmaxf(fmaxf(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1])),
+                           fmaxf(__uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3])));
+            const float mx = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
+            if (mx > tau) {
+              // rare: usually one or two of the warp's 1024 scores beat their row's threshold
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                if (m[g] > tau) {
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    if (__uint_as_float(v[4 * g + i]) > tau) {
+                      buf[cnt] = make_uint2(v[4 * g + i], id0 + 4 * g + i);
+                      ++cnt;
+                    }
+                  }
                 }
               }
             }
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(acc_empty + a);
+          if (lane == 0) mbar_arrive(acc_empty + acc);
         }
       }
-      // ---- end of unit: leave at most kKeep entries per list, publish count and threshold
-#pragma unroll
-      for (int a = 0; a < kATiles; ++a) {
-        unsigned need = __ballot_sync(0xffffffffu, cnt[a] > kKeep);
-        while (need) {
-          const int r = __ffs(need) - 1;
-          need &= need - 1;
-          compact_row(r, lane, buf[a], cnt[a], tau[a]);
-        }
-        if (qrow[a] < p.Q) {
-          const int64_t slot = (qrow[a] * p.S + s) * 2 + half;
-          p.cnts[slot] = cnt[a];
-          p.taus[slot] = tau[a];
-        }
+      // ---- end of unit: leave at most kKeep entries in the list, publish count and threshold
+      unsigned need = __ballot_sync(0xffffffffu, cnt > kKeep);
+      while (need) {
+        const int r = __ffs(need) - 1;
+        need &= need - 1;
+        compact_row(r, lane, true, buf, cnt, tau);
+      }
+      if (valid) {
+        p.cnts[slot] = cnt;
+        p.taus[slot] = tau;
       }
     }
   }
@@ -360,7 +401,7 @@ struct FinalParams {
   const __nv_bfloat16* items;
   int64_t Q, N, id_offset;
   int D, S, K;
-  const uint64_t* lists;
+  const uint2* lists;
   const int32_t* cnts;
   const float* taus;
   const uint32_t* max_norm_bits;
@@ -370,9 +411,10 @@ struct FinalParams {
   int32_t* n_flagged;    // [1]
 };
 
+template <int ITEMS>
 __global__ void __launch_bounds__(256) finalize_kernel(FinalParams p) {
-  using SortA = cub::BlockRadixSort<uint64_t, 256, 16>;
-  using SortB = cub::BlockRadixSort<uint64_t, 256, 2>;
+  using SortA = cub::BlockRadixSort<uint64_t, 256, ITEMS>;
+  using SortB = cub::BlockRadixSort<uint64_t, 256, 1>;
   __shared__ union {
     typename SortA::TempStorage a;
     typename SortB::TempStorage b;
@@ -383,7 +425,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalParams p) {
   __shared__ int s_total, s_P;
   const int q = blockIdx.x;
   const int tid = threadIdx.x;
-  const int L = 2 * p.S;
+  const int L = p.S;
   if (tid < p.D) qf[tid] = __bfloat162float(p.q[(int64_t)q * p.D + tid]);
   if (tid == 0) {
     int tot = 0;
@@ -403,22 +445,25 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalParams p) {
     for (int d = 0; d < p.D; ++d) n2 = fmaf(qf[d], qf[d], n2);
     s_qnorm2 = n2;
   }
-  uint64_t keys[16];
+  uint64_t keys[ITEMS];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int slot = tid * 16 + i;
+  for (int i = 0; i < ITEMS; ++i) {
+    const int slot = tid * ITEMS + i;
     const int l = slot / kKeep, pos = slot % kKeep;
     uint64_t k = kWorst;
-    if (l < L && pos < p.cnts[(int64_t)q * L + l]) k = ~p.lists[((int64_t)q * L + l) * kCap + pos];
+    if (l < L && pos < p.cnts[(int64_t)q * L + l]) {
+      const uint2 raw = p.lists[((int64_t)q * L + l) * kCap + pos];
+      k = ~cand_key(__uint_as_float(raw.x), raw.y);
+    }
     keys[i] = k;
   }
-  SortA(temp.a).Sort(keys);  // ascending in ~key: best tensor-core score first
+  SortA(temp.a).Sort(keys, 32, 64);  // ascending in ~key over the score bits: best tensor-core score first
   __syncthreads();
   const int total = s_total;
   const int kth = min(p.K, total) - 1;
 #pragma unroll
-  for (int i = 0; i < 16; ++i)
-    if (tid * 16 + i == kth) s_tk = key_score(~keys[i]);
+  for (int i = 0; i < ITEMS; ++i)
+    if (tid * ITEMS + i == kth) s_tk = key_score(~keys[i]);
   __syncthreads();
   // |tc - canonical| <= delta: both are fp32 accumulations of D exact products bounded by |q||item|
   const float max_norm = __uint_as_float(*p.max_norm_bits);
@@ -426,7 +471,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalParams p) {
   const float thr = s_tk - 2.f * delta;
   int mine = 0;
 #pragma unroll
-  for (int i = 0; i < 16; ++i)
+  for (int i = 0; i < ITEMS; ++i)
     if (keys[i] != kWorst && key_score(~keys[i]) >= thr) ++mine;
   if (mine) atomicAdd(&s_P, mine);
   __syncthreads();
@@ -438,30 +483,22 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalParams p) {
   }
   if (s_tq >= thr) flag = true;  // something a list dropped (score <= s_tq) could still belong to the top K
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int rank = tid * 16 + i;
+  for (int i = 0; i < ITEMS; ++i) {
+    const int rank = tid * ITEMS + i;
     if (rank < P) cand[rank] = key_id(~keys[i]);
   }
   __syncthreads();
-  uint64_t fk[2];
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int c = tid * 2 + i;
-    fk[i] = kWorst;
-    if (c < P) {
-      const uint32_t id = cand[c];
-      fk[i] = final_key(canonical_dot(qf, p.items + (int64_t)id * p.D, p.D), id);
-    }
+  uint64_t fk[1];
+  fk[0] = kWorst;
+  if (tid < P) {
+    const uint32_t id = cand[tid];
+    fk[0] = final_key(canonical_dot(qf, p.items + (int64_t)id * p.D, p.D), id);
   }
   SortB(temp.b).Sort(fk);
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int rank = tid * 2 + i;
-    if (rank < p.K) {
-      const bool valid = fk[i] != kWorst;
-      p.out_ids[(int64_t)q * p.K + rank] = valid ? (int64_t)(uint32_t)fk[i] + p.id_offset : -1;
-      p.out_scores[(int64_t)q * p.K + rank] = valid ? ordered_to_float(~(uint32_t)(fk[i] >> 32)) : -INFINITY;
-    }
+  if (tid < p.K) {
+    const bool valid = fk[0] != kWorst;
+    p.out_ids[(int64_t)q * p.K + tid] = valid ? (int64_t)(uint32_t)fk[0] + p.id_offset : -1;
+    p.out_scores[(int64_t)q * p.K + tid] = valid ? ordered_to_float(~(uint32_t)(fk[0] >> 32)) : -INFINITY;
   }
   if (flag && tid == 0) p.flagged[atomicAdd(p.n_flagged, 1)] = q;
 }
@@ -510,6 +547,10 @@ __global__ void __launch_bounds__(256) exact_rows_kernel(FinalParams p) {
 }
 
 // ---- host ---------------------------------------------------------------------------------------------------------------
+// Item splits per query block.  A unit costs max(MMA, epilogue) in units of one 256-item tile of tensor-core time:
+// the epilogue scans every tile (~0.5) and pays ~kKeep * (1 + ln(n / kKeep)) list insertions per query row for a stream
+// of n items, so many short streams are much worse than few long ones; splits only exist to fill the SMs when there
+// are fewer query blocks than SMs and to trim the last wave.
 static int choose_splits(int64_t Q, int64_t N) {
   const int64_t qblocks = ceil_div(Q, kQBlock), tiles = ceil_div(N, kBN);
   const int64_t sms = num_sms();
@@ -517,20 +558,25 @@ static int choose_splits(int64_t Q, int64_t N) {
   double best_cost = 1e300;
   for (int s = 1; s <= kMaxSplits; ++s) {
     if (s > tiles) break;
-    const int64_t units = qblocks * s;
-    const int64_t waves = ceil_div(units, sms);
-    // fixed cost per unit ~ 48 tiles: query-tile load, threshold warm-up and the final list compaction
-    const double cost = (double)waves * ((double)ceil_div(tiles, s) + 48.0);
+    const double t = (double)ceil_div(tiles, s);
+    const double n = t * kBN;
+    const double inserts = 160.0 * (1.0 + log(n / kKeep > 1.0 ? n / kKeep : 1.0));
+    const double unit = fmax(t, 0.5 * t + inserts) + 48.0;
+    const double cost = (double)ceil_div(qblocks * s, sms) * unit;
     if (cost < best_cost * 0.98) {
       best_cost = cost;
       best = s;
     }
   }
+  if (const char* e = getenv("TTAM_TOPK_SPLITS")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= kMaxSplits && v <= tiles) best = v;
+  }
   return best;
 }
 
 struct Workspace {
-  uint64_t* lists;
+  uint2* lists;
   int32_t* cnts;
   float* taus;
   uint32_t* max_norm_bits;
@@ -546,8 +592,8 @@ static Workspace carve(void* base, int64_t Q, int S) {
     off += align_up(n, 256);
     return ptr;
   };
-  const int64_t L = Q * S * 2;
-  w.lists = (uint64_t*)take(L * kCap * 8);
+  const int64_t L = Q * S;
+  w.lists = (uint2*)take(L * kCap * 8);
   w.cnts = (int32_t*)take(L * 4);
   w.taus = (float*)take(L * 4);
   w.max_norm_bits = (uint32_t*)take(256);
@@ -608,6 +654,10 @@ extern "C" int ttam_topk_bf16(const uint16_t* q, const uint16_t* items, int64_t 
   mp.tiles_total = (int)ceil_div(N, kBN);
   mp.tiles_per_split = (int)ceil_div(mp.tiles_total, S);
   mp.lists = w.lists; mp.cnts = w.cnts; mp.taus = w.taus;
+  {
+    const char* dbg = getenv("TTAM_TOPK_DEBUG");
+    mp.debug = dbg ? atoi(dbg) : 0;
+  }
   const int units = mp.qblocks * S;
   const int grid = units < num_sms() ? units : num_sms();
   if (KBOX == 1) {
@@ -624,7 +674,11 @@ extern "C" int ttam_topk_bf16(const uint16_t* q, const uint16_t* items, int64_t 
   fp.Q = Q; fp.N = N; fp.id_offset = id_offset; fp.D = (int)D; fp.S = S; fp.K = (int)K;
   fp.lists = w.lists; fp.cnts = w.cnts; fp.taus = w.taus; fp.max_norm_bits = w.max_norm_bits;
   fp.out_ids = out_ids; fp.out_scores = out_scores; fp.flagged = w.flagged; fp.n_flagged = w.n_flagged;
-  finalize_kernel<<<(unsigned)Q, 256, 0, st>>>(fp);
+  const int per_thread = (int)ceil_div((int64_t)S * kKeep, 256);
+  if (per_thread <= 1) finalize_kernel<1><<<(unsigned)Q, 256, 0, st>>>(fp);
+  else if (per_thread <= 2) finalize_kernel<2><<<(unsigned)Q, 256, 0, st>>>(fp);
+  else if (per_thread <= 4) finalize_kernel<4><<<(unsigned)Q, 256, 0, st>>>(fp);
+  else finalize_kernel<8><<<(unsigned)Q, 256, 0, st>>>(fp);
   TTAM_LAUNCH_CHECK();
   exact_rows_kernel<<<num_sms(), 256, 0, st>>>(fp);
   TTAM_LAUNCH_CHECK();
