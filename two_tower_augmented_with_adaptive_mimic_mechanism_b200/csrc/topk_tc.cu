@@ -7,10 +7,13 @@
 //   1. max_norm_kernel      max ||item||_2 (for the rounding-error bound used in step 3)
 //   2. score_topk_kernel    persistent, warp-specialised: 1 TMA warp, 1 MMA warp, 8 epilogue warps per CTA.
 //                           Work unit = (block of 256 queries, one of S item ranges).  Per 256-item tile the MMA warp
-//                           issues 4 x (D/16) tcgen05.mma (M=128, N=128, K=16, bf16 -> fp32) into four TMEM
-//                           accumulators [query tile a][item half h] (all 512 TMEM columns); epilogue warpgroup a
-//                           drains accumulators (a, 0) and (a, 1) with tcgen05.ld while the tensor core fills the
-//                           others: thread = query row, it owns that row's running threshold and candidate list.
+//                           issues 2 x (D/16) tcgen05.mma (M=128, N=256, K=16, bf16 -> fp32) into two TMEM
+//                           accumulators, one per query tile (all 512 TMEM columns; N=256 keeps the operand fetch at
+//                           96 B/clk of shared-memory bandwidth - N=128 needs all 128 and ran at half speed).
+//                           Epilogue warpgroup a drains accumulator a with tcgen05.ld, releasing it in two 128-column
+//                           halves, while the tensor core fills the other one: thread = query row, it owns that
+//                           row's running threshold and candidate list.  The hot loop is kept to one copy of the
+//                           chunk code (~6 KB) so that it stays in the instruction cache.
 //                           A 32-column chunk costs a 3-input-max tree and one compare; the rare survivors are
 //                           appended to the row's list in global memory, which a warp-cooperative bitonic sort
 //                           compacts to its best 128 whenever it fills up (raising the threshold).
@@ -79,7 +82,8 @@ __device__ __forceinline__ uint32_t key_id(uint64_t k) { return 0xFFFFFFFFu - (u
 // (unordered), and raises the row's threshold so that only scores >= t* are appended from now on.  `exact` (the final
 // compaction of a work unit) searches down to the last bit and truncates ties so that exactly kKeep entries remain.
 // Invariant kept for the finalize kernel: every item of the stream that is NOT in the list scored <= tau.
-__device__ __noinline__ void compact_row(int r, int lane, bool exact, uint2* my_buf, int& my_cnt, float& my_tau) {
+// Returns {new count, new threshold bits}; meaningful in lane r only.
+__device__ __noinline__ uint2 compact_row(int r, int lane, bool exact, uint2* my_buf, int my_cnt, float my_tau) {
   const unsigned long long base = __shfl_sync(0xffffffffu, (unsigned long long)my_buf, r);
   const int n = __shfl_sync(0xffffffffu, my_cnt, r);
   uint2* buf = reinterpret_cast<uint2*>(base);
@@ -151,11 +155,12 @@ __device__ __noinline__ void compact_row(int r, int lane, bool exact, uint2* my_
   }
   total += tie_budget;
   __syncwarp();
-  if (lane == r && n > kKeep) {
+  if (n > kKeep) {
     my_cnt = total;
     // appended from now on: keep_all_ties -> score >= t*  (tau = the float just below t*), else score > t*
     my_tau = ordered_to_float(keep_all_ties ? tstar - 1u : tstar);
   }
+  return make_uint2((uint32_t)my_cnt, __float_as_uint(my_tau));
 }
 
 struct MainParams {
@@ -179,8 +184,8 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + C::kStages * C::kBStage);
   uint64_t* a_full = bars + 0;
   uint64_t* a_empty = bars + 1;
-  uint64_t* acc_full = bars + 2;    // [4]: accumulator (a, h) at index a*2+h
-  uint64_t* acc_empty = bars + 6;   // [4]
+  uint64_t* acc_full = bars + 2;    // [2] (4 slots reserved): accumulator of query tile a
+  uint64_t* acc_empty = bars + 6;   // [4]: half h of accumulator a at index a*2+h
   uint64_t* b_full = bars + 10;     // [kStages]
   uint64_t* b_empty = bars + 10 + C::kStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * C::kStages);
@@ -237,7 +242,10 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(1 /*bf16*/, kBM, kHN);
+      constexpr uint32_t idesc = make_idesc(1 /*bf16*/, kBM, kBN);
+      // descriptors differ only in the 14-bit start-address field: precompute the bases once
+      const uint64_t a_desc0 = make_kmajor_desc<128>(smem_u32(smem_a));
+      const uint64_t b_desc0 = make_kmajor_desc<128>(smem_u32(smem_b));
       uint32_t it = 0, un = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x, ++un) {
         const int s = u / p.qblocks;
@@ -247,20 +255,21 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         for (int t = t0; t < t1; ++t, ++it) {
           const int stage = it % C::kStages;
           mbar_wait(b_full + stage, (it / C::kStages) & 1);
-          for (int h = 0; h < 2; ++h) {
-            for (int a = 0; a < kATiles; ++a) {
-              const int acc = a * 2 + h;
-              mbar_wait(acc_empty + acc, (it & 1) ^ 1);
-              tc_fence_after();
-              const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kHN);
-              for (int k = 0; k < ksteps; ++k) {
-                const uint32_t a_addr = smem_u32(smem_a + (a * KBOX + (k >> 2)) * kABoxBytes) + (uint32_t)(k & 3) * 32u;
-                const uint32_t b_addr = smem_u32(smem_b + stage * C::kBStage + (k >> 2) * kBBoxBytes + h * (kHN * 128)) +
-                                        (uint32_t)(k & 3) * 32u;
-                umma_f16(d_tmem, make_kmajor_desc<128>(a_addr), make_kmajor_desc<128>(b_addr), idesc, k > 0 ? 1u : 0u);
-              }
-              umma_commit(acc_full + acc);
+          const uint64_t b_desc = b_desc0 + (uint64_t)((stage * C::kBStage) >> 4);
+#pragma unroll 1
+          for (int a = 0; a < kATiles; ++a) {
+            // one N=256 MMA group fills both 128-column halves of query tile a: both must have been drained
+            mbar_wait(acc_empty + a * 2, (it & 1) ^ 1);
+            mbar_wait(acc_empty + a * 2 + 1, (it & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(a * kBN);
+            const uint64_t a_desc = a_desc0 + (uint64_t)((a * KBOX * kABoxBytes) >> 4);
+            for (int k = 0; k < ksteps; ++k) {
+              const uint32_t koff_a = (uint32_t)(((k >> 2) * kABoxBytes + (k & 3) * 32) >> 4);
+              const uint32_t koff_b = (uint32_t)(((k >> 2) * kBBoxBytes + (k & 3) * 32) >> 4);
+              umma_f16(d_tmem, a_desc + koff_a, b_desc + koff_b, idesc, k > 0 ? 1u : 0u);
             }
+            umma_commit(acc_full + a);
           }
           umma_commit(b_empty + stage);
         }
@@ -284,56 +293,72 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       int cnt = 0;
       const int64_t slot = (valid ? qrow : 0) * p.S + s;
       uint2* buf = p.lists + slot * kCap;
-      for (int t = t0; t < t1; ++t, ++it) {
-        const bool tail = (t == p.tiles_total - 1) && (p.N % kBN != 0);  // TMA zero-filled rows past the corpus end
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-          const int acc = a * 2 + h;
-          mbar_wait(acc_full + acc, it & 1);
-          tc_fence_after();
-#pragma unroll 1
-          for (int ch = 0; ch < 4; ++ch) {
-            if (p.debug & 1) continue;
-            unsigned need = __ballot_sync(0xffffffffu, cnt > kCap - 32);
-            while (need) {
-              const int r = __ffs(need) - 1;
-              need &= need - 1;
-              compact_row(r, lane, false, buf, cnt, tau);
-            }
-            uint32_t v[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * kHN + ch * 32);
-            tmem_ld_32x32(taddr, v);
-            const uint32_t id0 = (uint32_t)t * kBN + (uint32_t)(h * kHN + ch * 32);
-            if (tail) {
+      // one 32-column chunk of this thread's row: 3-input-max tree, one compare; survivors are rare
+      auto process = [&](uint32_t (&v)[32], uint32_t id0, bool tail) {
+        if (tail) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if ((int64_t)(id0 + i) >= p.N) v[i] = 0xFF800000u;  // -inf: never a candidate
-            }
-            float m[8];
+          for (int i = 0; i < 32; ++i)
+            if ((int64_t)(id0 + i) >= p.N) v[i] = 0xFF800000u;  // -inf: never a candidate
+        }
+        float m[8];
 #pragma unroll
-            for (int g = 0; g < 8; ++g)
-              m[g] = fmaxf(fmaxf(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1])),
-                           fmaxf(__uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3])));
-            const float mx = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
-            if (mx > tau) {
-              // rare: usually one or two of the warp's 1024 scores beat their row's threshold
+        for (int g = 0; g < 8; ++g)
+          m[g] = fmaxf(fmaxf(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1])),
+                       fmaxf(__uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3])));
+        const float mx = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
+        if (__any_sync(0xffffffffu, mx > tau) && !(p.debug & 2)) {
+          // usually one or two of the warp's 1024 scores beat their row's threshold: find the 4-column groups that
+          // hold them with warp votes (uniform branches), then append with predicated stores
+          unsigned gmask = 0;
 #pragma unroll
-              for (int g = 0; g < 8; ++g) {
-                if (m[g] > tau) {
+          for (int g = 0; g < 8; ++g) gmask |= (m[g] > tau) ? (1u << g) : 0u;
+          gmask = __reduce_or_sync(0xffffffffu, gmask);
 #pragma unroll
-                  for (int i = 0; i < 4; ++i) {
-                    if (__uint_as_float(v[4 * g + i]) > tau) {
-                      buf[cnt] = make_uint2(v[4 * g + i], id0 + 4 * g + i);
-                      ++cnt;
-                    }
-                  }
+          for (int g = 0; g < 8; ++g) {
+            if (gmask & (1u << g)) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                if (__uint_as_float(v[4 * g + i]) > tau) {
+                  buf[cnt] = make_uint2(v[4 * g + i], id0 + 4 * g + i);
+                  ++cnt;
                 }
               }
             }
           }
+        }
+      };
+      auto make_room = [&]() {
+        unsigned need = __ballot_sync(0xffffffffu, cnt > kCap - 32);
+        while (need) {
+          const int r = __ffs(need) - 1;
+          need &= need - 1;
+          const uint2 res = compact_row(r, lane, false, buf, cnt, tau);
+          if (lane == r) {
+            cnt = (int)res.x;
+            tau = __uint_as_float(res.y);
+          }
+        }
+      };
+      for (int t = t0; t < t1; ++t, ++it) {
+        const bool tail = (t == p.tiles_total - 1) && (p.N % kBN != 0);  // TMA zero-filled rows past the corpus end
+        mbar_wait(acc_full + a, it & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          if (!(p.debug & 1)) {
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ++ch) {
+              const int col = h * kHN + ch * 32;
+              uint32_t v[32];
+              tmem_ld_32x32_issue(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * kBN + col), v);
+              make_room();
+              tmem_ld_wait(v);
+              process(v, (uint32_t)t * kBN + (uint32_t)col, tail);
+            }
+          }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(acc_empty + acc);
+          if (lane == 0) mbar_arrive(acc_empty + a * 2 + h);
         }
       }
       // ---- end of unit: leave at most kKeep entries in the list, publish count and threshold
@@ -341,7 +366,11 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       while (need) {
         const int r = __ffs(need) - 1;
         need &= need - 1;
-        compact_row(r, lane, true, buf, cnt, tau);
+        const uint2 res = compact_row(r, lane, true, buf, cnt, tau);
+        if (lane == r) {
+          cnt = (int)res.x;
+          tau = __uint_as_float(res.y);
+        }
       }
       if (valid) {
         p.cnts[slot] = cnt;

@@ -42,12 +42,15 @@ def sample_negative_items(users: torch.Tensor, *, num_items: int, positives, num
         raise ValueError("num_items must be greater than one.")
     pset = positives if isinstance(positives, PositiveSet) else None
     if pset is None:
+        # single-entry cache keyed by the identity of the caller's dict; the dict itself is kept alive in the entry
+        # so that its id() cannot be recycled by another object while the entry exists
         key = (id(positives), int(num_items), str(device))
-        pset = _cache.get(key)
-        if pset is None:
-            pset = PositiveSet(positives, num_items, device)
+        entry = _cache.get(key)
+        if entry is None or entry[0] is not positives:
+            entry = (positives, PositiveSet(positives, num_items, device))
             _cache.clear()
-            _cache[key] = pset
+            _cache[key] = entry
+        pset = entry[1]
     users = users.to(device)
     B = users.shape[0]
     neg = torch.randint(0, num_items, (B, num_negatives), device=device, generator=generator)
