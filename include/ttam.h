@@ -154,15 +154,23 @@ int ttam_sort_rows(const int64_t* idx, int64_t R, int64_t num_rows, int64_t* sor
                    void* workspace, int64_t workspace_bytes, void* stream);
 int ttam_unique_rows(const int64_t* sorted_idx, int64_t R, int64_t* unique_out, int64_t* n_unique_out,
                      void* workspace, int64_t workspace_bytes, void* stream);
+/* Long segments: a popular row can own hundreds of the step's gradient rows (Zipf-distributed positives); one warp
+ * summing them would serialise the step.  ttam_find_long_segments lists the heads of the segments longer than 16
+ * (long_list[0] = count, long_list[1..] = positions in sorted_idx; ttam_long_segments_bytes(R) bytes); a row-wise
+ * update that is given the list sums those segments with a whole block each (fixed combination order:
+ * deterministic).  long_list may be null: every segment is then summed by one warp. */
+int64_t ttam_long_segments_bytes(int64_t R);
+int ttam_find_long_segments(const int64_t* sorted_idx, int64_t R, int32_t* long_list, void* stream);
 int ttam_sparse_adam_rows(float* p, float* m, float* v, int64_t D, const int64_t* sorted_idx,
                           const int32_t* perm, int64_t R, const float* grad_a, int64_t ld_a, int64_t n_a,
                           const float* grad_b, int64_t ld_b, const float* scalars, double lr, double beta1,
-                          double beta2, double eps, int64_t step, const ttam_step_state* state_dev, void* stream);
+                          double beta2, double eps, int64_t step, const ttam_step_state* state_dev,
+                          const int32_t* long_list, void* stream);
 int ttam_lazy_rows(int kind, float* p, float* m, float* v, int32_t* last_step, int64_t D,
                    const int64_t* sorted_idx, const int32_t* perm, int64_t R, const float* grad_a,
                    int64_t ld_a, int64_t n_a, const float* grad_b, int64_t ld_b, const float* scalars,
                    double lr, double weight_decay, double beta1, double beta2, double eps, double momentum,
-                   int64_t step, const ttam_step_state* state_dev, void* stream);
+                   int64_t step, const ttam_step_state* state_dev, const int32_t* long_list, void* stream);
 /* bring the unique rows of sorted_idx up to step-1 BEFORE the forward pass of step `step` reads them */
 int ttam_lazy_catchup(int kind, float* p, float* m, float* v, int32_t* last_step, int64_t D,
                       const int64_t* sorted_idx, int64_t R, const float* scalars, double lr, double weight_decay,

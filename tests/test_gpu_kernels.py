@@ -242,6 +242,51 @@ def test_sparse_adam_wide_rows_bit_exact_vs_oracle(F):
         np.testing.assert_allclose(p, po, rtol=1e-6, atol=1e-9)
 
 
+@pytest.mark.parametrize("D", [96, 256, 20])
+def test_long_segments_block_sum_matches_oracle(F, D):
+    """Zipf-like batches: a few rows own hundreds of gradient rows.  With the long-segment list those are summed by a
+    whole block (different, but fixed, summation order): same touched rows, values within fp32 summation tolerance,
+    and bit-identical from run to run."""
+    rng = np.random.default_rng(7 + D)
+    N, R = 400, 6000
+    hot = rng.integers(0, 5, size=R // 2)                        # 5 rows take half of the batch
+    idx = np.concatenate([hot, rng.integers(0, N, size=R - R // 2)]).astype(np.int64)
+    rng.shuffle(idx)
+    val = (rng.standard_normal((R, D)) * 0.01).astype(np.float32)
+    p0 = (rng.standard_normal((N, D)) * 0.02).astype(np.float32)
+    outs = []
+    for rep in range(2):
+        p = dev(p0.copy()); m, v = torch.zeros_like(p), torch.zeros_like(p)
+        sidx, perm = F.sort_rows(dev(idx), N)
+        ll = F.find_long_segments(sidx)
+        n_long = int(ll[0])
+        counts = np.bincount(idx, minlength=N)
+        assert n_long == int((counts > 16).sum())
+        assert set(sidx[ll[1:1 + n_long].long()].cpu().tolist()) == set(np.nonzero(counts > 16)[0].tolist())
+        F.sparse_adam_rows(p, m, v, sidx, perm, dev(val), lr=1e-3, step=1, long_list=ll)
+        # the lazy AdamW path on a second table, same list
+        p2 = dev(p0.copy()); m2, v2 = torch.zeros_like(p2), torch.zeros_like(p2)
+        last = torch.zeros(N, dtype=torch.int32, device="cuda")
+        scal = F.adam_scalar_table(2, 1e-3, (0.9, 0.999), "cuda")
+        F.lazy_rows("adamw", p2, m2, v2, last, sidx, perm, dev(val), scalars=scal, lr=1e-3, weight_decay=0.01, step=1,
+                    long_list=ll)
+        outs.append((p.cpu().numpy(), m.cpu().numpy(), p2.cpu().numpy(), last.cpu().numpy()))
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
+    po, st = p0.copy(), {"step": 0}
+    o_sparse_adam(po, st, idx, val, lr=1e-3)
+    np.testing.assert_allclose(outs[0][1], st["exp_avg"], rtol=2e-5, atol=1e-9)
+    np.testing.assert_allclose(outs[0][0], po, rtol=1e-5, atol=1e-7)
+    # lazy AdamW with long list == without
+    p3 = dev(p0.copy()); m3, v3 = torch.zeros_like(p3), torch.zeros_like(p3)
+    last3 = torch.zeros(N, dtype=torch.int32, device="cuda")
+    sidx, perm = F.sort_rows(dev(idx), N)
+    F.lazy_rows("adamw", p3, m3, v3, last3, sidx, perm, dev(val), scalars=F.adam_scalar_table(2, 1e-3, (0.9, 0.999), "cuda"),
+                lr=1e-3, weight_decay=0.01, step=1)
+    np.testing.assert_allclose(outs[0][2], p3.cpu().numpy(), rtol=1e-5, atol=1e-7)
+    assert np.array_equal(outs[0][3], last3.cpu().numpy())
+
+
 @pytest.mark.parametrize("kind", ["adamw", "adam", "sgd"])
 def test_lazy_rows_equal_dense_optimizer(F, kind):
     """Lazy-exact replay: touching a few rows per step + a final flush == the dense optimiser stepping every row

@@ -103,9 +103,11 @@ SIGNATURES = {
     "ttam_sort_workspace_bytes": (C.c_int64, [_i64]),
     "ttam_sort_rows": (C.c_int, [_p, _i64, _i64, _p, _p, _p, _i64, _p]),
     "ttam_unique_rows": (C.c_int, [_p, _i64, _p, _p, _p, _i64, _p]),
-    "ttam_sparse_adam_rows": (C.c_int, [_p, _p, _p, _i64, _p, _p, _i64, _p, _i64, _i64, _p, _i64, _p, _d, _d, _d, _d, _i64, _p, _p]),
+    "ttam_long_segments_bytes": (C.c_int64, [_i64]),
+    "ttam_find_long_segments": (C.c_int, [_p, _i64, _p, _p]),
+    "ttam_sparse_adam_rows": (C.c_int, [_p, _p, _p, _i64, _p, _p, _i64, _p, _i64, _i64, _p, _i64, _p, _d, _d, _d, _d, _i64, _p, _p, _p]),
     "ttam_lazy_rows": (C.c_int, [_i32, _p, _p, _p, _p, _i64, _p, _p, _i64, _p, _i64, _i64, _p, _i64, _p,
-                                 _d, _d, _d, _d, _d, _d, _i64, _p, _p]),
+                                 _d, _d, _d, _d, _d, _d, _i64, _p, _p, _p]),
     "ttam_lazy_catchup": (C.c_int, [_i32, _p, _p, _p, _p, _i64, _p, _i64, _p, _d, _d, _d, _d, _d, _d, _i64, _p, _p]),
     "ttam_lazy_flush": (C.c_int, [_i32, _p, _p, _p, _p, _i64, _i64, _p, _d, _d, _d, _d, _d, _d, _i64, _p, _p]),
     "ttam_dense_step": (C.c_int, [_i32, C.POINTER(TensorList), _p, _d, _d, _d, _d, _d, _d, _i64, _p, _p]),

@@ -19,23 +19,55 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
   }
 }
 
-// partial[s][n] = sum_{m in chunk s} dy[m][n]
+// partial[s][n] = sum_{m in chunk s} dy[m][n].  One block per row chunk; a warp reads 32 consecutive columns of a row
+// (128 B), the 8 warps take rows lo+0..7, lo+8..15, ...; the 8 partial sums are combined in warp order.
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ dy, int64_t lddy, int M, int N,
                                                              int chunk, float* __restrict__ partial) {
-  const int s = blockIdx.y;
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+  __shared__ float red[8][33];
+  const int s = blockIdx.x;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int lo = s * chunk, hi = min(M, lo + chunk);
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  int m = lo;
-  for (; m + 3 < hi; m += 4) {
-    a0 += dy[(int64_t)m * lddy + n];
-    a1 += dy[(int64_t)(m + 1) * lddy + n];
-    a2 += dy[(int64_t)(m + 2) * lddy + n];
-    a3 += dy[(int64_t)(m + 3) * lddy + n];
+  for (int n0 = 0; n0 < N; n0 += 32) {
+    const int n = n0 + tx;
+    float a0 = 0.f, a1 = 0.f;
+    if (n < N) {
+      int m = lo + ty;
+      for (; m + 8 < hi; m += 16) {
+        a0 += dy[(int64_t)m * lddy + n];
+        a1 += dy[(int64_t)(m + 8) * lddy + n];
+      }
+      if (m < hi) a0 += dy[(int64_t)m * lddy + n];
+    }
+    red[ty][tx] = a0 + a1;
+    __syncthreads();
+    if (ty == 0 && n < N) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red[w][tx];
+      partial[(int64_t)s * N + n] = t;
+    }
+    __syncthreads();
   }
-  for (; m < hi; ++m) a0 += dy[(int64_t)m * lddy + n];
-  partial[(int64_t)s * N + n] = (a0 + a1) + (a2 + a3);
+}
+
+// out[n] (+)= sum_s partial[s][n]: one warp per column, lanes stride over the splits, fixed-order tree at the end
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ partial, int splits, int N,
+                                                           float* __restrict__ out, int accumulate) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float a = 0.f;
+  for (int s = lane; s < splits; s += 32) a += partial[(int64_t)s * N + n];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+  if (lane == 0) out[n] = accumulate ? out[n] + a : a;
+}
+
+static int colsum_splits(int64_t M) {
+  int64_t s = ceil_div(M, 32);
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (s > cap) s = cap;
+  return (int)(s < 1 ? 1 : s);
 }
 
 static int wgrad_splits(int64_t M, int64_t N, int64_t K) {
@@ -100,7 +132,7 @@ extern "C" int ttam_linear_dgrad(const float* dy, int64_t lddy, const float* w, 
 
 extern "C" int64_t ttam_linear_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K) {
   int s = wgrad_splits(M, N, K);
-  return (int64_t)s * (N * K + N) * (int64_t)sizeof(float);
+  return ((int64_t)s * N * K + (int64_t)colsum_splits(M) * N) * (int64_t)sizeof(float);
 }
 
 extern "C" int ttam_linear_wgrad(const float* dy, int64_t lddy, const float* x, int64_t ldx, const int64_t* gather,
@@ -136,10 +168,12 @@ extern "C" int ttam_linear_wgrad(const float* dy, int64_t lddy, const float* x, 
     TTAM_LAUNCH_CHECK();
   }
   if (db) {
-    dim3 g2((unsigned)ceil_div(N, 256), (unsigned)real_splits, 1);
-    colsum_partial_kernel<<<g2, 256, 0, s>>>(dy, lddy, (int)M, (int)N, chunk, partial_b);
+    const int cs = colsum_splits(M);
+    const int cchunk = (int)ceil_div(M, cs);
+    const int real_cs = (int)ceil_div(M, cchunk);
+    colsum_partial_kernel<<<real_cs, 256, 0, s>>>(dy, lddy, (int)M, (int)N, cchunk, partial_b);
     TTAM_LAUNCH_CHECK();
-    splitk_reduce_kernel<<<(int)ceil_div(N, 256), 256, 0, s>>>(partial_b, real_splits, N, db, accumulate);
+    colsum_final_kernel<<<(int)ceil_div(N, 8), 256, 0, s>>>(partial_b, real_cs, (int)N, db, accumulate);
     TTAM_LAUNCH_CHECK();
   }
   return TTAM_OK;

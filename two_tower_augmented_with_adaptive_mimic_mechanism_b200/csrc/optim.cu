@@ -134,18 +134,118 @@ __device__ __forceinline__ void dense_elem(float g, float& p, float& m, float& v
   p = fmaf(-step_size, __fdiv_rn(m, denom), p);                        // addcdiv_
 }
 
+// ---- long segments ------------------------------------------------------------------------------------------------
+// A popular row (Zipf-distributed positives) can own hundreds of gradient rows of a batch; summing them with one warp
+// would serialise the whole step behind that warp.  Segments longer than kLongSeg are listed by
+// find_long_segments_kernel and processed by one whole block each: every warp sums a strided share of the rows with
+// four loads in flight, the eight partial sums are combined in warp order (a fixed order: results are deterministic),
+// and warp 0 applies the optimiser.  The row kernels skip those segments when they are given the list.
+constexpr int kLongSeg = 16;
+constexpr int kLongWarps = 8;
+
+__global__ void __launch_bounds__(256) find_long_segments_kernel(const int64_t* __restrict__ sorted, int64_t R,
+                                                                  int32_t* __restrict__ list) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i + kLongSeg >= R) return;
+  const int64_t row = sorted[i];
+  if (i > 0 && sorted[i - 1] == row) return;
+  if (sorted[i + kLongSeg] == row) list[1 + atomicAdd(list, 1)] = (int32_t)i;
+}
+
+__device__ __forceinline__ bool is_long_segment(const int64_t* __restrict__ sorted, int64_t i, int64_t R, int64_t row) {
+  return i + kLongSeg < R && sorted[i + kLongSeg] == row;
+}
+
+// first position after the segment that starts at i (32-ary search by one warp; every lane returns the result)
+__device__ __forceinline__ int64_t segment_end(const int64_t* __restrict__ sorted, int64_t i, int64_t R, int64_t row, int lane) {
+  int64_t lo = i, hi = R;  // sorted[lo] == row, (hi == R or sorted[hi] != row)
+  while (hi - lo > 1) {
+    const int64_t span = hi - lo;
+    const int64_t stepw = (span + 31) / 32;
+    const int64_t probe = lo + (int64_t)(lane + 1) * stepw;
+    const bool same = probe < hi && sorted[probe] == row;
+    const unsigned bal = __ballot_sync(0xffffffffu, same);
+    const int k = __popc(bal);  // probes 1..k hit the row (the predicate is monotone)
+    const int64_t new_lo = lo + (int64_t)k * stepw;
+    const int64_t new_hi = lo + (int64_t)(k + 1) * stepw;
+    lo = new_lo;
+    hi = new_hi < hi ? new_hi : hi;
+  }
+  return hi;
+}
+
+// Block-cooperative sum of gradient rows [i, end) for one column group; the result is valid in warp 0.
+template <bool VEC>
+__device__ __forceinline__ void segment_sum_block(const GradSrc& gs, const int32_t* __restrict__ perm, int64_t i,
+                                                  int64_t end, int col, bool active, float (*part)[128], float (&acc)[4]) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t j0 = i + warp; j0 < end; j0 += 4 * kLongWarps) {
+    float v[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t j = j0 + u * kLongWarps;
+      v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.f;
+      if (j < end && active) {
+        const float* src = gs.row(perm[j]) + col;
+        if (VEC) {
+          const float4 f = ld_f4(src);
+          v[u][0] = f.x; v[u][1] = f.y; v[u][2] = f.z; v[u][3] = f.w;
+        } else {
+          v[u][0] = src[0];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) a[e] = __fadd_rn(a[e], v[u][e]);
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) part[warp][lane * 4 + e] = a[e];
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float t = 0.f;
+      for (int w = 0; w < kLongWarps; ++w) t = __fadd_rn(t, part[w][lane * 4 + e]);
+      acc[e] = t;
+    }
+  }
+  __syncthreads();
+}
+
+template <bool VEC>
+__device__ __forceinline__ void sparse_adam_update(float* __restrict__ P, float* __restrict__ Mo, float* __restrict__ Vo,
+                                                   int64_t off, const float (&g)[4], const AdamScalars& s) {
+  if (VEC) {
+    float4 p4 = ld_f4(P + off), m4 = ld_f4(Mo + off), v4 = ld_f4(Vo + off);
+    float pp[4] = {p4.x, p4.y, p4.z, p4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) sparse_adam_elem(g[e], pp[e], mm[e], vv[e], s);
+    st_f4(P + off, make_float4(pp[0], pp[1], pp[2], pp[3]));
+    st_f4(Mo + off, make_float4(mm[0], mm[1], mm[2], mm[3]));
+    st_f4(Vo + off, make_float4(vv[0], vv[1], vv[2], vv[3]));
+  } else {
+    float pp = P[off], mm = Mo[off], vv = Vo[off];
+    sparse_adam_elem(g[0], pp, mm, vv, s);
+    P[off] = pp; Mo[off] = mm; Vo[off] = vv;
+  }
+}
+
 template <bool VEC>
 __global__ void __launch_bounds__(256) sparse_adam_rows_kernel(float* __restrict__ P, float* __restrict__ Mo,
                                                                float* __restrict__ Vo, int D,
                                                                const int64_t* __restrict__ sorted,
                                                                const int32_t* __restrict__ perm, int64_t R, GradSrc gs,
                                                                AdamScalars s, const float* __restrict__ scalars,
-                                                               const ttam_step_state* __restrict__ st) {
+                                                               const ttam_step_state* __restrict__ st, bool skip_long) {
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (i >= R) return;
   const int64_t row = sorted[i];
   if (i > 0 && sorted[i - 1] == row) return;  // not a segment head
+  if (skip_long && is_long_segment(sorted, i, R, row)) return;
   if (st) s.step_size = scalars[4 * st->step + 2];
   constexpr int W = VEC ? 128 : 32;
   for (int c0 = 0; c0 < D; c0 += W) {
@@ -154,19 +254,33 @@ __global__ void __launch_bounds__(256) sparse_adam_rows_kernel(float* __restrict
     float g[4];
     segment_sum<VEC>(gs, sorted, perm, i, R, row, col, active, g);
     if (!active) continue;
-    const int64_t off = row * (int64_t)D + col;
-    if (VEC) {
-      float4 p4 = ld_f4(P + off), m4 = ld_f4(Mo + off), v4 = ld_f4(Vo + off);
-      float pp[4] = {p4.x, p4.y, p4.z, p4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) sparse_adam_elem(g[e], pp[e], mm[e], vv[e], s);
-      st_f4(P + off, make_float4(pp[0], pp[1], pp[2], pp[3]));
-      st_f4(Mo + off, make_float4(mm[0], mm[1], mm[2], mm[3]));
-      st_f4(Vo + off, make_float4(vv[0], vv[1], vv[2], vv[3]));
-    } else {
-      float pp = P[off], mm = Mo[off], vv = Vo[off];
-      sparse_adam_elem(g[0], pp, mm, vv, s);
-      P[off] = pp; Mo[off] = mm; Vo[off] = vv;
+    sparse_adam_update<VEC>(P, Mo, Vo, row * (int64_t)D + col, g, s);
+  }
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) sparse_adam_long_kernel(float* __restrict__ P, float* __restrict__ Mo,
+                                                               float* __restrict__ Vo, int D,
+                                                               const int64_t* __restrict__ sorted,
+                                                               const int32_t* __restrict__ perm, int64_t R, GradSrc gs,
+                                                               AdamScalars s, const float* __restrict__ scalars,
+                                                               const ttam_step_state* __restrict__ st,
+                                                               const int32_t* __restrict__ list) {
+  __shared__ float part[kLongWarps][128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (st) s.step_size = scalars[4 * st->step + 2];
+  const int n = list[0];
+  constexpr int W = VEC ? 128 : 32;
+  for (int e = blockIdx.x; e < n; e += gridDim.x) {
+    const int64_t i = list[1 + e];
+    const int64_t row = sorted[i];
+    const int64_t end = segment_end(sorted, i, R, row, lane);
+    for (int c0 = 0; c0 < D; c0 += W) {
+      const int col = c0 + (VEC ? lane * 4 : lane);
+      const bool active = col < D;
+      float g[4];
+      segment_sum_block<VEC>(gs, perm, i, end, col, active, part, g);
+      if (warp == 0 && active) sparse_adam_update<VEC>(P, Mo, Vo, row * (int64_t)D + col, g, s);
     }
   }
 }
@@ -184,63 +298,100 @@ __device__ __forceinline__ void replay(float (&pp)[NE], float (&mm)[NE], float (
 }
 
 template <int KIND, bool VEC>
+__device__ __forceinline__ void lazy_update(float* __restrict__ P, float* __restrict__ Mo, float* __restrict__ Vo,
+                                            int64_t off, const float (&g)[4], int t_prev, int step,
+                                            const float* __restrict__ scalars, const AdamScalars& s) {
+  const bool has_v = KIND != TTAM_OPT_SGD;
+  const bool has_m = KIND != TTAM_OPT_SGD || s.momentum != 0.f;
+  constexpr int NE = VEC ? 4 : 1;
+  const float step_size = KIND == TTAM_OPT_SGD ? 0.f : scalars[4 * step];
+  const float bc2s = KIND == TTAM_OPT_SGD ? 1.f : scalars[4 * step + 1];
+  float pp[NE], mm[NE], vv[NE];
+  if (VEC) {
+    float4 p4 = ld_f4(P + off);
+    float4 m4 = has_m ? ld_f4(Mo + off) : make_float4(0, 0, 0, 0);
+    float4 v4 = has_v ? ld_f4(Vo + off) : make_float4(0, 0, 0, 0);
+    pp[0] = p4.x; mm[0] = m4.x; vv[0] = v4.x;
+    if (NE == 4) {
+      pp[1 % NE] = p4.y; pp[2 % NE] = p4.z; pp[3 % NE] = p4.w;
+      mm[1 % NE] = m4.y; mm[2 % NE] = m4.z; mm[3 % NE] = m4.w;
+      vv[1 % NE] = v4.y; vv[2 % NE] = v4.z; vv[3 % NE] = v4.w;
+    }
+  } else {
+    pp[0] = P[off];
+    mm[0] = has_m ? Mo[off] : 0.f;
+    vv[0] = has_v ? Vo[off] : 0.f;
+  }
+  replay<KIND, NE>(pp, mm, vv, t_prev, step - 1, scalars, s);
+#pragma unroll
+  for (int e = 0; e < NE; ++e) dense_elem<KIND>(g[e], pp[e], mm[e], vv[e], s, step_size, bc2s);
+  if (VEC) {
+    st_f4(P + off, make_float4(pp[0], pp[1 % NE], pp[2 % NE], pp[3 % NE]));
+    if (has_m) st_f4(Mo + off, make_float4(mm[0], mm[1 % NE], mm[2 % NE], mm[3 % NE]));
+    if (has_v) st_f4(Vo + off, make_float4(vv[0], vv[1 % NE], vv[2 % NE], vv[3 % NE]));
+  } else {
+    P[off] = pp[0];
+    if (has_m) Mo[off] = mm[0];
+    if (has_v) Vo[off] = vv[0];
+  }
+}
+
+template <int KIND, bool VEC>
 __global__ void __launch_bounds__(256) lazy_rows_kernel(float* __restrict__ P, float* __restrict__ Mo,
                                                         float* __restrict__ Vo, int32_t* __restrict__ last_step, int D,
                                                         const int64_t* __restrict__ sorted,
                                                         const int32_t* __restrict__ perm, int64_t R, GradSrc gs,
                                                         const float* __restrict__ scalars, AdamScalars s, int step,
-                                                        const ttam_step_state* __restrict__ st) {
+                                                        const ttam_step_state* __restrict__ st, bool skip_long) {
   const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (i >= R) return;
   const int64_t row = sorted[i];
   if (i > 0 && sorted[i - 1] == row) return;
+  if (skip_long && is_long_segment(sorted, i, R, row)) return;
   if (st) step = st->step;
   const int t_prev = last_step[row];
-  const bool has_v = KIND != TTAM_OPT_SGD;
-  const bool has_m = KIND != TTAM_OPT_SGD || s.momentum != 0.f;
   constexpr int W = VEC ? 128 : 32;
-  constexpr int NE = VEC ? 4 : 1;
-  const float step_size = KIND == TTAM_OPT_SGD ? 0.f : scalars[4 * step];
-  const float bc2s = KIND == TTAM_OPT_SGD ? 1.f : scalars[4 * step + 1];
   for (int c0 = 0; c0 < D; c0 += W) {
     const int col = c0 + (VEC ? lane * 4 : lane);
     const bool active = col < D;
     float g[4];
     segment_sum<VEC>(gs, sorted, perm, i, R, row, col, active, g);
     if (!active) continue;
-    const int64_t off = row * (int64_t)D + col;
-    float pp[NE], mm[NE], vv[NE];
-    if (VEC) {
-      float4 p4 = ld_f4(P + off);
-      float4 m4 = has_m ? ld_f4(Mo + off) : make_float4(0, 0, 0, 0);
-      float4 v4 = has_v ? ld_f4(Vo + off) : make_float4(0, 0, 0, 0);
-      pp[0] = p4.x; mm[0] = m4.x; vv[0] = v4.x;
-      if (NE == 4) {
-        pp[1 % NE] = p4.y; pp[2 % NE] = p4.z; pp[3 % NE] = p4.w;
-        mm[1 % NE] = m4.y; mm[2 % NE] = m4.z; mm[3 % NE] = m4.w;
-        vv[1 % NE] = v4.y; vv[2 % NE] = v4.z; vv[3 % NE] = v4.w;
-      }
-    } else {
-      pp[0] = P[off];
-      mm[0] = has_m ? Mo[off] : 0.f;
-      vv[0] = has_v ? Vo[off] : 0.f;
-    }
-    replay<KIND, NE>(pp, mm, vv, t_prev, step - 1, scalars, s);
-#pragma unroll
-    for (int e = 0; e < NE; ++e) dense_elem<KIND>(g[e], pp[e], mm[e], vv[e], s, step_size, bc2s);
-    if (VEC) {
-      st_f4(P + off, make_float4(pp[0], pp[1 % NE], pp[2 % NE], pp[3 % NE]));
-      if (has_m) st_f4(Mo + off, make_float4(mm[0], mm[1 % NE], mm[2 % NE], mm[3 % NE]));
-      if (has_v) st_f4(Vo + off, make_float4(vv[0], vv[1 % NE], vv[2 % NE], vv[3 % NE]));
-    } else {
-      P[off] = pp[0];
-      if (has_m) Mo[off] = mm[0];
-      if (has_v) Vo[off] = vv[0];
-    }
+    lazy_update<KIND, VEC>(P, Mo, Vo, row * (int64_t)D + col, g, t_prev, step, scalars, s);
   }
   __syncwarp();
   if (lane == 0) last_step[row] = step;
+}
+
+template <int KIND, bool VEC>
+__global__ void __launch_bounds__(256) lazy_long_kernel(float* __restrict__ P, float* __restrict__ Mo,
+                                                        float* __restrict__ Vo, int32_t* __restrict__ last_step, int D,
+                                                        const int64_t* __restrict__ sorted,
+                                                        const int32_t* __restrict__ perm, int64_t R, GradSrc gs,
+                                                        const float* __restrict__ scalars, AdamScalars s, int step,
+                                                        const ttam_step_state* __restrict__ st,
+                                                        const int32_t* __restrict__ list) {
+  __shared__ float part[kLongWarps][128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (st) step = st->step;
+  const int n = list[0];
+  constexpr int W = VEC ? 128 : 32;
+  for (int e = blockIdx.x; e < n; e += gridDim.x) {
+    const int64_t i = list[1 + e];
+    const int64_t row = sorted[i];
+    const int64_t end = segment_end(sorted, i, R, row, lane);
+    const int t_prev = last_step[row];
+    for (int c0 = 0; c0 < D; c0 += W) {
+      const int col = c0 + (VEC ? lane * 4 : lane);
+      const bool active = col < D;
+      float g[4];
+      segment_sum_block<VEC>(gs, perm, i, end, col, active, part, g);
+      if (warp == 0 && active) lazy_update<KIND, VEC>(P, Mo, Vo, row * (int64_t)D + col, g, t_prev, step, scalars, s);
+    }
+    __syncthreads();  // every warp has read last_step[row] before it changes
+    if (threadIdx.x == 0) last_step[row] = step;
+  }
 }
 
 // Bring the unique rows of `sorted` up to step-1 (zero-gradient replay) so that the forward pass of step `step`
@@ -428,6 +579,18 @@ extern "C" int ttam_unique_rows(const int64_t* sorted_idx, int64_t R, int64_t* u
   return TTAM_OK;
 }
 
+extern "C" int64_t ttam_long_segments_bytes(int64_t R) { return align_up((R / kLongSeg + 2) * 4, 256); }
+
+extern "C" int ttam_find_long_segments(const int64_t* sorted_idx, int64_t R, int32_t* long_list, void* stream) {
+  TTAM_CHECK_ARG(long_list && (R == 0 || sorted_idx), "find_long_segments: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  TTAM_CUDA(cudaMemsetAsync(long_list, 0, 4, s));
+  if (R <= kLongSeg) return TTAM_OK;
+  find_long_segments_kernel<<<(int)ceil_div(R, 256), 256, 0, s>>>(sorted_idx, R, long_list);
+  TTAM_LAUNCH_CHECK();
+  return TTAM_OK;
+}
+
 static bool vec_ok(int64_t D, const void* p, const void* m, const void* v, const float* ga, int64_t lda,
                    const float* gb, int64_t ldb) {
   auto al = [](const void* q) { return q == nullptr || ((uintptr_t)q & 15) == 0; };
@@ -438,7 +601,7 @@ extern "C" int ttam_sparse_adam_rows(float* p, float* m, float* v, int64_t D, co
                                      const int32_t* perm, int64_t R, const float* grad_a, int64_t ld_a, int64_t n_a,
                                      const float* grad_b, int64_t ld_b, const float* scalars, double lr, double beta1,
                                      double beta2, double eps, int64_t step, const ttam_step_state* state_dev,
-                                     void* stream) {
+                                     const int32_t* long_list, void* stream) {
   TTAM_CHECK_ARG(p && m && v && sorted_idx && perm && grad_a, "sparse_adam_rows: null pointer");
   TTAM_CHECK_ARG(!state_dev || scalars, "sparse_adam_rows: a device step needs the scalar table");
   TTAM_CHECK_ARG(D > 0 && step >= 1 && n_a >= 0 && n_a <= R && (n_a == R || grad_b), "sparse_adam_rows: bad argument");
@@ -448,11 +611,17 @@ extern "C" int ttam_sparse_adam_rows(float* p, float* m, float* v, int64_t D, co
   s.step_size = (float)(lr * sqrt(bc2) / bc1);
   GradSrc gs{grad_a, ld_a, n_a, grad_b, ld_b};
   const int blocks = (int)ceil_div(R * 32, 256);
-  if (vec_ok(D, p, m, v, grad_a, ld_a, grad_b, ld_b))
-    sparse_adam_rows_kernel<true><<<blocks, 256, 0, (cudaStream_t)stream>>>(p, m, v, (int)D, sorted_idx, perm, R, gs, s, scalars, state_dev);
-  else
-    sparse_adam_rows_kernel<false><<<blocks, 256, 0, (cudaStream_t)stream>>>(p, m, v, (int)D, sorted_idx, perm, R, gs, s, scalars, state_dev);
+  const bool vec = vec_ok(D, p, m, v, grad_a, ld_a, grad_b, ld_b);
+  const bool skip = long_list != nullptr;
+  cudaStream_t cs = (cudaStream_t)stream;
+  if (vec) sparse_adam_rows_kernel<true><<<blocks, 256, 0, cs>>>(p, m, v, (int)D, sorted_idx, perm, R, gs, s, scalars, state_dev, skip);
+  else sparse_adam_rows_kernel<false><<<blocks, 256, 0, cs>>>(p, m, v, (int)D, sorted_idx, perm, R, gs, s, scalars, state_dev, skip);
   TTAM_LAUNCH_CHECK();
+  if (skip) {
+    if (vec) sparse_adam_long_kernel<true><<<num_sms(), 256, 0, cs>>>(p, m, v, (int)D, sorted_idx, perm, R, gs, s, scalars, state_dev, long_list);
+    else sparse_adam_long_kernel<false><<<num_sms(), 256, 0, cs>>>(p, m, v, (int)D, sorted_idx, perm, R, gs, s, scalars, state_dev, long_list);
+    TTAM_LAUNCH_CHECK();
+  }
   return TTAM_OK;
 }
 
@@ -467,7 +636,7 @@ extern "C" int ttam_lazy_rows(int kind, float* p, float* m, float* v, int32_t* l
                               const int64_t* sorted_idx, const int32_t* perm, int64_t R, const float* grad_a,
                               int64_t ld_a, int64_t n_a, const float* grad_b, int64_t ld_b, const float* scalars,
                               double lr, double weight_decay, double beta1, double beta2, double eps, double momentum,
-                              int64_t step, const ttam_step_state* state_dev, void* stream) {
+                              int64_t step, const ttam_step_state* state_dev, const int32_t* long_list, void* stream) {
   TTAM_CHECK_ARG(p && last_step && sorted_idx && perm && grad_a, "lazy_rows: null pointer");
   TTAM_CHECK_ARG(kind >= TTAM_OPT_ADAMW && kind <= TTAM_OPT_SGD, "lazy_rows: unknown optimiser kind %d", kind);
   TTAM_CHECK_ARG(kind == TTAM_OPT_SGD || (m && v && scalars), "lazy_rows: Adam needs m, v and the scalar table");
@@ -479,11 +648,20 @@ extern "C" int ttam_lazy_rows(int kind, float* p, float* m, float* v, int32_t* l
   GradSrc gs{grad_a, ld_a, n_a, grad_b, ld_b};
   const int blocks = (int)ceil_div(R * 32, 256);
   cudaStream_t st = (cudaStream_t)stream;
-#define CALL(K, V) lazy_rows_kernel<K, V><<<blocks, 256, 0, st>>>(p, m, v, last_step, (int)D, sorted_idx, perm, R, gs, scalars, s, (int)step, state_dev)
-  if (vec_ok(D, p, m, v, grad_a, ld_a, grad_b, ld_b)) TTAM_DISPATCH_KIND(kind, true, CALL);
+  const bool skip = long_list != nullptr;
+  const bool vec = vec_ok(D, p, m, v, grad_a, ld_a, grad_b, ld_b);
+#define CALL(K, V) lazy_rows_kernel<K, V><<<blocks, 256, 0, st>>>(p, m, v, last_step, (int)D, sorted_idx, perm, R, gs, scalars, s, (int)step, state_dev, skip)
+  if (vec) TTAM_DISPATCH_KIND(kind, true, CALL);
   else TTAM_DISPATCH_KIND(kind, false, CALL);
 #undef CALL
   TTAM_LAUNCH_CHECK();
+  if (skip) {
+#define CALL(K, V) lazy_long_kernel<K, V><<<num_sms(), 256, 0, st>>>(p, m, v, last_step, (int)D, sorted_idx, perm, R, gs, scalars, s, (int)step, state_dev, long_list)
+    if (vec) TTAM_DISPATCH_KIND(kind, true, CALL);
+    else TTAM_DISPATCH_KIND(kind, false, CALL);
+#undef CALL
+    TTAM_LAUNCH_CHECK();
+  }
   return TTAM_OK;
 }
 

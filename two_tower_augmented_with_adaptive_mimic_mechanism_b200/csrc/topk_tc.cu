@@ -170,7 +170,8 @@ struct MainParams {
   uint2* lists;     // [Q][S][kCap] raw {score bits, id}
   int32_t* cnts;    // [Q][S]
   float* taus;      // [Q][S]
-  int debug;        // timing experiments only (TTAM_TOPK_DEBUG): 1 = epilogue drains nothing, 2 = no compaction
+  int debug;        // timing experiments only (TTAM_TOPK_DEBUG): 1 = epilogue drains nothing, 2 = no list appends,
+                    // 4 = no TMA item loads after the first stages, 8 = MMA does not wait for the drain
 };
 
 template <int KBOX>
@@ -233,6 +234,10 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         for (int t = t0; t < t1; ++t, ++it) {
           const int stage = it % C::kStages;
           mbar_wait(b_empty + stage, ((it / C::kStages) & 1) ^ 1);
+          if ((p.debug & 4) && it >= (uint32_t)C::kStages) {  // timing experiment: the MMA re-reads stale tiles
+            mbar_arrive(b_full + stage);
+            continue;
+          }
           mbar_expect_tx(b_full + stage, C::kBStage);
           for (int kb = 0; kb < KBOX; ++kb)
             tma_load_2d(smem_b + stage * C::kBStage + kb * kBBoxBytes, &tmap_items, b_full + stage, kb * kBoxK, t * kBN);
@@ -259,8 +264,10 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 #pragma unroll 1
           for (int a = 0; a < kATiles; ++a) {
             // one N=256 MMA group fills both 128-column halves of query tile a: both must have been drained
-            mbar_wait(acc_empty + a * 2, (it & 1) ^ 1);
-            mbar_wait(acc_empty + a * 2 + 1, (it & 1) ^ 1);
+            if (!(p.debug & 8)) {  // (8: timing experiment, accumulators overwritten without waiting for the drain)
+              mbar_wait(acc_empty + a * 2, (it & 1) ^ 1);
+              mbar_wait(acc_empty + a * 2 + 1, (it & 1) ^ 1);
+            }
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(a * kBN);
             const uint64_t a_desc = a_desc0 + (uint64_t)((a * KBOX * kABoxBytes) >> 4);
@@ -341,6 +348,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       };
       for (int t = t0; t < t1; ++t, ++it) {
         const bool tail = (t == p.tiles_total - 1) && (p.N % kBN != 0);  // TMA zero-filled rows past the corpus end
+        if (p.debug & 8) continue;
         mbar_wait(acc_full + a, it & 1);
         tc_fence_after();
 #pragma unroll 1

@@ -109,7 +109,9 @@ class FusedEngine:
         sorted_idx = self._misc(f"sorted_{tag}", (R,), torch.int64)
         perm = self._misc(f"perm_{tag}", (R,), torch.int32)
         F.sort_rows(idx, num_rows, sorted_idx=sorted_idx, perm=perm)
-        return sorted_idx, perm
+        long_list = self._misc(f"long_{tag}", (F.lib().ttam_long_segments_bytes(R) // 4,), torch.int32)
+        F.find_long_segments(sorted_idx, out=long_list)
+        return sorted_idx, perm, long_list
 
     def _lazy_kw(self):
         return dict(scalars=self.scal_dense, lr=self.lr, weight_decay=self.wd, betas=self.dense_betas, eps=self.eps,
@@ -121,14 +123,14 @@ class FusedEngine:
             F.lazy_catchup(self.kind, tab.weight, tab.m, tab.v, tab.last_step, sorted_idx, **self._lazy_kw())
 
     def _update_table(self, tab: _Table, sort, grad_a, grad_b=None):
-        sorted_idx, perm = sort
+        sorted_idx, perm, long_list = sort
         if tab.mode == "sparse_adam":
             F.sparse_adam_rows(tab.weight, tab.m, tab.v, sorted_idx, perm, grad_a, grad_b, lr=self.lr,
                                betas=self.sparse_betas, eps=self.eps, step=self.t, scalars=self.scal_sparse,
-                               state=self.state)
+                               state=self.state, long_list=long_list)
         else:
             F.lazy_rows(self.kind, tab.weight, tab.m, tab.v, tab.last_step, sorted_idx, perm, grad_a, grad_b,
-                        **self._lazy_kw())
+                        long_list=long_list, **self._lazy_kw())
 
     def _step_body(self, users, items, B, N, Xu, Xi):
         launches0 = F.lib().ttam_launch_count()

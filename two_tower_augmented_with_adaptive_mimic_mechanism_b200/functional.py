@@ -236,6 +236,16 @@ def unique_rows(sorted_idx: torch.Tensor) -> torch.Tensor:
     return out[: int(n.item())]
 
 
+def find_long_segments(sorted_idx: torch.Tensor, *, out=None) -> torch.Tensor:
+    """int32 list {count, head positions...} of the segments of `sorted_idx` longer than 16 rows (see ttam.h)."""
+    R = sorted_idx.numel()
+    n = lib().ttam_long_segments_bytes(R) // 4
+    if out is None or out.numel() < n:
+        out = torch.empty(n, dtype=torch.int32, device=sorted_idx.device)
+    check(lib().ttam_find_long_segments(sorted_idx.data_ptr(), R, out.data_ptr(), _stream()), "find_long_segments")
+    return out
+
+
 def _grad_src(grad_a, grad_b):
     ap, lda = _rows2d(grad_a, "grad_a")
     n_a = grad_a.shape[0]
@@ -246,22 +256,23 @@ def _grad_src(grad_a, grad_b):
 
 
 def sparse_adam_rows(p, m, v, sorted_idx, perm, grad_a, grad_b=None, *, lr, betas=(0.9, 0.999), eps=1e-8, step=1,
-                     scalars=None, state=None):
+                     scalars=None, state=None, long_list=None):
     ap, lda, n_a, bp, ldb = _grad_src(grad_a, grad_b)
     R = sorted_idx.numel()
     check(lib().ttam_sparse_adam_rows(p.data_ptr(), m.data_ptr(), v.data_ptr(), p.shape[1], sorted_idx.data_ptr(),
                                       perm.data_ptr(), R, ap, lda, n_a, bp, ldb, _ptr(scalars), float(lr), float(betas[0]),
-                                      float(betas[1]), float(eps), int(step), _ptr(state), _stream()), "sparse_adam_rows")
+                                      float(betas[1]), float(eps), int(step), _ptr(state), _ptr(long_list), _stream()),
+          "sparse_adam_rows")
 
 
 def lazy_rows(kind, p, m, v, last_step, sorted_idx, perm, grad_a, grad_b=None, *, scalars, lr, weight_decay=0.0,
-              betas=(0.9, 0.999), eps=1e-8, momentum=0.0, step=1, state=None):
+              betas=(0.9, 0.999), eps=1e-8, momentum=0.0, step=1, state=None, long_list=None):
     ap, lda, n_a, bp, ldb = _grad_src(grad_a, grad_b)
     R = sorted_idx.numel()
     check(lib().ttam_lazy_rows(OPT[kind], p.data_ptr(), _ptr(m), _ptr(v), last_step.data_ptr(), p.shape[1],
                                sorted_idx.data_ptr(), perm.data_ptr(), R, ap, lda, n_a, bp, ldb, _ptr(scalars),
                                float(lr), float(weight_decay), float(betas[0]), float(betas[1]), float(eps),
-                               float(momentum), int(step), _ptr(state), _stream()), "lazy_rows")
+                               float(momentum), int(step), _ptr(state), _ptr(long_list), _stream()), "lazy_rows")
 
 
 def lazy_catchup(kind, p, m, v, last_step, sorted_idx, *, scalars, lr, weight_decay=0.0, betas=(0.9, 0.999), eps=1e-8,
