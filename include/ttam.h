@@ -36,8 +36,8 @@ extern "C" {
 
 /* arithmetic of the GEMM-shaped ops */
 #define TTAM_PREC_FP32 0 /* SIMT FFMA, fp32 in / fp32 accumulate (bit-faithful to the fp32 reference up to summation order) */
-#define TTAM_PREC_TF32 1 /* tcgen05 kind::tf32, fp32 accumulate in TMEM */
-#define TTAM_PREC_BF16 2 /* tcgen05 kind::f16 (bf16 operands), fp32 accumulate in TMEM */
+#define TTAM_PREC_TF32 1 /* tcgen05 kind::tf32: operands rounded to TF32 (round-to-nearest), fp32 accumulate in TMEM */
+#define TTAM_PREC_BF16 2 /* reserved (the retrieval path, ttam_topk_bf16, is the bf16 tensor-core kernel) */
 
 /* dense optimiser kinds (training.py:1315-1333) */
 #define TTAM_OPT_ADAMW 0
@@ -73,6 +73,7 @@ int ttam_cast_f32_to_bf16(const float* src, int64_t ld_src, uint16_t* dst, int64
 
 /* ---- linear layers (encoders.py:121-144, 157-162) ------------------------------------------------
  * fwd  : y[M,N] = dropout_p(act(x[gather?][M,K] . w[N,K]^T + bias[N]))      nn.Linear + activation + nn.Dropout
+ *        (w rows are ldw floats apart: ldw = K, or a 16-byte-aligned padded copy for the tensor-core path)
  *        if `gather` is non-null the rows of x are x[gather[m]] (fused index_select, training.py:743-775)
  *        dropout: Philox4x32-10 keyed by (seed, offset + state_dev->rng_offset + m*N + n); kept value
  *        scaled by 1/(1-p).  state_dev (nullable) is the device-resident step state below, so that a
@@ -81,7 +82,7 @@ int ttam_cast_f32_to_bf16(const float* src, int64_t ld_src, uint16_t* dst, int64
  *        mask_mode 0: none; 1: multiply by (aux[m,k] > 0)  (ReLU/dropout backward through the saved output)
  *        accumulate != 0 adds into dx
  * wgrad: dw[N,K] = dy[M,N]^T . x[gather?][M,K] ; db[N] = colsum(dy)   (deterministic split-M reduction) */
-int ttam_linear_fwd(const float* x, int64_t ldx, const int64_t* gather, const float* w, const float* bias,
+int ttam_linear_fwd(const float* x, int64_t ldx, const int64_t* gather, const float* w, int64_t ldw, const float* bias,
                     float* y, int64_t ldy, int64_t M, int64_t N, int64_t K, int act, float dropout_p,
                     uint64_t seed, uint64_t offset, const ttam_step_state* state_dev, int precision,
                     void* stream);

@@ -88,6 +88,69 @@ def test_linear_dgrad_and_wgrad(F):
     assert torch.equal(dw, dw2) and torch.equal(db, db2)
 
 
+# ---------------------------------------------------------------------------------------------
+# TF32 tensor-core path (tcgen05 kind::tf32, operands rounded to 10-bit mantissas, fp32 accumulate).
+# Tolerance: |err| <= 2 * 2^-11 * sum_k |a_k b_k| (two rounded operands); checked against an fp64 product.
+# ---------------------------------------------------------------------------------------------
+def _tf32_close(got, a, b, extra=0.0):
+    """got ~= a @ b with the TF32 operand-rounding bound (a: [M,K], b: [K,N])."""
+    ref = a.astype(np.float64) @ b.astype(np.float64)
+    bound = 2.0 * 2.0 ** -11 * (np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64)) + 1e-5 + extra
+    err = np.abs(got.astype(np.float64) - ref)
+    assert (err <= bound).all(), f"max err {err.max():.3e}, bound at that point {bound.flat[err.argmax()]:.3e}"
+    # and on average it is much better than the bound (round-to-nearest, errors cancel)
+    assert err.mean() <= 0.2 * bound.mean()
+
+
+@pytest.mark.parametrize("M,N,K,gather,pad", [(1000, 192, 605, True, True), (1000, 192, 605, True, False),
+                                               (130, 96, 192, False, False), (257, 96, 96, False, False),
+                                               (64, 16, 32, False, False), (4099, 256, 64, True, False),
+                                               (333, 40, 21, True, False), (128, 300, 128, False, False)])
+def test_linear_fwd_tf32(F, M, N, K, gather, pad):
+    rng = np.random.default_rng(M + N)
+    X = rng.standard_normal((2000, K)).astype(np.float32)
+    W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    b = (rng.standard_normal(N) * 0.1).astype(np.float32)
+    idx = rng.integers(0, 2000, size=M).astype(np.int64)
+    x = X[idx] if gather else X[:M]
+    xd = dev(X) if gather else dev(x)
+    wd = dev(W)
+    if pad:                                # 16-byte aligned rows: the vectorised loader
+        xd, wd = F.pad_cols(xd), F.pad_cols(wd)
+        assert xd.stride(0) % 4 == 0 and wd.stride(0) % 4 == 0
+    got = F.linear_fwd(xd, wd, dev(b), gather=dev(idx) if gather else None, act="none", precision="tf32").cpu().numpy()
+    _tf32_close(got - b, x, W.T)
+    got_relu = F.linear_fwd(xd, wd, dev(b), gather=dev(idx) if gather else None, act="relu", precision="tf32").cpu().numpy()
+    assert np.array_equal(got_relu, np.maximum(got, 0))
+
+
+def test_linear_dgrad_and_wgrad_tf32(F):
+    rng = np.random.default_rng(11)
+    for M, N, K in [(999, 48, 37), (4096, 96, 192), (3000, 192, 605), (700, 96, 96)]:
+        X = rng.standard_normal((500, K)).astype(np.float32)
+        idx = rng.integers(0, 500, size=M).astype(np.int64)
+        dy = rng.standard_normal((M, N)).astype(np.float32)
+        W = rng.standard_normal((N, K)).astype(np.float32)
+        aux = rng.standard_normal((M, K)).astype(np.float32)
+        got = F.linear_dgrad(dev(dy), dev(W), precision="tf32").cpu().numpy()
+        _tf32_close(got, dy, W)
+        got_m = F.linear_dgrad(dev(dy), dev(W), aux=dev(aux), relu_mask=True, scale=1.25, precision="tf32").cpu().numpy()
+        np.testing.assert_allclose(got_m, got * (aux > 0) * np.float32(1.25), rtol=1e-6, atol=1e-7)
+        base = rng.standard_normal((M, K)).astype(np.float32)
+        out = dev(base)
+        F.linear_dgrad(dev(dy), dev(W), out=out, accumulate=True, precision="tf32")
+        np.testing.assert_allclose(out.cpu().numpy(), base + got, rtol=1e-6, atol=1e-6)
+        xd = F.pad_cols(dev(X))
+        dw, db = F.linear_wgrad(dev(dy), xd, gather=dev(idx), precision="tf32")
+        _tf32_close(dw.cpu().numpy(), dy.T, X[idx], extra=1e-4)
+        np.testing.assert_allclose(db.cpu().numpy(), dy.sum(0), rtol=1e-4, atol=5e-4)
+        dw2, _ = F.linear_wgrad(dev(dy), xd, gather=dev(idx), precision="tf32")
+        assert torch.equal(dw, dw2)
+        acc = dev(np.ones((N, K), np.float32))
+        F.linear_wgrad(dev(dy), xd, gather=dev(idx), dw=acc, db=dev(np.zeros(N, np.float32)), accumulate=True, precision="tf32")
+        np.testing.assert_allclose(acc.cpu().numpy(), dw.cpu().numpy() + 1.0, rtol=1e-6, atol=1e-5)
+
+
 def test_dropout_mask_is_reproducible_and_scaled(F):
     M, N, K, p = 512, 64, 16, 0.25
     x = torch.ones(M, K, device="cuda")

@@ -91,7 +91,7 @@ SIGNATURES = {
     "ttam_advance_step": (C.c_int, [_p, _u64, _p]),
     "ttam_act_fwd": (C.c_int, [_p, _p, _i64, _i64, _i32, _f, _u64, _u64, _p, _p]),
     "ttam_act_bwd": (C.c_int, [_p, _p, _p, _i64, _i64, _i32, _f, _u64, _u64, _p, _p]),
-    "ttam_linear_fwd": (C.c_int, [_p, _i64, _p, _p, _p, _p, _i64, _i64, _i64, _i64, _i32, _f, _u64, _u64, _p, _i32, _p]),
+    "ttam_linear_fwd": (C.c_int, [_p, _i64, _p, _p, _i64, _p, _p, _i64, _i64, _i64, _i64, _i32, _f, _u64, _u64, _p, _i32, _p]),
     "ttam_linear_dgrad": (C.c_int, [_p, _i64, _p, _p, _i64, _p, _i64, _i32, _f, _i32, _i64, _i64, _i64, _i32, _p]),
     "ttam_linear_wgrad_workspace_bytes": (C.c_int64, [_i64, _i64, _i64]),
     "ttam_linear_wgrad": (C.c_int, [_p, _i64, _p, _i64, _p, _p, _p, _i64, _i64, _i64, _i32, _p, _i64, _i32, _p]),

@@ -6,6 +6,7 @@
 //   dgrad (NN): dx[M,K] = (dy[M,:N] . w[:N,k]) * mask * scale   (+ dx)
 //   wgrad (TN): dw[N,K] = sum_m dy[m,n] * x[g(m),k]              (split over m, deterministic reduce)
 #include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
 
 namespace ttam {
 
@@ -84,7 +85,7 @@ static int wgrad_splits(int64_t M, int64_t N, int64_t K) {
 
 using namespace ttam;
 
-extern "C" int ttam_linear_fwd(const float* x, int64_t ldx, const int64_t* gather, const float* w, const float* bias,
+extern "C" int ttam_linear_fwd(const float* x, int64_t ldx, const int64_t* gather, const float* w, int64_t ldw, const float* bias,
                                float* y, int64_t ldy, int64_t M, int64_t N, int64_t K, int act, float dropout_p,
                                uint64_t seed, uint64_t offset, const ttam_step_state* state_dev, int precision,
                                void* stream) {
@@ -94,12 +95,16 @@ extern "C" int ttam_linear_fwd(const float* x, int64_t ldx, const int64_t* gathe
   TTAM_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, "linear_fwd: dropout must be in [0,1)");
   TTAM_CHECK_ARG(act >= TTAM_ACT_NONE && act <= TTAM_ACT_SELU, "linear_fwd: unknown activation %d", act);
   if (M == 0) return TTAM_OK;
+  TTAM_CHECK_ARG(ldw >= K, "linear_fwd: ldw < K");
+  if (precision == TTAM_PREC_TF32)
+    return tc_linear_fwd(x, ldx, gather, w, ldw, bias, y, ldy, M, N, K, act, dropout_p, seed, offset, state_dev,
+                         (cudaStream_t)stream);
   if (precision != TTAM_PREC_FP32) {
-    set_error("linear_fwd: precision %d is not built into this library yet", precision);
+    set_error("linear_fwd: precision %d is not built into this library", precision);
     return TTAM_EUNSUPPORTED;
   }
   GemmP p{};
-  p.A = x; p.B = w; p.C = y; p.lda = ldx; p.ldb = K; p.ldc = ldy; p.gatherA = gather;
+  p.A = x; p.B = w; p.C = y; p.lda = ldx; p.ldb = ldw; p.ldc = ldy; p.gatherA = gather;
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.bias = bias; p.act = act; p.dropout_p = dropout_p;
   p.seed = seed; p.offset = offset; p.st = state_dev; p.scale = 1.f;
   dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, BM), 1);
@@ -115,8 +120,10 @@ extern "C" int ttam_linear_dgrad(const float* dy, int64_t lddy, const float* w, 
   TTAM_CHECK_ARG(M >= 0 && N > 0 && K > 0 && lddy >= N && lddx >= K, "linear_dgrad: bad shape");
   TTAM_CHECK_ARG(mask_mode == 0 || (mask_mode == 1 && aux && ldaux >= K), "linear_dgrad: bad mask arguments");
   if (M == 0) return TTAM_OK;
+  if (precision == TTAM_PREC_TF32)
+    return tc_linear_dgrad(dy, lddy, w, dx, lddx, aux, ldaux, mask_mode, scale, accumulate, M, N, K, (cudaStream_t)stream);
   if (precision != TTAM_PREC_FP32) {
-    set_error("linear_dgrad: precision %d is not built into this library yet", precision);
+    set_error("linear_dgrad: precision %d is not built into this library", precision);
     return TTAM_EUNSUPPORTED;
   }
   // C[M,K] = A[M,N] . B where B(row=k, kk=n) = w[n*K + k]  (MN-contiguous)
@@ -131,7 +138,9 @@ extern "C" int ttam_linear_dgrad(const float* dy, int64_t lddy, const float* w, 
 }
 
 extern "C" int64_t ttam_linear_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K) {
-  int s = wgrad_splits(M, N, K);
+  int s = wgrad_splits(M, N, K);  // the workspace serves either precision
+  const int s_tc = tc_wgrad_splits(M, N, K);
+  if (s_tc > s) s = s_tc;
   return ((int64_t)s * N * K + (int64_t)colsum_splits(M) * N) * (int64_t)sizeof(float);
 }
 
@@ -140,8 +149,8 @@ extern "C" int ttam_linear_wgrad(const float* dy, int64_t lddy, const float* x, 
                                  void* workspace, int64_t workspace_bytes, int precision, void* stream) {
   TTAM_CHECK_ARG(dy && x && dw && workspace, "linear_wgrad: null pointer");
   TTAM_CHECK_ARG(M > 0 && N > 0 && K > 0 && lddy >= N && ldx >= K, "linear_wgrad: bad shape");
-  if (precision != TTAM_PREC_FP32) {
-    set_error("linear_wgrad: precision %d is not built into this library yet", precision);
+  if (precision != TTAM_PREC_FP32 && precision != TTAM_PREC_TF32) {
+    set_error("linear_wgrad: precision %d is not built into this library", precision);
     return TTAM_EUNSUPPORTED;
   }
   if (workspace_bytes < ttam_linear_wgrad_workspace_bytes(M, N, K)) {
@@ -149,10 +158,19 @@ extern "C" int ttam_linear_wgrad(const float* dy, int64_t lddy, const float* x, 
     return TTAM_EWORKSPACE;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  const int splits = wgrad_splits(M, N, K);
+  const int splits = precision == TTAM_PREC_TF32 ? tc_wgrad_splits(M, N, K) : wgrad_splits(M, N, K);
   const int chunk = (int)align_up(ceil_div(M, splits), BK);
   float* partial_w = (float*)workspace;
   float* partial_b = partial_w + (int64_t)splits * N * K;
+  if (precision == TTAM_PREC_TF32) {
+    int real = 0;
+    const int rc = tc_linear_wgrad_partials(dy, lddy, x, ldx, gather, partial_w, M, N, K, &real, s);
+    if (rc != TTAM_OK) return rc;
+    const int64_t numel = N * K;
+    const int blocks = (int)std::min<int64_t>(ceil_div(numel, 256), (int64_t)num_sms() * 8);
+    splitk_reduce_kernel<<<blocks, 256, 0, s>>>(partial_w, real, numel, dw, accumulate);
+    TTAM_LAUNCH_CHECK();
+  } else {
   // C[N,K] = sum_m A(row=n, k=m) * B(row=k, k=m);  A = dy (MN-contiguous), B = x rows (MN-contiguous, gathered on m)
   GemmP p{};
   p.A = dy; p.B = x; p.C = partial_w; p.lda = lddy; p.ldb = ldx; p.ldc = K; p.gatherK = gather;
@@ -166,6 +184,7 @@ extern "C" int ttam_linear_wgrad(const float* dy, int64_t lddy, const float* x, 
     int blocks = (int)std::min<int64_t>(ceil_div(numel, 256), (int64_t)num_sms() * 8);
     splitk_reduce_kernel<<<blocks, 256, 0, s>>>(partial_w, real_splits, numel, dw, accumulate);
     TTAM_LAUNCH_CHECK();
+  }
   }
   if (db) {
     const int cs = colsum_splits(M);

@@ -1,0 +1,387 @@
+// TF32 tensor-core GEMMs (tcgen05.mma kind::tf32, fp32 accumulate in TMEM) for the tower linear layers:
+// TTAM_PREC_TF32 of ttam_linear_fwd / _dgrad / _wgrad (reference encoders.py:121-144,157-162 + autograd).
+//
+// One kernel, three roles.  C[M,N] = sum_k A(m,k) B(n,k) with each operand either K-major (the reduction index is
+// contiguous in global memory) or MN-major (the row/column index is contiguous):
+//   fwd   : A = x[gather(m), k]  K-major        B = w[n, k]          K-major      bias + activation + dropout epilogue
+//   dgrad : A = dy[m, n']        K-major        B = w[n', k'] as (k', n')  MN-major   mask + scale (+ accumulate) epilogue
+//   wgrad : A = x[gather(r), k'] as (k', r)  MN-major, B = dy[r, n'] as (n', r)  MN-major, reduction over the rows r,
+//           split over blockIdx.z, transposed partial store  part[z][n'][k']  (summed by splitk_reduce_kernel)
+// Operands stay fp32 in global memory; 8 producer warps copy them through registers (16-byte loads, round-to-nearest
+// TF32) into shared memory in the canonical 128-byte-swizzled UMMA layouts, 32 reduction steps per stage; one thread
+// issues 4 tcgen05.mma (M=128, N=bn, K=8) per stage; the producers then become the epilogue (tcgen05.ld, thread = row).
+// The layer-1 GEMMs are bound by L2->SM operand traffic (2.4 kB of features + the 465 kB weight per 128 rows), not by
+// the tensor pipe, which is why the operands are not down-converted further.
+#include "gemm_tc.cuh"
+#include "sm100.cuh"
+
+namespace ttam {
+namespace tcg {
+
+using namespace ttam::sm100;
+
+constexpr int kBM = 128;
+constexpr int kKC = 32;  // reduction elements per stage: one 128-byte swizzled row of fp32
+constexpr int kProdWarps = 8;
+constexpr int kProdThreads = 32 * kProdWarps;
+constexpr int kThreads = kProdThreads + 32;
+constexpr uint32_t kABytes = kBM * 128;  // 16 KB per stage
+constexpr uint32_t kAtomBytes = 1024;    // 8 rows x 128 B
+constexpr uint32_t kMnLbo = (kKC / 8) * kAtomBytes;  // MN-major: distance between 32-element atoms along M/N
+
+struct TcP {
+  const float* A;
+  const float* B;
+  float* C;
+  int64_t lda, ldb, ldc;
+  const int64_t* gatherA;  // K-major A: row map (m -> source row); MN-major A: reduction-row map (k -> source row)
+  const int64_t* gatherB;  // MN-major B: reduction-row map
+  int M, N, K;
+  int k_chunk;  // reduction range per blockIdx.z (multiple of kKC); 0 = whole K
+  int bn;       // N tile: multiple of 32, <= 256
+  int stages;
+  int vecA, vecB, vecC;  // 16-byte accesses allowed (base and leading dimension aligned)
+  int transposed;        // store C(m,n) at C[z][n*ldc + m]
+  const float* bias;
+  int act;
+  float dropout_p;
+  uint64_t seed, offset;
+  const ttam_step_state* st;
+  const float* aux;
+  int64_t ldaux;
+  int mask_mode;
+  float scale;
+  int accumulate;
+};
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return u;
+}
+
+// 4 consecutive floats starting at src (elements >= n_valid are zero); `vec` = a 16-byte load is legal
+__device__ __forceinline__ float4 load4(const float* src, int n_valid, bool vec) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (n_valid <= 0) return v;
+  if (vec) {
+    v = ld_f4(src);
+    if (n_valid < 4) {
+      if (n_valid < 2) v.y = 0.f;
+      if (n_valid < 3) v.z = 0.f;
+      v.w = 0.f;
+    }
+  } else {
+    v.x = src[0];
+    if (n_valid > 1) v.y = src[1];
+    if (n_valid > 2) v.z = src[2];
+    if (n_valid > 3) v.w = src[3];
+  }
+  return v;
+}
+
+__device__ __forceinline__ void store_tf32x4(uint8_t* dst, const float4& v) {
+  *reinterpret_cast<uint4*>(dst) = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(TcP p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int bn = p.bn;
+  const uint32_t b_bytes = (uint32_t)bn * 128u;
+  const uint32_t stage_bytes = kABytes + b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (uint32_t)p.stages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + p.stages;
+  uint64_t* acc_full = bars + 2 * p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
+
+  const int t = threadIdx.x;
+  const int warp = t >> 5, lane = t & 31;
+  const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * bn;
+  int k_lo = 0, k_hi = p.K;
+  if (p.k_chunk > 0) {
+    k_lo = blockIdx.z * p.k_chunk;
+    k_hi = min(p.K, k_lo + p.k_chunk);
+  }
+  const int nchunks = (k_hi - k_lo + kKC - 1) / kKC;
+  const uint32_t tmem_cols = bn <= 32 ? 32u : bn <= 64 ? 64u : bn <= 128 ? 128u : 256u;
+
+  if (t == 0) {
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(full + i, kProdWarps);
+      mbar_init(empty + i, 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == kProdWarps) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < kProdWarps) {
+    // ===================== producers: global -> registers -> swizzled shared memory =====================
+    // K-major tile: chunk id = t + 256 j  ->  row = (t >> 3) + 32 j, 16-byte chunk c = t & 7 of the row's 128 bytes
+    // MN-major tile: warp w owns reduction rows k = w + 8 j; lanes walk the 16-byte chunks along M/N
+    const int kc = t & 7;
+    const int krow = t >> 3;  // 0..31
+    const float* a_ptr[4];
+    if (!A_MN) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = m0 + krow + 32 * j;
+        a_ptr[j] = r < p.M ? p.A + (p.gatherA ? p.gatherA[r] : (int64_t)r) * p.lda : nullptr;
+      }
+    }
+    const int nb_k = bn >> 5;          // K-major B: chunk passes (bn / 32), <= 8
+    const int nb_mn = (bn + 127) >> 7;  // MN-major B: lane passes over bn/4 chunks, <= 2
+    for (int c = 0; c < nchunks; ++c) {
+      const int stage = c % p.stages;
+      const int k0 = k_lo + c * kKC;
+      uint8_t* sA = smem + (uint32_t)stage * stage_bytes;
+      uint8_t* sB = sA + kABytes;
+      float4 va[4];
+      float4 vb[8];
+      // ---- issue every load of this stage before the first use
+      if (!A_MN) {
+        const int kq = k0 + 4 * kc;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) va[j] = a_ptr[j] ? load4(a_ptr[j] + kq, k_hi - kq, p.vecA) : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int kk = k0 + warp + 8 * j;
+          const int m = m0 + 4 * lane;
+          va[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (kk < k_hi) {
+            const int64_t src_row = p.gatherA ? p.gatherA[kk] : (int64_t)kk;
+            va[j] = load4(p.A + src_row * p.lda + m, p.M - m, p.vecA);
+          }
+        }
+      }
+      if (!B_MN) {
+        const int kq = k0 + 4 * kc;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (j < nb_k) {
+            const int n = n0 + krow + 32 * j;
+            vb[j] = n < p.N ? load4(p.B + (int64_t)n * p.ldb + kq, k_hi - kq, p.vecB) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int kk = k0 + warp + 8 * j;
+          const int64_t src_row = kk < k_hi ? (p.gatherB ? p.gatherB[kk] : (int64_t)kk) : -1;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (h < nb_mn) {
+              const int cc = lane + 32 * h;  // 16-byte chunk along N
+              const int n = n0 + 4 * cc;
+              vb[j * 2 + h] = (src_row >= 0 && 4 * cc < bn) ? load4(p.B + src_row * p.ldb + n, p.N - n, p.vecB)
+                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+        }
+      }
+      mbar_wait(empty + stage, ((c / p.stages) & 1) ^ 1);
+      // ---- round to TF32 and store in the UMMA layouts
+      if (!A_MN) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int row = krow + 32 * j;
+          store_tf32x4(sA + row * 128 + ((kc ^ (row & 7)) << 4), va[j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = warp + 8 * j;
+          store_tf32x4(sA + (lane >> 3) * kMnLbo + (k >> 3) * kAtomBytes + (k & 7) * 128 + (((lane & 7) ^ (k & 7)) << 4), va[j]);
+        }
+      }
+      if (!B_MN) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (j < nb_k) {
+            const int row = krow + 32 * j;
+            store_tf32x4(sB + row * 128 + ((kc ^ (row & 7)) << 4), vb[j]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = warp + 8 * j;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int cc = lane + 32 * h;
+            if (h < nb_mn && 4 * cc < bn)
+              store_tf32x4(sB + (cc >> 3) * kMnLbo + (k >> 3) * kAtomBytes + (k & 7) * 128 + (((cc & 7) ^ (k & 7)) << 4),
+                           vb[j * 2 + h]);
+          }
+        }
+      }
+      fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full + stage);
+    }
+
+    // ===================== epilogue: thread = output row (TMEM lane), 16 columns per tcgen05.ld =====================
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int quad = warp & 3, half = warp >> 2;
+    const int m = m0 + quad * 32 + lane;
+    const int cols_half = bn >> 1;
+    const float keep_scale = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
+    const uint64_t rng_base = p.offset + ((p.dropout_p > 0.f && p.st) ? p.st->rng_offset : 0ull);
+    float* Cz = p.C;
+    if (p.k_chunk > 0) Cz += (int64_t)blockIdx.z * (p.transposed ? (int64_t)p.N * p.ldc : (int64_t)p.M * p.ldc);
+    for (int cb = 0; cb < cols_half; cb += 16) {
+      const int col = half * cols_half + cb;
+      uint32_t r[16];
+      tmem_ld_32x16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)col, r);
+      if (m < p.M) {
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int n = n0 + col + i;
+        float x = __uint_as_float(r[i]);
+        if (n < p.N) {
+          if (p.bias) x += p.bias[n];
+          x = apply_act(p.act, x);
+          if (p.dropout_p > 0.f)
+            x = dropout_keep(p.seed, rng_base + (uint64_t)m * (uint64_t)p.N + (uint64_t)n, p.dropout_p) ? x * keep_scale : 0.f;
+          if (p.mask_mode == 1) x = (p.aux[(int64_t)m * p.ldaux + n] > 0.f) ? x : 0.f;
+          x *= p.scale;
+        }
+        v[i] = x;
+      }
+      if (p.transposed) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int n = n0 + col + i;
+          if (n < p.N) {
+            float* dst = Cz + (int64_t)n * p.ldc + m;
+            *dst = p.accumulate ? *dst + v[i] : v[i];
+          }
+        }
+      } else {
+        float* dst = Cz + (int64_t)m * p.ldc + n0 + col;
+        if (p.vecC && n0 + col + 15 < p.N) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            if (p.accumulate) {
+              const float4 old = ld_f4(dst + i);
+              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            st_f4(dst + i, o);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (n0 + col + i < p.N) dst[i] = p.accumulate ? dst[i] + v[i] : v[i];
+        }
+      }
+      }
+      __syncwarp();  // tcgen05.ld is warp-collective: reconverge before the next one
+    }
+  } else if (lane == 0) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = make_idesc(2 /*tf32*/, kBM, bn, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    for (int c = 0; c < nchunks; ++c) {
+      const int stage = c % p.stages;
+      mbar_wait(full + stage, (c / p.stages) & 1);
+      tc_fence_after();
+      const uint32_t sA = smem_u32(smem + (uint32_t)stage * stage_bytes);
+      const uint32_t sB = sA + kABytes;
+#pragma unroll
+      for (int ks = 0; ks < kKC / 8; ++ks) {
+        const uint64_t ad = A_MN ? make_mnmajor_desc_sw128(sA + ks * kAtomBytes, kMnLbo, kAtomBytes) : make_kmajor_desc<128>(sA + ks * 32);
+        const uint64_t bd = B_MN ? make_mnmajor_desc_sw128(sB + ks * kAtomBytes, kMnLbo, kAtomBytes) : make_kmajor_desc<128>(sB + ks * 32);
+        umma_tf32(tmem_base, ad, bd, idesc, (c | ks) != 0 ? 1u : 0u);
+      }
+      umma_commit(empty + stage);
+    }
+    umma_commit(acc_full);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kProdWarps) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+static int pick_bn(int64_t N) {
+  int64_t bn = N < 256 ? N : 256;
+  return (int)align_up(bn, 32);
+}
+
+template <bool A_MN, bool B_MN>
+static int launch(TcP& p, int splits, cudaStream_t st) {
+  p.stages = p.bn > 128 ? 2 : p.bn > 64 ? 3 : 4;
+  const size_t smem = (size_t)p.stages * (kABytes + (size_t)p.bn * 128) + 1024 + 256;
+  static bool attr_done = false;
+  if (!attr_done) {
+    TTAM_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr_done = true;
+  }
+  dim3 grid((unsigned)ceil_div(p.N, p.bn), (unsigned)ceil_div(p.M, kBM), (unsigned)splits);
+  gemm_tf32_kernel<A_MN, B_MN><<<grid, kThreads, smem, st>>>(p);
+  TTAM_LAUNCH_CHECK();
+  return TTAM_OK;
+}
+
+}  // namespace tcg
+
+using namespace tcg;
+
+int tc_linear_fwd(const float* x, int64_t ldx, const int64_t* gather, const float* w, int64_t ldw, const float* bias,
+                  float* y, int64_t ldy, int64_t M, int64_t N, int64_t K, int act, float dropout_p, uint64_t seed,
+                  uint64_t offset, const ttam_step_state* state_dev, cudaStream_t st) {
+  TcP p{};
+  p.A = x; p.B = w; p.C = y; p.lda = ldx; p.ldb = ldw; p.ldc = ldy; p.gatherA = gather;
+  p.M = (int)M; p.N = (int)N; p.K = (int)K; p.bn = pick_bn(N);
+  p.vecA = aligned16(x) && ldx % 4 == 0; p.vecB = aligned16(w) && ldw % 4 == 0; p.vecC = aligned16(y) && ldy % 4 == 0;
+  p.bias = bias; p.act = act; p.dropout_p = dropout_p; p.seed = seed; p.offset = offset; p.st = state_dev; p.scale = 1.f;
+  return launch<false, false>(p, 1, st);
+}
+
+int tc_linear_dgrad(const float* dy, int64_t lddy, const float* w, float* dx, int64_t lddx, const float* aux, int64_t ldaux,
+                    int mask_mode, float scale, int accumulate, int64_t M, int64_t N, int64_t K, cudaStream_t st) {
+  // dx[M,K] = dy[M,N] . w[N,K]:  reduction over N;  B(k', n') = w[n'*K + k'] is MN-major
+  TcP p{};
+  p.A = dy; p.B = w; p.C = dx; p.lda = lddy; p.ldb = K; p.ldc = lddx;
+  p.M = (int)M; p.N = (int)K; p.K = (int)N; p.bn = pick_bn(K);
+  p.vecA = aligned16(dy) && lddy % 4 == 0; p.vecB = aligned16(w) && K % 4 == 0; p.vecC = aligned16(dx) && lddx % 4 == 0;
+  p.aux = aux; p.ldaux = ldaux; p.mask_mode = mask_mode; p.scale = scale; p.accumulate = accumulate;
+  return launch<false, true>(p, 1, st);
+}
+
+int tc_wgrad_splits(int64_t M, int64_t N, int64_t K) {
+  const int64_t tiles = ceil_div(K, kBM) * ceil_div(N, pick_bn(N));
+  int64_t s = ceil_div((int64_t)num_sms() * 2, tiles);
+  const int64_t by_rows = ceil_div(M, 256);
+  if (s > by_rows) s = by_rows;
+  if (s < 1) s = 1;
+  return (int)s;
+}
+
+int tc_linear_wgrad_partials(const float* dy, int64_t lddy, const float* x, int64_t ldx, const int64_t* gather, float* partial,
+                             int64_t M, int64_t N, int64_t K, int* real_splits, cudaStream_t st) {
+  // part[z][n'][k'] = sum_{r in chunk z} dy[r, n'] x[g(r), k']:  C(m = k', n = n'), both operands MN-major over r
+  const int splits = tc_wgrad_splits(M, N, K);
+  const int chunk = (int)align_up(ceil_div(M, splits), kKC);
+  *real_splits = (int)ceil_div(M, chunk);
+  TcP p{};
+  p.A = x; p.B = dy; p.C = partial; p.lda = ldx; p.ldb = lddy; p.ldc = K; p.gatherA = gather;
+  p.M = (int)K; p.N = (int)N; p.K = (int)M; p.k_chunk = chunk; p.bn = pick_bn(N);
+  p.vecA = aligned16(x) && ldx % 4 == 0; p.vecB = aligned16(dy) && lddy % 4 == 0; p.vecC = 0;
+  p.transposed = 1; p.scale = 1.f;
+  return launch<true, true>(p, *real_splits, st);
+}
+
+}  // namespace ttam

@@ -1,0 +1,17 @@
+// TF32 tcgen05 implementations behind ttam_linear_fwd / _dgrad / _wgrad (TTAM_PREC_TF32); see gemm_tc.cu.
+#pragma once
+#include "gemm_simt.cuh"
+
+namespace ttam {
+
+int tc_linear_fwd(const float* x, int64_t ldx, const int64_t* gather, const float* w, int64_t ldw, const float* bias,
+                  float* y, int64_t ldy, int64_t M, int64_t N, int64_t K, int act, float dropout_p, uint64_t seed,
+                  uint64_t offset, const ttam_step_state* state_dev, cudaStream_t st);
+int tc_linear_dgrad(const float* dy, int64_t lddy, const float* w, float* dx, int64_t lddx, const float* aux, int64_t ldaux,
+                    int mask_mode, float scale, int accumulate, int64_t M, int64_t N, int64_t K, cudaStream_t st);
+int tc_wgrad_splits(int64_t M, int64_t N, int64_t K);
+// part[z][N][K] for z < *real_splits
+int tc_linear_wgrad_partials(const float* dy, int64_t lddy, const float* x, int64_t ldx, const int64_t* gather, float* partial,
+                             int64_t M, int64_t N, int64_t K, int* real_splits, cudaStream_t st);
+
+}  // namespace ttam

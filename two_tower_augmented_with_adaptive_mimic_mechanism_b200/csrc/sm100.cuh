@@ -129,6 +129,18 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
       : "memory");
 }
 
+// 16-column variant (epilogues whose column count per warp is a multiple of 16 but not of 32)
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      "tcgen05.wait::ld.sync.aligned;\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
 // Split form for software pipelining: issue the load, do other work, then wait.  The wait names the destination
 // registers as in/out operands so that the compiler cannot schedule a use of them above it.
 __device__ __forceinline__ void tmem_ld_32x32_issue(uint32_t taddr, uint32_t (&r)[32]) {
@@ -167,10 +179,24 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
   d |= layout << 61;                                 // [61,64) swizzle mode
   return d;
 }
+// MN-major operand tile, 128-byte swizzle: atoms of 8 reduction rows x 128 bytes (64 bf16 / 32 tf32 along M or N);
+// LBO = byte distance between atoms along M/N, SBO = byte distance between 8-row groups along K
+// (cute::UMMA::make_umma_desc<Major::MN>, LayoutType::B128: ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units).
+__device__ __forceinline__ uint64_t make_mnmajor_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // instruction descriptor, kind::f16 / kind::tf32, fp32 accumulate, both operands K-major
 // fmt: 0 = f16, 1 = bf16, 2 = tf32
-__host__ __device__ constexpr uint32_t make_idesc(int fmt, int M, int N) {
-  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// a_mn / b_mn: 1 = the operand tile is MN-major (bits 15 / 16)
+__host__ __device__ constexpr uint32_t make_idesc(int fmt, int M, int N, int a_mn = 0, int b_mn = 0) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 }  // namespace sm100

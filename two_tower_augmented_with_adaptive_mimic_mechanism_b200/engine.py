@@ -83,6 +83,7 @@ class FusedEngine:
         self.bufs_i: dict = {}
         self.misc: dict = {}
         self._graphs: dict = {}
+        self._xpad: dict = {}
 
     # --------------------------------------------------------------------------------------------
     def _add_table(self, name, weight, mode):
@@ -94,6 +95,20 @@ class FusedEngine:
         if mode == "lazy":
             t.last_step = torch.zeros(weight.shape[0], dtype=torch.int32, device=weight.device)
         self.tables[name] = t
+
+    def _x(self, X):
+        """Feature matrix as the GEMM loaders want it.  The tensor-core path needs 16-byte aligned rows: a matrix whose
+        row length is not a multiple of 4 floats (F = 605) is copied ONCE into a zero-padded layout (ld = 608) and the
+        copy is reused for as long as the caller keeps passing the same tensor."""
+        if X is None or self.precision == "fp32":
+            return X
+        key = (X.data_ptr(), tuple(X.shape))
+        hit = self._xpad.get(key)
+        if hit is None:
+            hit = F.pad_cols(X)
+            self._xpad = {k: v for k, v in self._xpad.items() if k[0] != key[0]}
+            self._xpad[key] = hit
+        return hit
 
     def _misc(self, name, shape, dtype):
         t = self.misc.get(name)
@@ -133,6 +148,7 @@ class FusedEngine:
                         long_list=long_list, **self._lazy_kw())
 
     def _step_body(self, users, items, B, N, Xu, Xi):
+        Xu, Xi = self._x(Xu), self._x(Xi)
         launches0 = F.lib().ttam_launch_count()
         F.advance_step(self.state, rng_stride=1 << 36)
         T = self.tables
@@ -256,7 +272,7 @@ class FusedEngine:
         self.flush()
         plan = self.user if side == "user" else self.item
         bufs = self.misc.setdefault(f"enc_{side}", {})
-        c = tower_forward(plan, idx.contiguous(), X, gather=True, train=False, bufs=bufs, precision=self.precision)
+        c = tower_forward(plan, idx.contiguous(), self._x(X), gather=True, train=False, bufs=bufs, precision=self.precision)
         if out is None:
             return c.o.clone()
         out.copy_(c.o)

@@ -69,12 +69,24 @@ def cast_bf16(src: torch.Tensor) -> torch.Tensor:
     return dst
 
 
+def pad_cols(t: torch.Tensor, mult: int = 4, *, out=None) -> torch.Tensor:
+    """View [R, C] of a zero-padded copy whose rows are a multiple of `mult` floats (16-byte aligned rows for the
+    tensor-core loaders).  Returns `t` itself when it already qualifies."""
+    R, Ccols = t.shape
+    if Ccols % mult == 0 and t.stride(1) == 1 and t.stride(0) % mult == 0 and t.data_ptr() % 16 == 0:
+        return t
+    ld = (Ccols + mult - 1) // mult * mult
+    if out is None or out.shape != (R, ld) or out.device != t.device:
+        out = torch.zeros((R, ld), dtype=t.dtype, device=t.device)
+    out[:, :Ccols].copy_(t)
+    return out[:, :Ccols]
+
+
 def linear_fwd(x, w, bias=None, *, gather=None, act="none", out=None, dropout_p=0.0, seed=0, offset=0,
                state=None, precision="fp32"):
     _chk(x, torch.float32, "x"); _chk(w, torch.float32, "w")
     xp, ldx = _rows2d(x, "x")
-    if not w.is_contiguous():
-        raise ValueError("w must be contiguous [N,K]")
+    wp, ldw = _rows2d(w, "w")          # [N,K], rows ldw apart (a padded view is fine)
     N, K = w.shape
     if x.shape[1] != K:
         raise ValueError(f"x has {x.shape[1]} columns, weight expects {K}")
@@ -86,7 +98,7 @@ def linear_fwd(x, w, bias=None, *, gather=None, act="none", out=None, dropout_p=
     if out is None:
         out = torch.empty((M, N), dtype=torch.float32, device=x.device)
     yp, ldy = _rows2d(out, "out")
-    check(lib().ttam_linear_fwd(xp, ldx, _ptr(gather), w.data_ptr(), _ptr(bias), yp, ldy, M, N, K, ACT[act],
+    check(lib().ttam_linear_fwd(xp, ldx, _ptr(gather), wp, ldw, _ptr(bias), yp, ldy, M, N, K, ACT[act],
                                 float(dropout_p), int(seed), int(offset), _ptr(state), PREC[precision], _stream()), "linear_fwd")
     return out
 

@@ -107,6 +107,20 @@ def _buf(bufs, name, shape, device):
     return torch.empty(shape, dtype=torch.float32, device=device)
 
 
+def _w_for(W: torch.Tensor, bufs, precision: str) -> torch.Tensor:
+    """Weight operand of a forward GEMM: the tensor-core path wants 16-byte aligned rows, so a weight whose row length
+    is not a multiple of 4 floats (the 605-wide layer 1) is copied into a padded buffer (refreshed on every call: the
+    optimiser rewrites the weight each step; 0.5 MB)."""
+    if precision == "fp32" or W.shape[1] % 4 == 0:
+        return W
+    if bufs is None:
+        return F.pad_cols(W)
+    key = f"wpad{id(W)}"
+    view = F.pad_cols(W, out=bufs.get(key))
+    bufs[key] = view._base if view._base is not None else view
+    return view
+
+
 def tower_forward(plan: TowerPlan, idx: torch.Tensor, X: Optional[torch.Tensor], *, gather: bool, train: bool,
                   bufs: Optional[dict] = None, seed: int = 0, rng_base: int = 0, state=None, precision="fp32",
                   want_q: bool = False, augment: bool = True) -> Cache:
@@ -143,7 +157,7 @@ def tower_forward(plan: TowerPlan, idx: torch.Tensor, X: Optional[torch.Tensor],
                 f_view.copy_(X)
         elif plan.fe_kind == "linear":
             W, b = plan.fe_layers[0]
-            F.linear_fwd(X, W, b, gather=gidx, out=f_view, precision=precision)
+            F.linear_fwd(X, _w_for(W, bufs, precision), b, gather=gidx, out=f_view, precision=precision)
         else:
             h_in, g_in = X, gidx
             c.pre, c.hd = [], []
@@ -151,6 +165,7 @@ def tower_forward(plan: TowerPlan, idx: torch.Tensor, X: Optional[torch.Tensor],
             for li, (W, b) in enumerate(plan.fe_layers[:-1]):
                 H = W.shape[0]
                 hd = _buf(bufs, f"hd{li}", (R, H), dev)
+                W = _w_for(W, bufs, precision)
                 if plan.activation == "relu":
                     F.linear_fwd(h_in, W, b, gather=g_in, act="relu", out=hd, dropout_p=p_drop, seed=seed, offset=off,
                                  state=state, precision=precision)
@@ -164,7 +179,7 @@ def tower_forward(plan: TowerPlan, idx: torch.Tensor, X: Optional[torch.Tensor],
                 off += R * H
                 h_in, g_in = hd, None
             W, b = plan.fe_layers[-1]
-            F.linear_fwd(h_in, W, b, gather=g_in, out=f_view, precision=precision)
+            F.linear_fwd(h_in, _w_for(W, bufs, precision), b, gather=g_in, out=f_view, precision=precision)
         # ---- fusion
         if plan.fusion == "sum":
             if Df != D:
