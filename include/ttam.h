@@ -119,12 +119,14 @@ int ttam_augment_fwd(const float* t, const float* aug_table, int64_t aug_rows, c
  * outputs, q_u,q_p[B,D] augmentation rows of the positive pairs (all four null when mimic is off).
  * loss_out[4] = {total, bce, mimic_user, mimic_item}.  Gradients (null pointers skip the backward):
  *   do_u[B,D], do_i[(1+N)B,D]  = dL/do = dL/dt ;  dq_u[B,D], dq_p[B,D] = dL/dq of the positive pairs
- *   (dL/dq of a negative row equals its do_i row). */
+ *   (dL/dq of a negative row equals its do_i row).
+ * batch_fraction (1 on one GPU, 1/world_size when the batch is data-parallel): every mean runs over the GLOBAL
+ * batch, so that the per-rank losses and gradients simply add up. */
 int64_t ttam_loss_workspace_bytes(int64_t B);
 int ttam_loss_fwd_bwd(const float* o_u, const float* o_i, const float* t_u, const float* t_p,
                       const float* q_u, const float* q_p, float lambda_u, float lambda_i, float* loss_out,
                       float* do_u, float* do_i, float* dq_u, float* dq_p, int64_t B, int64_t N, int64_t D,
-                      void* workspace, int64_t workspace_bytes, void* stream);
+                      float batch_fraction, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- sparse backward + row-wise optimisers ---------------------------------------------------------
  * Step 1  ttam_sort_rows: stable radix sort of the R touched row ids; sorted_idx[R], perm[R] (int32:

@@ -99,7 +99,7 @@ SIGNATURES = {
     "ttam_gate_bwd": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _p]),
     "ttam_augment_fwd": (C.c_int, [_p, _p, _i64, _p, _p, _p, _i64, _i64, _p]),
     "ttam_loss_workspace_bytes": (C.c_int64, [_i64]),
-    "ttam_loss_fwd_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _i64, _i64, _i64, _p, _i64, _p]),
+    "ttam_loss_fwd_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _i64, _i64, _i64, _f, _p, _i64, _p]),
     "ttam_sort_workspace_bytes": (C.c_int64, [_i64]),
     "ttam_sort_rows": (C.c_int, [_p, _i64, _i64, _p, _p, _p, _i64, _p]),
     "ttam_unique_rows": (C.c_int, [_p, _i64, _p, _p, _p, _i64, _p]),

@@ -8,7 +8,8 @@
 //   wgrad : A = x[gather(r), k'] as (k', r)  MN-major, B = dy[r, n'] as (n', r)  MN-major, reduction over the rows r,
 //           split over blockIdx.z, transposed partial store  part[z][n'][k']  (summed by splitk_reduce_kernel)
 // Operands stay fp32 in global memory; 8 producer warps copy them through registers (16-byte loads, round-to-nearest
-// TF32) into shared memory in the canonical 128-byte-swizzled UMMA layouts, 32 reduction steps per stage; one thread
+// TF32) into shared memory in the canonical swizzled UMMA layouts (K-major: SWIZZLE_128B; MN-major tf32:
+// SWIZZLE_128B_BASE32B, the only one the hardware accepts), 32 reduction steps per stage; one thread
 // issues 4 tcgen05.mma (M=128, N=bn, K=8) per stage; the producers then become the epilogue (tcgen05.ld, thread = row).
 // The layer-1 GEMMs are bound by L2->SM operand traffic (2.4 kB of features + the 465 kB weight per 128 rows), not by
 // the tensor pipe, which is why the operands are not down-converted further.
@@ -26,8 +27,7 @@ constexpr int kProdWarps = 8;
 constexpr int kProdThreads = 32 * kProdWarps;
 constexpr int kThreads = kProdThreads + 32;
 constexpr uint32_t kABytes = kBM * 128;  // 16 KB per stage
-constexpr uint32_t kAtomBytes = 1024;    // 8 rows x 128 B
-constexpr uint32_t kMnLbo = (kKC / 8) * kAtomBytes;  // MN-major: distance between 32-element atoms along M/N
+constexpr uint32_t kMnLbo = kKC * 128;   // MN-major: byte distance between 32-element atoms along M/N (32 rows x 128 B)
 
 struct TcP {
   const float* A;
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(TcP p) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int k = warp + 8 * j;
-          store_tf32x4(sA + (lane >> 3) * kMnLbo + (k >> 3) * kAtomBytes + (k & 7) * 128 + (((lane & 7) ^ (k & 7)) << 4), va[j]);
+          store_tf32x4(sA + mnmajor_tf32_offset(lane >> 3, k, lane & 7, kMnLbo), va[j]);
         }
       }
       if (!B_MN) {
@@ -218,8 +218,7 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(TcP p) {
           for (int h = 0; h < 2; ++h) {
             const int cc = lane + 32 * h;
             if (h < nb_mn && 4 * cc < bn)
-              store_tf32x4(sB + (cc >> 3) * kMnLbo + (k >> 3) * kAtomBytes + (k & 7) * 128 + (((cc & 7) ^ (k & 7)) << 4),
-                           vb[j * 2 + h]);
+              store_tf32x4(sB + mnmajor_tf32_offset(cc >> 3, k, cc & 7, kMnLbo), vb[j * 2 + h]);
           }
         }
       }
@@ -299,8 +298,9 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(TcP p) {
       const uint32_t sB = sA + kABytes;
 #pragma unroll
       for (int ks = 0; ks < kKC / 8; ++ks) {
-        const uint64_t ad = A_MN ? make_mnmajor_desc_sw128(sA + ks * kAtomBytes, kMnLbo, kAtomBytes) : make_kmajor_desc<128>(sA + ks * 32);
-        const uint64_t bd = B_MN ? make_mnmajor_desc_sw128(sB + ks * kAtomBytes, kMnLbo, kAtomBytes) : make_kmajor_desc<128>(sB + ks * 32);
+        // one MMA consumes 8 reduction steps: 32 bytes of a K-major row, or two 4-row groups (1024 B) of an MN-major tile
+        const uint64_t ad = A_MN ? make_mnmajor_desc_tf32(sA + ks * 1024, kMnLbo, 512) : make_kmajor_desc<128>(sA + ks * 32);
+        const uint64_t bd = B_MN ? make_mnmajor_desc_tf32(sB + ks * 1024, kMnLbo, 512) : make_kmajor_desc<128>(sB + ks * 32);
         umma_tf32(tmem_base, ad, bd, idesc, (c | ks) != 0 ? 1u : 0u);
       }
       umma_commit(empty + stage);

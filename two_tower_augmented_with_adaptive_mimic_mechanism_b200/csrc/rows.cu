@@ -371,8 +371,9 @@ extern "C" int64_t ttam_loss_workspace_bytes(int64_t B) { return B * 3 * (int64_
 extern "C" int ttam_loss_fwd_bwd(const float* o_u, const float* o_i, const float* t_u, const float* t_p,
                                  const float* q_u, const float* q_p, float lambda_u, float lambda_i, float* loss_out,
                                  float* do_u, float* do_i, float* dq_u, float* dq_p, int64_t B, int64_t N, int64_t D,
-                                 void* workspace, int64_t workspace_bytes, void* stream) {
+                                 float batch_fraction, void* workspace, int64_t workspace_bytes, void* stream) {
   TTAM_CHECK_ARG(o_u && o_i && loss_out && workspace, "loss: null pointer");
+  TTAM_CHECK_ARG(batch_fraction > 0.f && batch_fraction <= 1.f, "loss: batch_fraction must be in (0, 1]");
   TTAM_CHECK_ARG(B > 0 && N > 0 && N <= kMaxNeg && D > 0, "loss: need B>0, 0<N<=%d, D>0", kMaxNeg);
   TTAM_CHECK_ARG((q_u == nullptr) == (q_p == nullptr) && (q_u == nullptr) == (t_u == nullptr) &&
                      (q_u == nullptr) == (t_p == nullptr),
@@ -385,11 +386,12 @@ extern "C" int ttam_loss_fwd_bwd(const float* o_u, const float* o_i, const float
   }
   cudaStream_t s = (cudaStream_t)stream;
   const double M = (double)B * (double)(1 + N);
-  const float inv_M = (float)(1.0 / M);
-  const float inv_BD = (float)(1.0 / ((double)B * (double)D));
+  // data-parallel ranks each hold `batch_fraction` of the global batch: the means run over the global batch
+  const float inv_M = (float)((double)batch_fraction / M);
+  const float inv_BD = (float)((double)batch_fraction / ((double)B * (double)D));
   // dL/dq extra term: lambda * 2 (q - t) / (B*D)   (only when lambda > 0: training.py:800-803)
-  const float cu = lambda_u > 0.f ? (float)(2.0 * (double)lambda_u / ((double)B * (double)D)) : 0.f;
-  const float ci = lambda_i > 0.f ? (float)(2.0 * (double)lambda_i / ((double)B * (double)D)) : 0.f;
+  const float cu = lambda_u > 0.f ? (float)(2.0 * (double)lambda_u * (double)batch_fraction / ((double)B * (double)D)) : 0.f;
+  const float ci = lambda_i > 0.f ? (float)(2.0 * (double)lambda_i * (double)batch_fraction / ((double)B * (double)D)) : 0.f;
   const int threads = 256;
   const int blocks = (int)ceil_div(B * 32, threads);
   loss_kernel<<<blocks, threads, 0, s>>>(o_u, o_i, t_u, t_p, q_u, q_p, cu, ci, (float*)workspace, do_u, do_i, dq_u,

@@ -179,17 +179,25 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
   d |= layout << 61;                                 // [61,64) swizzle mode
   return d;
 }
-// MN-major operand tile, 128-byte swizzle: atoms of 8 reduction rows x 128 bytes (64 bf16 / 32 tf32 along M or N);
-// LBO = byte distance between atoms along M/N, SBO = byte distance between 8-row groups along K
-// (cute::UMMA::make_umma_desc<Major::MN>, LayoutType::B128: ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units).
-__device__ __forceinline__ uint64_t make_mnmajor_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// MN-major operand tile of 32-bit (tf32) elements.  The only legal shared-memory layout is "128-byte swizzle with
+// 32-byte atomicity" (cute::UMMA::Layout_MN_SW128_32B_Atom, LayoutType::SWIZZLE_128B_BASE32B = 1): atoms of
+// 4 reduction rows x 128 bytes (32 elements along M or N), the 32-byte chunk index of a row XOR-ed with the row index
+// (Swizzle<2,5,2> on the byte address).  LBO = byte distance between atoms along M/N, SBO = byte distance between
+// 4-row groups along K.
+__device__ __forceinline__ uint64_t make_mnmajor_desc_tf32(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)1 << 61;  // SWIZZLE_128B_BASE32B
   return d;
+}
+// byte offset of 16-byte chunk `c16` (0..7) of reduction row k inside an MN-major tf32 tile whose M/N atom `atom`
+// starts at atom * lbo (rows of one atom are contiguous groups of 4: 512 bytes per group)
+__device__ __forceinline__ uint32_t mnmajor_tf32_offset(int atom, int k, int c16, uint32_t lbo_bytes) {
+  return (uint32_t)atom * lbo_bytes + (uint32_t)(k >> 2) * 512u + (uint32_t)(k & 3) * 128u +
+         ((uint32_t)(((c16 >> 1) ^ (k & 3)) << 5)) + ((uint32_t)(c16 & 1) << 4);
 }
 // instruction descriptor, kind::f16 / kind::tf32, fp32 accumulate, both operands K-major
 // fmt: 0 = f16, 1 = bf16, 2 = tf32

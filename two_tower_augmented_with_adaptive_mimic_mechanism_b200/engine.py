@@ -147,9 +147,11 @@ class FusedEngine:
             F.lazy_rows(self.kind, tab.weight, tab.m, tab.v, tab.last_step, sorted_idx, perm, grad_a, grad_b,
                         long_list=long_list, **self._lazy_kw())
 
-    def _step_body(self, users, items, B, N, Xu, Xi):
+    # ---- the step, in three phases (the row-sharded engine runs phases 1 and 3 on the rows a rank OWNS and phase 2
+    # on the samples it was GIVEN, with an all-to-all in between; on one GPU they run back to back) -----------------
+    def _forward_phase(self, users, items, Xu, Xi):
+        """Sort + lazy catch-up + both towers for the rows `users` / `items` (row ids of THIS engine's tables)."""
         Xu, Xi = self._x(Xu), self._x(Xi)
-        launches0 = F.lib().ttam_launch_count()
         F.advance_step(self.state, rng_stride=1 << 36)
         T = self.tables
         sort_u = self._sort(users, "u", self.user.table.shape[0])
@@ -162,24 +164,38 @@ class FusedEngine:
                            rng_base=0, state=self.state, precision=self.precision, want_q=self.mimic)
         ci = tower_forward(self.item, items, Xi, gather=True, train=True, bufs=self.bufs_i, seed=self.seed,
                            rng_base=1 << 35, state=self.state, precision=self.precision, want_q=self.mimic)
-        D = cu.o.shape[1]
+        return dict(sort_u=sort_u, sort_i=sort_i, cu=cu, ci=ci)
+
+    def _loss_phase(self, o_u, o_i, t_u, t_p, q_u, q_p, items, B, N, batch_fraction=1.0):
+        """Fused loss forward + backward on one (local) batch.  Returns loss[4] and the gradient row blocks."""
+        D = o_u.shape[1]
         loss = self._misc("loss", (4,), torch.float32)
         do_u = self._misc("do_u", (B, D), torch.float32)
         do_i = self._misc("do_i", (B * (1 + N), D), torch.float32)
         dq_u = self._misc("dq_u", (B, D), torch.float32) if self.mimic else None
         dq_p = self._misc("dq_p", (B, D), torch.float32) if self.mimic else None
         if self.mimic:
-            F.loss_fwd_bwd(cu.o, ci.o, t_u=cu.t, t_p=ci.t[:B], q_u=cu.q, q_p=ci.q[:B], lambda_u=self.lambda_u,
-                           lambda_i=self.lambda_i, out=(loss, do_u, do_i, dq_u, dq_p))
+            F.loss_fwd_bwd(o_u, o_i, t_u=t_u, t_p=t_p, q_u=q_u, q_p=q_p, lambda_u=self.lambda_u,
+                           lambda_i=self.lambda_i, out=(loss, do_u, do_i, dq_u, dq_p), batch_fraction=batch_fraction)
         else:
-            F.loss_fwd_bwd(cu.o, ci.o, out=(loss, do_u, do_i, None, None))
+            F.loss_fwd_bwd(o_u, o_i, out=(loss, do_u, do_i, None, None), batch_fraction=batch_fraction)
         if self.lambda_c > 0 and self.cat_tensor is not None and self.major is not None:
-            cal, gcal = category_alignment(items, ci.o, self.cat_tensor, self.major)
+            if batch_fraction != 1.0:
+                raise NotImplementedError("category-alignment loss is not available with a sharded batch")
+            cal, gcal = category_alignment(items, o_i, self.cat_tensor, self.major)
             loss[0] += self.lambda_c * cal
             if gcal is not None:
                 do_i.add_(gcal, alpha=self.lambda_c)
                 if self.mimic:
                     dq_p.add_(gcal[:B], alpha=self.lambda_c)
+        return loss, do_u, do_i, dq_u, dq_p
+
+    def _backward_phase(self, ctx, do_u, do_i, dq_user, dq_item, dense_grad_hook=None):
+        """Tower backward for the rows of `ctx`, row-wise table updates, dense optimiser.
+        dq_user / dq_item: gradient rows of the augmentation tables, each a tensor or a (first rows, other rows) pair.
+        dense_grad_hook(list of gradient tensors): called before the dense optimiser (data-parallel all-reduce)."""
+        T = self.tables
+        sort_u, sort_i, cu, ci = ctx["sort_u"], ctx["sort_i"], ctx["cu"], ctx["ci"]
         grads: dict = {}
         de_i = tower_backward(self.item, ci, do_i, grads, bufs=self.bufs_i, state=self.state, precision=self.precision)
         de_u = tower_backward(self.user, cu, do_u, grads, bufs=self.bufs_u, state=self.state, precision=self.precision)
@@ -187,8 +203,9 @@ class FusedEngine:
         self._update_table(T["user_encoder.embedding.weight"], sort_u, de_u)
         self._update_table(T["item_encoder.embedding.weight"], sort_i, de_i)
         if self.mimic:
-            self._update_table(T["adaptive_mimic.user_augmented.weight"], sort_u, dq_u)
-            self._update_table(T["adaptive_mimic.item_augmented.weight"], sort_i, dq_p, do_i[B:])
+            pair = lambda g: g if isinstance(g, tuple) else (g, None)
+            self._update_table(T["adaptive_mimic.user_augmented.weight"], sort_u, *pair(dq_user))
+            self._update_table(T["adaptive_mimic.item_augmented.weight"], sort_i, *pair(dq_item))
         # ---- dense optimiser on the MLP / gate / projection tensors that received a gradient
         ps, gs, ms, vs = [], [], [], []
         for j, p in enumerate(self.dense):
@@ -201,10 +218,22 @@ class FusedEngine:
             if self.dense_v is not None:
                 vs.append(self.dense_v[j])
         if ps:
+            if dense_grad_hook is not None:
+                dense_grad_hook(gs)
             F.dense_step(self.kind, ps, gs, ms if self.dense_m is not None else None,
                          vs if self.dense_v is not None else None, lr=self.lr, weight_decay=self.wd,
                          betas=self.dense_betas, eps=self.eps, momentum=self.momentum, step=self.t,
                          scalars=self.scal_dense, state=self.state)
+
+    def _step_body(self, users, items, B, N, Xu, Xi):
+        launches0 = F.lib().ttam_launch_count()
+        ctx = self._forward_phase(users, items, Xu, Xi)
+        cu, ci = ctx["cu"], ctx["ci"]
+        if self.mimic:
+            loss, do_u, do_i, dq_u, dq_p = self._loss_phase(cu.o, ci.o, cu.t, ci.t[:B], cu.q, ci.q[:B], items, B, N)
+        else:
+            loss, do_u, do_i, dq_u, dq_p = self._loss_phase(cu.o, ci.o, None, None, None, None, items, B, N)
+        self._backward_phase(ctx, do_u, do_i, dq_u, (dq_p, do_i[B:]) if self.mimic else None)
         self.launches_per_step = F.lib().ttam_launch_count() - launches0
         return loss
 

@@ -202,7 +202,7 @@ def augment_fwd(t, aug_table, idx, *, out, q_out=None):
 
 
 def loss_fwd_bwd(o_u, o_i, *, t_u=None, t_p=None, q_u=None, q_p=None, lambda_u=0.0, lambda_i=0.0, backward=True,
-                 out=None):
+                 out=None, batch_fraction=1.0):
     """o_i = [positives (B rows); negatives (B*N rows, [B,N] row-major)].  Returns (loss[4], do_u, do_i, dq_u, dq_p)."""
     _chk(o_u, torch.float32, "o_u"); _chk(o_i, torch.float32, "o_i")
     B, D = o_u.shape
@@ -220,7 +220,7 @@ def loss_fwd_bwd(o_u, o_i, *, t_u=None, t_p=None, q_u=None, q_p=None, lambda_u=0
     ws = workspace(lib().ttam_loss_workspace_bytes(B), dev, "loss")
     check(lib().ttam_loss_fwd_bwd(o_u.data_ptr(), o_i.data_ptr(), _ptr(t_u), _ptr(t_p), _ptr(q_u), _ptr(q_p),
                                   float(lambda_u), float(lambda_i), loss.data_ptr(), _ptr(do_u), _ptr(do_i), _ptr(dq_u),
-                                  _ptr(dq_p), B, N, D, ws.data_ptr(), ws.numel(), _stream()), "loss_fwd_bwd")
+                                  _ptr(dq_p), B, N, D, float(batch_fraction), ws.data_ptr(), ws.numel(), _stream()), "loss_fwd_bwd")
     return loss, do_u, do_i, dq_u, dq_p
 
 
