@@ -1,0 +1,191 @@
+"""N-rank host logic on CPU: sharding arithmetic, the all-to-all row exchange and the sharded training step
+(world_size 2, gloo), the item-sharded top-K merge.  The compute inside the step is the numpy oracle
+(tests/sharding_backend.py); what is under test is routing, ordering, global-batch normalisation and the
+dense-gradient all-reduce of `ShardedEngine` — the code the GPU path runs unchanged over NCCL."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+sys.path.insert(0, str(Path(__file__).resolve().parent))
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+
+import oracle  # noqa: E402
+from helpers import load_case  # noqa: E402
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _spawn(fn, world, *args):
+    port = _free_port()
+    mp.spawn(_entry, args=(world, port, fn, args), nprocs=world, join=True)
+
+
+def _entry(rank, world, port, fn, args):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        fn(rank, world, *args)
+    finally:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------
+def test_shard_arithmetic_roundtrip():
+    from two_tower_augmented_with_adaptive_mimic_mechanism_b200 import sharding as S
+    for n, W in [(10, 3), (7, 8), (64, 4), (1, 2)]:
+        full = torch.arange(n * 2).view(n, 2)
+        shards = [S.shard_rows(full, r, W) for r in range(W)]
+        assert [s.shape[0] for s in shards] == [S.shard_size(n, r, W) for r in range(W)]
+        assert torch.equal(S.unshard_rows(shards), full)
+        idx = torch.arange(n)
+        for r in range(W):
+            mine = idx[S.owner_of(idx, W) == r]
+            assert torch.equal(full[mine], shards[r][S.local_row(mine, W)])
+            assert torch.equal(S.global_row(S.local_row(mine, W), r, W), mine)
+
+
+def test_exchange_world1_is_identity():
+    from two_tower_augmented_with_adaptive_mimic_mechanism_b200 import sharding as S
+    idx = torch.tensor([5, 1, 5, 0])
+    ex = S.Exchange(idx, 1)
+    rows = torch.randn(4, 3)
+    assert torch.equal(ex.local_rows, idx) and ex.to_requester(rows) is rows and ex.to_owner(rows) is rows
+
+
+def _exchange_worker(rank, world):
+    from two_tower_augmented_with_adaptive_mimic_mechanism_b200 import sharding as S
+    g = torch.Generator().manual_seed(100 + rank)
+    n_rows = 37
+    table = torch.arange(n_rows * 3, dtype=torch.float32).view(n_rows, 3)          # the same "global table" on every rank
+    shard = S.shard_rows(table, rank, world)
+    for R in (1, 8, 50 + 7 * rank):                                               # ragged: ranks request different counts
+        idx = torch.randint(0, n_rows, (R,), generator=g)
+        if R == 8:
+            idx[:] = rank                                                         # every row to a single owner
+        ex = S.Exchange(idx, world)
+        assert torch.equal(S.owner_of(ex.recv_idx, world), torch.full_like(ex.recv_idx, rank))
+        got = ex.to_requester(shard[ex.local_rows])                               # owner-side gather, routed back
+        assert torch.equal(got, table[idx])
+        # gradients: what the owner receives, accumulated by local row, equals the global scatter-add restricted to it
+        grads = torch.randn(R, 3, generator=g)
+        recv = ex.to_owner(grads)
+        acc = torch.zeros_like(shard).index_add_(0, ex.local_rows, recv)
+        all_idx = [torch.empty(0, dtype=torch.int64)] * world
+        all_g = [None] * world
+        dist.all_gather_object(all_idx, idx)
+        dist.all_gather_object(all_g, grads)
+        full = torch.zeros_like(table)
+        for i, gr in zip(all_idx, all_g):
+            full.index_add_(0, i, gr)
+        torch.testing.assert_close(acc, S.shard_rows(full, rank, world), rtol=1e-6, atol=1e-6)
+    flat = [torch.full((3,), float(rank + 1)), torch.full((2, 2), float(10 * (rank + 1)))]
+    S.all_reduce_flat(flat)
+    assert torch.equal(flat[0], torch.full((3,), 3.0)) and torch.equal(flat[1], torch.full((2, 2), 30.0))
+
+
+def test_exchange_roundtrip_world2():
+    _spawn(_exchange_worker, 2)
+
+
+# ---------------------------------------------------------------------------------------------
+def _train_worker(rank, world, case, steps, out_dir):
+    from sharding_backend import OracleEngine, shard_state
+    from two_tower_augmented_with_adaptive_mimic_mechanism_b200 import sharding as S
+    from two_tower_augmented_with_adaptive_mimic_mechanism_b200.sharded import ShardedEngine
+    d, meta, init = load_case(case)
+    lu, li, _ = meta["lambdas"]
+    eng = OracleEngine(shard_state(init, rank, world), lr=meta["lr"], weight_decay=meta["wd"], betas=meta["betas"],
+                       lambdas=(lu, li))
+    sh = ShardedEngine(eng)
+    ux = S.shard_rows(torch.from_numpy(d["user_x"]), rank, world) if "user_x" in d and d["user_x"].size else None
+    ix = S.shard_rows(torch.from_numpy(d["item_x"]), rank, world) if "item_x" in d and d["item_x"].size else None
+    losses = []
+    for s in range(steps):
+        u, p, n = (torch.from_numpy(d[f"step{s}/{k}"]) for k in ("users", "pos", "neg"))
+        B = u.shape[0] // world
+        sl = slice(rank * B, (rank + 1) * B)
+        share = sh.train_step(u[sl], p[sl], n[sl], ux, ix)
+        losses.append(sh.global_loss(share).numpy())
+    np.savez(Path(out_dir) / f"rank{rank}.npz", losses=np.stack(losses), **{"st/" + k: v for k, v in eng.state.items()},
+             **{"touched/" + k: v for k, v in eng.touched.items()})
+
+
+@pytest.mark.parametrize("case", ["train_gated_mlp", "train_embedding_only"])
+def test_sharded_step_world2_equals_single_process(case, tmp_path):
+    """Two ranks, each with half of the batch and half of the rows == the one-process oracle on the whole batch:
+    touched-row sets bit-exact (after mapping local rows back to global ids), values within fp32 summation tolerance."""
+    from sharding_backend import TABLES, unshard_state
+    world, steps = 2, 2
+    d, meta, init = load_case(case)
+    if (d["step0/users"].shape[0] // world) * world != d["step0/users"].shape[0]:
+        pytest.skip("batch not divisible")
+    _spawn(_train_worker, world, case, steps, str(tmp_path))
+    ranks = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
+    got = unshard_state([{k[3:]: z[k] for k in z.files if k.startswith("st/")} for z in ranks])
+    ref_state = {k: v.copy() for k, v in init.items()}
+    spec, opt = oracle.spec_from_state(ref_state), oracle.OptState()
+    lu, li, _ = meta["lambdas"]
+    has_x = "user_x" in d and d["user_x"].size
+    for s in range(steps):
+        ref = oracle.train_step(ref_state, opt, spec, d[f"step{s}/users"], d[f"step{s}/pos"], d[f"step{s}/neg"],
+                                d["user_x"] if has_x else None, d["item_x"] if has_x else None, lr=meta["lr"],
+                                weight_decay=meta["wd"], betas=meta["betas"], lambdas=(lu, li, 0.0))
+        for z in ranks:                                        # every rank reports the same global loss
+            assert z["losses"][s][0] == pytest.approx(ref["loss"], rel=2e-6)
+            assert z["losses"][s][1] == pytest.approx(ref["bce"], rel=2e-6)
+    for k, v in ref_state.items():
+        np.testing.assert_allclose(got[k], v, rtol=2e-5, atol=2e-7, err_msg=k)
+    for tab in TABLES[:2]:                                     # SparseAdam touched rows of the last step, as global ids
+        glob = np.sort(np.concatenate([ranks[r]["touched/" + tab] * world + r for r in range(world)]))
+        assert np.array_equal(glob, ref["touched"][tab])
+
+
+# ---------------------------------------------------------------------------------------------
+def _np_merge(ids, scores, k):
+    """(-score, +id) W-way merge in numpy (stands in for ttam_topk_merge on CPU)."""
+    q = ids.shape[0]
+    ids2, sc2 = ids.reshape(q, -1).numpy(), scores.reshape(q, -1).numpy()
+    out_i, out_s = np.empty((q, k), np.int64), np.empty((q, k), np.float32)
+    for r in range(q):
+        order = np.lexsort((ids2[r], -sc2[r]))[:k]
+        out_i[r], out_s[r] = ids2[r][order], sc2[r][order]
+    return torch.from_numpy(out_i), torch.from_numpy(out_s)
+
+
+def _topk_worker(rank, world, out_dir):
+    from two_tower_augmented_with_adaptive_mimic_mechanism_b200 import sharding as S
+    rng = np.random.default_rng(3)
+    Q, NI, D, K = 8, 101, 16, 10
+    q = rng.standard_normal((Q, D)).astype(np.float32)
+    items = rng.standard_normal((NI, D)).astype(np.float32)
+    items[50] = items[3]; items[77] = items[3]                                  # exact ties across shards
+    scores = oracle.canonical_scores(q, items)
+    mine = np.arange(rank, NI, world)
+    li, ls = oracle.topk_canonical(scores[:, mine], K, ids=mine)                 # local top-K with global ids
+    ids, sc = S.merge_topk_shards(torch.from_numpy(li), torch.from_numpy(ls), K, _np_merge)
+    np.savez(Path(out_dir) / f"topk{rank}.npz", ids=ids.numpy(), sc=sc.numpy())
+
+
+def test_item_sharded_topk_merge_world2(tmp_path):
+    _spawn(_topk_worker, 2, str(tmp_path))
+    rng = np.random.default_rng(3)
+    Q, NI, D, K = 8, 101, 16, 10
+    q = rng.standard_normal((Q, D)).astype(np.float32)
+    items = rng.standard_normal((NI, D)).astype(np.float32)
+    items[50] = items[3]; items[77] = items[3]
+    ref_i, ref_s = oracle.topk_canonical(oracle.canonical_scores(q, items), K)
+    got_i = np.concatenate([np.load(tmp_path / f"topk{r}.npz")["ids"] for r in range(2)])
+    got_s = np.concatenate([np.load(tmp_path / f"topk{r}.npz")["sc"] for r in range(2)])
+    assert np.array_equal(got_i, ref_i) and np.array_equal(got_s, ref_s)

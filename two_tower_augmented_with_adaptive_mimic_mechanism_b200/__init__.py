@@ -14,8 +14,9 @@ from .models import (  # noqa: F401
     build_tower_encoder,
 )
 from .engine import FusedEngine  # noqa: F401
-from . import functional, hooks, retrieval  # noqa: F401
+from .sharded import ShardedEngine, ShardedFlatIPIndex, build_sharded_engine  # noqa: F401
+from . import functional, hooks, retrieval, sharding  # noqa: F401
 
 __all__ = ["AdaptiveMimicMechanism", "FeatureFusionGate", "TowerEncoder", "TwoTowerModel", "build_feature_encoder",
            "build_id_embedding", "build_tower_encoder", "FusedEngine", "TtamError", "build", "lib", "functional",
-           "hooks", "retrieval"]
+           "hooks", "retrieval", "sharding", "ShardedEngine", "ShardedFlatIPIndex", "build_sharded_engine"]

@@ -237,6 +237,13 @@ class FusedEngine:
         self.launches_per_step = F.lib().ttam_launch_count() - launches0
         return loss
 
+    def begin_step(self) -> None:
+        """Advance the host-side step counter (the device-side one advances inside the forward phase)."""
+        if self.t + 1 > self.max_steps:
+            raise RuntimeError(f"max_steps={self.max_steps} exhausted; build the engine with a larger max_steps")
+        self.t += 1
+        self.dirty = True
+
     @torch.no_grad()
     def train_step(self, users: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor, user_x, item_x, *,
                    graph: bool = False) -> torch.Tensor:
