@@ -198,6 +198,7 @@ def main():
 
     import two_tower_augmented_with_adaptive_mimic_mechanism_b200 as tt
     from two_tower_augmented_with_adaptive_mimic_mechanism_b200 import functional as F
+    from two_tower_augmented_with_adaptive_mimic_mechanism_b200 import sharding as S
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
@@ -206,17 +207,25 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     torch.manual_seed(1234 + rank)
-    user_x, item_x = make_features(c["NI"], c["NU"], c["F"], c["n_cat"], c["n_auth"], dev, gen)
+    # N > 1: tables, optimiser state and feature matrices are ROW-SHARDED (row r on rank r % N), the batch is
+    # data-parallel with B samples per rank (weak scaling): SURVEY 8(e).  N = 1: everything on the one GPU.
+    nu_l, ni_l = S.shard_size(c["NU"], rank, world), S.shard_size(c["NI"], rank, world)
+    user_x, item_x = make_features(ni_l, nu_l, c["F"], c["n_cat"], c["n_auth"], dev, gen)
     tower = {"type": "tower", "id_embedding": {"params": {"embedding_dim": c["D"], "sparse": True}},
              "feature_encoder": {"type": "mlp", "hidden_dims": [c["H"]], "activation": "relu", "output_dim": c["D"], "dropout": 0.0},
              "fusion": "gated", "adaptive_mimic": {"hidden_dim": c["Hg"]}}
-    model = tt.TwoTowerModel(tt.build_tower_encoder(tower, num_embeddings=c["NU"], feature_dim=c["F"], device=dev),
-                             tt.build_tower_encoder(tower, num_embeddings=c["NI"], feature_dim=c["F"], device=dev),
-                             adaptive_mimic=tt.AdaptiveMimicMechanism(num_users=c["NU"], num_items=c["NI"], embedding_dim=c["D"]).to(dev))
+    model = tt.TwoTowerModel(tt.build_tower_encoder(tower, num_embeddings=nu_l, feature_dim=c["F"], device=dev),
+                             tt.build_tower_encoder(tower, num_embeddings=ni_l, feature_dim=c["F"], device=dev),
+                             adaptive_mimic=tt.AdaptiveMimicMechanism(num_users=nu_l, num_items=ni_l, embedding_dim=c["D"]).to(dev))
+    if world > 1:                      # replicas of the dense weights start identical
+        for name, prm in model.named_parameters():
+            if "embedding.weight" not in name and "augmented.weight" not in name:
+                dist.broadcast(prm.data, src=0)
     eng = tt.FusedEngine(model, optimizer="adamw", lr=c["lr"], weight_decay=c["wd"], precision=args.precision,
                          loss_weights={"mimic_user": c["lambdas"][0], "mimic_item": c["lambdas"][1]},
                          max_steps=4 * (K + W) + 64)
-    users, pos, neg = make_batches(K + W, c, dev, gen)
+    sh = tt.ShardedEngine(eng) if world > 1 else None
+    users, pos, neg = make_batches(K + W, c, dev, gen)          # global row ids
     h_users, h_pos, h_neg = (t.cpu().pin_memory() for t in (users, pos, neg))
 
     def barrier():
@@ -224,15 +233,21 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: inputs resident in HBM, graph replay
+    def step(u, p, n):
+        if sh is not None:
+            return sh.train_step(u, p, n, user_x, item_x)
+        return eng.train_step(u, p, n, user_x, item_x, graph=True)
+
+    # ---- value: batch index tensors resident in HBM (N = 1: CUDA-graph replay of the step)
+    launches0 = F.lib().ttam_launch_count()
     for s in range(W):
-        eng.train_step(users[s], pos[s], neg[s], user_x, item_x, graph=True)
+        step(users[s], pos[s], neg[s])
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
         e0.record()
         for s in range(W, W + K):
-            eng.train_step(users[s], pos[s], neg[s], user_x, item_x, graph=True)
+            step(users[s], pos[s], neg[s])
         e1.record()
         barrier()
     ms = e0.elapsed_time(e1)
@@ -244,7 +259,7 @@ def main():
     f0.record()
     for s in range(W, W + K):
         d_u.copy_(h_users[s], non_blocking=True); d_p.copy_(h_pos[s], non_blocking=True); d_n.copy_(h_neg[s], non_blocking=True)
-        loss = eng.train_step(d_u, d_p, d_n, user_x, item_x, graph=True)
+        loss = step(d_u, d_p, d_n)
         loss_host.copy_(loss, non_blocking=True)
         torch.cuda.current_stream().synchronize()          # the caller reads the loss every step (training.py:830)
     f1.record()
@@ -256,10 +271,12 @@ def main():
     ms, ms_e2e = float(t[0]), float(t[1])
     B, N, D, Fd, H = c["B"], c["N"], c["D"], c["F"], c["H"]
 
-    # ---- roofline of the dominant kernel: layer-1 of the item tower (fused feature gather + GEMM)
+    # ---- roofline of the dominant kernel: layer 1 of the item tower (feature-row gather fused into the GEMM loader)
     pk = peaks()
-    items_idx = torch.cat([pos[W], neg[W].reshape(-1)])
+    items_idx = torch.cat([pos[W], neg[W].reshape(-1)]) % ni_l
     W1, b1 = eng.item.fe_layers[0]
+    Xi = eng._x(item_x)
+    W1p = F.pad_cols(W1) if args.precision != "fp32" else W1
     hd = torch.empty((items_idx.numel(), H), device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -267,7 +284,7 @@ def main():
     for _ in range(5):
         flush.zero_()
         k0.record()
-        F.linear_fwd(item_x, W1, b1, gather=items_idx, act="relu", out=hd, precision=args.precision)
+        F.linear_fwd(Xi, W1p, b1, gather=items_idx, act="relu", out=hd, precision=args.precision)
         k1.record()
         torch.cuda.synchronize()
         tk += k0.elapsed_time(k1)
@@ -275,26 +292,31 @@ def main():
     R = items_idx.numel()
     flops = 2.0 * R * Fd * H
     bytes_alg = R * (Fd * 4 + 8) + H * Fd * 4 + R * H * 4
-    hbm_time, tensor_time = bytes_alg / (pk["hbm"] * 1e9), flops / (pk["tf"] * 1e12)
-    if hbm_time >= tensor_time:
-        roof = {"bound": "hbm", "achieved": bytes_alg / (tk * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s"}
-    else:
-        roof = {"bound": "tensor", "achieved": flops / (tk * 1e-3) / 1e12, "peak": pk["tf"], "unit": "TFLOP/s"}
+    roof = {"bound": "hbm", "achieved": bytes_alg / (tk * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s"}
     roof.update(frac=roof["achieved"] / roof["peak"], traffic=None, kernel="item tower layer 1: X[idx] . W1^T + b1, relu",
-                kernel_ms=tk, peak_source=pk["source"], algorithmic_bytes=bytes_alg, algorithmic_flops=flops)
+                kernel_ms=tk, peak_source=pk["source"], algorithmic_bytes=bytes_alg, algorithmic_flops=flops,
+                tensor_tflops=flops / (tk * 1e-3) / 1e12)
 
+    steps_launched = 2 * K + W
     line = {"metric": "train samples/sec", "value": world * K * B / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32", "bf16": "bf16"}[args.precision], "data": "synthetic",
-            "config": {"workload": workload, "parallelism": "1 gpu" if world == 1 else f"{world} independent replicas (weak)",
+            "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32"}[args.precision], "data": "synthetic",
+            "config": {"workload": workload,
+                       "parallelism": "1 gpu, CUDA-graph replay" if world == 1 else
+                       f"{world} gpus: tables/features row-sharded, batch data-parallel ({B} samples per gpu), 3 all-to-all + 1 all-reduce per step",
                        "l2_policy": "inputs larger than L2: each step gathers from 11.8 GB of tables/features"},
             "e2e": {"value": world * K * B / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": B * 8 * (2 + N),
                     "d2h_bytes_per_step": 16},
             "gpu_launches": None, "clocks": clk.summary(), "roofline": roof}
-    line["gpu_launches"] = int(getattr(eng, "launches_per_step", 0)) * K
+    if world == 1:
+        line["gpu_launches"] = int(getattr(eng, "launches_per_step", 0)) * K
+    else:
+        line["gpu_launches"] = int((F.lib().ttam_launch_count() - launches0) * K / steps_launched)
 
-    if rank == 0 and not args.no_retrieval:
-        line["retrieval"] = bench_retrieval(tt, c, dev, pk)
+    if not args.no_retrieval:
+        r = bench_retrieval(tt, c, dev, pk, world=world, rank=rank)
+        if rank == 0:
+            line["retrieval"] = r
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         del eng, model, user_x, item_x
         torch.cuda.empty_cache()
@@ -307,17 +329,41 @@ def main():
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
-def bench_retrieval(tt, c, dev, pk, Q=100_000, NI=2_000_000, K=100):
-    """top-100 over the full 2M x 96 corpus (BASELINE configs[2]); Q queries per launch sequence."""
+def bench_retrieval(tt, c, dev, pk, Q=100_000, NI=2_000_000, K=100, world=1, rank=0):
+    """top-100 over the full 2M x 96 corpus (BASELINE configs[2]); Q queries per launch sequence.  N > 1: the corpus is
+    item-sharded (NI/N contiguous items per rank), every rank scores all Q queries against its shard and merges the
+    lists of its own query block after an all-to-all."""
     from two_tower_augmented_with_adaptive_mimic_mechanism_b200 import functional as F
-    g = torch.Generator(device=dev).manual_seed(7)
+    import torch.distributed as dist
+    g = torch.Generator(device=dev).manual_seed(7)              # same corpus / queries on every rank
     items = (torch.randn((NI, c["D"]), device=dev, generator=g) * 0.3)
-    q = (torch.randn((Q, c["D"]), device=dev, generator=g) * 0.3)
+    q = (torch.randn((Q - Q % world, c["D"]), device=dev, generator=g) * 0.3)
     out = {}
+    if world > 1:
+        per = (NI + world - 1) // world
+        lo, hi = rank * per, min(NI, (rank + 1) * per)
+        index = tt.ShardedFlatIPIndex(items[lo:hi].contiguous(), dtype=torch.bfloat16, contiguous_offset=lo)
+        del items
+        index.search(q, K)
+        dist.barrier(); torch.cuda.synchronize()
+        best = float("inf")
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); index.search(q, K); e1.record()
+            dist.barrier(); torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            best = min(best, float(t[0]))
+        flops = 2.0 * q.shape[0] * NI * c["D"]
+        out["bf16"] = {"queries_per_s": q.shape[0] / (best * 1e-3), "ms": best, "queries": q.shape[0], "items": NI,
+                       "items_per_gpu": hi - lo, "tflops": flops / (best * 1e-3) / 1e12,
+                       "frac_of_bf16_peak": flops / (best * 1e-3) / 1e12 / (pk["tf"] * world)}
+        return out
     for name, (qi, it) in {"bf16": (q.bfloat16(), items.bfloat16()), "f32": (q[:1024], items)}.items():
         try:
             F.topk(qi, it, K)                          # warm-up at the timed shape (sizes the workspace)

@@ -145,7 +145,7 @@ def test_fused_step_tf32_tensor_cores_within_tolerance(graph):
     for k in ref_state:
         d = np.abs(got[k] - ref_state[k])
         assert d.max() <= 2.5e-3 * len(batches), (k, d.max())
-        assert (d > 3e-4 * len(batches)).mean() <= 1e-3, (k, (d > 3e-4 * len(batches)).mean())
+        assert (d > 3e-4 * len(batches)).sum() <= max(2, 1e-3 * d.size), (k, (d > 3e-4 * len(batches)).sum(), d.size)
         assert d.mean() <= 2e-5, (k, d.mean())
     touched = np.unique(np.concatenate([b[0] for b in batches]))
     changed = np.nonzero((got["user_encoder.embedding.weight"] != st["user_encoder.embedding.weight"]).any(1))[0]

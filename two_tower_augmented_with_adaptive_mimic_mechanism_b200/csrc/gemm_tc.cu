@@ -7,14 +7,16 @@
 //   dgrad : A = dy[m, n']        K-major        B = w[n', k'] as (k', n')  MN-major   mask + scale (+ accumulate) epilogue
 //   wgrad : A = x[gather(r), k'] as (k', r)  MN-major, B = dy[r, n'] as (n', r)  MN-major, reduction over the rows r,
 //           split over blockIdx.z, transposed partial store  part[z][n'][k']  (summed by splitk_reduce_kernel)
-// Operands stay fp32 in global memory; 8 producer warps copy them through registers (16-byte loads, round-to-nearest
-// TF32) into shared memory in the canonical swizzled UMMA layouts (K-major: SWIZZLE_128B; MN-major tf32:
+// Operands stay fp32 in global memory; 8 producer warps copy them with cp.async (16-byte LDGSTS, stages-1 chunks in
+// flight per thread, zero-filled tails), round each landed piece to TF32 (nearest) in place, and publish the stage
+// into shared memory in the canonical swizzled UMMA layouts (K-major: SWIZZLE_128B; MN-major tf32:
 // SWIZZLE_128B_BASE32B, the only one the hardware accepts), 32 reduction steps per stage; one thread
 // issues 4 tcgen05.mma (M=128, N=bn, K=8) per stage; the producers then become the epilogue (tcgen05.ld, thread = row).
 // The layer-1 GEMMs are bound by L2->SM operand traffic (2.4 kB of features + the 465 kB weight per 128 rows), not by
 // the tensor pipe, which is why the operands are not down-converted further.
 #include "gemm_tc.cuh"
 #include "sm100.cuh"
+#include <cstdlib>
 
 namespace ttam {
 namespace tcg {
@@ -60,28 +62,91 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
   return u;
 }
 
-// 4 consecutive floats starting at src (elements >= n_valid are zero); `vec` = a 16-byte load is legal
-__device__ __forceinline__ float4 load4(const float* src, int n_valid, bool vec) {
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (n_valid <= 0) return v;
-  if (vec) {
-    v = ld_f4(src);
-    if (n_valid < 4) {
-      if (n_valid < 2) v.y = 0.f;
-      if (n_valid < 3) v.z = 0.f;
-      v.w = 0.f;
-    }
-  } else {
-    v.x = src[0];
-    if (n_valid > 1) v.y = src[1];
-    if (n_valid > 2) v.z = src[2];
-    if (n_valid > 3) v.w = src[3];
+// ---- asynchronous global -> shared copies (LDGSTS): no registers, many chunks in flight per thread -------------------
+// 16-byte copy; bytes past `valid_bytes` (0..16) are zero-filled; valid_bytes == 0 reads nothing
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int valid_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, int valid_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(valid_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_pending(int n) {  // wait until at most n groups are pending
+  switch (n) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
   }
-  return v;
+}
+// one 16-byte piece: 4 floats starting at src, the first n_valid of them real (aligned source -> one 16-byte copy)
+__device__ __forceinline__ void copy_piece(uint32_t dst, const float* src, int n_valid, bool vec, const float* safe) {
+  n_valid = n_valid < 0 ? 0 : (n_valid > 4 ? 4 : n_valid);
+  if (n_valid == 0) src = safe;
+  if (vec) {
+    cp_async16(dst, src, n_valid * 4);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) cp_async4(dst + 4 * e, e < n_valid ? src + e : safe, e < n_valid ? 4 : 0);
+  }
+}
+// round the 4 floats of a landed piece to TF32 (nearest) in place: the tensor core would truncate otherwise
+__device__ __forceinline__ void round_piece(uint8_t* ptr) {
+  float4 v = *reinterpret_cast<float4*>(ptr);
+  *reinterpret_cast<uint4*>(ptr) = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
 }
 
-__device__ __forceinline__ void store_tf32x4(uint8_t* dst, const float4& v) {
-  *reinterpret_cast<uint4*>(dst) = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+// The 16-byte pieces of one stage that THIS thread copies (and later rounds).  f(byte offset in the stage, source
+// pointer or nullptr, number of valid floats).  K-major tile: piece id = t + 256 j -> row (t >> 3) + 32 j, 16-byte chunk
+// t & 7 of the row's 128 bytes.  MN-major tile: warp w owns reduction rows w + 8 j, lanes walk the chunks along M/N.
+template <bool A_MN, bool B_MN, bool WITH_SRC, class Fn>
+__device__ __forceinline__ void for_each_piece(const TcP& p, int t, int m0, int n0, int k0, int k_hi, const float* const (&a_ptr)[4],
+                                               Fn&& f) {
+  const int warp = t >> 5, lane = t & 31;
+  const int kc = t & 7, krow = t >> 3;
+  const int bn = p.bn;
+  if (!A_MN) {
+    const int kq = k0 + 4 * kc;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int row = krow + 32 * j;
+      f((uint32_t)(row * 128 + ((kc ^ (row & 7)) << 4)), (WITH_SRC && a_ptr[j]) ? a_ptr[j] + kq : nullptr, a_ptr[j] ? k_hi - kq : 0);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = warp + 8 * j, kk = k0 + k, m = m0 + 4 * lane;
+      const float* src = nullptr;
+      if (WITH_SRC && kk < k_hi) src = p.A + (p.gatherA ? p.gatherA[kk] : (int64_t)kk) * p.lda + m;
+      f(mnmajor_tf32_offset(lane >> 3, k, lane & 7, kMnLbo), src, kk < k_hi ? p.M - m : 0);
+    }
+  }
+  if (!B_MN) {
+    const int kq = k0 + 4 * kc;
+    const int nb_k = bn >> 5;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < nb_k) {
+        const int row = krow + 32 * j, n = n0 + row;
+        f(kABytes + (uint32_t)(row * 128 + ((kc ^ (row & 7)) << 4)), (WITH_SRC && n < p.N) ? p.B + (int64_t)n * p.ldb + kq : nullptr,
+          n < p.N ? k_hi - kq : 0);
+      }
+    }
+  } else {
+    const int nb_mn = (bn + 127) >> 7;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = warp + 8 * j, kk = k0 + k;
+      const float* row_ptr = nullptr;
+      if (WITH_SRC && kk < k_hi) row_ptr = p.B + (p.gatherB ? p.gatherB[kk] : (int64_t)kk) * p.ldb;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int cc = lane + 32 * h, n = n0 + 4 * cc;
+        if (h < nb_mn && 4 * cc < bn)
+          f(kABytes + mnmajor_tf32_offset(cc >> 3, k, cc & 7, kMnLbo), row_ptr ? row_ptr + n : nullptr, kk < k_hi ? p.N - n : 0);
+      }
+    }
+  }
 }
 
 template <bool A_MN, bool B_MN>
@@ -89,8 +154,7 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(TcP p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int bn = p.bn;
-  const uint32_t b_bytes = (uint32_t)bn * 128u;
-  const uint32_t stage_bytes = kABytes + b_bytes;
+  const uint32_t stage_bytes = kABytes + (uint32_t)bn * 128u;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (uint32_t)p.stages * stage_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + p.stages;
@@ -123,105 +187,37 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(TcP p) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < kProdWarps) {
-    // ===================== producers: global -> registers -> swizzled shared memory =====================
-    // K-major tile: chunk id = t + 256 j  ->  row = (t >> 3) + 32 j, 16-byte chunk c = t & 7 of the row's 128 bytes
-    // MN-major tile: warp w owns reduction rows k = w + 8 j; lanes walk the 16-byte chunks along M/N
-    const int kc = t & 7;
-    const int krow = t >> 3;  // 0..31
-    const float* a_ptr[4];
+    // ===================== producers: cp.async pipeline, `depth` chunks in flight per thread =====================
+    const float* a_ptr[4] = {nullptr, nullptr, nullptr, nullptr};
     if (!A_MN) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int r = m0 + krow + 32 * j;
+        const int r = m0 + (t >> 3) + 32 * j;
         a_ptr[j] = r < p.M ? p.A + (p.gatherA ? p.gatherA[r] : (int64_t)r) * p.lda : nullptr;
       }
     }
-    const int nb_k = bn >> 5;          // K-major B: chunk passes (bn / 32), <= 8
-    const int nb_mn = (bn + 127) >> 7;  // MN-major B: lane passes over bn/4 chunks, <= 2
-    for (int c = 0; c < nchunks; ++c) {
+    const int depth = p.stages - 1;  // chunk c + depth reuses the stage of chunk c - 1, whose MMAs were issued long ago
+    auto issue = [&](int c) {
       const int stage = c % p.stages;
-      const int k0 = k_lo + c * kKC;
-      uint8_t* sA = smem + (uint32_t)stage * stage_bytes;
-      uint8_t* sB = sA + kABytes;
-      float4 va[4];
-      float4 vb[8];
-      // ---- issue every load of this stage before the first use
-      if (!A_MN) {
-        const int kq = k0 + 4 * kc;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) va[j] = a_ptr[j] ? load4(a_ptr[j] + kq, k_hi - kq, p.vecA) : make_float4(0.f, 0.f, 0.f, 0.f);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int kk = k0 + warp + 8 * j;
-          const int m = m0 + 4 * lane;
-          va[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (kk < k_hi) {
-            const int64_t src_row = p.gatherA ? p.gatherA[kk] : (int64_t)kk;
-            va[j] = load4(p.A + src_row * p.lda + m, p.M - m, p.vecA);
-          }
-        }
-      }
-      if (!B_MN) {
-        const int kq = k0 + 4 * kc;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (j < nb_k) {
-            const int n = n0 + krow + 32 * j;
-            vb[j] = n < p.N ? load4(p.B + (int64_t)n * p.ldb + kq, k_hi - kq, p.vecB) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int kk = k0 + warp + 8 * j;
-          const int64_t src_row = kk < k_hi ? (p.gatherB ? p.gatherB[kk] : (int64_t)kk) : -1;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if (h < nb_mn) {
-              const int cc = lane + 32 * h;  // 16-byte chunk along N
-              const int n = n0 + 4 * cc;
-              vb[j * 2 + h] = (src_row >= 0 && 4 * cc < bn) ? load4(p.B + src_row * p.ldb + n, p.N - n, p.vecB)
-                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          }
-        }
-      }
       mbar_wait(empty + stage, ((c / p.stages) & 1) ^ 1);
-      // ---- round to TF32 and store in the UMMA layouts
-      if (!A_MN) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int row = krow + 32 * j;
-          store_tf32x4(sA + row * 128 + ((kc ^ (row & 7)) << 4), va[j]);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int k = warp + 8 * j;
-          store_tf32x4(sA + mnmajor_tf32_offset(lane >> 3, k, lane & 7, kMnLbo), va[j]);
-        }
-      }
-      if (!B_MN) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (j < nb_k) {
-            const int row = krow + 32 * j;
-            store_tf32x4(sB + row * 128 + ((kc ^ (row & 7)) << 4), vb[j]);
-          }
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int k = warp + 8 * j;
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int cc = lane + 32 * h;
-            if (h < nb_mn && 4 * cc < bn)
-              store_tf32x4(sB + mnmajor_tf32_offset(cc >> 3, k, cc & 7, kMnLbo), vb[j * 2 + h]);
-          }
-        }
-      }
+      const uint32_t base = smem_u32(smem + (uint32_t)stage * stage_bytes);
+      for_each_piece<A_MN, B_MN, true>(p, t, m0, n0, k_lo + c * kKC, k_hi, a_ptr, [&](uint32_t off, const float* src, int nv) {
+        const bool is_a = off < kABytes;
+        copy_piece(base + off, src, src ? nv : 0, is_a ? p.vecA != 0 : p.vecB != 0, is_a ? p.A : p.B);
+      });
+    };
+    for (int c = 0; c < depth; ++c) {
+      if (c < nchunks) issue(c);
+      cp_async_commit();
+    }
+    for (int c = 0; c < nchunks; ++c) {
+      if (c + depth < nchunks) issue(c + depth);
+      cp_async_commit();               // (possibly empty) group: keeps one group per chunk
+      cp_async_wait_pending(depth);    // chunk c has landed (this thread's pieces)
+      const int stage = c % p.stages;
+      uint8_t* base = smem + (uint32_t)stage * stage_bytes;
+      for_each_piece<A_MN, B_MN, false>(p, t, m0, n0, k_lo + c * kKC, k_hi, a_ptr,
+                                        [&](uint32_t off, const float*, int) { round_piece(base + off); });
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(full + stage);
@@ -233,8 +229,10 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(TcP p) {
     const int quad = warp & 3, half = warp >> 2;
     const int m = m0 + quad * 32 + lane;
     const int cols_half = bn >> 1;
-    const float keep_scale = p.dropout_p > 0.f ? 1.f / (1.f - p.dropout_p) : 1.f;
-    const uint64_t rng_base = p.offset + ((p.dropout_p > 0.f && p.st) ? p.st->rng_offset : 0ull);
+    const bool relu = p.act == TTAM_ACT_RELU;
+    const bool drop = p.dropout_p > 0.f;
+    const float keep_scale = drop ? 1.f / (1.f - p.dropout_p) : 1.f;
+    const uint64_t rng_base = p.offset + ((drop && p.st) ? p.st->rng_offset : 0ull);
     float* Cz = p.C;
     if (p.k_chunk > 0) Cz += (int64_t)blockIdx.z * (p.transposed ? (int64_t)p.N * p.ldc : (int64_t)p.M * p.ldc);
     for (int cb = 0; cb < cols_half; cb += 16) {
@@ -242,48 +240,63 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(TcP p) {
       uint32_t r[16];
       tmem_ld_32x16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)col, r);
       if (m < p.M) {
-      float v[16];
+        float v[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int n = n0 + col + i;
-        float x = __uint_as_float(r[i]);
-        if (n < p.N) {
-          if (p.bias) x += p.bias[n];
-          x = apply_act(p.act, x);
-          if (p.dropout_p > 0.f)
-            x = dropout_keep(p.seed, rng_base + (uint64_t)m * (uint64_t)p.N + (uint64_t)n, p.dropout_p) ? x * keep_scale : 0.f;
-          if (p.mask_mode == 1) x = (p.aux[(int64_t)m * p.ldaux + n] > 0.f) ? x : 0.f;
-          x *= p.scale;
-        }
-        v[i] = x;
-      }
-      if (p.transposed) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int n = n0 + col + i;
-          if (n < p.N) {
-            float* dst = Cz + (int64_t)n * p.ldc + m;
-            *dst = p.accumulate ? *dst + v[i] : v[i];
-          }
-        }
-      } else {
-        float* dst = Cz + (int64_t)m * p.ldc + n0 + col;
-        if (p.vecC && n0 + col + 15 < p.N) {
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-            if (p.accumulate) {
-              const float4 old = ld_f4(dst + i);
-              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-            }
-            st_f4(dst + i, o);
-          }
-        } else {
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+        if (p.bias) {
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            if (n0 + col + i < p.N) dst[i] = p.accumulate ? dst[i] + v[i] : v[i];
+            if (n0 + col + i < p.N) v[i] += p.bias[n0 + col + i];
         }
-      }
+        if (relu) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (drop) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int n = n0 + col + i;
+            if (n < p.N) v[i] = dropout_keep(p.seed, rng_base + (uint64_t)m * (uint64_t)p.N + (uint64_t)n, p.dropout_p) ? v[i] * keep_scale : 0.f;
+          }
+        }
+        if (p.mask_mode == 1) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int n = n0 + col + i;
+            if (n < p.N) v[i] = (p.aux[(int64_t)m * p.ldaux + n] > 0.f) ? v[i] : 0.f;
+          }
+        }
+        if (p.scale != 1.f) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] *= p.scale;
+        }
+        if (p.transposed) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int n = n0 + col + i;
+            if (n < p.N) {
+              float* dst = Cz + (int64_t)n * p.ldc + m;
+              *dst = p.accumulate ? *dst + v[i] : v[i];
+            }
+          }
+        } else {
+          float* dst = Cz + (int64_t)m * p.ldc + n0 + col;
+          if (p.vecC && n0 + col + 15 < p.N) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              if (p.accumulate) {
+                const float4 old = ld_f4(dst + i);
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+              }
+              st_f4(dst + i, o);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (n0 + col + i < p.N) dst[i] = p.accumulate ? dst[i] + v[i] : v[i];
+          }
+        }
       }
       __syncwarp();  // tcgen05.ld is warp-collective: reconverge before the next one
     }
@@ -322,11 +335,15 @@ static int pick_bn(int64_t N) {
 
 template <bool A_MN, bool B_MN>
 static int launch(TcP& p, int splits, cudaStream_t st) {
-  p.stages = p.bn > 128 ? 2 : p.bn > 64 ? 3 : 4;
+  p.stages = p.bn > 128 ? 2 : p.bn > 64 ? 3 : 4;  // two CTAs per SM: the epilogue of one overlaps the copies of the other
+  if (const char* e = getenv("TTAM_TC_STAGES")) {
+    const int v = atoi(e);
+    if (v >= 2 && v <= 4 && (size_t)v * (kABytes + (size_t)p.bn * 128) + 1280 <= 200 * 1024) p.stages = v;
+  }
   const size_t smem = (size_t)p.stages * (kABytes + (size_t)p.bn * 128) + 1024 + 256;
   static bool attr_done = false;
   if (!attr_done) {
-    TTAM_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    TTAM_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_done = true;
   }
   dim3 grid((unsigned)ceil_div(p.N, p.bn), (unsigned)ceil_div(p.M, kBM), (unsigned)splits);
@@ -342,6 +359,10 @@ using namespace tcg;
 int tc_linear_fwd(const float* x, int64_t ldx, const int64_t* gather, const float* w, int64_t ldw, const float* bias,
                   float* y, int64_t ldy, int64_t M, int64_t N, int64_t K, int act, float dropout_p, uint64_t seed,
                   uint64_t offset, const ttam_step_state* state_dev, cudaStream_t st) {
+  if (act != TTAM_ACT_NONE && act != TTAM_ACT_RELU) {
+    set_error("linear_fwd: the tensor-core path fuses ReLU only; run other activations with ttam_act_fwd");
+    return TTAM_EUNSUPPORTED;
+  }
   TcP p{};
   p.A = x; p.B = w; p.C = y; p.lda = ldx; p.ldb = ldw; p.ldc = ldy; p.gatherA = gather;
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.bn = pick_bn(N);
