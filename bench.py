@@ -169,6 +169,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("TTAM_PRECISION", "fp32"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-retrieval", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="N=1: launch the step eagerly instead of replaying a CUDA graph (diagnostic)")
     ap.add_argument("--small", action="store_true", help="1/16-size tables (debugging only; not a valid bench line)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
@@ -236,7 +237,7 @@ def main():
     def step(u, p, n):
         if sh is not None:
             return sh.train_step(u, p, n, user_x, item_x)
-        return eng.train_step(u, p, n, user_x, item_x, graph=True)
+        return eng.train_step(u, p, n, user_x, item_x, graph=not args.no_graph)
 
     # ---- value: batch index tensors resident in HBM (N = 1: CUDA-graph replay of the step)
     launches0 = F.lib().ttam_launch_count()
@@ -302,7 +303,7 @@ def main():
             "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32"}[args.precision], "data": "synthetic",
             "config": {"workload": workload,
-                       "parallelism": "1 gpu, CUDA-graph replay" if world == 1 else
+                       "parallelism": ("1 gpu, CUDA-graph replay" if not args.no_graph else "1 gpu, eager launches") if world == 1 else
                        f"{world} gpus: tables/features row-sharded, batch data-parallel ({B} samples per gpu), 3 all-to-all + 1 all-reduce per step",
                        "l2_policy": "inputs larger than L2: each step gathers from 11.8 GB of tables/features"},
             "e2e": {"value": world * K * B / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": B * 8 * (2 + N),

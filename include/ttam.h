@@ -114,6 +114,39 @@ int ttam_gate_bwd(const float* dt, const float* z, const float* g, float* dpre2,
 int ttam_augment_fwd(const float* t, const float* aug_table, int64_t aug_rows, const int64_t* idx, float* o,
                      float* q_out, int64_t R, int64_t D, void* stream);
 
+/* ---- composite: one gated tower (1-hidden-layer ReLU MLP) per call -----------------------------------------
+ * ttam_tower_fwd / ttam_tower_bwd enqueue the launch sequence of TowerEncoder.forward (encoders.py:221-255) +
+ * _apply_aug (adaptive_mimic.py:88-95), resp. their autograd, with ONE C call (an eager step then makes ~10 calls
+ * instead of ~85).  Buffers: z [R,2D] = [e ; f], hd [R,H], a [R,Hg], pre2/g/t/o/q [R,D]; gradients: dz [R,2D]
+ * (dz[:, :D] = dL/dE rows on return), dpre2 [R,D], dpre1 [R,Hg], dhd [R,H] and the weight gradients. */
+typedef struct {
+  const float* table;   /* [table_rows, D] ID embedding */
+  const float* aug;     /* [table_rows, D] augmentation table, nullable */
+  int64_t table_rows, D;
+  const float* X;       /* [*, F] feature matrix, rows ldx floats apart */
+  int64_t ldx, F;
+  const float *W1, *b1; /* [H, F] (rows ldw1 apart), [H] */
+  int64_t ldw1, H;
+  const float *W2, *b2; /* [D, H], [D] */
+  const float *G1, *c1; /* [Hg, 2D], [Hg] */
+  int64_t Hg;
+  const float *G2, *c2; /* [D, Hg], [D] */
+  float dropout_p;
+  int32_t precision;
+  uint64_t seed, rng_base;
+  const ttam_step_state* state;
+} ttam_tower_desc;
+typedef struct { float *z, *hd, *a, *pre2, *g, *t, *o, *q; } ttam_tower_bufs;
+typedef struct {
+  float *dpre2, *dz, *dpre1, *dhd;
+  float *dW1, *db1, *dW2, *db2, *dG1, *dc1, *dG2, *dc2;
+  int32_t accumulate, pad_;
+} ttam_tower_grads;
+int ttam_tower_fwd(const ttam_tower_desc* d, const int64_t* idx, int64_t R, const ttam_tower_bufs* bufs, void* stream);
+int64_t ttam_tower_bwd_workspace_bytes(const ttam_tower_desc* d, int64_t R);
+int ttam_tower_bwd(const ttam_tower_desc* d, const int64_t* idx, int64_t R, const ttam_tower_bufs* bufs, const float* dt,
+                   const ttam_tower_grads* grads, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- fused loss forward+backward (training.py:770-803, adaptive_mimic.py:59-68) -------------------
  * o_u[B,D], o_i[(1+N)B,D] (positives first, then negatives row-major [B,N]); t_u,t_p[B,D] base tower
  * outputs, q_u,q_p[B,D] augmentation rows of the positive pairs (all four null when mimic is off).

@@ -35,6 +35,27 @@ class TensorList(C.Structure):
     ]
 
 
+class TowerDesc(C.Structure):
+    _fields_ = [
+        ("table", C.c_void_p), ("aug", C.c_void_p), ("table_rows", C.c_int64), ("D", C.c_int64),
+        ("X", C.c_void_p), ("ldx", C.c_int64), ("F", C.c_int64),
+        ("W1", C.c_void_p), ("b1", C.c_void_p), ("ldw1", C.c_int64), ("H", C.c_int64),
+        ("W2", C.c_void_p), ("b2", C.c_void_p), ("G1", C.c_void_p), ("c1", C.c_void_p), ("Hg", C.c_int64),
+        ("G2", C.c_void_p), ("c2", C.c_void_p),
+        ("dropout_p", C.c_float), ("precision", C.c_int32), ("seed", C.c_uint64), ("rng_base", C.c_uint64),
+        ("state", C.c_void_p),
+    ]
+
+
+class TowerBufs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("z", "hd", "a", "pre2", "g", "t", "o", "q")]
+
+
+class TowerGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("dpre2", "dz", "dpre1", "dhd", "dW1", "db1", "dW2", "db2", "dG1", "dc1", "dG2", "dc2")] + \
+               [("accumulate", C.c_int32), ("pad_", C.c_int32)]
+
+
 def _sources():
     return sorted(CSRC.glob("*.cu"))
 
@@ -98,6 +119,9 @@ SIGNATURES = {
     "ttam_gate_fwd": (C.c_int, [_p, _p, _p, _i64, _p, _p, _p, _p, _p, _i64, _i64, _p]),
     "ttam_gate_bwd": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _p]),
     "ttam_augment_fwd": (C.c_int, [_p, _p, _i64, _p, _p, _p, _i64, _i64, _p]),
+    "ttam_tower_fwd": (C.c_int, [C.POINTER(TowerDesc), _p, _i64, C.POINTER(TowerBufs), _p]),
+    "ttam_tower_bwd_workspace_bytes": (C.c_int64, [C.POINTER(TowerDesc), _i64]),
+    "ttam_tower_bwd": (C.c_int, [C.POINTER(TowerDesc), _p, _i64, C.POINTER(TowerBufs), _p, C.POINTER(TowerGrads), _p, _i64, _p]),
     "ttam_loss_workspace_bytes": (C.c_int64, [_i64]),
     "ttam_loss_fwd_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _i64, _i64, _i64, _f, _p, _i64, _p]),
     "ttam_sort_workspace_bytes": (C.c_int64, [_i64]),

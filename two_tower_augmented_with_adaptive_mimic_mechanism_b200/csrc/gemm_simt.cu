@@ -164,12 +164,17 @@ extern "C" int ttam_linear_wgrad(const float* dy, int64_t lddy, const float* x, 
   float* partial_b = partial_w + (int64_t)splits * N * K;
   if (precision == TTAM_PREC_TF32) {
     int real = 0;
-    const int rc = tc_linear_wgrad_partials(dy, lddy, x, ldx, gather, partial_w, M, N, K, &real, s);
+    const int rc = tc_linear_wgrad_partials(dy, lddy, x, ldx, gather, partial_w, db ? partial_b : nullptr, M, N, K, &real, s);
     if (rc != TTAM_OK) return rc;
     const int64_t numel = N * K;
     const int blocks = (int)std::min<int64_t>(ceil_div(numel, 256), (int64_t)num_sms() * 8);
     splitk_reduce_kernel<<<blocks, 256, 0, s>>>(partial_w, real, numel, dw, accumulate);
     TTAM_LAUNCH_CHECK();
+    if (db) {  // the bias gradient came out of the same pass over dy
+      colsum_final_kernel<<<(int)ceil_div(N, 8), 256, 0, s>>>(partial_b, real, (int)N, db, accumulate);
+      TTAM_LAUNCH_CHECK();
+    }
+    return TTAM_OK;
   } else {
   // C[N,K] = sum_m A(row=n, k=m) * B(row=k, k=m);  A = dy (MN-contiguous), B = x rows (MN-contiguous, gathered on m)
   GemmP p{};

@@ -44,6 +44,7 @@ struct TcP {
   int stages;
   int vecA, vecB, vecC;  // 16-byte accesses allowed (base and leading dimension aligned)
   int transposed;        // store C(m,n) at C[z][n*ldc + m]
+  float* colsum_b;       // MN-major B only: colsum_b[z][n] = sum over this CTA's reduction range of B(n, k)  (bias gradient)
   const float* bias;
   int act;
   float dropout_p;
@@ -97,7 +98,8 @@ __device__ __forceinline__ void round_piece(uint8_t* ptr) {
 }
 
 // The 16-byte pieces of one stage that THIS thread copies (and later rounds).  f(byte offset in the stage, source
-// pointer or nullptr, number of valid floats).  K-major tile: piece id = t + 256 j -> row (t >> 3) + 32 j, 16-byte chunk
+// pointer or nullptr, number of valid floats, ordinal: -1 for an A piece, else the B pass index: for an MN-major B the
+// lane's column chunk is lane + 32 * ordinal).  K-major tile: piece id = t + 256 j -> row (t >> 3) + 32 j, 16-byte chunk
 // t & 7 of the row's 128 bytes.  MN-major tile: warp w owns reduction rows w + 8 j, lanes walk the chunks along M/N.
 template <bool A_MN, bool B_MN, bool WITH_SRC, class Fn>
 __device__ __forceinline__ void for_each_piece(const TcP& p, int t, int m0, int n0, int k0, int k_hi, const float* const (&a_ptr)[4],
@@ -110,7 +112,7 @@ __device__ __forceinline__ void for_each_piece(const TcP& p, int t, int m0, int 
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int row = krow + 32 * j;
-      f((uint32_t)(row * 128 + ((kc ^ (row & 7)) << 4)), (WITH_SRC && a_ptr[j]) ? a_ptr[j] + kq : nullptr, a_ptr[j] ? k_hi - kq : 0);
+      f((uint32_t)(row * 128 + ((kc ^ (row & 7)) << 4)), (WITH_SRC && a_ptr[j]) ? a_ptr[j] + kq : nullptr, a_ptr[j] ? k_hi - kq : 0, -1);
     }
   } else {
 #pragma unroll
@@ -118,7 +120,7 @@ __device__ __forceinline__ void for_each_piece(const TcP& p, int t, int m0, int 
       const int k = warp + 8 * j, kk = k0 + k, m = m0 + 4 * lane;
       const float* src = nullptr;
       if (WITH_SRC && kk < k_hi) src = p.A + (p.gatherA ? p.gatherA[kk] : (int64_t)kk) * p.lda + m;
-      f(mnmajor_tf32_offset(lane >> 3, k, lane & 7, kMnLbo), src, kk < k_hi ? p.M - m : 0);
+      f(mnmajor_tf32_offset(lane >> 3, k, lane & 7, kMnLbo), src, kk < k_hi ? p.M - m : 0, -1);
     }
   }
   if (!B_MN) {
@@ -129,7 +131,7 @@ __device__ __forceinline__ void for_each_piece(const TcP& p, int t, int m0, int 
       if (j < nb_k) {
         const int row = krow + 32 * j, n = n0 + row;
         f(kABytes + (uint32_t)(row * 128 + ((kc ^ (row & 7)) << 4)), (WITH_SRC && n < p.N) ? p.B + (int64_t)n * p.ldb + kq : nullptr,
-          n < p.N ? k_hi - kq : 0);
+          n < p.N ? k_hi - kq : 0, j);
       }
     }
   } else {
@@ -143,7 +145,7 @@ __device__ __forceinline__ void for_each_piece(const TcP& p, int t, int m0, int 
       for (int h = 0; h < 2; ++h) {
         const int cc = lane + 32 * h, n = n0 + 4 * cc;
         if (h < nb_mn && 4 * cc < bn)
-          f(kABytes + mnmajor_tf32_offset(cc >> 3, k, cc & 7, kMnLbo), row_ptr ? row_ptr + n : nullptr, kk < k_hi ? p.N - n : 0);
+          f(kABytes + mnmajor_tf32_offset(cc >> 3, k, cc & 7, kMnLbo), row_ptr ? row_ptr + n : nullptr, kk < k_hi ? p.N - n : 0, h);
       }
     }
   }
@@ -196,12 +198,14 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(TcP p) {
         a_ptr[j] = r < p.M ? p.A + (p.gatherA ? p.gatherA[r] : (int64_t)r) * p.lda : nullptr;
       }
     }
+    const bool want_colsum = B_MN && p.colsum_b != nullptr && blockIdx.y == 0;
+    float4 csum[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
     const int depth = p.stages - 1;  // chunk c + depth reuses the stage of chunk c - 1, whose MMAs were issued long ago
     auto issue = [&](int c) {
       const int stage = c % p.stages;
       mbar_wait(empty + stage, ((c / p.stages) & 1) ^ 1);
       const uint32_t base = smem_u32(smem + (uint32_t)stage * stage_bytes);
-      for_each_piece<A_MN, B_MN, true>(p, t, m0, n0, k_lo + c * kKC, k_hi, a_ptr, [&](uint32_t off, const float* src, int nv) {
+      for_each_piece<A_MN, B_MN, true>(p, t, m0, n0, k_lo + c * kKC, k_hi, a_ptr, [&](uint32_t off, const float* src, int nv, int) {
         const bool is_a = off < kABytes;
         copy_piece(base + off, src, src ? nv : 0, is_a ? p.vecA != 0 : p.vecB != 0, is_a ? p.A : p.B);
       });
@@ -216,8 +220,13 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(TcP p) {
       cp_async_wait_pending(depth);    // chunk c has landed (this thread's pieces)
       const int stage = c % p.stages;
       uint8_t* base = smem + (uint32_t)stage * stage_bytes;
-      for_each_piece<A_MN, B_MN, false>(p, t, m0, n0, k_lo + c * kKC, k_hi, a_ptr,
-                                        [&](uint32_t off, const float*, int) { round_piece(base + off); });
+      for_each_piece<A_MN, B_MN, false>(p, t, m0, n0, k_lo + c * kKC, k_hi, a_ptr, [&](uint32_t off, const float*, int, int slot) {
+        float4 v = *reinterpret_cast<float4*>(base + off);
+        if (B_MN && want_colsum && slot >= 0) {  // exact fp32 column sums of B (before the TF32 rounding)
+          csum[slot & 1].x += v.x; csum[slot & 1].y += v.y; csum[slot & 1].z += v.z; csum[slot & 1].w += v.w;
+        }
+        *reinterpret_cast<uint4*>(base + off) = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+      });
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(full + stage);
@@ -226,6 +235,23 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(TcP p) {
     // ===================== epilogue: thread = output row (TMEM lane), 16 columns per tcgen05.ld =====================
     mbar_wait(acc_full, 0);
     tc_fence_after();
+    if (want_colsum) {
+      // every MMA has completed: the stage memory is free.  Warp w summed the reduction rows w, w+8, ...; combine the
+      // eight partial sums in warp order (deterministic) and write this CTA's share of the bias gradient.
+      float* red = reinterpret_cast<float*>(smem);  // [kProdWarps][256]
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int cc = lane + 32 * h;
+        if (4 * cc < bn) *reinterpret_cast<float4*>(red + warp * 256 + 4 * cc) = csum[h];
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kProdThreads) : "memory");
+      if (t < bn && n0 + t < p.N) {
+        float sacc = 0.f;
+#pragma unroll
+        for (int w = 0; w < kProdWarps; ++w) sacc += red[w * 256 + t];
+        p.colsum_b[(int64_t)blockIdx.z * p.N + n0 + t] = sacc;
+      }
+    }
     const int quad = warp & 3, half = warp >> 2;
     const int m = m0 + quad * 32 + lane;
     const int cols_half = bn >> 1;
@@ -392,7 +418,7 @@ int tc_wgrad_splits(int64_t M, int64_t N, int64_t K) {
 }
 
 int tc_linear_wgrad_partials(const float* dy, int64_t lddy, const float* x, int64_t ldx, const int64_t* gather, float* partial,
-                             int64_t M, int64_t N, int64_t K, int* real_splits, cudaStream_t st) {
+                             float* colsum_partial, int64_t M, int64_t N, int64_t K, int* real_splits, cudaStream_t st) {
   // part[z][n'][k'] = sum_{r in chunk z} dy[r, n'] x[g(r), k']:  C(m = k', n = n'), both operands MN-major over r
   const int splits = tc_wgrad_splits(M, N, K);
   const int chunk = (int)align_up(ceil_div(M, splits), kKC);
@@ -401,7 +427,7 @@ int tc_linear_wgrad_partials(const float* dy, int64_t lddy, const float* x, int6
   p.A = x; p.B = dy; p.C = partial; p.lda = ldx; p.ldb = lddy; p.ldc = K; p.gatherA = gather;
   p.M = (int)K; p.N = (int)N; p.K = (int)M; p.k_chunk = chunk; p.bn = pick_bn(N);
   p.vecA = aligned16(x) && ldx % 4 == 0; p.vecB = aligned16(dy) && lddy % 4 == 0; p.vecC = 0;
-  p.transposed = 1; p.scale = 1.f;
+  p.transposed = 1; p.scale = 1.f; p.colsum_b = colsum_partial;
   return launch<true, true>(p, *real_splits, st);
 }
 

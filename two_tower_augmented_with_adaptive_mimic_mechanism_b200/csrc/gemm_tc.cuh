@@ -10,8 +10,8 @@ int tc_linear_fwd(const float* x, int64_t ldx, const int64_t* gather, const floa
 int tc_linear_dgrad(const float* dy, int64_t lddy, const float* w, float* dx, int64_t lddx, const float* aux, int64_t ldaux,
                     int mask_mode, float scale, int accumulate, int64_t M, int64_t N, int64_t K, cudaStream_t st);
 int tc_wgrad_splits(int64_t M, int64_t N, int64_t K);
-// part[z][N][K] for z < *real_splits
+// part[z][N][K] and (when colsum_partial is non-null) colsum_partial[z][N] = column sums of dy, for z < *real_splits
 int tc_linear_wgrad_partials(const float* dy, int64_t lddy, const float* x, int64_t ldx, const int64_t* gather, float* partial,
-                             int64_t M, int64_t N, int64_t K, int* real_splits, cudaStream_t st);
+                             float* colsum_partial, int64_t M, int64_t N, int64_t K, int* real_splits, cudaStream_t st);
 
 }  // namespace ttam

@@ -138,10 +138,11 @@ __device__ __forceinline__ void dense_elem(float g, float& p, float& m, float& v
 // A popular row (Zipf-distributed positives) can own hundreds of gradient rows of a batch; summing them with one warp
 // would serialise the whole step behind that warp.  Segments longer than kLongSeg are listed by
 // find_long_segments_kernel and processed by one whole block each: every warp sums a strided share of the rows with
-// four loads in flight, the eight partial sums are combined in warp order (a fixed order: results are deterministic),
+// eight loads in flight, the sixteen partial sums are combined in warp order (a fixed order: results are deterministic),
 // and warp 0 applies the optimiser.  The row kernels skip those segments when they are given the list.
 constexpr int kLongSeg = 16;
-constexpr int kLongWarps = 8;
+constexpr int kLongWarps = 16;   // 512 threads per long segment
+constexpr int kLongUnroll = 8;   // gradient rows in flight per warp
 
 __global__ void __launch_bounds__(256) find_long_segments_kernel(const int64_t* __restrict__ sorted, int64_t R,
                                                                   int32_t* __restrict__ list) {
@@ -180,10 +181,10 @@ __device__ __forceinline__ void segment_sum_block(const GradSrc& gs, const int32
                                                   int64_t end, int col, bool active, float (*part)[128], float (&acc)[4]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float a[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int64_t j0 = i + warp; j0 < end; j0 += 4 * kLongWarps) {
-    float v[4][4];
+  for (int64_t j0 = i + warp; j0 < end; j0 += kLongUnroll * kLongWarps) {
+    float v[kLongUnroll][4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kLongUnroll; ++u) {
       const int64_t j = j0 + u * kLongWarps;
       v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.f;
       if (j < end && active) {
@@ -197,7 +198,7 @@ __device__ __forceinline__ void segment_sum_block(const GradSrc& gs, const int32
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < kLongUnroll; ++u)
 #pragma unroll
       for (int e = 0; e < 4; ++e) a[e] = __fadd_rn(a[e], v[u][e]);
   }
@@ -259,7 +260,7 @@ __global__ void __launch_bounds__(256) sparse_adam_rows_kernel(float* __restrict
 }
 
 template <bool VEC>
-__global__ void __launch_bounds__(256) sparse_adam_long_kernel(float* __restrict__ P, float* __restrict__ Mo,
+__global__ void __launch_bounds__(32 * kLongWarps) sparse_adam_long_kernel(float* __restrict__ P, float* __restrict__ Mo,
                                                                float* __restrict__ Vo, int D,
                                                                const int64_t* __restrict__ sorted,
                                                                const int32_t* __restrict__ perm, int64_t R, GradSrc gs,
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(256) lazy_rows_kernel(float* __restrict__ P, f
 }
 
 template <int KIND, bool VEC>
-__global__ void __launch_bounds__(256) lazy_long_kernel(float* __restrict__ P, float* __restrict__ Mo,
+__global__ void __launch_bounds__(32 * kLongWarps) lazy_long_kernel(float* __restrict__ P, float* __restrict__ Mo,
                                                         float* __restrict__ Vo, int32_t* __restrict__ last_step, int D,
                                                         const int64_t* __restrict__ sorted,
                                                         const int32_t* __restrict__ perm, int64_t R, GradSrc gs,
@@ -618,8 +619,8 @@ extern "C" int ttam_sparse_adam_rows(float* p, float* m, float* v, int64_t D, co
   else sparse_adam_rows_kernel<false><<<blocks, 256, 0, cs>>>(p, m, v, (int)D, sorted_idx, perm, R, gs, s, scalars, state_dev, skip);
   TTAM_LAUNCH_CHECK();
   if (skip) {
-    if (vec) sparse_adam_long_kernel<true><<<num_sms(), 256, 0, cs>>>(p, m, v, (int)D, sorted_idx, perm, R, gs, s, scalars, state_dev, long_list);
-    else sparse_adam_long_kernel<false><<<num_sms(), 256, 0, cs>>>(p, m, v, (int)D, sorted_idx, perm, R, gs, s, scalars, state_dev, long_list);
+    if (vec) sparse_adam_long_kernel<true><<<num_sms(), 32 * kLongWarps, 0, cs>>>(p, m, v, (int)D, sorted_idx, perm, R, gs, s, scalars, state_dev, long_list);
+    else sparse_adam_long_kernel<false><<<num_sms(), 32 * kLongWarps, 0, cs>>>(p, m, v, (int)D, sorted_idx, perm, R, gs, s, scalars, state_dev, long_list);
     TTAM_LAUNCH_CHECK();
   }
   return TTAM_OK;
@@ -656,7 +657,7 @@ extern "C" int ttam_lazy_rows(int kind, float* p, float* m, float* v, int32_t* l
 #undef CALL
   TTAM_LAUNCH_CHECK();
   if (skip) {
-#define CALL(K, V) lazy_long_kernel<K, V><<<num_sms(), 256, 0, st>>>(p, m, v, last_step, (int)D, sorted_idx, perm, R, gs, scalars, s, (int)step, state_dev, long_list)
+#define CALL(K, V) lazy_long_kernel<K, V><<<num_sms(), 32 * kLongWarps, 0, st>>>(p, m, v, last_step, (int)D, sorted_idx, perm, R, gs, scalars, s, (int)step, state_dev, long_list)
     if (vec) TTAM_DISPATCH_KIND(kind, true, CALL);
     else TTAM_DISPATCH_KIND(kind, false, CALL);
 #undef CALL

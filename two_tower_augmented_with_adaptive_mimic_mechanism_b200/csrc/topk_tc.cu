@@ -90,18 +90,20 @@ __device__ __noinline__ uint2 compact_row(int r, int lane, bool exact, uint2* my
   __syncwarp();  // lane r's appends are visible to the whole warp
   uint32_t o[kPerLane], id[kPerLane];
   uint32_t lmax = 0u, lmin = 0xFFFFFFFFu;
+  // all 16 loads of this lane are issued before the first use (one round trip to L2 instead of sixteen): out-of-range
+  // slots read the last valid entry and are masked afterwards
+  uint2 raw[kPerLane];
+  const int last = n > 0 ? n - 1 : 0;
+#pragma unroll
+  for (int j = 0; j < kPerLane; ++j) raw[j] = buf[min(j * 32 + lane, last)];
 #pragma unroll
   for (int j = 0; j < kPerLane; ++j) {
     const int e = j * 32 + lane;
-    o[j] = 0u;  // below every real entry
-    id[j] = 0u;
-    if (e < n) {
-      const uint2 raw = buf[e];
-      o[j] = ordered_bits(__uint_as_float(raw.x));
-      id[j] = raw.y;
-      lmax = max(lmax, o[j]);
-      lmin = min(lmin, o[j]);
-    }
+    const bool ok = e < n;
+    o[j] = ok ? ordered_bits(__uint_as_float(raw[j].x)) : 0u;  // 0: below every real entry
+    id[j] = ok ? raw[j].y : 0u;
+    lmax = max(lmax, o[j]);
+    lmin = ok ? min(lmin, o[j]) : lmin;
   }
   const uint32_t omax = __reduce_max_sync(0xffffffffu, lmax);
   const uint32_t omin = __reduce_min_sync(0xffffffffu, lmin);
@@ -132,7 +134,7 @@ __device__ __noinline__ uint2 compact_row(int r, int lane, bool exact, uint2* my
   c_gt = __reduce_add_sync(0xffffffffu, c_gt);
   c_eq = __reduce_add_sync(0xffffffffu, c_eq);
   // ties: keep them all when there is room (then scores == t* stay admissible), else only enough to reach kKeep
-  const bool keep_all_ties = !exact && (c_gt + c_eq <= kCap - 4 * 32);
+  const bool keep_all_ties = !exact && (c_gt + c_eq <= kCap - 4 * 64);
   const int tie_budget = keep_all_ties ? c_eq : max(0, min(c_eq, kKeep - c_gt));
   __syncwarp();
   const unsigned lt = (1u << lane) - 1u;
@@ -224,7 +226,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       uint32_t it = 0, un = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x, ++un) {
         const int qb = u % p.qblocks, s = u / p.qblocks;
-        mbar_wait(a_empty, (un & 1) ^ 1);
+        mbar_wait_relaxed(a_empty, (un & 1) ^ 1, 256);
         mbar_expect_tx(a_full, C::kABytes);
         for (int a = 0; a < kATiles; ++a)
           for (int kb = 0; kb < KBOX; ++kb)
@@ -233,7 +235,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         const int t1 = min(p.tiles_total, t0 + p.tiles_per_split);
         for (int t = t0; t < t1; ++t, ++it) {
           const int stage = it % C::kStages;
-          mbar_wait(b_empty + stage, ((it / C::kStages) & 1) ^ 1);
+          mbar_wait_relaxed(b_empty + stage, ((it / C::kStages) & 1) ^ 1, 256);
           if ((p.debug & 4) && it >= (uint32_t)C::kStages) {  // timing experiment: the MMA re-reads stale tiles
             mbar_arrive(b_full + stage);
             continue;
@@ -264,7 +266,10 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 #pragma unroll 1
           for (int a = 0; a < kATiles; ++a) {
             // one N=256 MMA group fills both 128-column halves of query tile a: both must have been drained
-            if (!(p.debug & 8)) {  // (8: timing experiment, accumulators overwritten without waiting for the drain)
+            if (p.debug & 16) {    // (16: timing experiment, polls of the MMA thread back off with nanosleep)
+              mbar_wait_relaxed(acc_empty + a * 2, (it & 1) ^ 1, 32);
+              mbar_wait_relaxed(acc_empty + a * 2 + 1, (it & 1) ^ 1, 32);
+            } else if (!(p.debug & 8)) {  // (8: timing experiment, accumulators overwritten without waiting for the drain)
               mbar_wait(acc_empty + a * 2, (it & 1) ^ 1);
               mbar_wait(acc_empty + a * 2 + 1, (it & 1) ^ 1);
             }
@@ -300,34 +305,46 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       int cnt = 0;
       const int64_t slot = (valid ? qrow : 0) * p.S + s;
       uint2* buf = p.lists + slot * kCap;
-      // one 32-column chunk of this thread's row: 3-input-max tree, one compare; survivors are rare
-      auto process = [&](uint32_t (&v)[32], uint32_t id0, bool tail) {
+      // A pair of 32-column chunks of this thread's row per iteration (two tcgen05.ld in flight, two independent max
+      // trees: the loop is latency-bound, not issue-bound): 3-input-max trees, one compare; survivors are rare.
+      auto process2 = [&](uint32_t (&v0)[32], uint32_t (&v1)[32], uint32_t id0, bool tail) {
         if (tail) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if ((int64_t)(id0 + i) >= p.N) v[i] = 0xFF800000u;  // -inf: never a candidate
+          for (int i = 0; i < 32; ++i) {
+            if ((int64_t)(id0 + i) >= p.N) v0[i] = 0xFF800000u;  // -inf: never a candidate
+            if ((int64_t)(id0 + 32 + i) >= p.N) v1[i] = 0xFF800000u;
+          }
         }
-        float m[8];
+        float m[16];
 #pragma unroll
-        for (int g = 0; g < 8; ++g)
-          m[g] = fmaxf(fmaxf(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1])),
-                       fmaxf(__uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3])));
-        const float mx = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
+        for (int g = 0; g < 8; ++g) {
+          m[g] = fmaxf(fmaxf(__uint_as_float(v0[4 * g]), __uint_as_float(v0[4 * g + 1])),
+                       fmaxf(__uint_as_float(v0[4 * g + 2]), __uint_as_float(v0[4 * g + 3])));
+          m[8 + g] = fmaxf(fmaxf(__uint_as_float(v1[4 * g]), __uint_as_float(v1[4 * g + 1])),
+                           fmaxf(__uint_as_float(v1[4 * g + 2]), __uint_as_float(v1[4 * g + 3])));
+        }
+        float m4[4];  // maxima of the four 16-column quarters
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) m4[q4] = fmaxf(fmaxf(m[4 * q4], m[4 * q4 + 1]), fmaxf(m[4 * q4 + 2], m[4 * q4 + 3]));
+        const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
         if (__any_sync(0xffffffffu, mx > tau) && !(p.debug & 2)) {
-          // usually one or two of the warp's 1024 scores beat their row's threshold: find the 4-column groups that
-          // hold them with warp votes (uniform branches), then append with predicated stores
-          unsigned gmask = 0;
+          // usually one or two of the warp's 2048 scores beat their row's threshold: descend with warp votes (uniform
+          // branches) into the 16-column quarters and 4-column groups that hold them, append with predicated stores
 #pragma unroll
-          for (int g = 0; g < 8; ++g) gmask |= (m[g] > tau) ? (1u << g) : 0u;
-          gmask = __reduce_or_sync(0xffffffffu, gmask);
+          for (int q4 = 0; q4 < 4; ++q4) {
+            if (__any_sync(0xffffffffu, m4[q4] > tau)) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            if (gmask & (1u << g)) {
+              for (int gg = 0; gg < 4; ++gg) {
+                const int g = 4 * q4 + gg;
+                if (__any_sync(0xffffffffu, m[g] > tau)) {
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                if (__uint_as_float(v[4 * g + i]) > tau) {
-                  buf[cnt] = make_uint2(v[4 * g + i], id0 + 4 * g + i);
-                  ++cnt;
+                  for (int i = 0; i < 4; ++i) {
+                    const uint32_t bits = g < 8 ? v0[4 * (g & 7) + i] : v1[4 * (g & 7) + i];
+                    if (__uint_as_float(bits) > tau) {
+                      buf[cnt] = make_uint2(bits, id0 + 4 * g + i);
+                      ++cnt;
+                    }
+                  }
                 }
               }
             }
@@ -335,7 +352,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         }
       };
       auto make_room = [&]() {
-        unsigned need = __ballot_sync(0xffffffffu, cnt > kCap - 32);
+        unsigned need = __ballot_sync(0xffffffffu, cnt > kCap - 64);
         while (need) {
           const int r = __ffs(need) - 1;
           need &= need - 1;
@@ -355,13 +372,15 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         for (int h = 0; h < 2; ++h) {
           if (!(p.debug & 1)) {
 #pragma unroll 1
-            for (int ch = 0; ch < 4; ++ch) {
-              const int col = h * kHN + ch * 32;
-              uint32_t v[32];
-              tmem_ld_32x32_issue(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * kBN + col), v);
+            for (int cp = 0; cp < 2; ++cp) {
+              const int col = h * kHN + cp * 64;
+              uint32_t v0[32], v1[32];
+              const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * kBN + col);
+              tmem_ld_32x32_issue(taddr, v0);
+              tmem_ld_32x32_issue(taddr + 32u, v1);
               make_room();
-              tmem_ld_wait(v);
-              process(v, (uint32_t)t * kBN + (uint32_t)col, tail);
+              tmem_ld_wait2(v0, v1);
+              process2(v0, v1, (uint32_t)t * kBN + (uint32_t)col, tail);
             }
           }
           tc_fence_before();

@@ -1,0 +1,69 @@
+// Composite entry points: the whole forward / backward of one gated tower (1-hidden-layer ReLU MLP) as ONE C call that
+// enqueues the same launch sequence tower_ops.py issues op by op (reference encoders.py:221-255 + adaptive_mimic.py:88-95
+// and their autograd).  Nothing new is computed here; the point is host-side: an eager step (the row-sharded N-GPU
+// step, the training hooks) makes ~10 C calls instead of ~85, so the CPU stays ahead of the GPU.
+#include "common.cuh"
+
+using namespace ttam;
+
+#define TTAM_TRY(expr)            \
+  do {                            \
+    const int rc__ = (expr);      \
+    if (rc__ != TTAM_OK) return rc__; \
+  } while (0)
+
+extern "C" int ttam_tower_fwd(const ttam_tower_desc* d, const int64_t* idx, int64_t R, const ttam_tower_bufs* b, void* stream) {
+  TTAM_CHECK_ARG(d && b && (R == 0 || idx), "tower_fwd: null pointer");
+  TTAM_CHECK_ARG(d->table && d->X && d->W1 && d->W2 && d->G1 && d->G2, "tower_fwd: incomplete tower description");
+  TTAM_CHECK_ARG(b->z && b->hd && b->a && b->pre2 && b->g && b->t, "tower_fwd: missing activation buffer");
+  if (R == 0) return TTAM_OK;
+  const int64_t D = d->D, H = d->H, Hg = d->Hg, F = d->F;
+  // e = E[idx] -> z[:, :D]
+  TTAM_TRY(ttam_gather_rows_f32(d->table, D, d->table_rows, idx, b->z, 2 * D, R, D, stream));
+  // hd = dropout(relu(X[idx] W1^T + b1))
+  TTAM_TRY(ttam_linear_fwd(d->X, d->ldx, idx, d->W1, d->ldw1, d->b1, b->hd, H, R, H, F, TTAM_ACT_RELU, d->dropout_p, d->seed,
+                           d->rng_base, d->state, d->precision, stream));
+  // f = hd W2^T + b2 -> z[:, D:]
+  TTAM_TRY(ttam_linear_fwd(b->hd, H, nullptr, d->W2, H, d->b2, b->z + D, 2 * D, R, D, H, TTAM_ACT_NONE, 0.f, 0, 0, nullptr,
+                           d->precision, stream));
+  // a = relu(z G1^T + c1);  pre2 = a G2^T + c2
+  TTAM_TRY(ttam_linear_fwd(b->z, 2 * D, nullptr, d->G1, 2 * D, d->c1, b->a, Hg, R, Hg, 2 * D, TTAM_ACT_RELU, 0.f, 0, 0, nullptr,
+                           d->precision, stream));
+  TTAM_TRY(ttam_linear_fwd(b->a, Hg, nullptr, d->G2, Hg, d->c2, b->pre2, D, R, D, Hg, TTAM_ACT_NONE, 0.f, 0, 0, nullptr,
+                           d->precision, stream));
+  // g = sigmoid(pre2); t = g e + (1-g) f; o = t + A[idx]
+  return ttam_gate_fwd(b->z, b->pre2, d->aug, d->aug ? d->table_rows : 0, idx, b->g, b->t, d->aug ? b->o : nullptr,
+                       d->aug ? b->q : nullptr, R, D, stream);
+}
+
+extern "C" int64_t ttam_tower_bwd_workspace_bytes(const ttam_tower_desc* d, int64_t R) {
+  if (!d || R <= 0) return 256;
+  int64_t m = ttam_linear_wgrad_workspace_bytes(R, d->D, d->Hg);
+  const int64_t c[3] = {ttam_linear_wgrad_workspace_bytes(R, d->Hg, 2 * d->D), ttam_linear_wgrad_workspace_bytes(R, d->D, d->H),
+                        ttam_linear_wgrad_workspace_bytes(R, d->H, d->F)};
+  for (int i = 0; i < 3; ++i) m = c[i] > m ? c[i] : m;
+  return m;
+}
+
+extern "C" int ttam_tower_bwd(const ttam_tower_desc* d, const int64_t* idx, int64_t R, const ttam_tower_bufs* b, const float* dt,
+                              const ttam_tower_grads* g, void* workspace, int64_t workspace_bytes, void* stream) {
+  TTAM_CHECK_ARG(d && b && g && dt && workspace && (R == 0 || idx), "tower_bwd: null pointer");
+  TTAM_CHECK_ARG(g->dpre2 && g->dz && g->dpre1 && g->dhd && g->dW1 && g->db1 && g->dW2 && g->db2 && g->dG1 && g->dc1 && g->dG2 && g->dc2,
+                 "tower_bwd: missing gradient buffer");
+  if (R == 0) return TTAM_OK;
+  const int64_t D = d->D, H = d->H, Hg = d->Hg, F = d->F;
+  const int acc = g->accumulate;
+  const int prec = d->precision;
+  // dpre2 = dt (e-f) g (1-g);  dz = [dt g ; dt (1-g)]
+  TTAM_TRY(ttam_gate_bwd(dt, b->z, b->g, g->dpre2, g->dz, R, D, stream));
+  TTAM_TRY(ttam_linear_wgrad(g->dpre2, D, b->a, Hg, nullptr, g->dG2, g->dc2, R, D, Hg, acc, workspace, workspace_bytes, prec, stream));
+  TTAM_TRY(ttam_linear_dgrad(g->dpre2, D, d->G2, g->dpre1, Hg, b->a, Hg, 1, 1.f, 0, R, D, Hg, prec, stream));
+  TTAM_TRY(ttam_linear_wgrad(g->dpre1, Hg, b->z, 2 * D, nullptr, g->dG1, g->dc1, R, Hg, 2 * D, acc, workspace, workspace_bytes, prec, stream));
+  TTAM_TRY(ttam_linear_dgrad(g->dpre1, Hg, d->G1, g->dz, 2 * D, nullptr, 0, 0, 1.f, 1, R, Hg, 2 * D, prec, stream));
+  // feature MLP: df = dz[:, D:]
+  const float* df = g->dz + D;
+  TTAM_TRY(ttam_linear_wgrad(df, 2 * D, b->hd, H, nullptr, g->dW2, g->db2, R, D, H, acc, workspace, workspace_bytes, prec, stream));
+  const float scale = d->dropout_p > 0.f ? 1.f / (1.f - d->dropout_p) : 1.f;
+  TTAM_TRY(ttam_linear_dgrad(df, 2 * D, d->W2, g->dhd, H, b->hd, H, 1, scale, 0, R, D, H, prec, stream));
+  return ttam_linear_wgrad(g->dhd, H, d->X, d->ldx, idx, g->dW1, g->db1, R, H, F, acc, workspace, workspace_bytes, prec, stream);
+}

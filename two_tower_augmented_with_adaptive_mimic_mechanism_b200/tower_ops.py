@@ -121,12 +121,85 @@ def _w_for(W: torch.Tensor, bufs, precision: str) -> torch.Tensor:
     return view
 
 
+# ------------------------------------------------------------------------------------------------
+# composite path: the whole gated / 1-hidden-layer-ReLU tower as ONE C call per direction (ttam_tower_fwd / _bwd)
+# ------------------------------------------------------------------------------------------------
+def _composite_ok(plan: TowerPlan, X, gather: bool, bufs) -> bool:
+    return (bufs is not None and gather and X is not None and plan.fusion == "gated" and plan.fe_kind == "mlp"
+            and len(plan.fe_layers) == 2 and plan.activation == "relu" and plan.gate is not None
+            and plan.fe_layers[1][0].shape[0] == plan.D)
+
+
+def _tower_desc(plan: TowerPlan, X, W1, p_drop, seed, rng_base, state, precision, augment=True):
+    (_, b1), (W2, b2) = plan.fe_layers
+    G1, c1, G2, c2 = plan.gate
+    d = F._lib.TowerDesc()
+    d.table, d.table_rows, d.D = plan.table.data_ptr(), plan.table.shape[0], plan.D
+    d.aug = plan.aug.data_ptr() if (plan.aug is not None and augment) else None
+    d.X, d.ldx, d.F = X.data_ptr(), X.stride(0), X.shape[1]
+    d.W1, d.ldw1, d.b1, d.H = W1.data_ptr(), W1.stride(0), b1.data_ptr(), W1.shape[0]
+    d.W2, d.b2 = W2.data_ptr(), b2.data_ptr()
+    d.G1, d.c1, d.Hg, d.G2, d.c2 = G1.data_ptr(), c1.data_ptr(), G1.shape[0], G2.data_ptr(), c2.data_ptr()
+    d.dropout_p, d.precision, d.seed, d.rng_base = float(p_drop), F.PREC[precision], int(seed), int(rng_base)
+    d.state = None if state is None else state.data_ptr()
+    return d
+
+
+def _tower_forward_composite(plan, idx, X, *, train, bufs, seed, rng_base, state, precision, want_q, augment) -> Cache:
+    R, D, dev = idx.numel(), plan.D, plan.table.device
+    H, Hg = plan.fe_layers[0][0].shape[0], plan.gate[0].shape[0]
+    p_drop = plan.dropout if train else 0.0
+    W1 = _w_for(plan.fe_layers[0][0], bufs, precision)
+    c = Cache(idx=idx, X=X, gather=True, train=train, R=R, seed=seed, rng_base=rng_base, mode="gated", composite=True)
+    c.z = _buf(bufs, "z", (R, 2 * D), dev)
+    c.hd, c.pre = [_buf(bufs, "hd0", (R, H), dev)], [None]
+    c.a, pre2 = _buf(bufs, "a", (R, Hg), dev), _buf(bufs, "pre2", (R, D), dev)
+    c.g, c.t = _buf(bufs, "g", (R, D), dev), _buf(bufs, "t", (R, D), dev)
+    has_aug = plan.aug is not None and augment
+    o = _buf(bufs, "o", (R, D), dev) if has_aug else None
+    q = _buf(bufs, "q", (R, D), dev) if (has_aug and want_q) else None
+    c.desc = _tower_desc(plan, X, W1, p_drop, seed, rng_base, state, precision, augment)
+    b = F._lib.TowerBufs()
+    b.z, b.hd, b.a, b.pre2, b.g, b.t = (t.data_ptr() for t in (c.z, c.hd[0], c.a, pre2, c.g, c.t))
+    b.o, b.q = (None if o is None else o.data_ptr()), (None if q is None else q.data_ptr())
+    c.cbufs = b
+    F.check(F.lib().ttam_tower_fwd(c.desc, idx.data_ptr(), R, b, F._stream()), "tower_fwd")
+    c.o, c.q = (o if has_aug else c.t), q
+    return c
+
+
+def _tower_backward_composite(plan, c: Cache, dt, grads: dict, bufs):
+    R, D, dev = c.R, plan.D, dt.device
+    (W1, b1), (W2, b2) = plan.fe_layers
+    G1, c1, G2, c2 = plan.gate
+    g = F._lib.TowerGrads()
+    dz = _buf(bufs, "dz", (R, 2 * D), dev)
+    g.dz, g.dpre2 = dz.data_ptr(), _buf(bufs, "dpre2", (R, D), dev).data_ptr()
+    g.dpre1, g.dhd = _buf(bufs, "dpre1", (R, G1.shape[0]), dev).data_ptr(), _buf(bufs, "dpre_h0", (R, W1.shape[0]), dev).data_ptr()
+    acc = id(W1) in grads
+    for W, b, fw, fb in ((W1, b1, "dW1", "db1"), (W2, b2, "dW2", "db2"), (G1, c1, "dG1", "dc1"), (G2, c2, "dG2", "dc2")):
+        if not acc:
+            grads[id(W)] = _buf(bufs, f"dw{id(W)}", tuple(W.shape), dev)
+            grads[id(b)] = _buf(bufs, f"db{id(b)}", (b.shape[0], 1), dev).view(-1)
+        setattr(g, fw, grads[id(W)].data_ptr()); setattr(g, fb, grads[id(b)].data_ptr())
+    g.accumulate = 1 if acc else 0
+    L = F.lib()
+    ws = F.workspace(L.ttam_tower_bwd_workspace_bytes(c.desc, R), dev, "wgrad")
+    dt = dt if dt.is_contiguous() else dt.contiguous()
+    F.check(L.ttam_tower_bwd(c.desc, c.idx.data_ptr(), R, c.cbufs, dt.data_ptr(), g, ws.data_ptr(), ws.numel(), F._stream()),
+            "tower_bwd")
+    return dz[:, :D]
+
+
 def tower_forward(plan: TowerPlan, idx: torch.Tensor, X: Optional[torch.Tensor], *, gather: bool, train: bool,
                   bufs: Optional[dict] = None, seed: int = 0, rng_base: int = 0, state=None, precision="fp32",
                   want_q: bool = False, augment: bool = True) -> Cache:
     """idx [R] int64.  X: feature matrix; if `gather` its rows are X[idx] (fused index_select, reference
     training.py:743-775), else X is already [R, F].  Returns a cache with t (base output), o (= t + aug[idx]
     when the plan has an augmentation table), q and the intermediates the backward needs."""
+    if _composite_ok(plan, X, gather, bufs) and idx.numel() > 0:
+        return _tower_forward_composite(plan, idx, X, train=train, bufs=bufs, seed=seed, rng_base=rng_base, state=state,
+                                        precision=precision, want_q=want_q, augment=augment)
     R, D = idx.numel(), plan.D
     dev = plan.table.device
     c = Cache(idx=idx, X=X, gather=gather, train=train, R=R, seed=seed, rng_base=rng_base)
@@ -223,6 +296,8 @@ def tower_backward(plan: TowerPlan, c: Cache, dt: torch.Tensor, grads: dict, *, 
                    state=None, precision="fp32"):
     """dt [R, out_dim] = dL/dt.  Dense weight gradients are written to grads[id(param)] (accumulated when the
     key exists).  Returns de [R, D] (a view; rows of dL/dE[idx], duplicates NOT yet summed)."""
+    if c.composite:
+        return _tower_backward_composite(plan, c, dt, grads, bufs)
     R, D = c.R, plan.D
     dev = dt.device
     X, gidx = c.X, (c.idx if c.gather else None)
