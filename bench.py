@@ -169,6 +169,10 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("TTAM_PRECISION", "fp32"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-retrieval", action="store_true")
+    ap.add_argument("--batch", type=int, default=None, help="samples per GPU per step (default 8192; sweep: 4096..65536)")
+    ap.add_argument("--mode", default="hybrid", choices=["hybrid", "sparse", "dense"],
+                    help="optimiser sweep (BASELINE configs[4]): hybrid = AdamW + SparseAdam (reference default), "
+                         "sparse = embedding-only towers, mimic off, all SparseAdam, dense = sparse:false (AdamW semantics on every table)")
     ap.add_argument("--no-graph", action="store_true", help="N=1: launch the step eagerly instead of replaying a CUDA graph (diagnostic)")
     ap.add_argument("--small", action="store_true", help="1/16-size tables (debugging only; not a valid bench line)")
     args = ap.parse_args()
@@ -178,10 +182,17 @@ def main():
     c = dict(CFG)
     if args.small:
         c.update(NU=c["NU"] // 16, NI=c["NI"] // 16)
+    if args.batch:
+        c["B"] = int(args.batch)
     W = max(args.warmup, 3)
     K = args.steps
     workload = (f"synthetic {c['NU']} users x {c['NI']} items, D={c['D']}, F={c['F']}->H={c['H']}->D MLPs, gated fusion, "
                 f"adaptive mimic, B={c['B']}, {c['N']} sampled negatives, AdamW+SparseAdam")
+    if args.mode == "sparse":
+        workload = (f"synthetic {c['NU']} users x {c['NI']} items, D={c['D']}, embedding-only towers, no mimic, B={c['B']}, "
+                    f"{c['N']} sampled negatives, all-sparse SparseAdam")
+    elif args.mode == "dense":
+        workload = workload.replace("AdamW+SparseAdam", "all-dense AdamW (sparse:false, lazy-exact rows)")
 
     if args.impl == "reference":
         if rank != 0:
@@ -212,18 +223,22 @@ def main():
     # data-parallel with B samples per rank (weak scaling): SURVEY 8(e).  N = 1: everything on the one GPU.
     nu_l, ni_l = S.shard_size(c["NU"], rank, world), S.shard_size(c["NI"], rank, world)
     user_x, item_x = make_features(ni_l, nu_l, c["F"], c["n_cat"], c["n_auth"], dev, gen)
-    tower = {"type": "tower", "id_embedding": {"params": {"embedding_dim": c["D"], "sparse": True}},
+    tower = {"type": "tower", "id_embedding": {"params": {"embedding_dim": c["D"], "sparse": args.mode != "dense"}},
              "feature_encoder": {"type": "mlp", "hidden_dims": [c["H"]], "activation": "relu", "output_dim": c["D"], "dropout": 0.0},
              "fusion": "gated", "adaptive_mimic": {"hidden_dim": c["Hg"]}}
+    if args.mode == "sparse":
+        tower = {"type": "embedding", "params": {"embedding_dim": c["D"], "sparse": True}}
+    mimic = None if args.mode == "sparse" else \
+        tt.AdaptiveMimicMechanism(num_users=nu_l, num_items=ni_l, embedding_dim=c["D"]).to(dev)
     model = tt.TwoTowerModel(tt.build_tower_encoder(tower, num_embeddings=nu_l, feature_dim=c["F"], device=dev),
                              tt.build_tower_encoder(tower, num_embeddings=ni_l, feature_dim=c["F"], device=dev),
-                             adaptive_mimic=tt.AdaptiveMimicMechanism(num_users=nu_l, num_items=ni_l, embedding_dim=c["D"]).to(dev))
+                             adaptive_mimic=mimic)
     if world > 1:                      # replicas of the dense weights start identical
         for name, prm in model.named_parameters():
             if "embedding.weight" not in name and "augmented.weight" not in name:
                 dist.broadcast(prm.data, src=0)
     eng = tt.FusedEngine(model, optimizer="adamw", lr=c["lr"], weight_decay=c["wd"], precision=args.precision,
-                         loss_weights={"mimic_user": c["lambdas"][0], "mimic_item": c["lambdas"][1]},
+                         loss_weights={} if mimic is None else {"mimic_user": c["lambdas"][0], "mimic_item": c["lambdas"][1]},
                          max_steps=4 * (K + W) + 64)
     sh = tt.ShardedEngine(eng) if world > 1 else None
     users, pos, neg = make_batches(K + W, c, dev, gen)          # global row ids

@@ -603,32 +603,26 @@ __global__ void __launch_bounds__(256) exact_rows_kernel(FinalParams p) {
 }
 
 // ---- host ---------------------------------------------------------------------------------------------------------------
-// Item splits per query block.  A unit costs max(MMA, epilogue) in units of one 256-item tile of tensor-core time:
-// the epilogue scans every tile (~0.5) and pays ~kKeep * (1 + ln(n / kKeep)) list insertions per query row for a stream
-// of n items, so many short streams are much worse than few long ones; splits only exist to fill the SMs when there
-// are fewer query blocks than SMs and to trim the last wave.
+// Item splits per query block.  A split costs more than it saves as soon as the query blocks alone fill the SMs: every
+// split runs its own threshold warm-up (the expensive early part of a stream, where most scores still beat the row's
+// threshold) and adds a list to merge.  Measured at Q = 100 k x 2 M (391 query blocks, 148 SMs): S = 1: 76.9 ms,
+// S = 2: 96.6 ms, S = 3: 106.0 ms, S = 4: 120.0 ms.  Splits therefore only exist to occupy SMs that would otherwise idle.
 static int choose_splits(int64_t Q, int64_t N) {
   const int64_t qblocks = ceil_div(Q, kQBlock), tiles = ceil_div(N, kBN);
   const int64_t sms = num_sms();
-  int best = 1;
-  double best_cost = 1e300;
-  for (int s = 1; s <= kMaxSplits; ++s) {
-    if (s > tiles) break;
-    const double t = (double)ceil_div(tiles, s);
-    const double n = t * kBN;
-    const double inserts = 160.0 * (1.0 + log(n / kKeep > 1.0 ? n / kKeep : 1.0));
-    const double unit = fmax(t, 0.5 * t + inserts) + 48.0;
-    const double cost = (double)ceil_div(qblocks * s, sms) * unit;
-    if (cost < best_cost * 0.98) {
-      best_cost = cost;
-      best = s;
-    }
+  int64_t best = 1;
+  if (qblocks < sms) {
+    best = sms / qblocks;
+    if (best > kMaxSplits) best = kMaxSplits;
+    const int64_t min_tiles = 64;  // a split shorter than this is all warm-up
+    if (best > tiles / min_tiles) best = tiles / min_tiles;
+    if (best < 1) best = 1;
   }
   if (const char* e = getenv("TTAM_TOPK_SPLITS")) {
     const int v = atoi(e);
     if (v >= 1 && v <= kMaxSplits && v <= tiles) best = v;
   }
-  return best;
+  return (int)best;
 }
 
 struct Workspace {

@@ -50,8 +50,7 @@ class ShardedEngine:
         eng, W = self.eng, self.world
         B, N = neg.shape
         items = torch.cat([pos.reshape(-1), neg.reshape(-1)])
-        ex_u = S.Exchange(users, W, self.group)
-        ex_i = S.Exchange(items, W, self.group)
+        ex_u, ex_i = S.Exchange.build_many([users, items], W, self.group)
         if ex_u.n_owned == 0 or ex_i.n_owned == 0:
             raise RuntimeError("a rank owns none of the rows requested in this step; use a larger batch")
         self.last_exchange_rows = (ex_u.n_owned, ex_i.n_owned)

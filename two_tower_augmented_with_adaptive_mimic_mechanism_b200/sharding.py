@@ -58,7 +58,7 @@ def _world(group) -> int:
 class Exchange:
     """All-to-all route of one index set.  `idx` [R] int64 global row ids requested by this rank."""
 
-    def __init__(self, idx: torch.Tensor, world: Optional[int] = None, group=None) -> None:
+    def __init__(self, idx: torch.Tensor, world: Optional[int] = None, group=None, _counts=None) -> None:
         self.group = group
         self.world = W = _world(group) if world is None else int(world)
         idx = idx.reshape(-1)
@@ -71,16 +71,33 @@ class Exchange:
             return
         owner = owner_of(idx, W)
         self.order = torch.argsort(owner, stable=True)          # bucket by owner, original order kept inside a bucket
-        send_counts = torch.bincount(owner, minlength=W)
-        recv_counts = torch.empty_like(send_counts)
-        dist.all_to_all_single(recv_counts, send_counts, group=group)
-        # the split sizes of the payload exchanges are host integers: one small D2H per index set per step
-        both = torch.stack([send_counts, recv_counts]).cpu()
-        self.send_splits, self.recv_splits = both[0].tolist(), both[1].tolist()
+        if _counts is None:
+            send_counts = torch.bincount(owner, minlength=W)
+            recv_counts = torch.empty_like(send_counts)
+            dist.all_to_all_single(recv_counts, send_counts, group=group)
+            # the split sizes of the payload exchanges are host integers: one small D2H per step
+            both = torch.stack([send_counts, recv_counts]).cpu()
+            self.send_splits, self.recv_splits = both[0].tolist(), both[1].tolist()
+        else:
+            self.send_splits, self.recv_splits = _counts
         send_idx = idx[self.order]
         self.recv_idx = idx.new_empty(sum(self.recv_splits))
         dist.all_to_all_single(self.recv_idx, send_idx, self.recv_splits, self.send_splits, group=group)
         self.local_rows = local_row(self.recv_idx, W)
+
+    @staticmethod
+    def build_many(index_sets: list, world: Optional[int] = None, group=None) -> list:
+        """Exchanges for several index sets of one step with ONE count all-to-all and ONE host synchronisation."""
+        W = _world(group) if world is None else int(world)
+        if W == 1:
+            return [Exchange(ix, 1, group) for ix in index_sets]
+        n = len(index_sets)
+        send = torch.stack([torch.bincount(owner_of(ix.reshape(-1), W), minlength=W) for ix in index_sets], dim=1)  # [W, n]
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send.contiguous(), group=group)
+        both = torch.stack([send, recv]).cpu()                  # the step's only D2H of sizes
+        return [Exchange(ix, W, group, _counts=(both[0][:, j].tolist(), both[1][:, j].tolist()))
+                for j, ix in enumerate(index_sets)]
 
     @property
     def n_owned(self) -> int:
