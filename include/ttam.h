@@ -114,6 +114,16 @@ int ttam_gate_bwd(const float* dt, const float* z, const float* g, float* dpre2,
 int ttam_augment_fwd(const float* t, const float* aug_table, int64_t aug_rows, const int64_t* idx, float* o,
                      float* q_out, int64_t R, int64_t D, void* stream);
 
+/* ---- negative sampling (src/data/samplers.py:11-85) -------------------------------------------------------
+ * out[b, n] ~ U[0, num_items) with members of the user's positive set re-drawn, at most 1 + max_rounds draws each
+ * (the reference: 10 re-sampling rounds, then RuntimeError).  pos_keys: sorted int64 keys user * num_items + item of
+ * every known (user, item) positive (n_keys may be 0).  *fail_flag is set to 1 when a slot is still a positive after
+ * the last round (the caller raises).  Draws: Philox4x32-10 keyed by (seed, offset [+ state->rng_offset], element,
+ * round): statistical, not bit, parity with torch.randint. */
+int ttam_sample_negatives(const int64_t* users, int64_t B, int64_t N, int64_t num_items, const int64_t* pos_keys,
+                          int64_t n_keys, int max_rounds, uint64_t seed, uint64_t offset,
+                          const ttam_step_state* state_dev, int64_t* out, int32_t* fail_flag, void* stream);
+
 /* ---- composite: one gated tower (1-hidden-layer ReLU MLP) per call -----------------------------------------
  * ttam_tower_fwd / ttam_tower_bwd enqueue the launch sequence of TowerEncoder.forward (encoders.py:221-255) +
  * _apply_aug (adaptive_mimic.py:88-95), resp. their autograd, with ONE C call (an eager step then makes ~10 calls

@@ -119,6 +119,7 @@ SIGNATURES = {
     "ttam_gate_fwd": (C.c_int, [_p, _p, _p, _i64, _p, _p, _p, _p, _p, _i64, _i64, _p]),
     "ttam_gate_bwd": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i64, _p]),
     "ttam_augment_fwd": (C.c_int, [_p, _p, _i64, _p, _p, _p, _i64, _i64, _p]),
+    "ttam_sample_negatives": (C.c_int, [_p, _i64, _i64, _i64, _p, _i64, _i32, _u64, _u64, _p, _p, _p, _p]),
     "ttam_tower_fwd": (C.c_int, [C.POINTER(TowerDesc), _p, _i64, C.POINTER(TowerBufs), _p]),
     "ttam_tower_bwd_workspace_bytes": (C.c_int64, [C.POINTER(TowerDesc), _i64]),
     "ttam_tower_bwd": (C.c_int, [C.POINTER(TowerDesc), _p, _i64, C.POINTER(TowerBufs), _p, C.POINTER(TowerGrads), _p, _i64, _p]),

@@ -169,11 +169,35 @@ struct MainParams {
   int64_t Q, N;
   int D, S;
   int qblocks, tiles_total, tiles_per_split;
+  int sample_tiles;  // T0: tiles of a unit's range visited first in sampling mode (0 = none)
   uint2* lists;     // [Q][S][kCap] raw {score bits, id}
   int32_t* cnts;    // [Q][S]
   float* taus;      // [Q][S]
   int debug;        // timing experiments only (TTAM_TOPK_DEBUG): 1 = epilogue drains nothing, 2 = no list appends,
                     // 4 = no TMA item loads after the first stages, 8 = MMA does not wait for the drain
+};
+
+// Tile sequence of one work unit (identical in the TMA, MMA and epilogue roles).  The first T0 iterations visit T0 tiles
+// spread evenly over the unit's range in SAMPLING mode: the epilogue only tracks, per query row, the 8 largest
+// 64-column maxima it sees, and the 8th of them becomes the row's starting threshold.  At least 8 items of the range
+// score that high; with T0 = 64 tiles (16 k items of 2 M) about a thousand do.  Should fewer than K items of the whole
+// corpus beat a row's starting threshold, the finalize kernel sees fewer than K candidates and sends that query to the
+// exact fallback, so the result stays exact.  Then every tile of the range is visited in order, normally (the sampled
+// tiles a second time: +T0 tiles of tensor work, under 1 %).
+// Without this a row starts at -inf, and half of all list appends and most compactions of a stream happen in its
+// first 5 %.
+struct TileSeq {
+  int t0, n_tiles, T0, stride;
+  __device__ __forceinline__ TileSeq(const MainParams& p, int s) {
+    t0 = s * p.tiles_per_split;
+    const int t1 = min(p.tiles_total, t0 + p.tiles_per_split);
+    n_tiles = t1 - t0;
+    T0 = min(p.sample_tiles, n_tiles / 8);
+    if (T0 < 4) T0 = 0;
+    stride = T0 > 0 ? n_tiles / T0 : 1;
+  }
+  __device__ __forceinline__ int count() const { return T0 + n_tiles; }
+  __device__ __forceinline__ int tile(int i) const { return i < T0 ? t0 + i * stride : t0 + (i - T0); }
 };
 
 template <int KBOX>
@@ -231,9 +255,9 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         for (int a = 0; a < kATiles; ++a)
           for (int kb = 0; kb < KBOX; ++kb)
             tma_load_2d(smem_a + (a * KBOX + kb) * kABoxBytes, &tmap_q, a_full, kb * kBoxK, qb * kQBlock + a * kBM);
-        const int t0 = s * p.tiles_per_split;
-        const int t1 = min(p.tiles_total, t0 + p.tiles_per_split);
-        for (int t = t0; t < t1; ++t, ++it) {
+        const TileSeq seq(p, s);
+        for (int i = 0; i < seq.count(); ++i, ++it) {
+          const int t = seq.tile(i);
           const int stage = it % C::kStages;
           mbar_wait_relaxed(b_empty + stage, ((it / C::kStages) & 1) ^ 1, 256);
           if ((p.debug & 4) && it >= (uint32_t)C::kStages) {  // timing experiment: the MMA re-reads stale tiles
@@ -256,10 +280,9 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       uint32_t it = 0, un = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x, ++un) {
         const int s = u / p.qblocks;
-        const int t0 = s * p.tiles_per_split;
-        const int t1 = min(p.tiles_total, t0 + p.tiles_per_split);
+        const TileSeq seq(p, s);
         mbar_wait(a_full, un & 1);
-        for (int t = t0; t < t1; ++t, ++it) {
+        for (int i = 0; i < seq.count(); ++i, ++it) {
           const int stage = it % C::kStages;
           mbar_wait(b_full + stage, (it / C::kStages) & 1);
           const uint64_t b_desc = b_desc0 + (uint64_t)((stage * C::kBStage) >> 4);
@@ -297,8 +320,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     uint32_t it = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       const int qb = u % p.qblocks, s = u / p.qblocks;
-      const int t0 = s * p.tiles_per_split;
-      const int t1 = min(p.tiles_total, t0 + p.tiles_per_split);
+      const TileSeq seq(p, s);
       const int64_t qrow = (int64_t)qb * kQBlock + a * kBM + row_in_tile;
       const bool valid = qrow < p.Q;
       float tau = valid ? -INFINITY : INFINITY;  // rows past the end never collect anything
@@ -363,9 +385,15 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           }
         }
       };
-      for (int t = t0; t < t1; ++t, ++it) {
+      float top[8];  // sampling mode: the 8 largest 64-column maxima seen so far, descending
+#pragma unroll
+      for (int j = 0; j < 8; ++j) top[j] = -INFINITY;
+      for (int i = 0; i < seq.count(); ++i, ++it) {
+        const int t = seq.tile(i);
+        const bool sampling = i < seq.T0;
         const bool tail = (t == p.tiles_total - 1) && (p.N % kBN != 0);  // TMA zero-filled rows past the corpus end
         if (p.debug & 8) continue;
+        if (i == seq.T0 && seq.T0 > 0 && valid) tau = top[7];  // start of the real pass: adopt the sampled threshold
         mbar_wait(acc_full + a, it & 1);
         tc_fence_after();
 #pragma unroll 1
@@ -378,9 +406,29 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
               const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * kBN + col);
               tmem_ld_32x32_issue(taddr, v0);
               tmem_ld_32x32_issue(taddr + 32u, v1);
-              make_room();
+              if (!sampling) make_room();
               tmem_ld_wait2(v0, v1);
-              process2(v0, v1, (uint32_t)t * kBN + (uint32_t)col, tail);
+              if (!sampling) {
+                process2(v0, v1, (uint32_t)t * kBN + (uint32_t)col, tail);
+              } else {
+                const uint32_t id0 = (uint32_t)t * kBN + (uint32_t)col;
+                float mx = -INFINITY;
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                  const float x0 = (tail && (int64_t)(id0 + e) >= p.N) ? -INFINITY : __uint_as_float(v0[e]);
+                  const float x1 = (tail && (int64_t)(id0 + 32 + e) >= p.N) ? -INFINITY : __uint_as_float(v1[e]);
+                  mx = fmaxf(mx, fmaxf(x0, x1));
+                }
+                if (mx > top[7]) {  // sorted insert: carry the smaller value down
+                  float carry = mx;
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    const float hi = fmaxf(top[j], carry);
+                    carry = fminf(top[j], carry);
+                    top[j] = hi;
+                  }
+                }
+              }
             }
           }
           tc_fence_before();
@@ -538,6 +586,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalParams p) {
     flag = true;  // too many near-ties to re-score here
   }
   if (s_tq >= thr) flag = true;  // something a list dropped (score <= s_tq) could still belong to the top K
+  if (total < p.K) flag = true;  // the sampled starting threshold admitted fewer than K items (never seen in practice)
 #pragma unroll
   for (int i = 0; i < ITEMS; ++i) {
     const int rank = tid * ITEMS + i;
@@ -704,6 +753,8 @@ extern "C" int ttam_topk_bf16(const uint16_t* q, const uint16_t* items, int64_t 
   mp.tiles_total = (int)ceil_div(N, kBN);
   mp.tiles_per_split = (int)ceil_div(mp.tiles_total, S);
   mp.lists = w.lists; mp.cnts = w.cnts; mp.taus = w.taus;
+  mp.sample_tiles = 64;
+  if (const char* e = getenv("TTAM_TOPK_SAMPLE_TILES")) mp.sample_tiles = atoi(e);
   {
     const char* dbg = getenv("TTAM_TOPK_DEBUG");
     mp.debug = dbg ? atoi(dbg) : 0;

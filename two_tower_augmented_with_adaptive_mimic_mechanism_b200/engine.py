@@ -67,6 +67,15 @@ class FusedEngine:
                 seen.add(id(p))
                 self.dense.append(p)
         need_m = self.kind != "sgd" or self.momentum != 0.0
+        # dense gradients live in ONE flat buffer (views handed to the wgrad kernels): a data-parallel all-reduce needs
+        # no staging copies
+        pad = lambda n: (n + 63) // 64 * 64            # every view starts on a 256-byte boundary
+        self.dense_grad_flat = torch.zeros(sum(pad(p.numel()) for p in self.dense), dtype=torch.float32, device=dev)
+        off = 0
+        self._dense_grad_views = {}
+        for p in self.dense:
+            self._dense_grad_views[id(p)] = self.dense_grad_flat[off:off + p.numel()]
+            off += pad(p.numel())
         self.dense_m = [torch.zeros_like(p) for p in self.dense] if need_m else None
         self.dense_v = [torch.zeros_like(p) for p in self.dense] if self.kind != "sgd" else None
         # ---- tables
@@ -79,13 +88,25 @@ class FusedEngine:
         self.state = F.new_step_state(dev, 0, 0)
         self.scal_dense = F.adam_scalar_table(self.max_steps, self.lr, self.dense_betas, dev)
         self.scal_sparse = F.adam_scalar_table(self.max_steps, self.lr, self.sparse_betas, dev)
-        self.bufs_u: dict = {}
-        self.bufs_i: dict = {}
+        self.bufs_u = self._grad_bufs(self.user)
+        self.bufs_i = self._grad_bufs(self.item)
         self.misc: dict = {}
         self._graphs: dict = {}
         self._xpad: dict = {}
 
     # --------------------------------------------------------------------------------------------
+    def _grad_bufs(self, plan: TowerPlan) -> dict:
+        """Buffer dict of one tower, pre-seeded with the weight-gradient views of the flat dense-gradient buffer
+        (tower_ops looks gradients up as dw<id> [shape of W] and db<id> [n, 1])."""
+        bufs = {}
+        for p in plan.dense_params():
+            v = self._dense_grad_views[id(p)]
+            if p.dim() == 2:
+                bufs[f"dw{id(p)}"] = v.view(p.shape)
+            else:
+                bufs[f"db{id(p)}"] = v.view(p.shape[0], 1)
+        return bufs
+
     def _add_table(self, name, weight, mode):
         t = _Table(name=name, weight=weight, mode=mode)
         if mode == "sparse_adam" or self.kind != "sgd":

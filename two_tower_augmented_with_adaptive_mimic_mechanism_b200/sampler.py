@@ -32,6 +32,7 @@ class PositiveSet:
 
 
 _cache: dict = {}
+_draws = 0   # Philox counter base: advances with every call so that successive batches draw fresh numbers
 
 
 def sample_negative_items(users: torch.Tensor, *, num_items: int, positives, num_negatives: int, device,
@@ -51,15 +52,29 @@ def sample_negative_items(users: torch.Tensor, *, num_items: int, positives, num
             _cache.clear()
             _cache[key] = entry
         pset = entry[1]
-    users = users.to(device)
+    users = users.to(device).contiguous()
     B = users.shape[0]
+    if users.is_cuda:
+        # one launch: every (row, slot) draws and re-draws on its own (csrc/sampler.cu)
+        from . import functional as F
+        global _draws
+        neg = torch.empty((B, num_negatives), dtype=torch.int64, device=users.device)
+        fail = torch.zeros(1, dtype=torch.int32, device=users.device)
+        seed = int(generator.initial_seed()) if generator is not None else int(torch.initial_seed())
+        F.check(F.lib().ttam_sample_negatives(users.data_ptr(), B, num_negatives, int(num_items), F._ptr(pset.keys if pset.keys.numel() else None),
+                                              pset.keys.numel(), int(max_rounds), seed & 0xFFFFFFFFFFFFFFFF, _draws, None,
+                                              neg.data_ptr(), fail.data_ptr(), F._stream()), "sample_negatives")
+        _draws += B * num_negatives * (max_rounds + 1)
+        if pset.keys.numel() and int(fail.item()):
+            raise RuntimeError("Exceeded resampling attempts while drawing negatives.")
+        return neg
     neg = torch.randint(0, num_items, (B, num_negatives), device=device, generator=generator)
     if pset.keys.numel() == 0:
         return neg
     u2 = users.view(-1, 1).expand(B, num_negatives)
     bad = pset.contains(u2, neg)
     attempts = 0
-    while bool(bad.any()):               # one host sync per round; the common case leaves after the first check
+    while bool(bad.any()):               # host-side index logic only (CPU tensors: unit tests of the contract)
         redraw = torch.randint(0, num_items, (B, num_negatives), device=device, generator=generator)
         neg = torch.where(bad, redraw, neg)
         bad = pset.contains(u2, neg)

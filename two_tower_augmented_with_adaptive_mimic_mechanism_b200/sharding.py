@@ -51,6 +51,16 @@ def unshard_rows(shards: list) -> torch.Tensor:
     return out
 
 
+def bucket_order(owner: torch.Tensor, world: int) -> torch.Tensor:
+    """Stable permutation that groups positions by owner.  CUDA: one radix pass over log2(W) bits (ttam_sort_rows);
+    CPU (gloo tests): torch's stable argsort."""
+    if owner.is_cuda:
+        from . import functional as F
+        _, perm = F.sort_rows(owner.contiguous(), world)
+        return perm
+    return torch.argsort(owner, stable=True)
+
+
 def _world(group) -> int:
     return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
 
@@ -70,7 +80,7 @@ class Exchange:
             self.send_splits = self.recv_splits = [self.n_req]
             return
         owner = owner_of(idx, W)
-        self.order = torch.argsort(owner, stable=True)          # bucket by owner, original order kept inside a bucket
+        self.order = bucket_order(owner, W)                     # bucket by owner, original order kept inside a bucket
         if _counts is None:
             send_counts = torch.bincount(owner, minlength=W)
             recv_counts = torch.empty_like(send_counts)
@@ -126,8 +136,18 @@ class Exchange:
 
 
 def all_reduce_flat(tensors: list, group=None) -> None:
-    """Sum the tensors over the ranks in ONE collective (the dense MLP / gate gradients: ~1.3 MB at D=96, H=192)."""
+    """Sum the tensors over the ranks in ONE collective (the dense MLP / gate gradients: ~1.3 MB at D=96, H=192).
+    When the tensors are consecutive views of one flat buffer (FusedEngine lays its dense gradients out that way) the
+    buffer is reduced in place, without staging copies."""
     if _world(group) == 1 or not tensors:
+        return
+    base = tensors[0]._base if tensors[0]._base is not None else None
+    if base is not None and base.dim() == 1 and all(t._base is base for t in tensors):
+        # one span of the shared buffer covers them all (alignment gaps and gradients nobody asked for ride along)
+        lo = min(t.data_ptr() for t in tensors)
+        hi = max(t.data_ptr() + t.numel() * t.element_size() for t in tensors)
+        first = (lo - base.data_ptr()) // base.element_size()
+        dist.all_reduce(base[first:first + (hi - lo) // base.element_size()], group=group)
         return
     flat = torch.cat([t.reshape(-1) for t in tensors])
     dist.all_reduce(flat, group=group)
