@@ -37,6 +37,10 @@ extern "C" {
 /* arithmetic of the GEMM-shaped ops */
 #define TTAM_PREC_FP32 0 /* SIMT FFMA, fp32 in / fp32 accumulate (bit-faithful to the fp32 reference up to summation order) */
 #define TTAM_PREC_TF32 1 /* tcgen05 kind::tf32: operands rounded to TF32 (round-to-nearest), fp32 accumulate in TMEM */
+/* OR-ed into TTAM_PREC_TF32: the operand already holds TF32-representable values (ttam_round_tf32 when it was laid
+ * out), so the GEMM skips its in-place rounding pass for it.  X: x of linear_fwd / linear_wgrad; W: w of linear_fwd. */
+#define TTAM_PREC_X_ROUNDED 0x100
+#define TTAM_PREC_W_ROUNDED 0x200
 #define TTAM_PREC_BF16 2 /* reserved (the retrieval path, ttam_topk_bf16, is the bf16 tensor-core kernel) */
 
 /* dense optimiser kinds (training.py:1315-1333) */
@@ -67,6 +71,8 @@ int ttam_device_ok(void);
  * feature matrices (training.py:743,747,775). */
 int ttam_gather_rows_f32(const float* table, int64_t ld_table, int64_t num_rows, const int64_t* idx,
                          float* out, int64_t ld_out, int64_t R, int64_t ncols, void* stream);
+/* in place: x[r, 0:ncols] <- nearest TF32-representable value (10-bit mantissa, ties away from zero: cvt.rna.tf32) */
+int ttam_round_tf32(float* x, int64_t ld, int64_t R, int64_t ncols, void* stream);
 /* fp32 -> bf16 (round-to-nearest-even) row cast, used to build the retrieval corpus */
 int ttam_cast_f32_to_bf16(const float* src, int64_t ld_src, uint16_t* dst, int64_t ld_dst, int64_t R,
                           int64_t ncols, void* stream);
@@ -143,6 +149,7 @@ typedef struct {
   const float *G2, *c2; /* [D, Hg], [D] */
   float dropout_p;
   int32_t precision;
+  int32_t x_rounded, w1_rounded; /* X / W1 hold TF32-representable values (see TTAM_PREC_X_ROUNDED) */
   uint64_t seed, rng_base;
   const ttam_step_state* state;
 } ttam_tower_desc;

@@ -112,6 +112,31 @@ def test_device_sampler_excludes_positives(tt):
     assert int(neg.min()) >= 0 and int(neg.max()) < 10
 
 
+def test_device_sampler_kernel_statistics_and_failure(tt):
+    """csrc/sampler.cu: draws are uniform over the non-positive items, fresh on every call, and a user whose
+    positives cover every item raises like the reference (samplers.py:77-80)."""
+    from two_tower_augmented_with_adaptive_mimic_mechanism_b200.sampler import sample_negative_items
+    dev_ = torch.device("cuda")
+    NI = 50
+    positives = {u: set(range(0, NI, 10)) for u in range(8)}           # items 0, 10, .. 40 are positives of users 0..7
+    users = torch.arange(8, device="cuda").repeat(4096)
+    neg = sample_negative_items(users, num_items=NI, positives=positives, num_negatives=5, device=dev_)
+    assert neg.shape == (8 * 4096, 5) and neg.dtype == torch.long
+    assert int((neg % 10 == 0).sum()) == 0 and int(neg.min()) >= 1 and int(neg.max()) < NI
+    allowed = torch.tensor([i for i in range(NI) if i % 10], device="cuda")
+    counts = torch.bincount(neg.reshape(-1), minlength=NI)[allowed].double()
+    expect = neg.numel() / allowed.numel()
+    assert float(((counts - expect) ** 2 / expect).sum()) < 95.0         # chi-square, 44 dof: p ~ 1e-5 at 95
+    neg2 = sample_negative_items(users, num_items=NI, positives=positives, num_negatives=5, device=dev_)
+    assert not torch.equal(neg, neg2)
+    with pytest.raises(RuntimeError, match="Exceeded resampling attempts"):
+        sample_negative_items(torch.zeros(64, dtype=torch.long, device="cuda"), num_items=3, positives={0: {0, 1, 2}},
+                              num_negatives=4, device=dev_)
+    with pytest.raises(tt.TtamError, match="num_negatives must be greater than zero"):
+        tt.functional.check(tt.lib().ttam_sample_negatives(users.data_ptr(), 8, 0, NI, None, 0, 10, 0, 0, None,
+                                                          neg.data_ptr(), neg.data_ptr(), 0), "sample_negatives")
+
+
 # ---------------------------------------------------------------------------------------------
 # tcgen05 path (bf16 operands): ids AND canonical scores bit-exact against the oracle on the same bf16 values
 # ---------------------------------------------------------------------------------------------

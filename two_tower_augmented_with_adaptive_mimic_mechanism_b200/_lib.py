@@ -22,6 +22,7 @@ NVCC_FLAGS = [
 
 ACT = {"none": 0, None: 0, "identity": 0, "relu": 1, "gelu": 2, "tanh": 3, "selu": 4}
 PREC = {"fp32": 0, "tf32": 1, "bf16": 2}
+PREC_X_ROUNDED, PREC_W_ROUNDED = 0x100, 0x200
 OPT = {"adamw": 0, "adam": 1, "sgd": 2}
 MAX_TENSORS = 48
 
@@ -42,7 +43,8 @@ class TowerDesc(C.Structure):
         ("W1", C.c_void_p), ("b1", C.c_void_p), ("ldw1", C.c_int64), ("H", C.c_int64),
         ("W2", C.c_void_p), ("b2", C.c_void_p), ("G1", C.c_void_p), ("c1", C.c_void_p), ("Hg", C.c_int64),
         ("G2", C.c_void_p), ("c2", C.c_void_p),
-        ("dropout_p", C.c_float), ("precision", C.c_int32), ("seed", C.c_uint64), ("rng_base", C.c_uint64),
+        ("dropout_p", C.c_float), ("precision", C.c_int32), ("x_rounded", C.c_int32), ("w1_rounded", C.c_int32),
+        ("seed", C.c_uint64), ("rng_base", C.c_uint64),
         ("state", C.c_void_p),
     ]
 
@@ -108,6 +110,7 @@ SIGNATURES = {
     "ttam_launch_count": (C.c_int64, []),
     "ttam_device_ok": (C.c_int, []),
     "ttam_gather_rows_f32": (C.c_int, [_p, _i64, _i64, _p, _p, _i64, _i64, _i64, _p]),
+    "ttam_round_tf32": (C.c_int, [_p, _i64, _i64, _i64, _p]),
     "ttam_cast_f32_to_bf16": (C.c_int, [_p, _i64, _p, _i64, _i64, _i64, _p]),
     "ttam_advance_step": (C.c_int, [_p, _u64, _p]),
     "ttam_act_fwd": (C.c_int, [_p, _p, _i64, _i64, _i32, _f, _u64, _u64, _p, _p]),

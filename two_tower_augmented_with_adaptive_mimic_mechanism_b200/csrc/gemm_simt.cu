@@ -96,8 +96,10 @@ extern "C" int ttam_linear_fwd(const float* x, int64_t ldx, const int64_t* gathe
   TTAM_CHECK_ARG(act >= TTAM_ACT_NONE && act <= TTAM_ACT_SELU, "linear_fwd: unknown activation %d", act);
   if (M == 0) return TTAM_OK;
   TTAM_CHECK_ARG(ldw >= K, "linear_fwd: ldw < K");
+  const int prerounded = (precision >> 8) & 3;  // TTAM_PREC_X_ROUNDED / TTAM_PREC_W_ROUNDED
+  precision &= 0xFF;
   if (precision == TTAM_PREC_TF32)
-    return tc_linear_fwd(x, ldx, gather, w, ldw, bias, y, ldy, M, N, K, act, dropout_p, seed, offset, state_dev,
+    return tc_linear_fwd(x, ldx, gather, w, ldw, bias, y, ldy, M, N, K, act, dropout_p, seed, offset, state_dev, prerounded,
                          (cudaStream_t)stream);
   if (precision != TTAM_PREC_FP32) {
     set_error("linear_fwd: precision %d is not built into this library", precision);
@@ -120,6 +122,7 @@ extern "C" int ttam_linear_dgrad(const float* dy, int64_t lddy, const float* w, 
   TTAM_CHECK_ARG(M >= 0 && N > 0 && K > 0 && lddy >= N && lddx >= K, "linear_dgrad: bad shape");
   TTAM_CHECK_ARG(mask_mode == 0 || (mask_mode == 1 && aux && ldaux >= K), "linear_dgrad: bad mask arguments");
   if (M == 0) return TTAM_OK;
+  precision &= 0xFF;
   if (precision == TTAM_PREC_TF32)
     return tc_linear_dgrad(dy, lddy, w, dx, lddx, aux, ldaux, mask_mode, scale, accumulate, M, N, K, (cudaStream_t)stream);
   if (precision != TTAM_PREC_FP32) {
@@ -149,6 +152,8 @@ extern "C" int ttam_linear_wgrad(const float* dy, int64_t lddy, const float* x, 
                                  void* workspace, int64_t workspace_bytes, int precision, void* stream) {
   TTAM_CHECK_ARG(dy && x && dw && workspace, "linear_wgrad: null pointer");
   TTAM_CHECK_ARG(M > 0 && N > 0 && K > 0 && lddy >= N && ldx >= K, "linear_wgrad: bad shape");
+  const int prerounded = (precision >> 8) & 3;
+  precision &= 0xFF;
   if (precision != TTAM_PREC_FP32 && precision != TTAM_PREC_TF32) {
     set_error("linear_wgrad: precision %d is not built into this library", precision);
     return TTAM_EUNSUPPORTED;
@@ -164,7 +169,7 @@ extern "C" int ttam_linear_wgrad(const float* dy, int64_t lddy, const float* x, 
   float* partial_b = partial_w + (int64_t)splits * N * K;
   if (precision == TTAM_PREC_TF32) {
     int real = 0;
-    const int rc = tc_linear_wgrad_partials(dy, lddy, x, ldx, gather, partial_w, db ? partial_b : nullptr, M, N, K, &real, s);
+    const int rc = tc_linear_wgrad_partials(dy, lddy, x, ldx, gather, partial_w, db ? partial_b : nullptr, M, N, K, &real, prerounded, s);
     if (rc != TTAM_OK) return rc;
     const int64_t numel = N * K;
     const int blocks = (int)std::min<int64_t>(ceil_div(numel, 256), (int64_t)num_sms() * 8);

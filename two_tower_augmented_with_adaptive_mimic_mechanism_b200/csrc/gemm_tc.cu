@@ -43,6 +43,7 @@ struct TcP {
   int bn;       // N tile: multiple of 32, <= 256
   int stages;
   int vecA, vecB, vecC;  // 16-byte accesses allowed (base and leading dimension aligned)
+  int roundA, roundB;    // 0: the operand already holds TF32-representable values (rounded when it was laid out)
   int transposed;        // store C(m,n) at C[z][n*ldc + m]
   float* colsum_b;       // MN-major B only: colsum_b[z][n] = sum over this CTA's reduction range of B(n, k)  (bias gradient)
   const float* bias;
@@ -81,10 +82,11 @@ __device__ __forceinline__ void cp_async_wait_pending(int n) {  // wait until at
   }
 }
 // one 16-byte piece: 4 floats starting at src, the first n_valid of them real (aligned source -> one 16-byte copy)
-__device__ __forceinline__ void copy_piece(uint32_t dst, const float* src, int n_valid, bool vec, const float* safe) {
+template <bool VEC>
+__device__ __forceinline__ void copy_piece(uint32_t dst, const float* src, int n_valid, const float* safe) {
   n_valid = n_valid < 0 ? 0 : (n_valid > 4 ? 4 : n_valid);
   if (n_valid == 0) src = safe;
-  if (vec) {
+  if (VEC) {
     cp_async16(dst, src, n_valid * 4);
   } else {
 #pragma unroll
@@ -97,61 +99,9 @@ __device__ __forceinline__ void round_piece(uint8_t* ptr) {
   *reinterpret_cast<uint4*>(ptr) = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
 }
 
-// The 16-byte pieces of one stage that THIS thread copies (and later rounds).  f(byte offset in the stage, source
-// pointer or nullptr, number of valid floats, ordinal: -1 for an A piece, else the B pass index: for an MN-major B the
-// lane's column chunk is lane + 32 * ordinal).  K-major tile: piece id = t + 256 j -> row (t >> 3) + 32 j, 16-byte chunk
-// t & 7 of the row's 128 bytes.  MN-major tile: warp w owns reduction rows w + 8 j, lanes walk the chunks along M/N.
-template <bool A_MN, bool B_MN, bool WITH_SRC, class Fn>
-__device__ __forceinline__ void for_each_piece(const TcP& p, int t, int m0, int n0, int k0, int k_hi, const float* const (&a_ptr)[4],
-                                               Fn&& f) {
-  const int warp = t >> 5, lane = t & 31;
-  const int kc = t & 7, krow = t >> 3;
-  const int bn = p.bn;
-  if (!A_MN) {
-    const int kq = k0 + 4 * kc;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int row = krow + 32 * j;
-      f((uint32_t)(row * 128 + ((kc ^ (row & 7)) << 4)), (WITH_SRC && a_ptr[j]) ? a_ptr[j] + kq : nullptr, a_ptr[j] ? k_hi - kq : 0, -1);
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int k = warp + 8 * j, kk = k0 + k, m = m0 + 4 * lane;
-      const float* src = nullptr;
-      if (WITH_SRC && kk < k_hi) src = p.A + (p.gatherA ? p.gatherA[kk] : (int64_t)kk) * p.lda + m;
-      f(mnmajor_tf32_offset(lane >> 3, k, lane & 7, kMnLbo), src, kk < k_hi ? p.M - m : 0, -1);
-    }
-  }
-  if (!B_MN) {
-    const int kq = k0 + 4 * kc;
-    const int nb_k = bn >> 5;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (j < nb_k) {
-        const int row = krow + 32 * j, n = n0 + row;
-        f(kABytes + (uint32_t)(row * 128 + ((kc ^ (row & 7)) << 4)), (WITH_SRC && n < p.N) ? p.B + (int64_t)n * p.ldb + kq : nullptr,
-          n < p.N ? k_hi - kq : 0, j);
-      }
-    }
-  } else {
-    const int nb_mn = (bn + 127) >> 7;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int k = warp + 8 * j, kk = k0 + k;
-      const float* row_ptr = nullptr;
-      if (WITH_SRC && kk < k_hi) row_ptr = p.B + (p.gatherB ? p.gatherB[kk] : (int64_t)kk) * p.ldb;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int cc = lane + 32 * h, n = n0 + 4 * cc;
-        if (h < nb_mn && 4 * cc < bn)
-          f(kABytes + mnmajor_tf32_offset(cc >> 3, k, cc & 7, kMnLbo), row_ptr ? row_ptr + n : nullptr, kk < k_hi ? p.N - n : 0, h);
-      }
-    }
-  }
-}
-
-template <bool A_MN, bool B_MN>
+// VEC: both operands may be copied with 16-byte LDGSTS (bases and leading dimensions 16-byte aligned); the scalar
+// instantiation exists for arbitrary layouts and is not the fast path.
+template <bool A_MN, bool B_MN, bool VEC>
 __global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(TcP p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -175,6 +125,7 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(TcP p) {
   const uint32_t tmem_cols = bn <= 32 ? 32u : bn <= 64 ? 64u : bn <= 128 ? 128u : 256u;
 
   if (t == 0) {
+#pragma unroll 1
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(full + i, kProdWarps);
       mbar_init(empty + i, 1);
@@ -190,14 +141,52 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(TcP p) {
 
   if (warp < kProdWarps) {
     // ===================== producers: cp.async pipeline, `depth` chunks in flight per thread =====================
-    const float* a_ptr[4] = {nullptr, nullptr, nullptr, nullptr};
+    // The 16-byte pieces of a stage that THIS thread copies are the same in every chunk: their shared-memory offsets
+    // and source pointers are set up once, a chunk costs one LDGSTS + one pointer bump per piece.
+    //   K-major tile : piece j = row (t >> 3) + 32 j, 16-byte chunk t & 7 of the row's 128 bytes; source advances 32 floats
+    //   MN-major tile: warp w owns reduction rows w + 8 j, lanes walk the 16-byte chunks along M/N (B: two passes h);
+    //                  the source row changes with every chunk (k-th row, or gather[k])
+    constexpr int kMaxPieces = 12;  // 4 of A + up to 8 of B
+    uint32_t doff[kMaxPieces];
+    const float* sptr[kMaxPieces];  // K-major: current source (nullptr: row out of range -> zero fill)
+    int mn_valid[kMaxPieces];        // MN-major: valid floats of the piece (column range), 0 = piece unused
+    const int kc = t & 7, krow = t >> 3;
+    const int nb_k = bn >> 5, nb_mn = (bn + 127) >> 7;
+#pragma unroll
+    for (int i = 0; i < kMaxPieces; ++i) { doff[i] = 0; sptr[i] = nullptr; mn_valid[i] = 0; }
     if (!A_MN) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int r = m0 + (t >> 3) + 32 * j;
-        a_ptr[j] = r < p.M ? p.A + (p.gatherA ? p.gatherA[r] : (int64_t)r) * p.lda : nullptr;
+        const int row = krow + 32 * j, r = m0 + row;
+        doff[j] = (uint32_t)(row * 128 + ((kc ^ (row & 7)) << 4));
+        sptr[j] = r < p.M ? p.A + (p.gatherA ? p.gatherA[r] : (int64_t)r) * p.lda + k_lo + 4 * kc : nullptr;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int m = m0 + 4 * lane;
+        doff[j] = mnmajor_tf32_offset(lane >> 3, warp + 8 * j, lane & 7, kMnLbo);
+        mn_valid[j] = max(0, min(4, p.M - m));
       }
     }
+    if (!B_MN) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int row = krow + 32 * j, n = n0 + row;
+        doff[4 + j] = kABytes + (uint32_t)(row * 128 + ((kc ^ (row & 7)) << 4));
+        sptr[4 + j] = (j < nb_k && n < p.N) ? p.B + (int64_t)n * p.ldb + k_lo + 4 * kc : nullptr;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int cc = lane + 32 * h, n = n0 + 4 * cc;
+          doff[4 + 2 * j + h] = kABytes + mnmajor_tf32_offset(cc >> 3, warp + 8 * j, cc & 7, kMnLbo);
+          mn_valid[4 + 2 * j + h] = (h < nb_mn && 4 * cc < bn) ? max(0, min(4, p.N - n)) : -1;  // -1: no such piece
+        }
+    }
+    const int nB = B_MN ? 8 : nb_k;  // B pieces in use (K-major: the first nb_k)
     const bool want_colsum = B_MN && p.colsum_b != nullptr && blockIdx.y == 0;
     float4 csum[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
     const int depth = p.stages - 1;  // chunk c + depth reuses the stage of chunk c - 1, whose MMAs were issued long ago
@@ -205,29 +194,80 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(TcP p) {
       const int stage = c % p.stages;
       mbar_wait(empty + stage, ((c / p.stages) & 1) ^ 1);
       const uint32_t base = smem_u32(smem + (uint32_t)stage * stage_bytes);
-      for_each_piece<A_MN, B_MN, true>(p, t, m0, n0, k_lo + c * kKC, k_hi, a_ptr, [&](uint32_t off, const float* src, int nv, int) {
-        const bool is_a = off < kABytes;
-        copy_piece(base + off, src, src ? nv : 0, is_a ? p.vecA != 0 : p.vecB != 0, is_a ? p.A : p.B);
-      });
+      const int k0 = k_lo + c * kKC;
+      const int k_left = k_hi - (k0 + 4 * kc);  // K-major pieces: valid floats from this thread's chunk position on
+      if (!A_MN) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          copy_piece<VEC>(base + doff[j], sptr[j], sptr[j] ? k_left : 0, p.A);
+          if (sptr[j]) sptr[j] += kKC;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int kk = k0 + warp + 8 * j;
+          const float* src = nullptr;
+          if (kk < k_hi && mn_valid[j] > 0) src = p.A + (p.gatherA ? p.gatherA[kk] : (int64_t)kk) * p.lda + m0 + 4 * lane;
+          copy_piece<VEC>(base + doff[j], src, src ? mn_valid[j] : 0, p.A);
+        }
+      }
+      if (!B_MN) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (j < nb_k) {
+            copy_piece<VEC>(base + doff[4 + j], sptr[4 + j], sptr[4 + j] ? k_left : 0, p.B);
+            if (sptr[4 + j]) sptr[4 + j] += kKC;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int kk = k0 + warp + 8 * j;
+          const float* row_ptr = kk < k_hi ? p.B + (p.gatherB ? p.gatherB[kk] : (int64_t)kk) * p.ldb + n0 : nullptr;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int i = 4 + 2 * j + h;
+            if (mn_valid[i] >= 0) {
+              const bool ok = row_ptr && mn_valid[i] > 0;
+              copy_piece<VEC>(base + doff[i], ok ? row_ptr + 4 * (lane + 32 * h) : nullptr, ok ? mn_valid[i] : 0, p.B);
+            }
+          }
+        }
+      }
     };
     for (int c = 0; c < depth; ++c) {
       if (c < nchunks) issue(c);
       cp_async_commit();
     }
+    const bool any_round = p.roundA || p.roundB || want_colsum;
     for (int c = 0; c < nchunks; ++c) {
       if (c + depth < nchunks) issue(c + depth);
       cp_async_commit();               // (possibly empty) group: keeps one group per chunk
       cp_async_wait_pending(depth);    // chunk c has landed (this thread's pieces)
       const int stage = c % p.stages;
-      uint8_t* base = smem + (uint32_t)stage * stage_bytes;
-      for_each_piece<A_MN, B_MN, false>(p, t, m0, n0, k_lo + c * kKC, k_hi, a_ptr, [&](uint32_t off, const float*, int, int slot) {
-        float4 v = *reinterpret_cast<float4*>(base + off);
-        if (B_MN && want_colsum && slot >= 0) {  // exact fp32 column sums of B (before the TF32 rounding)
-          csum[slot & 1].x += v.x; csum[slot & 1].y += v.y; csum[slot & 1].z += v.z; csum[slot & 1].w += v.w;
+      if (any_round) {
+        // round the landed pieces to TF32 (nearest) in place - the tensor core would truncate - unless the operand was
+        // rounded when it was laid out (feature matrix, padded weight copy)
+        uint8_t* base = smem + (uint32_t)stage * stage_bytes;
+        if (p.roundA) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) round_piece(base + doff[j]);
         }
-        *reinterpret_cast<uint4*>(base + off) = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-      });
-      fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+        if (p.roundB || want_colsum) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (j < nB && (!B_MN || mn_valid[4 + j] >= 0)) {
+              float4 v = *reinterpret_cast<float4*>(base + doff[4 + j]);
+              if (B_MN && want_colsum) {  // exact fp32 column sums of B (before the rounding): piece 2 j' + h -> pass h
+                csum[j & 1].x += v.x; csum[j & 1].y += v.y; csum[j & 1].z += v.z; csum[j & 1].w += v.w;
+              }
+              if (p.roundB)
+                *reinterpret_cast<uint4*>(base + doff[4 + j]) = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+            }
+          }
+        }
+      }
+      fence_proxy_async_smem();  // writes of this thread (cp.async data it waited for, rounded pieces) -> async proxy
       __syncwarp();
       if (lane == 0) mbar_arrive(full + stage);
     }
@@ -359,8 +399,8 @@ static int pick_bn(int64_t N) {
   return (int)align_up(bn, 32);
 }
 
-template <bool A_MN, bool B_MN>
-static int launch(TcP& p, int splits, cudaStream_t st) {
+template <bool A_MN, bool B_MN, bool VEC>
+static int launch_v(TcP& p, int splits, cudaStream_t st) {
   p.stages = p.bn > 128 ? 2 : p.bn > 64 ? 3 : 4;  // two CTAs per SM: the epilogue of one overlaps the copies of the other
   if (const char* e = getenv("TTAM_TC_STAGES")) {
     const int v = atoi(e);
@@ -369,13 +409,18 @@ static int launch(TcP& p, int splits, cudaStream_t st) {
   const size_t smem = (size_t)p.stages * (kABytes + (size_t)p.bn * 128) + 1024 + 256;
   static bool attr_done = false;
   if (!attr_done) {
-    TTAM_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    TTAM_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel<A_MN, B_MN, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_done = true;
   }
   dim3 grid((unsigned)ceil_div(p.N, p.bn), (unsigned)ceil_div(p.M, kBM), (unsigned)splits);
-  gemm_tf32_kernel<A_MN, B_MN><<<grid, kThreads, smem, st>>>(p);
+  gemm_tf32_kernel<A_MN, B_MN, VEC><<<grid, kThreads, smem, st>>>(p);
   TTAM_LAUNCH_CHECK();
   return TTAM_OK;
+}
+
+template <bool A_MN, bool B_MN>
+static int launch(TcP& p, int splits, cudaStream_t st) {
+  return (p.vecA && p.vecB) ? launch_v<A_MN, B_MN, true>(p, splits, st) : launch_v<A_MN, B_MN, false>(p, splits, st);
 }
 
 }  // namespace tcg
@@ -384,7 +429,7 @@ using namespace tcg;
 
 int tc_linear_fwd(const float* x, int64_t ldx, const int64_t* gather, const float* w, int64_t ldw, const float* bias,
                   float* y, int64_t ldy, int64_t M, int64_t N, int64_t K, int act, float dropout_p, uint64_t seed,
-                  uint64_t offset, const ttam_step_state* state_dev, cudaStream_t st) {
+                  uint64_t offset, const ttam_step_state* state_dev, int prerounded, cudaStream_t st) {
   if (act != TTAM_ACT_NONE && act != TTAM_ACT_RELU) {
     set_error("linear_fwd: the tensor-core path fuses ReLU only; run other activations with ttam_act_fwd");
     return TTAM_EUNSUPPORTED;
@@ -394,6 +439,7 @@ int tc_linear_fwd(const float* x, int64_t ldx, const int64_t* gather, const floa
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.bn = pick_bn(N);
   p.vecA = aligned16(x) && ldx % 4 == 0; p.vecB = aligned16(w) && ldw % 4 == 0; p.vecC = aligned16(y) && ldy % 4 == 0;
   p.bias = bias; p.act = act; p.dropout_p = dropout_p; p.seed = seed; p.offset = offset; p.st = state_dev; p.scale = 1.f;
+  p.roundA = !(prerounded & 1); p.roundB = !(prerounded & 2);
   return launch<false, false>(p, 1, st);
 }
 
@@ -405,6 +451,7 @@ int tc_linear_dgrad(const float* dy, int64_t lddy, const float* w, float* dx, in
   p.M = (int)M; p.N = (int)K; p.K = (int)N; p.bn = pick_bn(K);
   p.vecA = aligned16(dy) && lddy % 4 == 0; p.vecB = aligned16(w) && K % 4 == 0; p.vecC = aligned16(dx) && lddx % 4 == 0;
   p.aux = aux; p.ldaux = ldaux; p.mask_mode = mask_mode; p.scale = scale; p.accumulate = accumulate;
+  p.roundA = 1; p.roundB = 1;
   return launch<false, true>(p, 1, st);
 }
 
@@ -418,7 +465,8 @@ int tc_wgrad_splits(int64_t M, int64_t N, int64_t K) {
 }
 
 int tc_linear_wgrad_partials(const float* dy, int64_t lddy, const float* x, int64_t ldx, const int64_t* gather, float* partial,
-                             float* colsum_partial, int64_t M, int64_t N, int64_t K, int* real_splits, cudaStream_t st) {
+                             float* colsum_partial, int64_t M, int64_t N, int64_t K, int* real_splits, int prerounded,
+                             cudaStream_t st) {
   // part[z][n'][k'] = sum_{r in chunk z} dy[r, n'] x[g(r), k']:  C(m = k', n = n'), both operands MN-major over r
   const int splits = tc_wgrad_splits(M, N, K);
   const int chunk = (int)align_up(ceil_div(M, splits), kKC);
@@ -428,6 +476,7 @@ int tc_linear_wgrad_partials(const float* dy, int64_t lddy, const float* x, int6
   p.M = (int)K; p.N = (int)N; p.K = (int)M; p.k_chunk = chunk; p.bn = pick_bn(N);
   p.vecA = aligned16(x) && ldx % 4 == 0; p.vecB = aligned16(dy) && lddy % 4 == 0; p.vecC = 0;
   p.transposed = 1; p.scale = 1.f; p.colsum_b = colsum_partial;
+  p.roundA = !(prerounded & 1); p.roundB = 1;   // A = x (bit 0 of prerounded), B = dy
   return launch<true, true>(p, *real_splits, st);
 }
 

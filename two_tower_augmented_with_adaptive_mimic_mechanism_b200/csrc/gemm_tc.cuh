@@ -4,14 +4,18 @@
 
 namespace ttam {
 
+// `prerounded`: bit 0 = x, bit 1 = w already hold TF32-representable values (TTAM_PREC_TF32_X / _XW): the kernel skips
+// its in-place rounding pass for that operand.
+
 int tc_linear_fwd(const float* x, int64_t ldx, const int64_t* gather, const float* w, int64_t ldw, const float* bias,
                   float* y, int64_t ldy, int64_t M, int64_t N, int64_t K, int act, float dropout_p, uint64_t seed,
-                  uint64_t offset, const ttam_step_state* state_dev, cudaStream_t st);
+                  uint64_t offset, const ttam_step_state* state_dev, int prerounded, cudaStream_t st);
 int tc_linear_dgrad(const float* dy, int64_t lddy, const float* w, float* dx, int64_t lddx, const float* aux, int64_t ldaux,
                     int mask_mode, float scale, int accumulate, int64_t M, int64_t N, int64_t K, cudaStream_t st);
 int tc_wgrad_splits(int64_t M, int64_t N, int64_t K);
 // part[z][N][K] and (when colsum_partial is non-null) colsum_partial[z][N] = column sums of dy, for z < *real_splits
 int tc_linear_wgrad_partials(const float* dy, int64_t lddy, const float* x, int64_t ldx, const int64_t* gather, float* partial,
-                             float* colsum_partial, int64_t M, int64_t N, int64_t K, int* real_splits, cudaStream_t st);
+                             float* colsum_partial, int64_t M, int64_t N, int64_t K, int* real_splits, int prerounded,
+                             cudaStream_t st);
 
 }  // namespace ttam

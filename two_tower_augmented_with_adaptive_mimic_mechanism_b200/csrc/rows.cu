@@ -326,6 +326,26 @@ extern "C" int ttam_gather_rows_f32(const float* table, int64_t ld_table, int64_
   return TTAM_OK;
 }
 
+__global__ void __launch_bounds__(256) round_tf32_kernel(float* __restrict__ x, int64_t ld, int64_t R, int64_t ncols) {
+  const int64_t total = R * ncols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / ncols, c = i - r * ncols;
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x[r * ld + c]));
+    x[r * ld + c] = __uint_as_float(u);
+  }
+}
+
+extern "C" int ttam_round_tf32(float* x, int64_t ld, int64_t R, int64_t ncols, void* stream) {
+  TTAM_CHECK_ARG(R >= 0 && ncols >= 0 && ld >= ncols, "round_tf32: bad shape");
+  if (R == 0 || ncols == 0) return TTAM_OK;
+  TTAM_CHECK_ARG(x, "round_tf32: null pointer");
+  const int blocks = (int)std::min<int64_t>(ceil_div(R * ncols, 256), (int64_t)num_sms() * 16);
+  round_tf32_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, ld, R, ncols);
+  TTAM_LAUNCH_CHECK();
+  return TTAM_OK;
+}
+
 extern "C" int ttam_cast_f32_to_bf16(const float* src, int64_t ld_src, uint16_t* dst, int64_t ld_dst, int64_t R,
                                      int64_t ncols, void* stream) {
   TTAM_CHECK_ARG(src && dst && R >= 0 && ncols > 0, "cast: bad argument");

@@ -21,8 +21,9 @@ extern "C" int ttam_tower_fwd(const ttam_tower_desc* d, const int64_t* idx, int6
   // e = E[idx] -> z[:, :D]
   TTAM_TRY(ttam_gather_rows_f32(d->table, D, d->table_rows, idx, b->z, 2 * D, R, D, stream));
   // hd = dropout(relu(X[idx] W1^T + b1))
+  const int prec1 = d->precision | (d->x_rounded ? TTAM_PREC_X_ROUNDED : 0) | (d->w1_rounded ? TTAM_PREC_W_ROUNDED : 0);
   TTAM_TRY(ttam_linear_fwd(d->X, d->ldx, idx, d->W1, d->ldw1, d->b1, b->hd, H, R, H, F, TTAM_ACT_RELU, d->dropout_p, d->seed,
-                           d->rng_base, d->state, d->precision, stream));
+                           d->rng_base, d->state, prec1, stream));
   // f = hd W2^T + b2 -> z[:, D:]
   TTAM_TRY(ttam_linear_fwd(b->hd, H, nullptr, d->W2, H, d->b2, b->z + D, 2 * D, R, D, H, TTAM_ACT_NONE, 0.f, 0, 0, nullptr,
                            d->precision, stream));
@@ -65,5 +66,6 @@ extern "C" int ttam_tower_bwd(const ttam_tower_desc* d, const int64_t* idx, int6
   TTAM_TRY(ttam_linear_wgrad(df, 2 * D, b->hd, H, nullptr, g->dW2, g->db2, R, D, H, acc, workspace, workspace_bytes, prec, stream));
   const float scale = d->dropout_p > 0.f ? 1.f / (1.f - d->dropout_p) : 1.f;
   TTAM_TRY(ttam_linear_dgrad(df, 2 * D, d->W2, g->dhd, H, b->hd, H, 1, scale, 0, R, D, H, prec, stream));
-  return ttam_linear_wgrad(g->dhd, H, d->X, d->ldx, idx, g->dW1, g->db1, R, H, F, acc, workspace, workspace_bytes, prec, stream);
+  return ttam_linear_wgrad(g->dhd, H, d->X, d->ldx, idx, g->dW1, g->db1, R, H, F, acc, workspace, workspace_bytes,
+                           prec | (d->x_rounded ? TTAM_PREC_X_ROUNDED : 0), stream);
 }

@@ -118,15 +118,17 @@ class FusedEngine:
         self.tables[name] = t
 
     def _x(self, X):
-        """Feature matrix as the GEMM loaders want it.  The tensor-core path needs 16-byte aligned rows: a matrix whose
-        row length is not a multiple of 4 floats (F = 605) is copied ONCE into a zero-padded layout (ld = 608) and the
-        copy is reused for as long as the caller keeps passing the same tensor."""
+        """Feature matrix as the GEMM loaders want it.  The tensor-core path keeps ONE private copy per feature matrix:
+        rows zero-padded to a multiple of 4 floats (F = 605 -> ld = 608: 16-byte aligned rows for the 16-byte LDGSTS)
+        and values rounded to TF32 once, here, so that the GEMMs need no rounding pass over this operand.  The copy is
+        reused for as long as the caller keeps passing the same tensor."""
         if X is None or self.precision == "fp32":
             return X
         key = (X.data_ptr(), tuple(X.shape))
         hit = self._xpad.get(key)
         if hit is None:
-            hit = F.pad_cols(X)
+            hit = F.round_tf32_(F.pad_cols(X, always_copy=True))   # private copy: padded rows, TF32-representable values
+            hit._ttam_tf32 = True
             self._xpad = {k: v for k, v in self._xpad.items() if k[0] != key[0]}
             self._xpad[key] = hit
         return hit

@@ -69,11 +69,19 @@ def cast_bf16(src: torch.Tensor) -> torch.Tensor:
     return dst
 
 
-def pad_cols(t: torch.Tensor, mult: int = 4, *, out=None) -> torch.Tensor:
+def round_tf32_(t: torch.Tensor) -> torch.Tensor:
+    """In place: every element of the 2-D tensor (unit inner stride) becomes its nearest TF32-representable value."""
+    _chk(t, torch.float32, "t")
+    ptr, ld = _rows2d(t, "t")
+    check(lib().ttam_round_tf32(ptr, ld, t.shape[0], t.shape[1], _stream()), "round_tf32")
+    return t
+
+
+def pad_cols(t: torch.Tensor, mult: int = 4, *, out=None, always_copy: bool = False) -> torch.Tensor:
     """View [R, C] of a zero-padded copy whose rows are a multiple of `mult` floats (16-byte aligned rows for the
     tensor-core loaders).  Returns `t` itself when it already qualifies."""
     R, Ccols = t.shape
-    if Ccols % mult == 0 and t.stride(1) == 1 and t.stride(0) % mult == 0 and t.data_ptr() % 16 == 0:
+    if not always_copy and Ccols % mult == 0 and t.stride(1) == 1 and t.stride(0) % mult == 0 and t.data_ptr() % 16 == 0:
         return t
     ld = (Ccols + mult - 1) // mult * mult
     if out is None or out.shape != (R, ld) or out.device != t.device:

@@ -107,6 +107,15 @@ def _buf(bufs, name, shape, device):
     return torch.empty(shape, dtype=torch.float32, device=device)
 
 
+def _w1_rounded(W: torch.Tensor, bufs) -> torch.Tensor:
+    """Layer-1 weight of the composite tensor-core path: padded copy (16-byte aligned rows), rounded to TF32 here so
+    that the GEMM skips its rounding pass (refreshed every call: the optimiser rewrites the weight each step)."""
+    key = f"wpad{id(W)}"
+    view = F.pad_cols(W, out=bufs.get(key), always_copy=True)
+    bufs[key] = view._base if view._base is not None else view
+    return F.round_tf32_(view)
+
+
 def _w_for(W: torch.Tensor, bufs, precision: str) -> torch.Tensor:
     """Weight operand of a forward GEMM: the tensor-core path wants 16-byte aligned rows, so a weight whose row length
     is not a multiple of 4 floats (the 605-wide layer 1) is copied into a padded buffer (refreshed on every call: the
@@ -149,7 +158,8 @@ def _tower_forward_composite(plan, idx, X, *, train, bufs, seed, rng_base, state
     R, D, dev = idx.numel(), plan.D, plan.table.device
     H, Hg = plan.fe_layers[0][0].shape[0], plan.gate[0].shape[0]
     p_drop = plan.dropout if train else 0.0
-    W1 = _w_for(plan.fe_layers[0][0], bufs, precision)
+    pre = precision != "fp32" and bool(getattr(X, "_ttam_tf32", False))   # the engine's private rounded copy of X
+    W1 = _w1_rounded(plan.fe_layers[0][0], bufs) if precision != "fp32" else plan.fe_layers[0][0]
     c = Cache(idx=idx, X=X, gather=True, train=train, R=R, seed=seed, rng_base=rng_base, mode="gated", composite=True)
     c.z = _buf(bufs, "z", (R, 2 * D), dev)
     c.hd, c.pre = [_buf(bufs, "hd0", (R, H), dev)], [None]
@@ -159,6 +169,7 @@ def _tower_forward_composite(plan, idx, X, *, train, bufs, seed, rng_base, state
     o = _buf(bufs, "o", (R, D), dev) if has_aug else None
     q = _buf(bufs, "q", (R, D), dev) if (has_aug and want_q) else None
     c.desc = _tower_desc(plan, X, W1, p_drop, seed, rng_base, state, precision, augment)
+    c.desc.x_rounded, c.desc.w1_rounded = int(pre), int(precision != "fp32")
     b = F._lib.TowerBufs()
     b.z, b.hd, b.a, b.pre2, b.g, b.t = (t.data_ptr() for t in (c.z, c.hd[0], c.a, pre2, c.g, c.t))
     b.o, b.q = (None if o is None else o.data_ptr()), (None if q is None else q.data_ptr())
