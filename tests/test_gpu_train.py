@@ -57,6 +57,45 @@ def test_fused_step_matches_reference_golden(name):
             np.testing.assert_allclose(st[pname][key].cpu().numpy(), v, rtol=2e-4, atol=1e-7, err_msg=k)
 
 
+def test_train_one_epoch_hook_replays_reference_golden(monkeypatch):
+    """hooks._train_one_epoch with the reference's call signature (training.py:700-716): a DataLoader of (users, pos)
+    batches, the torch optimisers `_run_single_experiment` would build (used as configuration carriers), the reference's
+    sampler replaced by a replay of the golden negatives.  Result: the golden state, the sample-weighted mean loss the
+    reference returns (training.py:833), and the moments published into `optimizer.state` for `_save_checkpoint`."""
+    import two_tower_augmented_with_adaptive_mimic_mechanism_b200 as tt
+    from torch import nn
+    name = "train_gated_mlp"
+    d, meta, init = load_case(name)
+    model = build_model(meta, TRAIN_CASES[name], init, "cuda")
+    sparse = [model.user_encoder.embedding.weight, model.item_encoder.embedding.weight]
+    dense = [p for p in model.parameters() if all(p is not q for q in sparse)]
+    opts = [torch.optim.AdamW(dense, lr=meta["lr"], weight_decay=meta["wd"]),
+            torch.optim.SparseAdam(sparse, lr=meta["lr"], betas=meta["betas"])]
+    steps = meta["steps"]
+    batches = [(torch.from_numpy(d[f"step{s}/users"]), torch.from_numpy(d[f"step{s}/pos"])) for s in range(steps)]
+    negs = iter([torch.from_numpy(d[f"step{s}/neg"]).cuda() for s in range(steps)])
+    monkeypatch.setattr(tt.hooks, "_sampler", lambda: (lambda users, **kw: next(negs)))
+    lu, li, _ = meta["lambdas"]
+    ux, ix = torch.from_numpy(d["user_x"]).cuda(), torch.from_numpy(d["item_x"]).cuda()
+    mean_loss = tt.hooks._train_one_epoch(model, batches, optimizers=opts, criterion=nn.BCEWithLogitsLoss(),
+                                          negatives_per_positive=meta["N"], num_items=meta["NI"], user_positive_items={},
+                                          user_features=ux, item_features=ix, device=torch.device("cuda"),
+                                          gradient_clip_norm=None, loss_weights={"mimic_user": lu, "mimic_item": li},
+                                          item_category_tensor=None, major_category_id=None)
+    sizes = np.array([b[0].shape[0] for b in batches], np.float64)
+    assert mean_loss == pytest.approx(float(np.dot(d["losses"][:steps], sizes) / sizes.sum()), rel=5e-6)
+    got, ref = model_state_np(model), state_after(d, steps - 1)
+    for k in ref:
+        np.testing.assert_allclose(got[k], ref[k], rtol=RTOL, atol=ATOL, err_msg=k)
+    st = opts[1].state[sparse[0]]
+    np.testing.assert_allclose(st["exp_avg"].cpu().numpy(), d["opt/user_encoder.embedding.weight/exp_avg"], rtol=2e-4, atol=1e-7)
+    assert model.training
+    with pytest.raises(NotImplementedError):
+        tt.hooks._train_one_epoch(model, [], optimizers=opts, criterion=nn.BCEWithLogitsLoss(), negatives_per_positive=5,
+                                  num_items=meta["NI"], user_positive_items={}, user_features=ux, item_features=ix,
+                                  device=torch.device("cuda"), gradient_clip_norm=1.0)
+
+
 def _synthetic(seed, NU, NI, D, H, Hg, F, B, N):
     rng = np.random.default_rng(seed)
     st = {}
