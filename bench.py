@@ -307,9 +307,11 @@ def main():
         # layer 1 of the item tower (feature-row gather fused into the GEMM loader): the largest byte stream of the step
         W1, b1 = eng.item.fe_layers[0]
         Xi = eng._x(item_x)
-        W1p = F.pad_cols(W1) if args.precision != "fp32" else W1
+        tc = args.precision != "fp32"
+        W1p = F.round_tf32_(F.pad_cols(W1, always_copy=True)) if tc else W1     # the layout the engine hands the kernel
         hd = torch.empty((R, H), device=dev)
-        tk = time_alone(lambda: F.linear_fwd(Xi, W1p, b1, gather=items_idx, act="relu", out=hd, precision=args.precision))
+        tk = time_alone(lambda: F.linear_fwd(Xi, W1p, b1, gather=items_idx, act="relu", out=hd, precision=args.precision,
+                                             x_rounded=tc, w_rounded=tc))
         flops = 2.0 * R * Fd * H
         bytes_alg = R * (Fd * 4 + 8) + H * Fd * 4 + R * H * 4
         kname = "item tower layer 1: X[idx] . W1^T + b1, relu"

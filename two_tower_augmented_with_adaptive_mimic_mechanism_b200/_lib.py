@@ -14,7 +14,7 @@ from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
-LIB_PATH = PKG_DIR / "libttam.so"
+LIB_PATH = Path(os.environ["TTAM_LIB"]) if os.environ.get("TTAM_LIB") else PKG_DIR / "libttam.so"   # TTAM_LIB: A/B builds
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

@@ -42,7 +42,7 @@ struct TcP {
   int k_chunk;  // reduction range per blockIdx.z (multiple of kKC); 0 = whole K
   int bn;       // N tile: multiple of 32, <= 256
   int stages;
-  int vecA, vecB, vecC;  // 16-byte accesses allowed (base and leading dimension aligned)
+  int vecA, vecB, vecC, vecAux;  // 16-byte accesses allowed (base and leading dimension aligned)
   int roundA, roundB;    // 0: the operand already holds TF32-representable values (rounded when it was laid out)
   int transposed;        // store C(m,n) at C[z][n*ldc + m]
   float* colsum_b;       // MN-major B only: colsum_b[z][n] = sum over this CTA's reduction range of B(n, k)  (bias gradient)
@@ -58,10 +58,13 @@ struct TcP {
   int accumulate;
 };
 
+// Round-to-nearest (ties away from zero) onto the TF32 grid, as cvt.rna.tf32.f32 does, with integer arithmetic: add
+// half a TF32 ulp to the magnitude; the tensor core then drops the low 13 mantissa bits.  (cvt.rna.tf32 compiles to a
+// long NaN/Inf-checking sequence: the rounding pass used to cost as much as everything else in the kernel.)  Inf/NaN
+// pass through unchanged.
 __device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return u;
+  const uint32_t u = __float_as_uint(x);
+  return ((u & 0x7F800000u) != 0x7F800000u) ? u + 0x1000u : u;
 }
 
 // ---- asynchronous global -> shared copies (LDGSTS): no registers, many chunks in flight per thread -------------------
@@ -326,10 +329,18 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(TcP p) {
           }
         }
         if (p.mask_mode == 1) {
+          const float* ax = p.aux + (int64_t)m * p.ldaux + n0 + col;
+          if (p.vecAux && n0 + col + 15 < p.N) {  // 64 contiguous bytes of this thread's row: four 16-byte loads
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int n = n0 + col + i;
-            if (n < p.N) v[i] = (p.aux[(int64_t)m * p.ldaux + n] > 0.f) ? v[i] : 0.f;
+            for (int i = 0; i < 16; i += 4) {
+              const float4 a4 = ld_f4(ax + i);
+              v[i] = a4.x > 0.f ? v[i] : 0.f; v[i + 1] = a4.y > 0.f ? v[i + 1] : 0.f;
+              v[i + 2] = a4.z > 0.f ? v[i + 2] : 0.f; v[i + 3] = a4.w > 0.f ? v[i + 3] : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (n0 + col + i < p.N) v[i] = (ax[i] > 0.f) ? v[i] : 0.f;
           }
         }
         if (p.scale != 1.f) {
@@ -451,6 +462,7 @@ int tc_linear_dgrad(const float* dy, int64_t lddy, const float* w, float* dx, in
   p.M = (int)M; p.N = (int)K; p.K = (int)N; p.bn = pick_bn(K);
   p.vecA = aligned16(dy) && lddy % 4 == 0; p.vecB = aligned16(w) && K % 4 == 0; p.vecC = aligned16(dx) && lddx % 4 == 0;
   p.aux = aux; p.ldaux = ldaux; p.mask_mode = mask_mode; p.scale = scale; p.accumulate = accumulate;
+  p.vecAux = aux != nullptr && aligned16(aux) && ldaux % 4 == 0;
   p.roundA = 1; p.roundB = 1;
   return launch<false, true>(p, 1, st);
 }

@@ -90,8 +90,14 @@ def pad_cols(t: torch.Tensor, mult: int = 4, *, out=None, always_copy: bool = Fa
     return out[:, :Ccols]
 
 
+def _prec(precision: str, x_rounded: bool = False, w_rounded: bool = False) -> int:
+    return PREC[precision] | (_lib.PREC_X_ROUNDED if x_rounded else 0) | (_lib.PREC_W_ROUNDED if w_rounded else 0)
+
+
 def linear_fwd(x, w, bias=None, *, gather=None, act="none", out=None, dropout_p=0.0, seed=0, offset=0,
-               state=None, precision="fp32"):
+               state=None, precision="fp32", x_rounded=False, w_rounded=False):
+    """x_rounded / w_rounded (tensor-core path): the operand was passed through round_tf32_ when it was laid out, the
+    GEMM skips its rounding pass for it."""
     _chk(x, torch.float32, "x"); _chk(w, torch.float32, "w")
     xp, ldx = _rows2d(x, "x")
     wp, ldw = _rows2d(w, "w")          # [N,K], rows ldw apart (a padded view is fine)
@@ -107,7 +113,8 @@ def linear_fwd(x, w, bias=None, *, gather=None, act="none", out=None, dropout_p=
         out = torch.empty((M, N), dtype=torch.float32, device=x.device)
     yp, ldy = _rows2d(out, "out")
     check(lib().ttam_linear_fwd(xp, ldx, _ptr(gather), wp, ldw, _ptr(bias), yp, ldy, M, N, K, ACT[act],
-                                float(dropout_p), int(seed), int(offset), _ptr(state), PREC[precision], _stream()), "linear_fwd")
+                                float(dropout_p), int(seed), int(offset), _ptr(state), _prec(precision, x_rounded, w_rounded),
+                                _stream()), "linear_fwd")
     return out
 
 
@@ -129,7 +136,8 @@ def linear_dgrad(dy, w, *, out=None, aux=None, relu_mask=False, scale=1.0, accum
     return out
 
 
-def linear_wgrad(dy, x, *, gather=None, dw=None, db=None, accumulate=False, precision="fp32", want_bias=True):
+def linear_wgrad(dy, x, *, gather=None, dw=None, db=None, accumulate=False, precision="fp32", want_bias=True,
+                 x_rounded=False):
     _chk(dy, torch.float32, "dy"); _chk(x, torch.float32, "x")
     dyp, lddy = _rows2d(dy, "dy")
     xp, ldx = _rows2d(x, "x")
@@ -143,7 +151,8 @@ def linear_wgrad(dy, x, *, gather=None, dw=None, db=None, accumulate=False, prec
     nbytes = lib().ttam_linear_wgrad_workspace_bytes(M, N, K)
     ws = workspace(nbytes, dy.device, "wgrad")
     check(lib().ttam_linear_wgrad(dyp, lddy, xp, ldx, _ptr(gather), dw.data_ptr(), _ptr(db), M, N, K,
-                                  1 if accumulate else 0, ws.data_ptr(), ws.numel(), PREC[precision], _stream()), "linear_wgrad")
+                                  1 if accumulate else 0, ws.data_ptr(), ws.numel(), _prec(precision, x_rounded), _stream()),
+          "linear_wgrad")
     return dw, db
 
 
