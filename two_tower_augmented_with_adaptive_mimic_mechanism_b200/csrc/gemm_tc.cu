@@ -42,7 +42,7 @@ struct TcP {
   int k_chunk;  // reduction range per blockIdx.z (multiple of kKC); 0 = whole K
   int bn;       // N tile: multiple of 32, <= 256
   int stages;
-  int vecA, vecB, vecC, vecAux;  // 16-byte accesses allowed (base and leading dimension aligned)
+  int vecA, vecB, vecC, vecAux, vecBias;  // 16-byte accesses allowed (base and leading dimension aligned)
   int roundA, roundB;    // 0: the operand already holds TF32-representable values (rounded when it was laid out)
   int transposed;        // store C(m,n) at C[z][n*ldc + m]
   float* colsum_b;       // MN-major B only: colsum_b[z][n] = sum over this CTA's reduction range of B(n, k)  (bias gradient)
@@ -105,7 +105,7 @@ __device__ __forceinline__ void round_piece(uint8_t* ptr) {
 // VEC: both operands may be copied with 16-byte LDGSTS (bases and leading dimensions 16-byte aligned); the scalar
 // instantiation exists for arbitrary layouts and is not the fast path.
 template <bool A_MN, bool B_MN, bool VEC>
-__global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(TcP p) {
+__global__ void __launch_bounds__(kThreads, 3) gemm_tf32_kernel(TcP p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int bn = p.bn;
@@ -313,9 +313,17 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(TcP p) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
         if (p.bias) {
+          if (p.vecBias && n0 + col + 15 < p.N) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (n0 + col + i < p.N) v[i] += p.bias[n0 + col + i];
+            for (int i = 0; i < 16; i += 4) {
+              const float4 b4 = ld_f4(p.bias + n0 + col + i);
+              v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (n0 + col + i < p.N) v[i] += p.bias[n0 + col + i];
+          }
         }
         if (relu) {
 #pragma unroll
@@ -407,12 +415,18 @@ static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 static int pick_bn(int64_t N) {
   int64_t bn = N < 256 ? N : 256;
+  if (const char* e = getenv("TTAM_TC_BN_SPLIT")) {  // experiment: two narrower N tiles (more CTAs per SM) instead of one wide one
+    if (atoi(e) && bn > 128) bn = (bn + 1) / 2;
+  }
   return (int)align_up(bn, 32);
 }
 
 template <bool A_MN, bool B_MN, bool VEC>
 static int launch_v(TcP& p, int splits, cudaStream_t st) {
-  p.stages = p.bn > 128 ? 2 : p.bn > 64 ? 3 : 4;  // two CTAs per SM: the epilogue of one overlaps the copies of the other
+  // several CTAs per SM (the epilogue of one overlaps the copies of the others; 384 tiles of 49 152 rows fit in one wave
+  // at three per SM): bn <= 128 -> 128 TMEM columns and 2 x 28-32 kB of stages each, three CTAs; wider tiles need 256
+  // TMEM columns each, two CTAs
+  p.stages = 2;
   if (const char* e = getenv("TTAM_TC_STAGES")) {
     const int v = atoi(e);
     if (v >= 2 && v <= 4 && (size_t)v * (kABytes + (size_t)p.bn * 128) + 1280 <= 200 * 1024) p.stages = v;
@@ -450,6 +464,7 @@ int tc_linear_fwd(const float* x, int64_t ldx, const int64_t* gather, const floa
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.bn = pick_bn(N);
   p.vecA = aligned16(x) && ldx % 4 == 0; p.vecB = aligned16(w) && ldw % 4 == 0; p.vecC = aligned16(y) && ldy % 4 == 0;
   p.bias = bias; p.act = act; p.dropout_p = dropout_p; p.seed = seed; p.offset = offset; p.st = state_dev; p.scale = 1.f;
+  p.vecBias = bias != nullptr && aligned16(bias);
   p.roundA = !(prerounded & 1); p.roundB = !(prerounded & 2);
   return launch<false, false>(p, 1, st);
 }
