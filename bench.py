@@ -166,7 +166,9 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("TTAM_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("TTAM_PRECISION", "tf32"), choices=["tf32", "fp32"],
+                    help="tower GEMMs: tf32 = tcgen05 kind::tf32 (round-to-nearest operands, fp32 accumulate in TMEM; the "
+                         "product path), fp32 = SIMT FFMA (bit-faithful arithmetic)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-retrieval", action="store_true")
     ap.add_argument("--batch", type=int, default=None, help="samples per GPU per step (default 8192; sweep: 4096..65536)")
@@ -323,7 +325,12 @@ def main():
         bytes_alg = R * (2 * D * 4 + 8)
         kname = "item table row gather: E[idx]"
     roof = {"bound": "hbm", "achieved": bytes_alg / (tk * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s"}
-    roof.update(frac=roof["achieved"] / roof["peak"], traffic=None, kernel=kname,
+    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed `ncu --set full` capture
+    traffic = None
+    tfile = ROOT / "profiles" / "roofline_traffic.json"
+    if tfile.exists():
+        traffic = json.loads(tfile.read_text()).get(f"{kname}|{args.precision}|R={R}")
+    roof.update(frac=roof["achieved"] / roof["peak"], traffic=traffic, kernel=kname,
                 kernel_ms=tk, peak_source=pk["source"], algorithmic_bytes=bytes_alg, algorithmic_flops=flops,
                 tensor_tflops=flops / (tk * 1e-3) / 1e12)
 

@@ -252,10 +252,25 @@ __global__ void __launch_bounds__(256) sparse_adam_rows_kernel(float* __restrict
   for (int c0 = 0; c0 < D; c0 += W) {
     const int col = c0 + (VEC ? lane * 4 : lane);
     const bool active = col < D;
+    // the row's p, m, v do not depend on the gradient rows: fetch them first so that both latency chains overlap
+    const int64_t off = row * (int64_t)D + col;
+    float4 p4 = make_float4(0, 0, 0, 0), m4 = p4, v4 = p4;
+    if (VEC && active) {
+      p4 = ld_f4(P + off); m4 = ld_f4(Mo + off); v4 = ld_f4(Vo + off);
+    }
     float g[4];
     segment_sum<VEC>(gs, sorted, perm, i, R, row, col, active, g);
     if (!active) continue;
-    sparse_adam_update<VEC>(P, Mo, Vo, row * (int64_t)D + col, g, s);
+    if (VEC) {
+      float pp[4] = {p4.x, p4.y, p4.z, p4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sparse_adam_elem(g[e], pp[e], mm[e], vv[e], s);
+      st_f4(P + off, make_float4(pp[0], pp[1], pp[2], pp[3]));
+      st_f4(Mo + off, make_float4(mm[0], mm[1], mm[2], mm[3]));
+      st_f4(Vo + off, make_float4(vv[0], vv[1], vv[2], vv[3]));
+    } else {
+      sparse_adam_update<VEC>(P, Mo, Vo, off, g, s);
+    }
   }
 }
 

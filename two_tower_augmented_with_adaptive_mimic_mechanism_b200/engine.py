@@ -19,6 +19,14 @@ from . import functional as F
 from .tower_ops import TowerPlan, plan_from_module, tower_backward, tower_forward
 
 
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
 @dataclass
 class _Table:
     """Optimiser state of one row-addressed table."""
@@ -93,6 +101,7 @@ class FusedEngine:
         self.misc: dict = {}
         self._graphs: dict = {}
         self._xpad: dict = {}
+        self._side_stream = torch.cuda.Stream(device=dev)
 
     # --------------------------------------------------------------------------------------------
     def _grad_bufs(self, plan: TowerPlan) -> dict:
@@ -136,7 +145,8 @@ class FusedEngine:
     def _misc(self, name, shape, dtype):
         t = self.misc.get(name)
         if t is None or t.shape[0] < shape[0] or t.shape[1:] != tuple(shape[1:]) or t.dtype != dtype:
-            t = torch.empty(shape, dtype=dtype, device=self.device)
+            rows = shape[0] if shape[0] < 4096 else (int(shape[0] * 1.125) + 1023) // 1024 * 1024   # headroom: see tower_ops._buf
+            t = torch.empty((rows,) + tuple(shape[1:]), dtype=dtype, device=self.device)
             self.misc[name] = t
         return t[: shape[0]]
 
@@ -172,21 +182,38 @@ class FusedEngine:
 
     # ---- the step, in three phases (the row-sharded engine runs phases 1 and 3 on the rows a rank OWNS and phase 2
     # on the samples it was GIVEN, with an all-to-all in between; on one GPU they run back to back) -----------------
+    # The user tower and the item tower are independent until the loss, and again from the loss to the dense optimiser:
+    # the user-side launches (8192 rows: 64 GEMM tiles for 148 SMs) run on a side stream next to the item-side ones
+    # (49 152 rows) instead of in front of them.  Under CUDA-graph capture this becomes two parallel branches.
+    def _fork(self):
+        side = self._side_stream
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        return side
+
+    def _join(self, side) -> None:
+        torch.cuda.current_stream(self.device).wait_stream(side)
+
     def _forward_phase(self, users, items, Xu, Xi):
         """Sort + lazy catch-up + both towers for the rows `users` / `items` (row ids of THIS engine's tables)."""
         Xu, Xi = self._x(Xu), self._x(Xi)
         F.advance_step(self.state, rng_stride=1 << 36)
         T = self.tables
-        sort_u = self._sort(users, "u", self.user.table.shape[0])
-        sort_i = self._sort(items, "i", self.item.table.shape[0])
-        for name, srt in (("user_encoder.embedding.weight", sort_u), ("item_encoder.embedding.weight", sort_i),
-                          ("adaptive_mimic.user_augmented.weight", sort_u), ("adaptive_mimic.item_augmented.weight", sort_i)):
-            if name in T:
-                self._catchup(T[name], srt[0])
-        cu = tower_forward(self.user, users, Xu, gather=True, train=True, bufs=self.bufs_u, seed=self.seed,
-                           rng_base=0, state=self.state, precision=self.precision, want_q=self.mimic)
-        ci = tower_forward(self.item, items, Xi, gather=True, train=True, bufs=self.bufs_i, seed=self.seed,
-                           rng_base=1 << 35, state=self.state, precision=self.precision, want_q=self.mimic)
+        side = self._fork()
+        with torch.cuda.stream(side), F.ws_scope("user"):
+            sort_u = self._sort(users, "u", self.user.table.shape[0])
+            for name in ("user_encoder.embedding.weight", "adaptive_mimic.user_augmented.weight"):
+                if name in T:
+                    self._catchup(T[name], sort_u[0])
+            cu = tower_forward(self.user, users, Xu, gather=True, train=True, bufs=self.bufs_u, seed=self.seed,
+                               rng_base=0, state=self.state, precision=self.precision, want_q=self.mimic)
+        with F.ws_scope("item"):
+            sort_i = self._sort(items, "i", self.item.table.shape[0])
+            for name in ("item_encoder.embedding.weight", "adaptive_mimic.item_augmented.weight"):
+                if name in T:
+                    self._catchup(T[name], sort_i[0])
+            ci = tower_forward(self.item, items, Xi, gather=True, train=True, bufs=self.bufs_i, seed=self.seed,
+                               rng_base=1 << 35, state=self.state, precision=self.precision, want_q=self.mimic)
+        self._join(side)
         return dict(sort_u=sort_u, sort_i=sort_i, cu=cu, ci=ci)
 
     def _loss_phase(self, o_u, o_i, t_u, t_p, q_u, q_p, items, B, N, batch_fraction=1.0):
@@ -220,15 +247,28 @@ class FusedEngine:
         T = self.tables
         sort_u, sort_i, cu, ci = ctx["sort_u"], ctx["sort_i"], ctx["cu"], ctx["ci"]
         grads: dict = {}
-        de_i = tower_backward(self.item, ci, do_i, grads, bufs=self.bufs_i, state=self.state, precision=self.precision)
-        de_u = tower_backward(self.user, cu, do_u, grads, bufs=self.bufs_u, state=self.state, precision=self.precision)
-        # ---- row-wise optimisers (no dense table gradient)
-        self._update_table(T["user_encoder.embedding.weight"], sort_u, de_u)
-        self._update_table(T["item_encoder.embedding.weight"], sort_i, de_i)
-        if self.mimic:
-            pair = lambda g: g if isinstance(g, tuple) else (g, None)
-            self._update_table(T["adaptive_mimic.user_augmented.weight"], sort_u, *pair(dq_user))
-            self._update_table(T["adaptive_mimic.item_augmented.weight"], sort_i, *pair(dq_item))
+        grads_u: dict = {}
+        pair = lambda g: g if isinstance(g, tuple) else (g, None)
+        shared = {id(p) for p in self.user.dense_params()} & {id(p) for p in self.item.dense_params()}
+        if shared:   # towers that share dense weights accumulate into the same gradient buffers: keep them in order
+            side = None
+        else:
+            side = self._fork()
+        # ---- tower backward + row-wise optimisers (no dense table gradient), user side next to item side
+        with (torch.cuda.stream(side) if side is not None else _null()), F.ws_scope("user"):
+            de_u = tower_backward(self.user, cu, do_u, grads_u if side is not None else grads, bufs=self.bufs_u, state=self.state,
+                                  precision=self.precision)
+            self._update_table(T["user_encoder.embedding.weight"], sort_u, de_u)
+            if self.mimic:
+                self._update_table(T["adaptive_mimic.user_augmented.weight"], sort_u, *pair(dq_user))
+        with F.ws_scope("item"):
+            de_i = tower_backward(self.item, ci, do_i, grads, bufs=self.bufs_i, state=self.state, precision=self.precision)
+            self._update_table(T["item_encoder.embedding.weight"], sort_i, de_i)
+            if self.mimic:
+                self._update_table(T["adaptive_mimic.item_augmented.weight"], sort_i, *pair(dq_item))
+        if side is not None:
+            self._join(side)
+            grads.update(grads_u)
         # ---- dense optimiser on the MLP / gate / projection tensors that received a gradient
         ps, gs, ms, vs = [], [], [], []
         for j, p in enumerate(self.dense):

@@ -37,12 +37,32 @@ def _ptr(t):
 _ws_cache: dict = {}
 
 
+_ws_scope = [""]
+
+
+class ws_scope:
+    """Scratch buffers requested inside this context are private to `name`: two branches of a step that run
+    concurrently on different CUDA streams (user tower / item tower) must not share scratch memory."""
+
+    def __init__(self, name: str) -> None:
+        self.name = name
+
+    def __enter__(self):
+        self.prev = _ws_scope[0]
+        _ws_scope[0] = self.name
+        return self
+
+    def __exit__(self, *a):
+        _ws_scope[0] = self.prev
+
+
 def workspace(nbytes: int, device, tag: str = "default") -> torch.Tensor:
-    """Grow-only scratch buffer per (device, tag) so that hot loops never allocate."""
-    key = (str(device), tag)
+    """Grow-only scratch buffer per (device, tag, scope) so that hot loops never allocate."""
+    key = (str(device), tag, _ws_scope[0])
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        grow = int(nbytes) if buf is None else int(nbytes * 1.25)   # regrowth gets headroom (row counts drift per step)
+        buf = torch.empty(max(grow, 256), dtype=torch.uint8, device=device)
         _ws_cache[key] = buf
     return buf
 

@@ -96,12 +96,19 @@ class Cache(dict):
     __getattr__ = dict.get
 
 
+def _headroom(rows: int) -> int:
+    return (int(rows * 1.125) + 1023) // 1024 * 1024
+
+
 def _buf(bufs, name, shape, device):
     """Pre-allocated buffer `name` (engine) or a fresh tensor (module API)."""
     if bufs is not None:
         t = bufs.get(name)
         if t is None or t.shape[0] < shape[0] or t.shape[1:] != tuple(shape[1:]):
-            t = torch.empty(shape, dtype=torch.float32, device=device)
+            # grow with headroom: the row count of a row-sharded step changes a little from step to step, and every
+            # reallocation is a cudaMalloc + synchronisation
+            rows = shape[0] if t is None and shape[0] < 4096 else _headroom(shape[0])
+            t = torch.empty((rows,) + tuple(shape[1:]), dtype=torch.float32, device=device)
             bufs[name] = t
         return t[: shape[0]]
     return torch.empty(shape, dtype=torch.float32, device=device)
