@@ -371,6 +371,12 @@ __global__ void __launch_bounds__(256) lazy_rows_kernel(float* __restrict__ P, f
   for (int c0 = 0; c0 < D; c0 += W) {
     const int col = c0 + (VEC ? lane * 4 : lane);
     const bool active = col < D;
+    if (active) {  // start fetching the row's p, m, v while the gradient rows are summed (independent latency chains)
+      const int64_t off = row * (int64_t)D + col;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(P + off));
+      if (Mo) asm volatile("prefetch.global.L2 [%0];" ::"l"(Mo + off));
+      if (Vo) asm volatile("prefetch.global.L2 [%0];" ::"l"(Vo + off));
+    }
     float g[4];
     segment_sum<VEC>(gs, sorted, perm, i, R, row, col, active, g);
     if (!active) continue;

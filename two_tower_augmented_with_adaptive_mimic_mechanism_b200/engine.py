@@ -10,6 +10,7 @@ The engine updates the model's own parameter storage in place, so `state_dict()`
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -102,6 +103,8 @@ class FusedEngine:
         self._graphs: dict = {}
         self._xpad: dict = {}
         self._side_stream = torch.cuda.Stream(device=dev)
+        self._aug_stream = torch.cuda.Stream(device=dev)
+        self._use_aug_stream = os.environ.get("TTAM_AUG_STREAM", "1") != "0"
 
     # --------------------------------------------------------------------------------------------
     def _grad_bufs(self, plan: TowerPlan) -> dict:
@@ -185,8 +188,8 @@ class FusedEngine:
     # The user tower and the item tower are independent until the loss, and again from the loss to the dense optimiser:
     # the user-side launches (8192 rows: 64 GEMM tiles for 148 SMs) run on a side stream next to the item-side ones
     # (49 152 rows) instead of in front of them.  Under CUDA-graph capture this becomes two parallel branches.
-    def _fork(self):
-        side = self._side_stream
+    def _fork(self, which: str = "side"):
+        side = self._side_stream if which == "side" else self._aug_stream
         side.wait_stream(torch.cuda.current_stream(self.device))
         return side
 
@@ -254,21 +257,29 @@ class FusedEngine:
             side = None
         else:
             side = self._fork()
-        # ---- tower backward + row-wise optimisers (no dense table gradient), user side next to item side
+        # ---- row-wise optimisers of the augmentation tables: their gradient rows came out of the loss kernel, nothing
+        # in the tower backward feeds them -> a third branch
+        aug = self._fork("aug") if (self.mimic and self._use_aug_stream) else None
+        if aug is not None:
+            with torch.cuda.stream(aug), F.ws_scope("aug"):
+                self._update_table(T["adaptive_mimic.user_augmented.weight"], sort_u, *pair(dq_user))
+                self._update_table(T["adaptive_mimic.item_augmented.weight"], sort_i, *pair(dq_item))
+        # ---- tower backward + row-wise optimisers of the ID tables (no dense table gradient), user side next to item side
         with (torch.cuda.stream(side) if side is not None else _null()), F.ws_scope("user"):
             de_u = tower_backward(self.user, cu, do_u, grads_u if side is not None else grads, bufs=self.bufs_u, state=self.state,
                                   precision=self.precision)
             self._update_table(T["user_encoder.embedding.weight"], sort_u, de_u)
-            if self.mimic:
-                self._update_table(T["adaptive_mimic.user_augmented.weight"], sort_u, *pair(dq_user))
         with F.ws_scope("item"):
             de_i = tower_backward(self.item, ci, do_i, grads, bufs=self.bufs_i, state=self.state, precision=self.precision)
             self._update_table(T["item_encoder.embedding.weight"], sort_i, de_i)
-            if self.mimic:
-                self._update_table(T["adaptive_mimic.item_augmented.weight"], sort_i, *pair(dq_item))
         if side is not None:
             self._join(side)
             grads.update(grads_u)
+        if aug is not None:
+            self._join(aug)
+        elif self.mimic:
+            self._update_table(T["adaptive_mimic.user_augmented.weight"], sort_u, *pair(dq_user))
+            self._update_table(T["adaptive_mimic.item_augmented.weight"], sort_i, *pair(dq_item))
         # ---- dense optimiser on the MLP / gate / projection tensors that received a gradient
         ps, gs, ms, vs = [], [], [], []
         for j, p in enumerate(self.dense):
