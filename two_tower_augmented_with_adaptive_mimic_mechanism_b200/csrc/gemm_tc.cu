@@ -189,6 +189,14 @@ __global__ void __launch_bounds__(kThreads, 3) gemm_tf32_kernel(TcP p) {
           mn_valid[4 + 2 * j + h] = (h < nb_mn && 4 * cc < bn) ? max(0, min(4, p.N - n)) : -1;  // -1: no such piece
         }
     }
+    int64_t arow[4] = {0, 0, 0, 0};  // MN-major gathered A: source rows of the NEXT chunk to issue
+    if (A_MN && p.gatherA) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int kk = k_lo + warp + 8 * j;
+        if (kk < k_hi) arow[j] = p.gatherA[kk];
+      }
+    }
     const int nB = B_MN ? 8 : nb_k;  // B pieces in use (K-major: the first nb_k)
     const bool want_colsum = B_MN && p.colsum_b != nullptr && blockIdx.y == 0;
     float4 csum[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
@@ -210,8 +218,11 @@ __global__ void __launch_bounds__(kThreads, 3) gemm_tf32_kernel(TcP p) {
         for (int j = 0; j < 4; ++j) {
           const int kk = k0 + warp + 8 * j;
           const float* src = nullptr;
-          if (kk < k_hi && mn_valid[j] > 0) src = p.A + (p.gatherA ? p.gatherA[kk] : (int64_t)kk) * p.lda + m0 + 4 * lane;
+          // the gathered source row of this chunk was fetched one chunk ago (arow): the index load is off the issue path
+          if (kk < k_hi && mn_valid[j] > 0) src = p.A + (p.gatherA ? arow[j] : (int64_t)kk) * p.lda + m0 + 4 * lane;
           copy_piece<VEC>(base + doff[j], src, src ? mn_valid[j] : 0, p.A);
+          const int kn = kk + kKC;
+          if (p.gatherA && kn < k_hi) arow[j] = p.gatherA[kn];
         }
       }
       if (!B_MN) {
@@ -484,7 +495,8 @@ int tc_linear_dgrad(const float* dy, int64_t lddy, const float* w, float* dx, in
 
 int tc_wgrad_splits(int64_t M, int64_t N, int64_t K) {
   const int64_t tiles = ceil_div(K, kBM) * ceil_div(N, pick_bn(N));
-  int64_t s = ceil_div((int64_t)num_sms() * 2, tiles);
+  const int ctas_per_sm = pick_bn(N) <= 128 ? 3 : 2;  // what fits (TMEM columns, shared memory): fill exactly one wave
+  int64_t s = ((int64_t)num_sms() * ctas_per_sm) / tiles;
   const int64_t by_rows = ceil_div(M, 256);
   if (s > by_rows) s = by_rows;
   if (s < 1) s = 1;
