@@ -178,6 +178,18 @@ int ttam_loss_fwd_bwd(const float* o_u, const float* o_i, const float* t_u, cons
                       float* do_u, float* do_i, float* dq_u, float* dq_p, int64_t B, int64_t N, int64_t D,
                       float batch_fraction, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- category-alignment loss (training.py:530-579, 805-820) ------------------------------------------------
+ * L_cal = mean over the non-major categories c with >= 2 rows of || Cov(emb rows of c) - Cov(emb rows of major) ||_F^2,
+ * categories = cat_tensor[item_idx] (primary category id of every item, values in [0, n_categories)).
+ * Adds lambda_c * L_cal to loss_out[0] (nullable), writes L_cal to cal_out[0] (nullable) and adds
+ * lambda_c * dL_cal/d emb[r] to grad_a[r] (dL/do_i, [R, D]) and, for r < B, to grad_b[r] (dL/dq of the positives,
+ * nullable).  Deterministic (sorted segments, fixed-order partial sums), no host synchronisation.  D <= 128. */
+int64_t ttam_category_alignment_workspace_bytes(int64_t R, int64_t D, int64_t n_categories);
+int ttam_category_alignment(const int64_t* item_idx, int64_t R, const float* emb, int64_t D, const int64_t* cat_tensor,
+                            int64_t num_items, int64_t n_categories, int64_t major, float lambda_c, float* loss_out,
+                            float* cal_out, float* grad_a, float* grad_b, int64_t B, void* workspace,
+                            int64_t workspace_bytes, void* stream);
+
 /* ---- sparse backward + row-wise optimisers ---------------------------------------------------------
  * Step 1  ttam_sort_rows: stable radix sort of the R touched row ids; sorted_idx[R], perm[R] (int32:
  *         original positions).  Replaces coalesce() of the uncoalesced COO gradient

@@ -151,6 +151,45 @@ def test_linear_dgrad_and_wgrad_tf32(F):
         np.testing.assert_allclose(acc.cpu().numpy(), dw.cpu().numpy() + 1.0, rtol=1e-6, atol=1e-5)
 
 
+@pytest.mark.parametrize("seed,n,D,ncat,NI", [(0, 96, 16, 4, 500), (1, 300, 8, 7, 500), (2, 10, 4, 6, 500), (3, 6000, 96, 40, 3000),
+                                              (4, 2048, 128, 300, 5000)])
+def test_category_alignment_kernel_matches_oracle(F, seed, n, D, ncat, NI):
+    """csrc/catalign.cu vs the oracle's restatement of training.py:530-579 (loss and gradient), a dominant major
+    category (as in the real data: almost every book's primary category is the same) and many small ones."""
+    rng = np.random.default_rng(seed)
+    cat = rng.integers(0, ncat, size=NI).astype(np.int64)
+    cat[: NI // 2] = 0
+    idx = rng.integers(0, NI, size=n).astype(np.int64)
+    emb = rng.standard_normal((n, D)).astype(np.float32)
+    ref_l, ref_g = oracle.category_alignment_loss(idx, emb, cat, 0)
+    lam, B = 0.25, n // 3
+    loss = dev(np.array([1.5, 0, 0, 0], np.float32))
+    ga, gb = dev(np.ones((n, D), np.float32)), dev(np.zeros((B, D), np.float32))
+    cal, _ = F.category_alignment(dev(idx), dev(emb), dev(cat), ncat, 0, lambda_c=lam, loss_out=loss, grad_a=ga, grad_b=gb, B=B)
+    assert float(cal[0]) == pytest.approx(float(ref_l), rel=2e-4, abs=1e-7)
+    assert float(loss[0]) == pytest.approx(1.5 + lam * float(ref_l), rel=2e-4)
+    scale = max(1e-6, float(np.abs(ref_g).max()))
+    np.testing.assert_allclose(ga.cpu().numpy() - 1.0, lam * ref_g, rtol=2e-3, atol=2e-4 * scale)
+    np.testing.assert_allclose(gb.cpu().numpy(), lam * ref_g[:B], rtol=2e-3, atol=2e-4 * scale)
+    # deterministic
+    ga2 = dev(np.ones((n, D), np.float32))
+    F.category_alignment(dev(idx), dev(emb), dev(cat), ncat, 0, lambda_c=lam, grad_a=ga2)
+    assert torch.equal(ga, ga2)
+
+
+def test_category_alignment_kernel_degenerate_cases(F):
+    emb = torch.randn(6, 4).cuda()
+    idx = torch.arange(6).cuda()
+    for cats in (torch.zeros(6, dtype=torch.long), torch.tensor([0, 1, 1, 1, 2, 2])):     # one category; major has < 2 rows
+        g = torch.zeros_like(emb)
+        cal, _ = F.category_alignment(idx, emb, cats.cuda(), 3, 0, grad_a=g)
+        assert float(cal[0]) == 0.0 and not bool(g.any())
+    cal, g = F.category_alignment(idx[:0], emb[:0], torch.zeros(6, dtype=torch.long).cuda(), 3, 0)   # empty batch
+    assert float(cal[0]) == 0.0 and g.shape == (0, 4)
+    with pytest.raises(Exception, match="not supported"):
+        F.category_alignment(torch.arange(4).cuda(), torch.randn(4, 256).cuda(), torch.zeros(4, dtype=torch.long).cuda(), 1, 0)
+
+
 def test_dropout_mask_is_reproducible_and_scaled(F):
     M, N, K, p = 512, 64, 16, 0.25
     x = torch.ones(M, K, device="cuda")

@@ -1,37 +1,11 @@
-"""Host-side logic that needs no GPU: category-alignment restatement, candidate filtering, sampler, hyper-parameter
-recovery from the reference's optimiser objects."""
+"""Host-side logic that needs no GPU: candidate filtering, sampler, hyper-parameter recovery from the reference's
+optimiser objects."""
 import numpy as np
 import pytest
 import torch
 
 import oracle
 from two_tower_augmented_with_adaptive_mimic_mechanism_b200 import engine, hooks, retrieval, sampler
-
-
-@pytest.mark.parametrize("seed,n,D,ncat", [(0, 96, 16, 4), (1, 300, 8, 7), (2, 10, 4, 6)])
-def test_category_alignment_matches_oracle(seed, n, D, ncat):
-    rng = np.random.default_rng(seed)
-    NI = 500
-    cat = rng.integers(0, ncat, size=NI).astype(np.int64)
-    cat[: NI // 2] = 0
-    idx = rng.integers(0, NI, size=n).astype(np.int64)
-    emb = rng.standard_normal((n, D)).astype(np.float32)
-    ref_l, ref_g = oracle.category_alignment_loss(idx, emb, cat, 0)
-    l, g = engine.category_alignment(torch.from_numpy(idx), torch.from_numpy(emb), torch.from_numpy(cat), 0)
-    assert float(l) == pytest.approx(float(ref_l), rel=1e-5, abs=1e-8)
-    if g is None:
-        assert not np.any(ref_g)
-    else:
-        np.testing.assert_allclose(g.numpy(), ref_g, rtol=1e-4, atol=1e-6)
-
-
-def test_category_alignment_degenerate_cases():
-    emb = torch.randn(6, 4)
-    idx = torch.arange(6)
-    assert engine.category_alignment(idx, emb, torch.zeros(6, dtype=torch.long), 0)[1] is None      # one category
-    cats = torch.tensor([0, 1, 1, 1, 2, 2])
-    assert engine.category_alignment(idx, emb, cats, 0)[1] is None                                   # major has < 2 rows
-    assert engine.category_alignment(idx[:0], emb[:0], cats, 0)[1] is None                           # empty batch
 
 
 def test_filter_candidates_matches_oracle_semantics():

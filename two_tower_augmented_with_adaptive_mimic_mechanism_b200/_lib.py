@@ -128,6 +128,8 @@ SIGNATURES = {
     "ttam_tower_bwd": (C.c_int, [C.POINTER(TowerDesc), _p, _i64, C.POINTER(TowerBufs), _p, C.POINTER(TowerGrads), _p, _i64, _p]),
     "ttam_loss_workspace_bytes": (C.c_int64, [_i64]),
     "ttam_loss_fwd_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _i64, _i64, _i64, _f, _p, _i64, _p]),
+    "ttam_category_alignment_workspace_bytes": (C.c_int64, [_i64, _i64, _i64]),
+    "ttam_category_alignment": (C.c_int, [_p, _i64, _p, _i64, _p, _i64, _i64, _i64, _f, _p, _p, _p, _p, _i64, _p, _i64, _p]),
     "ttam_sort_workspace_bytes": (C.c_int64, [_i64]),
     "ttam_sort_rows": (C.c_int, [_p, _i64, _i64, _p, _p, _p, _i64, _p]),
     "ttam_unique_rows": (C.c_int, [_p, _i64, _p, _p, _p, _i64, _p]),

@@ -145,6 +145,16 @@ class FusedEngine:
             self._xpad[key] = hit
         return hit
 
+    def _categories(self):
+        """(category tensor on the device, number of categories) - the count costs one host read, once per tensor."""
+        key = (self.cat_tensor.data_ptr(), self.cat_tensor.numel())
+        hit = self.__dict__.get("_cat_cache")
+        if hit is None or hit[0] != key:
+            cat = self.cat_tensor.to(self.device, torch.int64).contiguous()
+            hit = (key, cat, int(cat.max()) + 1 if cat.numel() else 1)
+            self._cat_cache = hit
+        return hit[1], hit[2]
+
     def _misc(self, name, shape, dtype):
         t = self.misc.get(name)
         if t is None or t.shape[0] < shape[0] or t.shape[1:] != tuple(shape[1:]) or t.dtype != dtype:
@@ -235,12 +245,9 @@ class FusedEngine:
         if self.lambda_c > 0 and self.cat_tensor is not None and self.major is not None:
             if batch_fraction != 1.0:
                 raise NotImplementedError("category-alignment loss is not available with a sharded batch")
-            cal, gcal = category_alignment(items, o_i, self.cat_tensor, self.major)
-            loss[0] += self.lambda_c * cal
-            if gcal is not None:
-                do_i.add_(gcal, alpha=self.lambda_c)
-                if self.mimic:
-                    dq_p.add_(gcal[:B], alpha=self.lambda_c)
+            cat, n_cat = self._categories()
+            F.category_alignment(items, o_i, cat, n_cat, int(self.major), lambda_c=self.lambda_c, loss_out=loss,
+                                 grad_a=do_i, grad_b=dq_p if self.mimic else None, B=B)
         return loss, do_u, do_i, dq_u, dq_p
 
     def _backward_phase(self, ctx, do_u, do_i, dq_user, dq_item, dense_grad_hook=None):
@@ -422,50 +429,3 @@ class FusedEngine:
                 "exp_avg": None if self.dense_m is None else self.dense_m[j],
                 "exp_avg_sq": None if self.dense_v is None else self.dense_v[j]}
         return out
-
-
-# ------------------------------------------------------------------------------------------------
-# category-alignment loss (reference training.py:530-579).  Data-dependent control flow over the categories
-# present in the batch; kept as vectorised torch ops on the device for now.
-# ------------------------------------------------------------------------------------------------
-def category_alignment(item_idx: torch.Tensor, emb: torch.Tensor, cat_tensor: torch.Tensor, major: int):
-    """Returns (loss scalar tensor, d loss / d emb or None)."""
-    zero = emb.new_zeros(())
-    if item_idx.numel() == 0:
-        return zero, None
-    cats = cat_tensor.to(emb.device)[item_idx]
-    uniq, inv, counts = torch.unique(cats, return_inverse=True, return_counts=True)
-    if uniq.numel() <= 1:
-        return zero, None
-    is_major = uniq == int(major)
-    if not bool(is_major.any()) or int(counts[is_major][0]) < 2:
-        return zero, None
-    C, D = uniq.numel(), emb.shape[1]
-    cnt = counts.to(emb.dtype)
-    sums = emb.new_zeros((C, D)).index_add_(0, inv, emb)
-    mean = sums / cnt[:, None]
-    cen = emb - mean[inv]                                       # centred rows
-    # per-category covariance: sort rows by category and use one batched matmul over padded segments
-    order = torch.argsort(inv, stable=True)
-    cen_s = cen[order]
-    starts = torch.cumsum(counts, 0) - counts
-    maxn = int(counts.max())
-    pos_in_seg = torch.arange(cen_s.shape[0], device=emb.device) - starts[inv[order]]
-    padded = emb.new_zeros((C, maxn, D))
-    padded[inv[order], pos_in_seg] = cen_s
-    cov = padded.transpose(1, 2) @ padded / (cnt - 1).clamp_min(1)[:, None, None]
-    mj = int(torch.nonzero(is_major)[0])
-    use = (~is_major) & (counts >= 2)
-    n_c = int(use.sum())
-    if n_c == 0:
-        return zero, None
-    diff = (cov - cov[mj]) * use[:, None, None].to(emb.dtype)
-    loss = (diff * diff).sum() / n_c
-    # gradient: dL/dCov_c = 2 diff_c / n_c ; dL/dCov_major = -sum_c 2 diff_c / n_c ; dCov/dx = 2/(n-1) cen @ G (G symmetric)
-    G = 2.0 * diff / n_c
-    G[mj] = -G.sum(0)
-    scale = 2.0 / (cnt - 1).clamp_min(1)
-    gp = (padded @ G) * scale[:, None, None]                    # [C, maxn, D], same padded-segment layout
-    grad = torch.empty_like(emb)
-    grad[order] = gp[inv[order], pos_in_seg]
-    return loss, grad

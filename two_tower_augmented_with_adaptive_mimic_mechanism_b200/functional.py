@@ -261,6 +261,24 @@ def loss_fwd_bwd(o_u, o_i, *, t_u=None, t_p=None, q_u=None, q_p=None, lambda_u=0
     return loss, do_u, do_i, dq_u, dq_p
 
 
+def category_alignment(item_idx, emb, cat_tensor, n_categories: int, major: int, *, lambda_c: float = 1.0,
+                       loss_out=None, grad_a=None, grad_b=None, B: int = 0):
+    """Category-alignment loss of `emb` [R, D] (rows = item_idx) and its gradient (see ttam.h).  Returns the raw loss
+    as a 1-element device tensor; lambda_c * loss is ADDED to loss_out[0], lambda_c * gradient to grad_a (and grad_b)."""
+    _chk(emb, torch.float32, "emb"); _chk(item_idx, torch.int64, "item_idx"); _chk(cat_tensor, torch.int64, "cat_tensor")
+    R, D = emb.shape
+    if grad_a is None:
+        grad_a = torch.zeros_like(emb)
+    cal = torch.zeros(1, dtype=torch.float32, device=emb.device)
+    L = lib()
+    ws = workspace(L.ttam_category_alignment_workspace_bytes(R, D, int(n_categories)), emb.device, "catalign")
+    check(L.ttam_category_alignment(item_idx.data_ptr(), R, emb.data_ptr(), D, cat_tensor.data_ptr(), cat_tensor.numel(),
+                                    int(n_categories), int(major), float(lambda_c), _ptr(loss_out), cal.data_ptr(),
+                                    grad_a.data_ptr(), _ptr(grad_b), int(B), ws.data_ptr(), ws.numel(), _stream()),
+          "category_alignment")
+    return cal, grad_a
+
+
 # ---------------------------------------------------------------------------------------------
 def sort_rows(idx: torch.Tensor, num_rows: int, *, sorted_idx=None, perm=None):
     """Stable sort of the touched row ids -> (sorted ids, original positions int32)."""
