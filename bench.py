@@ -83,24 +83,47 @@ def make_batches(steps, c, device, gen):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons during the timed region (B200_PROFILING.md recipe).  In-process NVML (nvidia_ml_py)
+    every 50 ms: spawning nvidia-smi from a thread takes the driver lock often enough to slow the timed launches down
+    (the first version of this bench measured `value` 10 % below `e2e` because of it); nvidia-smi is the fallback."""
 
     def __init__(self, index):
         self.rows, self.stop, self.index = [], threading.Event(), index
         self.thread = threading.Thread(target=self._run, daemon=True)
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        flag = lambda name: "Active" if (r & getattr(n, name, 0)) else "Not Active"
+        return [str(sm), str(mx), flag("nvmlClocksThrottleReasonHwSlowdown"), flag("nvmlClocksThrottleReasonHwThermalSlowdown"),
+                flag("nvmlClocksThrottleReasonSwThermalSlowdown"), flag("nvmlClocksThrottleReasonSwPowerCap")]
 
     def _run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self.stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                if self.nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.1)
+            self.stop.wait(0.05 if self.nvml is not None else 0.5)
 
     def __enter__(self):
         self.thread.start()
@@ -117,7 +140,8 @@ class ClockSampler:
         mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for j, n in enumerate(names) if any(r[2 + j].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -244,6 +268,14 @@ def main():
                          max_steps=4 * (K + W) + 64)
     sh = tt.ShardedEngine(eng) if world > 1 else None
     users, pos, neg = make_batches(K + W, c, dev, gen)          # global row ids
+    if sh is not None:
+        # N > 1: a few extra untimed steps before the W warm-up steps.  The number of rows a rank owns changes from step to
+        # step, so the first steps grow the engine's buffers (cudaMalloc + synchronisation) and open NCCL's send/recv
+        # channels; neither belongs in a timed region.
+        pu, pp, pn = make_batches(6, c, dev, gen)
+        for s in range(6):
+            sh.train_step(pu[s], pp[s], pn[s], user_x, item_x)
+        del pu, pp, pn
     h_users, h_pos, h_neg = (t.cpu().pin_memory() for t in (users, pos, neg))
 
     def barrier():
