@@ -376,8 +376,8 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           }
         }
       };
-      auto make_room = [&](int limit) {
-        unsigned need = __ballot_sync(0xffffffffu, cnt > limit);
+      auto make_room = [&]() {
+        unsigned need = __ballot_sync(0xffffffffu, cnt > kCap - 64);
         while (need) {
           const int r = __ffs(need) - 1;
           need &= need - 1;
@@ -409,7 +409,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
               const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * kBN + col);
               tmem_ld_32x32_issue(taddr, v0);
               tmem_ld_32x32_issue(taddr + 32u, v1);
-              if (!sampling) make_room(kCap - 64);  // safety: must not overflow while this accumulator is held
+              if (!sampling) make_room();
               tmem_ld_wait2(v0, v1);
               if (!sampling) {
                 process2(v0, v1, (uint32_t)t * kBN + (uint32_t)col, tail);
@@ -438,9 +438,6 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
           __syncwarp();
           if (lane == 0) mbar_arrive(acc_empty + a * 2 + h);
         }
-        // The accumulator is released: the tensor core now refills it and this warpgroup would only wait.  Lists that
-        // are getting full are compacted HERE, off the critical path, so that the in-drain safety check rarely fires.
-        if (!sampling) make_room(kCap - 160);
       }
       // ---- end of unit: leave at most kKeep entries in the list, publish count and threshold
       unsigned need = __ballot_sync(0xffffffffu, cnt > kKeep);
