@@ -200,6 +200,9 @@ def main():
                     help="optimiser sweep (BASELINE configs[4]): hybrid = AdamW + SparseAdam (reference default), "
                          "sparse = embedding-only towers, mimic off, all SparseAdam, dense = sparse:false (AdamW semantics on every table)")
     ap.add_argument("--no-graph", action="store_true", help="N=1: launch the step eagerly instead of replaying a CUDA graph (diagnostic)")
+    ap.add_argument("--route", default="static", choices=["static", "dynamic"],
+                    help="N>1: static = fixed-capacity slots, the whole sharded step replays as CUDA graphs; dynamic = per-step "
+                         "split sizes, eager launches (diagnostic)")
     ap.add_argument("--small", action="store_true", help="1/16-size tables (debugging only; not a valid bench line)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
@@ -266,7 +269,7 @@ def main():
     eng = tt.FusedEngine(model, optimizer="adamw", lr=c["lr"], weight_decay=c["wd"], precision=args.precision,
                          loss_weights={} if mimic is None else {"mimic_user": c["lambdas"][0], "mimic_item": c["lambdas"][1]},
                          max_steps=4 * (K + W) + 64)
-    sh = tt.ShardedEngine(eng) if world > 1 else None
+    sh = tt.ShardedEngine(eng, static=args.route == "static") if world > 1 else None
     users, pos, neg = make_batches(K + W, c, dev, gen)          # global row ids
     if sh is not None:
         # N > 1: a few extra untimed steps before the W warm-up steps.  The number of rows a rank owns changes from step to
@@ -274,7 +277,7 @@ def main():
         # channels; neither belongs in a timed region.
         pu, pp, pn = make_batches(6, c, dev, gen)
         for s in range(6):
-            sh.train_step(pu[s], pp[s], pn[s], user_x, item_x)
+            sh.train_step(pu[s], pp[s], pn[s], user_x, item_x, graph=not args.no_graph)
         del pu, pp, pn
     h_users, h_pos, h_neg = (t.cpu().pin_memory() for t in (users, pos, neg))
 
@@ -285,7 +288,7 @@ def main():
 
     def step(u, p, n):
         if sh is not None:
-            return sh.train_step(u, p, n, user_x, item_x)
+            return sh.train_step(u, p, n, user_x, item_x, graph=not args.no_graph)
         return eng.train_step(u, p, n, user_x, item_x, graph=not args.no_graph)
 
     # ---- value: batch index tensors resident in HBM (N = 1: CUDA-graph replay of the step)
@@ -372,7 +375,10 @@ def main():
             "vs_baseline": None, "dtype": {"fp32": "f32", "tf32": "tf32"}[args.precision], "data": "synthetic",
             "config": {"workload": workload,
                        "parallelism": ("1 gpu, CUDA-graph replay" if not args.no_graph else "1 gpu, eager launches") if world == 1 else
-                       f"{world} gpus: tables/features row-sharded, batch data-parallel ({B} samples per gpu), 3 all-to-all + 1 all-reduce per step",
+                       f"{world} gpus: tables/features row-sharded, batch data-parallel ({B} samples per gpu), 3 all-to-all + 1 all-reduce per step, "
+                       + (f"fixed-capacity slots ({sh.last_exchange_rows[0] // world}/{sh.last_exchange_rows[1] // world} user/item rows per "
+                          f"rank pair), CUDA-graph replay incl. collectives, {sh.fallback_steps} dynamic-route fallback steps"
+                          if args.route == "static" else "per-step split sizes, eager launches"),
                        "l2_policy": "inputs larger than L2: each step gathers from 11.8 GB of tables/features"},
             "e2e": {"value": world * K * B / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": B * 8 * (2 + N),
                     "d2h_bytes_per_step": 16},
@@ -380,7 +386,8 @@ def main():
     if world == 1:
         line["gpu_launches"] = int(getattr(eng, "launches_per_step", 0)) * K
     else:
-        line["gpu_launches"] = int((F.lib().ttam_launch_count() - launches0) * K / steps_launched)
+        line["gpu_launches"] = (int(sh.launches_per_step) * K if args.route == "static" and not args.no_graph else
+                                int((F.lib().ttam_launch_count() - launches0) * K / steps_launched))
 
     if not args.no_retrieval:
         r = bench_retrieval(tt, c, dev, pk, world=world, rank=rank)

@@ -244,3 +244,45 @@ def test_module_api_forward_backward_matches_oracle():
     n = torch.from_numpy(d["step0/neg"]).cuda()
     t_n = model.item_encoder({"indices": n.reshape(-1), "features": ix.index_select(0, n.reshape(-1))})
     assert model.adaptive_mimic.augment_items(n.reshape(-1), t_n).shape == t_n.shape
+
+
+@pytest.mark.parametrize("name,graph", [("train_gated_mlp", False), ("train_gated_mlp", True), ("train_embedding_only", True)])
+def test_static_slot_route_matches_reference_golden(name, graph):
+    """The static-shape sharded step (sharding.SlotExchange: fixed slots, padding = repeated real ids with zero gradient
+    rows) on the real kernels, world size 1: slot padding is live because the batches are not multiples of 128.  Same
+    bars as the plain fused step; with graph=True steps 1.. are CUDA-graph replays (plan + main)."""
+    from two_tower_augmented_with_adaptive_mimic_mechanism_b200 import ShardedEngine
+    d, meta, init = load_case(name)
+    kw = TRAIN_CASES[name]
+    model = build_model(meta, kw, init, "cuda")
+    sh = ShardedEngine(_engine(model, meta, kw), static=True)
+    ux, ix = torch.from_numpy(d["user_x"]).cuda(), torch.from_numpy(d["item_x"]).cuda()
+    for s in range(meta["steps"]):
+        u, p, n = (torch.from_numpy(d[f"step{s}/{k}"]).cuda() for k in ("users", "pos", "neg"))
+        loss = sh.train_step(u, p, n, ux, ix, graph=graph)
+        assert float(loss[0]) == pytest.approx(float(d["losses"][s]), rel=5e-6, abs=1e-7)
+        assert sh.last_exchange_rows[0] % 128 == 0 and sh.last_exchange_rows[0] >= u.numel()
+    assert sh.fallback_steps == 0
+    sh.eng.flush()
+    got, ref = model_state_np(model), state_after(d, meta["steps"] - 1)
+    for k in ref:
+        np.testing.assert_allclose(got[k], ref[k], rtol=RTOL, atol=ATOL, err_msg=f"{name} {k}")
+
+
+def test_static_slot_route_overflow_falls_back_and_grows():
+    from two_tower_augmented_with_adaptive_mimic_mechanism_b200 import ShardedEngine
+    name = "train_gated_mlp"
+    d, meta, init = load_case(name)
+    kw = TRAIN_CASES[name]
+    model = build_model(meta, kw, init, "cuda")
+    sh = ShardedEngine(_engine(model, meta, kw), static=True, capacity=(8, 8))
+    ux, ix = torch.from_numpy(d["user_x"]).cuda(), torch.from_numpy(d["item_x"]).cuda()
+    for s in range(meta["steps"]):
+        u, p, n = (torch.from_numpy(d[f"step{s}/{k}"]).cuda() for k in ("users", "pos", "neg"))
+        loss = sh.train_step(u, p, n, ux, ix, graph=True)
+        assert float(loss[0]) == pytest.approx(float(d["losses"][s]), rel=5e-6, abs=1e-7)
+    assert sh.fallback_steps >= 1 and sh.capacity[0] > 8
+    sh.eng.flush()
+    got, ref = model_state_np(model), state_after(d, meta["steps"] - 1)
+    for k in ref:
+        np.testing.assert_allclose(got[k], ref[k], rtol=RTOL, atol=ATOL, err_msg=f"{name} {k}")

@@ -99,8 +99,54 @@ def test_exchange_roundtrip_world2():
     _spawn(_exchange_worker, 2)
 
 
+def _slot_exchange_worker(rank, world):
+    from two_tower_augmented_with_adaptive_mimic_mechanism_b200 import sharding as S
+    g = torch.Generator().manual_seed(200 + rank)
+    n_rows, R = 41, 64
+    table = torch.arange(n_rows * 3, dtype=torch.float32).view(n_rows, 3)
+    shard = S.shard_rows(table, rank, world)
+    ex = S.SlotExchange(R, 48, world)                                             # 48 slots per (requester, owner) pair
+    for trial in range(3):
+        idx = torch.randint(0, n_rows, (R,), generator=g)
+        ex.plan(idx); ex.agree()
+        assert int(ex.flag) == 0
+        ex.exchange_ids()
+        assert ex.recv_idx.numel() == world * 48
+        assert torch.equal(S.owner_of(ex.recv_idx, world), torch.full_like(ex.recv_idx, rank))   # padding included
+        # padding repeats real ids: the owner's touched-row set is exactly the union of what the ranks requested from it
+        all_idx = [None] * world
+        dist.all_gather_object(all_idx, idx)
+        want = torch.unique(torch.cat([i[S.owner_of(i, world) == rank] for i in all_idx]))
+        assert torch.equal(torch.unique(ex.recv_idx), want)
+        got = ex.to_requester(shard[ex.local_rows])
+        assert torch.equal(got, table[idx])
+        grads = torch.randn(R, 3, generator=g)
+        recv = ex.to_owner(grads)                                                 # zeros in the padding slots
+        acc = torch.zeros_like(shard).index_add_(0, ex.local_rows, recv)
+        all_g = [None] * world
+        dist.all_gather_object(all_g, grads)
+        full = torch.zeros_like(table)
+        for i, gr in zip(all_idx, all_g):
+            full.index_add_(0, i, gr)
+        torch.testing.assert_close(acc, S.shard_rows(full, rank, world), rtol=1e-6, atol=1e-6)
+    # overflow on ONE rank only, and an empty bucket: every rank sees the flag after agree()
+    idx = torch.randint(0, n_rows, (R,), generator=g)
+    if rank == 0:
+        idx = idx - idx % world + 1                                               # all 64 ids to owner 1: > 48 slots, bucket 0 empty
+    ex.plan(idx)
+    assert int(ex.flag) == (1 if rank == 0 else 0)
+    ex.agree()
+    assert int(ex.flag) == 1
+    assert S.default_slot_capacity(49152, 8) % 128 == 0 and S.default_slot_capacity(49152, 8) >= 49152 // 8
+    assert S.default_slot_capacity(100, 2) <= 128
+
+
+def test_slot_exchange_roundtrip_world2():
+    _spawn(_slot_exchange_worker, 2)
+
+
 # ---------------------------------------------------------------------------------------------
-def _train_worker(rank, world, case, steps, out_dir):
+def _train_worker(rank, world, case, steps, out_dir, route="dynamic"):
     from sharding_backend import OracleEngine, shard_state
     from two_tower_augmented_with_adaptive_mimic_mechanism_b200 import sharding as S
     from two_tower_augmented_with_adaptive_mimic_mechanism_b200.sharded import ShardedEngine
@@ -108,7 +154,10 @@ def _train_worker(rank, world, case, steps, out_dir):
     lu, li, _ = meta["lambdas"]
     eng = OracleEngine(shard_state(init, rank, world), lr=meta["lr"], weight_decay=meta["wd"], betas=meta["betas"],
                        lambdas=(lu, li))
-    sh = ShardedEngine(eng)
+    if route == "dynamic":
+        sh = ShardedEngine(eng)
+    else:      # "static": slots sized by default; "static_tight": 8 slots per pair -> the first step overflows, falls back, grows
+        sh = ShardedEngine(eng, static=True, capacity=(8, 8) if route == "static_tight" else None)
     ux = S.shard_rows(torch.from_numpy(d["user_x"]), rank, world) if "user_x" in d and d["user_x"].size else None
     ix = S.shard_rows(torch.from_numpy(d["item_x"]), rank, world) if "item_x" in d and d["item_x"].size else None
     losses = []
@@ -119,11 +168,12 @@ def _train_worker(rank, world, case, steps, out_dir):
         share = sh.train_step(u[sl], p[sl], n[sl], ux, ix)
         losses.append(sh.global_loss(share).numpy())
     np.savez(Path(out_dir) / f"rank{rank}.npz", losses=np.stack(losses), **{"st/" + k: v for k, v in eng.state.items()},
-             **{"touched/" + k: v for k, v in eng.touched.items()})
+             **{"touched/" + k: v for k, v in eng.touched.items()}, fallback=np.array(sh.fallback_steps))
 
 
+@pytest.mark.parametrize("route", ["dynamic", "static", "static_tight"])
 @pytest.mark.parametrize("case", ["train_gated_mlp", "train_embedding_only"])
-def test_sharded_step_world2_equals_single_process(case, tmp_path):
+def test_sharded_step_world2_equals_single_process(case, route, tmp_path):
     """Two ranks, each with half of the batch and half of the rows == the one-process oracle on the whole batch:
     touched-row sets bit-exact (after mapping local rows back to global ids), values within fp32 summation tolerance."""
     from sharding_backend import TABLES, unshard_state
@@ -131,8 +181,10 @@ def test_sharded_step_world2_equals_single_process(case, tmp_path):
     d, meta, init = load_case(case)
     if (d["step0/users"].shape[0] // world) * world != d["step0/users"].shape[0]:
         pytest.skip("batch not divisible")
-    _spawn(_train_worker, world, case, steps, str(tmp_path))
+    _spawn(_train_worker, world, case, steps, str(tmp_path), route)
     ranks = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
+    for z in ranks:                                            # the tight slots must have taken the dynamic route at least once
+        assert (int(z["fallback"]) > 0) == (route == "static_tight")
     got = unshard_state([{k[3:]: z[k] for k in z.files if k.startswith("st/")} for z in ranks])
     ref_state = {k: v.copy() for k, v in init.items()}
     spec, opt = oracle.spec_from_state(ref_state), oracle.OptState()

@@ -318,6 +318,11 @@ class FusedEngine:
         self.launches_per_step = F.lib().ttam_launch_count() - launches0
         return loss
 
+    @staticmethod
+    def launch_count() -> int:
+        """libttam kernel launches issued so far by this process (host counter; graph replays are not counted)."""
+        return int(F.lib().ttam_launch_count())
+
     def begin_step(self) -> None:
         """Advance the host-side step counter (the device-side one advances inside the forward phase)."""
         if self.t + 1 > self.max_steps:

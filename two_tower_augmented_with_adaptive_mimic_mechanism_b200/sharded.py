@@ -29,36 +29,56 @@ import torch.distributed as dist
 from . import sharding as S
 
 
-class ShardedEngine:
-    """Drives the three phases of `FusedEngine` (or any object with the same phase methods) across ranks."""
+class _Static:
+    """Buffers of the static-shape step for one (B, N): input copies, the two slot exchanges, the combined flag."""
 
-    def __init__(self, engine, group=None) -> None:
+    def __init__(self, B, N, world, group, device, cap_u, cap_i):
+        self.B, self.N = B, N
+        self.users = torch.zeros(B, dtype=torch.int64, device=device)
+        self.items = torch.zeros(B * (1 + N), dtype=torch.int64, device=device)
+        self.ex_u = S.SlotExchange(B, cap_u, world, group, device)
+        self.ex_i = S.SlotExchange(B * (1 + N), cap_i, world, group, device)
+        self.flag = torch.zeros(1, dtype=torch.int32, device=device)
+        self.flag_host = torch.zeros(1, dtype=torch.int32)
+        if torch.device(device).type == "cuda":
+            self.flag_host = self.flag_host.pin_memory()
+        self.graph_plan = self.graph_main = None
+        self.loss = None
+        self.x_key = None
+
+
+class ShardedEngine:
+    """Drives the three phases of `FusedEngine` (or any object with the same phase methods) across ranks.
+
+    static=False: every step sizes its all-to-alls from the step's own counts (one host read per step, eager launches).
+    static=True:  fixed-capacity slots per (requester, owner) pair (`sharding.SlotExchange`): no data-dependent shape, so
+                  with graph=True the whole step - towers, loss, optimisers AND the collectives - is two CUDA-graph
+                  replays (plan, main) around the step's single host read (the overflow flag).  A step whose ids do not
+                  fit the slots runs on the dynamic route instead (same results), and the capacity grows."""
+
+    def __init__(self, engine, group=None, *, static: bool = False, capacity=None) -> None:
         self.eng = engine
         self.group = group
         self.world = S._world(group)
         self.rank = dist.get_rank(group) if self.world > 1 else 0
         self.last_exchange_rows = (0, 0)
+        self.static = bool(static)
+        self.capacity = capacity              # None or (cap_users, cap_items)
+        self._static: dict = {}
+        self.fallback_steps = 0
+        self.launches_per_step = 0
 
     def _hook(self, grads: list) -> None:
         S.all_reduce_flat(grads, self.group)
 
-    @torch.no_grad()
-    def train_step(self, users: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor, user_x_shard, item_x_shard):
-        """users [B], pos [B], neg [B, N]: GLOBAL row ids of this rank's samples.  user_x_shard / item_x_shard: the rows
-        of the feature matrices this rank owns (sharding.shard_rows).  Returns this rank's share loss[4] of the global
-        loss {total, bce, mimic_user, mimic_item}."""
+    # ---- the step body, shared by both routes ---------------------------------------------------------------------
+    def _body(self, ex_u, ex_i, items, B, N, user_x_shard, item_x_shard):
         eng, W = self.eng, self.world
-        B, N = neg.shape
-        items = torch.cat([pos.reshape(-1), neg.reshape(-1)])
-        ex_u, ex_i = S.Exchange.build_many([users, items], W, self.group)
-        if ex_u.n_owned == 0 or ex_i.n_owned == 0:
-            raise RuntimeError("a rank owns none of the rows requested in this step; use a larger batch")
-        self.last_exchange_rows = (ex_u.n_owned, ex_i.n_owned)
-        eng.begin_step()
         ctx = eng._forward_phase(ex_u.local_rows.contiguous(), ex_i.local_rows.contiguous(), user_x_shard, item_x_shard)
         cu, ci = ctx["cu"], ctx["ci"]
         mimic = bool(eng.mimic)
         D = cu.t.shape[1]
+        hook = self._hook if W > 1 else None
         if mimic:
             tq_u = ex_u.to_requester(torch.cat([cu.t, cu.q], dim=1))
             tq_i = ex_i.to_requester(torch.cat([ci.t, ci.q], dim=1))
@@ -70,15 +90,109 @@ class ShardedEngine:
             g_u = ex_u.to_owner(torch.cat([do_u, dq_u], dim=1))
             g_i = ex_i.to_owner(torch.cat([do_i, torch.cat([dq_p, do_i[B:]], dim=0)], dim=1))
             eng._backward_phase(ctx, g_u[:, :D].contiguous(), g_i[:, :D].contiguous(), g_u[:, D:].contiguous(),
-                                g_i[:, D:].contiguous(), dense_grad_hook=self._hook if W > 1 else None)
+                                g_i[:, D:].contiguous(), dense_grad_hook=hook)
         else:
             o_u = ex_u.to_requester(cu.t)
             o_i = ex_i.to_requester(ci.t)
             loss, do_u, do_i, _, _ = eng._loss_phase(o_u.contiguous(), o_i.contiguous(), None, None, None, None, items, B, N,
                                                      batch_fraction=1.0 / W)
-            eng._backward_phase(ctx, ex_u.to_owner(do_u), ex_i.to_owner(do_i), None, None,
-                                dense_grad_hook=self._hook if W > 1 else None)
+            eng._backward_phase(ctx, ex_u.to_owner(do_u), ex_i.to_owner(do_i), None, None, dense_grad_hook=hook)
         return loss
+
+    # ---- dynamic route ----------------------------------------------------------------------------------------------
+    def _dynamic_step(self, users, pos, neg, user_x_shard, item_x_shard):
+        B, N = neg.shape
+        items = torch.cat([pos.reshape(-1), neg.reshape(-1)])
+        ex_u, ex_i = S.Exchange.build_many([users, items], self.world, self.group)
+        if ex_u.n_owned == 0 or ex_i.n_owned == 0:
+            raise RuntimeError("a rank owns none of the rows requested in this step; use a larger batch")
+        self.last_exchange_rows = (ex_u.n_owned, ex_i.n_owned)
+        self.eng.begin_step()
+        return self._body(ex_u, ex_i, items, B, N, user_x_shard, item_x_shard)
+
+    # ---- static route -----------------------------------------------------------------------------------------------
+    def _static_state(self, B, N, device) -> _Static:
+        st = self._static.get((B, N))
+        if st is None:
+            cap_u, cap_i = self.capacity or (S.default_slot_capacity(B, self.world),
+                                             S.default_slot_capacity(B * (1 + N), self.world))
+            st = _Static(B, N, self.world, self.group, device, cap_u, cap_i)
+            self._static[(B, N)] = st
+        return st
+
+    def _plan(self, st: _Static) -> None:
+        st.ex_u.plan(st.users)
+        st.ex_i.plan(st.items)
+        torch.maximum(st.ex_u.flag, st.ex_i.flag, out=st.flag)
+        if self.world > 1:                  # every rank takes the same route
+            dist.all_reduce(st.flag, op=dist.ReduceOp.MAX, group=self.group)
+        st.flag_host.copy_(st.flag, non_blocking=True)
+
+    def _main(self, st: _Static, user_x_shard, item_x_shard):
+        st.ex_u.exchange_ids()
+        st.ex_i.exchange_ids()
+        return self._body(st.ex_u, st.ex_i, st.items, st.B, st.N, user_x_shard, item_x_shard)
+
+    def _overflowed(self, st: _Static) -> bool:
+        if st.flag.is_cuda:
+            torch.cuda.current_stream(st.flag.device).synchronize()      # the step's only host read
+        return bool(int(st.flag_host[0]))
+
+    def _grow(self, B, N) -> None:
+        """After a step that did not fit: 25 % more slots (graphs and buffers of this shape are rebuilt on next use)."""
+        st = self._static.pop((B, N))
+        up = lambda c, n: min((int(c * 1.25) + 127) // 128 * 128, (n + 127) // 128 * 128)
+        self.capacity = (up(st.ex_u.cap, B), up(st.ex_i.cap, B * (1 + N)))
+
+    def _static_step(self, users, pos, neg, user_x_shard, item_x_shard, graph: bool):
+        eng = self.eng
+        B, N = neg.shape
+        st = self._static_state(B, N, users.device)
+        st.users.copy_(users)
+        st.items[:B].copy_(pos.reshape(-1))
+        st.items[B:].copy_(neg.reshape(-1))
+        x_key = (None if user_x_shard is None else user_x_shard.data_ptr(), None if item_x_shard is None else item_x_shard.data_ptr())
+        use_graph = graph and users.is_cuda
+        if use_graph and st.graph_main is not None and st.x_key == x_key:
+            st.graph_plan.replay()
+        else:
+            self._plan(st)
+        if self._overflowed(st):
+            self.fallback_steps += 1
+            self._grow(B, N)
+            return self._dynamic_step(users, pos, neg, user_x_shard, item_x_shard)
+        self.last_exchange_rows = (st.ex_u.n_slots, st.ex_i.n_slots)
+        eng.begin_step()
+        if use_graph and st.graph_main is not None and st.x_key == x_key:
+            st.graph_main.replay()
+            return st.loss
+        count = getattr(eng, "launch_count", None)
+        c0 = count() if count is not None else 0
+        loss = self._main(st, user_x_shard, item_x_shard)
+        if count is not None:
+            self.launches_per_step = count() - c0            # libttam launches of one step (what a graph replay re-issues)
+        if use_graph:
+            # that eager step sized every buffer and opened the NCCL channels; record both halves for the next steps
+            # (capture does not execute anything, so the step counters stay where they are)
+            torch.cuda.synchronize()
+            gp, gm = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gp, capture_error_mode="thread_local"):
+                self._plan(st)
+            with torch.cuda.graph(gm, capture_error_mode="thread_local"):
+                st.loss = self._main(st, user_x_shard, item_x_shard)
+            st.graph_plan, st.graph_main, st.x_key = gp, gm, x_key
+        return loss
+
+    @torch.no_grad()
+    def train_step(self, users: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor, user_x_shard, item_x_shard, *,
+                   graph: bool = False):
+        """users [B], pos [B], neg [B, N]: GLOBAL row ids of this rank's samples.  user_x_shard / item_x_shard: the rows
+        of the feature matrices this rank owns (sharding.shard_rows).  Returns this rank's share loss[4] of the global
+        loss {total, bce, mimic_user, mimic_item} (valid until the next step).  graph=True (static route, CUDA): replay
+        the step as CUDA graphs; B and N must then be the same on every rank."""
+        if self.static:
+            return self._static_step(users, pos, neg, user_x_shard, item_x_shard, graph)
+        return self._dynamic_step(users, pos, neg, user_x_shard, item_x_shard)
 
     def global_loss(self, loss: torch.Tensor) -> torch.Tensor:
         out = loss.clone()
@@ -87,10 +201,10 @@ class ShardedEngine:
         return out
 
 
-def build_sharded_engine(model_shard, *, group=None, **engine_kwargs) -> ShardedEngine:
+def build_sharded_engine(model_shard, *, group=None, static: bool = False, **engine_kwargs) -> ShardedEngine:
     """`model_shard`: a TwoTowerModel whose tables hold this rank's rows (num_embeddings = sharding.shard_size(...))."""
     from .engine import FusedEngine
-    return ShardedEngine(FusedEngine(model_shard, **engine_kwargs), group=group)
+    return ShardedEngine(FusedEngine(model_shard, **engine_kwargs), group=group, static=static)
 
 
 class ShardedFlatIPIndex:

@@ -176,3 +176,105 @@ def merge_topk_shards(ids: torch.Tensor, scores: torch.Tensor, k: int, merge_fn,
     ids_in = ids_in.view(W, q, K1).transpose(0, 1).contiguous()
     sc_in = sc_in.view(W, q, K1).transpose(0, 1).contiguous()
     return merge_fn(ids_in, sc_in, k)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Static-shape route: the same exchange with FIXED-capacity slots, so that a whole sharded step has no data-dependent
+# shape, needs no host read of split sizes, and replays as one CUDA graph (collectives included).
+def default_slot_capacity(n_req: int, world: int) -> int:
+    """Slots per (requester, owner) pair.  Uniform ids put n_req/W rows (+- a few sqrt) on each owner; a Zipf head puts
+    one hot row's duplicates on a single owner, more visibly the smaller n_req/W is: headroom 3.5 % per rank + 64 rows,
+    rounded up to a multiple of 128 (the GEMM tile height: W*cap rows leave no ragged tile)."""
+    per = (n_req + world - 1) // world
+    cap = int(per * (1.0 + 0.035 * world)) + 64
+    return min((cap + 127) // 128 * 128, (n_req + 127) // 128 * 128)
+
+
+class SlotExchange:
+    """All-to-all route of one index set with `cap` slots per (requester, owner) pair.
+
+    Every collective is an equal-split all-to-all of W*cap rows.  A requester's unused slots are PADDING: they repeat the
+    first real id of their bucket, so the owner's set of touched rows is exactly the set of requested rows (the
+    SparseAdam / lazy-AdamW row sets stay bit-identical to the unpadded step), their tower outputs are dropped on the
+    way back, and their gradient rows are zeros (x + 0.0 == x: segment sums and weight gradients are unchanged).
+
+    `plan(idx)` buckets the ids and raises `flag` (device int32) when a bucket overflows `cap` or is empty (no id to
+    pad with); `agree()` max-reduces the flag over the ranks.  The caller reads it once per step and falls back to the
+    dynamic `Exchange` for that step when it is set - the only host read of the static step.
+    Same attribute / method names as `Exchange`: the step code does not care which one routes its rows."""
+
+    def __init__(self, n_req: int, cap: int, world: int, group=None, device="cpu") -> None:
+        self.group, self.world, self.n_req, self.cap = group, int(world), int(n_req), int(cap)
+        W, dev = self.world, torch.device(device)
+        self.n_slots = W * self.cap
+        self.send_idx = torch.zeros(self.n_slots + 1, dtype=torch.int64, device=dev)      # +1: dump slot of overflowing ids
+        self.slot_of = torch.zeros(self.n_req, dtype=torch.int64, device=dev)
+        self.recv_idx = torch.zeros(self.n_slots, dtype=torch.int64, device=dev)
+        self.local_rows = torch.zeros(self.n_slots, dtype=torch.int64, device=dev)
+        self.flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._arange_w = torch.arange(W, device=dev)
+        self._arange_r = torch.arange(self.n_req, device=dev)
+        self._bufs: dict = {}
+
+    @property
+    def n_owned(self) -> int:
+        return self.n_slots
+
+    def _buf(self, name, cols, dtype, like):
+        key = (name, cols, dtype)
+        t = self._bufs.get(key)
+        if t is None:
+            t = torch.zeros((self.n_slots + 1, cols), dtype=dtype, device=like.device)
+            self._bufs[key] = t
+        return t
+
+    def plan(self, idx: torch.Tensor) -> None:
+        """Bucket `idx` [n_req] by owner into the slot layout (no communication, no host read)."""
+        W, cap, R = self.world, self.cap, self.n_req
+        idx = idx.reshape(-1)
+        owner = owner_of(idx, W)
+        order = bucket_order(owner, W).long()                  # stable: original order inside a bucket
+        so, sid = owner[order], idx[order]
+        counts = (owner.unsqueeze(1) == self._arange_w).sum(0)
+        starts = torch.cumsum(counts, 0) - counts
+        j = self._arange_r - starts[so]
+        slot = torch.where(j < cap, so * cap + j, torch.full_like(j, self.n_slots))
+        self.slot_of.index_copy_(0, order, slot)
+        first = sid[torch.clamp(starts, max=R - 1)]             # first real id of every bucket (meaningless if empty: flagged)
+        self.send_idx[: self.n_slots].view(W, cap).copy_(first.unsqueeze(1).expand(W, cap))
+        self.send_idx.scatter_(0, slot, sid)                    # overflowing ids land in the dump slot
+        self.flag.copy_(((counts > cap) | (counts == 0)).any().to(torch.int32).reshape(1))
+
+    def agree(self) -> None:
+        if self.world > 1:
+            dist.all_reduce(self.flag, op=dist.ReduceOp.MAX, group=self.group)
+
+    def exchange_ids(self) -> None:
+        if self.world > 1:
+            dist.all_to_all_single(self.recv_idx, self.send_idx[: self.n_slots], group=self.group)
+        else:
+            self.recv_idx.copy_(self.send_idx[: self.n_slots])
+        torch.div(self.recv_idx, self.world, rounding_mode="floor", out=self.local_rows)
+
+    def to_requester(self, rows_owner: torch.Tensor) -> torch.Tensor:
+        """rows_owner [W*cap, C] (slot order of recv_idx) -> [n_req, C] in the order of the requester's idx."""
+        C = rows_owner.shape[1]
+        back = self._buf("back", C, rows_owner.dtype, rows_owner)
+        if self.world > 1:
+            dist.all_to_all_single(back[: self.n_slots], rows_owner.contiguous(), group=self.group)
+        else:
+            back[: self.n_slots].copy_(rows_owner)
+        return back.index_select(0, self.slot_of)
+
+    def to_owner(self, rows_req: torch.Tensor) -> torch.Tensor:
+        """rows_req [n_req, C] (order of idx) -> [W*cap, C] in slot order; padding slots carry zeros."""
+        C = rows_req.shape[1]
+        send = self._buf("send", C, rows_req.dtype, rows_req)
+        send.zero_()
+        send.index_copy_(0, self.slot_of, rows_req)
+        out = self._buf("out", C, rows_req.dtype, rows_req)
+        if self.world > 1:
+            dist.all_to_all_single(out[: self.n_slots], send[: self.n_slots], group=self.group)
+        else:
+            out[: self.n_slots].copy_(send[: self.n_slots])
+        return out[: self.n_slots]
