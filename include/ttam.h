@@ -260,6 +260,29 @@ int ttam_dense_step(int kind, const ttam_tensor_list* list_host, const float* sc
                     double weight_decay, double beta1, double beta2, double eps, double momentum, int64_t step,
                     const ttam_step_state* state_dev, void* stream);
 
+/* ---- fixed-capacity slot route of the row-sharded step (no reference counterpart: the reference is
+ * single-process.  Replaces the per-step split sizes of the id / row / gradient all-to-alls by W x cap static slots,
+ * so that the sharded step replays as a CUDA graph.)
+ * ttam_slot_plan  : owner(id) = id % world.  Bucket idx[R] by owner, original order kept inside a bucket, bucket o
+ *                   in slots [o*cap, (o+1)*cap): send_idx[world*cap] (padding slots repeat the bucket's first id: the
+ *                   owner's touched-row SET is unchanged), slot_of[R] (slot of every request; world*cap = did not
+ *                   fit), req_of[world*cap] (request held by a slot, -1 = padding), *flag = 1 when a bucket holds
+ *                   more than cap ids or none (the caller must then route this step dynamically), else 0.
+ * ttam_slot_unpack: t_src[w] / q_src[w] (HOST arrays of `world` device pointers, q_src may be NULL) = base of the
+ *                   rows owner w produced for THIS requester (row j of bucket w at base + j*ld_src): the local
+ *                   receive buffer of an all-to-all, or owner w's own buffer through an NVLink peer mapping.
+ *                   Writes, in request order, t_out[R,D], q_out[R,D], o_out[R,D] = t + q (each may be NULL).
+ * ttam_slot_pack  : for every slot s (bucket w, position j): a_dst[w][j*ld_dst ..] = a[r], b_dst[w][..] = (r < n0 ?
+ *                   b0[r] : b1[r]) with r = req_of[s]; zeros for padding slots.  b_dst may be NULL. */
+int64_t ttam_slot_plan_workspace_bytes(int64_t R, int64_t world);
+int ttam_slot_plan(const int64_t* idx, int64_t R, int64_t world, int64_t cap, int64_t* send_idx, int64_t* slot_of,
+                   int32_t* req_of, int32_t* flag, void* workspace, int64_t workspace_bytes, void* stream);
+int ttam_slot_unpack(const float* const* t_src, const float* const* q_src, int64_t ld_src, int64_t world, int64_t cap,
+                     const int64_t* slot_of, int64_t R, int64_t D, float* t_out, float* q_out, float* o_out,
+                     void* stream);
+int ttam_slot_pack(const float* a, const float* b0, int64_t n0, const float* b1, const int32_t* req_of, int64_t world,
+                   int64_t cap, int64_t D, float* const* a_dst, float* const* b_dst, int64_t ld_dst, void* stream);
+
 /* ---- retrieval (training.py:330-384, 613-679, 944-972; faiss.IndexFlatIP) --------------------------
  * Exact inner-product top-K of every query against the whole corpus, result in canonical order
  * (descending score, ascending id on ties).  Scores returned are the canonical fp32 scores

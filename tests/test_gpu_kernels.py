@@ -434,3 +434,47 @@ def test_dense_step_matches_oracle(F):
                 o_dense_step(kind, r, g, st, lr=1e-3, weight_decay=0.01, momentum=0.9)
         for a, r in zip(dp, ref):
             np.testing.assert_allclose(a.cpu().numpy(), r, rtol=1e-5, atol=1e-6, err_msg=kind)   # Adam divides by sqrt(v) ~ |g|: ulps of g move p by ulps of lr
+
+
+@pytest.mark.parametrize("W,R,cap", [(1, 77, 128), (2, 5000, 2688), (8, 49152, 7936), (8, 3000, 300), (4, 1024, 512)])
+def test_slot_plan_pack_unpack_bit_exact(W, R, cap):
+    """csrc/slots.cu against the torch-op restatement of the same layout (sharding.SlotExchange CPU path, the one the
+    gloo tests run): slot layout, padding ids, flag, un-bucket (t, q, o = t + q) and re-bucket with zero padding rows."""
+    from two_tower_augmented_with_adaptive_mimic_mechanism_b200 import functional as F
+    from two_tower_augmented_with_adaptive_mimic_mechanism_b200 import sharding as S
+    g = torch.Generator().manual_seed(W * 1000 + R)
+    idx = torch.randint(0, 100000, (R,), generator=g)
+    idx[: R // 8] = idx[0]                                       # a hot row: one bucket runs ahead of the others
+    ref, dev = S.SlotExchange(R, cap, W), S.SlotExchange(R, cap, W, device="cuda")
+    ref.plan(idx)
+    dev.plan(idx.cuda())
+    n = W * cap
+    assert int(dev.flag) == int(ref.flag)
+    if int(ref.flag):
+        counts = torch.bincount(idx % W, minlength=W)
+        assert bool((counts > cap).any()) or bool((counts == 0).any())
+        fits = ref.slot_of < n                                   # what fits is laid out identically; the rest is marked
+        assert torch.equal(dev.slot_of.cpu()[fits], ref.slot_of[fits]) and bool((dev.slot_of.cpu()[~fits] == n).all())
+        return
+    assert torch.equal(dev.send_idx[:n].cpu(), ref.send_idx[:n])
+    assert torch.equal(dev.slot_of.cpu(), ref.slot_of)
+    req_of = dev.req_of.cpu().long()
+    held = req_of >= 0
+    assert int(held.sum()) == R and torch.equal(ref.slot_of[req_of[held]], torch.nonzero(held).view(-1))
+    D = 96
+    t_own, q_own = torch.randn(n, D, generator=g), torch.randn(n, D, generator=g)
+    tc, qc = t_own.cuda(), q_own.cuda()
+    t, q, o = (torch.empty(R, D, device="cuda") for _ in range(3))
+    bases = lambda x: [x.data_ptr() + w * cap * D * 4 for w in range(W)]
+    F.slot_unpack(bases(tc), bases(qc), D, cap, dev.slot_of, D, t_out=t, q_out=q, o_out=o)
+    assert torch.equal(t.cpu(), t_own[ref.slot_of]) and torch.equal(q.cpu(), q_own[ref.slot_of])
+    assert torch.equal(o.cpu(), t_own[ref.slot_of] + q_own[ref.slot_of])
+    F.slot_unpack(bases(tc), None, D, cap, dev.slot_of, D, t_out=None, q_out=None, o_out=o)
+    assert torch.equal(o.cpu(), t_own[ref.slot_of])
+    a, b0, n0 = torch.randn(R, D, generator=g), torch.randn(R, D, generator=g), R // 6
+    ga, gb = torch.full((n, D), 7.0, device="cuda"), torch.full((n, D), 7.0, device="cuda")
+    ac = a.cuda()
+    F.slot_pack(ac, b0[:n0].cuda(), ac, dev.req_of, cap, bases(ga), bases(gb), D)
+    want_a = torch.zeros(n + 1, D).index_copy_(0, ref.slot_of, a)[:n]
+    want_b = torch.zeros(n + 1, D).index_copy_(0, ref.slot_of, torch.cat([b0[:n0], a[n0:]]))[:n]
+    assert torch.equal(ga.cpu(), want_a) and torch.equal(gb.cpu(), want_b)

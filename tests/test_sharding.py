@@ -118,10 +118,22 @@ def _slot_exchange_worker(rank, world):
         dist.all_gather_object(all_idx, idx)
         want = torch.unique(torch.cat([i[S.owner_of(i, world) == rank] for i in all_idx]))
         assert torch.equal(torch.unique(ex.recv_idx), want)
-        got = ex.to_requester(shard[ex.local_rows])
-        assert torch.equal(got, table[idx])
+        got_t, got_q, got_o = ex.pull(shard[ex.local_rows], 2 * shard[ex.local_rows])
+        assert torch.equal(got_t, table[idx]) and torch.equal(got_q, 2 * table[idx]) and torch.equal(got_o, 3 * table[idx])
+        only_t = ex.pull(shard[ex.local_rows])
+        assert torch.equal(only_t[0], table[idx]) and only_t[1] is None and only_t[2] is only_t[0]
         grads = torch.randn(R, 3, generator=g)
-        recv = ex.to_owner(grads)                                                 # zeros in the padding slots
+        b0 = torch.randn(10, 3, generator=g)
+        recv, recv_b = ex.push(grads, b0, grads)                                  # zeros in the padding slots
+        want_b = torch.cat([b0, grads[10:]])
+        acc_b = torch.zeros_like(shard).index_add_(0, ex.local_rows, recv_b)
+        all_b = [None] * world
+        dist.all_gather_object(all_b, want_b)
+        full_b = torch.zeros_like(table)
+        for i, gr in zip(all_idx, all_b):
+            full_b.index_add_(0, i, gr)
+        torch.testing.assert_close(acc_b, S.shard_rows(full_b, rank, world), rtol=1e-6, atol=1e-6)
+        assert ex.push(grads)[1] is None
         acc = torch.zeros_like(shard).index_add_(0, ex.local_rows, recv)
         all_g = [None] * world
         dist.all_gather_object(all_g, grads)

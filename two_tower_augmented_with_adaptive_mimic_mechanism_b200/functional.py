@@ -425,3 +425,38 @@ def topk_merge(ids: torch.Tensor, scores: torch.Tensor, k_out: int):
     check(lib().ttam_topk_merge(ids.contiguous().data_ptr(), scores.contiguous().data_ptr(), Q, parts, k_in, k_out,
                                 out_i.data_ptr(), out_s.data_ptr(), _stream()), "topk_merge")
     return out_i, out_s
+
+
+# ---- fixed-capacity slot route of the row-sharded step (csrc/slots.cu) -----------------------------------------------
+def slot_plan(idx: torch.Tensor, world: int, cap: int, *, send_idx, slot_of, req_of, flag) -> None:
+    _chk(idx, torch.int64, "idx")
+    idx = idx.contiguous().view(-1)
+    R = idx.numel()
+    if send_idx.numel() < world * cap or slot_of.numel() < R or req_of.numel() < world * cap:
+        raise ValueError("slot_plan: output buffers too small")
+    ws = workspace(lib().ttam_slot_plan_workspace_bytes(R, world), idx.device, "slots")
+    check(lib().ttam_slot_plan(idx.data_ptr(), R, world, cap, send_idx.data_ptr(), slot_of.data_ptr(), req_of.data_ptr(),
+                               flag.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "slot_plan")
+
+
+def _ptr_array(ptrs):
+    import ctypes as C
+    return None if ptrs is None else (C.c_void_p * len(ptrs))(*ptrs)
+
+
+def slot_unpack(t_src: list, q_src, ld_src: int, cap: int, slot_of: torch.Tensor, D: int, *, t_out=None, q_out=None,
+                o_out=None) -> None:
+    """t_src / q_src: one device address per owner (ints).  Outputs [R, D] fp32, request order."""
+    R = slot_of.numel()
+    check(lib().ttam_slot_unpack(_ptr_array(t_src), _ptr_array(q_src), ld_src, len(t_src), cap, slot_of.data_ptr(), R, D,
+                                 _ptr(t_out), _ptr(q_out), _ptr(o_out), _stream()), "slot_unpack")
+
+
+def slot_pack(a: torch.Tensor, b0, b1, req_of: torch.Tensor, cap: int, a_dst: list, b_dst, ld_dst: int) -> None:
+    """a [R, D]; b rows: b0[r] for r < b0.shape[0], b1[r] beyond (either may be None).  a_dst / b_dst: one device address
+    per owner."""
+    _chk(a, torch.float32, "a")
+    D = a.shape[1]
+    n0 = 0 if b0 is None else b0.shape[0]
+    check(lib().ttam_slot_pack(a.data_ptr(), _ptr(b0), n0, _ptr(b1), req_of.data_ptr(), len(a_dst), cap, D,
+                               _ptr_array(a_dst), _ptr_array(b_dst), ld_dst, _stream()), "slot_pack")

@@ -79,6 +79,21 @@ class ShardedEngine:
         mimic = bool(eng.mimic)
         D = cu.t.shape[1]
         hook = self._hook if W > 1 else None
+        bf = 1.0 / W
+        if isinstance(ex_u, S.SlotExchange):      # static route: fused un-bucket / re-bucket kernels around the collectives
+            if mimic:
+                t_u, q_u, o_u = ex_u.pull(cu.t, cu.q)
+                t_i, q_i, o_i = ex_i.pull(ci.t, ci.q)
+                loss, do_u, do_i, dq_u, dq_p = eng._loss_phase(o_u, o_i, t_u, t_i[:B], q_u, q_i[:B], items, B, N, batch_fraction=bf)
+                gu_a, gu_b = ex_u.push(do_u, dq_u)
+                gi_a, gi_b = ex_i.push(do_i, dq_p, do_i)          # aug-table rows: dq of the positives, do of the negatives
+                eng._backward_phase(ctx, gu_a, gi_a, gu_b, gi_b, dense_grad_hook=hook)
+            else:
+                _, _, o_u = ex_u.pull(cu.t)
+                _, _, o_i = ex_i.pull(ci.t)
+                loss, do_u, do_i, _, _ = eng._loss_phase(o_u, o_i, None, None, None, None, items, B, N, batch_fraction=bf)
+                eng._backward_phase(ctx, ex_u.push(do_u)[0], ex_i.push(do_i)[0], None, None, dense_grad_hook=hook)
+            return loss
         if mimic:
             tq_u = ex_u.to_requester(torch.cat([cu.t, cu.q], dim=1))
             tq_i = ex_i.to_requester(torch.cat([ci.t, ci.q], dim=1))

@@ -215,6 +215,7 @@ class SlotExchange:
         self._arange_w = torch.arange(W, device=dev)
         self._arange_r = torch.arange(self.n_req, device=dev)
         self._bufs: dict = {}
+        self.req_of = None                   # int32 [n_slots], CUDA route only: request held by a slot, -1 = padding
 
     @property
     def n_owned(self) -> int:
@@ -229,9 +230,16 @@ class SlotExchange:
         return t
 
     def plan(self, idx: torch.Tensor) -> None:
-        """Bucket `idx` [n_req] by owner into the slot layout (no communication, no host read)."""
+        """Bucket `idx` [n_req] by owner into the slot layout (no communication, no host read).
+        CUDA: ttam_slot_plan (4 launches); CPU (gloo tests): the same layout from torch ops."""
         W, cap, R = self.world, self.cap, self.n_req
         idx = idx.reshape(-1)
+        if idx.is_cuda:
+            from . import functional as F
+            if self.req_of is None:
+                self.req_of = torch.zeros(self.n_slots, dtype=torch.int32, device=idx.device)
+            F.slot_plan(idx, W, cap, send_idx=self.send_idx, slot_of=self.slot_of, req_of=self.req_of, flag=self.flag)
+            return
         owner = owner_of(idx, W)
         order = bucket_order(owner, W).long()                  # stable: original order inside a bucket
         so, sid = owner[order], idx[order]
@@ -256,25 +264,66 @@ class SlotExchange:
             self.recv_idx.copy_(self.send_idx[: self.n_slots])
         torch.div(self.recv_idx, self.world, rounding_mode="floor", out=self.local_rows)
 
-    def to_requester(self, rows_owner: torch.Tensor) -> torch.Tensor:
-        """rows_owner [W*cap, C] (slot order of recv_idx) -> [n_req, C] in the order of the requester's idx."""
-        C = rows_owner.shape[1]
-        back = self._buf("back", C, rows_owner.dtype, rows_owner)
-        if self.world > 1:
-            dist.all_to_all_single(back[: self.n_slots], rows_owner.contiguous(), group=self.group)
-        else:
-            back[: self.n_slots].copy_(rows_owner)
-        return back.index_select(0, self.slot_of)
+    def _a2a(self, out: torch.Tensor, inp: torch.Tensor) -> None:
+        dist.all_to_all_single(out, inp, group=self.group)
 
-    def to_owner(self, rows_req: torch.Tensor) -> torch.Tensor:
-        """rows_req [n_req, C] (order of idx) -> [W*cap, C] in slot order; padding slots carry zeros."""
-        C = rows_req.shape[1]
-        send = self._buf("send", C, rows_req.dtype, rows_req)
-        send.zero_()
-        send.index_copy_(0, self.slot_of, rows_req)
-        out = self._buf("out", C, rows_req.dtype, rows_req)
-        if self.world > 1:
-            dist.all_to_all_single(out[: self.n_slots], send[: self.n_slots], group=self.group)
+    def pull(self, t_owner: torch.Tensor, q_owner: Optional[torch.Tensor] = None):
+        """Forward exchange.  t_owner / q_owner [W*cap, D]: what this rank computed for the slots it received.
+        Returns (t, q, o = t + q), each [n_req, D] in the order of the requester's ids (q None and o = t without q_owner)."""
+        D, n = t_owner.shape[1], self.n_slots
+        srcs = []
+        for name, rows in (("back_t", t_owner), ("back_q", q_owner)):
+            if rows is None:
+                srcs.append(None)
+            elif self.world > 1:
+                back = self._buf(name, D, rows.dtype, rows)
+                self._a2a(back[:n], rows[:n].contiguous())
+                srcs.append(back)
+            else:
+                srcs.append(rows)
+        if t_owner.is_cuda:
+            from . import functional as F
+            t = self._buf("t", D, t_owner.dtype, t_owner)[: self.n_req]
+            q = self._buf("q", D, t_owner.dtype, t_owner)[: self.n_req] if q_owner is not None else None
+            o = self._buf("o", D, t_owner.dtype, t_owner)[: self.n_req] if q_owner is not None else None
+            step = self.cap * srcs[0].stride(0) * 4
+            bases = lambda x: None if x is None else [x.data_ptr() + w * step for w in range(self.world)]
+            F.slot_unpack(bases(srcs[0]), bases(srcs[1]), srcs[0].stride(0), self.cap, self.slot_of, D, t_out=t, q_out=q, o_out=o)
+            return t, q, (o if q is not None else t)
+        pad = lambda x: x if x.shape[0] > n else torch.cat([x, x.new_zeros((1, D))])      # dump slot of the ids that did not fit
+        t = pad(srcs[0]).index_select(0, self.slot_of)
+        if q_owner is None:
+            return t, None, t
+        q = pad(srcs[1]).index_select(0, self.slot_of)
+        return t, q, t + q
+
+    def push(self, a: torch.Tensor, b0: Optional[torch.Tensor] = None, b1: Optional[torch.Tensor] = None):
+        """Backward exchange.  a [n_req, D] and, optionally, b rows (b0[r] for r < len(b0), b1[r] beyond) in the order of
+        the requester's ids.  Returns (ga, gb) [W*cap, D] in this rank's slot order; padding slots carry zeros."""
+        D, n = a.shape[1], self.n_slots
+        has_b = b0 is not None or b1 is not None
+        direct = self.world == 1
+        send_a = self._buf("out_a" if direct else "send_a", D, a.dtype, a)
+        send_b = self._buf("out_b" if direct else "send_b", D, a.dtype, a) if has_b else None
+        if a.is_cuda:
+            from . import functional as F
+            step = self.cap * D * 4
+            bases = lambda x: None if x is None else [x.data_ptr() + w * step for w in range(self.world)]
+            F.slot_pack(a, b0, b1, self.req_of, self.cap, bases(send_a), bases(send_b), D)
         else:
-            out[: self.n_slots].copy_(send[: self.n_slots])
-        return out[: self.n_slots]
+            send_a.zero_()
+            send_a.index_copy_(0, self.slot_of, a)
+            if has_b:
+                n0 = 0 if b0 is None else b0.shape[0]
+                b = b0 if n0 >= self.n_req else (b1 if n0 == 0 else torch.cat([b0, b1[n0:]]))
+                send_b.zero_()
+                send_b.index_copy_(0, self.slot_of, b)
+        if direct:
+            return send_a[:n], (send_b[:n] if has_b else None)
+        out_a = self._buf("out_a", D, a.dtype, a)
+        self._a2a(out_a[:n], send_a[:n])
+        out_b = None
+        if has_b:
+            out_b = self._buf("out_b", D, a.dtype, a)
+            self._a2a(out_b[:n], send_b[:n])
+        return out_a[:n], (out_b[:n] if has_b else None)
