@@ -200,8 +200,9 @@ def main():
                     help="optimiser sweep (BASELINE configs[4]): hybrid = AdamW + SparseAdam (reference default), "
                          "sparse = embedding-only towers, mimic off, all SparseAdam, dense = sparse:false (AdamW semantics on every table)")
     ap.add_argument("--no-graph", action="store_true", help="N=1: launch the step eagerly instead of replaying a CUDA graph (diagnostic)")
-    ap.add_argument("--route", default="static", choices=["static", "dynamic"],
-                    help="N>1: static = fixed-capacity slots, the whole sharded step replays as CUDA graphs; dynamic = per-step "
+    ap.add_argument("--route", default="static", choices=["static", "peer", "dynamic"],
+                    help="N>1: static = fixed-capacity slots, the whole sharded step replays as CUDA graphs; peer = static, and the "
+                         "row payloads travel by NVLink peer loads/stores instead of NCCL all-to-alls; dynamic = per-step "
                          "split sizes, eager launches (diagnostic)")
     ap.add_argument("--small", action="store_true", help="1/16-size tables (debugging only; not a valid bench line)")
     args = ap.parse_args()
@@ -269,7 +270,7 @@ def main():
     eng = tt.FusedEngine(model, optimizer="adamw", lr=c["lr"], weight_decay=c["wd"], precision=args.precision,
                          loss_weights={} if mimic is None else {"mimic_user": c["lambdas"][0], "mimic_item": c["lambdas"][1]},
                          max_steps=4 * (K + W) + 64)
-    sh = tt.ShardedEngine(eng, static=args.route == "static") if world > 1 else None
+    sh = tt.ShardedEngine(eng, static=args.route != "dynamic", peer=args.route == "peer") if world > 1 else None
     users, pos, neg = make_batches(K + W, c, dev, gen)          # global row ids
     if sh is not None:
         # N > 1: a few extra untimed steps before the W warm-up steps.  The number of rows a rank owns changes from step to
@@ -378,7 +379,9 @@ def main():
                        f"{world} gpus: tables/features row-sharded, batch data-parallel ({B} samples per gpu), 3 all-to-all + 1 all-reduce per step, "
                        + (f"fixed-capacity slots ({sh.last_exchange_rows[0] // world}/{sh.last_exchange_rows[1] // world} user/item rows per "
                           f"rank pair), CUDA-graph replay incl. collectives, {sh.fallback_steps} dynamic-route fallback steps"
-                          if args.route == "static" else "per-step split sizes, eager launches"),
+                          + (", row payloads by NVLink peer loads/stores fused into the un-bucket/re-bucket kernels (2 device barriers per step)"
+                             if args.route == "peer" else "")
+                          if args.route != "dynamic" else "per-step split sizes, eager launches"),
                        "l2_policy": "inputs larger than L2: each step gathers from 11.8 GB of tables/features"},
             "e2e": {"value": world * K * B / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": B * 8 * (2 + N),
                     "d2h_bytes_per_step": 16},
@@ -386,7 +389,7 @@ def main():
     if world == 1:
         line["gpu_launches"] = int(getattr(eng, "launches_per_step", 0)) * K
     else:
-        line["gpu_launches"] = (int(sh.launches_per_step) * K if args.route == "static" and not args.no_graph else
+        line["gpu_launches"] = (int(sh.launches_per_step) * K if args.route != "dynamic" and not args.no_graph else
                                 int((F.lib().ttam_launch_count() - launches0) * K / steps_launched))
 
     if not args.no_retrieval:
@@ -403,10 +406,14 @@ def main():
             line["retrieval"]["cpu_baseline_qps"] = cpu_retrieval(c, 200_000, 2048)
             line["retrieval"]["cpu_sample"] = "2048 queries x 200k items fp32 matmul + torch.topk, all host cores"
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if dist is not None:
+        # leave without tearing the communicator down: destroy_process_group() behind CUDA graphs that hold NCCL kernels
+        # was seen to hang; every rank has printed / synchronised by now
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
     return 0
 
 

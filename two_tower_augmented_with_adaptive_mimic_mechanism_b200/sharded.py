@@ -51,12 +51,15 @@ class ShardedEngine:
     """Drives the three phases of `FusedEngine` (or any object with the same phase methods) across ranks.
 
     static=False: every step sizes its all-to-alls from the step's own counts (one host read per step, eager launches).
+    peer=True (with static): the row payloads of the exchanges do not go through NCCL at all - requesters load the
+                  owners' rows and store their gradient rows over NVLink peer mappings (symmetric memory), fused into
+                  the un-bucket / re-bucket kernels, between two device-side barriers per step.
     static=True:  fixed-capacity slots per (requester, owner) pair (`sharding.SlotExchange`): no data-dependent shape, so
                   with graph=True the whole step - towers, loss, optimisers AND the collectives - is two CUDA-graph
                   replays (plan, main) around the step's single host read (the overflow flag).  A step whose ids do not
                   fit the slots runs on the dynamic route instead (same results), and the capacity grows."""
 
-    def __init__(self, engine, group=None, *, static: bool = False, capacity=None) -> None:
+    def __init__(self, engine, group=None, *, static: bool = False, capacity=None, peer: bool = False) -> None:
         self.eng = engine
         self.group = group
         self.world = S._world(group)
@@ -64,6 +67,7 @@ class ShardedEngine:
         self.last_exchange_rows = (0, 0)
         self.static = bool(static)
         self.capacity = capacity              # None or (cap_users, cap_items)
+        self.peer = bool(peer) and self.static and self.world > 1
         self._static: dict = {}
         self.fallback_steps = 0
         self.launches_per_step = 0
@@ -81,18 +85,28 @@ class ShardedEngine:
         hook = self._hook if W > 1 else None
         bf = 1.0 / W
         if isinstance(ex_u, S.SlotExchange):      # static route: fused un-bucket / re-bucket kernels around the collectives
+            peer = ex_i.peer is not None          # rows travel by NVLink peer loads / stores between two device barriers
+            if peer:
+                ex_u.publish(cu.t, cu.q if mimic else None)
+                ex_i.publish(ci.t, ci.q if mimic else None)
+                ex_i.peer_barrier()               # every owner's rows are in place
             if mimic:
                 t_u, q_u, o_u = ex_u.pull(cu.t, cu.q)
                 t_i, q_i, o_i = ex_i.pull(ci.t, ci.q)
                 loss, do_u, do_i, dq_u, dq_p = eng._loss_phase(o_u, o_i, t_u, t_i[:B], q_u, q_i[:B], items, B, N, batch_fraction=bf)
                 gu_a, gu_b = ex_u.push(do_u, dq_u)
                 gi_a, gi_b = ex_i.push(do_i, dq_p, do_i)          # aug-table rows: dq of the positives, do of the negatives
+                if peer:
+                    ex_i.peer_barrier()           # every requester's gradient rows have landed
                 eng._backward_phase(ctx, gu_a, gi_a, gu_b, gi_b, dense_grad_hook=hook)
             else:
                 _, _, o_u = ex_u.pull(cu.t)
                 _, _, o_i = ex_i.pull(ci.t)
                 loss, do_u, do_i, _, _ = eng._loss_phase(o_u, o_i, None, None, None, None, items, B, N, batch_fraction=bf)
-                eng._backward_phase(ctx, ex_u.push(do_u)[0], ex_i.push(do_i)[0], None, None, dense_grad_hook=hook)
+                gu_a, gi_a = ex_u.push(do_u)[0], ex_i.push(do_i)[0]
+                if peer:
+                    ex_i.peer_barrier()
+                eng._backward_phase(ctx, gu_a, gi_a, None, None, dense_grad_hook=hook)
             return loss
         if mimic:
             tq_u = ex_u.to_requester(torch.cat([cu.t, cu.q], dim=1))
@@ -132,6 +146,14 @@ class ShardedEngine:
             cap_u, cap_i = self.capacity or (S.default_slot_capacity(B, self.world),
                                              S.default_slot_capacity(B * (1 + N), self.world))
             st = _Static(B, N, self.world, self.group, device, cap_u, cap_i)
+            if self.peer:
+                # row payloads over NVLink peer memory: the exchanges own symmetric buffers, and the towers write their
+                # t / q rows straight into them (the engine looks its buffers up by name before allocating)
+                eng = self.eng
+                for ex, plan, bufs in ((st.ex_u, eng.user, eng.bufs_u), (st.ex_i, eng.item, eng.bufs_i)):
+                    ex.enable_peer(plan.out_dim)
+                    if plan.D == plan.out_dim:
+                        bufs["t"], bufs["q"] = ex.own_t, ex.own_q
             self._static[(B, N)] = st
         return st
 

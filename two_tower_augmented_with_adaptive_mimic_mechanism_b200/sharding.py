@@ -216,6 +216,42 @@ class SlotExchange:
         self._arange_r = torch.arange(self.n_req, device=dev)
         self._bufs: dict = {}
         self.req_of = None                   # int32 [n_slots], CUDA route only: request held by a slot, -1 = padding
+        self.peer = None                     # symmetric-memory handle when the rows travel by peer loads / stores
+
+    # ---- NVLink peer route: no all-to-all for the row payloads ---------------------------------------------------
+    def enable_peer(self, D: int) -> None:
+        """Allocate this exchange's row buffers in symmetric memory (torch.distributed._symmetric_memory: every rank's
+        buffer is mapped into every other rank's address space over NVLink) and exchange the mappings.  COLLECTIVE.
+        own_t / own_q: what this rank computes for the slots it serves - requesters LOAD their rows from here
+        (ttam_slot_unpack with one peer base per owner); recv_a / recv_b: the gradient rows of those slots -
+        requesters STORE them here (ttam_slot_pack).  The caller separates producers from consumers with
+        `peer_barrier()` (a device-side barrier over NVLink signal pads, ~6 us, CUDA-graph capturable)."""
+        import torch.distributed._symmetric_memory as symm
+        group = self.group if self.group is not None else dist.group.WORLD
+        buf = symm.empty((4, self.n_slots, D), dtype=torch.float32, device=self.send_idx.device)
+        buf.zero_()
+        self.peer = symm.rendezvous(buf, group)
+        self._peer_buf = buf
+        self.own_t, self.own_q, self.recv_a, self.recv_b = buf[0], buf[1], buf[2], buf[3]
+        self._peer_ptrs = [int(p) for p in self.peer.buffer_ptrs]
+        self._peer_rank = dist.get_rank(group)
+        self._peer_D = D
+
+    def peer_barrier(self) -> None:
+        self.peer.barrier(channel=0)
+
+    def _peer_bases(self, which: int) -> list:
+        """Address, in every rank's buffer, of the rows exchanged with THIS rank: sub-buffer `which`, bucket = my rank."""
+        D = self._peer_D
+        off = (which * self.n_slots + self._peer_rank * self.cap) * D * 4
+        return [p + off for p in self._peer_ptrs]
+
+    def publish(self, t_owner: torch.Tensor, q_owner: Optional[torch.Tensor] = None) -> None:
+        """Make the rows this rank computed loadable by its peers: nothing to do when the tower already wrote them into
+        own_t / own_q (ShardedEngine seeds the engine's buffers with them), one local copy otherwise."""
+        for dst, src in ((self.own_t, t_owner), (self.own_q, q_owner)):
+            if src is not None and src.data_ptr() != dst.data_ptr():
+                dst.copy_(src[: self.n_slots])
 
     @property
     def n_owned(self) -> int:
@@ -271,6 +307,14 @@ class SlotExchange:
         """Forward exchange.  t_owner / q_owner [W*cap, D]: what this rank computed for the slots it received.
         Returns (t, q, o = t + q), each [n_req, D] in the order of the requester's ids (q None and o = t without q_owner)."""
         D, n = t_owner.shape[1], self.n_slots
+        if self.peer is not None:            # published + barrier already passed: load straight from the owners' buffers
+            from . import functional as F
+            t = self._buf("t", D, t_owner.dtype, t_owner)[: self.n_req]
+            q = self._buf("q", D, t_owner.dtype, t_owner)[: self.n_req] if q_owner is not None else None
+            o = self._buf("o", D, t_owner.dtype, t_owner)[: self.n_req] if q_owner is not None else None
+            F.slot_unpack(self._peer_bases(0), self._peer_bases(1) if q_owner is not None else None, D, self.cap, self.slot_of, D,
+                          t_out=t, q_out=q, o_out=o)
+            return t, q, (o if q is not None else t)
         srcs = []
         for name, rows in (("back_t", t_owner), ("back_q", q_owner)):
             if rows is None:
@@ -302,6 +346,10 @@ class SlotExchange:
         the requester's ids.  Returns (ga, gb) [W*cap, D] in this rank's slot order; padding slots carry zeros."""
         D, n = a.shape[1], self.n_slots
         has_b = b0 is not None or b1 is not None
+        if self.peer is not None:            # store straight into the owners' receive buffers; the caller's barrier follows
+            from . import functional as F
+            F.slot_pack(a, b0, b1, self.req_of, self.cap, self._peer_bases(2), self._peer_bases(3) if has_b else None, D)
+            return self.recv_a, (self.recv_b if has_b else None)
         direct = self.world == 1
         send_a = self._buf("out_a" if direct else "send_a", D, a.dtype, a)
         send_b = self._buf("out_b" if direct else "send_b", D, a.dtype, a) if has_b else None
