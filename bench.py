@@ -200,7 +200,7 @@ def main():
                     help="optimiser sweep (BASELINE configs[4]): hybrid = AdamW + SparseAdam (reference default), "
                          "sparse = embedding-only towers, mimic off, all SparseAdam, dense = sparse:false (AdamW semantics on every table)")
     ap.add_argument("--no-graph", action="store_true", help="N=1: launch the step eagerly instead of replaying a CUDA graph (diagnostic)")
-    ap.add_argument("--route", default="static", choices=["static", "peer", "dynamic"],
+    ap.add_argument("--route", default="peer", choices=["static", "peer", "dynamic"],
                     help="N>1: static = fixed-capacity slots, the whole sharded step replays as CUDA graphs; peer = static, and the "
                          "row payloads travel by NVLink peer loads/stores instead of NCCL all-to-alls; dynamic = per-step "
                          "split sizes, eager launches (diagnostic)")

@@ -24,19 +24,22 @@ model = tt.TwoTowerModel(tt.build_tower_encoder(tower, num_embeddings=nu_l, feat
                          adaptive_mimic=tt.AdaptiveMimicMechanism(num_users=nu_l, num_items=ni_l, embedding_dim=c["D"]).to(dev))
 eng = tt.FusedEngine(model, optimizer="adamw", lr=1e-3, weight_decay=0.01, precision="tf32",
                      loss_weights={"mimic_user": 0.15, "mimic_item": 0.15}, max_steps=64)
-sh = tt.ShardedEngine(eng)
+route = os.environ.get("TTAM_ROUTE", "peer")
+sh = tt.ShardedEngine(eng, static=route != "dynamic", peer=route == "peer")
+graph = route != "dynamic"
 users, pos, neg = bench.make_batches(12, c, dev, gen)
 for s in range(4):
-    sh.train_step(users[s], pos[s], neg[s], ux, ix)
+    sh.train_step(users[s], pos[s], neg[s], ux, ix, graph=graph)
 dist.barrier(); torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for s in range(4, 10):
-        sh.train_step(users[s], pos[s], neg[s], ux, ix)
+        sh.train_step(users[s], pos[s], neg[s], ux, ix, graph=graph)
     torch.cuda.synchronize()
 if rank == 0:
     ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     t0, t1 = min(e.time_range.start for e in ev), max(e.time_range.end for e in ev)
     busy = sum(e.time_range.end - e.time_range.start for e in ev)
+    print(f"route {route}, world {world}, slots {sh.last_exchange_rows}, fallback steps {sh.fallback_steps}")
     print(f"6 steps: span {(t1 - t0) / 6:.0f} us/step, GPU busy {busy / 6:.0f} us/step")
     agg = {}
     for e in ev:
@@ -44,4 +47,5 @@ if rank == 0:
         a = agg.setdefault(k, [0.0, 0]); a[0] += e.time_range.end - e.time_range.start; a[1] += 1
     for k, (v, n) in sorted(agg.items(), key=lambda x: -x[1][0])[:18]:
         print(f"{v / 6:8.1f} us/step {n / 6:6.1f} launches/step  {k}")
-dist.destroy_process_group()
+dist.barrier(); torch.cuda.synchronize(); sys.stdout.flush()
+os._exit(0)

@@ -136,6 +136,7 @@ class ShardedEngine:
         if ex_u.n_owned == 0 or ex_i.n_owned == 0:
             raise RuntimeError("a rank owns none of the rows requested in this step; use a larger batch")
         self.last_exchange_rows = (ex_u.n_owned, ex_i.n_owned)
+        self._last_max_bucket = (max(ex_u.send_splits), max(ex_i.send_splits))
         self.eng.begin_step()
         return self._body(ex_u, ex_i, items, B, N, user_x_shard, item_x_shard)
 
@@ -176,10 +177,20 @@ class ShardedEngine:
         return bool(int(st.flag_host[0]))
 
     def _grow(self, B, N) -> None:
-        """After a step that did not fit: 25 % more slots (graphs and buffers of this shape are rebuilt on next use)."""
-        st = self._static.pop((B, N))
-        up = lambda c, n: min((int(c * 1.25) + 127) // 128 * 128, (n + 127) // 128 * 128)
-        self.capacity = (up(st.ex_u.cap, B), up(st.ex_i.cap, B * (1 + N)))
+        """After a step that did not fit (it ran on the dynamic route): size the slots from the largest bucket any rank had
+        in that step (+6 % + 64 rows); graphs and buffers of this shape are rebuilt on next use."""
+        st = self._static[(B, N)]
+        big = torch.tensor(self._last_max_bucket, dtype=torch.int64, device=st.flag.device)
+        if self.world > 1:
+            dist.all_reduce(big, op=dist.ReduceOp.MAX, group=self.group)
+        big_u, big_i = (int(v) for v in big.tolist())
+        cap_u = st.ex_u.cap if big_u <= st.ex_u.cap else S.grown_slot_capacity(big_u, B)
+        cap_i = st.ex_i.cap if big_i <= st.ex_i.cap else S.grown_slot_capacity(big_i, B * (1 + N))
+        # the dynamic step may have re-allocated engine buffers the recorded graphs point into: never replay them again
+        st.graph_plan = st.graph_main = None
+        if (cap_u, cap_i) != (st.ex_u.cap, st.ex_i.cap):       # (an EMPTY bucket also raises the flag: nothing to grow then)
+            self.capacity = (cap_u, cap_i)
+            del self._static[(B, N)]
 
     def _static_step(self, users, pos, neg, user_x_shard, item_x_shard, graph: bool):
         eng = self.eng
@@ -196,8 +207,9 @@ class ShardedEngine:
             self._plan(st)
         if self._overflowed(st):
             self.fallback_steps += 1
+            loss = self._dynamic_step(users, pos, neg, user_x_shard, item_x_shard)
             self._grow(B, N)
-            return self._dynamic_step(users, pos, neg, user_x_shard, item_x_shard)
+            return loss
         self.last_exchange_rows = (st.ex_u.n_slots, st.ex_i.n_slots)
         eng.begin_step()
         if use_graph and st.graph_main is not None and st.x_key == x_key:

@@ -181,13 +181,22 @@ def merge_topk_shards(ids: torch.Tensor, scores: torch.Tensor, k: int, merge_fn,
 # ------------------------------------------------------------------------------------------------------------------
 # Static-shape route: the same exchange with FIXED-capacity slots, so that a whole sharded step has no data-dependent
 # shape, needs no host read of split sizes, and replays as one CUDA graph (collectives included).
+def _round_cap(cap: int, n_req: int) -> int:
+    """Multiple of 128 rows (the GEMM tile height: W*cap rows leave no ragged tile), never more than all requests."""
+    return min((int(cap) + 127) // 128 * 128, (n_req + 127) // 128 * 128)
+
+
 def default_slot_capacity(n_req: int, world: int) -> int:
-    """Slots per (requester, owner) pair.  Uniform ids put n_req/W rows (+- a few sqrt) on each owner; a Zipf head puts
-    one hot row's duplicates on a single owner, more visibly the smaller n_req/W is: headroom 3.5 % per rank + 64 rows,
-    rounded up to a multiple of 128 (the GEMM tile height: W*cap rows leave no ragged tile)."""
+    """Starting slots per (requester, owner) pair: what uniformly distributed ids need - n_req/W rows per owner plus six
+    standard deviations.  Skewed ids (a Zipf head puts all duplicates of a hot row on one owner) overflow this once: the
+    step that does not fit runs on the dynamic route and `grown_slot_capacity` sizes the slots from what it saw."""
     per = (n_req + world - 1) // world
-    cap = int(per * (1.0 + 0.035 * world)) + 64
-    return min((cap + 127) // 128 * 128, (n_req + 127) // 128 * 128)
+    return _round_cap(per + 6.0 * per ** 0.5 + 32, n_req)
+
+
+def grown_slot_capacity(max_count: int, n_req: int) -> int:
+    """Slots after an overflow: the largest bucket any rank had in that step + 6 % + 64 rows."""
+    return _round_cap(max_count * 1.06 + 64, n_req)
 
 
 class SlotExchange:
