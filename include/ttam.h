@@ -273,13 +273,18 @@ int ttam_dense_step(int kind, const ttam_tensor_list* list_host, const float* sc
  *                   receive buffer of an all-to-all, or owner w's own buffer through an NVLink peer mapping.
  *                   Writes, in request order, t_out[R,D], q_out[R,D], o_out[R,D] = t + q (each may be NULL).
  * ttam_slot_pack  : for every slot s (bucket w, position j): a_dst[w][j*ld_dst ..] = a[r], b_dst[w][..] = (r < n0 ?
- *                   b0[r] : b1[r]) with r = req_of[s]; zeros for padding slots.  b_dst may be NULL. */
+ *                   b0[r] : b1[r]) with r = req_of[s]; zeros for padding slots.  b_dst may be NULL.
+ * ttam_slot_ids   : the id exchange without a collective: src[w] (HOST array of device pointers) = address of the `cap`
+ *                   ids requester w bucketed for THIS owner (requester w's send_idx + my_rank*cap, through its peer
+ *                   mapping); writes recv_idx[world*cap] and local_rows = recv_idx / world. */
 int64_t ttam_slot_plan_workspace_bytes(int64_t R, int64_t world);
 int ttam_slot_plan(const int64_t* idx, int64_t R, int64_t world, int64_t cap, int64_t* send_idx, int64_t* slot_of,
                    int32_t* req_of, int32_t* flag, void* workspace, int64_t workspace_bytes, void* stream);
 int ttam_slot_unpack(const float* const* t_src, const float* const* q_src, int64_t ld_src, int64_t world, int64_t cap,
                      const int64_t* slot_of, int64_t R, int64_t D, float* t_out, float* q_out, float* o_out,
                      void* stream);
+int ttam_slot_ids(const int64_t* const* src, int64_t world, int64_t cap, int64_t* recv_idx, int64_t* local_rows,
+                  void* stream);
 int ttam_slot_pack(const float* a, const float* b0, int64_t n0, const float* b1, const int32_t* req_of, int64_t world,
                    int64_t cap, int64_t D, float* const* a_dst, float* const* b_dst, int64_t ld_dst, void* stream);
 

@@ -478,3 +478,17 @@ def test_slot_plan_pack_unpack_bit_exact(W, R, cap):
     want_a = torch.zeros(n + 1, D).index_copy_(0, ref.slot_of, a)[:n]
     want_b = torch.zeros(n + 1, D).index_copy_(0, ref.slot_of, torch.cat([b0[:n0], a[n0:]]))[:n]
     assert torch.equal(ga.cpu(), want_a) and torch.equal(gb.cpu(), want_b)
+
+
+def test_slot_ids_equals_all_to_all_of_send_idx():
+    """ttam_slot_ids with W 'requesters' emulated by W local buffers: what an equal-split all-to-all would deliver to owner
+    `me` (requester w's bucket `me`), and local_rows = id // W."""
+    from two_tower_augmented_with_adaptive_mimic_mechanism_b200 import functional as F
+    W, cap, me = 4, 96, 2
+    g = torch.Generator().manual_seed(5)
+    send = [torch.randint(0, 1 << 40, (W * cap,), generator=g) for _ in range(W)]        # send_idx of every requester
+    dev = [s.cuda() for s in send]
+    recv, rows = (torch.empty(W * cap, dtype=torch.int64, device="cuda") for _ in range(2))
+    F.slot_ids([d.data_ptr() + me * cap * 8 for d in dev], cap, recv, rows)
+    want = torch.cat([s.view(W, cap)[me] for s in send])
+    assert torch.equal(recv.cpu(), want) and torch.equal(rows.cpu(), want // W)

@@ -143,6 +143,7 @@ SIGNATURES = {
     "ttam_dense_step": (C.c_int, [_i32, C.POINTER(TensorList), _p, _d, _d, _d, _d, _d, _d, _i64, _p, _p]),
     "ttam_slot_plan_workspace_bytes": (C.c_int64, [_i64, _i64]),
     "ttam_slot_plan": (C.c_int, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _p, _i64, _p]),
+    "ttam_slot_ids": (C.c_int, [_p, _i64, _i64, _p, _p, _p]),
     "ttam_slot_unpack": (C.c_int, [_p, _p, _i64, _i64, _i64, _p, _i64, _i64, _p, _p, _p, _p]),
     "ttam_slot_pack": (C.c_int, [_p, _p, _i64, _p, _p, _i64, _i64, _i64, _p, _p, _i64, _p]),
     "ttam_topk_f32_workspace_bytes": (C.c_int64, [_i64, _i64, _i64, _i64]),

@@ -206,6 +206,21 @@ __global__ void __launch_bounds__(256) slot_pack_kernel(const float* __restrict_
   }
 }
 
+// ---- id exchange over peer mappings: what an all-to-all of send_idx would deliver, plus the local row (id / W) ----
+struct slot_id_srcs {
+  const int64_t* p[SLOT_MAX_W];
+};
+__global__ void __launch_bounds__(256) slot_ids_kernel(slot_id_srcs src, int W, int64_t cap, int64_t* __restrict__ recv_idx,
+                                                       int64_t* __restrict__ local_rows) {
+  const int64_t n_slots = (int64_t)W * cap;
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(s / cap);
+    const int64_t id = src.p[w][s - (int64_t)w * cap];
+    recv_idx[s] = id;
+    local_rows[s] = id / W;
+  }
+}
+
 static inline int copy_grid(int64_t chunks) {
   int64_t g = ceil_div(chunks, 256 * 4);
   const int64_t cap = (int64_t)num_sms() * 8;
@@ -286,6 +301,21 @@ extern "C" int ttam_slot_pack(const float* a, const float* b0, int64_t n0, const
   if (b_dst && !b0) { b0 = b1; }
   slot_pack_kernel<<<copy_grid(world * cap * (D / 4)), 256, 0, (cudaStream_t)stream>>>(a, b0, n0, b1, req_of, (int)world,
                                                                                         cap, D, d, ld_dst);
+  TTAM_LAUNCH_CHECK();
+  return TTAM_OK;
+}
+
+extern "C" int ttam_slot_ids(const int64_t* const* src, int64_t world, int64_t cap, int64_t* recv_idx, int64_t* local_rows,
+                             void* stream) {
+  TTAM_CHECK_ARG(world >= 1 && world <= SLOT_MAX_W && cap >= 1 && src && recv_idx && local_rows, "slot_ids: bad arguments");
+  slot_id_srcs p;
+  for (int w = 0; w < SLOT_MAX_W; ++w) {
+    p.p[w] = w < world ? src[w] : nullptr;
+    TTAM_CHECK_ARG(w >= world || p.p[w], "slot_ids: source %d is null", w);
+  }
+  const int64_t n = world * cap;
+  slot_ids_kernel<<<(int)std::min<int64_t>(ceil_div(n, 256), 1184), 256, 0, (cudaStream_t)stream>>>(p, (int)world, cap, recv_idx,
+                                                                                                    local_rows);
   TTAM_LAUNCH_CHECK();
   return TTAM_OK;
 }

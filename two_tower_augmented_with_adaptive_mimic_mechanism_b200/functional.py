@@ -460,3 +460,8 @@ def slot_pack(a: torch.Tensor, b0, b1, req_of: torch.Tensor, cap: int, a_dst: li
     n0 = 0 if b0 is None else b0.shape[0]
     check(lib().ttam_slot_pack(a.data_ptr(), _ptr(b0), n0, _ptr(b1), req_of.data_ptr(), len(a_dst), cap, D,
                                _ptr_array(a_dst), _ptr_array(b_dst), ld_dst, _stream()), "slot_pack")
+
+
+def slot_ids(src: list, cap: int, recv_idx: torch.Tensor, local_rows: torch.Tensor) -> None:
+    """src: one device address per requester (its ids for this owner).  recv_idx / local_rows int64 [len(src)*cap]."""
+    check(lib().ttam_slot_ids(_ptr_array(src), len(src), cap, recv_idx.data_ptr(), local_rows.data_ptr(), _stream()), "slot_ids")

@@ -245,6 +245,13 @@ class SlotExchange:
         self._peer_ptrs = [int(p) for p in self.peer.buffer_ptrs]
         self._peer_rank = dist.get_rank(group)
         self._peer_D = D
+        # the bucketed ids live in symmetric memory too: owners load them, no id all-to-all (the all-reduce of the
+        # overflow flag that follows every plan() orders those loads after every rank's plan)
+        ids = symm.empty(self.n_slots + 1, dtype=torch.int64, device=self.send_idx.device)
+        ids.zero_()
+        self._peer_ids = symm.rendezvous(ids, group)
+        self._peer_id_ptrs = [int(p) + self._peer_rank * self.cap * 8 for p in self._peer_ids.buffer_ptrs]
+        self.send_idx = ids
 
     def peer_barrier(self) -> None:
         self.peer.barrier(channel=0)
@@ -303,6 +310,10 @@ class SlotExchange:
             dist.all_reduce(self.flag, op=dist.ReduceOp.MAX, group=self.group)
 
     def exchange_ids(self) -> None:
+        if self.peer is not None:
+            from . import functional as F
+            F.slot_ids(self._peer_id_ptrs, self.cap, self.recv_idx, self.local_rows)
+            return
         if self.world > 1:
             dist.all_to_all_single(self.recv_idx, self.send_idx[: self.n_slots], group=self.group)
         else:
