@@ -206,7 +206,7 @@ int ttam_category_alignment(const int64_t* item_idx, int64_t R, const float* emb
  *                           last_step[row] records the last step applied; the zero-gradient steps in
  *                           between are replayed in registers before the real one.  scalars[4*t+0] =
  *                           lr/(1-beta1^t), [4*t+1] = sqrt(1-beta2^t), [4*t+2] = lr*sqrt(1-beta2^t)/(1-beta1^t)
- *                           (SparseAdam step size), [4*t+3] unused; t = 0..step, computed in double, stored fp32.
+ *                           (SparseAdam step size), [4*t+3] = fp32(beta2)^(t/2)/sqrt(1-beta2^t) (zero-gradient replay; see csrc/optim.cu replay()); t = 0..step, computed in double, stored fp32.
  *   Every row-wise update takes `step` by value and, optionally, `state_dev`: when non-null the step is
  *   read from the device (state_dev->step) and the scalars from the table, which makes the launch
  *   replayable inside a CUDA graph.

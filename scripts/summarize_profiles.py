@@ -50,5 +50,29 @@ def rep(src, dst, match=""):
                 w.writerow([k, row[hdr.index(k)], units[hdr.index(k)]])
 
 
+def rep_table(src, dst, peak_gbs="6553.6"):
+    """One line per captured launch of a `--set full` capture: duration, DRAM bytes, achieved DRAM GB/s and its fraction
+    of the measured copy peak, occupancy - the HBM-bound row kernels of a train step."""
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines())); hdr, units = rows[0], rows[1]
+    col = lambda r, k: r[hdr.index(k)] if k in hdr else ""
+    num = lambda x: float(x.replace(",", "")) if x else 0.0
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tscale = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}
+    with open(dst, "w") as f:
+        f.write(f"source: {src} (ncu --set full --clock-control none; cold-ish caches, each launch replayed)\n"
+                f"peak = {peak_gbs} GB/s (MEASURED_PEAKS.json copy bandwidth)\n\n"
+                "| kernel | grid | us | DRAM read MB | DRAM write MB | DRAM GB/s | of peak | dram pct (ncu) | warps active % | regs |\n|---|---|---|---|---|---|---|---|---|---|\n")
+        for r in rows[2:]:
+            name = re.sub(r"\(.*", "", col(r, "Kernel Name")).replace("void ", "")[:60]
+            t = num(col(r, "gpu__time_duration.sum")) * tscale.get(units[hdr.index("gpu__time_duration.sum")], 1e-9)
+            rd = num(col(r, "dram__bytes_read.sum")) * scale.get(units[hdr.index("dram__bytes_read.sum")], 1.0)
+            wr = num(col(r, "dram__bytes_write.sum")) * scale.get(units[hdr.index("dram__bytes_write.sum")], 1.0)
+            gbs = (rd + wr) / t / 1e9 if t > 0 else 0.0
+            f.write(f"| `{name}` | {col(r, 'Grid Size')} | {t * 1e6:.1f} | {rd / 1e6:.1f} | {wr / 1e6:.1f} | {gbs:.0f} | {gbs / float(peak_gbs):.2f} | "
+                    f"{col(r, 'dram__throughput.avg.pct_of_peak_sustained_elapsed')} | {col(r, 'sm__warps_active.avg.pct_of_peak_sustained_active')} | "
+                    f"{col(r, 'launch__registers_per_thread')} |\n")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "rep": rep}[sys.argv[1]](*sys.argv[2:])
+    {"launches": launches, "rep": rep, "rep_table": rep_table}[sys.argv[1]](*sys.argv[2:])

@@ -417,6 +417,44 @@ def test_lazy_rows_equal_dense_optimizer(F, kind):
         np.testing.assert_allclose(v.cpu().numpy(), z[f"{kind}/exp_avg_sq"], rtol=1e-5, atol=1e-12)
 
 
+@pytest.mark.parametrize("gap", [1, 7, 120, 1000])
+def test_lazy_replay_drift_against_float64_recurrence(F, gap):
+    """Zero-gradient replay of `gap` AdamW steps (csrc/optim.cu replay(): closed form of v, MUFU reciprocal) against the same
+    recurrence in float64.  Bound: 2e-7 absolute on parameters of magnitude 2e-2 (an fp32 step-by-step replay is itself
+    ~sqrt(gap) ulp = 6e-8 away from float64 at gap 1000) + 3e-6 of what the update terms moved them by, 2e-6 relative
+    (+1e-7 per step) on the moments; rows whose moments are still zero
+    only decay."""
+    rng = np.random.default_rng(gap)
+    N, D, lr, wd, b1, b2, eps = 64, 96, 1e-3, 0.01, 0.9, 0.999, 1e-8
+    t0 = 5                                                       # the rows were last updated at step t0
+    p0 = (rng.standard_normal((N, D)) * 0.02).astype(np.float32)
+    m0 = (rng.standard_normal((N, D)) * 2e-5).astype(np.float32)
+    # moments as Adam leaves them for gradients of a mean over 49k samples: |m| ~ 2e-5, sqrt(v) ~ |m| / 3
+    v0 = ((m0.astype(np.float64) / 3.0) ** 2 * rng.uniform(0.5, 2.0, (N, D)) + 1e-18).astype(np.float32)
+    m0[:8] = 0.0; v0[:8] = 0.0                                   # rows no gradient has reached yet
+    p, m, v = dev(p0.copy()), dev(m0.copy()), dev(v0.copy())
+    last = torch.full((N,), t0, dtype=torch.int32, device="cuda")
+    step = t0 + gap + 1                                          # catch-up brings the rows to step - 1
+    scal = F.adam_scalar_table(step + 1, lr, (b1, b2), "cuda")
+    sidx, _ = F.sort_rows(torch.arange(N, device="cuda"), N)
+    F.lazy_catchup("adamw", p, m, v, last, sidx, scalars=scal, lr=lr, weight_decay=wd, betas=(b1, b2), eps=eps, step=step)
+    P, M, V = p0.astype(np.float64), m0.astype(np.float64), v0.astype(np.float64)
+    f32 = lambda x: float(np.float32(x))                         # the reference's tensor ops take their scalars in fp32
+    for t in range(t0 + 1, step):
+        P *= f32(1.0 - lr * wd)
+        M -= f32(1.0 - b1) * M
+        V *= f32(b2)
+        P -= lr / (1.0 - b1 ** t) * M / (np.sqrt(V) / np.sqrt(1.0 - b2 ** t) + eps)
+    assert int(last.min()) == step - 1
+    moved = np.abs(P - p0 * f32(1.0 - lr * wd) ** gap)            # what the update terms contributed in total
+    assert moved.max() < 0.05
+    err = np.abs(p.cpu().numpy() - P)
+    assert (err <= 2e-7 + 3e-6 * moved).all(), (err.max(), moved.max())
+    np.testing.assert_allclose(m.cpu().numpy(), M, rtol=2e-6 + 1e-7 * gap, atol=1e-30)
+    np.testing.assert_allclose(v.cpu().numpy(), V, rtol=4e-6 + 2e-7 * gap, atol=1e-30)
+    assert np.array_equal(m.cpu().numpy()[:8], np.zeros((8, D), np.float32))
+
+
 def test_dense_step_matches_oracle(F):
     rng = np.random.default_rng(4)
     shapes = [(32, 21), (32,), (16, 32), (16,), (192, 605)]

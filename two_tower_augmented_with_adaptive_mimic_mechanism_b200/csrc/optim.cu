@@ -97,6 +97,7 @@ struct AdamScalars {
   float one_minus_b1, one_minus_b2;
   float decay;      // 1 - lr*wd   (AdamW)
   float step_size;  // SparseAdam: lr*sqrt(bc2)/bc1 for this step
+  int fast_replay;  // 1: zero-gradient replay from the closed form of v (default, see replay()); 0: dense_elem step by step
 };
 
 __device__ __forceinline__ void sparse_adam_elem(float g, float& p, float& m, float& v, const AdamScalars& s) {
@@ -302,9 +303,59 @@ __global__ void __launch_bounds__(32 * kLongWarps) sparse_adam_long_kernel(float
 }
 
 // Replay zero-gradient steps (t_from, t_to] ... i.e. steps t_from+1 .. t_to, on NE elements held in registers.
+//
+// A row that is touched every ~50 (items) / ~120 (users) steps replays that many steps each time, so this loop is most of
+// what the lazily-updated tables cost once training is under way (measured with dense_elem in the loop - IEEE sqrt and two
+// IEEE divisions, 52 instructions per element-step: the train step grew from 1.3 ms at step 10 to 2.3 ms at step 1000).
+// With a zero gradient (AdamW, or Adam without weight decay) the recurrence is
+//     p <- p*(1 - lr*wd);  m <- m - (1-b1)*m;  v <- b2*v;  p <- p - (lr/bc1_t) * m / (sqrt(v)/sqrt(bc2_t) + eps)
+// so v at step t is v0 * b2^(t - t0) and sqrt(v_t)/sqrt(bc2_t) = [sqrt(v0) / b2^(t0/2)] * h_t with the per-step scalar
+// h_t = b2^(t/2) / sqrt(1 - b2^t) (scalar table [4t+3], computed in double from the fp32-rounded b2 the reference multiplies
+// by).  The fast path (default) evaluates exactly that: one FMA for the denominator, MUFU.RCP + one multiply for the
+// division (2 ulp), no square root and no recurrence on v inside the loop - 6 instructions per element-step - and writes
+// v0 * (b2^(t1/2) / b2^(t0/2))^2 back.  p and m follow the reference's own fp32 recurrences.  Versus the step-by-step
+// arithmetic each replayed step differs by a few ulp of its UPDATE term (|update| <= ~lr, i.e. ~1e-10 absolute on
+// parameters of magnitude 1e-2); tests/test_gpu_kernels.py bounds the drift over 1000 replayed steps against float64.
+// m == 0 (a row no gradient has reached yet) makes every update term exactly zero: only the decay is applied.
+// TTAM_EXACT_REPLAY=1 selects the step-by-step loop.
 template <int KIND, int NE>
 __device__ __forceinline__ void replay(float (&pp)[NE], float (&mm)[NE], float (&vv)[NE], int t_from, int t_to,
                                        const float* __restrict__ scalars, const AdamScalars& s) {
+  if (t_from >= t_to) return;
+  const bool zero_grad = KIND == TTAM_OPT_ADAMW || (KIND == TTAM_OPT_ADAM && s.wd == 0.f);
+  // b2^(t/2) = h_t * sqrt(bc2_t); t = 0 -> 1
+  const float g_from = t_from > 0 ? __fmul_rn(scalars[4 * t_from + 3], scalars[4 * t_from + 1]) : 1.f;
+  if (zero_grad && s.fast_replay && g_from > 1e-30f) {
+    const bool decay = KIND == TTAM_OPT_ADAMW && s.wd != 0.f;
+    const float ratio = __fdiv_rn(__fmul_rn(scalars[4 * t_to + 3], scalars[4 * t_to + 1]), g_from);   // b2^((t1-t0)/2)
+    bool m_zero = true;
+#pragma unroll
+    for (int e = 0; e < NE; ++e) m_zero = m_zero && (mm[e] == 0.f);
+    if (m_zero) {
+      if (decay) {
+        for (int t = t_from + 1; t <= t_to; ++t) {
+#pragma unroll
+          for (int e = 0; e < NE; ++e) pp[e] = __fmul_rn(pp[e], s.decay);
+        }
+      }
+    } else {
+      float w0[NE];
+#pragma unroll
+      for (int e = 0; e < NE; ++e) w0[e] = __fdiv_rn(sqrtf(vv[e]), g_from);
+      for (int t = t_from + 1; t <= t_to; ++t) {
+        const float a = scalars[4 * t], h = scalars[4 * t + 3];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+          if (decay) pp[e] = __fmul_rn(pp[e], s.decay);
+          mm[e] = fmaf(s.one_minus_b1, -mm[e], mm[e]);
+          pp[e] = fmaf(-a, __fdividef(mm[e], fmaf(w0[e], h, s.eps)), pp[e]);
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < NE; ++e) vv[e] = __fmul_rn(__fmul_rn(vv[e], ratio), ratio);
+    return;
+  }
   for (int t = t_from + 1; t <= t_to; ++t) {
     const float step_size = KIND == TTAM_OPT_SGD ? 0.f : scalars[4 * t];
     const float bc2s = KIND == TTAM_OPT_SGD ? 1.f : scalars[4 * t + 1];
@@ -555,6 +606,8 @@ static AdamScalars make_scalars(double lr, double wd, double b1, double b2, doub
   s.one_minus_b1 = (float)(1.0 - b1);
   s.one_minus_b2 = (float)(1.0 - b2);
   s.decay = (float)(1.0 - lr * wd);
+  static const int exact = [] { const char* e = getenv("TTAM_EXACT_REPLAY"); return (e && e[0] == '1') ? 1 : 0; }();
+  s.fast_replay = exact ? 0 : 1;
   return s;
 }
 

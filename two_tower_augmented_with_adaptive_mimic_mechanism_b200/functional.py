@@ -379,14 +379,19 @@ def dense_step(kind, params, grads, ms, vs, *, lr, weight_decay=0.0, betas=(0.9,
 
 
 def adam_scalar_table(max_step: int, lr: float, betas=(0.9, 0.999), device="cuda") -> torch.Tensor:
-    """scalars[4t] = lr/(1-b1^t), [4t+1] = sqrt(1-b2^t), [4t+2] = lr*sqrt(1-b2^t)/(1-b1^t) (SparseAdam), [4t+3] = 0;
-    computed in float64 like torch does (Python doubles), stored fp32."""
+    """scalars[4t] = lr/(1-b1^t), [4t+1] = sqrt(1-b2^t), [4t+2] = lr*sqrt(1-b2^t)/(1-b1^t) (SparseAdam),
+    [4t+3] = b2f^(t/2)/sqrt(1-b2^t) with b2f = fp32(b2), the factor the reference's exp_avg_sq.mul_(beta2) multiplies by
+    (zero-gradient replay of the lazily-updated tables, csrc/optim.cu replay()); computed in float64 like torch does
+    (Python doubles), stored fp32."""
     t = torch.arange(0, max_step + 1, dtype=torch.float64)
     b1, b2 = betas
     bc1 = 1.0 - torch.pow(torch.tensor(b1, dtype=torch.float64), t)
     bc2 = 1.0 - torch.pow(torch.tensor(b2, dtype=torch.float64), t)
     bc1[0] = 1.0
-    tab = torch.stack([lr / bc1, torch.sqrt(bc2), lr * torch.sqrt(bc2) / bc1, torch.zeros_like(bc1)], dim=1).to(torch.float32).contiguous()
+    b2f = float(torch.tensor(b2, dtype=torch.float32))
+    h = torch.pow(torch.tensor(b2f, dtype=torch.float64), t / 2.0) / torch.sqrt(bc2.clamp_min(1e-300))
+    h[0] = 0.0
+    tab = torch.stack([lr / bc1, torch.sqrt(bc2), lr * torch.sqrt(bc2) / bc1, h], dim=1).to(torch.float32).contiguous()
     return tab.view(-1).to(device)
 
 
