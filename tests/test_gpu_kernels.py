@@ -418,12 +418,14 @@ def test_lazy_rows_equal_dense_optimizer(F, kind):
 
 
 @pytest.mark.parametrize("gap", [1, 7, 120, 1000])
-def test_lazy_replay_drift_against_float64_recurrence(F, gap):
-    """Zero-gradient replay of `gap` AdamW steps (csrc/optim.cu replay(): closed form of v, MUFU reciprocal) against the same
-    recurrence in float64.  Bound: 2e-7 absolute on parameters of magnitude 2e-2 (an fp32 step-by-step replay is itself
-    ~sqrt(gap) ulp = 6e-8 away from float64 at gap 1000) + 3e-6 of what the update terms moved them by, 2e-6 relative
-    (+1e-7 per step) on the moments; rows whose moments are still zero
-    only decay."""
+def test_lazy_replay_against_step_by_step_fp32(F, gap):
+    """Zero-gradient replay of `gap` AdamW steps (csrc/optim.cu replay(): closed form of v, MUFU reciprocal) against the
+    reference's own arithmetic: the same steps one by one in fp32 (numpy float32 ops = torch CPU's, torch/optim/adam.py:
+    347-547 with grad = 0).  Bound on the parameters: 5e-8 absolute (a few ulp of |p| ~ 6e-2: fused vs unfused final
+    add) + 3e-6 of what the update terms moved them by in total; moments: 2e-6 (+1e-7 per step) relative - the closed
+    form b2^k * v against k rounded multiplications; rows whose moments are still zero only decay.
+    (fp32 step by step is itself up to 6e-7 away from the float64 recurrence at gap 1000: the rounding of p * (1 - lr*wd)
+    is not random from one step to the next.)"""
     rng = np.random.default_rng(gap)
     N, D, lr, wd, b1, b2, eps = 64, 96, 1e-3, 0.01, 0.9, 0.999, 1e-8
     t0 = 5                                                       # the rows were last updated at step t0
@@ -438,20 +440,22 @@ def test_lazy_replay_drift_against_float64_recurrence(F, gap):
     scal = F.adam_scalar_table(step + 1, lr, (b1, b2), "cuda")
     sidx, _ = F.sort_rows(torch.arange(N, device="cuda"), N)
     F.lazy_catchup("adamw", p, m, v, last, sidx, scalars=scal, lr=lr, weight_decay=wd, betas=(b1, b2), eps=eps, step=step)
-    P, M, V = p0.astype(np.float64), m0.astype(np.float64), v0.astype(np.float64)
-    f32 = lambda x: float(np.float32(x))                         # the reference's tensor ops take their scalars in fp32
+    f = np.float32
+    P, M, V = p0.copy(), m0.copy(), v0.copy()
+    decay, c1, c2, e32 = f(1.0 - lr * wd), f(1.0 - b1), f(b2), f(eps)
     for t in range(t0 + 1, step):
-        P *= f32(1.0 - lr * wd)
-        M -= f32(1.0 - b1) * M
-        V *= f32(b2)
-        P -= lr / (1.0 - b1 ** t) * M / (np.sqrt(V) / np.sqrt(1.0 - b2 ** t) + eps)
-    assert int(last.min()) == step - 1
-    moved = np.abs(P - p0 * f32(1.0 - lr * wd) ** gap)            # what the update terms contributed in total
+        P = P * decay
+        M = M + (f(0.0) - M) * c1                                # lerp_(grad = 0, 1 - beta1)
+        V = V * c2
+        denom = np.sqrt(V) / f(np.sqrt(1.0 - b2 ** t)) + e32
+        P = P + f(-(lr / (1.0 - b1 ** t))) * (M / denom)         # addcdiv_(exp_avg, denom, value=-step_size)
+    assert P.dtype == np.float32 and int(last.min()) == step - 1
+    moved = np.abs(P.astype(np.float64) - p0.astype(np.float64) * float(decay) ** gap)   # what the update terms contributed
     assert moved.max() < 0.05
-    err = np.abs(p.cpu().numpy() - P)
-    assert (err <= 2e-7 + 3e-6 * moved).all(), (err.max(), moved.max())
-    np.testing.assert_allclose(m.cpu().numpy(), M, rtol=2e-6 + 1e-7 * gap, atol=1e-30)
-    np.testing.assert_allclose(v.cpu().numpy(), V, rtol=4e-6 + 2e-7 * gap, atol=1e-30)
+    err = np.abs(p.cpu().numpy().astype(np.float64) - P)
+    assert (err <= 5e-8 + 3e-6 * moved).all(), (err.max(), moved.max())
+    np.testing.assert_allclose(m.cpu().numpy(), M, rtol=2e-6 + 1e-7 * gap, atol=1e-36)
+    np.testing.assert_allclose(v.cpu().numpy(), V, rtol=4e-6 + 2e-7 * gap, atol=1e-36)
     assert np.array_equal(m.cpu().numpy()[:8], np.zeros((8, D), np.float32))
 
 

@@ -315,7 +315,8 @@ __global__ void __launch_bounds__(32 * kLongWarps) sparse_adam_long_kernel(float
 // division (2 ulp), no square root and no recurrence on v inside the loop - 6 instructions per element-step - and writes
 // v0 * (b2^(t1/2) / b2^(t0/2))^2 back.  p and m follow the reference's own fp32 recurrences.  Versus the step-by-step
 // arithmetic each replayed step differs by a few ulp of its UPDATE term (|update| <= ~lr, i.e. ~1e-10 absolute on
-// parameters of magnitude 1e-2); tests/test_gpu_kernels.py bounds the drift over 1000 replayed steps against float64.
+// parameters of magnitude 1e-2); tests/test_gpu_kernels.py bounds the drift over 1000 replayed steps against the
+// reference's step-by-step fp32 arithmetic.
 // m == 0 (a row no gradient has reached yet) makes every update term exactly zero: only the decay is applied.
 // TTAM_EXACT_REPLAY=1 selects the step-by-step loop.
 template <int KIND, int NE>

@@ -208,6 +208,88 @@ __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ o_u
   }
 }
 
+// 16-byte form for D <= 128, D % 4 == 0 (every BASELINE config with D in {96, 128}): lane l owns columns [4l, 4l+4).
+// Every row the pair needs - u, p, the N negatives, and the four mimic rows - is fetched with ONE float4 load per lane, all
+// issued before the first use (up to 2 + N + 4 loads in flight per lane), kept in registers for the gradient pass (the
+// scalar kernel re-read them), and every gradient row leaves as one float4 store per lane.
+template <int NMAX>
+__global__ void __launch_bounds__(256) loss_vec_kernel(const float* __restrict__ o_u, const float* __restrict__ o_i,
+                                                       const float* __restrict__ t_u, const float* __restrict__ t_p,
+                                                       const float* __restrict__ q_u, const float* __restrict__ q_p,
+                                                       float cu, float ci, float* __restrict__ partial,
+                                                       float* __restrict__ do_u, float* __restrict__ do_i,
+                                                       float* __restrict__ dq_u, float* __restrict__ dq_p, int B, int N,
+                                                       int D, float inv_M) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const int col = lane * 4;
+  const bool act = col < D;
+  const bool mimic = (q_u != nullptr);
+  const bool bwd = (do_u != nullptr);
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int64_t rb = (int64_t)b * D + col;                                  // row b of a [B, D] block
+  const int64_t rn = ((int64_t)B + (int64_t)b * N) * D + col;               // first negative of b in o_i / do_i
+  float4 uu = z4, pp = z4, nn[NMAX], qu = z4, tp = z4, qp = z4, tu = z4;
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n) nn[n] = z4;
+  if (act) {
+    uu = ld_f4(o_u + rb);
+    pp = ld_f4(o_i + rb);
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n)
+      if (n < N) nn[n] = ld_f4(o_i + rn + (int64_t)n * D);
+    if (mimic) {
+      qu = ld_f4(q_u + rb); tp = ld_f4(t_p + rb); qp = ld_f4(q_p + rb); tu = ld_f4(t_u + rb);
+    }
+  }
+  auto dot4 = [](const float4& a, const float4& c) { return fmaf(a.w, c.w, fmaf(a.z, c.z, fmaf(a.y, c.y, a.x * c.x))); };
+  const float sp = warp_sum(dot4(uu, pp));
+  float bce = softplusf_(-sp);
+  const float dsp = (sigmoidf_(sp) - 1.f) * inv_M;
+  float ds[NMAX];
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n) {
+    ds[n] = 0.f;
+    if (n < N) {
+      const float sc = warp_sum(dot4(uu, nn[n]));
+      bce += softplusf_(sc);
+      ds[n] = sigmoidf_(sc) * inv_M;
+    }
+  }
+  float mu = 0.f, mi = 0.f;
+  float4 gu = make_float4(dsp * pp.x, dsp * pp.y, dsp * pp.z, dsp * pp.w);
+  const float4 gp = make_float4(dsp * uu.x, dsp * uu.y, dsp * uu.z, dsp * uu.w);
+  if (bwd) {
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n)
+      if (n < N) {
+        gu.x = fmaf(ds[n], nn[n].x, gu.x); gu.y = fmaf(ds[n], nn[n].y, gu.y);
+        gu.z = fmaf(ds[n], nn[n].z, gu.z); gu.w = fmaf(ds[n], nn[n].w, gu.w);
+        if (act) st_f4(do_i + rn + (int64_t)n * D, make_float4(ds[n] * uu.x, ds[n] * uu.y, ds[n] * uu.z, ds[n] * uu.w));
+      }
+    if (act) {
+      st_f4(do_u + rb, gu);
+      st_f4(do_i + rb, gp);
+    }
+  }
+  if (mimic) {
+    const float4 du = make_float4(qu.x - tp.x, qu.y - tp.y, qu.z - tp.z, qu.w - tp.w);
+    const float4 di = make_float4(qp.x - tu.x, qp.y - tu.y, qp.z - tu.z, qp.w - tu.w);
+    mu = warp_sum(dot4(du, du));
+    mi = warp_sum(dot4(di, di));
+    if (bwd && act) {
+      st_f4(dq_u + rb, make_float4(fmaf(cu, du.x, gu.x), fmaf(cu, du.y, gu.y), fmaf(cu, du.z, gu.z), fmaf(cu, du.w, gu.w)));
+      st_f4(dq_p + rb, make_float4(fmaf(ci, di.x, gp.x), fmaf(ci, di.y, gp.y), fmaf(ci, di.z, gp.z), fmaf(ci, di.w, gp.w)));
+    }
+  }
+  if (lane == 0) {
+    partial[(int64_t)b * 3 + 0] = bce;
+    partial[(int64_t)b * 3 + 1] = mu;
+    partial[(int64_t)b * 3 + 2] = mi;
+  }
+}
+
 // deterministic final reduction: one block, fixed-order strided partial sums + tree
 __global__ void __launch_bounds__(1024) loss_reduce_kernel(const float* __restrict__ partial, int B, float inv_M,
                                                            float inv_BD, float lambda_u, float lambda_i, int mimic,
@@ -414,8 +496,18 @@ extern "C" int ttam_loss_fwd_bwd(const float* o_u, const float* o_i, const float
   const float ci = lambda_i > 0.f ? (float)(2.0 * (double)lambda_i * (double)batch_fraction / ((double)B * (double)D)) : 0.f;
   const int threads = 256;
   const int blocks = (int)ceil_div(B * 32, threads);
-  loss_kernel<<<blocks, threads, 0, s>>>(o_u, o_i, t_u, t_p, q_u, q_p, cu, ci, (float*)workspace, do_u, do_i, dq_u,
-                                         dq_p, (int)B, (int)N, (int)D, inv_M);
+  auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+  const bool vec = D % 4 == 0 && D <= 128 && N <= 8 && al16(o_u) && al16(o_i) && al16(t_u) && al16(t_p) && al16(q_u) &&
+                   al16(q_p) && al16(do_u) && al16(do_i) && al16(dq_u) && al16(dq_p);
+  if (vec && N <= 5)
+    loss_vec_kernel<5><<<blocks, threads, 0, s>>>(o_u, o_i, t_u, t_p, q_u, q_p, cu, ci, (float*)workspace, do_u, do_i, dq_u,
+                                                  dq_p, (int)B, (int)N, (int)D, inv_M);
+  else if (vec)
+    loss_vec_kernel<8><<<blocks, threads, 0, s>>>(o_u, o_i, t_u, t_p, q_u, q_p, cu, ci, (float*)workspace, do_u, do_i, dq_u,
+                                                  dq_p, (int)B, (int)N, (int)D, inv_M);
+  else
+    loss_kernel<<<blocks, threads, 0, s>>>(o_u, o_i, t_u, t_p, q_u, q_p, cu, ci, (float*)workspace, do_u, do_i, dq_u,
+                                           dq_p, (int)B, (int)N, (int)D, inv_M);
   TTAM_LAUNCH_CHECK();
   loss_reduce_kernel<<<1, 1024, 0, s>>>((const float*)workspace, (int)B, inv_M, inv_BD, lambda_u, lambda_i,
                                         q_u != nullptr, loss_out);
