@@ -104,6 +104,7 @@ class FusedEngine:
         self._xpad: dict = {}
         self._side_stream = torch.cuda.Stream(device=dev)
         self._aug_stream = torch.cuda.Stream(device=dev)
+        self._comm_stream = torch.cuda.Stream(device=dev)
         self._use_aug_stream = os.environ.get("TTAM_AUG_STREAM", "1") != "0"
 
     # --------------------------------------------------------------------------------------------
@@ -271,23 +272,26 @@ class FusedEngine:
             with torch.cuda.stream(aug), F.ws_scope("aug"):
                 self._update_table(T["adaptive_mimic.user_augmented.weight"], sort_u, *pair(dq_user))
                 self._update_table(T["adaptive_mimic.item_augmented.weight"], sort_i, *pair(dq_item))
-        # ---- tower backward + row-wise optimisers of the ID tables (no dense table gradient), user side next to item side
+        # ---- tower backward + row-wise optimisers of the ID tables (no dense table gradient), user side next to item side.
+        # With a dense_grad_hook (data-parallel all-reduce of the weight gradients) the hook runs on its own stream as soon
+        # as BOTH towers' weight gradients exist, next to the row-wise table updates instead of after them.
+        cur = torch.cuda.current_stream(self.device)
+        overlap = dense_grad_hook is not None and side is not None
         with (torch.cuda.stream(side) if side is not None else _null()), F.ws_scope("user"):
             de_u = tower_backward(self.user, cu, do_u, grads_u if side is not None else grads, bufs=self.bufs_u, state=self.state,
                                   precision=self.precision)
+            if overlap:
+                self._comm_stream.wait_stream(side)
             self._update_table(T["user_encoder.embedding.weight"], sort_u, de_u)
         with F.ws_scope("item"):
             de_i = tower_backward(self.item, ci, do_i, grads, bufs=self.bufs_i, state=self.state, precision=self.precision)
-            self._update_table(T["item_encoder.embedding.weight"], sort_i, de_i)
+            if overlap:
+                self._comm_stream.wait_stream(cur)
+            else:
+                self._update_table(T["item_encoder.embedding.weight"], sort_i, de_i)
         if side is not None:
-            self._join(side)
             grads.update(grads_u)
-        if aug is not None:
-            self._join(aug)
-        elif self.mimic:
-            self._update_table(T["adaptive_mimic.user_augmented.weight"], sort_u, *pair(dq_user))
-            self._update_table(T["adaptive_mimic.item_augmented.weight"], sort_i, *pair(dq_item))
-        # ---- dense optimiser on the MLP / gate / projection tensors that received a gradient
+        # ---- dense optimiser inputs: the MLP / gate / projection tensors that received a gradient
         ps, gs, ms, vs = [], [], [], []
         for j, p in enumerate(self.dense):
             g = grads.get(id(p))
@@ -298,8 +302,22 @@ class FusedEngine:
                 ms.append(self.dense_m[j])
             if self.dense_v is not None:
                 vs.append(self.dense_v[j])
+        if overlap:
+            if ps:
+                with torch.cuda.stream(self._comm_stream):
+                    dense_grad_hook(gs)
+            with F.ws_scope("item"):
+                self._update_table(T["item_encoder.embedding.weight"], sort_i, de_i)
+            cur.wait_stream(self._comm_stream)
+        if side is not None:
+            self._join(side)
+        if aug is not None:
+            self._join(aug)
+        elif self.mimic:
+            self._update_table(T["adaptive_mimic.user_augmented.weight"], sort_u, *pair(dq_user))
+            self._update_table(T["adaptive_mimic.item_augmented.weight"], sort_i, *pair(dq_item))
         if ps:
-            if dense_grad_hook is not None:
+            if dense_grad_hook is not None and not overlap:
                 dense_grad_hook(gs)
             F.dense_step(self.kind, ps, gs, ms if self.dense_m is not None else None,
                          vs if self.dense_v is not None else None, lr=self.lr, weight_decay=self.wd,
