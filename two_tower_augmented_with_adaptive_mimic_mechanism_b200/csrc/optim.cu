@@ -694,8 +694,8 @@ extern "C" int ttam_sparse_adam_rows(float* p, float* m, float* v, int64_t D, co
   else sparse_adam_rows_kernel<false><<<blocks, 256, 0, cs>>>(p, m, v, (int)D, sorted_idx, perm, R, gs, s, scalars, state_dev, skip);
   TTAM_LAUNCH_CHECK();
   if (skip) {
-    if (vec) sparse_adam_long_kernel<true><<<num_sms(), 32 * kLongWarps, 0, cs>>>(p, m, v, (int)D, sorted_idx, perm, R, gs, s, scalars, state_dev, long_list);
-    else sparse_adam_long_kernel<false><<<num_sms(), 32 * kLongWarps, 0, cs>>>(p, m, v, (int)D, sorted_idx, perm, R, gs, s, scalars, state_dev, long_list);
+    if (vec) sparse_adam_long_kernel<true><<<2 * num_sms(), 32 * kLongWarps, 0, cs>>>(p, m, v, (int)D, sorted_idx, perm, R, gs, s, scalars, state_dev, long_list);
+    else sparse_adam_long_kernel<false><<<2 * num_sms(), 32 * kLongWarps, 0, cs>>>(p, m, v, (int)D, sorted_idx, perm, R, gs, s, scalars, state_dev, long_list);
     TTAM_LAUNCH_CHECK();
   }
   return TTAM_OK;
@@ -732,7 +732,7 @@ extern "C" int ttam_lazy_rows(int kind, float* p, float* m, float* v, int32_t* l
 #undef CALL
   TTAM_LAUNCH_CHECK();
   if (skip) {
-#define CALL(K, V) lazy_long_kernel<K, V><<<num_sms(), 32 * kLongWarps, 0, st>>>(p, m, v, last_step, (int)D, sorted_idx, perm, R, gs, scalars, s, (int)step, state_dev, long_list)
+#define CALL(K, V) lazy_long_kernel<K, V><<<2 * num_sms(), 32 * kLongWarps, 0, st>>>(p, m, v, last_step, (int)D, sorted_idx, perm, R, gs, scalars, s, (int)step, state_dev, long_list)
     if (vec) TTAM_DISPATCH_KIND(kind, true, CALL);
     else TTAM_DISPATCH_KIND(kind, false, CALL);
 #undef CALL
