@@ -236,7 +236,7 @@ __device__ __forceinline__ void sparse_adam_update(float* __restrict__ P, float*
 }
 
 template <bool VEC>
-__global__ void __launch_bounds__(256) sparse_adam_rows_kernel(float* __restrict__ P, float* __restrict__ Mo,
+__global__ void __launch_bounds__(256, 6) sparse_adam_rows_kernel(float* __restrict__ P, float* __restrict__ Mo,
                                                                float* __restrict__ Vo, int D,
                                                                const int64_t* __restrict__ sorted,
                                                                const int32_t* __restrict__ perm, int64_t R, GradSrc gs,
@@ -405,7 +405,7 @@ __device__ __forceinline__ void lazy_update(float* __restrict__ P, float* __rest
 }
 
 template <int KIND, bool VEC>
-__global__ void __launch_bounds__(256) lazy_rows_kernel(float* __restrict__ P, float* __restrict__ Mo,
+__global__ void __launch_bounds__(256, 6) lazy_rows_kernel(float* __restrict__ P, float* __restrict__ Mo,
                                                         float* __restrict__ Vo, int32_t* __restrict__ last_step, int D,
                                                         const int64_t* __restrict__ sorted,
                                                         const int32_t* __restrict__ perm, int64_t R, GradSrc gs,
@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(32 * kLongWarps) lazy_long_kernel(float* __res
 // Bring the unique rows of `sorted` up to step-1 (zero-gradient replay) so that the forward pass of step `step`
 // reads current values; the row-wise update at the end of the step then finds nothing left to replay.
 template <int KIND, bool VEC>
-__global__ void __launch_bounds__(256) lazy_catchup_kernel(float* __restrict__ P, float* __restrict__ Mo,
+__global__ void __launch_bounds__(256, 6) lazy_catchup_kernel(float* __restrict__ P, float* __restrict__ Mo,
                                                            float* __restrict__ Vo, int32_t* __restrict__ last_step, int D,
                                                            const int64_t* __restrict__ sorted, int64_t R,
                                                            const float* __restrict__ scalars, AdamScalars s, int step,

@@ -4,6 +4,7 @@
 //   ttam_gate_fwd/bwd    : FeatureFusionGate tail + _apply_aug      (encoders.py:160-168, adaptive_mimic.py:88-95)
 //   ttam_loss_fwd_bwd    : dot products + BCEWithLogits + 2x MSE    (training.py:770-803, adaptive_mimic.py:66-67)
 #include "common.cuh"
+#include <initializer_list>
 
 namespace ttam {
 
@@ -125,6 +126,127 @@ __global__ void __launch_bounds__(256) augment_fwd_kernel(const float* __restric
     if (q_out) q_out[i] = q;
     o[i] = t[i] + q;
   }
+}
+
+// 16-byte forms of the three kernels above (D % 4 == 0, 16-byte aligned pointers): one float4 chunk per thread-iteration,
+// two chunks in flight per thread, no per-element 64-bit division (one per chunk).
+__device__ __forceinline__ float4 sigmoid4(const float4& x) {
+  return make_float4(sigmoidf_(x.x), sigmoidf_(x.y), sigmoidf_(x.z), sigmoidf_(x.w));
+}
+
+__global__ void __launch_bounds__(256) gate_fwd_vec_kernel(const float* __restrict__ z, const float* __restrict__ pre2,
+                                                           const float* __restrict__ aug, int64_t aug_rows,
+                                                           const int64_t* __restrict__ idx, float* __restrict__ g,
+                                                           float* __restrict__ t, float* __restrict__ o,
+                                                           float* __restrict__ q_out, int64_t R, int D) {
+  const int cpr = D >> 2;
+  const int64_t total = R * cpr, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 2 * stride) {
+    float4 e[2], f[2], p[2], q[2];
+    bool ok[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t i = i0 + u * stride;
+      ok[u] = i < total;
+      q[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok[u]) {
+        const int64_t r = i / cpr;
+        const int c = (int)(i - r * cpr) * 4;
+        e[u] = ld_f4(z + r * 2 * D + c);
+        f[u] = ld_f4(z + r * 2 * D + D + c);
+        p[u] = ld_f4(pre2 + i * 4);
+        if (aug) {
+          const int64_t src = idx[r];
+          if (src >= 0 && src < aug_rows) q[u] = ld_f4(aug + src * D + c);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (!ok[u]) continue;
+      const int64_t i = i0 + u * stride;
+      const float4 gg = sigmoid4(p[u]);
+      const float4 tt = make_float4(gg.x * e[u].x + (1.f - gg.x) * f[u].x, gg.y * e[u].y + (1.f - gg.y) * f[u].y,
+                                    gg.z * e[u].z + (1.f - gg.z) * f[u].z, gg.w * e[u].w + (1.f - gg.w) * f[u].w);
+      st_f4(g + i * 4, gg);
+      if (t) st_f4(t + i * 4, tt);
+      if (aug && q_out) st_f4(q_out + i * 4, q[u]);
+      if (o) st_f4(o + i * 4, make_float4(tt.x + q[u].x, tt.y + q[u].y, tt.z + q[u].z, tt.w + q[u].w));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) gate_bwd_vec_kernel(const float* __restrict__ dt, const float* __restrict__ z,
+                                                           const float* __restrict__ g, float* __restrict__ dpre2,
+                                                           float* __restrict__ dz, int64_t R, int D) {
+  const int cpr = D >> 2;
+  const int64_t total = R * cpr, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 2 * stride) {
+    float4 e[2], f[2], gg[2], d[2];
+    int64_t zo[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t i = i0 + u * stride;
+      zo[u] = -1;
+      if (i < total) {
+        const int64_t r = i / cpr;
+        zo[u] = r * 2 * D + (int64_t)(i - r * cpr) * 4;
+        e[u] = ld_f4(z + zo[u]);
+        f[u] = ld_f4(z + zo[u] + D);
+        gg[u] = ld_f4(g + i * 4);
+        d[u] = ld_f4(dt + i * 4);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (zo[u] < 0) continue;
+      const int64_t i = i0 + u * stride;
+      st_f4(dpre2 + i * 4, make_float4(d[u].x * (e[u].x - f[u].x) * gg[u].x * (1.f - gg[u].x),
+                                       d[u].y * (e[u].y - f[u].y) * gg[u].y * (1.f - gg[u].y),
+                                       d[u].z * (e[u].z - f[u].z) * gg[u].z * (1.f - gg[u].z),
+                                       d[u].w * (e[u].w - f[u].w) * gg[u].w * (1.f - gg[u].w)));
+      st_f4(dz + zo[u], make_float4(d[u].x * gg[u].x, d[u].y * gg[u].y, d[u].z * gg[u].z, d[u].w * gg[u].w));
+      st_f4(dz + zo[u] + D, make_float4(d[u].x * (1.f - gg[u].x), d[u].y * (1.f - gg[u].y), d[u].z * (1.f - gg[u].z),
+                                        d[u].w * (1.f - gg[u].w)));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) augment_fwd_vec_kernel(const float* __restrict__ t, const float* __restrict__ aug,
+                                                              int64_t aug_rows, const int64_t* __restrict__ idx,
+                                                              float* __restrict__ o, float* __restrict__ q_out, int64_t R,
+                                                              int D) {
+  const int cpr = D >> 2;
+  const int64_t total = R * cpr, stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
+    float4 tt[4], q[4];
+    bool ok[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t i = i0 + u * stride;
+      ok[u] = i < total;
+      q[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok[u]) {
+        const int64_t r = i / cpr;
+        const int64_t src = idx[r];
+        if (src >= 0 && src < aug_rows) q[u] = ld_f4(aug + src * D + (int64_t)(i - r * cpr) * 4);
+        tt[u] = ld_f4(t + i * 4);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (!ok[u]) continue;
+      const int64_t i = i0 + u * stride;
+      if (q_out) st_f4(q_out + i * 4, q[u]);
+      st_f4(o + i * 4, make_float4(tt[u].x + q[u].x, tt[u].y + q[u].y, tt[u].z + q[u].z, tt[u].w + q[u].w));
+    }
+  }
+}
+
+static inline bool al16_all(std::initializer_list<const void*> ps) {
+  for (const void* p : ps)
+    if ((uintptr_t)p & 15) return false;
+  return true;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -443,8 +565,12 @@ extern "C" int ttam_gate_fwd(const float* z, const float* pre2, const float* aug
   TTAM_CHECK_ARG(z && pre2 && g, "gate_fwd: null pointer");
   TTAM_CHECK_ARG(!aug_table || idx, "gate_fwd: augmentation needs indices");
   if (R == 0) return TTAM_OK;
-  gate_fwd_kernel<<<grid_for(R * D, 256, 2), 256, 0, (cudaStream_t)stream>>>(z, pre2, aug_table, aug_rows, idx, g, t,
-                                                                             o, q_out, R, D);
+  if (D % 4 == 0 && D < (1 << 20) && al16_all({z, pre2, aug_table, g, t, o, q_out}))
+    gate_fwd_vec_kernel<<<grid_for(R * (D / 4), 256, 2), 256, 0, (cudaStream_t)stream>>>(z, pre2, aug_table, aug_rows, idx, g,
+                                                                                        t, o, q_out, R, (int)D);
+  else
+    gate_fwd_kernel<<<grid_for(R * D, 256, 2), 256, 0, (cudaStream_t)stream>>>(z, pre2, aug_table, aug_rows, idx, g, t,
+                                                                               o, q_out, R, D);
   TTAM_LAUNCH_CHECK();
   return TTAM_OK;
 }
@@ -453,7 +579,10 @@ extern "C" int ttam_gate_bwd(const float* dt, const float* z, const float* g, fl
                              int64_t D, void* stream) {
   TTAM_CHECK_ARG(dt && z && g && dpre2 && dz, "gate_bwd: null pointer");
   if (R == 0) return TTAM_OK;
-  gate_bwd_kernel<<<grid_for(R * D, 256, 2), 256, 0, (cudaStream_t)stream>>>(dt, z, g, dpre2, dz, R, D);
+  if (D % 4 == 0 && D < (1 << 20) && al16_all({dt, z, g, dpre2, dz}))
+    gate_bwd_vec_kernel<<<grid_for(R * (D / 4), 256, 2), 256, 0, (cudaStream_t)stream>>>(dt, z, g, dpre2, dz, R, (int)D);
+  else
+    gate_bwd_kernel<<<grid_for(R * D, 256, 2), 256, 0, (cudaStream_t)stream>>>(dt, z, g, dpre2, dz, R, D);
   TTAM_LAUNCH_CHECK();
   return TTAM_OK;
 }
@@ -462,8 +591,12 @@ extern "C" int ttam_augment_fwd(const float* t, const float* aug_table, int64_t 
                                 float* o, float* q_out, int64_t R, int64_t D, void* stream) {
   TTAM_CHECK_ARG(t && aug_table && idx && o, "augment_fwd: null pointer");
   if (R == 0) return TTAM_OK;
-  augment_fwd_kernel<<<grid_for(R * D, 256, 2), 256, 0, (cudaStream_t)stream>>>(t, aug_table, aug_rows, idx, o, q_out,
-                                                                                R, D);
+  if (D % 4 == 0 && D < (1 << 20) && al16_all({t, aug_table, o, q_out}))
+    augment_fwd_vec_kernel<<<grid_for(R * (D / 4), 256, 4), 256, 0, (cudaStream_t)stream>>>(t, aug_table, aug_rows, idx, o,
+                                                                                           q_out, R, (int)D);
+  else
+    augment_fwd_kernel<<<grid_for(R * D, 256, 2), 256, 0, (cudaStream_t)stream>>>(t, aug_table, aug_rows, idx, o, q_out,
+                                                                                  R, D);
   TTAM_LAUNCH_CHECK();
   return TTAM_OK;
 }
