@@ -68,6 +68,17 @@ def main():
                 if err.max() > 0:
                     ok = False
                     print(f"[rank {rank}] {case} {route}: {k} off by {float(np.abs(mine - want).max()):.3e}", flush=True)
+            if has_x and "eval/item_embeddings" in d and route == "peer":
+                # corpus export (reference _encode_item_embeddings, training.py:613-643) and the reference-layout checkpoint
+                emb = sh.export_item_embeddings(None, ix, meta["NI"]).cpu().numpy()
+                if not np.allclose(emb, d["eval/item_embeddings"], rtol=2e-5, atol=2e-6):
+                    ok = False
+                    print(f"[rank {rank}] {case}: exported item embeddings differ from the reference's", flush=True)
+                full = sh.full_state_dict(meta["NU"], meta["NI"])
+                for k, v in ref_state.items():
+                    if not np.allclose(full[k].numpy(), v, rtol=5e-5, atol=2e-6):
+                        ok = False
+                        print(f"[rank {rank}] {case}: gathered state_dict[{k}] differs", flush=True)
             flag = torch.tensor([0 if ok else 1], device=dev)
             dist.all_reduce(flag)
             if rank == 0:

@@ -253,3 +253,59 @@ def test_item_sharded_topk_merge_world2(tmp_path):
     got_i = np.concatenate([np.load(tmp_path / f"topk{r}.npz")["ids"] for r in range(2)])
     got_s = np.concatenate([np.load(tmp_path / f"topk{r}.npz")["sc"] for r in range(2)])
     assert np.array_equal(got_i, ref_i) and np.array_equal(got_s, ref_s)
+
+
+# ---------------------------------------------------------------------------------------------
+class _TinyModel(torch.nn.Module):
+    """state_dict keys of the reference model (the row-sharded four + one replicated tensor)."""
+
+    def __init__(self, nu, ni, d):
+        super().__init__()
+        mk = lambda n: torch.nn.Embedding(n, d)
+        self.user_encoder = torch.nn.Module(); self.user_encoder.embedding = mk(nu)
+        self.item_encoder = torch.nn.Module(); self.item_encoder.embedding = mk(ni)
+        self.item_encoder.dense = torch.nn.Linear(d, d)
+        self.adaptive_mimic = torch.nn.Module()
+        self.adaptive_mimic.user_augmented = mk(nu); self.adaptive_mimic.item_augmented = mk(ni)
+
+
+class _TinyEngine:
+    def __init__(self, model):
+        self.model, self.flushed = model, 0
+
+    def flush(self):
+        self.flushed += 1
+
+    def optimizer_state(self):
+        return {n: {"step": 3, "exp_avg": p.detach() * 2, "exp_avg_sq": None} for n, p in self.model.named_parameters()}
+
+
+def _checkpoint_worker(rank, world, out_dir):
+    from two_tower_augmented_with_adaptive_mimic_mechanism_b200 import sharding as S
+    from two_tower_augmented_with_adaptive_mimic_mechanism_b200.sharded import ShardedEngine
+    NU, NI, D = 11, 14, 3                                                          # ragged: ranks own 6/5 and 7/7 rows
+    torch.manual_seed(0)
+    full = _TinyModel(NU, NI, D)                                                   # the same "unsharded model" on every rank
+    ref = {k: v.clone() for k, v in full.state_dict().items()}
+    sh = ShardedEngine(_TinyEngine(_TinyModel(S.shard_size(NU, rank, world), S.shard_size(NI, rank, world), D)))
+    sh.load_full_state_dict(ref)                                                   # reference checkpoint -> this rank's rows
+    mine = sh.eng.model.state_dict()
+    assert torch.equal(mine["user_encoder.embedding.weight"], ref["user_encoder.embedding.weight"][rank::world])
+    assert torch.equal(mine["item_encoder.dense.weight"], ref["item_encoder.dense.weight"])
+    got = sh.full_state_dict(NU, NI)                                               # ... and back
+    assert sh.eng.flushed == 1 and set(got) == set(ref)
+    for k in ref:
+        assert torch.equal(got[k], ref[k]), k
+    path = Path(out_dir) / "ckpt.pt"
+    sh.save_checkpoint(path, NU, NI, epoch=4, metric_name="recall@10", metric_value=0.5)
+    ck = torch.load(path, weights_only=False)
+    assert set(ck) == {"epoch", "model_state_dict", "optimizer_state_dicts", "metric_name", "metric_value", "timestamp"}
+    assert ck["epoch"] == 4 and all(torch.equal(ck["model_state_dict"][k], ref[k]) for k in ref)
+    opt = ck["optimizer_state_dicts"][0]
+    assert torch.equal(opt["adaptive_mimic.item_augmented.weight"]["exp_avg"], 2 * ref["adaptive_mimic.item_augmented.weight"])
+    with pytest.raises(ValueError):
+        S.gather_rows_from_shards(torch.zeros(1, D), NU, None)                     # wrong shard length for this rank
+
+
+def test_sharded_checkpoint_roundtrip_world2(tmp_path):
+    _spawn(_checkpoint_worker, 2, str(tmp_path))

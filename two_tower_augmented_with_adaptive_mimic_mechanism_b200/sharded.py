@@ -243,6 +243,75 @@ class ShardedEngine:
             return self._static_step(users, pos, neg, user_x_shard, item_x_shard, graph)
         return self._dynamic_step(users, pos, neg, user_x_shard, item_x_shard)
 
+    # ---- checkpoints in the reference's layout (reference training.py:141-182) ---------------------------
+    ROW_SHARDED = ("encoder.embedding.weight", "_augmented.weight")
+
+    def _is_row_sharded(self, name: str) -> bool:
+        return name.endswith(self.ROW_SHARDED)
+
+    @torch.no_grad()
+    def full_state_dict(self, num_users: int, num_items: int, *, to_cpu: bool = True) -> dict:
+        """`model.state_dict()` of the UNSHARDED model, with the reference's key names, assembled on every rank: lazily-updated
+        rows are flushed first, row-sharded tables ({user,item}_encoder.embedding.weight, adaptive_mimic.*_augmented.weight)
+        are gathered from all ranks, replicated tensors are taken from this rank.  What `_clone_state_dict` /
+        `_save_checkpoint` would have stored for a one-process run.  COLLECTIVE."""
+        flush = getattr(self.eng, "flush", None)
+        if flush is not None:
+            flush()
+        out = {}
+        for name, t in self.eng.model.state_dict().items():
+            if self._is_row_sharded(name):
+                n = num_users if ("user_encoder" in name or "user_augmented" in name) else num_items
+                t = S.gather_rows_from_shards(t.detach(), n, self.group)
+            out[name] = t.detach().cpu().clone() if to_cpu else t.detach().clone()
+        return out
+
+    @torch.no_grad()
+    def load_full_state_dict(self, state: dict) -> None:
+        """Load an unsharded (reference-layout) state_dict: this rank keeps rows r % W == rank of the row-sharded tables."""
+        mine = {}
+        for name, t in state.items():
+            mine[name] = S.shard_rows(t, self.rank, self.world) if self._is_row_sharded(name) else t
+        self.eng.model.load_state_dict(mine)
+
+    @torch.no_grad()
+    def save_checkpoint(self, path, num_users: int, num_items: int, *, epoch: int = 0, metric_name=None, metric_value=None):
+        """Rank 0 writes a `torch.save` dict with the reference's keys (training.py:173-181); every rank takes part in the
+        gather.  `optimizer_state_dicts` holds the engine's per-parameter moments under the same names (row-sharded ones
+        gathered likewise)."""
+        import time
+        model_state = self.full_state_dict(num_users, num_items)
+        opt = {}
+        if hasattr(self.eng, "optimizer_state"):
+            for name, st in self.eng.optimizer_state().items():
+                ent = {"step": st["step"]}
+                for k in ("exp_avg", "exp_avg_sq"):
+                    v = st.get(k)
+                    if v is not None and self._is_row_sharded(name):
+                        n = num_users if ("user_encoder" in name or "user_augmented" in name) else num_items
+                        v = S.gather_rows_from_shards(v, n, self.group)
+                    ent[k] = None if v is None else v.detach().cpu().clone()
+                opt[name] = ent
+        if self.rank == 0:
+            torch.save({"epoch": epoch, "model_state_dict": model_state, "optimizer_state_dicts": [opt],
+                        "metric_name": metric_name, "metric_value": metric_value, "timestamp": time.time()}, path)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+    @torch.no_grad()
+    def export_item_embeddings(self, path, item_x_shard, num_items: int):
+        """`item_embeddings.npy` of the reference (training.py:682-697: the encoded corpus next to the FAISS index): every rank
+        encodes the items it owns (eval mode, augmentation added), the shards are gathered, rank 0 writes the [NI, D] fp32
+        array.  Returns the full matrix on every rank.  COLLECTIVE."""
+        import numpy as np
+        local = self.eng.encode_all("item", item_x_shard)
+        full = S.gather_rows_from_shards(local, num_items, self.group)
+        if self.rank == 0 and path is not None:
+            np.save(path, full.cpu().numpy())
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        return full
+
     def global_loss(self, loss: torch.Tensor) -> torch.Tensor:
         out = loss.clone()
         if self.world > 1:

@@ -51,6 +51,24 @@ def unshard_rows(shards: list) -> torch.Tensor:
     return out
 
 
+def gather_rows_from_shards(shard: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """Inverse of `shard_rows` across the ranks of `group`: every rank passes the rows it owns (local-row order) and gets the
+    full [n_total, ...] tensor back (row r = rank r % W's local row r // W).  Shards differ by at most one row: they are
+    padded to the longest for the all-gather.  Used for checkpoints in the reference's layout and for the corpus export."""
+    W = _world(group)
+    if W == 1:
+        return shard
+    rank = dist.get_rank(group)
+    if shard.shape[0] != shard_size(n_total, rank, W):
+        raise ValueError(f"rank {rank} holds {shard.shape[0]} rows of a {n_total}-row table, expected {shard_size(n_total, rank, W)}")
+    longest = shard_size(n_total, 0, W)
+    padded = shard.new_zeros((longest,) + tuple(shard.shape[1:]))
+    padded[: shard.shape[0]].copy_(shard)
+    parts = [torch.empty_like(padded) for _ in range(W)]
+    dist.all_gather(parts, padded.contiguous(), group=group)
+    return unshard_rows([parts[r][: shard_size(n_total, r, W)] for r in range(W)])
+
+
 def bucket_order(owner: torch.Tensor, world: int) -> torch.Tensor:
     """Stable permutation that groups positions by owner.  CUDA: one radix pass over log2(W) bits (ttam_sort_rows);
     CPU (gloo tests): torch's stable argsort."""
