@@ -380,7 +380,7 @@ def main():
                        + (f"fixed-capacity slots ({sh.last_exchange_rows[0] // world}/{sh.last_exchange_rows[1] // world} user/item rows per "
                           f"rank pair), CUDA-graph replay incl. collectives, {sh.fallback_steps} dynamic-route fallback steps"
                           + (", row payloads by NVLink peer loads/stores fused into the un-bucket/re-bucket kernels (2 device barriers per step)"
-                             if args.route == "peer" else "")
+                             if sh.peer else ", row payloads by equal-split NCCL all-to-alls")
                           if args.route != "dynamic" else "per-step split sizes, eager launches"),
                        "l2_policy": "inputs larger than L2: each step gathers from 11.8 GB of tables/features"},
             "e2e": {"value": world * K * B / (ms_e2e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": B * 8 * (2 + N),

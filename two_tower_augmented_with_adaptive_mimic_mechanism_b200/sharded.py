@@ -71,6 +71,7 @@ class ShardedEngine:
         self._static: dict = {}
         self.fallback_steps = 0
         self.launches_per_step = 0
+        self.peer_error = None
 
     def _hook(self, grads: list) -> None:
         S.all_reduce_flat(grads, self.group)
@@ -151,10 +152,25 @@ class ShardedEngine:
                 # row payloads over NVLink peer memory: the exchanges own symmetric buffers, and the towers write their
                 # t / q rows straight into them (the engine looks its buffers up by name before allocating)
                 eng = self.eng
-                for ex, plan, bufs in ((st.ex_u, eng.user, eng.bufs_u), (st.ex_i, eng.item, eng.bufs_i)):
-                    ex.enable_peer(plan.out_dim)
-                    if plan.D == plan.out_dim:
-                        bufs["t"], bufs["q"] = ex.own_t, ex.own_q
+                ok = 1
+                try:
+                    for ex, plan in ((st.ex_u, eng.user), (st.ex_i, eng.item)):
+                        ex.enable_peer(plan.out_dim)
+                except Exception as e:  # noqa: BLE001 - no symmetric memory on this system: every rank must learn it
+                    ok, self.peer_error = 0, f"{type(e).__name__}: {e}"
+                agree = torch.tensor([ok], dtype=torch.int32, device=device)
+                dist.all_reduce(agree, op=dist.ReduceOp.MIN, group=self.group)
+                if int(agree) == 1:
+                    for ex, plan, bufs in ((st.ex_u, eng.user, eng.bufs_u), (st.ex_i, eng.item, eng.bufs_i)):
+                        if plan.D == plan.out_dim:
+                            bufs["t"], bufs["q"] = ex.own_t, ex.own_q
+                else:
+                    # same slots, equal-split NCCL all-to-alls instead of peer loads / stores (route "static")
+                    import warnings
+                    warnings.warn("symmetric memory is not available on every rank "
+                                  f"({getattr(self, 'peer_error', 'a peer failed')}); using the NCCL slot route")
+                    self.peer = False
+                    st = _Static(B, N, self.world, self.group, device, cap_u, cap_i)
             self._static[(B, N)] = st
         return st
 
