@@ -15,6 +15,10 @@ One "step" = one optimisation step on one batch.  Prints ONE JSON line (see the 
                 on a bounded sample of the same workload
   retrieval     top-100 exact inner-product search, bf16/fp32 corpus of 2M x 96 (BASELINE.json configs[2])
 
+N > 1 (torchrun, one rank per GPU): tables / optimiser state / feature matrices row-sharded, B samples per rank (weak
+scaling), `--route peer` (default: fixed-capacity slots, row payloads by NVLink peer loads/stores, the step replayed as CUDA
+graphs), `static` (same slots over NCCL all-to-alls) or `dynamic` (per-step split sizes, eager; diagnostic).
+
 `--impl reference` times the CPU port alone (rank 0 only) and prints the same line shape.
 """
 from __future__ import annotations
