@@ -157,7 +157,9 @@ typedef struct { float *z, *hd, *a, *pre2, *g, *t, *o, *q; } ttam_tower_bufs;
 typedef struct {
   float *dpre2, *dz, *dpre1, *dhd;
   float *dW1, *db1, *dW2, *db2, *dG1, *dc1, *dG2, *dc2;
-  int32_t accumulate, pad_;
+  int32_t accumulate;
+  int32_t phase; /* 0: whole backward; 1: data-gradient chain only (gate_bwd + the three dgrads: what the table updates
+                    wait for); 2: the four weight/bias gradients only (may run on another stream once phase 1 is done) */
 } ttam_tower_grads;
 int ttam_tower_fwd(const ttam_tower_desc* d, const int64_t* idx, int64_t R, const ttam_tower_bufs* bufs, void* stream);
 int64_t ttam_tower_bwd_workspace_bytes(const ttam_tower_desc* d, int64_t R);

@@ -55,7 +55,7 @@ class TowerBufs(C.Structure):
 
 class TowerGrads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("dpre2", "dz", "dpre1", "dhd", "dW1", "db1", "dW2", "db2", "dG1", "dc1", "dG2", "dc2")] + \
-               [("accumulate", C.c_int32), ("pad_", C.c_int32)]
+               [("accumulate", C.c_int32), ("phase", C.c_int32)]
 
 
 def _sources():

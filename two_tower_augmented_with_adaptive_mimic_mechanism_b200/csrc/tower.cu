@@ -55,17 +55,23 @@ extern "C" int ttam_tower_bwd(const ttam_tower_desc* d, const int64_t* idx, int6
   const int64_t D = d->D, H = d->H, Hg = d->Hg, F = d->F;
   const int acc = g->accumulate;
   const int prec = d->precision;
-  // dpre2 = dt (e-f) g (1-g);  dz = [dt g ; dt (1-g)]
-  TTAM_TRY(ttam_gate_bwd(dt, b->z, b->g, g->dpre2, g->dz, R, D, stream));
-  TTAM_TRY(ttam_linear_wgrad(g->dpre2, D, b->a, Hg, nullptr, g->dG2, g->dc2, R, D, Hg, acc, workspace, workspace_bytes, prec, stream));
-  TTAM_TRY(ttam_linear_dgrad(g->dpre2, D, d->G2, g->dpre1, Hg, b->a, Hg, 1, 1.f, 0, R, D, Hg, prec, stream));
-  TTAM_TRY(ttam_linear_wgrad(g->dpre1, Hg, b->z, 2 * D, nullptr, g->dG1, g->dc1, R, Hg, 2 * D, acc, workspace, workspace_bytes, prec, stream));
-  TTAM_TRY(ttam_linear_dgrad(g->dpre1, Hg, d->G1, g->dz, 2 * D, nullptr, 0, 0, 1.f, 1, R, Hg, 2 * D, prec, stream));
-  // feature MLP: df = dz[:, D:]
-  const float* df = g->dz + D;
-  TTAM_TRY(ttam_linear_wgrad(df, 2 * D, b->hd, H, nullptr, g->dW2, g->db2, R, D, H, acc, workspace, workspace_bytes, prec, stream));
+  TTAM_CHECK_ARG(g->phase >= 0 && g->phase <= 2, "tower_bwd: phase must be 0, 1 or 2");
+  const bool chain = g->phase != 2, weights = g->phase != 1;
+  const float* df = g->dz + D;   // feature MLP: df = dz[:, D:]
   const float scale = d->dropout_p > 0.f ? 1.f / (1.f - d->dropout_p) : 1.f;
-  TTAM_TRY(ttam_linear_dgrad(df, 2 * D, d->W2, g->dhd, H, b->hd, H, 1, scale, 0, R, D, H, prec, stream));
-  return ttam_linear_wgrad(g->dhd, H, d->X, d->ldx, idx, g->dW1, g->db1, R, H, F, acc, workspace, workspace_bytes,
-                           prec | (d->x_rounded ? TTAM_PREC_X_ROUNDED : 0), stream);
+  if (chain) {
+    // dpre2 = dt (e-f) g (1-g);  dz = [dt g ; dt (1-g)]
+    TTAM_TRY(ttam_gate_bwd(dt, b->z, b->g, g->dpre2, g->dz, R, D, stream));
+    TTAM_TRY(ttam_linear_dgrad(g->dpre2, D, d->G2, g->dpre1, Hg, b->a, Hg, 1, 1.f, 0, R, D, Hg, prec, stream));
+    TTAM_TRY(ttam_linear_dgrad(g->dpre1, Hg, d->G1, g->dz, 2 * D, nullptr, 0, 0, 1.f, 1, R, Hg, 2 * D, prec, stream));
+    TTAM_TRY(ttam_linear_dgrad(df, 2 * D, d->W2, g->dhd, H, b->hd, H, 1, scale, 0, R, D, H, prec, stream));
+  }
+  if (weights) {
+    TTAM_TRY(ttam_linear_wgrad(g->dpre2, D, b->a, Hg, nullptr, g->dG2, g->dc2, R, D, Hg, acc, workspace, workspace_bytes, prec, stream));
+    TTAM_TRY(ttam_linear_wgrad(g->dpre1, Hg, b->z, 2 * D, nullptr, g->dG1, g->dc1, R, Hg, 2 * D, acc, workspace, workspace_bytes, prec, stream));
+    TTAM_TRY(ttam_linear_wgrad(df, 2 * D, b->hd, H, nullptr, g->dW2, g->db2, R, D, H, acc, workspace, workspace_bytes, prec, stream));
+    TTAM_TRY(ttam_linear_wgrad(g->dhd, H, d->X, d->ldx, idx, g->dW1, g->db1, R, H, F, acc, workspace, workspace_bytes,
+                               prec | (d->x_rounded ? TTAM_PREC_X_ROUNDED : 0), stream));
+  }
+  return TTAM_OK;
 }

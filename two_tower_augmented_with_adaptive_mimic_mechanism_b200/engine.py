@@ -17,7 +17,7 @@ from typing import Optional
 import torch
 
 from . import functional as F
-from .tower_ops import TowerPlan, plan_from_module, tower_backward, tower_forward
+from .tower_ops import TowerPlan, plan_from_module, splits_backward, tower_backward, tower_forward
 
 
 class _null:
@@ -107,6 +107,8 @@ class FusedEngine:
         self._comm_stream = torch.cuda.Stream(device=dev)
         self._sort_streams = {"u": torch.cuda.Stream(device=dev), "i": torch.cuda.Stream(device=dev)}
         self._overlap_sort = os.environ.get("TTAM_OVERLAP_SORT", "1") != "0"
+        self._wgrad_streams = {"u": torch.cuda.Stream(device=dev), "i": torch.cuda.Stream(device=dev)}
+        self._split_wgrad = os.environ.get("TTAM_WGRAD_STREAM", "1") != "0"
         self._use_aug_stream = os.environ.get("TTAM_AUG_STREAM", "1") != "0"
 
     # --------------------------------------------------------------------------------------------
@@ -298,19 +300,39 @@ class FusedEngine:
         # ---- tower backward + row-wise optimisers of the ID tables (no dense table gradient), user side next to item side.
         # With a dense_grad_hook (data-parallel all-reduce of the weight gradients) the hook runs on its own stream as soon
         # as BOTH towers' weight gradients exist, next to the row-wise table updates instead of after them.
+        # The weight gradients of a tower feed nothing but the dense optimiser at the very end: they run on their own
+        # stream (phase 2 of the composite backward) next to the row-wise update of the tower's ID table, which only
+        # waits for the data-gradient chain (phase 1).
         cur = torch.cuda.current_stream(self.device)
         overlap = dense_grad_hook is not None and side is not None
+        split = self._split_wgrad and side is not None and splits_backward(cu) and splits_backward(ci)
+        wg_u, wg_i = self._wgrad_streams["u"], self._wgrad_streams["i"]
         with (torch.cuda.stream(side) if side is not None else _null()), F.ws_scope("user"):
             de_u = tower_backward(self.user, cu, do_u, grads_u if side is not None else grads, bufs=self.bufs_u, state=self.state,
-                                  precision=self.precision)
-            if overlap:
+                                  precision=self.precision, phase=1 if split else 0)
+            if split:
+                wg_u.wait_stream(side)
+                with torch.cuda.stream(wg_u), F.ws_scope("user_wgrad"):
+                    tower_backward(self.user, cu, do_u, grads_u, bufs=self.bufs_u, state=self.state, precision=self.precision, phase=2)
+                if overlap:
+                    self._comm_stream.wait_stream(wg_u)
+            elif overlap:
                 self._comm_stream.wait_stream(side)
             self._update_table(T["user_encoder.embedding.weight"], sort_u, de_u)
+            if split:
+                side.wait_stream(wg_u)
         with F.ws_scope("item"):
-            de_i = tower_backward(self.item, ci, do_i, grads, bufs=self.bufs_i, state=self.state, precision=self.precision)
-            if overlap:
+            de_i = tower_backward(self.item, ci, do_i, grads, bufs=self.bufs_i, state=self.state, precision=self.precision,
+                                  phase=1 if split else 0)
+            if split:
+                wg_i.wait_stream(cur)
+                with torch.cuda.stream(wg_i), F.ws_scope("item_wgrad"):
+                    tower_backward(self.item, ci, do_i, grads, bufs=self.bufs_i, state=self.state, precision=self.precision, phase=2)
+                if overlap:
+                    self._comm_stream.wait_stream(wg_i)
+            elif overlap:
                 self._comm_stream.wait_stream(cur)
-            else:
+            if not overlap:
                 self._update_table(T["item_encoder.embedding.weight"], sort_i, de_i)
         if side is not None:
             grads.update(grads_u)
@@ -332,6 +354,8 @@ class FusedEngine:
             with F.ws_scope("item"):
                 self._update_table(T["item_encoder.embedding.weight"], sort_i, de_i)
             cur.wait_stream(self._comm_stream)
+        if split:
+            cur.wait_stream(wg_i)
         if side is not None:
             self._join(side)
         if aug is not None:

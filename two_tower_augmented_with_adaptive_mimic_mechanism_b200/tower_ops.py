@@ -186,8 +186,19 @@ def _tower_forward_composite(plan, idx, X, *, train, bufs, seed, rng_base, state
     return c
 
 
-def _tower_backward_composite(plan, c: Cache, dt, grads: dict, bufs):
+def _tower_backward_composite(plan, c: Cache, dt, grads: dict, bufs, phase: int = 0):
+    """phase 0: whole backward.  phase 1: data-gradient chain only (returns dL/de; the weight gradients are registered in
+    `grads` but not yet computed).  phase 2: the weight / bias gradients of a cache whose phase 1 has run (any stream that
+    is ordered after it)."""
     R, D, dev = c.R, plan.D, dt.device
+    L = F.lib()
+    if phase == 2:
+        g = c.bwd_g
+        g.phase = 2
+        ws = F.workspace(L.ttam_tower_bwd_workspace_bytes(c.desc, R), dev, "wgrad")
+        F.check(L.ttam_tower_bwd(c.desc, c.idx.data_ptr(), R, c.cbufs, c.bwd_dt.data_ptr(), g, ws.data_ptr(), ws.numel(), F._stream()),
+                "tower_bwd")
+        return None
     (W1, b1), (W2, b2) = plan.fe_layers
     G1, c1, G2, c2 = plan.gate
     g = F._lib.TowerGrads()
@@ -201,9 +212,10 @@ def _tower_backward_composite(plan, c: Cache, dt, grads: dict, bufs):
             grads[id(b)] = _buf(bufs, f"db{id(b)}", (b.shape[0], 1), dev).view(-1)
         setattr(g, fw, grads[id(W)].data_ptr()); setattr(g, fb, grads[id(b)].data_ptr())
     g.accumulate = 1 if acc else 0
-    L = F.lib()
+    g.phase = phase
     ws = F.workspace(L.ttam_tower_bwd_workspace_bytes(c.desc, R), dev, "wgrad")
     dt = dt if dt.is_contiguous() else dt.contiguous()
+    c.bwd_g, c.bwd_dt = g, dt
     F.check(L.ttam_tower_bwd(c.desc, c.idx.data_ptr(), R, c.cbufs, dt.data_ptr(), g, ws.data_ptr(), ws.numel(), F._stream()),
             "tower_bwd")
     return dz[:, :D]
@@ -310,12 +322,21 @@ def tower_forward(plan: TowerPlan, idx: torch.Tensor, X: Optional[torch.Tensor],
     return c
 
 
+def splits_backward(c: Cache) -> bool:
+    """True when tower_backward(..., phase=1) / (phase=2) is available for this forward cache."""
+    return bool(c.composite)
+
+
 def tower_backward(plan: TowerPlan, c: Cache, dt: torch.Tensor, grads: dict, *, bufs: Optional[dict] = None,
-                   state=None, precision="fp32"):
+                   state=None, precision="fp32", phase: int = 0):
     """dt [R, out_dim] = dL/dt.  Dense weight gradients are written to grads[id(param)] (accumulated when the
-    key exists).  Returns de [R, D] (a view; rows of dL/dE[idx], duplicates NOT yet summed)."""
+    key exists).  Returns de [R, D] (a view; rows of dL/dE[idx], duplicates NOT yet summed).
+    phase (composite towers only, see `splits_backward`): 1 = data-gradient chain now, weight gradients later by a
+    phase-2 call on any stream ordered after this one."""
     if c.composite:
-        return _tower_backward_composite(plan, c, dt, grads, bufs)
+        return _tower_backward_composite(plan, c, dt, grads, bufs, phase)
+    if phase != 0:
+        raise ValueError("only composite (gated MLP, tensor-core) towers split their backward")
     R, D = c.R, plan.D
     dev = dt.device
     X, gidx = c.X, (c.idx if c.gather else None)
