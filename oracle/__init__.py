@@ -23,6 +23,7 @@ from .model import (  # noqa: F401
     tower_forward,
     tower_backward,
     loss_forward_backward,
+    inbatch_loss_forward_backward,
     category_alignment_loss,
     train_step,
     eval_loss,

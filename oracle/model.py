@@ -278,6 +278,47 @@ def loss_forward_backward(o_u, o_p, o_n, *, t_u=None, t_p=None, q_u=None, q_p=No
     return out
 
 
+def inbatch_loss_forward_backward(o_u, o_p, *, t_u=None, t_p=None, q_u=None, q_p=None, lambda_u=0.0, lambda_i=0.0,
+                                  need_grad=True):
+    """EXTENSION (BASELINE.json configs[1] names "in-batch negatives"; the reference has no such loss - its only training loss
+    is the sampled-negative BCE of training.py:770-803 - so this definition is pinned by tests/test_oracle_inbatch.py
+    against torch autograd, not against the reference: parity UNPINNED with respect to the reference).
+
+    In-batch softmax: scores S = o_u o_p^T [B, B]; row b's positive is column b, the other B-1 items of the batch are its
+    negatives; L_ce = mean_b (logsumexp_j S[b, j] - S[b, b]) (= F.cross_entropy(S, arange(B))).  The mimic terms are the
+    reference's (adaptive_mimic.py:66-67) and enter the total exactly as in training.py:800-803.
+    Returns dict(loss, ce, mimic_user, mimic_item, do_u, do_p, dq_u_extra, dq_p_extra)."""
+    B, D = o_u.shape
+    S = (o_u.astype(F32) @ o_p.astype(F32).T).astype(F32)
+    m = S.max(axis=1, keepdims=True)
+    e = np.exp(S - m, dtype=F32)
+    z = e.sum(axis=1, keepdims=True, dtype=F32)
+    lse = (np.log(z) + m)[:, 0].astype(F32)
+    ce = F32((lse - np.diagonal(S)).sum(dtype=F32) / F32(B))
+    out = {"ce": ce, "scores": S}
+    total = ce
+    mu = mi = None
+    if q_u is not None:
+        mu = F32(((q_u - t_p) ** 2).mean(dtype=F32))
+        mi = F32(((q_p - t_u) ** 2).mean(dtype=F32))
+        if lambda_u > 0:
+            total = F32(total + F32(lambda_u) * mu)
+        if lambda_i > 0:
+            total = F32(total + F32(lambda_i) * mi)
+    out.update(loss=total, mimic_user=mu, mimic_item=mi)
+    if not need_grad:
+        return out
+    P = (e / z).astype(F32)
+    P[np.arange(B), np.arange(B)] -= F32(1)
+    P /= F32(B)                                                   # dL/dS
+    out["do_u"] = (P @ o_p).astype(F32)
+    out["do_p"] = (P.T @ o_u).astype(F32)
+    if q_u is not None:
+        out["dq_u_extra"] = (F32(lambda_u if lambda_u > 0 else 0.0) * F32(2.0) * (q_u - t_p) / F32(B * D)).astype(F32)
+        out["dq_p_extra"] = (F32(lambda_i if lambda_i > 0 else 0.0) * F32(2.0) * (q_p - t_u) / F32(B * D)).astype(F32)
+    return out
+
+
 def _cov(m):
     """_compute_covariance (training.py:530-538)."""
     if m.shape[0] <= 1:
