@@ -51,13 +51,14 @@ class ShardedEngine:
     """Drives the three phases of `FusedEngine` (or any object with the same phase methods) across ranks.
 
     static=False: every step sizes its all-to-alls from the step's own counts (one host read per step, eager launches).
-    peer=True (with static): the row payloads of the exchanges do not go through NCCL at all - requesters load the
-                  owners' rows and store their gradient rows over NVLink peer mappings (symmetric memory), fused into
-                  the un-bucket / re-bucket kernels, between two device-side barriers per step.
     static=True:  fixed-capacity slots per (requester, owner) pair (`sharding.SlotExchange`): no data-dependent shape, so
                   with graph=True the whole step - towers, loss, optimisers AND the collectives - is two CUDA-graph
                   replays (plan, main) around the step's single host read (the overflow flag).  A step whose ids do not
-                  fit the slots runs on the dynamic route instead (same results), and the capacity grows."""
+                  fit the slots runs on the dynamic route instead (same results), and the capacity is re-sized from it.
+    peer=True (with static): the ids and row payloads of the exchanges do not go through NCCL at all - requesters load the
+                  owners' rows and store their gradient rows over NVLink peer mappings (symmetric memory), fused into
+                  the un-bucket / re-bucket kernels, between two device-side barriers per step.  Falls back to the NCCL
+                  slot route (with a warning) when symmetric memory cannot be set up on every rank."""
 
     def __init__(self, engine, group=None, *, static: bool = False, capacity=None, peer: bool = False) -> None:
         self.eng = engine
