@@ -190,6 +190,7 @@ def test_topk_bf16_full_corpus_agrees_with_fp32_path(tt):
 
 
 def test_flat_ip_index_bf16(tt):
+    torch.manual_seed(1234)
     emb = torch.randn(5000, 96, device="cuda")
     q = torch.randn(10, 96, device="cuda")
     idx = tt.retrieval.FlatIPIndex(emb, dtype=torch.bfloat16)
