@@ -88,7 +88,7 @@ def make_batches(steps, c, device, gen):
 
 class ClockSampler:
     """SM clock / throttle reasons during the timed region (B200_PROFILING.md recipe).  In-process NVML (nvidia_ml_py)
-    every 10 ms (the timed region of the default run is ~45 ms): spawning nvidia-smi from a thread takes the driver lock often enough to slow the timed launches down
+    every 25 ms (the timed region of the default run is ~45 ms): spawning nvidia-smi from a thread takes the driver lock often enough to slow the timed launches down
     (the first version of this bench measured `value` 10 % below `e2e` because of it); nvidia-smi is the fallback."""
 
     def __init__(self, index):
@@ -127,7 +127,7 @@ class ClockSampler:
                         self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self.stop.wait(0.01 if self.nvml is not None else 0.5)
+            self.stop.wait(0.025 if self.nvml is not None else 0.5)
 
     def __enter__(self):
         self.thread.start()
