@@ -309,3 +309,21 @@ def _checkpoint_worker(rank, world, out_dir):
 
 def test_sharded_checkpoint_roundtrip_world2(tmp_path):
     _spawn(_checkpoint_worker, 2, str(tmp_path))
+
+
+def _ragged_static_worker(rank, world):
+    from sharding_backend import OracleEngine, shard_state
+    from two_tower_augmented_with_adaptive_mimic_mechanism_b200.sharded import ShardedEngine
+    d, meta, init = load_case("train_embedding_only")
+    eng = OracleEngine(shard_state(init, rank, world), lr=meta["lr"], weight_decay=meta["wd"], betas=meta["betas"], lambdas=(0.0, 0.0))
+    sh = ShardedEngine(eng, static=True)
+    u, p, n = (torch.from_numpy(d[f"step0/{k}"]) for k in ("users", "pos", "neg"))
+    B = 8 + 2 * rank                                                               # ranks bring different batch sizes
+    with pytest.raises(ValueError, match="ranks disagree"):
+        sh.train_step(u[:B], p[:B], n[:B], None, None)
+    sh2 = ShardedEngine(eng)                                                       # the dynamic route takes ragged batches
+    sh2.train_step(u[:B], p[:B], n[:B], None, None)
+
+
+def test_static_route_rejects_ragged_batches_world2():
+    _spawn(_ragged_static_worker, 2)

@@ -148,6 +148,16 @@ class ShardedEngine:
         if st is None:
             cap_u, cap_i = self.capacity or (S.default_slot_capacity(B, self.world),
                                              S.default_slot_capacity(B * (1 + N), self.world))
+            if self.world > 1:
+                # equal-split exchanges: every rank must bring the same B and N and use the same capacities (checked once
+                # per shape; the dynamic route has no such requirement)
+                mine = torch.tensor([B, N, cap_u, cap_i], dtype=torch.int64, device=device)
+                lo, hi = mine.clone(), mine.clone()
+                dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.group)
+                dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.group)
+                if not torch.equal(lo, hi):
+                    raise ValueError(f"static route: ranks disagree on (B, N, slot capacities): min {lo.tolist()}, max {hi.tolist()}; "
+                                     "use the same per-rank batch on every rank, or static=False")
             st = _Static(B, N, self.world, self.group, device, cap_u, cap_i)
             if self.peer:
                 # row payloads over NVLink peer memory: the exchanges own symmetric buffers, and the towers write their
