@@ -277,9 +277,9 @@ def main():
     sh = tt.ShardedEngine(eng, static=args.route != "dynamic", peer=args.route == "peer") if world > 1 else None
     users, pos, neg = make_batches(K + W, c, dev, gen)          # global row ids
     if sh is not None:
-        # N > 1: a few extra untimed steps before the W warm-up steps.  The number of rows a rank owns changes from step to
-        # step, so the first steps grow the engine's buffers (cudaMalloc + synchronisation) and open NCCL's send/recv
-        # channels; neither belongs in a timed region.
+        # N > 1: a few extra untimed steps before the W warm-up steps: the 4 calibration steps of the slot capacities (eager),
+        # the step that records the CUDA graphs (or, on the dynamic route, the steps that grow the engine's buffers), and the
+        # opening of the NCCL / NVLink channels; none of it belongs in a timed region.
         pu, pp, pn = make_batches(6, c, dev, gen)
         for s in range(6):
             sh.train_step(pu[s], pp[s], pn[s], user_x, item_x, graph=not args.no_graph)

@@ -41,7 +41,10 @@ def main():
             lu, li, _ = meta["lambdas"]
             eng = tt.FusedEngine(model, optimizer=kw["optimizer"], lr=meta["lr"], weight_decay=meta["wd"], sparse_betas=meta["betas"],
                                  loss_weights={"mimic_user": lu, "mimic_item": li}, max_steps=64)
-            sh = tt.ShardedEngine(eng, static=route != "dynamic", peer=route == "peer")
+            # explicit (default-sized) capacities: no calibration steps, so steps 1.. of the 3-step goldens replay the graphs
+            Bl, Nn = meta["B"] // world, meta["N"]
+            caps = (S.default_slot_capacity(Bl, world), S.default_slot_capacity(Bl * (1 + Nn), world))
+            sh = tt.ShardedEngine(eng, static=route != "dynamic", peer=route == "peer", capacity=caps)
             has_x = "user_x" in d and d["user_x"].size
             ux = S.shard_rows(torch.from_numpy(d["user_x"]), rank, world).to(dev) if has_x else None
             ix = S.shard_rows(torch.from_numpy(d["item_x"]), rank, world).to(dev) if has_x else None

@@ -27,12 +27,12 @@ eng = tt.FusedEngine(model, optimizer="adamw", lr=1e-3, weight_decay=0.01, preci
 route = os.environ.get("TTAM_ROUTE", "peer")
 sh = tt.ShardedEngine(eng, static=route != "dynamic", peer=route == "peer")
 graph = route != "dynamic"
-users, pos, neg = bench.make_batches(12, c, dev, gen)
-for s in range(4):
+users, pos, neg = bench.make_batches(16, c, dev, gen)
+for s in range(8):          # calibration steps (eager) + the step that records the graphs + one replay
     sh.train_step(users[s], pos[s], neg[s], ux, ix, graph=graph)
 dist.barrier(); torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
-    for s in range(4, 10):
+    for s in range(8, 14):
         sh.train_step(users[s], pos[s], neg[s], ux, ix, graph=graph)
     torch.cuda.synchronize()
 if rank == 0:

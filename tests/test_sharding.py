@@ -327,3 +327,37 @@ def _ragged_static_worker(rank, world):
 
 def test_static_route_rejects_ragged_batches_world2():
     _spawn(_ragged_static_worker, 2)
+
+
+def _calibration_worker(rank, world):
+    from two_tower_augmented_with_adaptive_mimic_mechanism_b200 import sharding as S
+    from two_tower_augmented_with_adaptive_mimic_mechanism_b200.sharded import ShardedEngine
+    sh = ShardedEngine(object(), static=True)                                      # automatic capacities
+    B, N = 4096, 5
+    st = sh._static_state(B, N, "cpu")
+    cap0 = (st.ex_u.cap, st.ex_i.cap)
+    assert st.calib_left == ShardedEngine.CALIBRATION_STEPS and cap0[1] == S.default_slot_capacity(B * 6, world)
+    g = torch.Generator().manual_seed(7 + rank)
+    for step in range(ShardedEngine.CALIBRATION_STEPS):
+        st.users.copy_(torch.randint(0, 10**6, (B,), generator=g))
+        items = torch.randint(0, 10**6, (B * 6,), generator=g)
+        if rank == 1:
+            items[: B // 2] = 0                                                    # a hot row on owner 0, seen by ONE rank only
+        st.items.copy_(items)
+        assert (B, N) in sh._static
+        sh._calibrate(st)
+    # every rank re-sizes alike: the hot bucket (about B*6/2 + B/4 ids) does not fit the uniform starting capacity
+    hot = int(torch.bincount(items % world, minlength=world).max()) if rank == 1 else 0
+    assert (B, N) not in sh._static and (B, N) in sh._calibrated
+    assert sh.capacity[0] == cap0[0] and sh.capacity[1] > cap0[1] and sh.capacity[1] % 128 == 0
+    t = torch.tensor([hot]); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    assert sh.capacity[1] >= int(t) + 5 * int((B * 6 / world) ** 0.5)
+    st2 = sh._static_state(B, N, "cpu")                                            # rebuilt with the new capacity, no second calibration
+    assert st2.ex_i.cap == sh.capacity[1] and st2.calib_left == 0
+    # explicit capacities are respected: no calibration
+    sh3 = ShardedEngine(object(), static=True, capacity=(2048 + 128, 12288 + 256))
+    assert sh3._static_state(B, N, "cpu").calib_left == 0
+
+
+def test_slot_capacity_calibration_world2():
+    _spawn(_calibration_worker, 2)

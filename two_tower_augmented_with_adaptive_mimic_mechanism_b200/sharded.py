@@ -45,6 +45,8 @@ class _Static:
         self.graph_plan = self.graph_main = None
         self.loss = None
         self.x_key = None
+        self.calib_left = 0                 # calibration steps still to run on this shape (see ShardedEngine._calibrate)
+        self.max_seen = [0, 0]
 
 
 class ShardedEngine:
@@ -68,6 +70,8 @@ class ShardedEngine:
         self.last_exchange_rows = (0, 0)
         self.static = bool(static)
         self.capacity = capacity              # None or (cap_users, cap_items)
+        self._auto_capacity = capacity is None
+        self._calibrated: set = set()
         self.peer = bool(peer) and self.static and self.world > 1
         self._static: dict = {}
         self.fallback_steps = 0
@@ -182,8 +186,32 @@ class ShardedEngine:
                                   f"({getattr(self, 'peer_error', 'a peer failed')}); using the NCCL slot route")
                     self.peer = False
                     st = _Static(B, N, self.world, self.group, device, cap_u, cap_i)
+            if self._auto_capacity and self.world > 1 and (B, N) not in self._calibrated:
+                st.calib_left = self.CALIBRATION_STEPS
             self._static[(B, N)] = st
         return st
+
+    CALIBRATION_STEPS = 4
+
+    def _calibrate(self, st: _Static) -> None:
+        """First steps of a shape (automatic capacities only): record the largest bucket any rank fills - one bincount per
+        index set, one MAX all-reduce and one host read per calibration step - and, when they are over, re-size the slots to
+        `sharding.calibrated_slot_capacity` if that is more than they hold.  Calibration steps run eagerly; the (possibly
+        re-sized) state records its graphs on the first step after them, i.e. still inside the caller's warm-up."""
+        W, B, N = self.world, st.B, st.N
+        mx = torch.stack([torch.bincount(S.owner_of(st.users, W), minlength=W).max(),
+                          torch.bincount(S.owner_of(st.items, W), minlength=W).max()])
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
+        seen = mx.tolist()
+        st.max_seen = [max(a, int(b)) for a, b in zip(st.max_seen, seen)]
+        st.calib_left -= 1
+        if st.calib_left == 0:
+            self._calibrated.add((B, N))
+            cap_u = max(st.ex_u.cap, S.calibrated_slot_capacity(st.max_seen[0], B, W))
+            cap_i = max(st.ex_i.cap, S.calibrated_slot_capacity(st.max_seen[1], B * (1 + N), W))
+            if (cap_u, cap_i) != (st.ex_u.cap, st.ex_i.cap):
+                self.capacity = (cap_u, cap_i)
+                del self._static[(B, N)]
 
     def _plan(self, st: _Static) -> None:
         st.ex_u.plan(st.users)
@@ -227,7 +255,8 @@ class ShardedEngine:
         st.items[:B].copy_(pos.reshape(-1))
         st.items[B:].copy_(neg.reshape(-1))
         x_key = (None if user_x_shard is None else user_x_shard.data_ptr(), None if item_x_shard is None else item_x_shard.data_ptr())
-        use_graph = graph and users.is_cuda
+        # no graph is recorded before the calibration steps of the shape are over: the slots may still be re-sized
+        use_graph = graph and users.is_cuda and st.calib_left == 0
         if use_graph and st.graph_main is not None and st.x_key == x_key:
             st.graph_plan.replay()
         else:
@@ -235,8 +264,10 @@ class ShardedEngine:
         if self._overflowed(st):
             self.fallback_steps += 1
             loss = self._dynamic_step(users, pos, neg, user_x_shard, item_x_shard)
+            self._calibrated.add((B, N))         # the slots are about to be sized from a real overflow
             self._grow(B, N)
             return loss
+        calibrating = st.calib_left > 0
         self.last_exchange_rows = (st.ex_u.n_slots, st.ex_i.n_slots)
         eng.begin_step()
         if use_graph and st.graph_main is not None and st.x_key == x_key:
@@ -257,6 +288,8 @@ class ShardedEngine:
             with torch.cuda.graph(gm, capture_error_mode="thread_local"):
                 st.loss = self._main(st, user_x_shard, item_x_shard)
             st.graph_plan, st.graph_main, st.x_key = gp, gm, x_key
+        if calibrating:
+            self._calibrate(st)
         return loss
 
     @torch.no_grad()

@@ -212,6 +212,15 @@ def default_slot_capacity(n_req: int, world: int) -> int:
     return _round_cap(per + 6.0 * per ** 0.5 + 32, n_req)
 
 
+def calibrated_slot_capacity(max_seen: int, n_req: int, world: int) -> int:
+    """Slots after the calibration steps of a shape: the largest bucket seen so far on any rank + five standard deviations
+    of a bucket count (sqrt(n_req/W) bounds it) + 32 rows.  Keeps an overflow - an eager step plus a re-capture of the
+    step's graphs - out of steady state when the ids are skewed but stationary (a Zipf head adds a constant to one
+    owner's buckets: at W = 4 the uniform starting capacity sits only ~3.5 sigma above that owner's mean)."""
+    per = (n_req + world - 1) // world
+    return _round_cap(max_seen + 5.0 * per ** 0.5 + 32, n_req)
+
+
 def grown_slot_capacity(max_count: int, n_req: int) -> int:
     """Slots after an overflow: the largest bucket any rank had in that step + 6 % + 64 rows."""
     return _round_cap(max_count * 1.06 + 64, n_req)
