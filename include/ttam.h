@@ -265,7 +265,8 @@ int ttam_dense_step(int kind, const ttam_tensor_list* list_host, const float* sc
 /* ---- fixed-capacity slot route of the row-sharded step (no reference counterpart: the reference is
  * single-process.  Replaces the per-step split sizes of the id / row / gradient all-to-alls by W x cap static slots,
  * so that the sharded step replays as a CUDA graph.)
- * ttam_slot_plan  : owner(id) = id % world.  Bucket idx[R] by owner, original order kept inside a bucket, bucket o
+ * ttam_slot_plan  : owner(id) = id % world (ids are row ids: >= 0).  Bucket idx[R] by owner, original order kept
+ *                   inside a bucket, bucket o
  *                   in slots [o*cap, (o+1)*cap): send_idx[world*cap] (padding slots repeat the bucket's first id: the
  *                   owner's touched-row SET is unchanged), slot_of[R] (slot of every request; world*cap = did not
  *                   fit), req_of[world*cap] (request held by a slot, -1 = padding), *flag = 1 when a bucket holds
