@@ -64,3 +64,27 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and "model" not in line["config"]
+
+
+def test_filter_block_equals_per_user_filter():
+    """The block-wise candidate filter returns, for every user, exactly what the reference's per-user loop
+    (`filter_candidates`, training.py:959-972) returns: blocked ids, -1 padding, per-user search_k truncation, rows that fall
+    short of max_k (ground truth appended), repeated ids."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    for trial in range(30):
+        n, K, NI = int(rng.integers(1, 40)), int(rng.integers(1, 60)), int(rng.integers(5, 400))
+        max_k = int(rng.integers(1, 25))
+        users = rng.permutation(1000)[:n].tolist()
+        ids = np.stack([rng.permutation(max(NI, K))[:K] for _ in range(n)]).astype(np.int64)
+        ids[ids >= NI] = -1                                                     # padding where the corpus is smaller than K
+        if trial % 5 == 0:
+            ids[:, K // 2:] = ids[:, : K - K // 2]                              # repeated ids
+        need = rng.integers(1, K + 1, size=n).tolist()
+        blocked = {u: set(rng.integers(0, NI, size=int(rng.integers(0, NI))).tolist()) for u in users if rng.random() < 0.7}
+        gt = {u: set(rng.integers(0, NI, size=int(rng.integers(1, 4))).tolist()) for u in users}
+        got = retrieval.filter_block(ids, need, users, gt, blocked, max_k)
+        for r, u in enumerate(users):
+            want = retrieval.filter_candidates(ids[r, : need[r]].tolist(), set(blocked.get(u, ())), gt[u], max_k)
+            assert got[u] == want, (trial, r)
+    assert retrieval.filter_block(np.zeros((0, 4), np.int64), [], [], {}, {}, 3) == {}

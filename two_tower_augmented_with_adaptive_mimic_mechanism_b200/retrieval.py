@@ -6,8 +6,9 @@ launch sequence.  Result order is canonical: descending score, ascending item id
 """
 from __future__ import annotations
 
-from typing import Iterable, Mapping, Optional
+from typing import Iterable, Mapping, Optional, Sequence
 
+import numpy as np
 import torch
 
 from . import functional as F
@@ -72,11 +73,53 @@ def filter_candidates(candidate_ids: list[int], blocked: set[int], ground_truth:
     return kept[:max_k]
 
 
+def filter_block(ids: np.ndarray, need: Sequence[int], users: Sequence[int], ground_truth: Mapping[int, set],
+                 train_positive_map: Mapping[int, set], max_k: int) -> dict:
+    """`filter_candidates` for a whole block of users at once (the reference filters one user per Python
+    iteration, training.py:959-972).  ids [n, K] int64: row r holds user users[r]'s candidates, best first (-1 = none);
+    only its first need[r] columns count (the reference asks FAISS for search_k = need[r] results).
+    Rows that keep at least max_k candidates - nearly all of them - are handled by array operations: blocked-item
+    membership is one searchsorted over (row, item) keys, the survivors' first max_k columns one stable argsort.  Rows
+    that keep fewer (their ground truth gets appended) or repeat an id go through `filter_candidates` itself, so the
+    result is the reference's for every row."""
+    ids = np.asarray(ids, dtype=np.int64)
+    n, K = ids.shape
+    need = np.asarray(need, dtype=np.int64).reshape(n, 1)
+    valid = (ids >= 0) & (np.arange(K, dtype=np.int64)[None, :] < need)
+    rows, items = [], []
+    for r, u in enumerate(users):
+        b = train_positive_map.get(u)
+        if b:
+            rows.append(np.full(len(b), r, dtype=np.int64))
+            items.append(np.fromiter(b, dtype=np.int64, count=len(b)))
+    if rows and ids.size:
+        rows, items = np.concatenate(rows), np.concatenate(items)
+        M = int(max(ids.max(), items.max())) + 1
+        bk = np.sort(rows * M + items)
+        ck = np.arange(n, dtype=np.int64)[:, None] * M + np.where(valid, ids, 0)
+        pos = np.minimum(np.searchsorted(bk, ck), bk.size - 1)
+        valid &= bk[pos] != ck
+    out = {}
+    take = min(max_k, K)
+    order = np.argsort(~valid, axis=1, kind="stable")[:, :take]          # columns of the survivors first, in their order
+    sel = np.take_along_axis(ids, order, axis=1)
+    fast = valid.sum(axis=1) >= max_k
+    if take > 1:
+        srt = np.sort(sel, axis=1)
+        fast &= ~(srt[:, 1:] == srt[:, :-1]).any(axis=1)                 # a repeated id: the reference drops it, go slow
+    for r, u in enumerate(users):
+        if fast[r]:
+            out[u] = sel[r].tolist()
+        else:
+            out[u] = filter_candidates(ids[r, : int(need[r, 0])].tolist(), set(train_positive_map.get(u, ())), ground_truth[u], max_k)
+    return out
+
+
 def evaluate_users(index: FlatIPIndex, user_embeddings: torch.Tensor, user_ids: list[int],
                    ground_truth: Mapping[int, set[int]], train_positive_map: Mapping[int, set[int]],
                    k_values: Iterable[int], search_k: int = 0, query_block: int = 8192):
     """Batched `_evaluate_model` (FAISS branch): one top-K launch sequence per block of users, then the
-    reference's per-user filtering on the host.  user_embeddings[r] belongs to user_ids[r]."""
+    reference's filtering on the host, a block at a time (`filter_block`).  user_embeddings[r] belongs to user_ids[r]."""
     max_k = max(k_values)
     preds: dict[int, list[int]] = {}
     # the reference asks for search_k = max(faiss_search_k, max_k + |gt| + |blocked|) per user; a block uses its max
@@ -85,8 +128,5 @@ def evaluate_users(index: FlatIPIndex, user_embeddings: torch.Tensor, user_ids: 
         need = [max(search_k, max(max_k + len(ground_truth[u]), 1) + len(train_positive_map.get(u, ()))) for u in blk]
         k_blk = min(max(need), index.ntotal)
         ids, _ = index.search(user_embeddings[s:s + len(blk)], k_blk)
-        ids = ids.cpu().tolist()
-        for r, u in enumerate(blk):
-            cand = ids[r][: need[r]]
-            preds[u] = filter_candidates(cand, set(train_positive_map.get(u, set())), ground_truth[u], max_k)
+        preds.update(filter_block(ids.cpu().numpy(), need, blk, ground_truth, train_positive_map, max_k))
     return preds
