@@ -2,7 +2,6 @@
 inside a CUDA graph?  Prints one line per check.  Decides whether the sharded step can exchange rows with plain loads /
 stores over NVLink instead of NCCL all-to-alls."""
 import os
-import time
 
 import torch
 import torch.distributed as dist

@@ -16,7 +16,7 @@ row S) unless a device sampler is supplied.
 """
 from __future__ import annotations
 
-from typing import Any, Iterable, Mapping
+from typing import Iterable
 
 import numpy as np
 import torch

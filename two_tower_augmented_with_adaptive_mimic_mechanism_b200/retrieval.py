@@ -6,7 +6,7 @@ launch sequence.  Result order is canonical: descending score, ascending item id
 """
 from __future__ import annotations
 
-from typing import Iterable, Mapping, Optional, Sequence
+from typing import Iterable, Mapping, Sequence
 
 import numpy as np
 import torch
