@@ -361,3 +361,41 @@ def _calibration_worker(rank, world):
 
 def test_slot_capacity_calibration_world2():
     _spawn(_calibration_worker, 2)
+
+
+def _grid_topk_worker(rank, world, out_dir):
+    """Query-group x item-shard grid (W = 4, G = 2): the host logic of ShardedFlatIPIndex(query_groups=2) with the local
+    search done by the oracle (FlatIPIndex itself needs CUDA)."""
+    from two_tower_augmented_with_adaptive_mimic_mechanism_b200 import sharding as S
+    G = 2
+    g, s, n_shards = S.retrieval_grid(rank, world, G)
+    assert (g, s, n_shards) == (rank // 2, rank % 2, 2)
+    groups = S.retrieval_subgroups(world, G)                                      # collective: every rank builds both groups
+    rng = np.random.default_rng(11)
+    Q, NI, D, K = 16, 203, 12, 9
+    q = rng.standard_normal((Q, D)).astype(np.float32)
+    items = rng.standard_normal((NI, D)).astype(np.float32)
+    items[120] = items[7]; items[121] = items[7]                                  # exact ties across the two shards
+    per = Q // G
+    mine_q = q[g * per:(g + 1) * per]                                             # this rank's query group
+    mine_i = np.arange(s, NI, n_shards)                                           # training layout with S in the place of W
+    li, ls = oracle.topk_canonical(oracle.canonical_scores(mine_q, items[mine_i]), K)          # local rows of the shard
+    li = np.where(li >= 0, li * n_shards + s, li)                                 # -> global ids
+    ids, sc = S.merge_topk_shards(torch.from_numpy(li), torch.from_numpy(ls), K, _np_merge, groups[g])
+    assert ids.shape == (Q // world, K)
+    np.savez(Path(out_dir) / f"grid{rank}.npz", ids=ids.numpy(), sc=sc.numpy())
+    with pytest.raises(ValueError):
+        S.retrieval_grid(rank, world, 3)
+
+
+def test_query_group_item_shard_grid_world4(tmp_path):
+    _spawn(_grid_topk_worker, 4, str(tmp_path))
+    rng = np.random.default_rng(11)
+    Q, NI, D, K = 16, 203, 12, 9
+    q = rng.standard_normal((Q, D)).astype(np.float32)
+    items = rng.standard_normal((NI, D)).astype(np.float32)
+    items[120] = items[7]; items[121] = items[7]
+    ref_i, ref_s = oracle.topk_canonical(oracle.canonical_scores(q, items), K)
+    got_i = np.concatenate([np.load(tmp_path / f"grid{r}.npz")["ids"] for r in range(4)])       # rank r holds query block r
+    got_s = np.concatenate([np.load(tmp_path / f"grid{r}.npz")["sc"] for r in range(4)])
+    assert np.array_equal(got_i, ref_i) and np.array_equal(got_s, ref_s)

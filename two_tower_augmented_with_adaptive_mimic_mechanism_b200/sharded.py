@@ -386,15 +386,26 @@ def build_sharded_engine(model_shard, *, group=None, static: bool = False, **eng
 
 
 class ShardedFlatIPIndex:
-    """Item-sharded exact inner-product index.  Rank r holds `item_embeddings_shard` = rows r, r+W, r+2W, ... of the
-    corpus (the training layout), or a contiguous block when `contiguous_offset` is given."""
+    """Item-sharded exact inner-product index.
+
+    query_groups = 1 (default; BASELINE configs[2]: NI/W items per GPU): rank r holds `item_embeddings_shard` = rows r, r+W,
+    r+2W, ... of the corpus (the training layout), or a contiguous block when `contiguous_offset` is given; every rank
+    scores ALL queries against its shard.
+    query_groups = G > 1: a G x S grid (W = G*S, `sharding.retrieval_grid`): rank g*S+s holds item shard s of S (same two
+    layouts, with S in the place of W) and scores only query group g (Q/G queries); the merge runs inside the group's S
+    ranks.  Same FLOPs per rank, but the per-query work that does not shrink with the shard (candidate lists, finalize:
+    DESIGN 4.3) is paid for Q/G queries instead of Q - at the price of G copies of the corpus across the GPUs.
+    Either way rank r returns query block r of W, bit-identical to the one-GPU result."""
 
     def __init__(self, item_embeddings_shard: torch.Tensor, *, group=None, dtype=torch.bfloat16, normalize: bool = False,
-                 contiguous_offset: Optional[int] = None) -> None:
+                 contiguous_offset: Optional[int] = None, query_groups: int = 1) -> None:
         from .retrieval import FlatIPIndex
         self.group = group
         self.world = S._world(group)
         self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.query_groups = int(query_groups)
+        self.qgroup, self.shard, self.n_shards = S.retrieval_grid(self.rank, self.world, self.query_groups)
+        self.merge_group = S.retrieval_subgroups(self.world, self.query_groups, group)[self.qgroup] if self.world > 1 else group
         self.contiguous_offset = contiguous_offset
         self.local = FlatIPIndex(item_embeddings_shard, normalize=normalize, dtype=dtype,
                                  id_offset=0 if contiguous_offset is None else int(contiguous_offset))
@@ -403,7 +414,13 @@ class ShardedFlatIPIndex:
         """queries [Q, D]: the SAME Q queries on every rank (Q a multiple of W).  Returns (ids, scores) of this rank's
         query block [rank*Q/W, (rank+1)*Q/W) over the WHOLE corpus."""
         from . import functional as F
+        Q = queries.shape[0]
+        if Q % max(self.world, 1) != 0:
+            raise ValueError(f"number of queries ({Q}) must be a multiple of the world size ({self.world})")
+        if self.query_groups > 1:
+            per = Q // self.query_groups
+            queries = queries[self.qgroup * per:(self.qgroup + 1) * per]
         ids, scores = self.local.search(queries, k)
-        if self.contiguous_offset is None and self.world > 1:
-            ids = torch.where(ids >= 0, ids * self.world + self.rank, ids)     # local row -> global id (monotone: order kept)
-        return S.merge_topk_shards(ids, scores, k, F.topk_merge, self.group)
+        if self.contiguous_offset is None and self.n_shards > 1:
+            ids = torch.where(ids >= 0, ids * self.n_shards + self.shard, ids)   # local row -> global id (monotone: order kept)
+        return S.merge_topk_shards(ids, scores, k, F.topk_merge, self.merge_group)

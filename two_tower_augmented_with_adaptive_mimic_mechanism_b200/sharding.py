@@ -176,6 +176,25 @@ def all_reduce_flat(tensors: list, group=None) -> None:
         off += n
 
 
+def retrieval_grid(rank: int, world: int, query_groups: int):
+    """(query group g, item shard s, number of item shards S) of `rank` in a query-group x item-shard grid, W = G*S.
+    The S ranks of a query group are contiguous (g*S .. g*S+S-1): after the per-group merge rank g*S+s holds query block
+    g*S+s of W, the same contract as pure item sharding (G = 1)."""
+    if query_groups < 1 or world % query_groups != 0:
+        raise ValueError(f"query_groups ({query_groups}) must divide the world size ({world})")
+    S_ = world // query_groups
+    return rank // S_, rank % S_, S_
+
+
+def retrieval_subgroups(world: int, query_groups: int, group=None) -> list:
+    """One process group per query group (every rank must call this, in the same order: torch.distributed.new_group is
+    collective over the default group).  [None] when there is a single query group spanning the whole `group`."""
+    if query_groups == 1:
+        return [group]
+    S_ = world // query_groups
+    return [dist.new_group(list(range(g * S_, (g + 1) * S_))) for g in range(query_groups)]
+
+
 def merge_topk_shards(ids: torch.Tensor, scores: torch.Tensor, k: int, merge_fn, group=None):
     """Item-sharded retrieval: every rank holds the partial top-K lists of ALL queries over ITS item shard
     (ids [Q, K'] global ids, scores [Q, K']).  Query block b goes to rank b: all-to-all of [Q/W, K'] blocks, then a
