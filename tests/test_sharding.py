@@ -399,3 +399,58 @@ def test_query_group_item_shard_grid_world4(tmp_path):
     got_i = np.concatenate([np.load(tmp_path / f"grid{r}.npz")["ids"] for r in range(4)])       # rank r holds query block r
     got_s = np.concatenate([np.load(tmp_path / f"grid{r}.npz")["sc"] for r in range(4)])
     assert np.array_equal(got_i, ref_i) and np.array_equal(got_s, ref_s)
+
+
+class _CpuFlatIP:
+    """numpy stand-in for retrieval.FlatIPIndex (which needs CUDA): same constructor / search contract, oracle arithmetic."""
+
+    def __init__(self, item_embeddings, *, normalize=False, dtype=None, id_offset=0):
+        self.items, self.id_offset = item_embeddings.numpy(), int(id_offset)
+
+    def search(self, queries, k):
+        ids, sc = oracle.topk_canonical(oracle.canonical_scores(queries.numpy(), self.items), k)
+        return torch.from_numpy(np.where(ids >= 0, ids + self.id_offset, ids)), torch.from_numpy(sc)
+
+
+def _sharded_index_worker(rank, world, out_dir):
+    """ShardedFlatIPIndex itself (the class bench.py drives at N > 1), both item layouts, G = 1 and G = 2, on gloo with the
+    CUDA pieces (FlatIPIndex, ttam_topk_merge) replaced by their oracle equivalents."""
+    import two_tower_augmented_with_adaptive_mimic_mechanism_b200.functional as F
+    import two_tower_augmented_with_adaptive_mimic_mechanism_b200.retrieval as R
+    from two_tower_augmented_with_adaptive_mimic_mechanism_b200.sharded import ShardedFlatIPIndex
+    R.FlatIPIndex = _CpuFlatIP
+    F.topk_merge = _np_merge
+    rng = np.random.default_rng(23)
+    Q, NI, D, K = 16, 157, 10, 7
+    q = torch.from_numpy(rng.standard_normal((Q, D)).astype(np.float32))
+    items = rng.standard_normal((NI, D)).astype(np.float32)
+    items[90] = items[5]                                                          # a tie across shards
+    items_t = torch.from_numpy(items)
+    out = {}
+    for G in (1, 2):
+        S_ = world // G
+        s = rank % S_
+        # training layout: shard s = rows s, s+S, ...
+        idx = ShardedFlatIPIndex(items_t[s::S_].contiguous(), query_groups=G)
+        out[f"stride{G}"] = idx.search(q, K)[0].numpy()
+        # contiguous blocks
+        per = (NI + S_ - 1) // S_
+        lo, hi = s * per, min(NI, (s + 1) * per)
+        idx = ShardedFlatIPIndex(items_t[lo:hi].contiguous(), contiguous_offset=lo, query_groups=G)
+        out[f"block{G}"] = idx.search(q, K)[0].numpy()
+    with pytest.raises(ValueError):
+        ShardedFlatIPIndex(items_t, query_groups=3)
+    np.savez(Path(out_dir) / f"index{rank}.npz", **out)
+
+
+def test_sharded_flat_ip_index_world4(tmp_path):
+    _spawn(_sharded_index_worker, 4, str(tmp_path))
+    rng = np.random.default_rng(23)
+    Q, NI, D, K = 16, 157, 10, 7
+    q = rng.standard_normal((Q, D)).astype(np.float32)
+    items = rng.standard_normal((NI, D)).astype(np.float32)
+    items[90] = items[5]
+    ref_i, _ = oracle.topk_canonical(oracle.canonical_scores(q, items), K)
+    for key in ("stride1", "block1", "stride2", "block2"):
+        got = np.concatenate([np.load(tmp_path / f"index{r}.npz")[key] for r in range(4)])      # rank r: query block r
+        assert np.array_equal(got, ref_i), key
