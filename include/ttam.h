@@ -303,6 +303,17 @@ int64_t ttam_topk_f32_workspace_bytes(int64_t Q, int64_t N, int64_t D, int64_t K
 int ttam_topk_f32(const float* q, const float* items, int64_t Q, int64_t N, int64_t D, int64_t K,
                   int64_t id_offset, int64_t* out_ids, float* out_scores, void* workspace,
                   int64_t workspace_bytes, void* stream);
+/* Paged form of ttam_topk_f32: query r only admits items that sort strictly AFTER (after_scores[r], after_ids[r]) in the
+ * canonical order (after_ids[r] < 0: no restriction), so the caller walks down a ranking K results at a time - what a
+ * faiss.IndexFlatIP.search with search_k beyond the kernel's K limit needs (training.py:956-958: search_k grows with the
+ * user's number of training positives).  Same workspace as ttam_topk_f32. */
+int ttam_topk_f32_after(const float* q, const float* items, int64_t Q, int64_t N, int64_t D, int64_t K,
+                        int64_t id_offset, const float* after_scores, const int64_t* after_ids, int64_t* out_ids,
+                        float* out_scores, void* workspace, int64_t workspace_bytes, void* stream);
+/* out[r, c] = canonical fp32 score of query r against items[cand[r, c]] (cand < 0: -inf): the candidate scoring of
+ * `_retrieve_with_sampling` (training.py:986-1005), all users of an evaluation in one launch. */
+int ttam_score_pairs(const float* q, const float* items, const int64_t* cand, int64_t R, int64_t C, int64_t D,
+                     int64_t N, float* out, void* stream);
 int64_t ttam_topk_bf16_workspace_bytes(int64_t Q, int64_t N, int64_t D, int64_t K);
 int ttam_topk_bf16(const uint16_t* q, const uint16_t* items, int64_t Q, int64_t N, int64_t D, int64_t K,
                    int64_t id_offset, int64_t* out_ids, float* out_scores, void* workspace,

@@ -148,6 +148,8 @@ SIGNATURES = {
     "ttam_slot_pack": (C.c_int, [_p, _p, _i64, _p, _p, _i64, _i64, _i64, _p, _p, _i64, _p]),
     "ttam_topk_f32_workspace_bytes": (C.c_int64, [_i64, _i64, _i64, _i64]),
     "ttam_topk_f32": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _i64, _p]),
+    "ttam_topk_f32_after": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p, _i64, _p]),
+    "ttam_score_pairs": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _p, _p]),
     "ttam_topk_bf16_workspace_bytes": (C.c_int64, [_i64, _i64, _i64, _i64]),
     "ttam_topk_bf16": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _i64, _p]),
     "ttam_topk_merge": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _p, _p, _p]),

@@ -32,11 +32,14 @@ constexpr int kSelCap = kSelThreads * kSelItems;
 
 // One block per query: new running top-K = best K of (running K keys  U  chunk scores).
 // scores: [Q, ld] fp32 for ids id0 .. id0+n-1.  running: [Q, K] keys (sorted ascending).
+// after: optional [Q] keys; a candidate is admitted only if it sorts strictly AFTER its query's key (paged search).
 __global__ void __launch_bounds__(kSelThreads) select_topk_kernel(const float* __restrict__ scores, int64_t ld, int n,
-                                                                  uint32_t id0, uint64_t* __restrict__ running, int K) {
+                                                                  uint32_t id0, uint64_t* __restrict__ running, int K,
+                                                                  const uint64_t* __restrict__ after) {
   using Sort = cub::BlockRadixSort<uint64_t, kSelThreads, kSelItems>;
   __shared__ typename Sort::TempStorage temp;
   const int q = blockIdx.x;
+  const uint64_t floor_key = after ? after[q] : 0ull;
   uint64_t keys[kSelItems];
   // blocked arrangement: thread t owns slots t*kSelItems .. +kSelItems-1
 #pragma unroll
@@ -44,7 +47,10 @@ __global__ void __launch_bounds__(kSelThreads) select_topk_kernel(const float* _
     const int slot = threadIdx.x * kSelItems + i;
     uint64_t k = kWorstKey;
     if (slot < K) k = running[(int64_t)q * K + slot];
-    else if (slot - K < n) k = make_key(scores[(int64_t)q * ld + (slot - K)], id0 + (uint32_t)(slot - K));
+    else if (slot - K < n) {
+      k = make_key(scores[(int64_t)q * ld + (slot - K)], id0 + (uint32_t)(slot - K));
+      if (after && k <= floor_key) k = kWorstKey;
+    }
     keys[i] = k;
   }
   Sort(temp).Sort(keys);
@@ -53,6 +59,32 @@ __global__ void __launch_bounds__(kSelThreads) select_topk_kernel(const float* _
     const int slot = threadIdx.x * kSelItems + i;
     if (slot < K) running[(int64_t)q * K + slot] = keys[i];
   }
+}
+
+// (score, returned id) of the last result of the previous page -> key; id < 0: no previous page (admit everything)
+__global__ void after_keys_kernel(const float* __restrict__ scores, const int64_t* __restrict__ ids, int64_t id_offset,
+                                  int64_t Q, uint64_t* __restrict__ keys) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Q) keys[i] = ids[i] < 0 ? 0ull : make_key(scores[i], (uint32_t)(ids[i] - id_offset));
+}
+
+// out[r, c] = <q[r, :], items[cand[r, c], :]> with the canonical arithmetic (products rounded to fp32, accumulated in
+// the order d = 0..D-1); cand < 0 -> -inf.  One thread per pair: candidate lists are short (reference training.py:974-1009:
+// ground truth + 50 sampled items per user).
+__global__ void score_pairs_kernel(const float* __restrict__ q, const float* __restrict__ items, const int64_t* __restrict__ cand,
+                                   int64_t R, int64_t C, int D, int64_t N, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * C) return;
+  const int64_t r = i / C, id = cand[i];
+  if (id < 0 || id >= N) {
+    out[i] = -INFINITY;
+    return;
+  }
+  const float* a = q + r * D;
+  const float* b = items + id * D;
+  float acc = 0.f;
+  for (int d = 0; d < D; ++d) acc = __fadd_rn(acc, __fmul_rn(a[d], b[d]));
+  out[i] = acc;
 }
 
 __global__ void fill_keys_kernel(uint64_t* keys, int64_t n) {
@@ -134,12 +166,31 @@ using namespace ttam;
 extern "C" int64_t ttam_topk_f32_workspace_bytes(int64_t Q, int64_t N, int64_t D, int64_t K) {
   (void)N; (void)D;
   int64_t qb = Q < kQBlock ? Q : kQBlock;
-  return align_up(qb * kChunk * 4, 256) + align_up(Q * K * 8, 256) + 256;
+  return align_up(qb * kChunk * 4, 256) + align_up(Q * K * 8, 256) + align_up(Q * 8, 256) + 256;
 }
 
 extern "C" int ttam_topk_f32(const float* q, const float* items, int64_t Q, int64_t N, int64_t D, int64_t K,
                              int64_t id_offset, int64_t* out_ids, float* out_scores, void* workspace,
                              int64_t workspace_bytes, void* stream) {
+  return ttam_topk_f32_after(q, items, Q, N, D, K, id_offset, nullptr, nullptr, out_ids, out_scores, workspace,
+                             workspace_bytes, stream);
+}
+
+extern "C" int ttam_score_pairs(const float* q, const float* items, const int64_t* cand, int64_t R, int64_t C, int64_t D,
+                                int64_t N, float* out, void* stream) {
+  TTAM_CHECK_ARG(q && items && cand && out, "score_pairs: null pointer");
+  TTAM_CHECK_ARG(R >= 0 && C >= 0 && D > 0 && N > 0, "score_pairs: bad shape");
+  if (R * C == 0) return TTAM_OK;
+  score_pairs_kernel<<<(unsigned)ceil_div(R * C, 256), 256, 0, (cudaStream_t)stream>>>(q, items, cand, R, C, (int)D, N, out);
+  TTAM_LAUNCH_CHECK();
+  return TTAM_OK;
+}
+
+extern "C" int ttam_topk_f32_after(const float* q, const float* items, int64_t Q, int64_t N, int64_t D, int64_t K,
+                                   int64_t id_offset, const float* after_scores, const int64_t* after_ids,
+                                   int64_t* out_ids, float* out_scores, void* workspace, int64_t workspace_bytes,
+                                   void* stream) {
+  TTAM_CHECK_ARG((after_scores == nullptr) == (after_ids == nullptr), "topk_f32_after: pass both after arrays or neither");
   TTAM_CHECK_ARG(q && items && out_ids && workspace, "topk_f32: null pointer");
   TTAM_CHECK_ARG(Q >= 0 && N > 0 && D > 0 && K > 0, "topk_f32: bad shape");
   TTAM_CHECK_ARG(K + kChunk <= kSelCap, "topk_f32: K must be <= %d", kSelCap - kChunk);
@@ -153,6 +204,12 @@ extern "C" int ttam_topk_f32(const float* q, const float* items, int64_t Q, int6
   const int64_t qb = Q < kQBlock ? Q : kQBlock;
   float* scores = (float*)workspace;
   uint64_t* running = (uint64_t*)((char*)workspace + align_up(qb * kChunk * 4, 256));
+  uint64_t* after = nullptr;
+  if (after_ids) {
+    after = running + align_up(Q * K * 8, 256) / 8;
+    after_keys_kernel<<<(unsigned)ceil_div(Q, 256), 256, 0, s>>>(after_scores, after_ids, id_offset, Q, after);
+    TTAM_LAUNCH_CHECK();
+  }
   fill_keys_kernel<<<(int)std::min<int64_t>(ceil_div(Q * K, 256), 4096), 256, 0, s>>>(running, Q * K);
   TTAM_LAUNCH_CHECK();
   for (int64_t q0 = 0; q0 < Q; q0 += qb) {
@@ -166,7 +223,7 @@ extern "C" int ttam_topk_f32(const float* q, const float* items, int64_t Q, int6
       gemm_f32_kernel<true, true, true><<<grid, 256, 0, s>>>(p);
       TTAM_LAUNCH_CHECK();
       select_topk_kernel<<<(unsigned)nq, kSelThreads, 0, s>>>(scores, kChunk, (int)nc, (uint32_t)c0,
-                                                              running + q0 * K, (int)K);
+                                                              running + q0 * K, (int)K, after ? after + q0 : nullptr);
       TTAM_LAUNCH_CHECK();
     }
   }

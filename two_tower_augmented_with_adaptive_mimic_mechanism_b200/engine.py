@@ -11,6 +11,7 @@ The engine updates the model's own parameter storage in place, so `state_dict()`
 from __future__ import annotations
 
 import os
+import weakref
 from dataclasses import dataclass
 from typing import Optional
 
@@ -37,6 +38,10 @@ class _Table:
     m: Optional[torch.Tensor] = None
     v: Optional[torch.Tensor] = None
     last_step: Optional[torch.Tensor] = None   # int32 [N], lazy tables only
+
+
+class _Rebuild(Exception):
+    """set_hyper: the change needs a freshly built engine (optimiser kind before the first step)."""
 
 
 class FusedEngine:
@@ -95,8 +100,7 @@ class FusedEngine:
                 self._add_table(f"adaptive_mimic.{side}_augmented.weight", plan.aug, "lazy")
         # ---- step state + bias-correction tables (device resident: the step is CUDA-graph replayable)
         self.state = F.new_step_state(dev, 0, 0)
-        self.scal_dense = F.adam_scalar_table(self.max_steps, self.lr, self.dense_betas, dev)
-        self.scal_sparse = F.adam_scalar_table(self.max_steps, self.lr, self.sparse_betas, dev)
+        self._build_scalar_tables()
         self.bufs_u = self._grad_bufs(self.user)
         self.bufs_i = self._grad_bufs(self.item)
         self.misc: dict = {}
@@ -112,6 +116,46 @@ class FusedEngine:
         self._use_aug_stream = os.environ.get("TTAM_AUG_STREAM", "1") != "0"
 
     # --------------------------------------------------------------------------------------------
+    def _build_scalar_tables(self) -> None:
+        self.scal_dense = F.adam_scalar_table(self.max_steps, self.lr, self.dense_betas, self.device)
+        self.scal_sparse = F.adam_scalar_table(self.max_steps, self.lr, self.sparse_betas, self.device)
+
+    def _ensure_steps(self, t: int) -> None:
+        """The bias-correction tables are indexed by the optimiser step; they grow (doubling) instead of the engine
+        refusing step max_steps + 1.  Kernels - and captured graphs - address the tables by pointer, so growing them
+        invalidates every captured graph (re-captured on the next graph step)."""
+        if t <= self.max_steps:
+            return
+        self.max_steps = max(2 * self.max_steps, t + 1024)
+        torch.cuda.current_stream(self.device).synchronize()     # in-flight steps still read the old tables
+        self._build_scalar_tables()
+        F.note_realloc()
+
+    def set_hyper(self, *, optimizer=None, lr=None, weight_decay=None, momentum=None, dense_betas=None, sparse_betas=None) -> bool:
+        """Change optimiser hyper-parameters in place.  Returns True when anything changed.  The optimiser KIND can only
+        change before the first step (the moment buffers depend on it)."""
+        new = dict(kind=self.kind if optimizer is None else optimizer.lower(), lr=self.lr if lr is None else float(lr),
+                   wd=self.wd if weight_decay is None else float(weight_decay),
+                   momentum=self.momentum if momentum is None else float(momentum),
+                   dense_betas=self.dense_betas if dense_betas is None else tuple(dense_betas),
+                   sparse_betas=self.sparse_betas if sparse_betas is None else tuple(sparse_betas))
+        old = dict(kind=self.kind, lr=self.lr, wd=self.wd, momentum=self.momentum, dense_betas=self.dense_betas,
+                   sparse_betas=self.sparse_betas)
+        if new == old:
+            return False
+        if new["kind"] != self.kind or (self.kind == "sgd" and (new["momentum"] != 0.0) != (self.momentum != 0.0)):
+            if self.t > 0:
+                raise ValueError("the optimiser kind cannot change after the first step: build a new engine")
+            raise _Rebuild()
+        if self.dirty:
+            self.flush()          # rows that are behind were to be replayed with the OLD hyper-parameters
+        self.lr, self.wd, self.momentum = new["lr"], new["wd"], new["momentum"]
+        self.dense_betas, self.sparse_betas = new["dense_betas"], new["sparse_betas"]
+        torch.cuda.current_stream(self.device).synchronize()
+        self._build_scalar_tables()
+        F.note_realloc()
+        return True
+
     def _grad_bufs(self, plan: TowerPlan) -> dict:
         """Buffer dict of one tower, pre-seeded with the weight-gradient views of the flat dense-gradient buffer
         (tower_ops looks gradients up as dw<id> [shape of W] and db<id> [n, 1])."""
@@ -141,14 +185,20 @@ class FusedEngine:
         reused for as long as the caller keeps passing the same tensor."""
         if X is None or self.precision == "fp32":
             return X
+        # keyed by the tensor OBJECT (weak reference) and its version counter: a new tensor that lands on a freed
+        # matrix's address, or an in-place edit of the matrix, gets a fresh copy
         key = (X.data_ptr(), tuple(X.shape))
         hit = self._xpad.get(key)
+        if hit is not None and (hit[0]() is not X or hit[1] != X._version):
+            hit = None
         if hit is None:
-            hit = F.round_tf32_(F.pad_cols(X, always_copy=True))   # private copy: padded rows, TF32-representable values
-            hit._ttam_tf32 = True
+            cp = F.round_tf32_(F.pad_cols(X, always_copy=True))   # private copy: padded rows, TF32-representable values
+            cp._ttam_tf32 = True
             self._xpad = {k: v for k, v in self._xpad.items() if k[0] != key[0]}
+            hit = (weakref.ref(X), X._version, cp)
             self._xpad[key] = hit
-        return hit
+            F.note_realloc()       # graphs captured on the old copy are stale
+        return hit[2]
 
     def _categories(self):
         """(category tensor on the device, number of categories) - the count costs one host read, once per tensor."""
@@ -164,6 +214,8 @@ class FusedEngine:
         t = self.misc.get(name)
         if t is None or t.shape[0] < shape[0] or t.shape[1:] != tuple(shape[1:]) or t.dtype != dtype:
             rows = shape[0] if shape[0] < 4096 else (int(shape[0] * 1.125) + 1023) // 1024 * 1024   # headroom: see tower_ops._buf
+            if name in self.misc:
+                F.note_realloc()
             t = torch.empty((rows,) + tuple(shape[1:]), dtype=dtype, device=self.device)
             self.misc[name] = t
         return t[: shape[0]]
@@ -390,8 +442,7 @@ class FusedEngine:
 
     def begin_step(self) -> None:
         """Advance the host-side step counter (the device-side one advances inside the forward phase)."""
-        if self.t + 1 > self.max_steps:
-            raise RuntimeError(f"max_steps={self.max_steps} exhausted; build the engine with a larger max_steps")
+        self._ensure_steps(self.t + 1)
         self.t += 1
         self.dirty = True
 
@@ -401,8 +452,7 @@ class FusedEngine:
         """One optimisation step on a batch (users [B], pos [B], neg [B,N], all int64 on the device).
         Returns a device tensor loss[4] = {total, bce, mimic_user, mimic_item} (valid until the next step)."""
         B, N = neg.shape
-        if self.t + 1 > self.max_steps:
-            raise RuntimeError(f"max_steps={self.max_steps} exhausted; build the engine with a larger max_steps")
+        self._ensure_steps(self.t + 1)
         if graph:
             return self._graph_step(users, pos, neg, user_x, item_x)
         items = self._misc("items", (B * (1 + N),), torch.int64)
@@ -417,6 +467,11 @@ class FusedEngine:
         B, N = neg.shape
         key = (B, N, None if user_x is None else user_x.data_ptr(), None if item_x is None else item_x.data_ptr())
         entry = self._graphs.get(key)
+        if entry is not None and entry[4] != F.alloc_generation():
+            # a buffer / workspace / scalar table the captured launches address has been reallocated since: every graph of
+            # this engine may hold dangling pointers
+            self._graphs.clear()
+            entry = None
         if entry is None:
             su = torch.empty(B, dtype=torch.int64, device=self.device)
             si = torch.empty(B * (1 + N), dtype=torch.int64, device=self.device)
@@ -429,11 +484,11 @@ class FusedEngine:
             # capture advances the device step once without executing: compensate afterwards
             with torch.cuda.graph(g):
                 loss = self._step_body(su, si, B, N, user_x, item_x)
-            entry = (g, su, si, loss)
+            entry = (g, su, si, loss, F.alloc_generation())
             self._graphs[key] = entry
             self.dirty = True
             return loss
-        g, su, si, loss = entry
+        g, su, si, loss, _ = entry
         su.copy_(users); si[:B].copy_(pos); si[B:].copy_(neg.reshape(-1))
         self.t += 1
         self.dirty = True
@@ -474,6 +529,34 @@ class FusedEngine:
             e = min(n, s + chunk)
             self.encode(side, torch.arange(s, e, device=self.device, dtype=torch.int64), X, out=out[s:e])
         return out
+
+    def _param_version(self) -> tuple:
+        """Changes whenever the parameters may have: our own steps (t) and torch-side writes (load_state_dict bumps the
+        tensors' version counters; our kernels write through raw pointers and do not)."""
+        return (self.t, tuple(p._version for p in self.model.parameters()))
+
+    @torch.no_grad()
+    def corpus(self, item_x) -> torch.Tensor:
+        """Eval-mode embeddings of the whole item corpus [NI, D] (reference `_encode_item_embeddings`, training.py:613-643),
+        encoded once per parameter version: the validation and test evaluations of an epoch, `_score_all_items_for_user`
+        and the final index all share it (the reference re-encodes the corpus for each of them)."""
+        key = (self._param_version(), None if item_x is None else (item_x.data_ptr(), item_x._version), bool(self.model.training))
+        hit = self.__dict__.get("_corpus_cache")
+        if hit is None or hit[0] != key:
+            hit = (key, self.encode_all("item", item_x), {})
+            self._corpus_cache = hit
+        return hit[1]
+
+    @torch.no_grad()
+    def corpus_index(self, item_x, *, normalize: bool = False, dtype=torch.float32):
+        """FlatIPIndex over `corpus(item_x)`, cached next to it."""
+        from .retrieval import FlatIPIndex
+        self.corpus(item_x)
+        cache = self._corpus_cache[2]
+        k = (bool(normalize), dtype)
+        if k not in cache:
+            cache[k] = FlatIPIndex(self._corpus_cache[1], normalize=normalize, dtype=dtype)
+        return cache[k]
 
     @torch.no_grad()
     def eval_loss(self, users, pos, neg, user_x, item_x) -> torch.Tensor:

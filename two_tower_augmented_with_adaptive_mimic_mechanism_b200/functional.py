@@ -35,6 +35,18 @@ def _ptr(t):
 
 
 _ws_cache: dict = {}
+_alloc_generation = [0]
+
+
+def alloc_generation() -> int:
+    """Bumped whenever a grow-only buffer that kernels address by raw pointer (scratch workspace, engine / tower
+    buffers) is reallocated.  A captured CUDA graph holds the OLD pointers: holders of graphs compare the generation
+    they captured at with this one before every replay and re-capture when it moved."""
+    return _alloc_generation[0]
+
+
+def note_realloc() -> None:
+    _alloc_generation[0] += 1
 
 
 _ws_scope = [""]
@@ -62,6 +74,8 @@ def workspace(nbytes: int, device, tag: str = "default") -> torch.Tensor:
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         grow = int(nbytes) if buf is None else int(nbytes * 1.25)   # regrowth gets headroom (row counts drift per step)
+        if buf is not None:
+            note_realloc()
         buf = torch.empty(max(grow, 256), dtype=torch.uint8, device=device)
         _ws_cache[key] = buf
     return buf
@@ -396,8 +410,25 @@ def adam_scalar_table(max_step: int, lr: float, betas=(0.9, 0.999), device="cuda
 
 
 # ---------------------------------------------------------------------------------------------
-def topk(q: torch.Tensor, items: torch.Tensor, k: int, *, id_offset: int = 0):
-    """Exact inner-product top-k in canonical (-score,+id) order.  fp32 -> SIMT path; bf16 -> tcgen05 path."""
+TOPK_F32_MAX_K = 1024     # csrc/topk.cu: kSelCap - kChunk
+TOPK_BF16_MAX_K = 128     # csrc/topk_tc.cu
+
+
+def score_pairs(q: torch.Tensor, items: torch.Tensor, cand: torch.Tensor) -> torch.Tensor:
+    """out[r, c] = canonical fp32 score of q[r] against items[cand[r, c]] (-inf where cand < 0)."""
+    _chk(q, torch.float32, "q"); _chk(items, torch.float32, "items"); _chk(cand, torch.int64, "cand")
+    q, items, cand = q.contiguous(), items.contiguous(), cand.contiguous()
+    R, C = cand.shape
+    out = torch.empty((R, C), dtype=torch.float32, device=q.device)
+    check(lib().ttam_score_pairs(q.data_ptr(), items.data_ptr(), cand.data_ptr(), R, C, q.shape[1], items.shape[0],
+                                 out.data_ptr(), _stream()), "score_pairs")
+    return out
+
+
+def topk(q: torch.Tensor, items: torch.Tensor, k: int, *, id_offset: int = 0, after=None):
+    """Exact inner-product top-k in canonical (-score,+id) order.  fp32 -> SIMT path; bf16 -> tcgen05 path.
+    after = (scores [Q] fp32, ids [Q] int64): fp32 only - query r admits only items that sort strictly after
+    (scores[r], ids[r]) (ids[r] < 0: all of them); the next page of a ranking."""
     if q.dtype != items.dtype:
         raise ValueError("q and items must have the same dtype")
     if not (q.is_cuda and items.is_cuda):
@@ -409,10 +440,15 @@ def topk(q: torch.Tensor, items: torch.Tensor, k: int, *, id_offset: int = 0):
     ids = torch.empty((Q, k_eff), dtype=torch.int64, device=q.device)
     scores = torch.empty((Q, k_eff), dtype=torch.float32, device=q.device)
     L = lib()
+    if after is not None and q.dtype != torch.float32:
+        raise ValueError("paged search (after=) is available on the fp32 path only")
     if q.dtype == torch.float32:
         ws = workspace(L.ttam_topk_f32_workspace_bytes(Q, N, D, k_eff), q.device, "topk")
-        check(L.ttam_topk_f32(q.data_ptr(), items.data_ptr(), Q, N, D, k_eff, id_offset, ids.data_ptr(), scores.data_ptr(),
-                              ws.data_ptr(), ws.numel(), _stream()), "topk_f32")
+        a_s, a_i = (None, None) if after is None else (after[0].contiguous(), after[1].contiguous())
+        if after is not None:
+            _chk(a_s, torch.float32, "after scores"); _chk(a_i, torch.int64, "after ids")
+        check(L.ttam_topk_f32_after(q.data_ptr(), items.data_ptr(), Q, N, D, k_eff, id_offset, _ptr(a_s), _ptr(a_i),
+                                    ids.data_ptr(), scores.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "topk_f32")
     elif q.dtype == torch.bfloat16:
         ws = workspace(L.ttam_topk_bf16_workspace_bytes(Q, N, D, k_eff), q.device, "topk")
         check(L.ttam_topk_bf16(q.data_ptr(), items.data_ptr(), Q, N, D, k_eff, id_offset, ids.data_ptr(), scores.data_ptr(),

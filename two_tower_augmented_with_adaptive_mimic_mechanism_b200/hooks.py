@@ -3,29 +3,53 @@ exact signatures and return values, so that `scripts/train.py` runs unchanged:
 
     import src.pipelines.training as training
     from two_tower_augmented_with_adaptive_mimic_mechanism_b200 import hooks
-    hooks.install(training)          # then training.run_training(cfg) as usual
+    hooks.install(training)          # then training.run_training(cfg) as usual   (scripts/train_b200.py does this)
 
-  _train_one_epoch        reference training.py:700-833   -> FusedEngine.train_step per batch
-  _compute_loss           reference training.py:836-914   -> FusedEngine.eval_loss per batch
-  _encode_item_embeddings reference training.py:613-643   -> FusedEngine.encode_all
-  _evaluate_model         reference training.py:917-1043  -> batched exact top-K + the reference's host filter
-  _score_all_items_for_user reference training.py:330-384 -> exact top-K over the encoded corpus
+  _train_one_epoch          reference training.py:700-833   -> FusedEngine.train_step per batch (CUDA-graph replay)
+  _compute_loss             reference training.py:836-914   -> FusedEngine.eval_loss per batch
+  _encode_item_embeddings   reference training.py:613-643   -> FusedEngine.encode_all (cached per parameter version)
+  _prepare_faiss_resources  reference training.py:646-679   -> a GPU-resident FlatIPIndex in place of faiss.IndexFlatIP
+  _save_faiss_artifacts     reference training.py:682-697   -> item_embeddings.npy (+ the index as a second .npy)
+  _evaluate_model           reference training.py:917-1043  -> batched exact top-K + the reference's host filter, or the
+                                                               reference's candidate-sampling branch (eval_mode="reference")
+  _score_all_items_for_user reference training.py:330-384   -> exact top-K over the encoded corpus
 
-Negative sampling stays the reference's `sample_negative_items` (it is an input of the hot path, SURVEY 8(a)
-row S) unless a device sampler is supplied.
+What `install()` delivers is the fast path: tensor-core (TF32) tower GEMMs, the step replayed as a CUDA graph, negatives
+drawn by the device sampler (`sampler.PositiveSet`, built once per positives dict) and batches cut from device-resident
+interaction tensors (the reference's DataLoader calls `Dataset.__getitem__` once per SAMPLE: datasets.py:44).
+`sampler="reference"` keeps the reference's per-row Python sampler and its DataLoader order instead - slow, but the global
+torch generator is then consumed exactly as in a reference CPU run, which is what the parity test compares against.
 """
 from __future__ import annotations
 
-from typing import Iterable
+from dataclasses import dataclass
+from typing import Iterable, Optional
 
 import numpy as np
 import torch
 from torch import nn
 
-from .engine import FusedEngine
-from .retrieval import FlatIPIndex, evaluate_users
+from .engine import FusedEngine, _Rebuild
+from .retrieval import FlatIPIndex, evaluate_users, score_candidates
+from . import sampler as _sampler_mod
 
 _ENGINE_ATTR = "_ttam_engine"
+
+
+@dataclass
+class HookOptions:
+    precision: str = "tf32"       # tower GEMMs: "tf32" (tcgen05) | "fp32" (SIMT, bit-faithful arithmetic)
+    graph: bool = True            # replay the step as a CUDA graph
+    sampler: str = "device"       # "device": PositiveSet + sample_negatives_kernel, device batch iterator
+                                  # "reference": the reference's Python sampler + its DataLoader (parity runs)
+    eval_mode: str = "exact"      # "exact": full-corpus top-K for every evaluation
+                                  # "reference": exact where the reference would use FAISS, its candidate-sampling
+                                  #              branch (training.py:974-1009, same rng draws) where it would sample
+    reference_sampler: object = None   # the reference's own sample_negative_items, captured at install time
+    stats: Optional[dict] = None  # filled by the hooks: steps, samples, seconds inside _train_one_epoch
+
+
+OPTIONS = HookOptions()
 
 
 def _hyper_from_optimizers(optimizers) -> dict:
@@ -53,9 +77,20 @@ def _hyper_from_optimizers(optimizers) -> dict:
 
 
 def engine_for(model, optimizers=(), **overrides) -> FusedEngine:
+    """The model's engine.  An engine that was first built by an evaluation call (no optimisers in sight: default
+    hyper-parameters) takes the optimisers' hyper-parameters as soon as a training call brings them; a change after the
+    first step is applied in place (lr / weight decay / betas) or refused (optimiser kind)."""
     eng = getattr(model, _ENGINE_ATTR, None)
+    optimizers = list(optimizers or ())
+    if eng is not None and optimizers:
+        hp = _hyper_from_optimizers(optimizers)
+        try:
+            eng.set_hyper(**hp)
+        except _Rebuild:
+            eng = None
     if eng is None:
         hp = _hyper_from_optimizers(optimizers)
+        hp.setdefault("precision", OPTIONS.precision)
         hp.update(overrides)
         eng = FusedEngine(model, **hp)
         object.__setattr__(model, _ENGINE_ATTR, eng)
@@ -82,13 +117,93 @@ def _publish_optimizer_state(eng: FusedEngine, optimizers) -> None:
                     slot["exp_avg_sq"] = s["exp_avg_sq"]
 
 
-def _sampler():
-    try:
-        from src.data.samplers import sample_negative_items  # the reference's sampler, when importable
-        return sample_negative_items
-    except Exception:  # pragma: no cover - standalone use
-        from .sampler import sample_negative_items
-        return sample_negative_items
+# ------------------------------------------------------------------------------------------------
+# batches and negatives
+# ------------------------------------------------------------------------------------------------
+def _interaction_tensors(dataloader, device):
+    """(users, items) of the loader's dataset as device tensors, cached on the dataset; None when the dataset is not an
+    index-pair dataset (reference datasets.py:12-45 keeps them as `_users` / `_items`)."""
+    ds = getattr(dataloader, "dataset", None)
+    u, i = getattr(ds, "_users", None), getattr(ds, "_items", None)
+    if not (isinstance(u, torch.Tensor) and isinstance(i, torch.Tensor) and u.dim() == 1 and u.shape == i.shape):
+        return None
+    hit = getattr(ds, "_ttam_device", None)
+    if hit is None or hit[0].device != torch.device(device):
+        hit = (u.to(device=device, dtype=torch.int64), i.to(device=device, dtype=torch.int64))
+        try:
+            ds._ttam_device = hit
+        except Exception:  # noqa: BLE001 - a dataset that refuses attributes just is not cached
+            pass
+    return hit
+
+
+def _device_epoch(dataloader, device):
+    """One epoch of (users, pos) batches cut from device-resident interaction tensors: the replacement of the per-sample
+    DataLoader (training.py:260-264): same batch size / shuffle / drop_last semantics, the permutation drawn on the
+    device.  Returns None when the loader cannot be mirrored (the caller iterates it as it is)."""
+    pair = _interaction_tensors(dataloader, device)
+    bs = getattr(dataloader, "batch_size", None)
+    if pair is None or not bs:
+        return None
+    users, items = pair
+    n = users.shape[0]
+    if isinstance(getattr(dataloader, "sampler", None), torch.utils.data.RandomSampler):
+        perm = torch.randperm(n, device=users.device)
+        users, items = users[perm], items[perm]
+    elif not isinstance(getattr(dataloader, "sampler", None), torch.utils.data.SequentialSampler):
+        return None
+    stop = n - (n % bs) if getattr(dataloader, "drop_last", False) else n
+    return users, items, [(s, min(s + bs, stop)) for s in range(0, stop, bs)]
+
+
+_positive_sets: dict = {}
+
+
+def _positive_set(positives, num_items, device):
+    """Sorted (user, item) keys of `user_positive_items` on the device, built once per dict (sampler.PositiveSet)."""
+    key = (id(positives), int(num_items), str(device))
+    hit = _positive_sets.get(key)
+    if hit is None or hit[0] is not positives:
+        hit = (positives, _sampler_mod.PositiveSet(positives, num_items, device))
+        _positive_sets.clear()
+        _positive_sets[key] = hit
+    return hit[1]
+
+
+def _batches(dataloader, *, num_items, positives, num_negatives, device):
+    """Yields (users, pos, neg) device tensors for one pass over `dataloader`."""
+    if OPTIONS.sampler == "device":
+        ep = _device_epoch(dataloader, device)
+        pset = _positive_set(positives, num_items, device)
+        if ep is not None:
+            users, items, cuts = ep
+            # negatives of the whole epoch in ONE launch of the sampler kernel
+            neg = _sampler_mod.sample_negative_items(users, num_items=num_items, positives=pset,
+                                                     num_negatives=num_negatives, device=device) if users.numel() else None
+            for s, e in cuts:
+                yield users[s:e], items[s:e], neg[s:e]
+            return
+        for users, pos in dataloader:
+            users, pos = users.to(device), pos.to(device)
+            yield users, pos, _sampler_mod.sample_negative_items(users, num_items=num_items, positives=pset,
+                                                                 num_negatives=num_negatives, device=device)
+        return
+    # parity mode: the reference's DataLoader order and its per-row Python sampler, drawn on the CPU so that the global
+    # torch generator advances exactly as in a reference run with model.device == "cpu"
+    sample = OPTIONS.reference_sampler
+    if sample is None:
+        from src.data.samplers import sample_negative_items as sample  # the reference's, when importable
+    for users, pos in dataloader:
+        neg = sample(users.cpu(), num_items=num_items, positives=positives, num_negatives=num_negatives,
+                     device=torch.device("cpu"))
+        yield users.to(device), pos.to(device), neg.to(device)
+
+
+def _weighted_mean(losses, sizes) -> float:
+    if not losses:
+        return 0.0
+    per_step = torch.cat(losses).double().cpu().numpy()          # the epoch's only device -> host read
+    return float(np.dot(per_step, np.asarray(sizes, dtype=np.float64)) / max(int(np.sum(sizes)), 1))
 
 
 def _train_one_epoch(model, dataloader, *, optimizers, criterion, negatives_per_positive, num_items,
@@ -98,6 +213,7 @@ def _train_one_epoch(model, dataloader, *, optimizers, criterion, negatives_per_
         raise NotImplementedError("gradient clipping is not supported by the fused step (reference default: null)")
     if not isinstance(criterion, nn.BCEWithLogitsLoss):
         raise ValueError("the fused step implements nn.BCEWithLogitsLoss (reference training.py:1366) only")
+    import time
     model.train()
     eng = engine_for(model, optimizers)
     w = loss_weights or {}
@@ -105,80 +221,162 @@ def _train_one_epoch(model, dataloader, *, optimizers, criterion, negatives_per_
     eng.lambda_c = float(w.get("category_alignment", 0.0))
     eng.cat_tensor = None if item_category_tensor is None else item_category_tensor.to(device)
     eng.major = major_category_id
-    sample = _sampler()
+    graph = OPTIONS.graph
+    t0 = time.perf_counter()
     losses, sizes = [], []
-    for users, pos in dataloader:
-        users, pos = users.to(device), pos.to(device)
-        neg = sample(users, num_items=num_items, positives=user_positive_items,
-                     num_negatives=negatives_per_positive, device=device)
-        loss = eng.train_step(users, pos, neg, user_features, item_features)
-        losses.append(loss[0:1].clone())       # no host sync inside the loop (reference syncs per step, :830)
+    for users, pos, neg in _batches(dataloader, num_items=num_items, positives=user_positive_items,
+                                    num_negatives=negatives_per_positive, device=device):
+        loss = eng.train_step(users, pos, neg, user_features, item_features, graph=graph)
+        losses.append(loss[0:1].clone())       # no host sync inside the loop (the reference syncs per step, :830)
         sizes.append(users.shape[0])
     eng.flush()
     _publish_optimizer_state(eng, optimizers)
-    if not losses:
-        return 0.0
-    per_step = torch.cat(losses).double().cpu().numpy()
-    total = int(np.sum(sizes))
-    return float(np.dot(per_step, np.asarray(sizes, dtype=np.float64)) / max(total, 1))
+    out = _weighted_mean(losses, sizes)
+    if OPTIONS.stats is not None:
+        OPTIONS.stats["train_steps"] = OPTIONS.stats.get("train_steps", 0) + len(sizes)
+        OPTIONS.stats["train_samples"] = OPTIONS.stats.get("train_samples", 0) + (int(np.sum(sizes)) if sizes else 0)
+        OPTIONS.stats["train_seconds"] = OPTIONS.stats.get("train_seconds", 0.0) + (time.perf_counter() - t0)
+        OPTIONS.stats.setdefault("epoch_seconds", []).append(time.perf_counter() - t0)
+        OPTIONS.stats.setdefault("epoch_samples", []).append(int(np.sum(sizes)) if sizes else 0)
+    return out
 
 
 def _compute_loss(model, dataloader, *, criterion, negatives_per_positive, num_items, user_positive_items,
                   user_features, item_features, device) -> float:
     model.eval()
     eng = engine_for(model)
-    sample = _sampler()
     losses, sizes = [], []
-    for users, pos in dataloader:
-        users, pos = users.to(device), pos.to(device)
-        neg = sample(users, num_items=num_items, positives=user_positive_items,
-                     num_negatives=negatives_per_positive, device=device)
+    for users, pos, neg in _batches(dataloader, num_items=num_items, positives=user_positive_items,
+                                    num_negatives=negatives_per_positive, device=device):
         losses.append(eng.eval_loss(users, pos, neg, user_features, item_features)[1:2].clone())
         sizes.append(users.shape[0])
-    if not losses:
-        return 0.0
-    per_step = torch.cat(losses).double().cpu().numpy()
-    return float(np.dot(per_step, np.asarray(sizes, dtype=np.float64)) / max(int(np.sum(sizes)), 1))
+    return _weighted_mean(losses, sizes)
+
+
+# ------------------------------------------------------------------------------------------------
+# retrieval
+# ------------------------------------------------------------------------------------------------
+def _feat(t):
+    return t if (t is not None and t.numel() > 0) else None
 
 
 def _encode_item_embeddings(model, *, num_items, item_features, device, batch_size: int = 8192) -> torch.Tensor:
     if num_items == 0:
         return torch.empty((0, 0), dtype=torch.float32)
     model.eval()
-    eng = engine_for(model)
-    feats = item_features if (item_features is not None and item_features.numel() > 0) else None
-    return eng.encode_all("item", feats, chunk=max(int(batch_size), 65536)).cpu()
+    return engine_for(model).corpus(_feat(item_features)).cpu()
 
 
-def _evaluate_model(model, *, train_positive_map, val_interactions, item_feature_tensor, user_feature_tensor,
-                    device, num_items, candidate_samples, k_values: Iterable[int], rng, faiss_resources=None,
-                    faiss_search_k: int = 0):
-    """Exact full-corpus retrieval for every validation user (the FAISS branch's semantics; the sampling
-    branch is an approximation of it that exists only because FAISS is optional in the reference)."""
-    if val_interactions.empty:
-        return {}, {}
+class GpuFlatIndex:
+    """What `_prepare_faiss_resources` hands around in place of a `faiss.IndexFlatIP`: the encoded corpus resident in
+    HBM (FlatIPIndex) with the two members the reference touches, `search` and `ntotal`."""
+
+    def __init__(self, index: FlatIPIndex) -> None:
+        self.index = index
+        self.ntotal, self.d = index.ntotal, index.d
+
+    def search(self, queries, k: int):
+        q = torch.as_tensor(np.asarray(queries), dtype=torch.float32, device=self.index.items.device)
+        ids, scores = self.index.search(q, k)
+        return scores.cpu().numpy(), ids.cpu().numpy()
+
+
+def _prepare_faiss_resources(model, *, num_items, item_features, device, similarity_module, batch_size,
+                             retain_embeddings: bool = False):
+    if num_items == 0:
+        return None
     model.eval()
-    k_values = list(k_values)
     eng = engine_for(model)
+    corpus = eng.corpus(_feat(item_features))
+    if corpus.numel() == 0:
+        return None
+    normalize = isinstance(similarity_module, nn.CosineSimilarity)
+    index = FlatIPIndex(corpus, normalize=normalize)
+    payload = {"index": GpuFlatIndex(index), "normalize": normalize}
+    if retain_embeddings:
+        payload["embeddings"] = index.items.float().cpu().numpy()      # normalised when the reference normalises (:669-672)
+    return payload
+
+
+def _save_faiss_artifacts(resources, *, index_path, embedding_path) -> None:
+    """`item_embeddings.npy` exactly as the reference writes it (training.py:694-697).  The index file itself cannot be
+    a FAISS file without FAISS; `IndexFlatIP` holds nothing but the vectors, so downstream users rebuild it with
+    `index.add(np.load(embedding_path))`."""
+    if resources is None or resources.get("embeddings") is None:
+        return
+    from pathlib import Path
+    Path(embedding_path).parent.mkdir(parents=True, exist_ok=True)
+    np.save(embedding_path, resources["embeddings"])
+
+
+def _ground_truth(val_interactions):
     gts: dict[int, set[int]] = {}
     for user_idx, group in val_interactions.groupby("user_idx"):
         gt = set(map(int, group["item_idx"].tolist()))
         if gt:
             gts[int(user_idx)] = gt
+    return gts
+
+
+def _evaluate_model(model, *, train_positive_map, val_interactions, item_feature_tensor, user_feature_tensor,
+                    device, num_items, candidate_samples, k_values: Iterable[int], rng, faiss_resources=None,
+                    faiss_search_k: int = 0):
+    """Exact full-corpus retrieval for every validation user (the FAISS branch's semantics).  With
+    `eval_mode="reference"` and no FAISS resources - where the reference takes its candidate-sampling branch - the
+    candidates are drawn exactly as the reference draws them (same `rng` calls, training.py:979-985) and scored on the
+    device; the default `eval_mode="exact"` answers with exact retrieval there too (the sampling
+    branch only exists because FAISS is optional in the reference)."""
+    if val_interactions.empty:
+        return {}, {}
+    model.eval()
+    k_values = list(k_values)
+    eng = engine_for(model)
+    gts = _ground_truth(val_interactions)
     if not gts:
         return {}, {}
     users = list(gts)
-    ifeat = item_feature_tensor if (item_feature_tensor is not None and item_feature_tensor.numel() > 0) else None
-    ufeat = user_feature_tensor if (user_feature_tensor is not None and user_feature_tensor.numel() > 0) else None
-    corpus = eng.encode_all("item", ifeat)
+    corpus = eng.corpus(_feat(item_feature_tensor))
     cosine = isinstance(model.similarity, nn.CosineSimilarity)
-    if faiss_resources is not None and "normalize" in faiss_resources:
-        cosine = bool(faiss_resources["normalize"])
-    index = FlatIPIndex(corpus, normalize=cosine)
     uidx = torch.tensor(users, device=device, dtype=torch.long)
-    uemb = eng.encode("user", uidx, ufeat)
+    uemb = eng.encode("user", uidx, _feat(user_feature_tensor))
+    if faiss_resources is None and OPTIONS.eval_mode == "reference":
+        return _evaluate_by_sampling(corpus, uemb, users, gts, train_positive_map, num_items, candidate_samples,
+                                     max(k_values), rng, cosine), gts
+    index = None
+    if faiss_resources is not None:
+        cosine = bool(faiss_resources.get("normalize", cosine))
+        held = faiss_resources.get("index")
+        index = held.index if isinstance(held, GpuFlatIndex) else None
+    if index is None:
+        index = FlatIPIndex(corpus, normalize=cosine)
     preds = evaluate_users(index, uemb, users, gts, train_positive_map, k_values, search_k=int(faiss_search_k))
     return preds, gts
+
+
+def _evaluate_by_sampling(corpus, uemb, users, gts, train_positive_map, num_items, candidate_samples, max_k, rng, cosine):
+    """`_retrieve_with_sampling` (training.py:974-1009) for all users: the candidate lists are built on the host with the
+    reference's own statements (they define how `rng` is consumed), every (user, candidate) pair is scored by one launch,
+    the per-user top-k is taken under the canonical (-score, +position) order."""
+    lists = []
+    for u in users:
+        blocked = set(train_positive_map.get(int(u), set()))
+        candidates = set(gts[u])
+        available = list(set(range(num_items)) - blocked)
+        if available:
+            budget = max(0, min(candidate_samples, len(available)))
+            if budget > 0:
+                candidates.update(int(n) for n in rng.choice(available, size=budget, replace=False).tolist())
+        lists.append(list(candidates))
+    width = max(len(c) for c in lists)
+    cand = np.full((len(lists), width), -1, dtype=np.int64)
+    for r, c in enumerate(lists):
+        cand[r, :len(c)] = c
+    scores = score_candidates(uemb, corpus, torch.from_numpy(cand).to(corpus.device), cosine=cosine).cpu().numpy()
+    preds = {}
+    for r, (u, c) in enumerate(zip(users, lists)):
+        order = np.argsort(-scores[r, :len(c)], kind="stable")[: min(max_k, len(c))]
+        preds[u] = [c[i] for i in order]
+    return preds
 
 
 def _score_all_items_for_user(model, *, user_idx: int, top_k: int, num_items: int, user_features, item_features,
@@ -187,22 +385,43 @@ def _score_all_items_for_user(model, *, user_idx: int, top_k: int, num_items: in
         return []
     model.eval()
     eng = engine_for(model)
-    ifeat = item_features if (item_features is not None and item_features.numel() > 0) else None
-    ufeat = user_features if (user_features is not None and user_features.numel() > 0) else None
-    corpus = eng.encode_all("item", ifeat)
-    index = FlatIPIndex(corpus, normalize=isinstance(model.similarity, nn.CosineSimilarity))
-    q = eng.encode("user", torch.tensor([user_idx], device=device, dtype=torch.long), ufeat)
+    index = eng.corpus_index(_feat(item_features), normalize=isinstance(model.similarity, nn.CosineSimilarity))
+    q = eng.encode("user", torch.tensor([user_idx], device=device, dtype=torch.long), _feat(user_features))
     ids, _ = index.search(q, min(top_k, num_items))
     return ids[0].cpu().tolist()
 
 
-def install(training_module) -> None:
+class _FaissStandIn:
+    """Truthy placeholder for `training.faiss` when FAISS is not installed and eval_mode == "exact": keeps
+    `faiss_enabled` on (training.py:1408-1412) so that the corpus is encoded once per epoch by the hooked
+    `_prepare_faiss_resources` and shared by the validation and test evaluations.  Nothing of FAISS is called through it."""
+
+    def __getattr__(self, name):
+        raise AttributeError(f"faiss.{name} is not available: every FAISS call site of the reference is hooked")
+
+
+_HOOKED = ("_train_one_epoch", "_compute_loss", "_encode_item_embeddings", "_prepare_faiss_resources",
+           "_save_faiss_artifacts", "_evaluate_model", "_score_all_items_for_user")
+
+
+def install(training_module, *, precision: str = "tf32", graph: bool = True, sampler: str = "device",
+            eval_mode: str = "exact", stats: Optional[dict] = None) -> HookOptions:
     """Assign the fused implementations onto the reference's `src.pipelines.training` module and swap its
     model classes for the B200 ones; the reference file itself is untouched."""
     from . import models
-    for name in ("_train_one_epoch", "_compute_loss", "_encode_item_embeddings", "_evaluate_model",
-                 "_score_all_items_for_user"):
+    if precision not in ("tf32", "fp32"):
+        raise ValueError("precision must be 'tf32' or 'fp32'")
+    if sampler not in ("device", "reference"):
+        raise ValueError("sampler must be 'device' or 'reference'")
+    if eval_mode not in ("exact", "reference"):
+        raise ValueError("eval_mode must be 'exact' or 'reference'")
+    OPTIONS.precision, OPTIONS.graph, OPTIONS.sampler, OPTIONS.eval_mode, OPTIONS.stats = precision, bool(graph), sampler, eval_mode, stats
+    OPTIONS.reference_sampler = getattr(training_module, "sample_negative_items", None)
+    for name in _HOOKED:
         setattr(training_module, name, globals()[name])
     for name in ("AdaptiveMimicMechanism", "TwoTowerModel", "build_tower_encoder"):
         if hasattr(training_module, name):
             setattr(training_module, name, getattr(models, name))
+    if eval_mode == "exact" and getattr(training_module, "faiss", None) is None:
+        training_module.faiss = _FaissStandIn()
+    return OPTIONS

@@ -39,19 +39,54 @@ class FlatIPIndex:
         self.items = x.contiguous() if dtype == torch.float32 else F.cast_bf16(x.contiguous())
         self.ntotal, self.d = self.items.shape
 
-    def search(self, queries: torch.Tensor, k: int):
-        """queries [Q, D] -> (ids [Q, k] int64, scores [Q, k] fp32); missing slots (k > ntotal) hold id -1."""
+    @property
+    def max_k(self) -> int:
+        """Largest k one launch sequence returns (deeper rankings: `search(..., after=)` page by page, fp32 only)."""
+        return F.TOPK_F32_MAX_K if self.dtype == torch.float32 else F.TOPK_BF16_MAX_K
+
+    def _prepare(self, queries: torch.Tensor) -> torch.Tensor:
         q = queries.float()
         if self.normalize:
             q = l2_normalize(q)
-        q = q.contiguous() if self.dtype == torch.float32 else F.cast_bf16(q.contiguous())
+        return q.contiguous() if self.dtype == torch.float32 else F.cast_bf16(q.contiguous())
+
+    def search(self, queries: torch.Tensor, k: int, *, after=None):
+        """queries [Q, D] -> (ids [Q, k] int64, scores [Q, k] fp32); missing slots (k > ntotal) hold id -1.
+        after = (scores [Q], ids [Q]): only results ranked strictly after that pair (fp32 index)."""
+        q = self._prepare(queries)
         k_eff = min(int(k), self.ntotal)
-        ids, scores = F.topk(q, self.items, k_eff, id_offset=self.id_offset)
+        ids, scores = F.topk(q, self.items, k_eff, id_offset=self.id_offset, after=after)
         if k_eff < k:
             pad_i = torch.full((q.shape[0], k - k_eff), -1, dtype=torch.int64, device=q.device)
             pad_s = torch.full((q.shape[0], k - k_eff), float("-inf"), dtype=torch.float32, device=q.device)
             ids, scores = torch.cat([ids, pad_i], 1), torch.cat([scores, pad_s], 1)
         return ids, scores
+
+
+    def search_deep(self, queries: torch.Tensor, k: int):
+        """`search` for k beyond `max_k`: the ranking is walked down page by page (each page = one launch sequence that
+        only admits items ranked after the previous page's last result).  Returns (ids, scores) as numpy [Q, k]."""
+        k = min(int(k), self.ntotal)
+        page = min(k, self.max_k)
+        ids, scores = self.search(queries, page)
+        out_i, out_s = [ids], [scores]
+        got = page
+        if got < k and self.dtype != torch.float32:
+            raise F._lib.TtamError(f"a ranking deeper than {self.max_k} needs an fp32 index (dtype=torch.float32)")
+        while got < k:
+            ids, scores = self.search(queries, min(self.max_k, k - got), after=(out_s[-1][:, -1], out_i[-1][:, -1]))
+            out_i.append(ids); out_s.append(scores)
+            got += ids.shape[1]
+        return torch.cat(out_i, 1).cpu().numpy(), torch.cat(out_s, 1).cpu().numpy()
+
+
+def score_candidates(queries: torch.Tensor, corpus: torch.Tensor, cand: torch.Tensor, *, cosine: bool = False) -> torch.Tensor:
+    """scores [R, C] of query r against corpus[cand[r, c]] (-inf where cand < 0): the scoring half of the reference's
+    candidate-sampling evaluation (training.py:986-1005); with `cosine` both sides are L2-normalised first (:999-1003)."""
+    q, it = queries.float(), corpus.float()
+    if cosine:
+        q, it = l2_normalize(q), l2_normalize(it)
+    return F.score_pairs(q, it, cand)
 
 
 def filter_candidates(candidate_ids: list[int], blocked: set[int], ground_truth: set[int], max_k: int) -> list[int]:
@@ -74,14 +109,17 @@ def filter_candidates(candidate_ids: list[int], blocked: set[int], ground_truth:
 
 
 def filter_block(ids: np.ndarray, need: Sequence[int], users: Sequence[int], ground_truth: Mapping[int, set],
-                 train_positive_map: Mapping[int, set], max_k: int) -> dict:
+                 train_positive_map: Mapping[int, set], max_k: int, deeper=None) -> dict:
     """`filter_candidates` for a whole block of users at once (the reference filters one user per Python
     iteration, training.py:959-972).  ids [n, K] int64: row r holds user users[r]'s candidates, best first (-1 = none);
     only its first need[r] columns count (the reference asks FAISS for search_k = need[r] results).
     Rows that keep at least max_k candidates - nearly all of them - are handled by array operations: blocked-item
     membership is one searchsorted over (row, item) keys, the survivors' first max_k columns one stable argsort.  Rows
     that keep fewer (their ground truth gets appended) or repeat an id go through `filter_candidates` itself, so the
-    result is the reference's for every row."""
+    result is the reference's for every row.
+    deeper(r, k) -> list of row r's first k candidates: called for the rare row that keeps fewer than max_k of its K
+    columns although the reference would have asked for more than K results (a user with more training positives than
+    one launch returns)."""
     ids = np.asarray(ids, dtype=np.int64)
     n, K = ids.shape
     need = np.asarray(need, dtype=np.int64).reshape(n, 1)
@@ -111,7 +149,9 @@ def filter_block(ids: np.ndarray, need: Sequence[int], users: Sequence[int], gro
         if fast[r]:
             out[u] = sel[r].tolist()
         else:
-            out[u] = filter_candidates(ids[r, : int(need[r, 0])].tolist(), set(train_positive_map.get(u, ())), ground_truth[u], max_k)
+            k_r = int(need[r, 0])
+            row = ids[r, :k_r].tolist() if (k_r <= K or deeper is None) else deeper(r, k_r)
+            out[u] = filter_candidates(row, set(train_positive_map.get(u, ())), ground_truth[u], max_k)
     return out
 
 
@@ -126,7 +166,12 @@ def evaluate_users(index: FlatIPIndex, user_embeddings: torch.Tensor, user_ids: 
     for s in range(0, len(user_ids), query_block):
         blk = user_ids[s:s + query_block]
         need = [max(search_k, max(max_k + len(ground_truth[u]), 1) + len(train_positive_map.get(u, ()))) for u in blk]
-        k_blk = min(max(need), index.ntotal)
-        ids, _ = index.search(user_embeddings[s:s + len(blk)], k_blk)
-        preds.update(filter_block(ids.cpu().numpy(), need, blk, ground_truth, train_positive_map, max_k))
+        # one launch returns at most index.max_k results per query; search_k grows with a user's number of training
+        # positives (training.py:956-958), so a heavy user can ask for more: such a row is only walked further down
+        # (search_deep) when its first max_k columns do not already hold max_k unblocked items
+        k_blk = min(max(need), index.ntotal, index.max_k)
+        q_blk = user_embeddings[s:s + len(blk)]
+        ids, _ = index.search(q_blk, k_blk)
+        deeper = lambda r, k, q_blk=q_blk: index.search_deep(q_blk[r:r + 1], k)[0][0].tolist()
+        preds.update(filter_block(ids.cpu().numpy(), need, blk, ground_truth, train_positive_map, max_k, deeper=deeper))
     return preds

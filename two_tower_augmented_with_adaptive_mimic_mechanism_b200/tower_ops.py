@@ -108,6 +108,8 @@ def _buf(bufs, name, shape, device):
             # grow with headroom: the row count of a row-sharded step changes a little from step to step, and every
             # reallocation is a cudaMalloc + synchronisation
             rows = shape[0] if t is None and shape[0] < 4096 else _headroom(shape[0])
+            if t is not None:
+                F.note_realloc()       # captured graphs that address the old buffer are stale from here on
             t = torch.empty((rows,) + tuple(shape[1:]), dtype=torch.float32, device=device)
             bufs[name] = t
         return t[: shape[0]]
