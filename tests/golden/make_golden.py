@@ -90,12 +90,12 @@ def _fake_faiss():
     return mod
 
 
-def _tower_cfg(D, H, Hg, fe_type="mlp", fusion="gated", sparse=True, dropout=0.0):
+def _tower_cfg(D, H, Hg, fe_type="mlp", fusion="gated", sparse=True, dropout=0.0, activation="relu"):
     cfg = {
         "type": "tower",
         "id_embedding": {"params": {"embedding_dim": D, "sparse": sparse}, "init": {"type": "normal", "std": 0.02}},
         "feature_encoder": {"type": fe_type, "hidden_dims": [H] if fe_type == "mlp" else None,
-                            "activation": "relu", "output_dim": D, "dropout": dropout},
+                            "activation": activation, "output_dim": D, "dropout": dropout},
         "fusion": fusion,
         "output_dim": D,
     }
@@ -124,7 +124,7 @@ def _state_np(module):
 def make_train_case(name, *, seed, NU, NI, D, H, Hg, n_cat, n_auth, n_dense, B, N, steps,
                     optimizer="adamw", lr=1e-3, wd=0.01, betas=(0.9, 0.999), lambdas=(0.15, 0.15, 0.0),
                     fe_type="mlp", fusion="gated", mimic=True, sparse=True, tower_type="tower",
-                    momentum=0.0, with_eval=False, similarity="dot"):
+                    momentum=0.0, with_eval=False, similarity="dot", activation="relu"):
     import torch
     from torch import nn
 
@@ -146,8 +146,8 @@ def make_train_case(name, *, seed, NU, NI, D, H, Hg, n_cat, n_auth, n_dense, B, 
         ue = models.build_tower_encoder(ucfg, num_embeddings=NU, feature_dim=F, device=device)
         ie = models.build_tower_encoder(icfg, num_embeddings=NI, feature_dim=F, device=device)
     else:
-        ue = models.build_tower_encoder(_tower_cfg(D, H, Hg, fe_type, fusion, sparse), num_embeddings=NU, feature_dim=F, device=device)
-        ie = models.build_tower_encoder(_tower_cfg(D, H, Hg, fe_type, fusion, sparse), num_embeddings=NI, feature_dim=F, device=device)
+        ue = models.build_tower_encoder(_tower_cfg(D, H, Hg, fe_type, fusion, sparse, activation=activation), num_embeddings=NU, feature_dim=F, device=device)
+        ie = models.build_tower_encoder(_tower_cfg(D, H, Hg, fe_type, fusion, sparse, activation=activation), num_embeddings=NI, feature_dim=F, device=device)
     mm = models.AdaptiveMimicMechanism(num_users=NU, num_items=NI, embedding_dim=D, init_std=0.02) if mimic else None
     sim = training._select_similarity(similarity)
     model = models.TwoTowerModel(ue, ie, similarity=sim, adaptive_mimic=mm)
@@ -367,6 +367,8 @@ def main():
     make_train_case("train_dense_adam", seed=12, D=16, H=32, Hg=None, optimizer="adam", sparse=False, **common)
     make_train_case("train_sgd", seed=13, D=16, H=32, Hg=None, optimizer="sgd", momentum=0.9, **common)
     make_train_case("train_linear_sum", seed=14, D=16, H=None, Hg=None, fe_type="linear", fusion="sum", **common)
+    # concat fusion (+ projection, encoders.py:211-217,242-244) with a GELU feature MLP (encoders.py:68-78)
+    make_train_case("train_concat_gelu", seed=15, D=16, H=32, Hg=None, fusion="concat", activation="gelu", **common)
     make_optimizer_case()
     make_metrics_case()
 

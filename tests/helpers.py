@@ -16,6 +16,7 @@ TRAIN_CASES = {
     "train_dense_adam": dict(optimizer="adam", sparse=False),
     "train_sgd": dict(optimizer="sgd"),
     "train_linear_sum": dict(optimizer="adamw", fusion="sum"),
+    "train_concat_gelu": dict(optimizer="adamw", fusion="concat", activation="gelu"),
 }
 
 
@@ -48,7 +49,7 @@ def tower_cfg(meta, kw, state, side):
     cfg = {"type": "tower",
            "id_embedding": {"params": {"embedding_dim": D, "sparse": sparse}},
            "feature_encoder": {"type": fe_type, "hidden_dims": [H] if fe_type == "mlp" else None,
-                               "activation": "relu", "output_dim": D, "dropout": 0.0},
+                               "activation": kw.get("activation", "relu"), "output_dim": D, "dropout": 0.0},
            "fusion": kw.get("fusion", "gated"), "output_dim": D}
     if Hg:
         cfg["adaptive_mimic"] = {"hidden_dim": Hg}

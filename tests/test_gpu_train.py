@@ -74,7 +74,10 @@ def test_train_one_epoch_hook_replays_reference_golden(monkeypatch):
     steps = meta["steps"]
     batches = [(torch.from_numpy(d[f"step{s}/users"]), torch.from_numpy(d[f"step{s}/pos"])) for s in range(steps)]
     negs = iter([torch.from_numpy(d[f"step{s}/neg"]).cuda() for s in range(steps)])
-    monkeypatch.setattr(tt.hooks, "_sampler", lambda: (lambda users, **kw: next(negs)))
+    monkeypatch.setattr(tt.hooks.OPTIONS, "sampler", "reference")       # the caller's DataLoader order + its sampler:
+    monkeypatch.setattr(tt.hooks.OPTIONS, "reference_sampler", lambda users, **kw: next(negs))   # here a replay
+    monkeypatch.setattr(tt.hooks.OPTIONS, "precision", "fp32")
+    monkeypatch.setattr(tt.hooks.OPTIONS, "graph", False)
     lu, li, _ = meta["lambdas"]
     ux, ix = torch.from_numpy(d["user_x"]).cuda(), torch.from_numpy(d["item_x"]).cuda()
     mean_loss = tt.hooks._train_one_epoch(model, batches, optimizers=opts, criterion=nn.BCEWithLogitsLoss(),
@@ -124,7 +127,7 @@ def _synthetic(seed, NU, NI, D, H, Hg, F, B, N):
 
 
 @pytest.mark.parametrize("D,H,Hg,F,B,graph", [(96, 192, 96, 605, 512, False), (128, 256, 128, 64, 256, False),
-                                              (96, 192, 96, 608, 512, True)])
+                                              (96, 192, 96, 608, 512, True), (256, 512, 256, 605, 384, False)])
 def test_fused_step_matches_oracle_at_tower_shapes(D, H, Hg, F, B, graph):
     """North-star tower shapes (96-dim, 192->96 MLP, F=605), duplicate-heavy Zipf positives, 3 steps, and the same
     steps replayed from a captured CUDA graph."""
@@ -157,14 +160,14 @@ def test_fused_step_matches_oracle_at_tower_shapes(D, H, Hg, F, B, graph):
     np.testing.assert_allclose(a1, a0 * np.float32(1 - 1e-3 * 0.01) ** 3, rtol=1e-6)
 
 
-@pytest.mark.parametrize("graph", [False, True])
-def test_fused_step_tf32_tensor_cores_within_tolerance(graph):
+@pytest.mark.parametrize("graph,D,H,Hg", [(False, 96, 192, 96), (True, 96, 192, 96), (False, 256, 512, 256), (False, 128, 256, 128)])
+def test_fused_step_tf32_tensor_cores_within_tolerance(graph, D, H, Hg):
     """The same three steps with every tower GEMM on the tcgen05 TF32 path.  Stated tolerance: losses rel 2e-3; updated
     parameters: mean |diff| <= 2e-5, at most 0.1 % of the elements off by more than 3e-4 per step, none by more than
     2.5 lr per step (Adam normalises every update to ~lr = 1e-3, so where a gradient is ~0 a rounding-level
     disagreement about it moves the weight by up to ~lr: the update is ill-conditioned there, in any precision);
     touched-row index sets bit-exact."""
-    NU, NI, N, D, H, Hg, F, B = 3000, 5000, 5, 96, 192, 96, 605, 512
+    NU, NI, N, F, B = 3000, 5000, 5, 605, 512
     st, user_x, item_x, batches = _synthetic(7, NU, NI, D, H, Hg, F, B, N)
     meta = dict(NU=NU, NI=NI, D=D, H=H, Hg=Hg, F=F, lr=1e-3, wd=0.01, momentum=0.0, betas=(0.9, 0.999), lambdas=(0.15, 0.15, 0.0))
     kw = dict(optimizer="adamw")
@@ -189,6 +192,30 @@ def test_fused_step_tf32_tensor_cores_within_tolerance(graph):
     touched = np.unique(np.concatenate([b[0] for b in batches]))
     changed = np.nonzero((got["user_encoder.embedding.weight"] != st["user_encoder.embedding.weight"]).any(1))[0]
     assert np.array_equal(changed, touched)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_fused_step_concat_gelu_golden(precision):
+    """Concat fusion + projection with a GELU feature MLP (the non-composite launch sequence) against the golden the
+    unmodified reference produced; TF32 variant within the stated TF32 tolerance."""
+    name = "train_concat_gelu"
+    d, meta, init = load_case(name)
+    kw = TRAIN_CASES[name]
+    model = build_model(meta, kw, init, "cuda")
+    eng = _engine(model, meta, kw, precision=precision)
+    ux, ix = torch.from_numpy(d["user_x"]).cuda(), torch.from_numpy(d["item_x"]).cuda()
+    for s in range(meta["steps"]):
+        u, p, n = (torch.from_numpy(d[f"step{s}/{k}"]).cuda() for k in ("users", "pos", "neg"))
+        loss = eng.train_step(u, p, n, ux, ix)
+        assert float(loss[0]) == pytest.approx(float(d["losses"][s]), rel=5e-6 if precision == "fp32" else 2e-3)
+    eng.flush()
+    got, ref = model_state_np(model), state_after(d, meta["steps"] - 1)
+    assert set(got) == set(ref)
+    for k in ref:
+        if precision == "fp32":
+            np.testing.assert_allclose(got[k], ref[k], rtol=RTOL, atol=ATOL, err_msg=k)
+        else:
+            assert np.abs(got[k] - ref[k]).mean() <= 2e-5, k
 
 
 def test_dropout_training_step_runs_and_differs_per_step():

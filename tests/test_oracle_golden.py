@@ -14,7 +14,7 @@ def test_train_steps_match_reference(name):
     d, meta, state = load_case(name)
     kw = TRAIN_CASES[name]
     spec = oracle.spec_from_state(state, fusion_user=kw.get("fusion"), fusion_item=kw.get("fusion"),
-                                  sparse=kw.get("sparse", True))
+                                  sparse=kw.get("sparse", True), activation=kw.get("activation", "relu"))
     opt = oracle.OptState()
     for s in range(meta["steps"]):
         out = oracle.train_step(state, opt, spec, d[f"step{s}/users"], d[f"step{s}/pos"], d[f"step{s}/neg"],
