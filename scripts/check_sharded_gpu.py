@@ -1,6 +1,7 @@
 """torchrun -N ranks (NCCL, one GPU each): the row-sharded step on the real kernels, every route
 (dynamic / static / peer), against the golden fixtures produced by the unmodified reference
-(tests/golden/train_gated_mlp.npz, train_embedding_only.npz).
+(tests/golden/train_gated_mlp.npz, train_embedding_only.npz), and at tower shapes (D = 96, F = 605, 192 -> 96 MLPs,
+B = 128 samples per rank, TF32 tensor-core GEMMs as in the bench) against the numpy oracle's un-sharded step.
 
 Each rank holds rows r % W == rank of the four tables and of the feature matrices, takes B/W samples of every golden
 batch, and runs ShardedEngine.train_step; the un-sharded result must match the reference state after the last step
@@ -17,7 +18,7 @@ import torch.distributed as dist
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "tests"))
-from helpers import TRAIN_CASES, build_model, load_case, state_after  # noqa: E402
+from helpers import TRAIN_CASES, build_model, load_case, state_after, synthetic_gated  # noqa: E402
 
 TABLES = ("user_encoder.embedding.weight", "item_encoder.embedding.weight",
           "adaptive_mimic.user_augmented.weight", "adaptive_mimic.item_augmented.weight")
@@ -89,10 +90,67 @@ def main():
                       f"{'OK' if int(flag) == 0 else 'MISMATCH'} (worst margin {worst:.2e})", flush=True)
             bad += int(flag)
             del sh, eng, model
+    bad += tower_shape_case(tt, S, rank, world, dev)
     dist.barrier()
     torch.cuda.synchronize()
     sys.stdout.flush()
     os._exit(1 if bad else 0)
+
+
+def tower_shape_case(tt, S, rank, world, dev) -> int:
+    """North-star tower shapes on the routes the bench uses (peer when world > 1, static otherwise), precision tf32 and fp32:
+    W ranks x 128 samples against the oracle's step on the whole batch."""
+    import oracle
+    NU, NI, D, H, Hg, F, N, steps = 3000, 5000, 96, 192, 96, 605, 5, 3
+    B = 128 * world
+    st, user_x, item_x, batches = synthetic_gated(7, NU, NI, D, H, Hg, F, B, N, steps=steps)
+    ref_state = {k: v.copy() for k, v in st.items()}
+    spec, opt = oracle.spec_from_state(ref_state), oracle.OptState()
+    ref_losses = [oracle.train_step(ref_state, opt, spec, u, p, n, user_x, item_x, lr=1e-3, weight_decay=0.01,
+                                    lambdas=(0.15, 0.15, 0.0))["loss"] for u, p, n in batches]
+    bad = 0
+    for precision, ltol, mean_tol in (("fp32", 5e-6, 2e-7), ("tf32", 2e-3, 2e-5)):
+        meta = dict(NU=S.shard_size(NU, rank, world), NI=S.shard_size(NI, rank, world), D=D, H=H, Hg=Hg, F=F)
+        shard = {k: (np.ascontiguousarray(v[rank::world]) if k in TABLES else v) for k, v in st.items()}
+        model = build_model(meta, dict(optimizer="adamw"), shard, dev)
+        eng = tt.FusedEngine(model, optimizer="adamw", lr=1e-3, weight_decay=0.01, precision=precision,
+                             loss_weights={"mimic_user": 0.15, "mimic_item": 0.15}, max_steps=64)
+        sh = tt.ShardedEngine(eng, static=True, peer=world > 1)
+        ux = S.shard_rows(torch.from_numpy(user_x), rank, world).to(dev)
+        ix = S.shard_rows(torch.from_numpy(item_x), rank, world).to(dev)
+        ok = True
+        for s, (u, p, n) in enumerate(batches):
+            sl = slice(rank * 128, (rank + 1) * 128)
+            share = sh.train_step(torch.from_numpy(u[sl]).to(dev), torch.from_numpy(p[sl]).to(dev), torch.from_numpy(n[sl]).to(dev),
+                                  ux, ix, graph=True)
+            loss = float(sh.global_loss(share)[0])
+            if abs(loss - ref_losses[s]) > ltol * abs(ref_losses[s]):
+                ok = False
+                print(f"[rank {rank}] tower shapes {precision} step {s}: loss {loss} != {ref_losses[s]}", flush=True)
+        eng.flush()
+        torch.cuda.synchronize()
+        worst = 0.0
+        for k, v in model.state_dict().items():
+            want = ref_state[k][rank::world] if k in TABLES else ref_state[k]
+            worst = max(worst, float(np.abs(v.detach().cpu().numpy() - want).mean()))
+        if worst > mean_tol:
+            ok = False
+            print(f"[rank {rank}] tower shapes {precision}: parameters mean |diff| {worst:.3e} > {mean_tol}", flush=True)
+        # bit-exact: the rows of the sparse user table this rank changed are exactly the users of the batches it owns
+        touched = np.unique(np.concatenate([b[0] for b in batches]))
+        mine = touched[touched % world == rank] // world
+        changed = np.nonzero((model.state_dict()["user_encoder.embedding.weight"].cpu().numpy() != shard["user_encoder.embedding.weight"]).any(1))[0]
+        if not np.array_equal(changed, mine):
+            ok = False
+            print(f"[rank {rank}] tower shapes {precision}: touched-row set differs", flush=True)
+        flag = torch.tensor([0 if ok else 1], device=dev)
+        dist.all_reduce(flag)
+        if rank == 0:
+            print(f"{'tower_shapes_' + precision:24s} {'peer' if sh.peer else 'static':8s} world={world} fallback_steps={sh.fallback_steps} "
+                  f"{'OK' if int(flag) == 0 else 'MISMATCH'} (params mean |diff| {worst:.2e})", flush=True)
+        bad += int(flag)
+        del sh, eng, model
+    return bad
 
 
 if __name__ == "__main__":

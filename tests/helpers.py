@@ -36,6 +36,35 @@ def state_after(d, step):
     return {k[len(pre):]: v for k, v in d.items() if k.startswith(pre)}
 
 
+def synthetic_gated(seed, NU, NI, D, H, Hg, F, B, N, steps=3):
+    """Seeded gated-MLP model state (reference key layout), feature matrices in the reference's column layout and `steps`
+    batches with Zipf positives (duplicate-heavy) at caller-chosen tower shapes."""
+    rng = np.random.default_rng(seed)
+    st = {}
+    for side, n in (("user", NU), ("item", NI)):
+        pre = f"{side}_encoder."
+        st[pre + "embedding.weight"] = (rng.standard_normal((n, D)) * 0.02).astype(np.float32)
+        st[pre + "feature_encoder.network.0.weight"] = (rng.standard_normal((H, F)) * np.sqrt(2.0 / (H + F))).astype(np.float32)
+        st[pre + "feature_encoder.network.0.bias"] = (rng.standard_normal(H) * 0.05).astype(np.float32)
+        st[pre + "feature_encoder.network.2.weight"] = (rng.standard_normal((D, H)) * np.sqrt(2.0 / (H + D))).astype(np.float32)
+        st[pre + "feature_encoder.network.2.bias"] = (rng.standard_normal(D) * 0.05).astype(np.float32)
+        st[pre + "adaptive_mimic.gate_network.0.weight"] = (rng.standard_normal((Hg, 2 * D)) * np.sqrt(2.0 / (Hg + 2 * D))).astype(np.float32)
+        st[pre + "adaptive_mimic.gate_network.0.bias"] = (rng.standard_normal(Hg) * 0.05).astype(np.float32)
+        st[pre + "adaptive_mimic.gate_network.2.weight"] = (rng.standard_normal((D, Hg)) * np.sqrt(2.0 / (Hg + D))).astype(np.float32)
+        st[pre + "adaptive_mimic.gate_network.2.bias"] = (rng.standard_normal(D) * 0.05).astype(np.float32)
+        st[f"adaptive_mimic.{side}_augmented.weight"] = (rng.standard_normal((n, D)) * 0.02).astype(np.float32)
+    item_x = np.zeros((NI, F), dtype=np.float32)
+    for r in range(NI):
+        item_x[r, rng.choice(F - 5, size=3, replace=False)] = (1.0, 0.5, 1.0)
+    item_x[:, F - 5:] = rng.standard_normal((NI, 5)).astype(np.float32)
+    user_x = np.stack([item_x[rng.integers(0, NI, size=4)].mean(0) for _ in range(NU)]).astype(np.float32)
+    pop = 1.0 / np.arange(1, NI + 1) ** 1.05
+    pop /= pop.sum()
+    batches = [(rng.integers(0, NU, size=B).astype(np.int64), rng.choice(NI, size=B, p=pop).astype(np.int64),
+                rng.integers(0, NI, size=(B, N)).astype(np.int64)) for _ in range(steps)]
+    return st, user_x, item_x, batches
+
+
 # ---------------------------------------------------------------------------------------------
 # GPU-side helpers (import torch lazily so that the CPU-only oracle tests stay light)
 # ---------------------------------------------------------------------------------------------
