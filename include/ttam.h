@@ -152,6 +152,11 @@ typedef struct {
   int32_t x_rounded, w1_rounded; /* X / W1 hold TF32-representable values (see TTAM_PREC_X_ROUNDED) */
   uint64_t seed, rng_base;
   const ttam_step_state* state;
+  /* bag form of X (null rowptr: dense layer 1): see ttam_bag_linear_fwd */
+  const int64_t* bag_rowptr;
+  const void* bag_entries;
+  const float* bag_tail;
+  int64_t bag_T, bag_tail_start;
 } ttam_tower_desc;
 typedef struct { float *z, *hd, *a, *pre2, *g, *t, *o, *q; } ttam_tower_bufs;
 typedef struct {
@@ -165,6 +170,29 @@ int ttam_tower_fwd(const ttam_tower_desc* d, const int64_t* idx, int64_t R, cons
 int64_t ttam_tower_bwd_workspace_bytes(const ttam_tower_desc* d, int64_t R);
 int ttam_tower_bwd(const ttam_tower_desc* d, const int64_t* idx, int64_t R, const ttam_tower_bufs* bufs, const float* dt,
                    const ttam_tower_grads* grads, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- bag form of the first feature-encoder layer (the "EmbeddingBag" restatement of index_select + nn.Linear(F, H):
+ * training.py:743-775 + encoders.py:133; feature layout features.py:242-252) ------------------------------------
+ * The feature matrix X [N, F] is held as CSR over its sparse columns [0, tail_start): rowptr int64 [N+1], entries
+ * packed 8-byte pairs {int32 column, fp32 value} in column order, at most 64 per row - plus a dense block tail [N, T]
+ * (T <= 8, tail_start + T == F) for the trailing columns that are non-zero in most rows (z-scored numerics).
+ *   ttam_bag_linear_fwd  : y[r, :] = act(b + sum_j x_j W[:, j]) for x = X[gather[r]] (gather null: row r), fp32 FMA,
+ *                          optional Philox dropout (same element numbering as ttam_linear_fwd) and, when
+ *                          round_tf32_out != 0, y rounded to TF32 (its consumer is a tensor-core GEMM that skips its
+ *                          own rounding pass).  w is the nn.Linear weight [H, F] with row stride ldw.
+ *   ttam_bag_linear_wgrad: dw[h, j] (+)= sum_r dh[r, h] x_j(r), db[h] (+)= sum_r dh[r, h].  Deterministic (no atomics).
+ * Supported when ttam_bag_supported(H, F, T) != 0 (H % 32 == 0, F*32*4 <= 172 kB); both take
+ * ttam_bag_linear_workspace_bytes(R, H, F) bytes of scratch. */
+int ttam_bag_supported(int64_t H, int64_t F, int64_t T);
+int64_t ttam_bag_linear_workspace_bytes(int64_t R, int64_t H, int64_t F);
+int ttam_bag_linear_fwd(const int64_t* rowptr, const void* entries, const float* tail, int64_t T, int64_t tail_start,
+                        const int64_t* gather, int64_t R, const float* w, int64_t ldw, const float* bias, float* y,
+                        int64_t ldy, int64_t H, int64_t F, int act, float dropout_p, uint64_t seed, uint64_t offset,
+                        const void* state_dev, int round_tf32_out, void* workspace, int64_t workspace_bytes, void* stream);
+int ttam_bag_linear_wgrad(const int64_t* rowptr, const void* entries, const float* tail, int64_t T, int64_t tail_start,
+                          const int64_t* gather, int64_t R, const float* dh, int64_t lddh, float* dw, int64_t lddw,
+                          float* db, int64_t H, int64_t F, int accumulate, void* workspace, int64_t workspace_bytes,
+                          void* stream);
 
 /* ---- fused loss forward+backward (training.py:770-803, adaptive_mimic.py:59-68) -------------------
  * o_u[B,D], o_i[(1+N)B,D] (positives first, then negatives row-major [B,N]); t_u,t_p[B,D] base tower

@@ -536,3 +536,83 @@ def test_slot_ids_equals_all_to_all_of_send_idx():
     F.slot_ids([d.data_ptr() + me * cap * 8 for d in dev], cap, recv, rows)
     want = torch.cat([s.view(W, cap)[me] for s in send])
     assert torch.equal(recv.cpu(), want) and torch.equal(rows.cpu(), want // W)
+
+
+# ---- bag form of layer 1 (csrc/bag.cu): the "EmbeddingBag" restatement of index_select + nn.Linear ----------------
+def _sparse_features(rng, n, F, nnz_lo, nnz_hi, tail):
+    """Reference feature layout (features.py:242-252): multi-hot columns with weights 1 / 0.5, then `tail` dense columns."""
+    x = np.zeros((n, F), dtype=np.float32)
+    for r in range(n):
+        k = int(rng.integers(nnz_lo, nnz_hi + 1))
+        if k:
+            x[r, rng.choice(F - tail, size=k, replace=False)] = rng.choice([1.0, 0.5, 0.125], size=k)
+    if tail:
+        x[:, F - tail:] = rng.standard_normal((n, tail)).astype(np.float32)
+    return x
+
+
+@pytest.mark.parametrize("R,H,Fd,nnz,tail,act", [(1000, 192, 605, (2, 5), 5, "relu"), (8192, 192, 605, (20, 45), 5, "relu"),
+                                                (49152, 192, 605, (2, 5), 5, "relu"), (77, 32, 21, (0, 3), 5, "none"),
+                                                (513, 256, 418, (0, 64), 0, "relu"), (300, 512, 605, (1, 9), 8, "none"),
+                                                (1, 64, 40, (3, 3), 2, "relu"), (0, 64, 40, (3, 3), 2, "relu")])
+def test_bag_linear_fwd_and_wgrad_match_dense_product(F, R, H, Fd, nnz, tail, act):
+    """Oracle = the dense product the reference computes (encoders.py:133 on X.index_select(0, idx)), in float64.
+    fp32 FMA over the row's non-zeros: |err| <= 1e-6 * sum |x_j||w_j| (+ bias); weight gradient likewise over the rows."""
+    rng = np.random.default_rng(R + H)
+    NI = 3000
+    X = _sparse_features(rng, NI, Fd, nnz[0], nnz[1], tail)
+    W = (rng.standard_normal((H, Fd)) / np.sqrt(8)).astype(np.float32)
+    b = (rng.standard_normal(H) * 0.1).astype(np.float32)
+    pop = 1.0 / np.arange(1, NI + 1) ** 1.05
+    idx = rng.choice(NI, size=R, p=pop / pop.sum()).astype(np.int64)       # duplicate-heavy, like the positives
+    bag = F.BagMatrix.build(dev(X))
+    assert bag is not None and bag.T == tail and F.bag_supported(H, Fd, bag.T)
+    y = F.bag_linear_fwd(bag, dev(idx), dev(W), dev(b), act=act).cpu().numpy()
+    xr = X[idx].astype(np.float64)
+    ref = xr @ W.astype(np.float64).T + b
+    bound = 2e-6 * (np.abs(xr) @ np.abs(W.astype(np.float64)).T + np.abs(b)) + 1e-7
+    if act == "relu":
+        ref = np.maximum(ref, 0)
+    assert y.shape == (R, H) and np.all(np.abs(y - ref) <= bound)
+    if R == 0:
+        return
+    dh = (rng.standard_normal((R, H)) * 1e-3).astype(np.float32)
+    dw, db = F.bag_linear_wgrad(bag, dev(idx), dev(dh))
+    ref_w = dh.astype(np.float64).T @ xr
+    bound_w = 4e-6 * (np.abs(dh.astype(np.float64)).T @ np.abs(xr)) + 1e-9
+    assert np.all(np.abs(dw.cpu().numpy() - ref_w) <= bound_w)
+    np.testing.assert_allclose(db.cpu().numpy(), dh.astype(np.float64).sum(0), rtol=1e-5, atol=1e-7)
+    # accumulate, and run-to-run bit-reproducibility (no atomics: fixed ownership and summation order)
+    dw2, db2 = dw.clone(), db.clone()
+    F.bag_linear_wgrad(bag, dev(idx), dev(dh), dw=dw2, db=db2, accumulate=True)
+    np.testing.assert_allclose(dw2.cpu().numpy(), 2 * dw.cpu().numpy(), rtol=1e-6, atol=1e-12)
+    dw3, db3 = F.bag_linear_wgrad(bag, dev(idx), dev(dh))
+    assert torch.equal(dw3, dw) and torch.equal(db3, db)
+
+
+def test_bag_linear_fwd_dropout_mask_equals_gemm_path(F):
+    """Same Philox element numbering as ttam_linear_fwd: the two layer-1 paths drop the same elements for the same
+    (seed, offset), so the backward mask (h > 0) of either is valid for both."""
+    rng = np.random.default_rng(5)
+    NI, R, H, Fd = 500, 300, 64, 40
+    X = _sparse_features(rng, NI, Fd, 2, 4, 2)
+    W = (np.abs(rng.standard_normal((H, Fd))) + 0.1).astype(np.float32)     # positive pre-activations: zeros are drops
+    X = np.abs(X)
+    b = np.ones(H, dtype=np.float32)
+    idx = rng.integers(0, NI, size=R).astype(np.int64)
+    bag = F.BagMatrix.build(dev(X))
+    a = F.bag_linear_fwd(bag, dev(idx), dev(W), dev(b), act="relu", dropout_p=0.3, seed=99, offset=1 << 20)
+    g = F.linear_fwd(dev(X), dev(W), dev(b), gather=dev(idx), act="relu", dropout_p=0.3, seed=99, offset=1 << 20)
+    assert torch.equal(a == 0, g == 0) and 0.2 < float((a == 0).float().mean()) < 0.4
+    np.testing.assert_allclose(a.cpu().numpy(), g.cpu().numpy(), rtol=2e-5, atol=1e-6)
+
+
+def test_bag_linear_fwd_tf32_rounded_output(F):
+    rng = np.random.default_rng(6)
+    X = _sparse_features(rng, 200, 40, 2, 4, 2)
+    W = rng.standard_normal((64, 40)).astype(np.float32)
+    bag = F.BagMatrix.build(dev(X))
+    idx = dev(np.arange(200, dtype=np.int64))
+    y = F.bag_linear_fwd(bag, idx, dev(W), None)
+    yr = F.bag_linear_fwd(bag, idx, dev(W), None, round_tf32_out=True)
+    assert torch.equal(yr, F.round_tf32_(y.clone()))

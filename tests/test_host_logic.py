@@ -88,3 +88,31 @@ def test_filter_block_equals_per_user_filter():
             want = retrieval.filter_candidates(ids[r, : need[r]].tolist(), set(blocked.get(u, ())), gt[u], max_k)
             assert got[u] == want, (trial, r)
     assert retrieval.filter_block(np.zeros((0, 4), np.int64), [], [], {}, {}, 3) == {}
+
+
+def test_bag_matrix_layout_roundtrip():
+    """functional.BagMatrix (CSR over the sparse columns + dense tail) reproduces the dense matrix; a matrix with a row of more
+    than 64 sparse non-zeros is refused (the engine keeps the dense GEMM path for it)."""
+    import torch
+    from two_tower_augmented_with_adaptive_mimic_mechanism_b200.functional import BagMatrix
+    rng = np.random.default_rng(0)
+    N, F = 300, 37
+    x = np.zeros((N, F), dtype=np.float32)
+    for r in range(N):
+        x[r, rng.choice(F - 5, size=rng.integers(0, 6), replace=False)] = rng.choice([1.0, 0.5], size=1)
+    x[:, F - 5:] = rng.standard_normal((N, 5)).astype(np.float32)
+    x[7, F - 2] = 0.0                                     # a zero inside the dense tail stays a stored value
+    bag = BagMatrix.build(torch.from_numpy(x), chunk_rows=64)
+    assert bag is not None and bag.tail_start == F - 5 and bag.T == 5
+    dense = np.zeros_like(x)
+    ptr, ent = bag.rowptr.numpy(), bag.entries.numpy()
+    for r in range(N):
+        seg = ent[ptr[r]:ptr[r + 1]]
+        assert np.all(np.diff(seg[:, 0]) > 0)             # column order inside a row
+        dense[r, seg[:, 0]] = seg[:, 1].view(np.float32)
+    dense[:, bag.tail_start:] = bag.tail.numpy()
+    assert np.array_equal(dense, x)
+    assert BagMatrix.build(torch.ones((4, 100))) is None  # every column dense: 92 sparse non-zeros per row
+    few = torch.zeros((5, 12)); few[:, 3] = 1.0
+    b2 = BagMatrix.build(few)
+    assert b2.T == 0 and b2.tail is None and b2.rowptr.tolist() == [0, 1, 2, 3, 4, 5]

@@ -12,21 +12,66 @@ using namespace ttam;
     if (rc__ != TTAM_OK) return rc__; \
   } while (0)
 
+// scratch of the bag-form layer 1 inside the composite calls: the forward has no workspace argument, so the transposed weight
+// lives in a per-device, per-stream-slot buffer owned by the library (grown on demand, never freed while the library lives)
+static int bag_scratch(int64_t bytes, void* stream, void** out) {
+  struct Slot { void* stream; void* ptr; int64_t bytes; int dev; };
+  static Slot slots[64];
+  static int n = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  for (int i = 0; i < n; ++i)
+    if (slots[i].stream == stream && slots[i].dev == dev) {
+      if (slots[i].bytes < bytes) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing((cudaStream_t)stream, &cs);
+        TTAM_CHECK_ARG(cs == cudaStreamCaptureStatusNone, "tower_fwd: bag scratch must be sized by an eager call before graph capture");
+        TTAM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+        TTAM_CUDA(cudaFree(slots[i].ptr));
+        TTAM_CUDA(cudaMalloc(&slots[i].ptr, (size_t)bytes));
+        slots[i].bytes = bytes;
+      }
+      *out = slots[i].ptr;
+      return TTAM_OK;
+    }
+  TTAM_CHECK_ARG(n < 64, "tower_fwd: too many streams use the bag scratch");
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing((cudaStream_t)stream, &cs);
+  TTAM_CHECK_ARG(cs == cudaStreamCaptureStatusNone, "tower_fwd: bag scratch must be sized by an eager call before graph capture");
+  void* ptr = nullptr;
+  TTAM_CUDA(cudaMalloc(&ptr, (size_t)bytes));
+  slots[n++] = Slot{stream, ptr, bytes, dev};
+  *out = ptr;
+  return TTAM_OK;
+}
+
 extern "C" int ttam_tower_fwd(const ttam_tower_desc* d, const int64_t* idx, int64_t R, const ttam_tower_bufs* b, void* stream) {
   TTAM_CHECK_ARG(d && b && (R == 0 || idx), "tower_fwd: null pointer");
-  TTAM_CHECK_ARG(d->table && d->X && d->W1 && d->W2 && d->G1 && d->G2, "tower_fwd: incomplete tower description");
+  TTAM_CHECK_ARG(d->table && (d->X || d->bag_rowptr) && d->W1 && d->W2 && d->G1 && d->G2, "tower_fwd: incomplete tower description");
   TTAM_CHECK_ARG(b->z && b->hd && b->a && b->pre2 && b->g && b->t, "tower_fwd: missing activation buffer");
   if (R == 0) return TTAM_OK;
   const int64_t D = d->D, H = d->H, Hg = d->Hg, F = d->F;
   // e = E[idx] -> z[:, :D]
   TTAM_TRY(ttam_gather_rows_f32(d->table, D, d->table_rows, idx, b->z, 2 * D, R, D, stream));
   // hd = dropout(relu(X[idx] W1^T + b1))
-  const int prec1 = d->precision | (d->x_rounded ? TTAM_PREC_X_ROUNDED : 0) | (d->w1_rounded ? TTAM_PREC_W_ROUNDED : 0);
-  TTAM_TRY(ttam_linear_fwd(d->X, d->ldx, idx, d->W1, d->ldw1, d->b1, b->hd, H, R, H, F, TTAM_ACT_RELU, d->dropout_p, d->seed,
-                           d->rng_base, d->state, prec1, stream));
+  const bool bag = d->bag_rowptr != nullptr;
+  const bool tc = (d->precision & 0xFF) != TTAM_PREC_FP32;
+  if (bag) {
+    // bag form: b1 + sum_j x_j W1[:, j] in fp32, written TF32-rounded when the next GEMM runs on the tensor cores
+    const int64_t need = ttam_bag_linear_workspace_bytes(0, H, F);
+    void* scratch = nullptr;
+    TTAM_TRY(bag_scratch(need, stream, &scratch));
+    TTAM_TRY(ttam_bag_linear_fwd(d->bag_rowptr, d->bag_entries, d->bag_tail, d->bag_T, d->bag_tail_start, idx, R, d->W1, d->ldw1,
+                                 d->b1, b->hd, H, H, F, TTAM_ACT_RELU, d->dropout_p, d->seed, d->rng_base, d->state, tc ? 1 : 0,
+                                 scratch, need, stream));
+  } else {
+    const int prec1 = d->precision | (d->x_rounded ? TTAM_PREC_X_ROUNDED : 0) | (d->w1_rounded ? TTAM_PREC_W_ROUNDED : 0);
+    TTAM_TRY(ttam_linear_fwd(d->X, d->ldx, idx, d->W1, d->ldw1, d->b1, b->hd, H, R, H, F, TTAM_ACT_RELU, d->dropout_p, d->seed,
+                             d->rng_base, d->state, prec1, stream));
+  }
   // f = hd W2^T + b2 -> z[:, D:]
   TTAM_TRY(ttam_linear_fwd(b->hd, H, nullptr, d->W2, H, d->b2, b->z + D, 2 * D, R, D, H, TTAM_ACT_NONE, 0.f, 0, 0, nullptr,
-                           d->precision, stream));
+                           d->precision | ((bag && tc) ? TTAM_PREC_X_ROUNDED : 0), stream));
   // a = relu(z G1^T + c1);  pre2 = a G2^T + c2
   TTAM_TRY(ttam_linear_fwd(b->z, 2 * D, nullptr, d->G1, 2 * D, d->c1, b->a, Hg, R, Hg, 2 * D, TTAM_ACT_RELU, 0.f, 0, 0, nullptr,
                            d->precision, stream));
@@ -41,7 +86,7 @@ extern "C" int64_t ttam_tower_bwd_workspace_bytes(const ttam_tower_desc* d, int6
   if (!d || R <= 0) return 256;
   int64_t m = ttam_linear_wgrad_workspace_bytes(R, d->D, d->Hg);
   const int64_t c[3] = {ttam_linear_wgrad_workspace_bytes(R, d->Hg, 2 * d->D), ttam_linear_wgrad_workspace_bytes(R, d->D, d->H),
-                        ttam_linear_wgrad_workspace_bytes(R, d->H, d->F)};
+                        d->bag_rowptr ? ttam_bag_linear_workspace_bytes(R, d->H, d->F) : ttam_linear_wgrad_workspace_bytes(R, d->H, d->F)};
   for (int i = 0; i < 3; ++i) m = c[i] > m ? c[i] : m;
   return m;
 }
@@ -69,9 +114,17 @@ extern "C" int ttam_tower_bwd(const ttam_tower_desc* d, const int64_t* idx, int6
   if (weights) {
     TTAM_TRY(ttam_linear_wgrad(g->dpre2, D, b->a, Hg, nullptr, g->dG2, g->dc2, R, D, Hg, acc, workspace, workspace_bytes, prec, stream));
     TTAM_TRY(ttam_linear_wgrad(g->dpre1, Hg, b->z, 2 * D, nullptr, g->dG1, g->dc1, R, Hg, 2 * D, acc, workspace, workspace_bytes, prec, stream));
-    TTAM_TRY(ttam_linear_wgrad(df, 2 * D, b->hd, H, nullptr, g->dW2, g->db2, R, D, H, acc, workspace, workspace_bytes, prec, stream));
-    TTAM_TRY(ttam_linear_wgrad(g->dhd, H, d->X, d->ldx, idx, g->dW1, g->db1, R, H, F, acc, workspace, workspace_bytes,
-                               prec | (d->x_rounded ? TTAM_PREC_X_ROUNDED : 0), stream));
+    const bool bag = d->bag_rowptr != nullptr;
+    const bool tc = (prec & 0xFF) != TTAM_PREC_FP32;
+    TTAM_TRY(ttam_linear_wgrad(df, 2 * D, b->hd, H, nullptr, g->dW2, g->db2, R, D, H, acc, workspace, workspace_bytes,
+                               prec | ((bag && tc) ? TTAM_PREC_X_ROUNDED : 0), stream));
+    if (bag) {
+      TTAM_TRY(ttam_bag_linear_wgrad(d->bag_rowptr, d->bag_entries, d->bag_tail, d->bag_T, d->bag_tail_start, idx, R, g->dhd, H,
+                                     g->dW1, F, g->db1, H, F, acc, workspace, workspace_bytes, stream));
+    } else {
+      TTAM_TRY(ttam_linear_wgrad(g->dhd, H, d->X, d->ldx, idx, g->dW1, g->db1, R, H, F, acc, workspace, workspace_bytes,
+                                 prec | (d->x_rounded ? TTAM_PREC_X_ROUNDED : 0), stream));
+    }
   }
   return TTAM_OK;
 }

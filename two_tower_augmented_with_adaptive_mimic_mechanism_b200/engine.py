@@ -48,7 +48,7 @@ class FusedEngine:
     def __init__(self, model, *, optimizer: str = "adamw", lr: float = 1e-3, weight_decay: float = 0.0,
                  momentum: float = 0.0, dense_betas=(0.9, 0.999), sparse_betas=(0.9, 0.999), eps: float = 1e-8,
                  loss_weights: Optional[dict] = None, precision: str = "fp32", seed: int = 1234,
-                 max_steps: int = 1 << 16, item_category_tensor=None, major_category_id=None) -> None:
+                 max_steps: int = 1 << 16, item_category_tensor=None, major_category_id=None, bag="auto") -> None:
         self.model = model
         mimic = getattr(model, "adaptive_mimic", None)
         self.user: TowerPlan = plan_from_module(model.user_encoder, mimic.user_augmented if mimic is not None else None)
@@ -70,6 +70,11 @@ class FusedEngine:
         self.lambda_c = float(w.get("category_alignment", 0.0))
         self.cat_tensor, self.major = item_category_tensor, major_category_id
         self.precision = precision
+        # layer 1 of the feature encoders from the bag (CSR + dense tail) form of the feature matrices: "auto" = whenever
+        # a matrix is sparse enough for the bag kernels (<= 64 non-zeros per row outside the dense tail), False = always
+        # the dense GEMM (X[idx] . W1^T), True = like "auto" but a matrix that cannot be converted raises
+        self.bag = bag
+        self._bags: dict = {}
         self.seed = int(seed)
         self.max_steps = int(max_steps)
         self.t = 0                         # optimiser steps taken
@@ -183,7 +188,20 @@ class FusedEngine:
         rows zero-padded to a multiple of 4 floats (F = 605 -> ld = 608: 16-byte aligned rows for the 16-byte LDGSTS)
         and values rounded to TF32 once, here, so that the GEMMs need no rounding pass over this operand.  The copy is
         reused for as long as the caller keeps passing the same tensor."""
-        if X is None or self.precision == "fp32":
+        if X is None:
+            return X
+        if self.bag:
+            bag = self._bag_for(X)
+            if bag is not None:
+                try:
+                    X._ttam_bag = bag
+                except Exception:  # noqa: BLE001
+                    bag = None
+            if bag is not None:
+                return X
+            if self.bag is True:
+                raise ValueError("bag=True: the feature matrix has rows with more than 64 non-zeros outside its dense tail")
+        if self.precision == "fp32":
             return X
         # keyed by the tensor OBJECT (weak reference) and its version counter: a new tensor that lands on a freed
         # matrix's address, or an in-place edit of the matrix, gets a fresh copy
@@ -198,6 +216,19 @@ class FusedEngine:
             hit = (weakref.ref(X), X._version, cp)
             self._xpad[key] = hit
             F.note_realloc()       # graphs captured on the old copy are stale
+        return hit[2]
+
+    def _bag_for(self, X):
+        """BagMatrix of a feature matrix, built once per tensor object / version (None: too dense for the bag kernels)."""
+        key = (X.data_ptr(), tuple(X.shape))
+        hit = self._bags.get(key)
+        if hit is not None and (hit[0]() is not X or hit[1] != X._version):
+            hit = None
+        if hit is None:
+            hit = (weakref.ref(X), X._version, F.BagMatrix.build(X))
+            self._bags = {k: v for k, v in self._bags.items() if k[0] != key[0]}
+            self._bags[key] = hit
+            F.note_realloc()
         return hit[2]
 
     def _categories(self):

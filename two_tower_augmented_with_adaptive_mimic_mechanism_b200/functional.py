@@ -190,6 +190,116 @@ def linear_wgrad(dy, x, *, gather=None, dw=None, db=None, accumulate=False, prec
     return dw, db
 
 
+# ---------------------------------------------------------------------------------------------
+# bag form of a feature matrix (csrc/bag.cu)
+# ---------------------------------------------------------------------------------------------
+BAG_MAX_NNZ = 64      # sparse entries per row the kernels stage (csrc/bag.cu kMaxNnz)
+BAG_MAX_TAIL = 8      # dense trailing columns (kMaxTail)
+
+
+class BagMatrix:
+    """CSR + dense-tail layout of a feature matrix X [N, F] (reference features.py:242-252: one-/multi-hot category and
+    author columns, then a few z-scored numerics that are non-zero in every row).
+
+      tail_start : the trailing columns [tail_start, F) whose density is >= 1/2 (at most 8) are kept as a dense [N, T] block
+      rowptr     : int64 [N + 1], entries of row r are entries[rowptr[r] : rowptr[r + 1]] in column order
+      entries    : int32 [nnz, 2] = (column, fp32 value bits): one 8-byte load per non-zero
+    Built with torch index ops, once per feature matrix (layout preparation, like the padded copy of the dense path).
+    `BagMatrix.build` returns None when the matrix is too dense for the bag kernels (a row with more than 64 non-zeros
+    outside the tail): the caller keeps the dense GEMM path."""
+
+    def __init__(self, rowptr, entries, tail, tail_start, shape, mean_nnz):
+        self.rowptr, self.entries, self.tail, self.tail_start, self.shape, self.mean_nnz = rowptr, entries, tail, tail_start, shape, mean_nnz
+        self.T = shape[1] - tail_start
+
+    @staticmethod
+    def build(X: torch.Tensor, chunk_rows: int = 1 << 18):
+        if X.dtype != torch.float32 or X.dim() != 2:
+            raise ValueError("BagMatrix.build needs a 2-D float32 matrix")
+        N, Fd = X.shape
+        if N == 0 or Fd == 0:
+            return None
+        # dense tail: the longest suffix of columns (<= 8) that are non-zero in at least half of the rows
+        probe = X[: min(N, 1 << 16), max(0, Fd - BAG_MAX_TAIL):]
+        dens = (probe != 0).float().mean(0).cpu().tolist()
+        T = 0
+        for d in reversed(dens):
+            if d >= 0.5:
+                T += 1
+            else:
+                break
+        tail_start = Fd - T
+        counts, cols, vals = [], [], []
+        for s in range(0, N, chunk_rows):
+            blk = X[s:s + chunk_rows, :tail_start]
+            nz = blk != 0
+            cnt = nz.sum(1)
+            if int(cnt.max()) > BAG_MAX_NNZ:
+                return None
+            rc = nz.nonzero()                      # row-major order: columns ascending inside a row
+            counts.append(cnt)
+            cols.append(rc[:, 1].to(torch.int32))
+            vals.append(blk[nz])
+        cnt = torch.cat(counts)
+        rowptr = torch.zeros(N + 1, dtype=torch.int64, device=X.device)
+        torch.cumsum(cnt, 0, out=rowptr[1:])
+        col = torch.cat(cols)
+        val = torch.cat(vals)
+        entries = torch.empty((max(col.numel(), 1), 2), dtype=torch.int32, device=X.device)
+        if col.numel():
+            entries[:, 0] = col
+            entries[:, 1] = val.view(torch.int32)
+        tail = X[:, tail_start:].contiguous() if T > 0 else None
+        return BagMatrix(rowptr, entries, tail, tail_start, (N, Fd), float(col.numel()) / N + T)
+
+
+def bag_supported(H: int, Fdim: int, T: int = 0) -> bool:
+    return bool(lib().ttam_bag_supported(int(H), int(Fdim), int(T)))
+
+
+def bag_linear_fwd(bag: BagMatrix, gather, w, bias=None, *, act="none", out=None, dropout_p=0.0, seed=0, offset=0, state=None,
+                   round_tf32_out=False):
+    """out[r] = act(bias + sum_j X[gather[r], j] w[:, j]) from the bag form of X (fp32 FMA)."""
+    _chk(w, torch.float32, "w")
+    wp, ldw = _rows2d(w, "w")
+    H, Fd = w.shape
+    if Fd != bag.shape[1]:
+        raise ValueError(f"weight expects {Fd} features, the bag matrix has {bag.shape[1]}")
+    if gather is not None:
+        _chk(gather, torch.int64, "gather")
+        R = gather.numel()
+    else:
+        R = bag.shape[0]
+    if out is None:
+        out = torch.empty((R, H), dtype=torch.float32, device=w.device)
+    yp, ldy = _rows2d(out, "out")
+    L = lib()
+    ws = workspace(L.ttam_bag_linear_workspace_bytes(R, H, Fd), w.device, "bag")
+    check(L.ttam_bag_linear_fwd(bag.rowptr.data_ptr(), bag.entries.data_ptr(), _ptr(bag.tail), bag.T, bag.tail_start, _ptr(gather), R,
+                                wp, ldw, _ptr(bias), yp, ldy, H, Fd, ACT[act], float(dropout_p), int(seed), int(offset), _ptr(state),
+                                1 if round_tf32_out else 0, ws.data_ptr(), ws.numel(), _stream()), "bag_linear_fwd")
+    return out
+
+
+def bag_linear_wgrad(bag: BagMatrix, gather, dh, *, dw=None, db=None, accumulate=False, want_bias=True):
+    """dw[h, j] (+)= sum_r dh[r, h] X[gather[r], j];  db[h] (+)= sum_r dh[r, h].  Deterministic."""
+    _chk(dh, torch.float32, "dh")
+    dp, lddh = _rows2d(dh, "dh")
+    R, H = dh.shape
+    Fd = bag.shape[1]
+    if dw is None:
+        dw = torch.empty((H, Fd), dtype=torch.float32, device=dh.device)
+        accumulate = False
+    if db is None and want_bias:
+        db = torch.empty((H,), dtype=torch.float32, device=dh.device)
+    L = lib()
+    ws = workspace(L.ttam_bag_linear_workspace_bytes(R, H, Fd), dh.device, "bag")
+    check(L.ttam_bag_linear_wgrad(bag.rowptr.data_ptr(), bag.entries.data_ptr(), _ptr(bag.tail), bag.T, bag.tail_start, _ptr(gather), R,
+                                  dp, lddh, dw.data_ptr(), dw.stride(0), _ptr(db), H, Fd, 1 if accumulate else 0, ws.data_ptr(),
+                                  ws.numel(), _stream()), "bag_linear_wgrad")
+    return dw, db
+
+
 def new_step_state(device, step: int = 0, rng_offset: int = 0) -> torch.Tensor:
     """Device-resident ttam_step_state {int32 step; int32 pad; uint64 rng_offset} as an int64[2] tensor."""
     return torch.tensor([int(step) & 0xFFFFFFFF, int(rng_offset)], dtype=torch.int64, device=device)

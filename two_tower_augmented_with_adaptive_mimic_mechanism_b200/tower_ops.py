@@ -148,13 +148,25 @@ def _composite_ok(plan: TowerPlan, X, gather: bool, bufs) -> bool:
             and plan.fe_layers[1][0].shape[0] == plan.D)
 
 
-def _tower_desc(plan: TowerPlan, X, W1, p_drop, seed, rng_base, state, precision, augment=True):
+def _bag_of(X, H: int):
+    """The bag form attached to a feature matrix by the engine (`FusedEngine._x`), when the bag kernels take this layer."""
+    bag = getattr(X, "_ttam_bag", None) if X is not None else None
+    if bag is not None and F.bag_supported(H, bag.shape[1], bag.T):
+        return bag
+    return None
+
+
+def _tower_desc(plan: TowerPlan, X, W1, p_drop, seed, rng_base, state, precision, augment=True, bag=None):
     (_, b1), (W2, b2) = plan.fe_layers
     G1, c1, G2, c2 = plan.gate
     d = F._lib.TowerDesc()
     d.table, d.table_rows, d.D = plan.table.data_ptr(), plan.table.shape[0], plan.D
     d.aug = plan.aug.data_ptr() if (plan.aug is not None and augment) else None
     d.X, d.ldx, d.F = X.data_ptr(), X.stride(0), X.shape[1]
+    if bag is not None:
+        d.bag_rowptr, d.bag_entries = bag.rowptr.data_ptr(), bag.entries.data_ptr()
+        d.bag_tail = None if bag.tail is None else bag.tail.data_ptr()
+        d.bag_T, d.bag_tail_start = bag.T, bag.tail_start
     d.W1, d.ldw1, d.b1, d.H = W1.data_ptr(), W1.stride(0), b1.data_ptr(), W1.shape[0]
     d.W2, d.b2 = W2.data_ptr(), b2.data_ptr()
     d.G1, d.c1, d.Hg, d.G2, d.c2 = G1.data_ptr(), c1.data_ptr(), G1.shape[0], G2.data_ptr(), c2.data_ptr()
@@ -167,8 +179,9 @@ def _tower_forward_composite(plan, idx, X, *, train, bufs, seed, rng_base, state
     R, D, dev = idx.numel(), plan.D, plan.table.device
     H, Hg = plan.fe_layers[0][0].shape[0], plan.gate[0].shape[0]
     p_drop = plan.dropout if train else 0.0
-    pre = precision != "fp32" and bool(getattr(X, "_ttam_tf32", False))   # the engine's private rounded copy of X
-    W1 = _w1_rounded(plan.fe_layers[0][0], bufs) if precision != "fp32" else plan.fe_layers[0][0]
+    bag = _bag_of(X, H)
+    pre = bag is None and precision != "fp32" and bool(getattr(X, "_ttam_tf32", False))   # the engine's private rounded copy of X
+    W1 = _w1_rounded(plan.fe_layers[0][0], bufs) if (precision != "fp32" and bag is None) else plan.fe_layers[0][0]
     c = Cache(idx=idx, X=X, gather=True, train=train, R=R, seed=seed, rng_base=rng_base, mode="gated", composite=True)
     c.z = _buf(bufs, "z", (R, 2 * D), dev)
     c.hd, c.pre = [_buf(bufs, "hd0", (R, H), dev)], [None]
@@ -177,8 +190,9 @@ def _tower_forward_composite(plan, idx, X, *, train, bufs, seed, rng_base, state
     has_aug = plan.aug is not None and augment
     o = _buf(bufs, "o", (R, D), dev) if has_aug else None
     q = _buf(bufs, "q", (R, D), dev) if (has_aug and want_q) else None
-    c.desc = _tower_desc(plan, X, W1, p_drop, seed, rng_base, state, precision, augment)
-    c.desc.x_rounded, c.desc.w1_rounded = int(pre), int(precision != "fp32")
+    c.desc = _tower_desc(plan, X, W1, p_drop, seed, rng_base, state, precision, augment, bag)
+    c.desc.x_rounded, c.desc.w1_rounded = int(pre), int(precision != "fp32" and bag is None)
+    c.bag = bag            # keeps the CSR tensors alive as long as the cache
     b = F._lib.TowerBufs()
     b.z, b.hd, b.a, b.pre2, b.g, b.t = (t.data_ptr() for t in (c.z, c.hd[0], c.a, pre2, c.g, c.t))
     b.o, b.q = (None if o is None else o.data_ptr()), (None if q is None else q.data_ptr())
@@ -262,14 +276,34 @@ def tower_forward(plan: TowerPlan, idx: torch.Tensor, X: Optional[torch.Tensor],
                 f_view.copy_(X)
         elif plan.fe_kind == "linear":
             W, b = plan.fe_layers[0]
-            F.linear_fwd(X, _w_for(W, bufs, precision), b, gather=gidx, out=f_view, precision=precision)
+            c.bag = _bag_of(X, W.shape[0]) if gather else None
+            if c.bag is not None:
+                tmp = _buf(bufs, "f_bag", (R, W.shape[0]), dev)      # 16-byte aligned rows for the bag kernel's stores
+                F.bag_linear_fwd(c.bag, idx, W, b, out=tmp)
+                f_view.copy_(tmp)
+            else:
+                F.linear_fwd(X, _w_for(W, bufs, precision), b, gather=gidx, out=f_view, precision=precision)
         else:
             h_in, g_in = X, gidx
             c.pre, c.hd = [], []
             off = rng_base
+            c.bag = _bag_of(X, plan.fe_layers[0][0].shape[0]) if gather else None
             for li, (W, b) in enumerate(plan.fe_layers[:-1]):
                 H = W.shape[0]
                 hd = _buf(bufs, f"hd{li}", (R, H), dev)
+                if li == 0 and c.bag is not None:            # bag form of layer 1 (fp32 FMA over the row's non-zeros)
+                    if plan.activation == "relu":
+                        F.bag_linear_fwd(c.bag, idx, W, b, act="relu", out=hd, dropout_p=p_drop, seed=seed, offset=off, state=state)
+                        c.pre.append(None)
+                    else:
+                        pre = _buf(bufs, f"pre{li}", (R, H), dev)
+                        F.bag_linear_fwd(c.bag, idx, W, b, out=pre)
+                        F.act_fwd(pre, act=plan.activation, out=hd, dropout_p=p_drop, seed=seed, offset=off, state=state)
+                        c.pre.append(pre)
+                    c.hd.append(hd)
+                    off += R * H
+                    h_in, g_in = hd, None
+                    continue
                 W = _w_for(W, bufs, precision)
                 if plan.activation == "relu":
                     F.linear_fwd(h_in, W, b, gather=g_in, act="relu", out=hd, dropout_p=p_drop, seed=seed, offset=off,
@@ -352,6 +386,12 @@ def tower_backward(plan: TowerPlan, c: Cache, dt: torch.Tensor, grads: dict, *, 
             grads[id(W)], grads[id(b)] = dw, db
         else:
             db = grads[id(b)]
+        if gather is not None and c.bag is not None and x is X:
+            dyc = dy
+            if dy.stride(0) % 4 != 0 or dy.data_ptr() % 16 != 0 or (dy.shape[1] > 1 and dy.stride(1) != 1):
+                dyc = dy.contiguous()
+            F.bag_linear_wgrad(c.bag, gather, dyc, dw=dw, db=db, accumulate=acc)
+            return
         F.linear_wgrad(dy, x, gather=gather, dw=dw, db=db, accumulate=acc, precision=precision)
 
     if c.mode == "identity":
