@@ -157,6 +157,8 @@ typedef struct {
   const void* bag_entries;
   const float* bag_tail;
   int64_t bag_T, bag_tail_start;
+  void* bag_scratch;          /* >= F*H*4 bytes, private to this tower (ttam_tower_fwd transposes W1 into it) */
+  int64_t bag_scratch_bytes;
 } ttam_tower_desc;
 typedef struct { float *z, *hd, *a, *pre2, *g, *t, *o, *q; } ttam_tower_bufs;
 typedef struct {

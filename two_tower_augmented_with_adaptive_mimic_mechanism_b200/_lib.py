@@ -48,6 +48,7 @@ class TowerDesc(C.Structure):
         ("state", C.c_void_p),
         ("bag_rowptr", C.c_void_p), ("bag_entries", C.c_void_p), ("bag_tail", C.c_void_p),
         ("bag_T", C.c_int64), ("bag_tail_start", C.c_int64),
+        ("bag_scratch", C.c_void_p), ("bag_scratch_bytes", C.c_int64),
     ]
 
 

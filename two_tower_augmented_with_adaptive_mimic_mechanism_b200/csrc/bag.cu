@@ -410,6 +410,7 @@ extern "C" int ttam_bag_linear_fwd(const int64_t* rowptr, const void* entries, c
                                    const int64_t* gather, int64_t R, const float* w, int64_t ldw, const float* bias, float* y,
                                    int64_t ldy, int64_t H, int64_t F, int act, float dropout_p, uint64_t seed, uint64_t offset,
                                    const void* state_dev, int round_tf32_out, void* workspace, int64_t workspace_bytes, void* stream) {
+  if (R == 0) return TTAM_OK;
   TTAM_CHECK_ARG(rowptr && entries && w && y && workspace, "bag_linear_fwd: null pointer");
   TTAM_CHECK_ARG(act == TTAM_ACT_NONE || act == TTAM_ACT_RELU, "bag_linear_fwd: fuses ReLU only");
   TTAM_CHECK_ARG(T >= 0 && T <= kMaxTail && tail_start + T == F && (T == 0 || tail), "bag_linear_fwd: bad dense tail");
@@ -451,7 +452,7 @@ extern "C" int ttam_bag_linear_wgrad(const int64_t* rowptr, const void* entries,
                                      const int64_t* gather, int64_t R, const float* dh, int64_t lddh, float* dw, int64_t lddw,
                                      float* db, int64_t H, int64_t F, int accumulate, void* workspace, int64_t workspace_bytes,
                                      void* stream) {
-  TTAM_CHECK_ARG(rowptr && entries && dh && dw && workspace, "bag_linear_wgrad: null pointer");
+  TTAM_CHECK_ARG(rowptr && entries && (dh || R == 0) && dw && workspace, "bag_linear_wgrad: null pointer");
   TTAM_CHECK_ARG(T >= 0 && T <= kMaxTail && tail_start + T == F && (T == 0 || tail), "bag_linear_wgrad: bad dense tail");
   const int sw = slice_width(H, F);
   TTAM_CHECK_ARG(sw != 0, "bag_linear_wgrad: unsupported shape H=%lld F=%lld", (long long)H, (long long)F);

@@ -12,39 +12,6 @@ using namespace ttam;
     if (rc__ != TTAM_OK) return rc__; \
   } while (0)
 
-// scratch of the bag-form layer 1 inside the composite calls: the forward has no workspace argument, so the transposed weight
-// lives in a per-device, per-stream-slot buffer owned by the library (grown on demand, never freed while the library lives)
-static int bag_scratch(int64_t bytes, void* stream, void** out) {
-  struct Slot { void* stream; void* ptr; int64_t bytes; int dev; };
-  static Slot slots[64];
-  static int n = 0;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  for (int i = 0; i < n; ++i)
-    if (slots[i].stream == stream && slots[i].dev == dev) {
-      if (slots[i].bytes < bytes) {
-        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-        cudaStreamIsCapturing((cudaStream_t)stream, &cs);
-        TTAM_CHECK_ARG(cs == cudaStreamCaptureStatusNone, "tower_fwd: bag scratch must be sized by an eager call before graph capture");
-        TTAM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-        TTAM_CUDA(cudaFree(slots[i].ptr));
-        TTAM_CUDA(cudaMalloc(&slots[i].ptr, (size_t)bytes));
-        slots[i].bytes = bytes;
-      }
-      *out = slots[i].ptr;
-      return TTAM_OK;
-    }
-  TTAM_CHECK_ARG(n < 64, "tower_fwd: too many streams use the bag scratch");
-  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-  cudaStreamIsCapturing((cudaStream_t)stream, &cs);
-  TTAM_CHECK_ARG(cs == cudaStreamCaptureStatusNone, "tower_fwd: bag scratch must be sized by an eager call before graph capture");
-  void* ptr = nullptr;
-  TTAM_CUDA(cudaMalloc(&ptr, (size_t)bytes));
-  slots[n++] = Slot{stream, ptr, bytes, dev};
-  *out = ptr;
-  return TTAM_OK;
-}
-
 extern "C" int ttam_tower_fwd(const ttam_tower_desc* d, const int64_t* idx, int64_t R, const ttam_tower_bufs* b, void* stream) {
   TTAM_CHECK_ARG(d && b && (R == 0 || idx), "tower_fwd: null pointer");
   TTAM_CHECK_ARG(d->table && (d->X || d->bag_rowptr) && d->W1 && d->W2 && d->G1 && d->G2, "tower_fwd: incomplete tower description");
@@ -58,12 +25,10 @@ extern "C" int ttam_tower_fwd(const ttam_tower_desc* d, const int64_t* idx, int6
   const bool tc = (d->precision & 0xFF) != TTAM_PREC_FP32;
   if (bag) {
     // bag form: b1 + sum_j x_j W1[:, j] in fp32, written TF32-rounded when the next GEMM runs on the tensor cores
-    const int64_t need = ttam_bag_linear_workspace_bytes(0, H, F);
-    void* scratch = nullptr;
-    TTAM_TRY(bag_scratch(need, stream, &scratch));
+    TTAM_CHECK_ARG(d->bag_scratch, "tower_fwd: the bag form needs bag_scratch (room for W1^T)");
     TTAM_TRY(ttam_bag_linear_fwd(d->bag_rowptr, d->bag_entries, d->bag_tail, d->bag_T, d->bag_tail_start, idx, R, d->W1, d->ldw1,
                                  d->b1, b->hd, H, H, F, TTAM_ACT_RELU, d->dropout_p, d->seed, d->rng_base, d->state, tc ? 1 : 0,
-                                 scratch, need, stream));
+                                 d->bag_scratch, d->bag_scratch_bytes, stream));
   } else {
     const int prec1 = d->precision | (d->x_rounded ? TTAM_PREC_X_ROUNDED : 0) | (d->w1_rounded ? TTAM_PREC_W_ROUNDED : 0);
     TTAM_TRY(ttam_linear_fwd(d->X, d->ldx, idx, d->W1, d->ldw1, d->b1, b->hd, H, R, H, F, TTAM_ACT_RELU, d->dropout_p, d->seed,

@@ -167,6 +167,8 @@ def _tower_desc(plan: TowerPlan, X, W1, p_drop, seed, rng_base, state, precision
         d.bag_rowptr, d.bag_entries = bag.rowptr.data_ptr(), bag.entries.data_ptr()
         d.bag_tail = None if bag.tail is None else bag.tail.data_ptr()
         d.bag_T, d.bag_tail_start = bag.T, bag.tail_start
+        ws = F.workspace(F.lib().ttam_bag_linear_workspace_bytes(0, W1.shape[0], X.shape[1]), X.device, "bag_fwd")
+        d.bag_scratch, d.bag_scratch_bytes = ws.data_ptr(), ws.numel()
     d.W1, d.ldw1, d.b1, d.H = W1.data_ptr(), W1.stride(0), b1.data_ptr(), W1.shape[0]
     d.W2, d.b2 = W2.data_ptr(), b2.data_ptr()
     d.G1, d.c1, d.Hg, d.G2, d.c2 = G1.data_ptr(), c1.data_ptr(), G1.shape[0], G2.data_ptr(), c2.data_ptr()
