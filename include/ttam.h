@@ -156,7 +156,7 @@ typedef struct {
   const int64_t* bag_rowptr;
   const void* bag_entries;
   const float* bag_tail;
-  int64_t bag_T, bag_tail_start;
+  int64_t bag_T, bag_tail_start, bag_max_nnz;
   void* bag_scratch;          /* >= F*H*4 bytes, private to this tower (ttam_tower_fwd transposes W1 into it) */
   int64_t bag_scratch_bytes;
 } ttam_tower_desc;
@@ -183,16 +183,17 @@ int ttam_tower_bwd(const ttam_tower_desc* d, const int64_t* idx, int64_t R, cons
  *                          round_tf32_out != 0, y rounded to TF32 (its consumer is a tensor-core GEMM that skips its
  *                          own rounding pass).  w is the nn.Linear weight [H, F] with row stride ldw.
  *   ttam_bag_linear_wgrad: dw[h, j] (+)= sum_r dh[r, h] x_j(r), db[h] (+)= sum_r dh[r, h].  Deterministic (no atomics).
- * Supported when ttam_bag_supported(H, F, T) != 0 (H % 32 == 0, F*32*4 <= 172 kB); both take
- * ttam_bag_linear_workspace_bytes(R, H, F) bytes of scratch. */
-int ttam_bag_supported(int64_t H, int64_t F, int64_t T);
+ * max_nnz = the largest number of CSR entries any row holds (<= 64); it sizes the kernels' shared-memory tile ring.
+ * Supported when ttam_bag_supported(H, F, T, max_nnz) != 0 (H % 32 == 0; weight slice + ring fit in shared memory);
+ * both take ttam_bag_linear_workspace_bytes(R, H, F) bytes of scratch. */
+int ttam_bag_supported(int64_t H, int64_t F, int64_t T, int64_t max_nnz);
 int64_t ttam_bag_linear_workspace_bytes(int64_t R, int64_t H, int64_t F);
 int ttam_bag_linear_fwd(const int64_t* rowptr, const void* entries, const float* tail, int64_t T, int64_t tail_start,
-                        const int64_t* gather, int64_t R, const float* w, int64_t ldw, const float* bias, float* y,
+                        int64_t max_nnz, const int64_t* gather, int64_t R, const float* w, int64_t ldw, const float* bias, float* y,
                         int64_t ldy, int64_t H, int64_t F, int act, float dropout_p, uint64_t seed, uint64_t offset,
                         const void* state_dev, int round_tf32_out, void* workspace, int64_t workspace_bytes, void* stream);
 int ttam_bag_linear_wgrad(const int64_t* rowptr, const void* entries, const float* tail, int64_t T, int64_t tail_start,
-                          const int64_t* gather, int64_t R, const float* dh, int64_t lddh, float* dw, int64_t lddw,
+                          int64_t max_nnz, const int64_t* gather, int64_t R, const float* dh, int64_t lddh, float* dw, int64_t lddw,
                           float* db, int64_t H, int64_t F, int accumulate, void* workspace, int64_t workspace_bytes,
                           void* stream);
 

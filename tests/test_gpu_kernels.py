@@ -566,7 +566,7 @@ def test_bag_linear_fwd_and_wgrad_match_dense_product(F, R, H, Fd, nnz, tail, ac
     pop = 1.0 / np.arange(1, NI + 1) ** 1.05
     idx = rng.choice(NI, size=R, p=pop / pop.sum()).astype(np.int64)       # duplicate-heavy, like the positives
     bag = F.BagMatrix.build(dev(X))
-    assert bag is not None and bag.T == tail and F.bag_supported(H, Fd, bag.T)
+    assert bag is not None and bag.T == tail and F.bag_supported(H, Fd, bag.T, bag.max_nnz)
     y = F.bag_linear_fwd(bag, dev(idx), dev(W), dev(b), act=act).cpu().numpy()
     xr = X[idx].astype(np.float64)
     ref = xr @ W.astype(np.float64).T + b

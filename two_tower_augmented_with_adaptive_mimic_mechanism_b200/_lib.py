@@ -47,7 +47,7 @@ class TowerDesc(C.Structure):
         ("seed", C.c_uint64), ("rng_base", C.c_uint64),
         ("state", C.c_void_p),
         ("bag_rowptr", C.c_void_p), ("bag_entries", C.c_void_p), ("bag_tail", C.c_void_p),
-        ("bag_T", C.c_int64), ("bag_tail_start", C.c_int64),
+        ("bag_T", C.c_int64), ("bag_tail_start", C.c_int64), ("bag_max_nnz", C.c_int64),
         ("bag_scratch", C.c_void_p), ("bag_scratch_bytes", C.c_int64),
     ]
 
@@ -129,11 +129,11 @@ SIGNATURES = {
     "ttam_tower_fwd": (C.c_int, [C.POINTER(TowerDesc), _p, _i64, C.POINTER(TowerBufs), _p]),
     "ttam_tower_bwd_workspace_bytes": (C.c_int64, [C.POINTER(TowerDesc), _i64]),
     "ttam_tower_bwd": (C.c_int, [C.POINTER(TowerDesc), _p, _i64, C.POINTER(TowerBufs), _p, C.POINTER(TowerGrads), _p, _i64, _p]),
-    "ttam_bag_supported": (C.c_int, [_i64, _i64, _i64]),
+    "ttam_bag_supported": (C.c_int, [_i64, _i64, _i64, _i64]),
     "ttam_bag_linear_workspace_bytes": (C.c_int64, [_i64, _i64, _i64]),
-    "ttam_bag_linear_fwd": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _i64, _i64, _i32, _f, _u64, _u64,
+    "ttam_bag_linear_fwd": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _i64, _i64, _i32, _f, _u64, _u64,
                                       _p, _i32, _p, _i64, _p]),
-    "ttam_bag_linear_wgrad": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i32, _p, _i64, _p]),
+    "ttam_bag_linear_wgrad": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i32, _p, _i64, _p]),
     "ttam_loss_workspace_bytes": (C.c_int64, [_i64]),
     "ttam_loss_fwd_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _i64, _i64, _i64, _f, _p, _i64, _p]),
     "ttam_category_alignment_workspace_bytes": (C.c_int64, [_i64, _i64, _i64]),

@@ -26,7 +26,7 @@ extern "C" int ttam_tower_fwd(const ttam_tower_desc* d, const int64_t* idx, int6
   if (bag) {
     // bag form: b1 + sum_j x_j W1[:, j] in fp32, written TF32-rounded when the next GEMM runs on the tensor cores
     TTAM_CHECK_ARG(d->bag_scratch, "tower_fwd: the bag form needs bag_scratch (room for W1^T)");
-    TTAM_TRY(ttam_bag_linear_fwd(d->bag_rowptr, d->bag_entries, d->bag_tail, d->bag_T, d->bag_tail_start, idx, R, d->W1, d->ldw1,
+    TTAM_TRY(ttam_bag_linear_fwd(d->bag_rowptr, d->bag_entries, d->bag_tail, d->bag_T, d->bag_tail_start, d->bag_max_nnz, idx, R, d->W1, d->ldw1,
                                  d->b1, b->hd, H, H, F, TTAM_ACT_RELU, d->dropout_p, d->seed, d->rng_base, d->state, tc ? 1 : 0,
                                  d->bag_scratch, d->bag_scratch_bytes, stream));
   } else {
@@ -84,7 +84,7 @@ extern "C" int ttam_tower_bwd(const ttam_tower_desc* d, const int64_t* idx, int6
     TTAM_TRY(ttam_linear_wgrad(df, 2 * D, b->hd, H, nullptr, g->dW2, g->db2, R, D, H, acc, workspace, workspace_bytes,
                                prec | ((bag && tc) ? TTAM_PREC_X_ROUNDED : 0), stream));
     if (bag) {
-      TTAM_TRY(ttam_bag_linear_wgrad(d->bag_rowptr, d->bag_entries, d->bag_tail, d->bag_T, d->bag_tail_start, idx, R, g->dhd, H,
+      TTAM_TRY(ttam_bag_linear_wgrad(d->bag_rowptr, d->bag_entries, d->bag_tail, d->bag_T, d->bag_tail_start, d->bag_max_nnz, idx, R, g->dhd, H,
                                      g->dW1, F, g->db1, H, F, acc, workspace, workspace_bytes, stream));
     } else {
       TTAM_TRY(ttam_linear_wgrad(g->dhd, H, d->X, d->ldx, idx, g->dW1, g->db1, R, H, F, acc, workspace, workspace_bytes,

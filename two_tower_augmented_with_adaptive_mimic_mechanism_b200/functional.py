@@ -208,8 +208,9 @@ class BagMatrix:
     `BagMatrix.build` returns None when the matrix is too dense for the bag kernels (a row with more than 64 non-zeros
     outside the tail): the caller keeps the dense GEMM path."""
 
-    def __init__(self, rowptr, entries, tail, tail_start, shape, mean_nnz):
+    def __init__(self, rowptr, entries, tail, tail_start, shape, mean_nnz, max_nnz):
         self.rowptr, self.entries, self.tail, self.tail_start, self.shape, self.mean_nnz = rowptr, entries, tail, tail_start, shape, mean_nnz
+        self.max_nnz = int(max_nnz)          # most CSR entries in one row: sizes the kernels' tile ring
         self.T = shape[1] - tail_start
 
     @staticmethod
@@ -230,11 +231,13 @@ class BagMatrix:
                 break
         tail_start = Fd - T
         counts, cols, vals = [], [], []
+        max_nnz = 0
         for s in range(0, N, chunk_rows):
             blk = X[s:s + chunk_rows, :tail_start]
             nz = blk != 0
             cnt = nz.sum(1)
-            if int(cnt.max()) > BAG_MAX_NNZ:
+            max_nnz = max(max_nnz, int(cnt.max()) if cnt.numel() else 0)
+            if max_nnz > BAG_MAX_NNZ:
                 return None
             rc = nz.nonzero()                      # row-major order: columns ascending inside a row
             counts.append(cnt)
@@ -250,11 +253,11 @@ class BagMatrix:
             entries[:, 0] = col
             entries[:, 1] = val.view(torch.int32)
         tail = X[:, tail_start:].contiguous() if T > 0 else None
-        return BagMatrix(rowptr, entries, tail, tail_start, (N, Fd), float(col.numel()) / N + T)
+        return BagMatrix(rowptr, entries, tail, tail_start, (N, Fd), float(col.numel()) / N + T, max_nnz)
 
 
-def bag_supported(H: int, Fdim: int, T: int = 0) -> bool:
-    return bool(lib().ttam_bag_supported(int(H), int(Fdim), int(T)))
+def bag_supported(H: int, Fdim: int, T: int = 0, max_nnz: int = BAG_MAX_NNZ) -> bool:
+    return bool(lib().ttam_bag_supported(int(H), int(Fdim), int(T), int(max_nnz)))
 
 
 def bag_linear_fwd(bag: BagMatrix, gather, w, bias=None, *, act="none", out=None, dropout_p=0.0, seed=0, offset=0, state=None,
@@ -275,7 +278,7 @@ def bag_linear_fwd(bag: BagMatrix, gather, w, bias=None, *, act="none", out=None
     yp, ldy = _rows2d(out, "out")
     L = lib()
     ws = workspace(L.ttam_bag_linear_workspace_bytes(R, H, Fd), w.device, "bag")
-    check(L.ttam_bag_linear_fwd(bag.rowptr.data_ptr(), bag.entries.data_ptr(), _ptr(bag.tail), bag.T, bag.tail_start, _ptr(gather), R,
+    check(L.ttam_bag_linear_fwd(bag.rowptr.data_ptr(), bag.entries.data_ptr(), _ptr(bag.tail), bag.T, bag.tail_start, bag.max_nnz, _ptr(gather), R,
                                 wp, ldw, _ptr(bias), yp, ldy, H, Fd, ACT[act], float(dropout_p), int(seed), int(offset), _ptr(state),
                                 1 if round_tf32_out else 0, ws.data_ptr(), ws.numel(), _stream()), "bag_linear_fwd")
     return out
@@ -294,7 +297,7 @@ def bag_linear_wgrad(bag: BagMatrix, gather, dh, *, dw=None, db=None, accumulate
         db = torch.empty((H,), dtype=torch.float32, device=dh.device)
     L = lib()
     ws = workspace(L.ttam_bag_linear_workspace_bytes(R, H, Fd), dh.device, "bag")
-    check(L.ttam_bag_linear_wgrad(bag.rowptr.data_ptr(), bag.entries.data_ptr(), _ptr(bag.tail), bag.T, bag.tail_start, _ptr(gather), R,
+    check(L.ttam_bag_linear_wgrad(bag.rowptr.data_ptr(), bag.entries.data_ptr(), _ptr(bag.tail), bag.T, bag.tail_start, bag.max_nnz, _ptr(gather), R,
                                   dp, lddh, dw.data_ptr(), dw.stride(0), _ptr(db), H, Fd, 1 if accumulate else 0, ws.data_ptr(),
                                   ws.numel(), _stream()), "bag_linear_wgrad")
     return dw, db

@@ -151,7 +151,7 @@ def _composite_ok(plan: TowerPlan, X, gather: bool, bufs) -> bool:
 def _bag_of(X, H: int):
     """The bag form attached to a feature matrix by the engine (`FusedEngine._x`), when the bag kernels take this layer."""
     bag = getattr(X, "_ttam_bag", None) if X is not None else None
-    if bag is not None and F.bag_supported(H, bag.shape[1], bag.T):
+    if bag is not None and F.bag_supported(H, bag.shape[1], bag.T, bag.max_nnz):
         return bag
     return None
 
@@ -166,7 +166,7 @@ def _tower_desc(plan: TowerPlan, X, W1, p_drop, seed, rng_base, state, precision
     if bag is not None:
         d.bag_rowptr, d.bag_entries = bag.rowptr.data_ptr(), bag.entries.data_ptr()
         d.bag_tail = None if bag.tail is None else bag.tail.data_ptr()
-        d.bag_T, d.bag_tail_start = bag.T, bag.tail_start
+        d.bag_T, d.bag_tail_start, d.bag_max_nnz = bag.T, bag.tail_start, bag.max_nnz
         ws = F.workspace(F.lib().ttam_bag_linear_workspace_bytes(0, W1.shape[0], X.shape[1]), X.device, "bag_fwd")
         d.bag_scratch, d.bag_scratch_bytes = ws.data_ptr(), ws.numel()
     d.W1, d.ldw1, d.b1, d.H = W1.data_ptr(), W1.stride(0), b1.data_ptr(), W1.shape[0]
