@@ -120,12 +120,13 @@ struct Ring {
   Layout L;
   int64_t r_begin, r_end;
   int ntiles, lane, warp, rpl;
+  int pad_mask;  // 3: every row's entry list is padded to a multiple of 4 with zero entries (forward), 0: compact (wgrad)
   // warp 0's look-ahead registers (rpl = TR / 32 rows per lane)
   int64_t g_rp[2], beg_rp[2];  // rows whose rowptr has been loaded: the tile written to the meta block next
   int n_rp[2];
   int64_t g_ga[2];             // rows whose gather index has been loaded: the tile after that
 
-  __device__ Ring(const BagP& p_, uint8_t* smem_, const Layout& L_) : p(p_), smem(smem_), L(L_) {
+  __device__ Ring(const BagP& p_, uint8_t* smem_, const Layout& L_, int pad_mask_) : p(p_), smem(smem_), L(L_), pad_mask(pad_mask_) {
     lane = threadIdx.x & 31;
     warp = threadIdx.x >> 5;
     rpl = p.TR / 32;
@@ -162,7 +163,8 @@ struct Ring {
   }
   __device__ __forceinline__ void write_meta(int tile) {  // scan of n over the tile's rows, then publish
     MetaView m = meta(tile);
-    const int s = n_rp[0] + (rpl > 1 ? n_rp[1] : 0);
+    const int np0 = (n_rp[0] + pad_mask) & ~pad_mask, np1 = (n_rp[1] + pad_mask) & ~pad_mask;
+    const int s = np0 + (rpl > 1 ? np1 : 0);
     int v = s;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -178,33 +180,37 @@ struct Ring {
         m.beg[row] = beg_rp[k];
         m.n[row] = n_rp[k];
         m.off[row] = off;
-        off += n_rp[k];
+        off += k == 0 ? np0 : np1;
       }
     }
     if (lane == 31) m.off[p.TR] = v;
   }
 
-  // ---- all warps: cp.async the entries / tail (and, through `extra`, whatever else) of a tile ----
+  // ---- cp.async the entries / tail of a tile: thread t copies tile row t (a row has a handful of entries; a warp per row
+  // with a lane per entry cost ten times the instructions); `extra` adds whatever else the kernel stages ----
   template <bool ROWID, typename Extra>
   __device__ __forceinline__ void stage(int tile, Extra& extra) {
     if (tile < ntiles) {
       uint8_t* sp = stage_ptr(tile);
-      int2* ent_s = reinterpret_cast<int2*>(sp + L.ent_off);
-      float* tail_s = reinterpret_cast<float*>(sp + L.tail_off);
-      uint8_t* rowid_s = sp + L.rowid_off;
-      const MetaView m = meta(tile);
-      for (int row = warp; row < p.TR; row += kWarps) {
-        const int n = m.n[row];
+      const int row = threadIdx.x;
+      if (row < p.TR) {
+        const MetaView m = meta(tile);
         const int64_t g = m.g[row];
-        if (n > 0) {
-          const int64_t beg = m.beg[row];
-          const int off = m.off[row];
-          for (int i = lane; i < n; i += 32) {
-            cp_async8(s32(ent_s + off + i), p.ent + beg + i);
-            if (ROWID) rowid_s[off + i] = (uint8_t)row;
+        if (g >= 0) {
+          const int n = m.n[row], off = m.off[row];
+          const int2* src = p.ent + m.beg[row];
+          int2* dst = reinterpret_cast<int2*>(sp + L.ent_off) + off;
+          uint8_t* rid = sp + L.rowid_off + off;
+          for (int i = 0; i < n; ++i) {
+            cp_async8(s32(dst + i), src + i);
+            if (ROWID) rid[i] = (uint8_t)row;
           }
+          const int npad = (n + pad_mask) & ~pad_mask;
+          for (int i = n; i < npad; ++i) dst[i] = make_int2(0, 0);   // zero-weight padding entries
+          float* tl = reinterpret_cast<float*>(sp + L.tail_off) + row * kMaxTail;
+          const float* ts = p.tail + g * p.T;
+          for (int t = 0; t < p.T; ++t) cp_async4(s32(tl + t), ts + t);
         }
-        if (g >= 0 && lane < p.T) cp_async4(s32(tail_s + row * kMaxTail + lane), p.tail + g * p.T + lane);
       }
       extra(tile, sp);
     }
@@ -250,11 +256,12 @@ __global__ void __launch_bounds__(kThreads, 1) bag_fwd_kernel(BagP p) {
   const Layout L = make_layout((size_t)p.F * SW, p.TR, p.ecap, SW, false);
   float4* Ws = reinterpret_cast<float4*>(smem_raw);
   const int h0 = blockIdx.x * SW;
+#pragma unroll 4
   for (int i = threadIdx.x; i < p.F * LPR; i += kThreads) {
     const int j = i / LPR, c = i - j * LPR;
     Ws[i] = ld_f4(p.WT + (int64_t)j * p.H + h0 + 4 * c);
   }
-  Ring ring(p, smem_raw, L);
+  Ring ring(p, smem_raw, L, 3);
   const int l = threadIdx.x % LPR, slot = threadIdx.x / LPR;
   const float4 b4 = p.bias ? ld_f4(p.bias + h0 + 4 * l) : make_float4(0.f, 0.f, 0.f, 0.f);
   const bool drop = p.dropout_p > 0.f;
@@ -270,11 +277,10 @@ __global__ void __launch_bounds__(kThreads, 1) bag_fwd_kernel(BagP p) {
     for (int row = slot; row < p.TR; row += kSlots) {
       const int64_t r = row0 + row;
       if (r >= ring.r_end) break;
-      const int n = m.n[row];
+      const int n = (m.n[row] + 3) & ~3;   // the stage pads every row to a multiple of four entries (zero weights)
       const int2* e = ent_s + m.off[row];
       float4 acc = b4;
-      int i = 0;
-      for (; i + 4 <= n; i += 4) {  // entries are broadcast loads; four weight rows in flight
+      for (int i = 0; i < n; i += 4) {  // entries are broadcast loads; four weight rows in flight
         const int2 e0 = e[i], e1 = e[i + 1], e2 = e[i + 2], e3 = e[i + 3];
         const float4 w0 = Wl[e0.x * LPR], w1 = Wl[e1.x * LPR], w2 = Wl[e2.x * LPR], w3 = Wl[e3.x * LPR];
         const float x0 = __int_as_float(e0.y), x1 = __int_as_float(e1.y), x2 = __int_as_float(e2.y), x3 = __int_as_float(e3.y);
@@ -282,12 +288,6 @@ __global__ void __launch_bounds__(kThreads, 1) bag_fwd_kernel(BagP p) {
         acc.x = fmaf(x1, w1.x, acc.x); acc.y = fmaf(x1, w1.y, acc.y); acc.z = fmaf(x1, w1.z, acc.z); acc.w = fmaf(x1, w1.w, acc.w);
         acc.x = fmaf(x2, w2.x, acc.x); acc.y = fmaf(x2, w2.y, acc.y); acc.z = fmaf(x2, w2.z, acc.z); acc.w = fmaf(x2, w2.w, acc.w);
         acc.x = fmaf(x3, w3.x, acc.x); acc.y = fmaf(x3, w3.y, acc.y); acc.z = fmaf(x3, w3.z, acc.z); acc.w = fmaf(x3, w3.w, acc.w);
-      }
-      for (; i < n; ++i) {
-        const int2 e0 = e[i];
-        const float4 w0 = Wl[e0.x * LPR];
-        const float x0 = __int_as_float(e0.y);
-        acc.x = fmaf(x0, w0.x, acc.x); acc.y = fmaf(x0, w0.y, acc.y); acc.z = fmaf(x0, w0.z, acc.z); acc.w = fmaf(x0, w0.w, acc.w);
       }
       for (int t = 0; t < p.T; ++t) {
         const float x0 = tail_s[row * kMaxTail + t];
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(kThreads, 1) bag_wgrad_kernel(BagP p) {
   const Layout L = make_layout((size_t)Fs * SW, p.TR, p.ecap, SW, true);
   float* acc = reinterpret_cast<float*>(smem_raw);  // [Fs][SW]
   for (int i = threadIdx.x; i < Fs * SW / 4; i += kThreads) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  Ring ring(p, smem_raw, L);
+  Ring ring(p, smem_raw, L, 0);
   const int lane = ring.lane, warp = ring.warp;
   const int h0 = blockIdx.x * SW;
 
@@ -468,7 +468,7 @@ static bool configure(int64_t H, int64_t F, int64_t tail_start, int64_t max_nnz,
   for (int sw : {64, 32}) {
     if (H % sw) continue;
     for (int TR : {64, 32}) {
-      const int ecap = (int)(TR * max_nnz);
+      const int ecap = (int)(TR * (wgrad ? max_nnz : (max_nnz + 3) / 4 * 4));
       const Layout L = make_layout((size_t)(wgrad ? tail_start : F) * sw, TR, ecap, sw, wgrad);
       const size_t red = (size_t)kWarps * (kMaxTail + 1) * sw * 4;
       if (L.total <= kSmemLimit && (!wgrad || red <= kStages * L.stage_bytes)) {
