@@ -8,11 +8,12 @@
 // int64 [N+1], entries (int32 column, fp32 value), at most max_nnz <= 64 per row - plus a dense [N, T] block for the
 // trailing T <= 8 columns that are non-zero in most rows (the z-scored numerics).  All arithmetic is fp32 FMA.
 //
-// Both kernels: CTA = (slice of SW = 64 | 32 hidden columns, chunk of rows), 16 warps, one CTA per SM.  The rows of a chunk
-// are staged through shared memory in tiles of TR = 64 | 32 rows by a 3-stage cp.async ring (two tiles in flight while one
-// is processed), and the dependent index chain  gather[r] -> rowptr[g] -> entries  is resolved by warp 0 three to five
-// tiles ahead (each of its loads is issued one iteration before its consumer), published through a 4-deep ring of
-// meta blocks (a tile's meta is written 3 iterations before the tile is processed), so that no warp ever waits for a dependent global load.
+// Both kernels: CTA = (slice of SW = 64 | 32 hidden columns, chunk of <= 1024 rows), 16 warps, one CTA per SM.
+//   1. the dependent index chain  gather[r] -> rowptr[g]  of the WHOLE chunk is resolved up front by all 512 threads at once
+//      (two global-memory latencies per CTA instead of two per tile) into a 12-byte-per-row table in shared memory
+//      (row id, first entry, entry count + offset inside the row's tile);
+//   2. the rows are then staged through shared memory in tiles of TR = 64 | 32 rows by a 3-stage cp.async ring (two tiles in
+//      flight while one is processed): entries, dense tail (and, for the weight gradient, the dh slice).
 //   bag_fwd_kernel   the slice of W1^T ([F][SW] fp32, 155 kB at F = 605) is loaded into shared memory once; SW/4 lanes per
 //                    row accumulate b1 + sum_j x_j W1^T[j] (entry = one broadcast 8-byte LDS, weight = one 16-byte LDS,
 //                    4 FMA), apply ReLU / Philox dropout / optional TF32 rounding (when the consumer is a tensor-core GEMM)
@@ -81,6 +82,7 @@ struct Layout {
   size_t ent_off, tail_off, dh_off, rowid_off, stage_bytes;
   size_t meta_off, meta_bytes, total;
 };
+constexpr int kChunkRows = 1024;  // rows per CTA (a multiple of every TR): bounds the meta table
 __host__ __device__ inline Layout make_layout(size_t main_floats, int TR, int ecap, int SW, bool wgrad) {
   Layout L;
   L.main_bytes = (main_floats * 4 + 127) / 128 * 128;
@@ -91,29 +93,22 @@ __host__ __device__ inline Layout make_layout(size_t main_floats, int TR, int ec
   L.rowid_off = o; o += wgrad ? ((size_t)ecap + 15) / 16 * 16 : 0;
   L.stage_bytes = (o + 127) / 128 * 128;
   L.meta_off = L.main_bytes + kStages * L.stage_bytes;
-  // per meta buffer: g[TR], beg[TR] (int64), n[TR], off[TR + 1] (int32)
-  L.meta_bytes = ((size_t)TR * 16 + (size_t)TR * 4 + (size_t)(TR + 1) * 4 + 127) / 128 * 128;
-  L.total = L.meta_off + 4 * L.meta_bytes;
+  // meta table of the chunk: g[rows] (int32), beg[rows] (uint32), offn[rows] (uint32: offset in the tile << 8 | count)
+  L.meta_bytes = (size_t)kChunkRows * 12;
+  L.total = L.meta_off + L.meta_bytes;
   return L;
 }
 
-struct MetaView {
-  int64_t* g;
-  int64_t* beg;
-  int* n;
-  int* off;
+struct MetaView {   // the chunk's row table; row = index inside the chunk
+  int* g;
+  uint32_t* beg;
+  uint32_t* offn;
+  __device__ __forceinline__ int n(int row) const { return (int)(offn[row] & 0xFFu); }
+  __device__ __forceinline__ int off(int row) const { return (int)(offn[row] >> 8); }
 };
-__device__ __forceinline__ MetaView meta_view(uint8_t* base, int TR) {
-  MetaView m;
-  m.g = reinterpret_cast<int64_t*>(base);
-  m.beg = m.g + TR;
-  m.n = reinterpret_cast<int*>(m.beg + TR);
-  m.off = m.n + TR;
-  return m;
-}
 
 // The tile pipeline shared by both kernels: run<ROWID>(extra, process) with extra(tile, stage) issuing additional
-// cp.async copies of a tile (wgrad: its dh slice) and process(tile, stage, meta) consuming a landed tile.
+// cp.async copies of a tile (wgrad: its dh slice) and process(tile, stage, meta, first row of the tile in the chunk).
 struct Ring {
   const BagP& p;
   uint8_t* smem;
@@ -121,10 +116,7 @@ struct Ring {
   int64_t r_begin, r_end;
   int ntiles, lane, warp, rpl;
   int pad_mask;  // 3: every row's entry list is padded to a multiple of 4 with zero entries (forward), 0: compact (wgrad)
-  // warp 0's look-ahead registers (rpl = TR / 32 rows per lane)
-  int64_t g_rp[2], beg_rp[2];  // rows whose rowptr has been loaded: the tile written to the meta block next
-  int n_rp[2];
-  int64_t g_ga[2];             // rows whose gather index has been loaded: the tile after that
+  MetaView m;
 
   __device__ Ring(const BagP& p_, uint8_t* smem_, const Layout& L_, int pad_mask_) : p(p_), smem(smem_), L(L_), pad_mask(pad_mask_) {
     lane = threadIdx.x & 31;
@@ -133,57 +125,53 @@ struct Ring {
     r_begin = (int64_t)blockIdx.y * p.rows_per_chunk;
     r_end = min(p.R, r_begin + p.rows_per_chunk);
     ntiles = (int)((r_end - r_begin + p.TR - 1) / p.TR);
+    m.g = reinterpret_cast<int*>(smem + L.meta_off);
+    m.beg = reinterpret_cast<uint32_t*>(m.g + kChunkRows);
+    m.offn = m.beg + kChunkRows;
   }
   __device__ __forceinline__ uint8_t* stage_ptr(int tile) const { return smem + L.main_bytes + (size_t)(tile % kStages) * L.stage_bytes; }
-  __device__ __forceinline__ MetaView meta(int tile) const { return meta_view(smem + L.meta_off + (size_t)(tile & 3) * L.meta_bytes, p.TR); }
-  __device__ __forceinline__ int64_t tile_row0(int tile) const { return r_begin + (int64_t)tile * p.TR; }
 
-  // ---- warp 0 only ----
-  __device__ __forceinline__ void load_gather(int tile) {
+  // gather -> rowptr for every row of the chunk: thread t takes the rows base + t*rpl .. +rpl-1, so that one warp covers
+  // exactly one tile and the offsets inside the tile are a warp scan
+  __device__ __forceinline__ void build_table() {
+    const int rows = ntiles * p.TR;
+    for (int base = 0; base < rows; base += kThreads * rpl) {
+      int64_t g[2] = {-1, -1};
+      int row[2];
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      g_ga[k] = -1;
-      if (k < rpl) {
-        const int64_t r = tile_row0(tile) + lane * rpl + k;
-        if (tile < ntiles && r < r_end) g_ga[k] = p.gather ? p.gather[r] : r;
+      for (int k = 0; k < 2; ++k) {
+        row[k] = base + (int)threadIdx.x * rpl + k;
+        if (k < rpl && row[k] < rows) {
+          const int64_t r = r_begin + row[k];
+          if (r < r_end) g[k] = p.gather ? p.gather[r] : r;
+        }
       }
-    }
-  }
-  __device__ __forceinline__ void load_rowptr() {  // for the rows in g_ga
+      int64_t beg[2] = {0, 0};
+      int n[2] = {0, 0};
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      g_rp[k] = g_ga[k];
-      beg_rp[k] = 0;
-      n_rp[k] = 0;
-      if (k < rpl && g_ga[k] >= 0) {
-        beg_rp[k] = p.rowptr[g_ga[k]];
-        n_rp[k] = min((int)(p.rowptr[g_ga[k] + 1] - beg_rp[k]), kMaxNnz);
+      for (int k = 0; k < 2; ++k)
+        if (g[k] >= 0) {
+          beg[k] = p.rowptr[g[k]];
+          n[k] = min((int)(p.rowptr[g[k] + 1] - beg[k]), kMaxNnz);
+        }
+      const int np0 = (n[0] + pad_mask) & ~pad_mask, np1 = (n[1] + pad_mask) & ~pad_mask;
+      const int s = np0 + np1;
+      int v = s;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
       }
-    }
-  }
-  __device__ __forceinline__ void write_meta(int tile) {  // scan of n over the tile's rows, then publish
-    MetaView m = meta(tile);
-    const int np0 = (n_rp[0] + pad_mask) & ~pad_mask, np1 = (n_rp[1] + pad_mask) & ~pad_mask;
-    const int s = np0 + (rpl > 1 ? np1 : 0);
-    int v = s;
+      int off = v - s;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int u = __shfl_up_sync(0xffffffffu, v, o);
-      if (lane >= o) v += u;
+      for (int k = 0; k < 2; ++k)
+        if (k < rpl && row[k] < rows) {
+          m.g[row[k]] = (int)g[k];
+          m.beg[row[k]] = (uint32_t)beg[k];
+          m.offn[row[k]] = ((uint32_t)off << 8) | (uint32_t)n[k];
+          off += k == 0 ? np0 : np1;
+        }
     }
-    int off = v - s;
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      if (k < rpl) {
-        const int row = lane * rpl + k;
-        m.g[row] = g_rp[k];
-        m.beg[row] = beg_rp[k];
-        m.n[row] = n_rp[k];
-        m.off[row] = off;
-        off += k == 0 ? np0 : np1;
-      }
-    }
-    if (lane == 31) m.off[p.TR] = v;
   }
 
   // ---- cp.async the entries / tail of a tile: thread t copies tile row t (a row has a handful of entries; a warp per row
@@ -192,23 +180,23 @@ struct Ring {
   __device__ __forceinline__ void stage(int tile, Extra& extra) {
     if (tile < ntiles) {
       uint8_t* sp = stage_ptr(tile);
-      const int row = threadIdx.x;
-      if (row < p.TR) {
-        const MetaView m = meta(tile);
-        const int64_t g = m.g[row];
+      const int trow = threadIdx.x;
+      if (trow < p.TR) {
+        const int row = tile * p.TR + trow;
+        const int g = m.g[row];
         if (g >= 0) {
-          const int n = m.n[row], off = m.off[row];
+          const int n = m.n(row), off = m.off(row);
           const int2* src = p.ent + m.beg[row];
           int2* dst = reinterpret_cast<int2*>(sp + L.ent_off) + off;
           uint8_t* rid = sp + L.rowid_off + off;
           for (int i = 0; i < n; ++i) {
             cp_async8(s32(dst + i), src + i);
-            if (ROWID) rid[i] = (uint8_t)row;
+            if (ROWID) rid[i] = (uint8_t)trow;
           }
           const int npad = (n + pad_mask) & ~pad_mask;
           for (int i = n; i < npad; ++i) dst[i] = make_int2(0, 0);   // zero-weight padding entries
-          float* tl = reinterpret_cast<float*>(sp + L.tail_off) + row * kMaxTail;
-          const float* ts = p.tail + g * p.T;
+          float* tl = reinterpret_cast<float*>(sp + L.tail_off) + trow * kMaxTail;
+          const float* ts = p.tail + (int64_t)g * p.T;
           for (int t = 0; t < p.T; ++t) cp_async4(s32(tl + t), ts + t);
         }
       }
@@ -219,29 +207,15 @@ struct Ring {
 
   template <bool ROWID, typename Extra, typename Process>
   __device__ __forceinline__ void run(Extra& extra, Process& process) {
-    // prologue: meta of tiles 0 and 1, stage them, meta of tile 2; look-ahead registers for tiles 3 (rowptr) and 4 (gather)
-    if (warp == 0) {
-      load_gather(0); load_rowptr(); write_meta(0);
-      load_gather(1); load_rowptr(); write_meta(1);
-    }
-    __syncthreads();
+    build_table();
+    __syncthreads();   // table (and whatever the kernel wrote to shared memory before) visible
     stage<ROWID>(0, extra);
     stage<ROWID>(1, extra);
-    if (warp == 0) {
-      load_gather(2); load_rowptr(); write_meta(2);
-      load_gather(3); load_rowptr();
-      load_gather(4);
-    }
     for (int tile = 0; tile < ntiles; ++tile) {
       asm volatile("cp.async.wait_group 1;" ::: "memory");  // tile `tile` has landed (this thread's copies)
-      __syncthreads();  // ... for everyone; tile - 1 is fully processed (its stage is free); meta(tile + 2) is visible
+      __syncthreads();  // ... for everyone; tile - 1 is fully processed (its stage is free)
       stage<ROWID>(tile + 2, extra);
-      if (warp == 0) {
-        write_meta(tile + 3);  // rowptr values were loaded one iteration ago
-        load_rowptr();         // tile + 4: its gather indices were loaded one iteration ago
-        load_gather(tile + 5);
-      }
-      process(tile, stage_ptr(tile), meta(tile));
+      process(tile, stage_ptr(tile), m, tile * p.TR);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
@@ -256,11 +230,11 @@ __global__ void __launch_bounds__(kThreads, 1) bag_fwd_kernel(BagP p) {
   const Layout L = make_layout((size_t)p.F * SW, p.TR, p.ecap, SW, false);
   float4* Ws = reinterpret_cast<float4*>(smem_raw);
   const int h0 = blockIdx.x * SW;
-#pragma unroll 4
-  for (int i = threadIdx.x; i < p.F * LPR; i += kThreads) {
+  for (int i = threadIdx.x; i < p.F * LPR; i += kThreads) {   // asynchronous: lands behind the index-chain prologue
     const int j = i / LPR, c = i - j * LPR;
-    Ws[i] = ld_f4(p.WT + (int64_t)j * p.H + h0 + 4 * c);
+    cp_async16(s32(Ws + i), p.WT + (int64_t)j * p.H + h0 + 4 * c, 16);
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");   // the oldest group: complete before tile 0 is consumed
   Ring ring(p, smem_raw, L, 3);
   const int l = threadIdx.x % LPR, slot = threadIdx.x / LPR;
   const float4 b4 = p.bias ? ld_f4(p.bias + h0 + 4 * l) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -270,15 +244,14 @@ __global__ void __launch_bounds__(kThreads, 1) bag_fwd_kernel(BagP p) {
   const float4* Wl = Ws + l;
 
   auto none = [](int, uint8_t*) {};
-  auto process = [&](int tile, uint8_t* sp, const MetaView& m) {
+  auto process = [&](int tile, uint8_t* sp, const MetaView& m, int crow0) {
     const int2* ent_s = reinterpret_cast<const int2*>(sp + L.ent_off);
     const float* tail_s = reinterpret_cast<const float*>(sp + L.tail_off);
-    const int64_t row0 = ring.tile_row0(tile);
     for (int row = slot; row < p.TR; row += kSlots) {
-      const int64_t r = row0 + row;
+      const int64_t r = ring.r_begin + crow0 + row;
       if (r >= ring.r_end) break;
-      const int n = (m.n[row] + 3) & ~3;   // the stage pads every row to a multiple of four entries (zero weights)
-      const int2* e = ent_s + m.off[row];
+      const int n = (m.n(crow0 + row) + 3) & ~3;   // the stage pads every row to a multiple of four entries (zero weights)
+      const int2* e = ent_s + m.off(crow0 + row);
       float4 acc = b4;
       for (int i = 0; i < n; i += 4) {  // entries are broadcast loads; four weight rows in flight
         const int2 e0 = e[i], e1 = e[i + 1], e2 = e[i + 2], e3 = e[i + 3];
@@ -320,7 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1) bag_fwd_kernel(BagP p) {
       st_f4(p.y + r * p.ldy + h0 + 4 * l, acc);
     }
   };
-  ring.run<false>(none, process);  // the first barrier inside run() also covers the W slice
+  ring.run<false>(none, process);
 }
 
 // W [H][ldw] -> WT [F][H]
@@ -359,7 +332,7 @@ __global__ void __launch_bounds__(kThreads, 1) bag_wgrad_kernel(BagP p) {
 
   auto extra = [&](int tile, uint8_t* sp) {  // the dh slice of the tile: TR rows x SW floats in 16-byte pieces
     float* dh_s = reinterpret_cast<float*>(sp + L.dh_off);
-    const int64_t r0 = ring.tile_row0(tile);
+    const int64_t r0 = ring.r_begin + (int64_t)tile * p.TR;
     for (int i = threadIdx.x; i < p.TR * (SW / 4); i += kThreads) {
       const int row = i / (SW / 4), c = i - row * (SW / 4);
       const int64_t r = r0 + row;
@@ -367,12 +340,12 @@ __global__ void __launch_bounds__(kThreads, 1) bag_wgrad_kernel(BagP p) {
       cp_async16(s32(dh_s + (size_t)row * SW + 4 * c), ok ? (const void*)(p.dh + r * p.lddh + h0 + 4 * c) : (const void*)p.dh, ok ? 16 : 0);
     }
   };
-  auto process = [&](int tile, uint8_t* sp, const MetaView& m) {
+  auto process = [&](int tile, uint8_t* sp, const MetaView& m, int crow0) {
     const int2* ent_s = reinterpret_cast<const int2*>(sp + L.ent_off);
     const float* tail_s = reinterpret_cast<const float*>(sp + L.tail_off);
     const float* dh_s = reinterpret_cast<const float*>(sp + L.dh_off);
     const uint8_t* rowid_s = sp + L.rowid_off;
-    const int E = m.off[p.TR];
+    const int E = m.off(crow0 + p.TR - 1) + m.n(crow0 + p.TR - 1);
     // sparse columns: flat scan, 32 entries at a time; this warp applies the entries of the columns it owns, in order
     for (int base = 0; base < E; base += 32) {
       int2 e = make_int2(-1, 0);
@@ -396,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, 1) bag_wgrad_kernel(BagP p) {
       }
     }
     // dense tail + bias gradient: warp w takes the tile rows w, w + 16, ...
-    const int rows_here = (int)min((int64_t)p.TR, ring.r_end - ring.tile_row0(tile));
+    const int rows_here = (int)min((int64_t)p.TR, ring.r_end - (ring.r_begin + crow0));
     for (int row = warp; row < rows_here; row += kWarps) {
       float d[CPL];
 #pragma unroll
@@ -479,11 +452,14 @@ static bool configure(int64_t H, int64_t F, int64_t tail_start, int64_t max_nnz,
   }
   return false;
 }
-static int64_t chunks_for(int64_t R, int slices, int TR) {
+// rows per CTA: one chunk per SM where that keeps a chunk within the meta table (kChunkRows), more (smaller) chunks otherwise
+static int64_t rows_per_chunk_for(int64_t R, int slices, int TR) {
   int64_t c = num_sms() / slices;
   if (c < 1) c = 1;
-  const int64_t by_rows = ceil_div(R, TR);
-  return c < by_rows ? c : (by_rows < 1 ? 1 : by_rows);
+  int64_t rows = align_up(ceil_div(R, c), TR);
+  if (rows > kChunkRows) rows = kChunkRows;
+  if (rows < TR) rows = TR;
+  return rows;
 }
 
 }  // namespace bag
@@ -500,9 +476,13 @@ extern "C" int ttam_bag_supported(int64_t H, int64_t F, int64_t T, int64_t max_n
 extern "C" int64_t ttam_bag_linear_workspace_bytes(int64_t R, int64_t H, int64_t F) {
   // forward: W^T; weight gradient: one [F+1][H] partial per row chunk (at most one chunk per SM)
   const int64_t fwd = align_up(F * H * 4, 256);
-  int64_t chunks = ceil_div(R, 32);
-  if (chunks > num_sms()) chunks = num_sms();
-  if (chunks < 1) chunks = 1;
+  // chunk count of the configuration with the most chunks (slices = H / 64 or H / 32, TR = 32)
+  int64_t chunks = 1;
+  for (int sw : {64, 32})
+    if (H % sw == 0) {
+      const int64_t c = ceil_div(R > 0 ? R : 1, rows_per_chunk_for(R > 0 ? R : 1, (int)(H / sw), 32));
+      if (c > chunks) chunks = c;
+    }
   const int64_t wg = chunks * (F + 1) * H * 4;
   return (fwd > wg ? fwd : wg) + 256;
 }
@@ -540,8 +520,7 @@ extern "C" int ttam_bag_linear_fwd(const int64_t* rowptr, const void* entries, c
   p.WT = WT; p.bias = bias; p.y = y; p.ldy = ldy; p.relu = act == TTAM_ACT_RELU;
   p.dropout_p = dropout_p; p.seed = seed; p.offset = offset; p.st = (const ttam_step_state*)state_dev; p.round_out = round_tf32_out;
   const int slices = (int)(H / cfg.sw);
-  const int64_t chunks = chunks_for(R, slices, cfg.TR);
-  p.rows_per_chunk = align_up(ceil_div(R, chunks), cfg.TR);
+  p.rows_per_chunk = rows_per_chunk_for(R, slices, cfg.TR);
   dim3 grid((unsigned)slices, (unsigned)ceil_div(R, p.rows_per_chunk));
   if (cfg.sw == 64) {
     static bool done = false;
@@ -576,8 +555,7 @@ extern "C" int ttam_bag_linear_wgrad(const int64_t* rowptr, const void* entries,
     BagP p{};
     fill_common(p, rowptr, entries, tail, T, tail_start, gather, R, H, F, cfg);
     p.dh = dh; p.lddh = lddh; p.partial = (float*)workspace;
-    const int64_t chunks = chunks_for(R, slices, cfg.TR);
-    p.rows_per_chunk = align_up(ceil_div(R, chunks), cfg.TR);
+    p.rows_per_chunk = rows_per_chunk_for(R, slices, cfg.TR);
     dim3 grid((unsigned)slices, (unsigned)ceil_div(R, p.rows_per_chunk));
     const int64_t real_chunks = grid.y;
     if (cfg.sw == 64) {

@@ -218,7 +218,7 @@ class BagMatrix:
         if X.dtype != torch.float32 or X.dim() != 2:
             raise ValueError("BagMatrix.build needs a 2-D float32 matrix")
         N, Fd = X.shape
-        if N == 0 or Fd == 0:
+        if N == 0 or Fd == 0 or N >= 2 ** 31:      # the kernels keep row ids as int32 in shared memory
             return None
         # dense tail: the longest suffix of columns (<= 8) that are non-zero in at least half of the rows
         probe = X[: min(N, 1 << 16), max(0, Fd - BAG_MAX_TAIL):]
@@ -248,6 +248,8 @@ class BagMatrix:
         torch.cumsum(cnt, 0, out=rowptr[1:])
         col = torch.cat(cols)
         val = torch.cat(vals)
+        if col.numel() >= 2 ** 32:                  # ... and entry offsets as uint32
+            return None
         entries = torch.empty((max(col.numel(), 1), 2), dtype=torch.int32, device=X.device)
         if col.numel():
             entries[:, 0] = col
