@@ -41,6 +41,11 @@ extern "C" {
  * out), so the GEMM skips its in-place rounding pass for it.  X: x of linear_fwd / linear_wgrad; W: w of linear_fwd. */
 #define TTAM_PREC_X_ROUNDED 0x100
 #define TTAM_PREC_W_ROUNDED 0x200
+/* the GEMM writes its result rounded to TF32 (for outputs whose only consumers are tensor-core GEMMs and sign masks:
+ * the consumer is then called with TTAM_PREC_X_ROUNDED; the values it multiplies are the same either way) */
+#define TTAM_PREC_OUT_ROUNDED 0x400
+/* ttam_linear_dgrad only: `w` is the TF32-rounded TRANSPOSED weight [K, N] written by ttam_prepare_weights */
+#define TTAM_PREC_WT 0x800
 #define TTAM_PREC_BF16 2 /* reserved (the retrieval path, ttam_topk_bf16, is the bf16 tensor-core kernel) */
 
 /* dense optimiser kinds (training.py:1315-1333) */
@@ -95,6 +100,11 @@ int ttam_linear_fwd(const float* x, int64_t ldx, const int64_t* gather, const fl
 int ttam_linear_dgrad(const float* dy, int64_t lddy, const float* w, float* dx, int64_t lddx,
                       const float* aux, int64_t ldaux, int mask_mode, float scale, int accumulate,
                       int64_t M, int64_t N, int64_t K, int precision, void* stream);
+/* Once per step, for up to 4 small weight matrices src[i] [rows, cols] (row stride ld): dst[i] = TF32-rounded copy
+ * [rows, cols], dst_t[i] = TF32-rounded transposed copy [cols, rows] (either may be null).  With them the forward GEMMs
+ * (TTAM_PREC_W_ROUNDED) and the data-gradient GEMMs (TTAM_PREC_WT) of a layer both run on the TMA-fed kernel. */
+int ttam_prepare_weights(const float* const* src, const int64_t* ld, const int64_t* rows, const int64_t* cols,
+                         float* const* dst, float* const* dst_t, int64_t count, void* stream);
 int64_t ttam_linear_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int ttam_linear_wgrad(const float* dy, int64_t lddy, const float* x, int64_t ldx, const int64_t* gather,
                       float* dw, float* db, int64_t M, int64_t N, int64_t K, int accumulate,
@@ -159,6 +169,9 @@ typedef struct {
   int64_t bag_T, bag_tail_start, bag_max_nnz;
   void* bag_scratch;          /* >= F*H*4 bytes, private to this tower (ttam_tower_fwd transposes W1 into it) */
   int64_t bag_scratch_bytes;
+  /* TF32 path: room for the rounded / rounded-transposed copies of W2 [D,H], G1 [Hg,2D], G2 [D,Hg] (all six or none);
+   * ttam_tower_fwd fills them (ttam_prepare_weights), forward and backward GEMMs of the chain read them */
+  float *W2r, *W2rT, *G1r, *G1rT, *G2r, *G2rT;
 } ttam_tower_desc;
 typedef struct { float *z, *hd, *a, *pre2, *g, *t, *o, *q; } ttam_tower_bufs;
 typedef struct {

@@ -616,3 +616,51 @@ def test_bag_linear_fwd_tf32_rounded_output(F):
     y = F.bag_linear_fwd(bag, idx, dev(W), None)
     yr = F.bag_linear_fwd(bag, idx, dev(W), None, round_tf32_out=True)
     assert torch.equal(yr, F.round_tf32_(y.clone()))
+
+
+# ---- TMA-fed persistent TF32 GEMM (csrc/gemm_tma.cu): forward with a prepared weight, dgrad with its transposed copy ----
+@pytest.mark.parametrize("M,N,K", [(49152, 96, 192), (130, 96, 192), (257, 96, 96), (64, 16, 32), (4099, 256, 64), (128, 300, 128),
+                                   (1000, 512, 256), (5, 96, 100), (20000, 192, 96)])
+def test_tma_gemm_forward_matches_cp_async_kernel_bit_for_bit(F, M, N, K):
+    """Same operands, same TF32 rounding, same K order of the tcgen05.mma: the TMA-fed kernel must reproduce the cp.async
+    kernel's bits (and with them its error bound against the fp64 product); ReLU, bias, rounded output, pre-rounded A."""
+    rng = np.random.default_rng(M + N + K)
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    W = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    b = (rng.standard_normal(N) * 0.1).astype(np.float32)
+    (Wr,), (WrT,) = F.prepare_weights([dev(W)])
+    assert torch.equal(Wr, F.round_tf32_(dev(W))) and torch.equal(WrT, Wr.t().contiguous())
+    ref = F.linear_fwd(dev(x), dev(W), dev(b), act="relu", precision="tf32")                      # cp.async kernel (weight not prepared)
+    got = F.linear_fwd(dev(x), Wr, dev(b), act="relu", precision="tf32", w_rounded=True)          # TMA kernel
+    assert torch.equal(got, ref)
+    _tf32_close(F.linear_fwd(dev(x), Wr, dev(b), precision="tf32", w_rounded=True).cpu().numpy() - b, x, W.T)
+    xr = F.round_tf32_(dev(x))
+    assert torch.equal(F.linear_fwd(xr, Wr, dev(b), act="relu", precision="tf32", w_rounded=True, x_rounded=True), ref)
+    got_r = F.linear_fwd(dev(x), Wr, dev(b), act="relu", precision="tf32", w_rounded=True, out_rounded=True)
+    assert torch.equal(got_r, F.round_tf32_(ref.clone()))
+    # strided output view (z[:, D:]) and strided input view
+    z = torch.zeros((M, N + 32), device="cuda")
+    F.linear_fwd(dev(x), Wr, dev(b), act="relu", out=z[:, 32:], precision="tf32", w_rounded=True)
+    assert torch.equal(z[:, 32:], ref) and float(z[:, :32].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("M,N,K", [(49152, 96, 192), (4096, 96, 96), (3000, 192, 96), (700, 96, 96), (999, 48, 36), (333, 512, 256)])
+def test_tma_gemm_dgrad_with_transposed_weight(F, M, N, K):
+    rng = np.random.default_rng(M + 3 * N + K)
+    dy = rng.standard_normal((M, N)).astype(np.float32)
+    W = rng.standard_normal((N, K)).astype(np.float32)
+    aux = rng.standard_normal((M, K)).astype(np.float32)
+    (_,), (WrT,) = F.prepare_weights([dev(W)])
+    ref = F.linear_dgrad(dev(dy), dev(W), precision="tf32")
+    got = F.linear_dgrad(dev(dy), WrT, precision="tf32", w_transposed=True)
+    assert torch.equal(got, ref)
+    _tf32_close(got.cpu().numpy(), dy, W)
+    got_m = F.linear_dgrad(dev(dy), WrT, aux=dev(aux), relu_mask=True, scale=1.25, precision="tf32", w_transposed=True)
+    assert torch.equal(got_m, F.linear_dgrad(dev(dy), dev(W), aux=dev(aux), relu_mask=True, scale=1.25, precision="tf32"))
+    base = rng.standard_normal((M, K)).astype(np.float32)
+    out, out_ref = dev(base), dev(base)
+    F.linear_dgrad(dev(dy), WrT, out=out, accumulate=True, precision="tf32", w_transposed=True)
+    F.linear_dgrad(dev(dy), dev(W), out=out_ref, accumulate=True, precision="tf32")
+    assert torch.equal(out, out_ref)
+    got_r = F.linear_dgrad(dev(dy), WrT, precision="tf32", w_transposed=True, out_rounded=True)
+    assert torch.equal(got_r, F.round_tf32_(ref.clone()))

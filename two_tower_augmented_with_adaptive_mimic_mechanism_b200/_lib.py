@@ -22,7 +22,7 @@ NVCC_FLAGS = [
 
 ACT = {"none": 0, None: 0, "identity": 0, "relu": 1, "gelu": 2, "tanh": 3, "selu": 4}
 PREC = {"fp32": 0, "tf32": 1, "bf16": 2}
-PREC_X_ROUNDED, PREC_W_ROUNDED = 0x100, 0x200
+PREC_X_ROUNDED, PREC_W_ROUNDED, PREC_OUT_ROUNDED, PREC_WT = 0x100, 0x200, 0x400, 0x800
 OPT = {"adamw": 0, "adam": 1, "sgd": 2}
 MAX_TENSORS = 48
 
@@ -49,6 +49,7 @@ class TowerDesc(C.Structure):
         ("bag_rowptr", C.c_void_p), ("bag_entries", C.c_void_p), ("bag_tail", C.c_void_p),
         ("bag_T", C.c_int64), ("bag_tail_start", C.c_int64), ("bag_max_nnz", C.c_int64),
         ("bag_scratch", C.c_void_p), ("bag_scratch_bytes", C.c_int64),
+        ("W2r", C.c_void_p), ("W2rT", C.c_void_p), ("G1r", C.c_void_p), ("G1rT", C.c_void_p), ("G2r", C.c_void_p), ("G2rT", C.c_void_p),
     ]
 
 
@@ -120,6 +121,7 @@ SIGNATURES = {
     "ttam_act_bwd": (C.c_int, [_p, _p, _p, _i64, _i64, _i32, _f, _u64, _u64, _p, _p]),
     "ttam_linear_fwd": (C.c_int, [_p, _i64, _p, _p, _i64, _p, _p, _i64, _i64, _i64, _i64, _i32, _f, _u64, _u64, _p, _i32, _p]),
     "ttam_linear_dgrad": (C.c_int, [_p, _i64, _p, _p, _i64, _p, _i64, _i32, _f, _i32, _i64, _i64, _i64, _i32, _p]),
+    "ttam_prepare_weights": (C.c_int, [_p, _p, _p, _p, _p, _p, _i64, _p]),
     "ttam_linear_wgrad_workspace_bytes": (C.c_int64, [_i64, _i64, _i64]),
     "ttam_linear_wgrad": (C.c_int, [_p, _i64, _p, _i64, _p, _p, _p, _i64, _i64, _i64, _i32, _p, _i64, _i32, _p]),
     "ttam_gate_fwd": (C.c_int, [_p, _p, _p, _i64, _p, _p, _p, _p, _p, _i64, _i64, _p]),

@@ -127,10 +127,20 @@ extern "C" int ttam_linear_fwd(const float* x, int64_t ldx, const int64_t* gathe
   if (M == 0) return TTAM_OK;
   TTAM_CHECK_ARG(ldw >= K, "linear_fwd: ldw < K");
   const int prerounded = (precision >> 8) & 3;  // TTAM_PREC_X_ROUNDED / TTAM_PREC_W_ROUNDED
+  const int round_out = (precision & TTAM_PREC_OUT_ROUNDED) ? 1 : 0;
   precision &= 0xFF;
-  if (precision == TTAM_PREC_TF32)
-    return tc_linear_fwd(x, ldx, gather, w, ldw, bias, y, ldy, M, N, K, act, dropout_p, seed, offset, state_dev, prerounded,
-                         (cudaStream_t)stream);
+  if (precision == TTAM_PREC_TF32) {
+    if (!gather && (prerounded & 2) && (act == TTAM_ACT_NONE || act == TTAM_ACT_RELU)) {
+      // plain K-major operands with a pre-rounded weight: the TMA-fed persistent kernel (gemm_tma.cu)
+      const int rc = tma_gemm(x, ldx, w, ldw, y, ldy, M, N, K, bias, act == TTAM_ACT_RELU, dropout_p, seed, offset, state_dev,
+                              nullptr, 0, 0, 1.f, 0, !(prerounded & 1), round_out, (cudaStream_t)stream);
+      if (rc <= 0) return rc;
+    }
+    const int rc = tc_linear_fwd(x, ldx, gather, w, ldw, bias, y, ldy, M, N, K, act, dropout_p, seed, offset, state_dev, prerounded,
+                                 (cudaStream_t)stream);
+    if (rc != TTAM_OK || !round_out) return rc;
+    return ttam_round_tf32(y, ldy, M, N, stream);
+  }
   if (precision != TTAM_PREC_FP32) {
     set_error("linear_fwd: precision %d is not built into this library", precision);
     return TTAM_EUNSUPPORTED;
@@ -152,9 +162,25 @@ extern "C" int ttam_linear_dgrad(const float* dy, int64_t lddy, const float* w, 
   TTAM_CHECK_ARG(M >= 0 && N > 0 && K > 0 && lddy >= N && lddx >= K, "linear_dgrad: bad shape");
   TTAM_CHECK_ARG(mask_mode == 0 || (mask_mode == 1 && aux && ldaux >= K), "linear_dgrad: bad mask arguments");
   if (M == 0) return TTAM_OK;
+  const int flags = precision;
   precision &= 0xFF;
-  if (precision == TTAM_PREC_TF32)
-    return tc_linear_dgrad(dy, lddy, w, dx, lddx, aux, ldaux, mask_mode, scale, accumulate, M, N, K, (cudaStream_t)stream);
+  if (flags & TTAM_PREC_WT) {
+    // w is the TF32-rounded TRANSPOSED weight [K, N] (ttam_prepare_weights): dx = dy . w is then the K-major x K-major
+    // product of the TMA-fed kernel
+    TTAM_CHECK_ARG(precision == TTAM_PREC_TF32, "linear_dgrad: TTAM_PREC_WT needs TTAM_PREC_TF32");
+    const int rc = tma_gemm(dy, lddy, w, N, dx, lddx, M, K, N, nullptr, 0, 0.f, 0, 0, nullptr, aux, ldaux, mask_mode, scale, accumulate,
+                            !(flags & TTAM_PREC_X_ROUNDED), (flags & TTAM_PREC_OUT_ROUNDED) ? 1 : 0, (cudaStream_t)stream);
+    if (rc == 1) {
+      set_error("linear_dgrad: TTAM_PREC_WT needs 16-byte aligned operands and N %% 4 == 0");
+      return TTAM_EINVAL;
+    }
+    return rc;
+  }
+  if (precision == TTAM_PREC_TF32) {
+    const int rc = tc_linear_dgrad(dy, lddy, w, dx, lddx, aux, ldaux, mask_mode, scale, accumulate, M, N, K, (cudaStream_t)stream);
+    if (rc != TTAM_OK || !(flags & TTAM_PREC_OUT_ROUNDED)) return rc;
+    return ttam_round_tf32(dx, lddx, M, K, stream);
+  }
   if (precision != TTAM_PREC_FP32) {
     set_error("linear_dgrad: precision %d is not built into this library", precision);
     return TTAM_EUNSUPPORTED;

@@ -18,4 +18,11 @@ int tc_linear_wgrad_partials(const float* dy, int64_t lddy, const float* x, int6
                              float* colsum_partial, int64_t M, int64_t N, int64_t K, int* real_splits, int prerounded,
                              cudaStream_t st);
 
+// gemm_tma.cu: C[M,N] = A[M,K] . B[N,K]^T with TMA-fed operands (B pre-rounded to TF32; A rounded in the kernel when roundA).
+// Returns TTAM_OK, a negative error, or +1 when the operands do not qualify (alignment): the caller falls back to tc_linear_*.
+int tma_gemm(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+             const float* bias, int relu, float dropout_p, uint64_t seed, uint64_t offset, const ttam_step_state* st,
+             const float* aux, int64_t ldaux, int mask_mode, float scale, int accumulate, int roundA, int round_out,
+             cudaStream_t stream);
+
 }  // namespace ttam

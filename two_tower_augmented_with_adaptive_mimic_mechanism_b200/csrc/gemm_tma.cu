@@ -1,0 +1,363 @@
+// TMA-fed, persistent, warp-specialised TF32 GEMM (tcgen05.mma kind::tf32, fp32 accumulate in TMEM) for the K-major x
+// K-major products of the tower chain: the forward GEMMs  y = x . w^T  of nn.Linear (reference encoders.py:121-144,157-162)
+// on activation matrices that are NOT row-gathered, and their data gradients  dx = dy . w  taken against a transposed copy of
+// the weight (ttam_prepare_weights), which makes them the same product.
+//
+//   C[M, N] = A[M, K] . B[N, K]^T      A: activations, rows lda floats apart;  B: weight (or transposed weight), pre-rounded to TF32
+//
+// Why a second GEMM kernel: gemm_tc.cu stages its operands with 8 producer warps (cp.async + an in-place rounding pass +
+// a per-chunk mbarrier hand-shake) because it also has to gather rows and to lay out MN-major operands; for plain K-major
+// operands that machinery is the bottleneck (ncu: 1.3 % tensor pipe, 12 % DRAM, latency-bound: profiles/r1_gemm_*).  Here
+//   warp 0      one thread issues cp.async.bulk.tensor (TMA, 128-byte swizzle) for A and B chunks of 32 reduction elements into
+//               a ring of shared-memory stages - no registers, no per-thread copies, the swizzled UMMA layout comes for free
+//   warp 1      one thread issues 4 tcgen05.mma (M = 128, N = bn <= 256, K = 8) per chunk; accumulators are DOUBLE-BUFFERED in
+//               TMEM, so the tensor core starts tile t+1 while tile t is drained
+//   warps 2-5   epilogue: tcgen05.ld (thread = output row), bias / ReLU / ReLU-mask / scale / accumulate / Philox dropout /
+//               optional TF32 rounding of the output, 16-byte stores
+//   warps 6-9   only when A is not pre-rounded: round the landed A chunk to TF32 (nearest) in place before the MMA reads it -
+//               the tensor core would truncate (same arithmetic as gemm_tc.cu: results are bit-identical)
+// CTAs are persistent (one per SM) and walk the (M tile, N tile) units round-robin.
+#include "gemm_tc.cuh"
+#include "sm100.cuh"
+#include <cstdlib>
+
+namespace ttam {
+namespace tma {
+
+using namespace ttam::sm100;
+
+constexpr int kBM = 128;
+constexpr int kKC = 32;                   // reduction elements per stage: one 128-byte swizzled row of fp32
+constexpr uint32_t kABytes = kBM * 128;   // 16 KB
+constexpr int kEpiWarps = 4, kRoundWarps = 4;
+constexpr int kThreads = 32 * (2 + kEpiWarps + kRoundWarps);
+constexpr int kMaxStages = 8;
+
+struct TmaP {
+  float* C;
+  int64_t ldc;
+  int M, N, K;
+  int bn, acc_stride, n_tiles_n, units, nchunks, stages;
+  int roundA, round_out, vecC, vecAux, vecBias;
+  const float* bias;
+  int relu;
+  float dropout_p;
+  uint64_t seed, offset;
+  const ttam_step_state* st;
+  const float* aux;
+  int64_t ldaux;
+  int mask_mode;
+  float scale;
+  int accumulate;
+};
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  const uint32_t u = __float_as_uint(x);
+  return ((u & 0x7F800000u) != 0x7F800000u) ? u + 0x1000u : u;
+}
+__device__ __forceinline__ float round_out_tf32(float x) {
+  const uint32_t u = __float_as_uint(x);
+  return __uint_as_float(((u & 0x7F800000u) != 0x7F800000u) ? ((u + 0x1000u) & 0xFFFFE000u) : u);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tf32_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TmaP p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t stage_bytes = kABytes + (uint32_t)p.bn * 128u;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (uint32_t)p.stages * stage_bytes);
+  uint64_t* full = bars;                          // [stages]  TMA bytes landed
+  uint64_t* ready = bars + kMaxStages;            // [stages]  A chunk rounded (only when roundA)
+  uint64_t* empty = bars + 2 * kMaxStages;        // [stages]  MMAs that read the stage have completed
+  uint64_t* acc_full = bars + 3 * kMaxStages;     // [2]
+  uint64_t* acc_empty = bars + 3 * kMaxStages + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kMaxStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tmem_cols = 2 * p.acc_stride <= 32 ? 32u : 2 * p.acc_stride <= 64 ? 64u : 2 * p.acc_stride <= 128 ? 128u
+                             : 2 * p.acc_stride <= 256 ? 256u : 512u;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(full + i, 1);
+      mbar_init(ready + i, kRoundWarps);
+      mbar_init(empty + i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(acc_full + i, 1);
+      mbar_init(acc_empty + i, kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+        const int mt = u / p.n_tiles_n, nt = u - mt * p.n_tiles_n;
+        for (int c = 0; c < p.nchunks; ++c, ++it) {
+          const int stage = it % p.stages;
+          mbar_wait_relaxed(empty + stage, ((it / p.stages) & 1) ^ 1, 64);
+          uint8_t* sA = smem + (uint32_t)stage * stage_bytes;
+          mbar_expect_tx(full + stage, stage_bytes);
+          tma_load_2d(sA, &tmA, full + stage, c * kKC, mt * kBM);
+          tma_load_2d(sA + kABytes, &tmB, full + stage, c * kKC, nt * p.bn);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(2 /*tf32*/, kBM, p.bn, 0, 0);
+      uint32_t it = 0, un = 0;
+      for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++un) {
+        const int buf = un & 1;
+        mbar_wait(acc_empty + buf, ((un >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(buf * p.acc_stride);
+        for (int c = 0; c < p.nchunks; ++c, ++it) {
+          const int stage = it % p.stages;
+          mbar_wait((p.roundA ? ready : full) + stage, (it / p.stages) & 1);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + (uint32_t)stage * stage_bytes);
+          const uint32_t sB = sA + kABytes;
+#pragma unroll
+          for (int ks = 0; ks < kKC / 8; ++ks)
+            umma_tf32(d_tmem, make_kmajor_desc<128>(sA + ks * 32), make_kmajor_desc<128>(sB + ks * 32), idesc, (c | ks) != 0 ? 1u : 0u);
+          umma_commit(empty + stage);
+        }
+        umma_commit(acc_full + buf);
+      }
+    }
+  } else if (warp < 2 + kEpiWarps) {
+    // ===================== epilogue: thread = output row =====================
+    const int quad = warp & 3;   // the TMEM lanes this warp may read: 32*quad .. +31
+    const bool drop = p.dropout_p > 0.f;
+    const float keep_scale = drop ? 1.f / (1.f - p.dropout_p) : 1.f;
+    const uint64_t rng_base = p.offset + ((drop && p.st) ? p.st->rng_offset : 0ull);
+    uint32_t un = 0;
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++un) {
+      const int mt = u / p.n_tiles_n, nt = u - mt * p.n_tiles_n;
+      const int buf = un & 1;
+      const int m = mt * kBM + quad * 32 + lane, n0 = nt * p.bn;
+      mbar_wait(acc_full + buf, (un >> 1) & 1);
+      tc_fence_after();
+      for (int col = 0; col < p.bn; col += 16) {
+        uint32_t r[16];
+        tmem_ld_32x16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.acc_stride + col), r);
+        if (m < p.M && n0 + col < p.N) {
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+          const bool full16 = n0 + col + 15 < p.N;
+          if (p.bias) {
+            if (p.vecBias && full16) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                const float4 b4 = ld_f4(p.bias + n0 + col + i);
+                v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (n0 + col + i < p.N) v[i] += p.bias[n0 + col + i];
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (drop) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int n = n0 + col + i;
+              if (n < p.N) v[i] = dropout_keep(p.seed, rng_base + (uint64_t)m * (uint64_t)p.N + (uint64_t)n, p.dropout_p) ? v[i] * keep_scale : 0.f;
+            }
+          }
+          if (p.mask_mode == 1) {
+            const float* ax = p.aux + (int64_t)m * p.ldaux + n0 + col;
+            if (p.vecAux && full16) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                const float4 a4 = ld_f4(ax + i);
+                v[i] = a4.x > 0.f ? v[i] : 0.f; v[i + 1] = a4.y > 0.f ? v[i + 1] : 0.f;
+                v[i + 2] = a4.z > 0.f ? v[i + 2] : 0.f; v[i + 3] = a4.w > 0.f ? v[i + 3] : 0.f;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (n0 + col + i < p.N) v[i] = (ax[i] > 0.f) ? v[i] : 0.f;
+            }
+          }
+          if (p.scale != 1.f) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] *= p.scale;
+          }
+          float* dst = p.C + (int64_t)m * p.ldc + n0 + col;
+          if (p.vecC && full16) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              if (p.accumulate) {
+                const float4 old = ld_f4(dst + i);
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+              }
+              if (p.round_out) {
+                o.x = round_out_tf32(o.x); o.y = round_out_tf32(o.y); o.z = round_out_tf32(o.z); o.w = round_out_tf32(o.w);
+              }
+              st_f4(dst + i, o);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (n0 + col + i < p.N) {
+                float o = p.accumulate ? dst[i] + v[i] : v[i];
+                dst[i] = p.round_out ? round_out_tf32(o) : o;
+              }
+          }
+        }
+        __syncwarp();  // tcgen05.ld is warp-collective: reconverge before the next one
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty + buf);
+    }
+  } else if (p.roundA) {
+    // ===================== rounding warps: A chunk -> nearest TF32, in place =====================
+    const int t = threadIdx.x - 32 * (2 + kEpiWarps);   // 0 .. 127
+    uint32_t it = 0;
+    for (int u = blockIdx.x; u < p.units; u += gridDim.x) {
+      for (int c = 0; c < p.nchunks; ++c, ++it) {
+        const int stage = it % p.stages;
+        mbar_wait(full + stage, (it / p.stages) & 1);
+        uint8_t* sA = smem + (uint32_t)stage * stage_bytes;
+#pragma unroll
+        for (int i = 0; i < (int)(kABytes / 16) / (32 * kRoundWarps); ++i) {
+          uint4* q = reinterpret_cast<uint4*>(sA) + t + 32 * kRoundWarps * i;
+          const float4 v = *reinterpret_cast<float4*>(q);
+          *q = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ready + stage);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+}  // namespace tma
+
+using namespace tma;
+
+// Returns TTAM_OK, an error, or +1 when the operands do not qualify for TMA (the caller falls back to gemm_tc.cu).
+int tma_gemm(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+             const float* bias, int relu, float dropout_p, uint64_t seed, uint64_t offset, const ttam_step_state* st,
+             const float* aux, int64_t ldaux, int mask_mode, float scale, int accumulate, int roundA, int round_out,
+             cudaStream_t stream) {
+  if (!aligned16(A) || !aligned16(B) || lda % 4 || ldb % 4 || K % 4 || M <= 0 || N <= 0 || K <= 0) return 1;
+  if (getenv("TTAM_NO_TMA_GEMM")) return 1;
+  TmaP p{};
+  p.C = C; p.ldc = ldc; p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  // N tile: a multiple of 16 (UMMA N for M = 128), at most 256; wide N is split into equal tiles
+  const int n_tiles = (int)ceil_div(N, 256);
+  p.bn = (int)align_up(ceil_div(N, n_tiles), 16);
+  p.n_tiles_n = (int)ceil_div(N, p.bn);
+  p.acc_stride = (int)align_up(p.bn, 32);
+  p.units = (int)ceil_div(M, kBM) * p.n_tiles_n;
+  p.nchunks = (int)ceil_div(K, kKC);
+  const size_t stage_bytes = kABytes + (size_t)p.bn * 128;
+  p.stages = (int)((200 * 1024) / stage_bytes);
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  if (p.stages < 2) return 1;
+  p.roundA = roundA; p.round_out = round_out;
+  p.vecC = aligned16(C) && ldc % 4 == 0;
+  p.bias = bias; p.vecBias = bias != nullptr && aligned16(bias);
+  p.relu = relu; p.dropout_p = dropout_p; p.seed = seed; p.offset = offset; p.st = st;
+  p.aux = aux; p.ldaux = ldaux; p.mask_mode = mask_mode; p.vecAux = aux != nullptr && aligned16(aux) && ldaux % 4 == 0;
+  p.scale = scale; p.accumulate = accumulate;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_2d(&tmA, A, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 4, kKC, kBM,
+                        CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != TTAM_OK) return rc;
+  rc = make_tmap_2d(&tmB, B, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 4, kKC, (uint32_t)p.bn,
+                    CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != TTAM_OK) return rc;
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + (3 * kMaxStages + 6) * 8;
+  static bool attr_done = false;
+  if (!attr_done) {
+    TTAM_CUDA(cudaFuncSetAttribute(gemm_tf32_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_done = true;
+  }
+  const int grid = p.units < num_sms() ? p.units : num_sms();
+  gemm_tf32_tma_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
+  TTAM_LAUNCH_CHECK();
+  return TTAM_OK;
+}
+
+// ---- per-step weight preparation: TF32-rounded copy and TF32-rounded transposed copy of up to 4 small matrices ------------
+struct PrepItem {
+  const float* src;
+  float* dst;
+  float* dst_t;
+  int rows, cols;
+  int64_t ld;
+};
+struct PrepList {
+  PrepItem it[4];
+  int count;
+};
+__global__ void prepare_weights_kernel(PrepList L) {
+  __shared__ float tile[32][33];
+  const PrepItem w = L.it[blockIdx.z];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  if (r0 >= w.rows || c0 >= w.cols) return;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (r < w.rows && c < w.cols) {
+      v = tma::round_out_tf32(w.src[(int64_t)r * w.ld + c]);
+      if (w.dst) w.dst[(int64_t)r * w.cols + c] = v;
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (w.dst_t)
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int c = c0 + i, r = r0 + threadIdx.x;
+      if (c < w.cols && r < w.rows) w.dst_t[(int64_t)c * w.rows + r] = tile[threadIdx.x][i];
+    }
+}
+
+}  // namespace ttam
+
+using namespace ttam;
+
+extern "C" int ttam_prepare_weights(const float* const* src, const int64_t* ld, const int64_t* rows, const int64_t* cols,
+                                    float* const* dst, float* const* dst_t, int64_t count, void* stream) {
+  TTAM_CHECK_ARG(src && ld && rows && cols && dst && dst_t && count >= 1 && count <= 4, "prepare_weights: 1..4 matrices");
+  PrepList L{};
+  L.count = (int)count;
+  int64_t mr = 0, mc = 0;
+  for (int i = 0; i < count; ++i) {
+    TTAM_CHECK_ARG(src[i] && rows[i] > 0 && cols[i] > 0 && ld[i] >= cols[i], "prepare_weights: bad matrix %d", i);
+    L.it[i] = PrepItem{src[i], dst[i], dst_t[i], (int)rows[i], (int)cols[i], ld[i]};
+    mr = rows[i] > mr ? rows[i] : mr;
+    mc = cols[i] > mc ? cols[i] : mc;
+  }
+  prepare_weights_kernel<<<dim3((unsigned)ceil_div(mc, 32), (unsigned)ceil_div(mr, 32), (unsigned)count), dim3(32, 8), 0, (cudaStream_t)stream>>>(L);
+  TTAM_LAUNCH_CHECK();
+  return TTAM_OK;
+}

@@ -23,6 +23,15 @@ extern "C" int ttam_tower_fwd(const ttam_tower_desc* d, const int64_t* idx, int6
   // hd = dropout(relu(X[idx] W1^T + b1))
   const bool bag = d->bag_rowptr != nullptr;
   const bool tc = (d->precision & 0xFF) != TTAM_PREC_FP32;
+  const bool prep = tc && d->W2r && d->W2rT && d->G1r && d->G1rT && d->G2r && d->G2rT;
+  if (prep) {   // rounded + rounded-transposed copies of the three small weights, one launch; the backward reuses them
+    const float* src[3] = {d->W2, d->G1, d->G2};
+    const int64_t ld[3] = {H, 2 * D, Hg}, rows[3] = {D, Hg, D}, cols[3] = {H, 2 * D, Hg};
+    float* dst[3] = {d->W2r, d->G1r, d->G2r};
+    float* dst_t[3] = {d->W2rT, d->G1rT, d->G2rT};
+    TTAM_TRY(ttam_prepare_weights(src, ld, rows, cols, dst, dst_t, 3, stream));
+  }
+  const int wr = prep ? TTAM_PREC_W_ROUNDED : 0;
   if (bag) {
     // bag form: b1 + sum_j x_j W1[:, j] in fp32, written TF32-rounded when the next GEMM runs on the tensor cores
     TTAM_CHECK_ARG(d->bag_scratch, "tower_fwd: the bag form needs bag_scratch (room for W1^T)");
@@ -35,13 +44,14 @@ extern "C" int ttam_tower_fwd(const ttam_tower_desc* d, const int64_t* idx, int6
                              d->rng_base, d->state, prec1, stream));
   }
   // f = hd W2^T + b2 -> z[:, D:]
-  TTAM_TRY(ttam_linear_fwd(b->hd, H, nullptr, d->W2, H, d->b2, b->z + D, 2 * D, R, D, H, TTAM_ACT_NONE, 0.f, 0, 0, nullptr,
-                           d->precision | ((bag && tc) ? TTAM_PREC_X_ROUNDED : 0), stream));
-  // a = relu(z G1^T + c1);  pre2 = a G2^T + c2
-  TTAM_TRY(ttam_linear_fwd(b->z, 2 * D, nullptr, d->G1, 2 * D, d->c1, b->a, Hg, R, Hg, 2 * D, TTAM_ACT_RELU, 0.f, 0, 0, nullptr,
-                           d->precision, stream));
-  TTAM_TRY(ttam_linear_fwd(b->a, Hg, nullptr, d->G2, Hg, d->c2, b->pre2, D, R, D, Hg, TTAM_ACT_NONE, 0.f, 0, 0, nullptr,
-                           d->precision, stream));
+  TTAM_TRY(ttam_linear_fwd(b->hd, H, nullptr, prep ? d->W2r : d->W2, H, d->b2, b->z + D, 2 * D, R, D, H, TTAM_ACT_NONE, 0.f, 0, 0, nullptr,
+                           d->precision | wr | ((bag && tc) ? TTAM_PREC_X_ROUNDED : 0), stream));
+  // a = relu(z G1^T + c1);  pre2 = a G2^T + c2.  With prepared weights `a` is written TF32-rounded: its consumers are the
+  // next GEMM, the ReLU mask of the backward and the weight-gradient GEMM - the values they use are the same either way
+  TTAM_TRY(ttam_linear_fwd(b->z, 2 * D, nullptr, prep ? d->G1r : d->G1, 2 * D, d->c1, b->a, Hg, R, Hg, 2 * D, TTAM_ACT_RELU, 0.f, 0, 0,
+                           nullptr, d->precision | wr | (prep ? TTAM_PREC_OUT_ROUNDED : 0), stream));
+  TTAM_TRY(ttam_linear_fwd(b->a, Hg, nullptr, prep ? d->G2r : d->G2, Hg, d->c2, b->pre2, D, R, D, Hg, TTAM_ACT_NONE, 0.f, 0, 0, nullptr,
+                           d->precision | wr | (prep ? TTAM_PREC_X_ROUNDED : 0), stream));
   // g = sigmoid(pre2); t = g e + (1-g) f; o = t + A[idx]
   return ttam_gate_fwd(b->z, b->pre2, d->aug, d->aug ? d->table_rows : 0, idx, b->g, b->t, d->aug ? b->o : nullptr,
                        d->aug ? b->q : nullptr, R, D, stream);
@@ -69,15 +79,23 @@ extern "C" int ttam_tower_bwd(const ttam_tower_desc* d, const int64_t* idx, int6
   const bool chain = g->phase != 2, weights = g->phase != 1;
   const float* df = g->dz + D;   // feature MLP: df = dz[:, D:]
   const float scale = d->dropout_p > 0.f ? 1.f / (1.f - d->dropout_p) : 1.f;
+  const bool prep = (prec & 0xFF) != TTAM_PREC_FP32 && d->W2r && d->W2rT && d->G1r && d->G1rT && d->G2r && d->G2rT;
   if (chain) {
     // dpre2 = dt (e-f) g (1-g);  dz = [dt g ; dt (1-g)]
     TTAM_TRY(ttam_gate_bwd(dt, b->z, b->g, g->dpre2, g->dz, R, D, stream));
-    TTAM_TRY(ttam_linear_dgrad(g->dpre2, D, d->G2, g->dpre1, Hg, b->a, Hg, 1, 1.f, 0, R, D, Hg, prec, stream));
-    TTAM_TRY(ttam_linear_dgrad(g->dpre1, Hg, d->G1, g->dz, 2 * D, nullptr, 0, 0, 1.f, 1, R, Hg, 2 * D, prec, stream));
-    TTAM_TRY(ttam_linear_dgrad(df, 2 * D, d->W2, g->dhd, H, b->hd, H, 1, scale, 0, R, D, H, prec, stream));
+    if (prep) {   // data gradients against the transposed weight copies the forward prepared: TMA-fed kernel
+      TTAM_TRY(ttam_linear_dgrad(g->dpre2, D, d->G2rT, g->dpre1, Hg, b->a, Hg, 1, 1.f, 0, R, D, Hg, prec | TTAM_PREC_WT | TTAM_PREC_OUT_ROUNDED, stream));
+      TTAM_TRY(ttam_linear_dgrad(g->dpre1, Hg, d->G1rT, g->dz, 2 * D, nullptr, 0, 0, 1.f, 1, R, Hg, 2 * D, prec | TTAM_PREC_WT | TTAM_PREC_X_ROUNDED, stream));
+      TTAM_TRY(ttam_linear_dgrad(df, 2 * D, d->W2rT, g->dhd, H, b->hd, H, 1, scale, 0, R, D, H, prec | TTAM_PREC_WT, stream));
+    } else {
+      TTAM_TRY(ttam_linear_dgrad(g->dpre2, D, d->G2, g->dpre1, Hg, b->a, Hg, 1, 1.f, 0, R, D, Hg, prec, stream));
+      TTAM_TRY(ttam_linear_dgrad(g->dpre1, Hg, d->G1, g->dz, 2 * D, nullptr, 0, 0, 1.f, 1, R, Hg, 2 * D, prec, stream));
+      TTAM_TRY(ttam_linear_dgrad(df, 2 * D, d->W2, g->dhd, H, b->hd, H, 1, scale, 0, R, D, H, prec, stream));
+    }
   }
   if (weights) {
-    TTAM_TRY(ttam_linear_wgrad(g->dpre2, D, b->a, Hg, nullptr, g->dG2, g->dc2, R, D, Hg, acc, workspace, workspace_bytes, prec, stream));
+    TTAM_TRY(ttam_linear_wgrad(g->dpre2, D, b->a, Hg, nullptr, g->dG2, g->dc2, R, D, Hg, acc, workspace, workspace_bytes,
+                               prec | (prep ? TTAM_PREC_X_ROUNDED : 0), stream));
     TTAM_TRY(ttam_linear_wgrad(g->dpre1, Hg, b->z, 2 * D, nullptr, g->dG1, g->dc1, R, Hg, 2 * D, acc, workspace, workspace_bytes, prec, stream));
     const bool bag = d->bag_rowptr != nullptr;
     const bool tc = (prec & 0xFF) != TTAM_PREC_FP32;

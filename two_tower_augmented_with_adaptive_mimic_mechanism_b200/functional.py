@@ -124,12 +124,28 @@ def pad_cols(t: torch.Tensor, mult: int = 4, *, out=None, always_copy: bool = Fa
     return out[:, :Ccols]
 
 
-def _prec(precision: str, x_rounded: bool = False, w_rounded: bool = False) -> int:
-    return PREC[precision] | (_lib.PREC_X_ROUNDED if x_rounded else 0) | (_lib.PREC_W_ROUNDED if w_rounded else 0)
+def _prec(precision: str, x_rounded: bool = False, w_rounded: bool = False, out_rounded: bool = False, wt: bool = False) -> int:
+    return (PREC[precision] | (_lib.PREC_X_ROUNDED if x_rounded else 0) | (_lib.PREC_W_ROUNDED if w_rounded else 0)
+            | (_lib.PREC_OUT_ROUNDED if out_rounded else 0) | (_lib.PREC_WT if wt else 0))
+
+
+def prepare_weights(weights, want_rounded=True, want_transposed=True):
+    """[(W [rows, cols])...] (at most 4) -> ([TF32-rounded copies], [TF32-rounded transposed copies]) in one launch."""
+    import ctypes as C
+    n = len(weights)
+    dst = [torch.empty_like(w) if want_rounded else None for w in weights]
+    dst_t = [torch.empty((w.shape[1], w.shape[0]), dtype=torch.float32, device=w.device) if want_transposed else None for w in weights]
+    arr_p = lambda ts: (C.c_void_p * n)(*[None if t is None else t.data_ptr() for t in ts])
+    arr_i = lambda vs: (C.c_int64 * n)(*vs)
+    for w in weights:
+        _chk(w, torch.float32, "weight")
+    check(lib().ttam_prepare_weights(arr_p(weights), arr_i([w.stride(0) for w in weights]), arr_i([w.shape[0] for w in weights]),
+                                     arr_i([w.shape[1] for w in weights]), arr_p(dst), arr_p(dst_t), n, _stream()), "prepare_weights")
+    return dst, dst_t
 
 
 def linear_fwd(x, w, bias=None, *, gather=None, act="none", out=None, dropout_p=0.0, seed=0, offset=0,
-               state=None, precision="fp32", x_rounded=False, w_rounded=False):
+               state=None, precision="fp32", x_rounded=False, w_rounded=False, out_rounded=False):
     """x_rounded / w_rounded (tensor-core path): the operand was passed through round_tf32_ when it was laid out, the
     GEMM skips its rounding pass for it."""
     _chk(x, torch.float32, "x"); _chk(w, torch.float32, "w")
@@ -147,15 +163,19 @@ def linear_fwd(x, w, bias=None, *, gather=None, act="none", out=None, dropout_p=
         out = torch.empty((M, N), dtype=torch.float32, device=x.device)
     yp, ldy = _rows2d(out, "out")
     check(lib().ttam_linear_fwd(xp, ldx, _ptr(gather), wp, ldw, _ptr(bias), yp, ldy, M, N, K, ACT[act],
-                                float(dropout_p), int(seed), int(offset), _ptr(state), _prec(precision, x_rounded, w_rounded),
+                                float(dropout_p), int(seed), int(offset), _ptr(state), _prec(precision, x_rounded, w_rounded, out_rounded),
                                 _stream()), "linear_fwd")
     return out
 
 
-def linear_dgrad(dy, w, *, out=None, aux=None, relu_mask=False, scale=1.0, accumulate=False, precision="fp32"):
+def linear_dgrad(dy, w, *, out=None, aux=None, relu_mask=False, scale=1.0, accumulate=False, precision="fp32",
+                 w_transposed=False, x_rounded=False, out_rounded=False):
+    """w_transposed: `w` is the TF32-rounded transposed weight [K, N] from prepare_weights (TMA-fed kernel)."""
     _chk(dy, torch.float32, "dy"); _chk(w, torch.float32, "w")
     dyp, lddy = _rows2d(dy, "dy")
-    N, K = w.shape
+    N, K = (w.shape[1], w.shape[0]) if w_transposed else w.shape
+    if w_transposed and not w.is_contiguous():
+        raise ValueError("the transposed weight must be contiguous")
     M = dy.shape[0]
     if out is None:
         if accumulate:
@@ -166,7 +186,8 @@ def linear_dgrad(dy, w, *, out=None, aux=None, relu_mask=False, scale=1.0, accum
     if relu_mask:
         auxp, ldaux = _rows2d(aux, "aux")
     check(lib().ttam_linear_dgrad(dyp, lddy, w.data_ptr(), dxp, lddx, auxp, ldaux, 1 if relu_mask else 0, float(scale),
-                                  1 if accumulate else 0, M, N, K, PREC[precision], _stream()), "linear_dgrad")
+                                  1 if accumulate else 0, M, N, K, _prec(precision, x_rounded, False, out_rounded, w_transposed),
+                                  _stream()), "linear_dgrad")
     return out
 
 

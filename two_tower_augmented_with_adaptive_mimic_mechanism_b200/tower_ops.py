@@ -195,6 +195,13 @@ def _tower_forward_composite(plan, idx, X, *, train, bufs, seed, rng_base, state
     c.desc = _tower_desc(plan, X, W1, p_drop, seed, rng_base, state, precision, augment, bag)
     c.desc.x_rounded, c.desc.w1_rounded = int(pre), int(precision != "fp32" and bag is None)
     c.bag = bag            # keeps the CSR tensors alive as long as the cache
+    if precision != "fp32":
+        # TF32-rounded and rounded-transposed copies of the three small weights (ttam_prepare_weights inside the forward call)
+        (_, _), (W2, _) = plan.fe_layers
+        G1, _, G2, _ = plan.gate
+        for name, W in (("W2r", W2), ("G1r", G1), ("G2r", G2)):
+            setattr(c.desc, name, _buf(bufs, f"prep_{name}", (W.shape[0], W.shape[1]), dev).data_ptr())
+            setattr(c.desc, name + "T", _buf(bufs, f"prep_{name}T", (W.shape[1], W.shape[0]), dev).data_ptr())
     b = F._lib.TowerBufs()
     b.z, b.hd, b.a, b.pre2, b.g, b.t = (t.data_ptr() for t in (c.z, c.hd[0], c.a, pre2, c.g, c.t))
     b.o, b.q = (None if o is None else o.data_ptr()), (None if q is None else q.data_ptr())
