@@ -137,93 +137,104 @@ gemm_tf32_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
     }
   } else if (warp < 2 + kEpiWarps) {
-    // ===================== epilogue: thread = output row =====================
+    // ===================== epilogue =====================
+    // tcgen05.ld hands every thread one accumulator ROW (32 columns of it per load).  Stored like that, a warp's store would
+    // touch 32 rows x 16 bytes - half-used sectors on 32 different lines - and the mask / accumulate operands would be read
+    // the same way (measured: the kernel ran at the speed of this epilogue, 2x slower for 2x the columns).  So each warp
+    // transposes its 32 x 32 block through a private shared-memory tile (row pitch 36 floats: conflict-free both ways) and
+    // does all global traffic with 8 lanes per row: 128 contiguous bytes per row, 4 rows per instruction.
     const int quad = warp & 3;   // the TMEM lanes this warp may read: 32*quad .. +31
+    float* stg = reinterpret_cast<float*>(smem + (uint32_t)p.stages * stage_bytes + 512) + (warp - 2) * (32 * 36);
     const bool drop = p.dropout_p > 0.f;
     const float keep_scale = drop ? 1.f / (1.f - p.dropout_p) : 1.f;
     const uint64_t rng_base = p.offset + ((drop && p.st) ? p.st->rng_offset : 0ull);
+    const int sub_row = lane >> 3, c4 = (lane & 7) * 4;
     uint32_t un = 0;
     for (int u = blockIdx.x; u < p.units; u += gridDim.x, ++un) {
       const int mt = u / p.n_tiles_n, nt = u - mt * p.n_tiles_n;
       const int buf = un & 1;
-      const int m = mt * kBM + quad * 32 + lane, n0 = nt * p.bn;
+      const int m_base = mt * kBM + quad * 32, n0 = nt * p.bn;
       mbar_wait(acc_full + buf, (un >> 1) & 1);
       tc_fence_after();
-      for (int col = 0; col < p.bn; col += 16) {
-        uint32_t r[16];
-        tmem_ld_32x16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.acc_stride + col), r);
-        if (m < p.M && n0 + col < p.N) {
-          float v[16];
+      for (int col = 0; col < p.bn; col += 32) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * p.acc_stride + col);
+        uint32_t r[32];
+        if (col + 32 <= p.bn) {
+          tmem_ld_32x32(taddr, r);
+        } else {   // bn is a multiple of 16: a last half chunk
+          uint32_t h[16];
+          tmem_ld_32x16(taddr, h);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-          const bool full16 = n0 + col + 15 < p.N;
-          if (p.bias) {
-            if (p.vecBias && full16) {
+          for (int i = 0; i < 16; ++i) { r[i] = h[i]; r[16 + i] = 0u; }
+        }
 #pragma unroll
-              for (int i = 0; i < 16; i += 4) {
-                const float4 b4 = ld_f4(p.bias + n0 + col + i);
-                v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+        for (int i = 0; i < 32; i += 4) *reinterpret_cast<uint4*>(stg + lane * 36 + i) = make_uint4(r[i], r[i + 1], r[i + 2], r[i + 3]);
+        __syncwarp();
+        const int n = n0 + col + c4;            // this lane's 4 columns in every row of the chunk
+        const bool in4 = n + 3 < p.N;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias && n < p.N) {
+          if (p.vecBias && in4) b4 = ld_f4(p.bias + n);
+          else {
+            b4.x = p.bias[n];
+            if (n + 1 < p.N) b4.y = p.bias[n + 1];
+            if (n + 2 < p.N) b4.z = p.bias[n + 2];
+            if (n + 3 < p.N) b4.w = p.bias[n + 3];
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = i * 4 + sub_row;
+          const int m = m_base + row;
+          if (m < p.M && n < p.N && col + c4 < p.bn) {
+            const float4 a = *reinterpret_cast<const float4*>(stg + row * 36 + c4);
+            float v[4] = {a.x + b4.x, a.y + b4.y, a.z + b4.z, a.w + b4.w};
+            if (p.relu) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+            }
+            if (drop) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (n + e < p.N) v[e] = dropout_keep(p.seed, rng_base + (uint64_t)m * (uint64_t)p.N + (uint64_t)(n + e), p.dropout_p) ? v[e] * keep_scale : 0.f;
+            }
+            if (p.mask_mode == 1) {
+              const float* ax = p.aux + (int64_t)m * p.ldaux + n;
+              if (p.vecAux && in4) {
+                const float4 q = ld_f4(ax);
+                v[0] = q.x > 0.f ? v[0] : 0.f; v[1] = q.y > 0.f ? v[1] : 0.f; v[2] = q.z > 0.f ? v[2] : 0.f; v[3] = q.w > 0.f ? v[3] : 0.f;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (n + e < p.N) v[e] = ax[e] > 0.f ? v[e] : 0.f;
               }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (n0 + col + i < p.N) v[i] += p.bias[n0 + col + i];
             }
-          }
-          if (p.relu) {
+            if (p.scale != 1.f) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
-          if (drop) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int n = n0 + col + i;
-              if (n < p.N) v[i] = dropout_keep(p.seed, rng_base + (uint64_t)m * (uint64_t)p.N + (uint64_t)n, p.dropout_p) ? v[i] * keep_scale : 0.f;
+              for (int e = 0; e < 4; ++e) v[e] *= p.scale;
             }
-          }
-          if (p.mask_mode == 1) {
-            const float* ax = p.aux + (int64_t)m * p.ldaux + n0 + col;
-            if (p.vecAux && full16) {
-#pragma unroll
-              for (int i = 0; i < 16; i += 4) {
-                const float4 a4 = ld_f4(ax + i);
-                v[i] = a4.x > 0.f ? v[i] : 0.f; v[i + 1] = a4.y > 0.f ? v[i + 1] : 0.f;
-                v[i + 2] = a4.z > 0.f ? v[i + 2] : 0.f; v[i + 3] = a4.w > 0.f ? v[i + 3] : 0.f;
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (n0 + col + i < p.N) v[i] = (ax[i] > 0.f) ? v[i] : 0.f;
-            }
-          }
-          if (p.scale != 1.f) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] *= p.scale;
-          }
-          float* dst = p.C + (int64_t)m * p.ldc + n0 + col;
-          if (p.vecC && full16) {
-#pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            float* dst = p.C + (int64_t)m * p.ldc + n;
+            if (p.vecC && in4) {
+              float4 o = make_float4(v[0], v[1], v[2], v[3]);
               if (p.accumulate) {
-                const float4 old = ld_f4(dst + i);
+                const float4 old = ld_f4(dst);
                 o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
               }
               if (p.round_out) {
                 o.x = round_out_tf32(o.x); o.y = round_out_tf32(o.y); o.z = round_out_tf32(o.z); o.w = round_out_tf32(o.w);
               }
-              st_f4(dst + i, o);
-            }
-          } else {
+              st_f4(dst, o);
+            } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (n0 + col + i < p.N) {
-                float o = p.accumulate ? dst[i] + v[i] : v[i];
-                dst[i] = p.round_out ? round_out_tf32(o) : o;
-              }
+              for (int e = 0; e < 4; ++e)
+                if (n + e < p.N) {
+                  const float o = p.accumulate ? dst[e] + v[e] : v[e];
+                  dst[e] = p.round_out ? round_out_tf32(o) : o;
+                }
+            }
           }
         }
-        __syncwarp();  // tcgen05.ld is warp-collective: reconverge before the next one
+        __syncwarp();  // the tile is rewritten by the next chunk
       }
       tc_fence_before();
       __syncwarp();
@@ -279,7 +290,7 @@ int tma_gemm(const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
   p.units = (int)ceil_div(M, kBM) * p.n_tiles_n;
   p.nchunks = (int)ceil_div(K, kKC);
   const size_t stage_bytes = kABytes + (size_t)p.bn * 128;
-  p.stages = (int)((200 * 1024) / stage_bytes);
+  p.stages = (int)((196 * 1024) / stage_bytes);
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   if (p.stages < 2) return 1;
   p.roundA = roundA; p.round_out = round_out;
@@ -295,7 +306,7 @@ int tma_gemm(const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
   rc = make_tmap_2d(&tmB, B, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 4, kKC, (uint32_t)p.bn,
                     CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != TTAM_OK) return rc;
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + (3 * kMaxStages + 6) * 8;
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*alignment*/ + 512 /*barriers*/ + (size_t)kEpiWarps * 32 * 36 * 4 /*epilogue tiles*/;
   static bool attr_done = false;
   if (!attr_done) {
     TTAM_CUDA(cudaFuncSetAttribute(gemm_tf32_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
