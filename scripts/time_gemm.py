@@ -30,6 +30,7 @@ def main():
         tot = 0.0
         for _ in range(a.reps):
             flush.zero_()
+            torch.cuda._sleep(400_000)      # the host enqueues fn() while the GPU spins: e0 -> e1 is device time only
             e0.record(); fn(); e1.record()
             torch.cuda.synchronize()
             tot += e0.elapsed_time(e1)

@@ -182,11 +182,42 @@ gemm_tf32_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             if (n + 3 < p.N) b4.w = p.bias[n + 3];
           }
         }
+        const bool lane_ok = n < p.N && col + c4 < p.bn;
+        const bool fast = in4 && p.vecC && (p.mask_mode != 1 || p.vecAux) && !drop;
+        if (fast) {
+          // all global operands of the 8 rows this lane touches are requested before the first one is used
+          float4 auxv[8], oldv[8];
 #pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int m = m_base + i * 4 + sub_row;
+            const bool ok = lane_ok && m < p.M;
+            auxv[i] = (ok && p.mask_mode == 1) ? ld_f4(p.aux + (int64_t)m * p.ldaux + n) : make_float4(1.f, 1.f, 1.f, 1.f);
+            oldv[i] = (ok && p.accumulate) ? ld_f4(p.C + (int64_t)m * p.ldc + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = i * 4 + sub_row;
+            const int m = m_base + row;
+            if (lane_ok && m < p.M) {
+              const float4 a = *reinterpret_cast<const float4*>(stg + row * 36 + c4);
+              float4 o = make_float4(a.x + b4.x, a.y + b4.y, a.z + b4.z, a.w + b4.w);
+              if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              o.x = auxv[i].x > 0.f ? o.x : 0.f; o.y = auxv[i].y > 0.f ? o.y : 0.f;
+              o.z = auxv[i].z > 0.f ? o.z : 0.f; o.w = auxv[i].w > 0.f ? o.w : 0.f;
+              if (p.scale != 1.f) { o.x *= p.scale; o.y *= p.scale; o.z *= p.scale; o.w *= p.scale; }
+              o.x += oldv[i].x; o.y += oldv[i].y; o.z += oldv[i].z; o.w += oldv[i].w;
+              if (p.round_out) {
+                o.x = round_out_tf32(o.x); o.y = round_out_tf32(o.y); o.z = round_out_tf32(o.z); o.w = round_out_tf32(o.w);
+              }
+              st_f4(p.C + (int64_t)m * p.ldc + n, o);
+            }
+          }
+        } else {
+#pragma unroll 1
         for (int i = 0; i < 8; ++i) {
           const int row = i * 4 + sub_row;
           const int m = m_base + row;
-          if (m < p.M && n < p.N && col + c4 < p.bn) {
+          if (m < p.M && lane_ok) {
             const float4 a = *reinterpret_cast<const float4*>(stg + row * 36 + c4);
             float v[4] = {a.x + b4.x, a.y + b4.y, a.z + b4.z, a.w + b4.w};
             if (p.relu) {
@@ -200,39 +231,23 @@ gemm_tf32_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             }
             if (p.mask_mode == 1) {
               const float* ax = p.aux + (int64_t)m * p.ldaux + n;
-              if (p.vecAux && in4) {
-                const float4 q = ld_f4(ax);
-                v[0] = q.x > 0.f ? v[0] : 0.f; v[1] = q.y > 0.f ? v[1] : 0.f; v[2] = q.z > 0.f ? v[2] : 0.f; v[3] = q.w > 0.f ? v[3] : 0.f;
-              } else {
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  if (n + e < p.N) v[e] = ax[e] > 0.f ? v[e] : 0.f;
-              }
+              for (int e = 0; e < 4; ++e)
+                if (n + e < p.N) v[e] = ax[e] > 0.f ? v[e] : 0.f;
             }
             if (p.scale != 1.f) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) v[e] *= p.scale;
             }
             float* dst = p.C + (int64_t)m * p.ldc + n;
-            if (p.vecC && in4) {
-              float4 o = make_float4(v[0], v[1], v[2], v[3]);
-              if (p.accumulate) {
-                const float4 old = ld_f4(dst);
-                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-              }
-              if (p.round_out) {
-                o.x = round_out_tf32(o.x); o.y = round_out_tf32(o.y); o.z = round_out_tf32(o.z); o.w = round_out_tf32(o.w);
-              }
-              st_f4(dst, o);
-            } else {
 #pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (n + e < p.N) {
-                  const float o = p.accumulate ? dst[e] + v[e] : v[e];
-                  dst[e] = p.round_out ? round_out_tf32(o) : o;
-                }
-            }
+            for (int e = 0; e < 4; ++e)
+              if (n + e < p.N) {
+                const float o = p.accumulate ? dst[e] + v[e] : v[e];
+                dst[e] = p.round_out ? round_out_tf32(o) : o;
+              }
           }
+        }
         }
         __syncwarp();  // the tile is rewritten by the next chunk
       }
