@@ -167,6 +167,8 @@ typedef struct {
   const void* bag_entries;
   const float* bag_tail;
   int64_t bag_T, bag_tail_start, bag_max_nnz;
+  int64_t bag_wgrad;          /* 0: the weight gradient of layer 1 stays the dense GEMM dh^T . X[idx] (rows with dozens of
+                                 non-zeros: the scatter costs more than the GEMM), the forward still uses the bag form */
   void* bag_scratch;          /* >= F*H*4 bytes, private to this tower (ttam_tower_fwd transposes W1 into it) */
   int64_t bag_scratch_bytes;
   /* TF32 path: room for the rounded / rounded-transposed copies of W2 [D,H], G1 [Hg,2D], G2 [D,Hg] (all six or none);

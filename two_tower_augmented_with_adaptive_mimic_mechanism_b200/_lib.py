@@ -47,7 +47,7 @@ class TowerDesc(C.Structure):
         ("seed", C.c_uint64), ("rng_base", C.c_uint64),
         ("state", C.c_void_p),
         ("bag_rowptr", C.c_void_p), ("bag_entries", C.c_void_p), ("bag_tail", C.c_void_p),
-        ("bag_T", C.c_int64), ("bag_tail_start", C.c_int64), ("bag_max_nnz", C.c_int64),
+        ("bag_T", C.c_int64), ("bag_tail_start", C.c_int64), ("bag_max_nnz", C.c_int64), ("bag_wgrad", C.c_int64),
         ("bag_scratch", C.c_void_p), ("bag_scratch_bytes", C.c_int64),
         ("W2r", C.c_void_p), ("W2rT", C.c_void_p), ("G1r", C.c_void_p), ("G1rT", C.c_void_p), ("G2r", C.c_void_p), ("G2rT", C.c_void_p),
     ]

@@ -61,7 +61,7 @@ extern "C" int64_t ttam_tower_bwd_workspace_bytes(const ttam_tower_desc* d, int6
   if (!d || R <= 0) return 256;
   int64_t m = ttam_linear_wgrad_workspace_bytes(R, d->D, d->Hg);
   const int64_t c[3] = {ttam_linear_wgrad_workspace_bytes(R, d->Hg, 2 * d->D), ttam_linear_wgrad_workspace_bytes(R, d->D, d->H),
-                        d->bag_rowptr ? ttam_bag_linear_workspace_bytes(R, d->H, d->F) : ttam_linear_wgrad_workspace_bytes(R, d->H, d->F)};
+                        (d->bag_rowptr && d->bag_wgrad) ? ttam_bag_linear_workspace_bytes(R, d->H, d->F) : ttam_linear_wgrad_workspace_bytes(R, d->H, d->F)};
   for (int i = 0; i < 3; ++i) m = c[i] > m ? c[i] : m;
   return m;
 }
@@ -101,7 +101,7 @@ extern "C" int ttam_tower_bwd(const ttam_tower_desc* d, const int64_t* idx, int6
     const bool tc = (prec & 0xFF) != TTAM_PREC_FP32;
     TTAM_TRY(ttam_linear_wgrad(df, 2 * D, b->hd, H, nullptr, g->dW2, g->db2, R, D, H, acc, workspace, workspace_bytes,
                                prec | ((bag && tc) ? TTAM_PREC_X_ROUNDED : 0), stream));
-    if (bag) {
+    if (bag && d->bag_wgrad) {
       TTAM_TRY(ttam_bag_linear_wgrad(d->bag_rowptr, d->bag_entries, d->bag_tail, d->bag_T, d->bag_tail_start, d->bag_max_nnz, idx, R, g->dhd, H,
                                      g->dW1, F, g->db1, H, F, acc, workspace, workspace_bytes, stream));
     } else {

@@ -190,17 +190,14 @@ class FusedEngine:
         reused for as long as the caller keeps passing the same tensor."""
         if X is None:
             return X
+        bag = None
         if self.bag:
             bag = self._bag_for(X)
-            if bag is not None:
-                try:
-                    X._ttam_bag = bag
-                except Exception:  # noqa: BLE001
-                    bag = None
-            if bag is not None:
-                return X
-            if self.bag is True:
+            if bag is None and self.bag is True:
                 raise ValueError("bag=True: the feature matrix has rows with more than 64 non-zeros outside its dense tail")
+            if bag is not None and (bag.wgrad or self.precision == "fp32"):
+                X._ttam_bag = bag          # the bag form serves both directions (or the dense wgrad reads X as it is)
+                return X
         if self.precision == "fp32":
             return X
         # keyed by the tensor OBJECT (weak reference) and its version counter: a new tensor that lands on a freed
@@ -216,6 +213,8 @@ class FusedEngine:
             hit = (weakref.ref(X), X._version, cp)
             self._xpad[key] = hit
             F.note_realloc()       # graphs captured on the old copy are stale
+        if bag is not None:
+            hit[2]._ttam_bag = bag     # forward from the bag form, weight gradient from the padded TF32 copy
         return hit[2]
 
     def _bag_for(self, X):

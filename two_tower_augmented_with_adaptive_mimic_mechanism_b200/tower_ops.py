@@ -167,6 +167,7 @@ def _tower_desc(plan: TowerPlan, X, W1, p_drop, seed, rng_base, state, precision
         d.bag_rowptr, d.bag_entries = bag.rowptr.data_ptr(), bag.entries.data_ptr()
         d.bag_tail = None if bag.tail is None else bag.tail.data_ptr()
         d.bag_T, d.bag_tail_start, d.bag_max_nnz = bag.T, bag.tail_start, bag.max_nnz
+        d.bag_wgrad = 1 if bag.wgrad else 0
         ws = F.workspace(F.lib().ttam_bag_linear_workspace_bytes(0, W1.shape[0], X.shape[1]), X.device, "bag_fwd")
         d.bag_scratch, d.bag_scratch_bytes = ws.data_ptr(), ws.numel()
     d.W1, d.ldw1, d.b1, d.H = W1.data_ptr(), W1.stride(0), b1.data_ptr(), W1.shape[0]
@@ -182,7 +183,7 @@ def _tower_forward_composite(plan, idx, X, *, train, bufs, seed, rng_base, state
     H, Hg = plan.fe_layers[0][0].shape[0], plan.gate[0].shape[0]
     p_drop = plan.dropout if train else 0.0
     bag = _bag_of(X, H)
-    pre = bag is None and precision != "fp32" and bool(getattr(X, "_ttam_tf32", False))   # the engine's private rounded copy of X
+    pre = precision != "fp32" and bool(getattr(X, "_ttam_tf32", False))   # the engine's private rounded copy of X (dense layer 1 / wgrad)
     W1 = _w1_rounded(plan.fe_layers[0][0], bufs) if (precision != "fp32" and bag is None) else plan.fe_layers[0][0]
     c = Cache(idx=idx, X=X, gather=True, train=train, R=R, seed=seed, rng_base=rng_base, mode="gated", composite=True)
     c.z = _buf(bufs, "z", (R, 2 * D), dev)
@@ -395,7 +396,7 @@ def tower_backward(plan: TowerPlan, c: Cache, dt: torch.Tensor, grads: dict, *, 
             grads[id(W)], grads[id(b)] = dw, db
         else:
             db = grads[id(b)]
-        if gather is not None and c.bag is not None and x is X:
+        if gather is not None and c.bag is not None and c.bag.wgrad and x is X:
             dyc = dy
             if dy.stride(0) % 4 != 0 or dy.data_ptr() % 16 != 0 or (dy.shape[1] > 1 and dy.stride(1) != 1):
                 dyc = dy.contiguous()
