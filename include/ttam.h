@@ -181,7 +181,9 @@ typedef struct {
   float *dW1, *db1, *dW2, *db2, *dG1, *dc1, *dG2, *dc2;
   int32_t accumulate;
   int32_t phase; /* 0: whole backward; 1: data-gradient chain only (gate_bwd + the three dgrads: what the table updates
-                    wait for); 2: the four weight/bias gradients only (may run on another stream once phase 1 is done) */
+                    wait for); 2: the four weight/bias gradients only (may run on another stream once phase 1 is done);
+                    10..13: ONE link of the chain (gate_bwd, dgrad through G2, G1, W2); 20..23: ONE weight gradient (G2, G1,
+                    W2, W1) - weight gradient 2x needs link 1x only, so the caller can overlap them on two streams */
 } ttam_tower_grads;
 int ttam_tower_fwd(const ttam_tower_desc* d, const int64_t* idx, int64_t R, const ttam_tower_bufs* bufs, void* stream);
 int64_t ttam_tower_bwd_workspace_bytes(const ttam_tower_desc* d, int64_t R);

@@ -305,9 +305,13 @@ int tma_gemm(const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
   p.units = (int)ceil_div(M, kBM) * p.n_tiles_n;
   p.nchunks = (int)ceil_div(K, kKC);
   const size_t stage_bytes = kABytes + (size_t)p.bn * 128;
-  p.stages = (int)((196 * 1024) / stage_bytes);
+  // ring depth: ~128 kB of operands in flight per SM is several times what the HBM latency needs at this CTA's share of the
+  // bandwidth, and it leaves room for a CTA of another kernel (the weight-gradient GEMMs run next to the data-gradient chain)
+  p.stages = (int)((128 * 1024) / stage_bytes);
+  if (const char* e = getenv("TTAM_TMA_STAGES")) p.stages = atoi(e);
+  if (p.stages < 3) p.stages = 3;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
-  if (p.stages < 2) return 1;
+  if ((size_t)p.stages * stage_bytes > 196 * 1024) return 1;
   p.roundA = roundA; p.round_out = round_out;
   p.vecC = aligned16(C) && ldc % 4 == 0;
   p.bias = bias; p.vecBias = bias != nullptr && aligned16(bias);

@@ -75,33 +75,41 @@ extern "C" int ttam_tower_bwd(const ttam_tower_desc* d, const int64_t* idx, int6
   const int64_t D = d->D, H = d->H, Hg = d->Hg, F = d->F;
   const int acc = g->accumulate;
   const int prec = d->precision;
-  TTAM_CHECK_ARG(g->phase >= 0 && g->phase <= 2, "tower_bwd: phase must be 0, 1 or 2");
-  const bool chain = g->phase != 2, weights = g->phase != 1;
+  TTAM_CHECK_ARG((g->phase >= 0 && g->phase <= 2) || (g->phase >= 10 && g->phase <= 13) || (g->phase >= 20 && g->phase <= 23),
+                 "tower_bwd: phase must be 0, 1, 2, 10..13 or 20..23");
+  // 0: everything; 1: the data-gradient chain; 2: the four weight gradients; 10..13 / 20..23: ONE link of the chain / ONE
+  // weight gradient (gate, gate layer 2, gate layer 1, MLP layer 2 | G2, G1, W2, W1), so that the caller can start each
+  // weight gradient on a second stream as soon as the chain link that produces its input has run
+  const int ph = g->phase;
+  const bool chain = ph != 2 && ph < 20, weights = ph != 1 && (ph < 10 || ph >= 20);
+  const auto link = [&](int i) { return ph < 10 || ph == 10 + i; };
+  const auto wg = [&](int i) { return ph < 10 || ph == 20 + i; };
   const float* df = g->dz + D;   // feature MLP: df = dz[:, D:]
   const float scale = d->dropout_p > 0.f ? 1.f / (1.f - d->dropout_p) : 1.f;
   const bool prep = (prec & 0xFF) != TTAM_PREC_FP32 && d->W2r && d->W2rT && d->G1r && d->G1rT && d->G2r && d->G2rT;
   if (chain) {
     // dpre2 = dt (e-f) g (1-g);  dz = [dt g ; dt (1-g)]
-    TTAM_TRY(ttam_gate_bwd(dt, b->z, b->g, g->dpre2, g->dz, R, D, stream));
+    if (link(0)) TTAM_TRY(ttam_gate_bwd(dt, b->z, b->g, g->dpre2, g->dz, R, D, stream));
     if (prep) {   // data gradients against the transposed weight copies the forward prepared: TMA-fed kernel
-      TTAM_TRY(ttam_linear_dgrad(g->dpre2, D, d->G2rT, g->dpre1, Hg, b->a, Hg, 1, 1.f, 0, R, D, Hg, prec | TTAM_PREC_WT | TTAM_PREC_OUT_ROUNDED, stream));
-      TTAM_TRY(ttam_linear_dgrad(g->dpre1, Hg, d->G1rT, g->dz, 2 * D, nullptr, 0, 0, 1.f, 1, R, Hg, 2 * D, prec | TTAM_PREC_WT | TTAM_PREC_X_ROUNDED, stream));
-      TTAM_TRY(ttam_linear_dgrad(df, 2 * D, d->W2rT, g->dhd, H, b->hd, H, 1, scale, 0, R, D, H, prec | TTAM_PREC_WT, stream));
+      if (link(1)) TTAM_TRY(ttam_linear_dgrad(g->dpre2, D, d->G2rT, g->dpre1, Hg, b->a, Hg, 1, 1.f, 0, R, D, Hg, prec | TTAM_PREC_WT | TTAM_PREC_OUT_ROUNDED, stream));
+      if (link(2)) TTAM_TRY(ttam_linear_dgrad(g->dpre1, Hg, d->G1rT, g->dz, 2 * D, nullptr, 0, 0, 1.f, 1, R, Hg, 2 * D, prec | TTAM_PREC_WT | TTAM_PREC_X_ROUNDED, stream));
+      if (link(3)) TTAM_TRY(ttam_linear_dgrad(df, 2 * D, d->W2rT, g->dhd, H, b->hd, H, 1, scale, 0, R, D, H, prec | TTAM_PREC_WT, stream));
     } else {
-      TTAM_TRY(ttam_linear_dgrad(g->dpre2, D, d->G2, g->dpre1, Hg, b->a, Hg, 1, 1.f, 0, R, D, Hg, prec, stream));
-      TTAM_TRY(ttam_linear_dgrad(g->dpre1, Hg, d->G1, g->dz, 2 * D, nullptr, 0, 0, 1.f, 1, R, Hg, 2 * D, prec, stream));
-      TTAM_TRY(ttam_linear_dgrad(df, 2 * D, d->W2, g->dhd, H, b->hd, H, 1, scale, 0, R, D, H, prec, stream));
+      if (link(1)) TTAM_TRY(ttam_linear_dgrad(g->dpre2, D, d->G2, g->dpre1, Hg, b->a, Hg, 1, 1.f, 0, R, D, Hg, prec, stream));
+      if (link(2)) TTAM_TRY(ttam_linear_dgrad(g->dpre1, Hg, d->G1, g->dz, 2 * D, nullptr, 0, 0, 1.f, 1, R, Hg, 2 * D, prec, stream));
+      if (link(3)) TTAM_TRY(ttam_linear_dgrad(df, 2 * D, d->W2, g->dhd, H, b->hd, H, 1, scale, 0, R, D, H, prec, stream));
     }
   }
   if (weights) {
-    TTAM_TRY(ttam_linear_wgrad(g->dpre2, D, b->a, Hg, nullptr, g->dG2, g->dc2, R, D, Hg, acc, workspace, workspace_bytes,
-                               prec | (prep ? TTAM_PREC_X_ROUNDED : 0), stream));
-    TTAM_TRY(ttam_linear_wgrad(g->dpre1, Hg, b->z, 2 * D, nullptr, g->dG1, g->dc1, R, Hg, 2 * D, acc, workspace, workspace_bytes, prec, stream));
+    if (wg(0)) TTAM_TRY(ttam_linear_wgrad(g->dpre2, D, b->a, Hg, nullptr, g->dG2, g->dc2, R, D, Hg, acc, workspace, workspace_bytes,
+                                          prec | (prep ? TTAM_PREC_X_ROUNDED : 0), stream));
+    if (wg(1)) TTAM_TRY(ttam_linear_wgrad(g->dpre1, Hg, b->z, 2 * D, nullptr, g->dG1, g->dc1, R, Hg, 2 * D, acc, workspace, workspace_bytes, prec, stream));
     const bool bag = d->bag_rowptr != nullptr;
     const bool tc = (prec & 0xFF) != TTAM_PREC_FP32;
-    TTAM_TRY(ttam_linear_wgrad(df, 2 * D, b->hd, H, nullptr, g->dW2, g->db2, R, D, H, acc, workspace, workspace_bytes,
-                               prec | ((bag && tc) ? TTAM_PREC_X_ROUNDED : 0), stream));
-    if (bag && d->bag_wgrad) {
+    if (wg(2)) TTAM_TRY(ttam_linear_wgrad(df, 2 * D, b->hd, H, nullptr, g->dW2, g->db2, R, D, H, acc, workspace, workspace_bytes,
+                                          prec | ((bag && tc) ? TTAM_PREC_X_ROUNDED : 0), stream));
+    if (!wg(3)) {
+    } else if (bag && d->bag_wgrad) {
       TTAM_TRY(ttam_bag_linear_wgrad(d->bag_rowptr, d->bag_entries, d->bag_tail, d->bag_T, d->bag_tail_start, d->bag_max_nnz, idx, R, g->dhd, H,
                                      g->dW1, F, g->db1, H, F, acc, workspace, workspace_bytes, stream));
     } else {

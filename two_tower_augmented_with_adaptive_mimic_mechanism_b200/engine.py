@@ -119,6 +119,7 @@ class FusedEngine:
         self._wgrad_streams = {"u": torch.cuda.Stream(device=dev), "i": torch.cuda.Stream(device=dev)}
         self._split_wgrad = os.environ.get("TTAM_WGRAD_STREAM", "1") != "0"
         self._use_aug_stream = os.environ.get("TTAM_AUG_STREAM", "1") != "0"
+        self._interleave = os.environ.get("TTAM_INTERLEAVE_WGRAD", "1") != "0"
 
     # --------------------------------------------------------------------------------------------
     def _build_scalar_tables(self) -> None:
@@ -391,7 +392,7 @@ class FusedEngine:
         wg_u, wg_i = self._wgrad_streams["u"], self._wgrad_streams["i"]
         with (torch.cuda.stream(side) if side is not None else _null()), F.ws_scope("user"):
             de_u = tower_backward(self.user, cu, do_u, grads_u if side is not None else grads, bufs=self.bufs_u, state=self.state,
-                                  precision=self.precision, phase=1 if split else 0)
+                                  precision=self.precision, phase=1 if split else 0, wgrad_stream=wg_u if (split and self._interleave) else None)
             if split:
                 wg_u.wait_stream(side)
                 with torch.cuda.stream(wg_u), F.ws_scope("user_wgrad"):
@@ -405,7 +406,7 @@ class FusedEngine:
                 side.wait_stream(wg_u)
         with F.ws_scope("item"):
             de_i = tower_backward(self.item, ci, do_i, grads, bufs=self.bufs_i, state=self.state, precision=self.precision,
-                                  phase=1 if split else 0)
+                                  phase=1 if split else 0, wgrad_stream=wg_i if (split and self._interleave) else None)
             if split:
                 wg_i.wait_stream(cur)
                 with torch.cuda.stream(wg_i), F.ws_scope("item_wgrad"):

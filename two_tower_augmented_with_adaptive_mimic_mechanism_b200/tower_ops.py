@@ -212,13 +212,15 @@ def _tower_forward_composite(plan, idx, X, *, train, bufs, seed, rng_base, state
     return c
 
 
-def _tower_backward_composite(plan, c: Cache, dt, grads: dict, bufs, phase: int = 0):
+def _tower_backward_composite(plan, c: Cache, dt, grads: dict, bufs, phase: int = 0, wgrad_stream=None):
     """phase 0: whole backward.  phase 1: data-gradient chain only (returns dL/de; the weight gradients are registered in
     `grads` but not yet computed).  phase 2: the weight / bias gradients of a cache whose phase 1 has run (any stream that
     is ordered after it)."""
     R, D, dev = c.R, plan.D, dt.device
     L = F.lib()
     if phase == 2:
+        if c.wgrads_issued:        # phase 1 already interleaved them on the weight-gradient stream
+            return None
         g = c.bwd_g
         g.phase = 2
         ws = F.workspace(L.ttam_tower_bwd_workspace_bytes(c.desc, R), dev, "wgrad")
@@ -239,9 +241,26 @@ def _tower_backward_composite(plan, c: Cache, dt, grads: dict, bufs, phase: int 
         setattr(g, fw, grads[id(W)].data_ptr()); setattr(g, fb, grads[id(b)].data_ptr())
     g.accumulate = 1 if acc else 0
     g.phase = phase
-    ws = F.workspace(L.ttam_tower_bwd_workspace_bytes(c.desc, R), dev, "wgrad")
     dt = dt if dt.is_contiguous() else dt.contiguous()
     c.bwd_g, c.bwd_dt = g, dt
+    if phase == 1 and wgrad_stream is not None:
+        # Interleaved: link i of the data-gradient chain on the current stream, weight gradient i on `wgrad_stream` as soon
+        # as that link has run (it needs nothing later), instead of all four weight gradients after the whole chain.
+        cur = torch.cuda.current_stream(dev)
+        with F.ws_scope(F._ws_scope[0] + "_wgrad"):
+            ws = F.workspace(L.ttam_tower_bwd_workspace_bytes(c.desc, R), dev, "wgrad")
+        for i in range(4):
+            g.phase = 10 + i
+            F.check(L.ttam_tower_bwd(c.desc, c.idx.data_ptr(), R, c.cbufs, dt.data_ptr(), g, ws.data_ptr(), ws.numel(), cur.cuda_stream),
+                    "tower_bwd")
+            wgrad_stream.wait_stream(cur)
+            g.phase = 20 + i
+            F.check(L.ttam_tower_bwd(c.desc, c.idx.data_ptr(), R, c.cbufs, dt.data_ptr(), g, ws.data_ptr(), ws.numel(),
+                                     wgrad_stream.cuda_stream), "tower_bwd")
+        g.phase = 1
+        c.wgrads_issued = True
+        return dz[:, :D]
+    ws = F.workspace(L.ttam_tower_bwd_workspace_bytes(c.desc, R), dev, "wgrad")
     F.check(L.ttam_tower_bwd(c.desc, c.idx.data_ptr(), R, c.cbufs, dt.data_ptr(), g, ws.data_ptr(), ws.numel(), F._stream()),
             "tower_bwd")
     return dz[:, :D]
@@ -374,13 +393,13 @@ def splits_backward(c: Cache) -> bool:
 
 
 def tower_backward(plan: TowerPlan, c: Cache, dt: torch.Tensor, grads: dict, *, bufs: Optional[dict] = None,
-                   state=None, precision="fp32", phase: int = 0):
+                   state=None, precision="fp32", phase: int = 0, wgrad_stream=None):
     """dt [R, out_dim] = dL/dt.  Dense weight gradients are written to grads[id(param)] (accumulated when the
     key exists).  Returns de [R, D] (a view; rows of dL/dE[idx], duplicates NOT yet summed).
     phase (composite towers only, see `splits_backward`): 1 = data-gradient chain now, weight gradients later by a
     phase-2 call on any stream ordered after this one."""
     if c.composite:
-        return _tower_backward_composite(plan, c, dt, grads, bufs, phase)
+        return _tower_backward_composite(plan, c, dt, grads, bufs, phase, wgrad_stream)
     if phase != 0:
         raise ValueError("only composite (gated MLP, tensor-core) towers split their backward")
     R, D = c.R, plan.D
