@@ -228,6 +228,17 @@ int ttam_loss_fwd_bwd(const float* o_u, const float* o_i, const float* t_u, cons
                       float* do_u, float* do_i, float* dq_u, float* dq_p, int64_t B, int64_t N, int64_t D,
                       float batch_fraction, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- in-batch softmax loss (EXTENSION: BASELINE.json configs[1] "in-batch negatives"; the reference has no such loss, its
+ * training loss is the sampled-negative BCE above - definition and parity: oracle/model.py inbatch_loss_forward_backward) ----
+ * S = o_u o_p^T [B,B]; L_ce = mean_b (logsumexp_j S[b,j] - S[b,b]); mimic terms as in ttam_loss_fwd_bwd.
+ * loss_out[4] = {total, ce, mimic_user, mimic_item}; do_u, do_p [B,D] = dL/do; dq_u, dq_p [B,D] = dL/dq (mimic only).
+ * do_u == NULL: forward only.  precision: TTAM_PREC_FP32 | TTAM_PREC_TF32 (the three B x B x D GEMMs).  The workspace holds S. */
+int64_t ttam_inbatch_loss_workspace_bytes(int64_t B, int64_t D);
+int ttam_inbatch_loss_fwd_bwd(const float* o_u, const float* o_p, const float* t_u, const float* t_p, const float* q_u,
+                              const float* q_p, float lambda_u, float lambda_i, float* loss_out, float* do_u, float* do_p,
+                              float* dq_u, float* dq_p, int64_t B, int64_t D, int precision, void* workspace,
+                              int64_t workspace_bytes, void* stream);
+
 /* ---- category-alignment loss (training.py:530-579, 805-820) ------------------------------------------------
  * L_cal = mean over the non-major categories c with >= 2 rows of || Cov(emb rows of c) - Cov(emb rows of major) ||_F^2,
  * categories = cat_tensor[item_idx] (primary category id of every item, values in [0, n_categories)).

@@ -386,10 +386,14 @@ def _dense_param_names(state, spec: ModelSpec):
 
 def train_step(state, opt: OptState, spec: ModelSpec, users, pos, neg, user_x, item_x, *,
                lr=1e-3, weight_decay=0.01, betas=(0.9, 0.999), optimizer="adamw", momentum=0.0,
-               lambdas=(0.0, 0.0, 0.0), cat_tensor=None, major=None, masks=None):
+               lambdas=(0.0, 0.0, 0.0), cat_tensor=None, major=None, masks=None, loss="sampled"):
     """One iteration of the `_train_one_epoch` loop body.  Mutates `state` and `opt` in place;
-    returns dict(loss, bce, mimic_user, mimic_item, cal, touched_user_rows, touched_item_rows)."""
+    returns dict(loss, bce, mimic_user, mimic_item, cal, touched_user_rows, touched_item_rows).
+    loss="inbatch" (EXTENSION, not in the reference): the in-batch softmax of inbatch_loss_forward_backward replaces the
+    sampled-negative BCE; `neg` is ignored."""
     lam_u, lam_i, lam_c = (float(v) for v in lambdas)
+    if loss == "inbatch":
+        neg = np.zeros((len(users), 0), dtype=np.int64)
     B, N = neg.shape
     neg_flat = neg.reshape(-1)
     train = True
@@ -403,11 +407,16 @@ def train_step(state, opt: OptState, spec: ModelSpec, users, pos, neg, user_x, i
         Au, Ai = state["adaptive_mimic.user_augmented.weight"], state["adaptive_mimic.item_augmented.weight"]
         q_u, q_p, q_n = Au[users], Ai[pos], Ai[neg_flat]        # adaptive_mimic.py:97-105
         o_u, o_p, o_n = (t_u + q_u).astype(F32), (t_p + q_p).astype(F32), (t_n + q_n).astype(F32)
-        L = loss_forward_backward(o_u, o_p, o_n.reshape(B, N, D), t_u=t_u, t_p=t_p, q_u=q_u, q_p=q_p,
-                                  lambda_u=lam_u, lambda_i=lam_i)
+        if loss == "inbatch":
+            L = inbatch_loss_forward_backward(o_u, o_p, t_u=t_u, t_p=t_p, q_u=q_u, q_p=q_p, lambda_u=lam_u, lambda_i=lam_i)
+        else:
+            L = loss_forward_backward(o_u, o_p, o_n.reshape(B, N, D), t_u=t_u, t_p=t_p, q_u=q_u, q_p=q_p,
+                                      lambda_u=lam_u, lambda_i=lam_i)
     else:
         o_u, o_p, o_n = t_u, t_p, t_n
-        L = loss_forward_backward(o_u, o_p, o_n.reshape(B, N, D))
+        L = inbatch_loss_forward_backward(o_u, o_p) if loss == "inbatch" else loss_forward_backward(o_u, o_p, o_n.reshape(B, N, D))
+    if loss == "inbatch":
+        L["do_n"], L["bce"] = np.zeros((0, D), dtype=F32), L["ce"]
     total = L["loss"]
     do_u, do_p, do_n = L["do_u"], L["do_p"], L["do_n"].reshape(B * N, D)
     cal = None

@@ -48,7 +48,8 @@ class FusedEngine:
     def __init__(self, model, *, optimizer: str = "adamw", lr: float = 1e-3, weight_decay: float = 0.0,
                  momentum: float = 0.0, dense_betas=(0.9, 0.999), sparse_betas=(0.9, 0.999), eps: float = 1e-8,
                  loss_weights: Optional[dict] = None, precision: str = "fp32", seed: int = 1234,
-                 max_steps: int = 1 << 16, item_category_tensor=None, major_category_id=None, bag="auto") -> None:
+                 max_steps: int = 1 << 16, item_category_tensor=None, major_category_id=None, bag="auto",
+                 loss: str = "sampled") -> None:
         self.model = model
         mimic = getattr(model, "adaptive_mimic", None)
         self.user: TowerPlan = plan_from_module(model.user_encoder, mimic.user_augmented if mimic is not None else None)
@@ -70,6 +71,11 @@ class FusedEngine:
         self.lambda_c = float(w.get("category_alignment", 0.0))
         self.cat_tensor, self.major = item_category_tensor, major_category_id
         self.precision = precision
+        # "sampled": the reference's loss, BCE over 1 positive + N sampled negatives per sample (training.py:770-803).
+        # "inbatch": softmax over the batch's own positives (BASELINE configs[1]; an extension, see ttam_inbatch_loss_fwd_bwd)
+        if loss not in ("sampled", "inbatch"):
+            raise ValueError("loss must be 'sampled' or 'inbatch'")
+        self.loss_kind = loss
         # layer 1 of the feature encoders from the bag (CSR + dense tail) form of the feature matrices: "auto" = whenever
         # a matrix is sparse enough for the bag kernels (<= 64 non-zeros per row outside the dense tail), False = always
         # the dense GEMM (X[idx] . W1^T), True = like "auto" but a matrix that cannot be converted raises
@@ -359,6 +365,17 @@ class FusedEngine:
                                  grad_a=do_i, grad_b=dq_p if self.mimic else None, B=B)
         return loss, do_u, do_i, dq_u, dq_p
 
+    def _inbatch_phase(self, o_u, o_p, t_u, t_p, q_u, q_p, B):
+        """In-batch softmax loss forward + backward on the B (user, positive) pairs of the step."""
+        D = o_u.shape[1]
+        loss = self._misc("loss", (4,), torch.float32)
+        do_u, do_i = self._misc("do_u", (B, D), torch.float32), self._misc("do_i", (B, D), torch.float32)
+        dq_u = self._misc("dq_u", (B, D), torch.float32) if self.mimic else None
+        dq_p = self._misc("dq_p", (B, D), torch.float32) if self.mimic else None
+        kw = dict(t_u=t_u, t_p=t_p, q_u=q_u, q_p=q_p, lambda_u=self.lambda_u, lambda_i=self.lambda_i) if self.mimic else {}
+        F.inbatch_loss_fwd_bwd(o_u, o_p, out=(loss, do_u, do_i, dq_u, dq_p), precision=self.precision, **kw)
+        return loss, do_u, do_i, dq_u, dq_p
+
     def _backward_phase(self, ctx, do_u, do_i, dq_user, dq_item, dense_grad_hook=None):
         """Tower backward for the rows of `ctx`, row-wise table updates, dense optimiser.
         dq_user / dq_item: gradient rows of the augmentation tables, each a tensor or a (first rows, other rows) pair.
@@ -458,11 +475,15 @@ class FusedEngine:
         launches0 = F.lib().ttam_launch_count()
         ctx = self._forward_phase(users, items, Xu, Xi)
         cu, ci = ctx["cu"], ctx["ci"]
-        if self.mimic:
-            loss, do_u, do_i, dq_u, dq_p = self._loss_phase(cu.o, ci.o, cu.t, ci.t[:B], cu.q, ci.q[:B], items, B, N)
+        if self.loss_kind == "inbatch":
+            loss, do_u, do_i, dq_u, dq_p = self._inbatch_phase(cu.o, ci.o, cu.t, ci.t, cu.q, ci.q, B)
+            self._backward_phase(ctx, do_u, do_i, dq_u, dq_p)
         else:
-            loss, do_u, do_i, dq_u, dq_p = self._loss_phase(cu.o, ci.o, None, None, None, None, items, B, N)
-        self._backward_phase(ctx, do_u, do_i, dq_u, (dq_p, do_i[B:]) if self.mimic else None)
+            if self.mimic:
+                loss, do_u, do_i, dq_u, dq_p = self._loss_phase(cu.o, ci.o, cu.t, ci.t[:B], cu.q, ci.q[:B], items, B, N)
+            else:
+                loss, do_u, do_i, dq_u, dq_p = self._loss_phase(cu.o, ci.o, None, None, None, None, items, B, N)
+            self._backward_phase(ctx, do_u, do_i, dq_u, (dq_p, do_i[B:]) if self.mimic else None)
         self.launches_per_step = F.lib().ttam_launch_count() - launches0
         return loss
 
@@ -481,21 +502,27 @@ class FusedEngine:
     def train_step(self, users: torch.Tensor, pos: torch.Tensor, neg: torch.Tensor, user_x, item_x, *,
                    graph: bool = False) -> torch.Tensor:
         """One optimisation step on a batch (users [B], pos [B], neg [B,N], all int64 on the device).
-        Returns a device tensor loss[4] = {total, bce, mimic_user, mimic_item} (valid until the next step)."""
-        B, N = neg.shape
+        Returns a device tensor loss[4] = {total, bce | ce, mimic_user, mimic_item} (valid until the next step).
+        loss="inbatch": `neg` is ignored (may be None) - the other positives of the batch are the negatives."""
+        if self.loss_kind == "inbatch":
+            neg = None
+        elif neg is None:
+            raise ValueError("the sampled-negative loss needs neg [B, N]")
+        B, N = (users.shape[0], 0) if neg is None else neg.shape
         self._ensure_steps(self.t + 1)
         if graph:
             return self._graph_step(users, pos, neg, user_x, item_x)
         items = self._misc("items", (B * (1 + N),), torch.int64)
         items[:B].copy_(pos)
-        items[B:].copy_(neg.reshape(-1))
+        if N:
+            items[B:].copy_(neg.reshape(-1))
         users = users.contiguous()
         self.t += 1
         self.dirty = True
         return self._step_body(users, items, B, N, user_x, item_x)
 
     def _graph_step(self, users, pos, neg, user_x, item_x):
-        B, N = neg.shape
+        B, N = (users.shape[0], 0) if neg is None else neg.shape
         key = (B, N, None if user_x is None else user_x.data_ptr(), None if item_x is None else item_x.data_ptr())
         entry = self._graphs.get(key)
         if entry is not None and entry[4] != F.alloc_generation():
@@ -506,7 +533,9 @@ class FusedEngine:
         if entry is None:
             su = torch.empty(B, dtype=torch.int64, device=self.device)
             si = torch.empty(B * (1 + N), dtype=torch.int64, device=self.device)
-            su.copy_(users); si[:B].copy_(pos); si[B:].copy_(neg.reshape(-1))
+            su.copy_(users); si[:B].copy_(pos)
+            if N:
+                si[B:].copy_(neg.reshape(-1))
             # warm-up outside capture sizes every buffer; run it on copies of nothing: it IS a real step
             self.t += 1
             loss = self._step_body(su, si, B, N, user_x, item_x)
@@ -520,7 +549,9 @@ class FusedEngine:
             self.dirty = True
             return loss
         g, su, si, loss, _ = entry
-        su.copy_(users); si[:B].copy_(pos); si[B:].copy_(neg.reshape(-1))
+        su.copy_(users); si[:B].copy_(pos)
+        if N:
+            si[B:].copy_(neg.reshape(-1))
         self.t += 1
         self.dirty = True
         g.replay()

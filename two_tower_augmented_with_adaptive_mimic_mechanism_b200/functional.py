@@ -416,6 +416,32 @@ def loss_fwd_bwd(o_u, o_i, *, t_u=None, t_p=None, q_u=None, q_p=None, lambda_u=0
     return loss, do_u, do_i, dq_u, dq_p
 
 
+def inbatch_loss_fwd_bwd(o_u, o_p, *, t_u=None, t_p=None, q_u=None, q_p=None, lambda_u=0.0, lambda_i=0.0, backward=True, out=None,
+                         precision="fp32"):
+    """In-batch softmax loss (extension; see ttam.h): o_u, o_p [B, D].  Returns (loss[4], do_u, do_p, dq_u, dq_p)."""
+    _chk(o_u, torch.float32, "o_u"); _chk(o_p, torch.float32, "o_p")
+    B, D = o_u.shape
+    dev = o_u.device
+    mimic = q_u is not None
+    for name, ten in (("o_u", o_u), ("o_p", o_p), ("t_u", t_u), ("t_p", t_p), ("q_u", q_u), ("q_p", q_p)):
+        if ten is not None and not ten.is_contiguous():
+            raise ValueError(f"inbatch_loss_fwd_bwd: {name} must be contiguous")
+    if out is not None:
+        loss, do_u, do_p, dq_u, dq_p = out
+    else:
+        loss = torch.empty(4, dtype=torch.float32, device=dev)
+        do_u = torch.empty_like(o_u) if backward else None
+        do_p = torch.empty_like(o_p) if backward else None
+        dq_u = torch.empty_like(o_u) if (backward and mimic) else None
+        dq_p = torch.empty_like(o_u) if (backward and mimic) else None
+    L = lib()
+    ws = workspace(L.ttam_inbatch_loss_workspace_bytes(B, D), dev, "inbatch")
+    check(L.ttam_inbatch_loss_fwd_bwd(o_u.data_ptr(), o_p.data_ptr(), _ptr(t_u), _ptr(t_p), _ptr(q_u), _ptr(q_p), float(lambda_u),
+                                      float(lambda_i), loss.data_ptr(), _ptr(do_u), _ptr(do_p), _ptr(dq_u), _ptr(dq_p), B, D,
+                                      PREC[precision], ws.data_ptr(), ws.numel(), _stream()), "inbatch_loss_fwd_bwd")
+    return loss, do_u, do_p, dq_u, dq_p
+
+
 def category_alignment(item_idx, emb, cat_tensor, n_categories: int, major: int, *, lambda_c: float = 1.0,
                        loss_out=None, grad_a=None, grad_b=None, B: int = 0):
     """Category-alignment loss of `emb` [R, D] (rows = item_idx) and its gradient (see ttam.h).  Returns the raw loss
