@@ -40,11 +40,11 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {  // fixed shuff
 }
 
 // one block per row b of S
-__global__ void __launch_bounds__(kRowThreads) inbatch_rows_kernel(float* __restrict__ S, int64_t B, float* __restrict__ rowloss,
-                                                                   int backward) {
+__global__ void __launch_bounds__(kRowThreads) inbatch_rows_kernel(float* __restrict__ S, int64_t ldS, int64_t B,
+                                                                   float* __restrict__ rowloss, int backward) {
   __shared__ float sh[kRowThreads / 32];
   const int64_t b = blockIdx.x;
-  float* row = S + b * B;
+  float* row = S + b * ldS;   // ldS is a multiple of 4 floats: every row starts 16-byte aligned
   float m = -INFINITY;
   for (int64_t j = threadIdx.x * 4; j < B; j += kRowThreads * 4) {
     if (j + 3 < B) {
@@ -149,7 +149,7 @@ using namespace ttam::inbatch;
 
 extern "C" int64_t ttam_inbatch_loss_workspace_bytes(int64_t B, int64_t D) {
   if (B <= 0 || D <= 0) return 256;
-  return align_up(B * B * 4, 256) + align_up(B * 4, 256) + align_up(kMimicBlocks * 2 * 4, 256) +
+  return align_up(B * align_up(B, 4) * 4, 256) + align_up(B * 4, 256) + align_up(kMimicBlocks * 2 * 4, 256) +
          align_up(ttam_linear_wgrad_workspace_bytes(B, B, D), 256) + 256;
 }
 
@@ -170,23 +170,24 @@ extern "C" int ttam_inbatch_loss_fwd_bwd(const float* o_u, const float* o_p, con
   }
   cudaStream_t s = (cudaStream_t)stream;
   char* w = (char*)workspace;
-  float* S = (float*)w;                 w += align_up(B * B * 4, 256);
+  const int64_t ldS = align_up(B, 4);
+  float* S = (float*)w;                 w += align_up(B * ldS * 4, 256);
   float* rowloss = (float*)w;           w += align_up(B * 4, 256);
   float* partial = (float*)w;           w += align_up(kMimicBlocks * 2 * 4, 256);
   void* wg_ws = (void*)w;
   const int64_t wg_bytes = workspace_bytes - (w - (char*)workspace);
   // 1. S = o_u . o_p^T
-  int rc = ttam_linear_fwd(o_u, D, nullptr, o_p, D, nullptr, S, B, B, B, D, TTAM_ACT_NONE, 0.f, 0, 0, nullptr, precision & 0xFF, stream);
+  int rc = ttam_linear_fwd(o_u, D, nullptr, o_p, D, nullptr, S, ldS, B, B, D, TTAM_ACT_NONE, 0.f, 0, 0, nullptr, precision & 0xFF, stream);
   if (rc != TTAM_OK) return rc;
   // 2. row statistics, per-row loss, S <- dL/dS
-  inbatch_rows_kernel<<<(unsigned)B, kRowThreads, 0, s>>>(S, B, rowloss, backward ? 1 : 0);
+  inbatch_rows_kernel<<<(unsigned)B, kRowThreads, 0, s>>>(S, ldS, B, rowloss, backward ? 1 : 0);
   TTAM_LAUNCH_CHECK();
   if (backward) {
     // 3. do_u = dL/dS . o_p          (dx[M,K] = dy[M,N] . w[N,K] with M = N = B, K = D)
-    rc = ttam_linear_dgrad(S, B, o_p, do_u, D, nullptr, 0, 0, 1.f, 0, B, B, D, precision & 0xFF, stream);
+    rc = ttam_linear_dgrad(S, ldS, o_p, do_u, D, nullptr, 0, 0, 1.f, 0, B, B, D, precision & 0xFF, stream);
     if (rc != TTAM_OK) return rc;
     // 4. do_p = dL/dS^T . o_u        (dw[N,K] = dy[M,N]^T . x[M,K])
-    rc = ttam_linear_wgrad(S, B, o_u, D, nullptr, do_p, nullptr, B, B, D, 0, wg_ws, wg_bytes, precision & 0xFF, stream);
+    rc = ttam_linear_wgrad(S, ldS, o_u, D, nullptr, do_p, nullptr, B, B, D, 0, wg_ws, wg_bytes, precision & 0xFF, stream);
     if (rc != TTAM_OK) return rc;
   }
   // 5. mimic terms and the loss scalars
