@@ -208,7 +208,8 @@ def time_kernel_classes(eng, F, c, dev, users, pos, neg, user_x, item_x, nu_l, n
             tot += k0.elapsed_time(k1)
         return tot / reps
 
-    idx = (torch.cat([pos, neg.reshape(-1)]) % ni_l).contiguous()
+    inbatch = getattr(eng, "loss_kind", "sampled") == "inbatch"
+    idx = ((pos if inbatch else torch.cat([pos, neg.reshape(-1)])) % ni_l).contiguous()
     R = idx.numel()
     out = []
 
@@ -259,8 +260,13 @@ def time_kernel_classes(eng, F, c, dev, users, pos, neg, user_x, item_x, nu_l, n
     add("gate_fwd: sigmoid, blend, + A_item[idx]", lambda: F.gate_fwd(z, pre2, aug_table=plan.aug, idx=idx, g=g, t=t, o=o, q=q),
         R * (2 * D + D + D + 4 * D) * 4 + R * 8)
     ou, tu, qu = f32(B, D).normal_(), f32(B, D).normal_(), f32(B, D).normal_()
-    add("loss_fwd_bwd: dots, BCE, mimic MSEs, all gradients", lambda: F.loss_fwd_bwd(ou, o, t_u=tu, t_p=t[:B], q_u=qu, q_p=q[:B], lambda_u=0.15, lambda_i=0.15),
-        2 * (R + 4 * B) * D * 4)
+    if inbatch:
+        add("inbatch_loss_fwd_bwd: S = o_u o_p^T, row softmax, dS . o_p, dS^T . o_u, mimic",
+            lambda: F.inbatch_loss_fwd_bwd(ou, o, t_u=tu, t_p=t, q_u=qu, q_p=q, lambda_u=0.15, lambda_i=0.15, precision=precision),
+            4 * B * B * 4 + 12 * B * D * 4, 3 * 2.0 * B * B * D)
+    else:
+        add("loss_fwd_bwd: dots, BCE, mimic MSEs, all gradients", lambda: F.loss_fwd_bwd(ou, o, t_u=tu, t_p=t[:B], q_u=qu, q_p=q[:B], lambda_u=0.15, lambda_i=0.15),
+            2 * (R + 4 * B) * D * 4)
     add("gate_bwd", lambda: F.gate_bwd(dt, z, g, dpre2=dpre2, dz=dz), R * (D + 2 * D + D + D + 2 * D) * 4)
     add("gemm gate 2 dgrad (relu mask)", lambda: F.linear_dgrad(dpre2, G2, out=dpre1, aux=a, relu_mask=True, precision=precision),
         R * (D + 2 * Hg) * 4, 2.0 * R * Hg * D)
@@ -345,6 +351,10 @@ def main():
     ap.add_argument("--mode", default="hybrid", choices=["hybrid", "sparse", "dense"],
                     help="optimiser sweep (BASELINE configs[4]): hybrid = AdamW + SparseAdam (reference default), "
                          "sparse = embedding-only towers, mimic off, all SparseAdam, dense = sparse:false (AdamW semantics on every table)")
+    ap.add_argument("--loss", default="sampled", choices=["sampled", "inbatch"],
+                    help="sampled = the reference's loss (BCE over 1 positive + 5 sampled negatives, training.py:770-803; the headline); "
+                         "inbatch = in-batch softmax over the batch's positives (BASELINE configs[1] wording; an extension the reference "
+                         "does not have - a separately labelled line)")
     ap.add_argument("--no-graph", action="store_true", help="N=1: launch the step eagerly instead of replaying a CUDA graph (diagnostic)")
     ap.add_argument("--route", default="peer", choices=["static", "peer", "dynamic"],
                     help="N>1: static = fixed-capacity slots, the whole sharded step replays as CUDA graphs; peer = static, and the "
@@ -369,6 +379,8 @@ def main():
                     f"{c['N']} sampled negatives, all-sparse SparseAdam")
     elif args.mode == "dense":
         workload = workload.replace("AdamW+SparseAdam", "all-dense AdamW (sparse:false, lazy-exact rows)")
+    if args.loss == "inbatch":
+        workload = workload.replace(f"{c['N']} sampled negatives", "IN-BATCH SOFTMAX over the batch's positives (extension: not a reference loss)")
 
     if args.impl == "reference":
         if rank != 0:
@@ -415,7 +427,7 @@ def main():
                 dist.broadcast(prm.data, src=0)
     eng = tt.FusedEngine(model, optimizer="adamw", lr=c["lr"], weight_decay=c["wd"], precision=args.precision,
                          loss_weights={} if mimic is None else {"mimic_user": c["lambdas"][0], "mimic_item": c["lambdas"][1]},
-                         max_steps=4 * (K + W) + 64)
+                         max_steps=4 * (K + W) + 64, loss=args.loss)
     sh = tt.ShardedEngine(eng, static=args.route != "dynamic", peer=args.route == "peer") if world > 1 else None
     users, pos, neg = make_batches(K + W, c, dev, gen)          # global row ids
     if sh is not None:
@@ -518,7 +530,7 @@ def main():
     # ---- through the drop-in hook: hooks._train_one_epoch (the function scripts/train_b200.py binds over the reference's
     # training.py:700-833) fed by a DataLoader over K*B interactions, device sampler + device batch iterator + graph replay
     hook_line = None
-    if world == 1 and not args.no_hook:
+    if world == 1 and not args.no_hook and args.loss == "sampled":
         try:
             hook_line = bench_hook(tt, eng, model, c, K, users[W:W + K].reshape(-1), pos[W:W + K].reshape(-1), user_x, item_x, dev, args.precision)
         except Exception as e:  # noqa: BLE001
