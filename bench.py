@@ -361,11 +361,16 @@ def main():
                          "row payloads travel by NVLink peer loads/stores instead of NCCL all-to-alls; dynamic = per-step "
                          "split sizes, eager launches (diagnostic)")
     ap.add_argument("--small", action="store_true", help="1/16-size tables (debugging only; not a valid bench line)")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 4],
+                    help="2 = BASELINE configs[1] (1M x 2M, D=96; the headline), 4 = configs[3] (10M users x 50M items, D=256, "
+                         "H=512: row-sharded over 8 GPUs, ~70 GB per GPU; a separately labelled record, run with --gpus 8)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     c = dict(CFG)
+    if args.config == 4:
+        c.update(NU=10_000_000, NI=50_000_000, D=256, H=512, Hg=256)
     if args.small:
         c.update(NU=c["NU"] // 16, NI=c["NI"] // 16)
     if args.batch:
@@ -564,7 +569,10 @@ def main():
         line["gpu_launches"] = (int(sh.launches_per_step) * K if args.route != "dynamic" and not args.no_graph else
                                 int((F.lib().ttam_launch_count() - launches0) * K / steps_launched))
 
-    if not args.no_retrieval:
+    if not args.no_retrieval and c["D"] > 128:
+        if rank == 0:
+            line["retrieval"] = {"skipped": f"the bf16 tensor-core top-K takes D <= 128 (this config has D = {c['D']}); FlatIPIndex(dtype=float32) covers it"}
+    elif not args.no_retrieval:
         r = bench_retrieval(tt, c, dev, pk, world=world, rank=rank)
         if rank == 0:
             line["retrieval"] = r
