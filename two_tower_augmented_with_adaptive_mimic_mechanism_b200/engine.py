@@ -79,7 +79,7 @@ class FusedEngine:
         # layer 1 of the feature encoders from the bag (CSR + dense tail) form of the feature matrices: "auto" = whenever
         # a matrix is sparse enough for the bag kernels (<= 64 non-zeros per row outside the dense tail), False = always
         # the dense GEMM (X[idx] . W1^T), True = like "auto" but a matrix that cannot be converted raises
-        self.bag = bag
+        self.bag = bag if os.environ.get("TTAM_BAG", "1") != "0" else False      # TTAM_BAG=0: A/B switch for measurements
         self._bags: dict = {}
         self.seed = int(seed)
         self.max_steps = int(max_steps)

@@ -8,6 +8,7 @@ Math follows SURVEY.md Appendix A (reference encoders.py:102-168,221-255; adapti
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Optional
 
@@ -196,7 +197,7 @@ def _tower_forward_composite(plan, idx, X, *, train, bufs, seed, rng_base, state
     c.desc = _tower_desc(plan, X, W1, p_drop, seed, rng_base, state, precision, augment, bag)
     c.desc.x_rounded, c.desc.w1_rounded = int(pre), int(precision != "fp32" and bag is None)
     c.bag = bag            # keeps the CSR tensors alive as long as the cache
-    if precision != "fp32":
+    if precision != "fp32" and os.environ.get("TTAM_NO_PREP", "0") == "0":
         # TF32-rounded and rounded-transposed copies of the three small weights (ttam_prepare_weights inside the forward call)
         (_, _), (W2, _) = plan.fe_layers
         G1, _, G2, _ = plan.gate
