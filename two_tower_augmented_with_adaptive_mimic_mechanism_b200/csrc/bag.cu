@@ -113,18 +113,25 @@ struct Ring {
   const BagP& p;
   uint8_t* smem;
   Layout L;
-  int64_t r_begin, r_end;
+  int64_t chunk_begin, chunk_end;  // this CTA's rows
+  int64_t r_begin, r_end;          // the block of <= kChunkRows rows of the chunk that is in the table / ring right now
   int ntiles, lane, warp, rpl;
   int pad_mask;  // 3: every row's entry list is padded to a multiple of 4 with zero entries (forward), 0: compact (wgrad)
   MetaView m;
+
+  __device__ __forceinline__ void set_block(int64_t first) {
+    r_begin = chunk_begin + first;
+    r_end = min(chunk_end, r_begin + kChunkRows);
+    ntiles = (int)((r_end - r_begin + p.TR - 1) / p.TR);
+  }
 
   __device__ Ring(const BagP& p_, uint8_t* smem_, const Layout& L_, int pad_mask_) : p(p_), smem(smem_), L(L_), pad_mask(pad_mask_) {
     lane = threadIdx.x & 31;
     warp = threadIdx.x >> 5;
     rpl = p.TR / 32;
-    r_begin = (int64_t)blockIdx.y * p.rows_per_chunk;
-    r_end = min(p.R, r_begin + p.rows_per_chunk);
-    ntiles = (int)((r_end - r_begin + p.TR - 1) / p.TR);
+    chunk_begin = (int64_t)blockIdx.y * p.rows_per_chunk;
+    chunk_end = min(p.R, chunk_begin + p.rows_per_chunk);
+    set_block(0);
     m.g = reinterpret_cast<int*>(smem + L.meta_off);
     m.beg = reinterpret_cast<uint32_t*>(m.g + kChunkRows);
     m.offn = m.beg + kChunkRows;
@@ -207,17 +214,22 @@ struct Ring {
 
   template <bool ROWID, typename Extra, typename Process>
   __device__ __forceinline__ void run(Extra& extra, Process& process) {
-    build_table();
-    __syncthreads();   // table (and whatever the kernel wrote to shared memory before) visible
-    stage<ROWID>(0, extra);
-    stage<ROWID>(1, extra);
-    for (int tile = 0; tile < ntiles; ++tile) {
-      asm volatile("cp.async.wait_group 1;" ::: "memory");  // tile `tile` has landed (this thread's copies)
-      __syncthreads();  // ... for everyone; tile - 1 is fully processed (its stage is free)
-      stage<ROWID>(tile + 2, extra);
-      process(tile, stage_ptr(tile), m, tile * p.TR);
+    // a chunk longer than the table is walked in blocks of kChunkRows rows (two more global latencies per block)
+    for (int64_t first = 0; first < chunk_end - chunk_begin; first += kChunkRows) {
+      set_block(first);
+      build_table();
+      __syncthreads();   // table (and whatever the kernel wrote to shared memory before) visible
+      stage<ROWID>(0, extra);
+      stage<ROWID>(1, extra);
+      for (int tile = 0; tile < ntiles; ++tile) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");  // tile `tile` has landed (this thread's copies)
+        __syncthreads();  // ... for everyone; tile - 1 is fully processed (its stage is free)
+        stage<ROWID>(tile + 2, extra);
+        process(tile, stage_ptr(tile), m, tile * p.TR);
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();   // everyone is done with the table and the ring before the next block rewrites them
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
 };
 
@@ -452,12 +464,12 @@ static bool configure(int64_t H, int64_t F, int64_t tail_start, int64_t max_nnz,
   }
   return false;
 }
-// rows per CTA: one chunk per SM where that keeps a chunk within the meta table (kChunkRows), more (smaller) chunks otherwise
+// rows per CTA: one chunk per SM - 153 CTAs on 148 SMs would be two waves (the kernel walks a chunk longer than its meta
+// table in blocks)
 static int64_t rows_per_chunk_for(int64_t R, int slices, int TR) {
   int64_t c = num_sms() / slices;
   if (c < 1) c = 1;
   int64_t rows = align_up(ceil_div(R, c), TR);
-  if (rows > kChunkRows) rows = kChunkRows;
   if (rows < TR) rows = TR;
   return rows;
 }
