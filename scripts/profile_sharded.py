@@ -35,6 +35,14 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     for s in range(8, 14):
         sh.train_step(users[s], pos[s], neg[s], ux, ix, graph=graph)
     torch.cuda.synchronize()
+if rank == 0 and os.environ.get("TTAM_TIMELINE"):
+    # one step's device timeline (rank 0): start offset, duration, stream, kernel
+    ev = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA), key=lambda e: e.time_range.start)
+    starts = [e.time_range.start for e in ev if "advance_step" in e.name]
+    lo, hi = starts[-2], starts[-1]
+    for e in ev:
+        if lo <= e.time_range.start < hi:
+            print(f"{e.time_range.start - lo:8.1f} {e.time_range.end - e.time_range.start:7.1f} us  {e.name[:70]}")
 if rank == 0:
     ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     t0, t1 = min(e.time_range.start for e in ev), max(e.time_range.end for e in ev)
