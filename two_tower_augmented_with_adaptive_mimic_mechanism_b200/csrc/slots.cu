@@ -125,8 +125,12 @@ __global__ void __launch_bounds__(256) slot_pad_kernel(int W, int64_t cap, const
   for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += (int64_t)gridDim.x * blockDim.x) {
     const int o = (int)(s / cap);
     const int64_t j = s - (int64_t)o * cap;
-    if (j >= counts[o]) {
-      send_idx[s] = first[o];
+    const int64_t cnt = counts[o];
+    if (j >= cnt) {
+      // padding repeats REAL ids of the bucket (zero gradient rows: the owner's touched-row sets stay exact), cycling through
+      // them: repeating only the first one handed the owner one segment of ~cap - count duplicates, which the long-segment
+      // kernels of the row-wise optimisers then summed serially (85-96 us per table at N = 2)
+      send_idx[s] = cnt > 0 ? send_idx[(int64_t)o * cap + (j - cnt) % (cnt < cap ? cnt : cap)] : first[o];
       req_of[s] = -1;
     }
   }

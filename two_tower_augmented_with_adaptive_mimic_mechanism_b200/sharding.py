@@ -249,7 +249,7 @@ class SlotExchange:
     """All-to-all route of one index set with `cap` slots per (requester, owner) pair.
 
     Every collective is an equal-split all-to-all of W*cap rows.  A requester's unused slots are PADDING: they repeat the
-    first real id of their bucket, so the owner's set of touched rows is exactly the set of requested rows (the
+    real ids of their bucket (cyclically), so the owner's set of touched rows is exactly the set of requested rows (the
     SparseAdam / lazy-AdamW row sets stay bit-identical to the unpadded step), their tower outputs are dropped on the
     way back, and their gradient rows are zeros (x + 0.0 == x: segment sums and weight gradients are unchanged).
 
@@ -346,8 +346,13 @@ class SlotExchange:
         j = self._arange_r - starts[so]
         slot = torch.where(j < cap, so * cap + j, torch.full_like(j, self.n_slots))
         self.slot_of.index_copy_(0, order, slot)
-        first = sid[torch.clamp(starts, max=R - 1)]             # first real id of every bucket (meaningless if empty: flagged)
-        self.send_idx[: self.n_slots].view(W, cap).copy_(first.unsqueeze(1).expand(W, cap))
+        # padding slots repeat the bucket's real ids cyclically (slot j >= count holds the id of slot (j - count) % count;
+        # an empty bucket is flagged and its content is meaningless)
+        real = torch.clamp(counts, min=1, max=cap)
+        jj = torch.arange(cap, device=idx.device).unsqueeze(0).expand(W, cap)
+        src_j = torch.where(jj < counts.unsqueeze(1), jj, (jj - counts.unsqueeze(1)) % real.unsqueeze(1))
+        src_pos = torch.clamp(starts.unsqueeze(1) + src_j, max=R - 1)
+        self.send_idx[: self.n_slots].view(W, cap).copy_(sid[src_pos])
         self.send_idx.scatter_(0, slot, sid)                    # overflowing ids land in the dump slot
         self.flag.copy_(((counts > cap) | (counts == 0)).any().to(torch.int32).reshape(1))
 
