@@ -120,7 +120,11 @@ class FusedEngine:
         self._side_stream = torch.cuda.Stream(device=dev)
         self._aug_stream = torch.cuda.Stream(device=dev)
         self._comm_stream = torch.cuda.Stream(device=dev)
-        self._sort_streams = {"u": torch.cuda.Stream(device=dev), "i": torch.cuda.Stream(device=dev)}
+        # the sort + lazy catch-up branch is a chain of small dependent kernels that the forward's last launch (o = t + A[idx])
+        # waits for: high priority, so that its CTAs are placed ahead of the towers' persistent GEMM CTAs whenever an SM frees up
+        # (device timeline of a step: the chain's kernels started 20-30 us late each, and the tower waited for them)
+        prio = -1 if os.environ.get("TTAM_SORT_PRIORITY", "1") != "0" else 0
+        self._sort_streams = {"u": torch.cuda.Stream(device=dev, priority=prio), "i": torch.cuda.Stream(device=dev, priority=prio)}
         self._overlap_sort = os.environ.get("TTAM_OVERLAP_SORT", "1") != "0"
         self._wgrad_streams = {"u": torch.cuda.Stream(device=dev), "i": torch.cuda.Stream(device=dev)}
         self._split_wgrad = os.environ.get("TTAM_WGRAD_STREAM", "1") != "0"
