@@ -664,3 +664,29 @@ def test_tma_gemm_dgrad_with_transposed_weight(F, M, N, K):
     assert torch.equal(out, out_ref)
     got_r = F.linear_dgrad(dev(dy), WrT, precision="tf32", w_transposed=True, out_rounded=True)
     assert torch.equal(got_r, F.round_tf32_(ref.clone()))
+
+
+@pytest.mark.parametrize("M,N,K", [(49152, 96, 96), (49152, 96, 192), (8192, 96, 192), (4096, 192, 96), (999, 48, 36), (3000, 192, 608),
+                                   (700, 512, 256), (33, 96, 96), (20000, 256, 512)])
+def test_tma_wgrad_matches_cp_async_kernel(F, M, N, K, monkeypatch):
+    """dw = dy^T x and db = colsum(dy) from the TMA-fed MN-major kernel against the cp.async kernel (same TF32 rounding; the split
+    of the row range differs, so the fp32 partial sums are combined in a different order) and against the fp64 product."""
+    rng = np.random.default_rng(M + N + K)
+    dy = rng.standard_normal((M, N)).astype(np.float32)
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    monkeypatch.setenv("TTAM_NO_TMA_WGRAD", "1")
+    dw_ref, db_ref = F.linear_wgrad(dev(dy), dev(x), precision="tf32")
+    monkeypatch.delenv("TTAM_NO_TMA_WGRAD")
+    dw, db = F.linear_wgrad(dev(dy), dev(x), precision="tf32")
+    _tf32_close(dw.cpu().numpy(), dy.T, x, extra=1e-4)
+    np.testing.assert_allclose(dw.cpu().numpy(), dw_ref.cpu().numpy(), rtol=1e-4, atol=2e-3 * np.sqrt(M / 1000))
+    np.testing.assert_allclose(db.cpu().numpy(), dy.astype(np.float64).sum(0), rtol=1e-4, atol=5e-4 * np.sqrt(M / 1000))
+    np.testing.assert_allclose(db.cpu().numpy(), db_ref.cpu().numpy(), rtol=1e-5, atol=1e-3)
+    dw2, db2 = F.linear_wgrad(dev(dy), dev(x), precision="tf32")
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)                      # deterministic
+    xr = F.round_tf32_(dev(x))
+    dw3, _ = F.linear_wgrad(dev(dy), xr, precision="tf32", x_rounded=True)
+    assert torch.equal(dw3, dw)
+    acc = dev(np.ones((N, K), np.float32))
+    F.linear_wgrad(dev(dy), dev(x), dw=acc, db=dev(np.zeros(N, np.float32)), accumulate=True, precision="tf32")
+    np.testing.assert_allclose(acc.cpu().numpy(), dw.cpu().numpy() + 1.0, rtol=1e-6, atol=1e-5)

@@ -197,9 +197,10 @@ extern "C" int ttam_linear_dgrad(const float* dy, int64_t lddy, const float* w, 
 }
 
 extern "C" int64_t ttam_linear_wgrad_workspace_bytes(int64_t M, int64_t N, int64_t K) {
-  int s = wgrad_splits(M, N, K);  // the workspace serves either precision
-  const int s_tc = tc_wgrad_splits(M, N, K);
+  int s = wgrad_splits(M, N, K);  // the workspace serves either precision / kernel
+  const int s_tc = tc_wgrad_splits(M, N, K), s_tma = tma_wgrad_splits(M, N, K);
   if (s_tc > s) s = s_tc;
+  if (s_tma > s) s = s_tma;
   return ((int64_t)s * N * K + (int64_t)colsum_splits(M) * N) * (int64_t)sizeof(float);
 }
 
@@ -219,13 +220,16 @@ extern "C" int ttam_linear_wgrad(const float* dy, int64_t lddy, const float* x, 
     return TTAM_EWORKSPACE;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  const int splits = precision == TTAM_PREC_TF32 ? tc_wgrad_splits(M, N, K) : wgrad_splits(M, N, K);
+  int splits = precision == TTAM_PREC_TF32 ? tc_wgrad_splits(M, N, K) : wgrad_splits(M, N, K);
+  if (precision == TTAM_PREC_TF32 && tma_wgrad_splits(M, N, K) > splits) splits = tma_wgrad_splits(M, N, K);
   const int chunk = (int)align_up(ceil_div(M, splits), BK);
   float* partial_w = (float*)workspace;
   float* partial_b = partial_w + (int64_t)splits * N * K;
   if (precision == TTAM_PREC_TF32) {
     int real = 0;
-    const int rc = tc_linear_wgrad_partials(dy, lddy, x, ldx, gather, partial_w, db ? partial_b : nullptr, M, N, K, &real, prerounded, s);
+    int rc = gather ? 1 : tma_wgrad_partials(dy, lddy, x, ldx, partial_w, db ? partial_b : nullptr, M, N, K, &real, prerounded, s);
+    if (rc < 0) return rc;
+    if (rc == 1) rc = tc_linear_wgrad_partials(dy, lddy, x, ldx, gather, partial_w, db ? partial_b : nullptr, M, N, K, &real, prerounded, s);
     if (rc != TTAM_OK) return rc;
     // one launch sums the weight-gradient partials and (the bias gradient came out of the same pass over dy) the
     // column-sum partials

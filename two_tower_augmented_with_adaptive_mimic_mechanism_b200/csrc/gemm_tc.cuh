@@ -25,4 +25,10 @@ int tma_gemm(const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
              const float* aux, int64_t ldaux, int mask_mode, float scale, int accumulate, int roundA, int round_out,
              cudaStream_t stream);
 
+// gemm_tma.cu: the weight gradient with TMA-fed MN-major operands (no row gather).  Same partial layout as
+// tc_linear_wgrad_partials; +1 when the operands do not qualify.
+int tma_wgrad_splits(int64_t M, int64_t N, int64_t K);
+int tma_wgrad_partials(const float* dy, int64_t lddy, const float* x, int64_t ldx, float* partial, float* colsum_partial, int64_t M,
+                       int64_t N, int64_t K, int* real_splits, int prerounded, cudaStream_t stream);
+
 }  // namespace ttam

@@ -282,6 +282,174 @@ gemm_tf32_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Weight gradient  dW[N, K] = dy[R, N]^T . x[R, K]  (reduction over the rows r, split over blockIdx.y), both operands MN-major:
+// the reduction index r is the ROW of both row-major matrices.  TMA lays the tiles out for the tensor core directly: a box of
+// 32 columns x 32 rows with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B is exactly one "MN-major, 128-byte swizzle, 32-byte atom" block of
+// the UMMA layout (32 M/N elements x 32 reduction rows, rows 128 bytes apart, the 32-byte chunk index XOR-ed with the row index
+// mod 4) - the layout gemm_tc.cu builds with 8 warps of cp.async.  C(m = feature k', n = n') is stored transposed,
+// part[z][n'][k'], and summed over z by splitk_reduce_kernel like the partials of gemm_tc.cu.  The bias gradient (exact fp32
+// column sums of dy, taken before the TF32 rounding) comes out of the same pass: the rounding warps accumulate it.
+struct WgP {
+  float* part;     // [splits][N][K]
+  float* colsum;   // [splits][N] or null
+  int R, N, K;
+  int bn, m_tiles, rows_per_split, stages;
+  int roundA, roundB;
+};
+constexpr uint32_t kAtomBytes = 32 * 128;   // one 32 x 32 fp32 block
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tf32_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDy, WgP p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nb_atoms = p.bn >> 5;
+  const uint32_t stage_bytes = kABytes + (uint32_t)nb_atoms * kAtomBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (uint32_t)p.stages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* ready = bars + kMaxStages;
+  uint64_t* empty = bars + 2 * kMaxStages;
+  uint64_t* acc_full = bars + 3 * kMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kMaxStages + 4);
+  float* tail = reinterpret_cast<float*>(smem + (uint32_t)p.stages * stage_bytes + 512);   // epilogue tiles / colsum reduction
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = blockIdx.x % p.m_tiles, nt = blockIdx.x / p.m_tiles;
+  const int m0 = mt * kBM, n0 = nt * p.bn;
+  const int r_lo = blockIdx.y * p.rows_per_split, r_hi = min(p.R, r_lo + p.rows_per_split);
+  const int nchunks = (r_hi - r_lo + kKC - 1) / kKC;
+  const bool want_colsum = p.colsum != nullptr && mt == 0;
+  const bool need_round = p.roundA || p.roundB || want_colsum;
+  const uint32_t tmem_cols = p.bn <= 32 ? 32u : p.bn <= 64 ? 64u : p.bn <= 128 ? 128u : 256u;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDy);
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(full + i, 1);
+      mbar_init(ready + i, kRoundWarps);
+      mbar_init(empty + i, 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int c = 0; c < nchunks; ++c) {
+        const int stage = c % p.stages;
+        mbar_wait_relaxed(empty + stage, ((c / p.stages) & 1) ^ 1, 64);
+        uint8_t* sA = smem + (uint32_t)stage * stage_bytes;
+        mbar_expect_tx(full + stage, stage_bytes);
+        const int r = r_lo + c * kKC;
+        for (int a = 0; a < 4; ++a) tma_load_2d(sA + a * kAtomBytes, &tmX, full + stage, m0 + 32 * a, r);
+        for (int b = 0; b < nb_atoms; ++b) tma_load_2d(sA + kABytes + b * kAtomBytes, &tmDy, full + stage, n0 + 32 * b, r);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(2 /*tf32*/, kBM, p.bn, 1, 1);
+      for (int c = 0; c < nchunks; ++c) {
+        const int stage = c % p.stages;
+        mbar_wait((need_round ? ready : full) + stage, (c / p.stages) & 1);
+        tc_fence_after();
+        const uint32_t sA = smem_u32(smem + (uint32_t)stage * stage_bytes);
+        const uint32_t sB = sA + kABytes;
+#pragma unroll
+        for (int ks = 0; ks < kKC / 8; ++ks)   // one MMA consumes 8 reduction rows: two 4-row groups (1024 B) of every block
+          umma_tf32(tmem_base, make_mnmajor_desc_tf32(sA + ks * 1024, kAtomBytes, 512), make_mnmajor_desc_tf32(sB + ks * 1024, kAtomBytes, 512),
+                    idesc, (c | ks) != 0 ? 1u : 0u);
+        umma_commit(empty + stage);
+      }
+      umma_commit(acc_full);
+    }
+  } else if (warp < 2 + kEpiWarps) {
+    // ===================== epilogue: transposed store  part[z][n][m]  through a [32][33] tile per warp =====================
+    const int quad = warp & 3;
+    float* stg = tail + (warp - 2) * (32 * 33);
+    float* Cz = p.part + (int64_t)blockIdx.y * p.N * p.K;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    for (int col = 0; col < p.bn; col += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)col, r);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = __uint_as_float(r[i]);
+      __syncwarp();
+      const int m = m0 + quad * 32 + lane;
+#pragma unroll 4
+      for (int i = 0; i < 32; ++i) {
+        const int n = n0 + col + i;
+        if (n < p.N && m < p.K) Cz[(int64_t)n * p.K + m] = stg[lane * 33 + i];   // lanes = 32 consecutive m: one 128-byte store
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== rounding warps (+ exact column sums of dy) =====================
+    const int t = threadIdx.x - 32 * (2 + kEpiWarps);   // 0 .. 127
+    // B pieces of this thread: piece t + 128 i -> block i >> 1, reduction row (t >> 3) + 16 (i & 1), physical 16-byte chunk t & 7
+    // -> logical chunk ((c >> 1) ^ (row & 3)) << 1 | (c & 1), the same for every i
+    const int c16 = ((((t & 7) >> 1) ^ ((t >> 3) & 3)) << 1) | (t & 1);
+    float4 csum[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) csum[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (need_round) {
+      for (int c = 0; c < nchunks; ++c) {
+        const int stage = c % p.stages;
+        mbar_wait(full + stage, (c / p.stages) & 1);
+        uint8_t* sA = smem + (uint32_t)stage * stage_bytes;
+        if (p.roundA) {
+#pragma unroll
+          for (int i = 0; i < (int)(kABytes / 16) / (32 * kRoundWarps); ++i) {
+            uint4* q = reinterpret_cast<uint4*>(sA) + t + 32 * kRoundWarps * i;
+            const float4 v = *reinterpret_cast<float4*>(q);
+            *q = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+          }
+        }
+        if (p.roundB || want_colsum) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (i < 2 * nb_atoms) {
+              uint4* q = reinterpret_cast<uint4*>(sA + kABytes) + t + 128 * i;
+              const float4 v = *reinterpret_cast<float4*>(q);
+              if (want_colsum) { csum[i >> 1].x += v.x; csum[i >> 1].y += v.y; csum[i >> 1].z += v.z; csum[i >> 1].w += v.w; }
+              if (p.roundB) *q = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ready + stage);
+      }
+    }
+    if (want_colsum) {
+      // combine the 16 threads that hold the same logical chunk, in thread order (deterministic)
+      mbar_wait(acc_full, 0);   // every MMA has read the stages: the ring memory is free
+      float4* red = reinterpret_cast<float4*>(smem);   // [128 threads][8 blocks]
+#pragma unroll
+      for (int b = 0; b < 8; ++b) red[t * 8 + b] = csum[b];
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kRoundWarps) : "memory");
+      for (int n = t; n < p.bn; n += 32 * kRoundWarps) {
+        const int b = n >> 5, want = (n & 31) >> 2, comp = n & 3;
+        float sacc = 0.f;
+        for (int u = 0; u < 32 * kRoundWarps; ++u) {
+          const int cu = ((((u & 7) >> 1) ^ ((u >> 3) & 3)) << 1) | (u & 1);
+          if (cu == want) sacc += reinterpret_cast<const float*>(red + u * 8 + b)[comp];
+        }
+        if (n0 + n < p.N) p.colsum[(int64_t)blockIdx.y * p.N + n0 + n] = sacc;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 }  // namespace tma
@@ -333,6 +501,56 @@ int tma_gemm(const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
   }
   const int grid = p.units < num_sms() ? p.units : num_sms();
   gemm_tf32_tma_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
+  TTAM_LAUNCH_CHECK();
+  return TTAM_OK;
+}
+
+// Splits of the TMA weight gradient: about two CTAs per SM, at least 256 rows each.
+int tma_wgrad_splits(int64_t M, int64_t N, int64_t K) {
+  const int64_t tiles = ceil_div(K, kBM) * ceil_div(N, 256);
+  int64_t s = (2 * (int64_t)num_sms()) / tiles;
+  const int64_t by_rows = ceil_div(M, 256);
+  if (s > by_rows) s = by_rows;
+  return (int)(s < 1 ? 1 : s);
+}
+
+// part[z][N][K] (and colsum[z][N]) for z < *real_splits.  +1: operands do not qualify (the caller uses gemm_tc.cu).
+int tma_wgrad_partials(const float* dy, int64_t lddy, const float* x, int64_t ldx, float* partial, float* colsum_partial, int64_t M,
+                       int64_t N, int64_t K, int* real_splits, int prerounded, cudaStream_t stream) {
+  if (!aligned16(dy) || !aligned16(x) || lddy % 4 || ldx % 4 || M <= 0 || N <= 0 || K <= 0) return 1;
+  if (getenv("TTAM_NO_TMA_GEMM") || getenv("TTAM_NO_TMA_WGRAD")) return 1;
+  WgP p{};
+  p.part = partial; p.colsum = colsum_partial; p.R = (int)M; p.N = (int)N; p.K = (int)K;
+  const int n_tiles = (int)ceil_div(N, 256);
+  p.bn = (int)align_up(ceil_div(N, n_tiles), 32);
+  const int nt = (int)ceil_div(N, p.bn);
+  p.m_tiles = (int)ceil_div(K, kBM);
+  const int splits = tma_wgrad_splits(M, N, K);
+  p.rows_per_split = (int)align_up(ceil_div(M, splits), kKC);
+  *real_splits = (int)ceil_div(M, p.rows_per_split);
+  p.roundA = !(prerounded & 1); p.roundB = 1;
+  const size_t stage_bytes = kABytes + (size_t)(p.bn / 32) * kAtomBytes;
+  p.stages = (int)((96 * 1024) / stage_bytes);       // two CTAs per SM
+  if (p.stages < 2) p.stages = 2;
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  CUtensorMap tmX, tmDy;
+  int rc = make_tmap_2d(&tmX, x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)M, (uint64_t)K, (uint64_t)ldx * 4, 32, 32,
+                        CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (rc != TTAM_OK) return rc;
+  rc = make_tmap_2d(&tmDy, dy, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)M, (uint64_t)N, (uint64_t)lddy * 4, 32, 32,
+                    CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (rc != TTAM_OK) return rc;
+  size_t tail = (size_t)kEpiWarps * 32 * 33 * 4;
+  size_t smem = (size_t)p.stages * stage_bytes;
+  if (smem < (size_t)128 * 8 * 16) smem = (size_t)128 * 8 * 16;     // the column-sum reduction reuses the ring
+  smem += 1024 + 512 + tail;
+  static bool attr_done = false;
+  if (!attr_done) {
+    TTAM_CUDA(cudaFuncSetAttribute(gemm_tf32_tma_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_done = true;
+  }
+  dim3 grid((unsigned)(p.m_tiles * nt), (unsigned)*real_splits);
+  gemm_tf32_tma_wgrad_kernel<<<grid, kThreads, smem, stream>>>(tmX, tmDy, p);
   TTAM_LAUNCH_CHECK();
   return TTAM_OK;
 }
