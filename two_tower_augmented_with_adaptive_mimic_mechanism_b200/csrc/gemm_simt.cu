@@ -8,6 +8,12 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 
+#define TTAM_TRY_RC(expr)             \
+  do {                                \
+    const int rc__ = (expr);          \
+    if (rc__ != TTAM_OK) return rc__; \
+  } while (0)
+
 namespace ttam {
 
 // out[i] (+)= sum_s partial[s][i] for two tensors at once (a weight gradient and its bias gradient), fixed order:
@@ -48,6 +54,73 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
 
 static inline int reduce_blocks(int64_t total) {
   return (int)std::min<int64_t>(ceil_div(total * 8, 256), (int64_t)num_sms() * 16);
+}
+
+// Vector form (every count a multiple of 4, 16-byte aligned buffers): L lanes (a power of two, <= 32) share one group of FOUR
+// consecutive output elements, lane l sums the splits l, l + L, ... with two independent chains, the L partial sums are
+// combined by a fixed shuffle tree.  A warp load then reads (32 / L) * 16 contiguous bytes of each of L splits - whole
+// sectors - where the scalar form above reads 16 bytes of each of 8 splits (half sectors): the 15 MB of partials of the
+// [192, 608] layer-1 gradient took 47 us with it.  L is chosen by the host from the problem size only, so the summation
+// order (and the result) does not depend on the launch geometry.
+__global__ void __launch_bounds__(256) splitk_reduce_vec_kernel(const float* __restrict__ partial_a, int64_t numel_a,
+                                                                float* __restrict__ out_a, const float* __restrict__ partial_b,
+                                                                int64_t numel_b, float* __restrict__ out_b, int splits,
+                                                                int accumulate, int L) {
+  const int64_t groups = (numel_a + numel_b) >> 2;
+  const int l = threadIdx.x & (L - 1);
+  const int64_t gstride = ((int64_t)gridDim.x * blockDim.x) / L;
+  const int64_t gmax = (groups + (32 / L) - 1) / (32 / L) * (32 / L);   // whole warps stay in the loop (shuffles)
+  for (int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / L; q < gmax; q += gstride) {
+    const bool live = q < groups;
+    const int64_t e = q << 2;
+    const bool in_a = e < numel_a;
+    const float* src = in_a ? partial_a + e : partial_b + (e - numel_a);
+    const int64_t stride = in_a ? numel_a : numel_b;
+    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+    if (live) {
+      int k = l;
+      for (; k + L < splits; k += 2 * L) {
+        const float4 a = ld_f4(src + (int64_t)k * stride), b = ld_f4(src + (int64_t)(k + L) * stride);
+        s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
+        s1.x += b.x; s1.y += b.y; s1.z += b.z; s1.w += b.w;
+      }
+      if (k < splits) {
+        const float4 a = ld_f4(src + (int64_t)k * stride);
+        s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
+      }
+    }
+    float4 t = make_float4(s0.x + s1.x, s0.y + s1.y, s0.z + s1.z, s0.w + s1.w);
+    for (int o = 1; o < L; o <<= 1) {
+      t.x += __shfl_xor_sync(0xffffffffu, t.x, o); t.y += __shfl_xor_sync(0xffffffffu, t.y, o);
+      t.z += __shfl_xor_sync(0xffffffffu, t.z, o); t.w += __shfl_xor_sync(0xffffffffu, t.w, o);
+    }
+    if (live && l == 0) {
+      float* dst = in_a ? out_a + e : out_b + (e - numel_a);
+      if (accumulate) {
+        const float4 old = ld_f4(dst);
+        t.x += old.x; t.y += old.y; t.z += old.z; t.w += old.w;
+      }
+      st_f4(dst, t);
+    }
+  }
+}
+
+// one entry point for both forms
+static int launch_splitk_reduce(const float* pa, int64_t na, float* oa, const float* pb, int64_t nb, float* ob, int splits,
+                                int accumulate, cudaStream_t s) {
+  const bool vec = na % 4 == 0 && nb % 4 == 0 && (((uintptr_t)pa | (uintptr_t)oa | (uintptr_t)pb | (uintptr_t)ob) & 15) == 0;
+  if (!vec) {
+    splitk_reduce_kernel<<<reduce_blocks(na + nb), 256, 0, s>>>(pa, na, oa, pb, nb, ob, splits, accumulate);
+  } else {
+    const int64_t groups = (na + nb) / 4;
+    int L = 1;
+    while (L < 32 && 2 * L <= splits && groups * L < 75000) L <<= 1;   // enough threads to hide the load latency
+    const int64_t threads = align_up(groups, 32 / L) * L;
+    const int blocks = (int)std::min<int64_t>(ceil_div(threads, 256), (int64_t)num_sms() * 16);
+    splitk_reduce_vec_kernel<<<blocks, 256, 0, s>>>(pa, na, oa, pb, nb, ob, splits, accumulate, L);
+  }
+  TTAM_LAUNCH_CHECK();
+  return TTAM_OK;
 }
 
 // partial[s][n] = sum_{m in chunk s} dy[m][n].  One block per row chunk; a warp reads 32 consecutive columns of a row
@@ -234,9 +307,7 @@ extern "C" int ttam_linear_wgrad(const float* dy, int64_t lddy, const float* x, 
     // one launch sums the weight-gradient partials and (the bias gradient came out of the same pass over dy) the
     // column-sum partials
     const int64_t numel = N * K, numel_b = db ? N : 0;
-    splitk_reduce_kernel<<<reduce_blocks(numel + numel_b), 256, 0, s>>>(partial_w, numel, dw, partial_b, numel_b, db, real, accumulate);
-    TTAM_LAUNCH_CHECK();
-    return TTAM_OK;
+    return launch_splitk_reduce(partial_w, numel, dw, partial_b, numel_b, db, real, accumulate, s);
   } else {
   // C[N,K] = sum_m A(row=n, k=m) * B(row=k, k=m);  A = dy (MN-contiguous), B = x rows (MN-contiguous, gathered on m)
   GemmP p{};
@@ -248,8 +319,7 @@ extern "C" int ttam_linear_wgrad(const float* dy, int64_t lddy, const float* x, 
   TTAM_LAUNCH_CHECK();
   {
     int64_t numel = N * K;
-    splitk_reduce_kernel<<<reduce_blocks(numel), 256, 0, s>>>(partial_w, numel, dw, nullptr, 0, nullptr, real_splits, accumulate);
-    TTAM_LAUNCH_CHECK();
+    TTAM_TRY_RC(launch_splitk_reduce(partial_w, numel, dw, nullptr, 0, nullptr, real_splits, accumulate, s));
   }
   }
   if (db) {
