@@ -241,9 +241,12 @@ def time_kernel_classes(eng, F, c, dev, users, pos, neg, user_x, item_x, nu_l, n
     if bag is not None:
         nnz = int(bag.rowptr[-1]) / bag.shape[0]
         row_bytes = 8 + 16 + nnz * 8 + bag.T * 4
+        # SURVEY 8(d) "feature gather, bag form": per row nnz*(4+4) + tail*4 bytes of CSR + nnz*H*4 bytes of W1^T rows (those
+        # are served from shared memory / L2, not HBM: the figure is the survey's algorithmic one) + the output row
+        w_rows = (nnz + bag.T) * H * 4
         add("bag_fwd: layer 1 of the item tower from CSR rows (b1 + sum_j x_j W1[:, j], relu)",
             lambda: F.bag_linear_fwd(bag, idx, W1, b1, act="relu", out=hd, round_tf32_out=tc),
-            R * (row_bytes + H * 4) + H * Fd * 4, 2.0 * R * (nnz + bag.T) * H)
+            R * (row_bytes + w_rows + H * 4), 2.0 * R * (nnz + bag.T) * H)
     else:
         W1p = F.round_tf32_(F.pad_cols(W1, always_copy=True)) if tc else W1
         add("gemm layer 1 fwd: X[idx] . W1^T + b1, relu",
@@ -279,7 +282,7 @@ def time_kernel_classes(eng, F, c, dev, users, pos, neg, user_x, item_x, nu_l, n
     add("gemm layer 2 wgrad", lambda: F.linear_wgrad(dz[:, D:], hd, precision=precision, x_rounded=tc and bag is not None), R * (D + H) * 4, 2.0 * R * H * D)
     if bag is not None:
         add("bag_wgrad: layer 1 weight gradient (deterministic column-owner scatter)", lambda: F.bag_linear_wgrad(bag, idx, dhd),
-            R * (row_bytes + H * 4) + H * Fd * 4, 2.0 * R * (nnz + bag.T) * H)
+            R * (row_bytes + w_rows + H * 4), 2.0 * R * (nnz + bag.T) * H)
     else:
         add("gemm layer 1 wgrad: dh^T . X[idx]", lambda: F.linear_wgrad(dhd, Xi, gather=idx, precision=precision, x_rounded=tc),
             R * (Fd * 4 + 8 + H * 4) + H * Fd * 4, 2.0 * R * Fd * H)

@@ -45,6 +45,8 @@ class HookOptions:
     eval_mode: str = "exact"      # "exact": full-corpus top-K for every evaluation
                                   # "reference": exact where the reference would use FAISS, its candidate-sampling
                                   #              branch (training.py:974-1009, same rng draws) where it would sample
+    loss: str = "sampled"         # "sampled": the reference's BCE over sampled negatives; "inbatch": the in-batch softmax
+                                  # extension (no negatives are drawn; NOT a reference loss)
     reference_sampler: object = None   # the reference's own sample_negative_items, captured at install time
     stats: Optional[dict] = None  # filled by the hooks: steps, samples, seconds inside _train_one_epoch
 
@@ -91,6 +93,7 @@ def engine_for(model, optimizers=(), **overrides) -> FusedEngine:
     if eng is None:
         hp = _hyper_from_optimizers(optimizers)
         hp.setdefault("precision", OPTIONS.precision)
+        hp.setdefault("loss", OPTIONS.loss)
         hp.update(overrides)
         eng = FusedEngine(model, **hp)
         object.__setattr__(model, _ENGINE_ATTR, eng)
@@ -405,7 +408,7 @@ _HOOKED = ("_train_one_epoch", "_compute_loss", "_encode_item_embeddings", "_pre
 
 
 def install(training_module, *, precision: str = "tf32", graph: bool = True, sampler: str = "device",
-            eval_mode: str = "exact", stats: Optional[dict] = None) -> HookOptions:
+            eval_mode: str = "exact", stats: Optional[dict] = None, loss: str = "sampled") -> HookOptions:
     """Assign the fused implementations onto the reference's `src.pipelines.training` module and swap its
     model classes for the B200 ones; the reference file itself is untouched."""
     from . import models
@@ -415,7 +418,10 @@ def install(training_module, *, precision: str = "tf32", graph: bool = True, sam
         raise ValueError("sampler must be 'device' or 'reference'")
     if eval_mode not in ("exact", "reference"):
         raise ValueError("eval_mode must be 'exact' or 'reference'")
+    if loss not in ("sampled", "inbatch"):
+        raise ValueError("loss must be 'sampled' or 'inbatch'")
     OPTIONS.precision, OPTIONS.graph, OPTIONS.sampler, OPTIONS.eval_mode, OPTIONS.stats = precision, bool(graph), sampler, eval_mode, stats
+    OPTIONS.loss = loss
     OPTIONS.reference_sampler = getattr(training_module, "sample_negative_items", None)
     for name in _HOOKED:
         setattr(training_module, name, globals()[name])
