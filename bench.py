@@ -200,10 +200,12 @@ def time_kernel_classes(eng, F, c, dev, users, pos, neg, user_x, item_x, nu_l, n
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    def alone(fn, reps=5):
+    def alone(fn, reps=5, prep=None):
         fn()
         tot = 0.0
         for _ in range(reps):
+            if prep is not None:
+                prep()
             flush.zero_()
             torch.cuda._sleep(400_000)      # the host enqueues fn() while the GPU spins: k0 -> k1 is device time only
             k0.record(); fn(); k1.record()
@@ -216,9 +218,9 @@ def time_kernel_classes(eng, F, c, dev, users, pos, neg, user_x, item_x, nu_l, n
     R = idx.numel()
     out = []
 
-    def add(name, fn, nbytes, flops=0.0):
+    def add(name, fn, nbytes, flops=0.0, prep=None):
         try:
-            ms = alone(fn)
+            ms = alone(fn, prep=prep)
         except Exception as e:  # noqa: BLE001
             out.append({"kernel": name, "error": str(e)[:200], "ms": 0.0, "achieved": 0.0, "frac": 0.0, "bytes": int(nbytes), "flops": flops})
             return
@@ -297,7 +299,16 @@ def time_kernel_classes(eng, F, c, dev, users, pos, neg, user_x, item_x, nu_l, n
         add("sparse_adam_rows: segment-reduce + SparseAdam on E_item", lambda: eng._update_table(e_tab, srt, dz[:, :D]),
             R * (D * 4 + 12) + uniq * 6 * D * 4)
     if a_tab is not None:
-        add("lazy_catchup: zero-gradient replay of the touched A_item rows", lambda: eng._catchup(a_tab, srt[0]), uniq * (6 * D * 4 + 8) + R * 8)
+        # every repetition replays the same gap (a caught-up row is skipped: without the reset only the first call does any work)
+        stamps = a_tab.last_step.clone()
+        gap = max(1, min(49, int(eng.t) - 1))    # an item row of this workload is touched every ~49 steps
+        def behind():
+            a_tab.last_step.copy_(stamps)
+            a_tab.last_step[idx] = max(0, int(eng.t) - 1 - gap)
+        add(f"lazy_catchup: zero-gradient replay ({gap} steps) of the touched A_item rows", lambda: eng._catchup(a_tab, srt[0]),
+            uniq * (6 * D * 4 + 8) + R * 8, prep=behind)
+        a_tab.last_step.copy_(stamps)
+        eng._catchup(a_tab, srt[0])
         add("lazy_rows: segment-reduce + lazy-exact AdamW on A_item", lambda: eng._update_table(a_tab, srt, dt), R * (D * 4 + 12) + uniq * (6 * D * 4 + 8))
     return out
 

@@ -396,6 +396,50 @@ def test_long_segments_block_sum_matches_oracle(F, D):
     assert np.array_equal(outs[0][3], last3.cpu().numpy())
 
 
+@pytest.mark.parametrize("D,with_list", [(96, False), (96, True), (256, True), (20, False)])
+def test_row_windows_segment_shapes(F, D, with_list):
+    """The window kernels (one warp per 32 sorted positions, csrc/optim.cu): segments of every length 1..70 laid end to end,
+    so that heads fall on every lane, segments cross window ends, run on behind the 16 positions a window carries
+    (only without a long-segment list) and the list ends inside a window.  m and v are bit-identical to the
+    sequential-order oracle where the window role sums (length <= 16, or no list); p within 1e-6."""
+    rng = np.random.default_rng(D + int(with_list))
+    lens = list(range(1, 71)) + [1] * 37 + [16, 17, 15, 33, 32, 31, 48, 49, 47, 1, 2, 3, 5]
+    rows = rng.permutation(len(lens) * 3)[: len(lens)]
+    idx = np.concatenate([np.full(n, r, dtype=np.int64) for r, n in zip(rows, lens)])
+    rng.shuffle(idx)
+    R, N = idx.size, len(lens) * 3
+    assert R % 32 != 0
+    val = (rng.standard_normal((R, D)) * 0.01).astype(np.float32)
+    p0 = (rng.standard_normal((N, D)) * 0.02).astype(np.float32)
+    p = dev(p0.copy()); m, v = torch.zeros_like(p), torch.zeros_like(p)
+    sidx, perm = F.sort_rows(dev(idx), N)
+    ll = F.find_long_segments(sidx) if with_list else None
+    F.sparse_adam_rows(p, m, v, sidx, perm, dev(val), lr=1e-3, step=1, long_list=ll)
+    po, st = p0.copy(), {"step": 0}
+    o_sparse_adam(po, st, idx, val, lr=1e-3)
+    counts = np.bincount(idx, minlength=N)
+    exact = (counts <= 16) if with_list else np.ones(N, bool)
+    assert np.array_equal(m.cpu().numpy()[exact], st["exp_avg"][exact])
+    assert np.array_equal(v.cpu().numpy()[exact], st["exp_avg_sq"][exact])
+    np.testing.assert_allclose(m.cpu().numpy(), st["exp_avg"], rtol=2e-5, atol=2e-7)
+    untouched = counts == 0
+    assert np.array_equal(p.cpu().numpy()[untouched], p0[untouched])
+    gsum = np.zeros_like(p0); np.add.at(gsum, idx, val)
+    ok = np.abs(gsum) > 1e-4
+    np.testing.assert_allclose(p.cpu().numpy()[ok], po[ok], rtol=1e-5, atol=2e-6)
+    # the lazily-updated table through the same windows: stamps, and equality with the one-segment-at-a-time result
+    p2 = dev(p0.copy()); m2, v2 = torch.zeros_like(p2), torch.zeros_like(p2)
+    last = torch.zeros(N, dtype=torch.int32, device="cuda")
+    scal = F.adam_scalar_table(4, 1e-3, (0.9, 0.999), "cuda")
+    F.lazy_catchup("adamw", p2, m2, v2, last, sidx, scalars=scal, lr=1e-3, weight_decay=0.01, step=3)
+    assert np.array_equal(last.cpu().numpy(), np.where(counts > 0, 2, 0))
+    np.testing.assert_allclose(p2.cpu().numpy()[~untouched], (p0 * np.float32(1 - 1e-5) * np.float32(1 - 1e-5))[~untouched], rtol=2e-7)
+    F.lazy_rows("adamw", p2, m2, v2, last, sidx, perm, dev(val), scalars=scal, lr=1e-3, weight_decay=0.01, step=3, long_list=ll)
+    assert np.array_equal(last.cpu().numpy(), np.where(counts > 0, 3, 0))
+    assert np.array_equal(p2.cpu().numpy()[untouched], p0[untouched])
+    np.testing.assert_allclose(m2.cpu().numpy(), 0.1 * gsum, rtol=3e-5, atol=3e-8)
+
+
 @pytest.mark.parametrize("kind", ["adamw", "adam", "sgd"])
 def test_lazy_rows_equal_dense_optimizer(F, kind):
     """Lazy-exact replay: touching a few rows per step + a final flush == the dense optimiser stepping every row

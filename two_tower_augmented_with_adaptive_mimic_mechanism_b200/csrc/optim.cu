@@ -45,53 +45,6 @@ struct GradSrc {
   }
 };
 
-// Sum the gradient rows of one segment [i, end) for a 128-float (VEC) / 32-float (scalar) column group.
-template <bool VEC>
-__device__ __forceinline__ void segment_sum(const GradSrc& gs, const int64_t* __restrict__ sorted,
-                                            const int32_t* __restrict__ perm, int64_t i, int64_t R, int64_t row,
-                                            int col, bool active, float (&acc)[4]) {
-  acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
-  int64_t j = i;
-  while (j < R) {
-    // up to 4 rows in flight
-    int32_t pos[4];
-    int cnt = 0;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (j + u < R && sorted[j + u] == row) {
-        pos[u] = perm[j + u];
-        cnt = u + 1;
-      } else {
-        break;
-      }
-    }
-    if (cnt == 0) break;
-    float v[4][4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (u < cnt && active) {
-        const float* src = gs.row(pos[u]) + col;
-        if (VEC) {
-          float4 f = ld_f4(src);
-          v[u][0] = f.x; v[u][1] = f.y; v[u][2] = f.z; v[u][3] = f.w;
-        } else {
-          v[u][0] = src[0]; v[u][1] = v[u][2] = v[u][3] = 0.f;
-        }
-      } else {
-        v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.f;
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (u < cnt) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) acc[e] = __fadd_rn(acc[e], v[u][e]);
-      }
-    j += cnt;
-    if (cnt < 4) break;
-  }
-}
-
 struct AdamScalars {
   float lr, wd, b1, b2, eps, momentum;
   float one_minus_b1, one_minus_b2;
@@ -135,15 +88,29 @@ __device__ __forceinline__ void dense_elem(float g, float& p, float& m, float& v
   p = fmaf(-step_size, __fdiv_rn(m, denom), p);                        // addcdiv_
 }
 
-// ---- long segments ------------------------------------------------------------------------------------------------
-// A popular row (Zipf-distributed positives) can own hundreds of gradient rows of a batch; summing them with one warp
-// would serialise the whole step behind that warp.  Segments longer than kLongSeg are listed by
-// find_long_segments_kernel and processed by one whole block each: every warp sums a strided share of the rows with
-// eight loads in flight, the sixteen partial sums are combined in warp order (a fixed order: results are deterministic),
-// and warp 0 applies the optimiser.  The row kernels skip those segments when they are given the list.
+// ---- row-wise update kernels ---------------------------------------------------------------------------------------
+// HBM-bound: per unique row one read + one write of p, m, v (2304 B at D = 96) plus the row's gradient rows.
+//
+// Window role.  One warp owns a WINDOW of 32 consecutive positions of the sorted index list.  Its index work is
+// lane-parallel and happens once: lane l loads sorted[base + l] and perm[base + l] (lanes 0..15 also the 16 positions
+// behind the window, so that a segment that starts inside the window can be followed across its end), segment heads
+// come out of one shuffle + ballot.  The dependent chain  sorted -> perm -> gradient row  of the one-warp-per-position
+// kernels this replaces (three latencies for every 384-byte row) is paid once per window, and the rows of kHB segment
+// heads are fetched together: 4 heads x (p, m, v, first gradient row) = 16 independent 16-byte loads per lane in
+// flight before the first one is used.  Further members of a segment are added in sorted order (deterministic).
+//
+// Long role.  A popular row (Zipf-distributed positives) can own hundreds of gradient rows of a batch; segments longer
+// than kLongSeg are listed by find_long_segments_kernel and summed by a whole block each - every warp takes a strided
+// share with kLongUnroll loads in flight, its perm entries fetched 32 at a time by the lanes, the partial sums combined
+// in warp order (a fixed order: deterministic).  The first `long_blocks` blocks of the SAME launch take that role, so
+// the long segments run next to the windows instead of behind them.
 constexpr int kLongSeg = 16;
-constexpr int kLongWarps = 16;   // 512 threads per long segment
-constexpr int kLongUnroll = 8;   // gradient rows in flight per warp
+constexpr int kRowThreads = 256;
+constexpr int kRowWarps = kRowThreads / 32;
+constexpr int kCatchHB = 4;      // rows in flight per warp (catch-up)
+constexpr int kCatchStride = 8;  // sorted positions per warp (catch-up: arithmetic-bound, many short warps balance better)
+constexpr int kLongUnroll = 8;   // gradient rows in flight per warp (long role)
+constexpr unsigned kFull = 0xffffffffu;
 
 __global__ void __launch_bounds__(256) find_long_segments_kernel(const int64_t* __restrict__ sorted, int64_t R,
                                                                   int32_t* __restrict__ list) {
@@ -154,10 +121,6 @@ __global__ void __launch_bounds__(256) find_long_segments_kernel(const int64_t* 
   if (sorted[i + kLongSeg] == row) list[1 + atomicAdd(list, 1)] = (int32_t)i;
 }
 
-__device__ __forceinline__ bool is_long_segment(const int64_t* __restrict__ sorted, int64_t i, int64_t R, int64_t row) {
-  return i + kLongSeg < R && sorted[i + kLongSeg] == row;
-}
-
 // first position after the segment that starts at i (32-ary search by one warp; every lane returns the result)
 __device__ __forceinline__ int64_t segment_end(const int64_t* __restrict__ sorted, int64_t i, int64_t R, int64_t row, int lane) {
   int64_t lo = i, hi = R;  // sorted[lo] == row, (hi == R or sorted[hi] != row)
@@ -166,7 +129,7 @@ __device__ __forceinline__ int64_t segment_end(const int64_t* __restrict__ sorte
     const int64_t stepw = (span + 31) / 32;
     const int64_t probe = lo + (int64_t)(lane + 1) * stepw;
     const bool same = probe < hi && sorted[probe] == row;
-    const unsigned bal = __ballot_sync(0xffffffffu, same);
+    const unsigned bal = __ballot_sync(kFull, same);
     const int k = __popc(bal);  // probes 1..k hit the row (the predicate is monotone)
     const int64_t new_lo = lo + (int64_t)k * stepw;
     const int64_t new_hi = lo + (int64_t)(k + 1) * stepw;
@@ -176,32 +139,123 @@ __device__ __forceinline__ int64_t segment_end(const int64_t* __restrict__ sorte
   return hi;
 }
 
+template <bool VEC>
+__device__ __forceinline__ void ld_elems(const float* __restrict__ src, float (&v)[4]) {
+  if (VEC) {
+    const float4 f = ld_f4(src);
+    v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+  } else {
+    v[0] = src[0]; v[1] = v[2] = v[3] = 0.f;
+  }
+}
+template <bool VEC>
+__device__ __forceinline__ void st_elems(float* __restrict__ dst, const float (&v)[4]) {
+  if (VEC) st_f4(dst, make_float4(v[0], v[1], v[2], v[3]));
+  else dst[0] = v[0];
+}
+
+struct Window {
+  int64_t s;        // row id at position base + lane (-1 behind the end of the list)
+  int32_t pm;       // perm[base + lane]
+  unsigned bounds;  // lanes at which a new segment starts (or the list ends)
+  unsigned todo;    // segment heads this warp processes: the heads among its first `stride` lanes
+};
+
+// A warp LOADS 32 positions and OWNS the first `stride` of them (consecutive warps overlap by 32 - stride positions; the
+// index list is a few hundred kB and stays in L2).  With stride <= 16 every member of a segment of at most kLongSeg rows
+// whose head the warp owns lies inside the loaded window.
+__device__ __forceinline__ Window load_window(const int64_t* __restrict__ sorted, const int32_t* __restrict__ perm,
+                                              int64_t R, int64_t base, int stride, int lane, bool skip_long) {
+  Window w;
+  const int64_t pos = base + lane;
+  const bool valid = pos < R;
+  w.s = valid ? sorted[pos] : -1;
+  const int64_t s16 = pos + kLongSeg < R ? sorted[pos + kLongSeg] : -2;
+  int64_t prev = (lane == 0 && base > 0) ? sorted[base - 1] : -1;
+  w.pm = (valid && perm) ? perm[pos] : 0;
+  const int64_t up = __shfl_up_sync(kFull, w.s, 1);
+  if (lane > 0) prev = up;
+  const bool head = valid && w.s != prev;
+  const bool is_long = head && s16 == w.s;
+  w.bounds = __ballot_sync(kFull, head || !valid);
+  w.todo = __ballot_sync(kFull, head && lane < stride && !(skip_long && is_long));
+  return w;
+}
+
+// acc += gradient rows of the window members q0 .. q1-1, in order, four loads in flight
+template <bool VEC>
+__device__ __forceinline__ void add_members(const GradSrc& gs, const Window& w, int q0, int q1, int col, bool active,
+                                            float (&acc)[4]) {
+  for (int q = q0; q < q1; q += 4) {
+    float v[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.f;
+      if (q + u < q1) {
+        const int32_t pos = __shfl_sync(kFull, w.pm, q + u);
+        if (active) ld_elems<VEC>(gs.row(pos) + col, v[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (q + u < q1) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[e] = __fadd_rn(acc[e], v[u][e]);
+      }
+  }
+}
+
+// acc += gradient rows of the positions j, j+1, ... while they belong to `row` (a segment that runs on behind the window
+// and is not handled by the long role: only without a long-segment list)
+template <bool VEC>
+__device__ __forceinline__ void add_far(const GradSrc& gs, const int64_t* __restrict__ sorted, const int32_t* __restrict__ perm,
+                                        int64_t j, int64_t R, int64_t row, int col, bool active, float (&acc)[4]) {
+  while (j < R && sorted[j] == row) {
+    float v[4];
+    v[0] = v[1] = v[2] = v[3] = 0.f;
+    if (active) ld_elems<VEC>(gs.row(perm[j]) + col, v);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[e] = __fadd_rn(acc[e], v[e]);
+    ++j;
+  }
+}
+
+// sum of the gradient rows of segment head lane h (first member already in acc)
+template <bool VEC>
+__device__ __forceinline__ void finish_segment(const GradSrc& gs, const Window& w, const int64_t* __restrict__ sorted,
+                                               const int32_t* __restrict__ perm, int64_t base, int64_t R, int h, int64_t row,
+                                               int col, bool active, float (&acc)[4]) {
+  const unsigned above = w.bounds & ~((2u << h) - 1u);
+  const int e = above ? __ffs(above) - 1 : 32;
+  if (e > h + 1) add_members<VEC>(gs, w, h + 1, e, col, active, acc);
+  if (e == 32) add_far<VEC>(gs, sorted, perm, base + 32, R, row, col, active, acc);   // runs on behind the window (rare)
+}
+
 // Block-cooperative sum of gradient rows [i, end) for one column group; the result is valid in warp 0.
 template <bool VEC>
 __device__ __forceinline__ void segment_sum_block(const GradSrc& gs, const int32_t* __restrict__ perm, int64_t i,
                                                   int64_t end, int col, bool active, float (*part)[128], float (&acc)[4]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float a[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int64_t j0 = i + warp; j0 < end; j0 += kLongUnroll * kLongWarps) {
-    float v[kLongUnroll][4];
+  // this warp's members: j = i + warp + kRowWarps * k; lane l fetches the perm entry of member kb + l
+  for (int64_t kb = 0; i + warp + kRowWarps * kb < end; kb += 32) {
+    const int64_t jl = i + warp + kRowWarps * (kb + lane);
+    const int32_t pl = jl < end ? perm[jl] : -1;
 #pragma unroll
-    for (int u = 0; u < kLongUnroll; ++u) {
-      const int64_t j = j0 + u * kLongWarps;
-      v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.f;
-      if (j < end && active) {
-        const float* src = gs.row(perm[j]) + col;
-        if (VEC) {
-          const float4 f = ld_f4(src);
-          v[u][0] = f.x; v[u][1] = f.y; v[u][2] = f.z; v[u][3] = f.w;
-        } else {
-          v[u][0] = src[0];
-        }
+    for (int k0 = 0; k0 < 32; k0 += kLongUnroll) {
+      if (i + warp + kRowWarps * (kb + k0) >= end) break;
+      float v[kLongUnroll][4];
+#pragma unroll
+      for (int u = 0; u < kLongUnroll; ++u) {
+        const int32_t pos = __shfl_sync(kFull, pl, k0 + u);
+        v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.f;
+        if (pos >= 0 && active) ld_elems<VEC>(gs.row(pos) + col, v[u]);
       }
+#pragma unroll
+      for (int u = 0; u < kLongUnroll; ++u)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) a[e] = __fadd_rn(a[e], v[u][e]);
     }
-#pragma unroll
-    for (int u = 0; u < kLongUnroll; ++u)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) a[e] = __fadd_rn(a[e], v[u][e]);
   }
 #pragma unroll
   for (int e = 0; e < 4; ++e) part[warp][lane * 4 + e] = a[e];
@@ -210,94 +264,88 @@ __device__ __forceinline__ void segment_sum_block(const GradSrc& gs, const int32
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       float t = 0.f;
-      for (int w = 0; w < kLongWarps; ++w) t = __fadd_rn(t, part[w][lane * 4 + e]);
+#pragma unroll
+      for (int w = 0; w < kRowWarps; ++w) t = __fadd_rn(t, part[w][lane * 4 + e]);
       acc[e] = t;
     }
   }
   __syncthreads();
 }
 
-template <bool VEC>
-__device__ __forceinline__ void sparse_adam_update(float* __restrict__ P, float* __restrict__ Mo, float* __restrict__ Vo,
-                                                   int64_t off, const float (&g)[4], const AdamScalars& s) {
-  if (VEC) {
-    float4 p4 = ld_f4(P + off), m4 = ld_f4(Mo + off), v4 = ld_f4(Vo + off);
-    float pp[4] = {p4.x, p4.y, p4.z, p4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-    for (int e = 0; e < 4; ++e) sparse_adam_elem(g[e], pp[e], mm[e], vv[e], s);
-    st_f4(P + off, make_float4(pp[0], pp[1], pp[2], pp[3]));
-    st_f4(Mo + off, make_float4(mm[0], mm[1], mm[2], mm[3]));
-    st_f4(Vo + off, make_float4(vv[0], vv[1], vv[2], vv[3]));
-  } else {
-    float pp = P[off], mm = Mo[off], vv = Vo[off];
-    sparse_adam_elem(g[0], pp, mm, vv, s);
-    P[off] = pp; Mo[off] = mm; Vo[off] = vv;
-  }
-}
-
-template <bool VEC>
-__global__ void __launch_bounds__(256, 6) sparse_adam_rows_kernel(float* __restrict__ P, float* __restrict__ Mo,
-                                                               float* __restrict__ Vo, int D,
-                                                               const int64_t* __restrict__ sorted,
-                                                               const int32_t* __restrict__ perm, int64_t R, GradSrc gs,
-                                                               AdamScalars s, const float* __restrict__ scalars,
-                                                               const ttam_step_state* __restrict__ st, bool skip_long) {
-  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (i >= R) return;
-  const int64_t row = sorted[i];
-  if (i > 0 && sorted[i - 1] == row) return;  // not a segment head
-  if (skip_long && is_long_segment(sorted, i, R, row)) return;
-  if (st) s.step_size = scalars[4 * st->step + 2];
-  constexpr int W = VEC ? 128 : 32;
-  for (int c0 = 0; c0 < D; c0 += W) {
-    const int col = c0 + (VEC ? lane * 4 : lane);
-    const bool active = col < D;
-    // the row's p, m, v do not depend on the gradient rows: fetch them first so that both latency chains overlap
-    const int64_t off = row * (int64_t)D + col;
-    float4 p4 = make_float4(0, 0, 0, 0), m4 = p4, v4 = p4;
-    if (VEC && active) {
-      p4 = ld_f4(P + off); m4 = ld_f4(Mo + off); v4 = ld_f4(Vo + off);
-    }
-    float g[4];
-    segment_sum<VEC>(gs, sorted, perm, i, R, row, col, active, g);
-    if (!active) continue;
-    if (VEC) {
-      float pp[4] = {p4.x, p4.y, p4.z, p4.w}, mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) sparse_adam_elem(g[e], pp[e], mm[e], vv[e], s);
-      st_f4(P + off, make_float4(pp[0], pp[1], pp[2], pp[3]));
-      st_f4(Mo + off, make_float4(mm[0], mm[1], mm[2], mm[3]));
-      st_f4(Vo + off, make_float4(vv[0], vv[1], vv[2], vv[3]));
-    } else {
-      sparse_adam_update<VEC>(P, Mo, Vo, off, g, s);
-    }
-  }
-}
-
-template <bool VEC>
-__global__ void __launch_bounds__(32 * kLongWarps) sparse_adam_long_kernel(float* __restrict__ P, float* __restrict__ Mo,
+template <bool VEC, int kHB>
+__global__ void __launch_bounds__(kRowThreads, kHB == 2 ? 4 : 2) sparse_adam_rows_kernel(float* __restrict__ P, float* __restrict__ Mo,
                                                                float* __restrict__ Vo, int D,
                                                                const int64_t* __restrict__ sorted,
                                                                const int32_t* __restrict__ perm, int64_t R, GradSrc gs,
                                                                AdamScalars s, const float* __restrict__ scalars,
                                                                const ttam_step_state* __restrict__ st,
-                                                               const int32_t* __restrict__ list) {
-  __shared__ float part[kLongWarps][128];
+                                                               const int32_t* __restrict__ long_list, int long_blocks,
+                                                               int stride) {
+  __shared__ float part[kRowWarps][128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (st) s.step_size = scalars[4 * st->step + 2];
-  const int n = list[0];
   constexpr int W = VEC ? 128 : 32;
-  for (int e = blockIdx.x; e < n; e += gridDim.x) {
-    const int64_t i = list[1 + e];
-    const int64_t row = sorted[i];
-    const int64_t end = segment_end(sorted, i, R, row, lane);
-    for (int c0 = 0; c0 < D; c0 += W) {
-      const int col = c0 + (VEC ? lane * 4 : lane);
-      const bool active = col < D;
-      float g[4];
-      segment_sum_block<VEC>(gs, perm, i, end, col, active, part, g);
-      if (warp == 0 && active) sparse_adam_update<VEC>(P, Mo, Vo, row * (int64_t)D + col, g, s);
+  constexpr int NE = VEC ? 4 : 1;
+  if ((int)blockIdx.x < long_blocks) {  // ---- long role
+    const int n = long_list[0];
+    for (int e = blockIdx.x; e < n; e += long_blocks) {
+      const int64_t i = long_list[1 + e];
+      const int64_t row = sorted[i];
+      const int64_t end = segment_end(sorted, i, R, row, lane);
+      for (int c0 = 0; c0 < D; c0 += W) {
+        const int col = c0 + lane * NE;
+        const bool active = col < D;
+        float g[4];
+        segment_sum_block<VEC>(gs, perm, i, end, col, active, part, g);
+        if (warp == 0 && active) {
+          const int64_t off = row * (int64_t)D + col;
+          float pp[4], mm[4], vv[4];
+          ld_elems<VEC>(P + off, pp); ld_elems<VEC>(Mo + off, mm); ld_elems<VEC>(Vo + off, vv);
+#pragma unroll
+          for (int k = 0; k < NE; ++k) sparse_adam_elem(g[k], pp[k], mm[k], vv[k], s);
+          st_elems<VEC>(P + off, pp); st_elems<VEC>(Mo + off, mm); st_elems<VEC>(Vo + off, vv);
+        }
+      }
+    }
+    return;
+  }
+  // ---- window role
+  const int64_t base = (((int64_t)blockIdx.x - long_blocks) * kRowWarps + warp) * stride;
+  if (base >= R) return;
+  const Window w = load_window(sorted, perm, R, base, stride, lane, long_list != nullptr);
+  for (int c0 = 0; c0 < D; c0 += W) {
+    const int col = c0 + lane * NE;
+    const bool active = col < D;
+    unsigned todo = w.todo;
+    while (todo) {
+      int h[kHB];
+      int64_t row[kHB];
+      float pp[kHB][4], mm[kHB][4], vv[kHB][4], g[kHB][4];
+#pragma unroll
+      for (int u = 0; u < kHB; ++u) {
+        h[u] = todo ? __ffs(todo) - 1 : -1;
+        todo &= todo - 1;
+        if (h[u] >= 0) {
+          row[u] = __shfl_sync(kFull, w.s, h[u]);
+          const int32_t pos = __shfl_sync(kFull, w.pm, h[u]);
+          if (active) {
+            const int64_t off = row[u] * (int64_t)D + col;
+            ld_elems<VEC>(P + off, pp[u]); ld_elems<VEC>(Mo + off, mm[u]); ld_elems<VEC>(Vo + off, vv[u]);
+            ld_elems<VEC>(gs.row(pos) + col, g[u]);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kHB; ++u) {
+        if (h[u] < 0) break;
+        finish_segment<VEC>(gs, w, sorted, perm, base, R, h[u], row[u], col, active, g[u]);
+        if (active) {
+          const int64_t off = row[u] * (int64_t)D + col;
+#pragma unroll
+          for (int k = 0; k < NE; ++k) sparse_adam_elem(g[u][k], pp[u][k], mm[u][k], vv[u][k], s);
+          st_elems<VEC>(P + off, pp[u]); st_elems<VEC>(Mo + off, mm[u]); st_elems<VEC>(Vo + off, vv[u]);
+        }
+      }
     }
   }
 }
@@ -319,6 +367,14 @@ __global__ void __launch_bounds__(32 * kLongWarps) sparse_adam_long_kernel(float
 // reference's step-by-step fp32 arithmetic.
 // m == 0 (a row no gradient has reached yet) makes every update term exactly zero: only the decay is applied.
 // TTAM_EXACT_REPLAY=1 selects the step-by-step loop.
+// MUFU.RCP alone: div.approx (__fdividef) wraps it in a denormal-range test and two rescaling multiplies per element; the
+// denominators here are >= eps
+__device__ __forceinline__ float rcp_ftz(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 template <int KIND, int NE>
 __device__ __forceinline__ void replay(float (&pp)[NE], float (&mm)[NE], float (&vv)[NE], int t_from, int t_to,
                                        const float* __restrict__ scalars, const AdamScalars& s) {
@@ -349,7 +405,7 @@ __device__ __forceinline__ void replay(float (&pp)[NE], float (&mm)[NE], float (
         for (int e = 0; e < NE; ++e) {
           if (decay) pp[e] = __fmul_rn(pp[e], s.decay);
           mm[e] = fmaf(s.one_minus_b1, -mm[e], mm[e]);
-          pp[e] = fmaf(-a, __fdividef(mm[e], fmaf(w0[e], h, s.eps)), pp[e]);
+          pp[e] = fmaf(-a, __fmul_rn(mm[e], rcp_ftz(fmaf(w0[e], h, s.eps))), pp[e]);
         }
       }
     }
@@ -365,162 +421,189 @@ __device__ __forceinline__ void replay(float (&pp)[NE], float (&mm)[NE], float (
   }
 }
 
-template <int KIND, bool VEC>
-__device__ __forceinline__ void lazy_update(float* __restrict__ P, float* __restrict__ Mo, float* __restrict__ Vo,
-                                            int64_t off, const float (&g)[4], int t_prev, int step,
-                                            const float* __restrict__ scalars, const AdamScalars& s) {
-  const bool has_v = KIND != TTAM_OPT_SGD;
-  const bool has_m = KIND != TTAM_OPT_SGD || s.momentum != 0.f;
-  constexpr int NE = VEC ? 4 : 1;
+// one lazily-updated row group held in registers: replay the zero-gradient steps (t_prev, step-1], then step `step`
+template <int KIND, int NE>
+__device__ __forceinline__ void lazy_apply(float (&pp)[4], float (&mm)[4], float (&vv)[4], const float (&g)[4], int t_prev,
+                                           int step, const float* __restrict__ scalars, const AdamScalars& s) {
   const float step_size = KIND == TTAM_OPT_SGD ? 0.f : scalars[4 * step];
   const float bc2s = KIND == TTAM_OPT_SGD ? 1.f : scalars[4 * step + 1];
-  float pp[NE], mm[NE], vv[NE];
-  if (VEC) {
-    float4 p4 = ld_f4(P + off);
-    float4 m4 = has_m ? ld_f4(Mo + off) : make_float4(0, 0, 0, 0);
-    float4 v4 = has_v ? ld_f4(Vo + off) : make_float4(0, 0, 0, 0);
-    pp[0] = p4.x; mm[0] = m4.x; vv[0] = v4.x;
-    if (NE == 4) {
-      pp[1 % NE] = p4.y; pp[2 % NE] = p4.z; pp[3 % NE] = p4.w;
-      mm[1 % NE] = m4.y; mm[2 % NE] = m4.z; mm[3 % NE] = m4.w;
-      vv[1 % NE] = v4.y; vv[2 % NE] = v4.z; vv[3 % NE] = v4.w;
-    }
-  } else {
-    pp[0] = P[off];
-    mm[0] = has_m ? Mo[off] : 0.f;
-    vv[0] = has_v ? Vo[off] : 0.f;
-  }
-  replay<KIND, NE>(pp, mm, vv, t_prev, step - 1, scalars, s);
+  float p1[NE], m1[NE], v1[NE];
 #pragma unroll
-  for (int e = 0; e < NE; ++e) dense_elem<KIND>(g[e], pp[e], mm[e], vv[e], s, step_size, bc2s);
-  if (VEC) {
-    st_f4(P + off, make_float4(pp[0], pp[1 % NE], pp[2 % NE], pp[3 % NE]));
-    if (has_m) st_f4(Mo + off, make_float4(mm[0], mm[1 % NE], mm[2 % NE], mm[3 % NE]));
-    if (has_v) st_f4(Vo + off, make_float4(vv[0], vv[1 % NE], vv[2 % NE], vv[3 % NE]));
-  } else {
-    P[off] = pp[0];
-    if (has_m) Mo[off] = mm[0];
-    if (has_v) Vo[off] = vv[0];
+  for (int e = 0; e < NE; ++e) { p1[e] = pp[e]; m1[e] = mm[e]; v1[e] = vv[e]; }
+  replay<KIND, NE>(p1, m1, v1, t_prev, step - 1, scalars, s);
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+    dense_elem<KIND>(g[e], p1[e], m1[e], v1[e], s, step_size, bc2s);
+    pp[e] = p1[e]; mm[e] = m1[e]; vv[e] = v1[e];
   }
 }
 
-template <int KIND, bool VEC>
-__global__ void __launch_bounds__(256, 6) lazy_rows_kernel(float* __restrict__ P, float* __restrict__ Mo,
-                                                        float* __restrict__ Vo, int32_t* __restrict__ last_step, int D,
-                                                        const int64_t* __restrict__ sorted,
-                                                        const int32_t* __restrict__ perm, int64_t R, GradSrc gs,
-                                                        const float* __restrict__ scalars, AdamScalars s, int step,
-                                                        const ttam_step_state* __restrict__ st, bool skip_long) {
-  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (i >= R) return;
-  const int64_t row = sorted[i];
-  if (i > 0 && sorted[i - 1] == row) return;
-  if (skip_long && is_long_segment(sorted, i, R, row)) return;
-  if (st) step = st->step;
-  const int t_prev = last_step[row];
-  constexpr int W = VEC ? 128 : 32;
-  for (int c0 = 0; c0 < D; c0 += W) {
-    const int col = c0 + (VEC ? lane * 4 : lane);
-    const bool active = col < D;
-    if (active) {  // start fetching the row's p, m, v while the gradient rows are summed (independent latency chains)
-      const int64_t off = row * (int64_t)D + col;
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(P + off));
-      if (Mo) asm volatile("prefetch.global.L2 [%0];" ::"l"(Mo + off));
-      if (Vo) asm volatile("prefetch.global.L2 [%0];" ::"l"(Vo + off));
-    }
-    float g[4];
-    segment_sum<VEC>(gs, sorted, perm, i, R, row, col, active, g);
-    if (!active) continue;
-    lazy_update<KIND, VEC>(P, Mo, Vo, row * (int64_t)D + col, g, t_prev, step, scalars, s);
-  }
-  __syncwarp();
-  if (lane == 0) last_step[row] = step;
+template <bool VEC>
+__device__ __forceinline__ void ld_state(const float* __restrict__ P, const float* __restrict__ Mo, const float* __restrict__ Vo,
+                                         int64_t off, bool has_m, bool has_v, float (&pp)[4], float (&mm)[4], float (&vv)[4]) {
+  ld_elems<VEC>(P + off, pp);
+  if (has_m) ld_elems<VEC>(Mo + off, mm); else mm[0] = mm[1] = mm[2] = mm[3] = 0.f;
+  if (has_v) ld_elems<VEC>(Vo + off, vv); else vv[0] = vv[1] = vv[2] = vv[3] = 0.f;
+}
+template <bool VEC>
+__device__ __forceinline__ void st_state(float* __restrict__ P, float* __restrict__ Mo, float* __restrict__ Vo, int64_t off,
+                                         bool has_m, bool has_v, const float (&pp)[4], const float (&mm)[4], const float (&vv)[4]) {
+  st_elems<VEC>(P + off, pp);
+  if (has_m) st_elems<VEC>(Mo + off, mm);
+  if (has_v) st_elems<VEC>(Vo + off, vv);
 }
 
-template <int KIND, bool VEC>
-__global__ void __launch_bounds__(32 * kLongWarps) lazy_long_kernel(float* __restrict__ P, float* __restrict__ Mo,
+template <int KIND, bool VEC, int kHB>
+__global__ void __launch_bounds__(kRowThreads, kHB == 2 ? 3 : 2) lazy_rows_kernel(float* __restrict__ P, float* __restrict__ Mo,
                                                         float* __restrict__ Vo, int32_t* __restrict__ last_step, int D,
                                                         const int64_t* __restrict__ sorted,
                                                         const int32_t* __restrict__ perm, int64_t R, GradSrc gs,
                                                         const float* __restrict__ scalars, AdamScalars s, int step,
                                                         const ttam_step_state* __restrict__ st,
-                                                        const int32_t* __restrict__ list) {
-  __shared__ float part[kLongWarps][128];
+                                                        const int32_t* __restrict__ long_list, int long_blocks,
+                                                        int stride) {
+  __shared__ float part[kRowWarps][128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (st) step = st->step;
-  const int n = list[0];
-  constexpr int W = VEC ? 128 : 32;
-  for (int e = blockIdx.x; e < n; e += gridDim.x) {
-    const int64_t i = list[1 + e];
-    const int64_t row = sorted[i];
-    const int64_t end = segment_end(sorted, i, R, row, lane);
-    const int t_prev = last_step[row];
-    for (int c0 = 0; c0 < D; c0 += W) {
-      const int col = c0 + (VEC ? lane * 4 : lane);
-      const bool active = col < D;
-      float g[4];
-      segment_sum_block<VEC>(gs, perm, i, end, col, active, part, g);
-      if (warp == 0 && active) lazy_update<KIND, VEC>(P, Mo, Vo, row * (int64_t)D + col, g, t_prev, step, scalars, s);
-    }
-    __syncthreads();  // every warp has read last_step[row] before it changes
-    if (threadIdx.x == 0) last_step[row] = step;
-  }
-}
-
-// Bring the unique rows of `sorted` up to step-1 (zero-gradient replay) so that the forward pass of step `step`
-// reads current values; the row-wise update at the end of the step then finds nothing left to replay.
-template <int KIND, bool VEC>
-__global__ void __launch_bounds__(256, 6) lazy_catchup_kernel(float* __restrict__ P, float* __restrict__ Mo,
-                                                           float* __restrict__ Vo, int32_t* __restrict__ last_step, int D,
-                                                           const int64_t* __restrict__ sorted, int64_t R,
-                                                           const float* __restrict__ scalars, AdamScalars s, int step,
-                                                           const ttam_step_state* __restrict__ st) {
-  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (i >= R) return;
-  const int64_t row = sorted[i];
-  if (i > 0 && sorted[i - 1] == row) return;
-  if (st) step = st->step;
-  const int t_prev = last_step[row];
-  if (t_prev >= step - 1) return;
   const bool has_v = KIND != TTAM_OPT_SGD;
   const bool has_m = KIND != TTAM_OPT_SGD || s.momentum != 0.f;
   constexpr int W = VEC ? 128 : 32;
   constexpr int NE = VEC ? 4 : 1;
-  for (int c0 = 0; c0 < D; c0 += W) {
-    const int col = c0 + (VEC ? lane * 4 : lane);
-    if (col >= D) continue;
-    const int64_t off = row * (int64_t)D + col;
-    float pp[NE], mm[NE], vv[NE];
-    if (VEC) {
-      float4 p4 = ld_f4(P + off);
-      float4 m4 = has_m ? ld_f4(Mo + off) : make_float4(0, 0, 0, 0);
-      float4 v4 = has_v ? ld_f4(Vo + off) : make_float4(0, 0, 0, 0);
-      pp[0] = p4.x; mm[0] = m4.x; vv[0] = v4.x;
-      if (NE == 4) {
-        pp[1 % NE] = p4.y; pp[2 % NE] = p4.z; pp[3 % NE] = p4.w;
-        mm[1 % NE] = m4.y; mm[2 % NE] = m4.z; mm[3 % NE] = m4.w;
-        vv[1 % NE] = v4.y; vv[2 % NE] = v4.z; vv[3 % NE] = v4.w;
+  if ((int)blockIdx.x < long_blocks) {  // ---- long role
+    const int n = long_list[0];
+    for (int e = blockIdx.x; e < n; e += long_blocks) {
+      const int64_t i = long_list[1 + e];
+      const int64_t row = sorted[i];
+      const int t_prev = last_step[row];
+      const int64_t end = segment_end(sorted, i, R, row, lane);
+      for (int c0 = 0; c0 < D; c0 += W) {
+        const int col = c0 + lane * NE;
+        const bool active = col < D;
+        float g[4];
+        segment_sum_block<VEC>(gs, perm, i, end, col, active, part, g);
+        if (warp == 0 && active) {
+          const int64_t off = row * (int64_t)D + col;
+          float pp[4], mm[4], vv[4];
+          ld_state<VEC>(P, Mo, Vo, off, has_m, has_v, pp, mm, vv);
+          lazy_apply<KIND, NE>(pp, mm, vv, g, t_prev, step, scalars, s);
+          st_state<VEC>(P, Mo, Vo, off, has_m, has_v, pp, mm, vv);
+        }
       }
-    } else {
-      pp[0] = P[off];
-      mm[0] = has_m ? Mo[off] : 0.f;
-      vv[0] = has_v ? Vo[off] : 0.f;
+      __syncthreads();  // every warp has read last_step[row] before it changes
+      if (threadIdx.x == 0) last_step[row] = step;
     }
-    replay<KIND, NE>(pp, mm, vv, t_prev, step - 1, scalars, s);
-    if (VEC) {
-      st_f4(P + off, make_float4(pp[0], pp[1 % NE], pp[2 % NE], pp[3 % NE]));
-      if (has_m) st_f4(Mo + off, make_float4(mm[0], mm[1 % NE], mm[2 % NE], mm[3 % NE]));
-      if (has_v) st_f4(Vo + off, make_float4(vv[0], vv[1 % NE], vv[2 % NE], vv[3 % NE]));
-    } else {
-      P[off] = pp[0];
-      if (has_m) Mo[off] = mm[0];
-      if (has_v) Vo[off] = vv[0];
+    return;
+  }
+  // ---- window role
+  const int64_t base = (((int64_t)blockIdx.x - long_blocks) * kRowWarps + warp) * stride;
+  if (base >= R) return;
+  const Window w = load_window(sorted, perm, R, base, stride, lane, long_list != nullptr);
+  const bool mine = (w.todo >> lane) & 1u;
+  const int tp_lane = mine ? last_step[w.s] : 0;
+  for (int c0 = 0; c0 < D; c0 += W) {
+    const int col = c0 + lane * NE;
+    const bool active = col < D;
+    unsigned todo = w.todo;
+    while (todo) {
+      int h[kHB];
+      int64_t row[kHB];
+      float pp[kHB][4], mm[kHB][4], vv[kHB][4], g[kHB][4];
+#pragma unroll
+      for (int u = 0; u < kHB; ++u) {
+        h[u] = todo ? __ffs(todo) - 1 : -1;
+        todo &= todo - 1;
+        if (h[u] >= 0) {
+          row[u] = __shfl_sync(kFull, w.s, h[u]);
+          const int32_t pos = __shfl_sync(kFull, w.pm, h[u]);
+          if (active) {
+            ld_state<VEC>(P, Mo, Vo, row[u] * (int64_t)D + col, has_m, has_v, pp[u], mm[u], vv[u]);
+            ld_elems<VEC>(gs.row(pos) + col, g[u]);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kHB; ++u) {
+        if (h[u] < 0) break;
+        finish_segment<VEC>(gs, w, sorted, perm, base, R, h[u], row[u], col, active, g[u]);
+        const int t_prev = __shfl_sync(kFull, tp_lane, h[u]);
+        if (active) {
+          lazy_apply<KIND, NE>(pp[u], mm[u], vv[u], g[u], t_prev, step, scalars, s);
+          st_state<VEC>(P, Mo, Vo, row[u] * (int64_t)D + col, has_m, has_v, pp[u], mm[u], vv[u]);
+        }
+      }
     }
   }
-  __syncwarp();
-  if (lane == 0) last_step[row] = step - 1;
+  if (mine) last_step[w.s] = step;
+}
+
+// Bring the unique rows of `sorted` up to step-1 (zero-gradient replay) so that the forward pass of step `step`
+// reads current values; the row-wise update at the end of the step then finds nothing left to replay.
+// The replay loop is arithmetic (a row that is touched every ~50 steps replays ~50 steps x D elements), so the row is
+// spread over all 32 lanes: lane l holds the NE = D/32 elements l, l + 32, ... (coalesced 128-byte accesses) instead of
+// four consecutive ones in 24 of the 32 lanes.
+template <int KIND, int NE>
+__global__ void __launch_bounds__(kRowThreads) lazy_catchup_kernel(float* __restrict__ P, float* __restrict__ Mo,
+                                                           float* __restrict__ Vo, int32_t* __restrict__ last_step, int D,
+                                                           const int64_t* __restrict__ sorted, int64_t R,
+                                                           const float* __restrict__ scalars, AdamScalars s, int step,
+                                                           const ttam_step_state* __restrict__ st) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t base = ((int64_t)blockIdx.x * kRowWarps + warp) * kCatchStride;
+  if (base >= R) return;
+  if (st) step = st->step;
+  const bool has_v = KIND != TTAM_OPT_SGD;
+  const bool has_m = KIND != TTAM_OPT_SGD || s.momentum != 0.f;
+  constexpr int W = 32 * NE;
+  // heads of the window (lane-parallel), then the ones that are behind
+  const int64_t pos = base + lane;
+  const bool valid = pos < R && lane < kCatchStride;
+  const int64_t srow = valid ? sorted[pos] : -1;
+  int64_t prev = (lane == 0 && base > 0) ? sorted[base - 1] : -1;
+  const int64_t up = __shfl_up_sync(kFull, srow, 1);
+  if (lane > 0) prev = up;
+  const bool head = valid && srow != prev;
+  const int tp_lane = head ? last_step[srow] : 0;
+  const bool mine = head && tp_lane < step - 1;
+  const unsigned all = __ballot_sync(kFull, mine);
+  for (int c0 = 0; c0 < D; c0 += W) {
+    const int col = c0 + lane;
+    unsigned todo = all;
+    while (todo) {
+      int h[kCatchHB];
+      int64_t off[kCatchHB];
+      float pp[kCatchHB][NE], mm[kCatchHB][NE], vv[kCatchHB][NE];
+#pragma unroll
+      for (int u = 0; u < kCatchHB; ++u) {
+        h[u] = todo ? __ffs(todo) - 1 : -1;
+        todo &= todo - 1;
+        if (h[u] >= 0) {
+          off[u] = __shfl_sync(kFull, srow, h[u]) * (int64_t)D + col;
+#pragma unroll
+          for (int e = 0; e < NE; ++e) {
+            const bool ok = col + 32 * e < D;
+            pp[u][e] = ok ? P[off[u] + 32 * e] : 0.f;
+            mm[u][e] = (ok && has_m) ? Mo[off[u] + 32 * e] : 0.f;
+            vv[u][e] = (ok && has_v) ? Vo[off[u] + 32 * e] : 0.f;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kCatchHB; ++u) {
+        if (h[u] < 0) break;
+        const int t_prev = __shfl_sync(kFull, tp_lane, h[u]);
+        replay<KIND, NE>(pp[u], mm[u], vv[u], t_prev, step - 1, scalars, s);
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+          if (col + 32 * e < D) {
+            P[off[u] + 32 * e] = pp[u][e];
+            if (has_m) Mo[off[u] + 32 * e] = mm[u][e];
+            if (has_v) Vo[off[u] + 32 * e] = vv[u][e];
+          }
+        }
+      }
+    }
+  }
+  if (mine) last_step[srow] = step - 1;
 }
 
 template <int KIND, bool VEC>
@@ -667,6 +750,18 @@ extern "C" int ttam_find_long_segments(const int64_t* sorted_idx, int64_t R, int
   return TTAM_OK;
 }
 
+// positions a warp owns (TTAM_ROWS_STRIDE: 8 | 16 | 32 for experiments; with a long-segment list 16 keeps every member of a
+// segment inside the window a warp loads)
+static int row_stride(bool with_list) {
+  static const int env = [] { const char* e = getenv("TTAM_ROWS_STRIDE"); const int v = e ? atoi(e) : 0; return (v == 8 || v == 16 || v == 32) ? v : 0; }();
+  return env ? env : (with_list ? 16 : 32);
+}
+
+static int rows_hb() {   // segment heads in flight per warp (TTAM_ROWS_HB = 2 | 4; 2 leaves room for twice the warps)
+  static const int v = [] { const char* e = getenv("TTAM_ROWS_HB"); return (e && atoi(e) == 4) ? 4 : 2; }();
+  return v;
+}
+
 static bool vec_ok(int64_t D, const void* p, const void* m, const void* v, const float* ga, int64_t lda,
                    const float* gb, int64_t ldb) {
   auto al = [](const void* q) { return q == nullptr || ((uintptr_t)q & 15) == 0; };
@@ -686,18 +781,17 @@ extern "C" int ttam_sparse_adam_rows(float* p, float* m, float* v, int64_t D, co
   const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
   s.step_size = (float)(lr * sqrt(bc2) / bc1);
   GradSrc gs{grad_a, ld_a, n_a, grad_b, ld_b};
-  const int blocks = (int)ceil_div(R * 32, 256);
   const bool vec = vec_ok(D, p, m, v, grad_a, ld_a, grad_b, ld_b);
-  const bool skip = long_list != nullptr;
+  const int long_blocks = long_list ? num_sms() : 0;   // the long role of the same launch (most exit at once: few long segments)
+  const int stride = row_stride(long_list != nullptr);
+  const int blocks = long_blocks + (int)ceil_div(R, (int64_t)stride * kRowWarps);
   cudaStream_t cs = (cudaStream_t)stream;
-  if (vec) sparse_adam_rows_kernel<true><<<blocks, 256, 0, cs>>>(p, m, v, (int)D, sorted_idx, perm, R, gs, s, scalars, state_dev, skip);
-  else sparse_adam_rows_kernel<false><<<blocks, 256, 0, cs>>>(p, m, v, (int)D, sorted_idx, perm, R, gs, s, scalars, state_dev, skip);
+#define SA_ARGS p, m, v, (int)D, sorted_idx, perm, R, gs, s, scalars, state_dev, long_list, long_blocks, stride
+  if (!vec) sparse_adam_rows_kernel<false, 4><<<blocks, kRowThreads, 0, cs>>>(SA_ARGS);
+  else if (rows_hb() == 2) sparse_adam_rows_kernel<true, 2><<<blocks, kRowThreads, 0, cs>>>(SA_ARGS);
+  else sparse_adam_rows_kernel<true, 4><<<blocks, kRowThreads, 0, cs>>>(SA_ARGS);
+#undef SA_ARGS
   TTAM_LAUNCH_CHECK();
-  if (skip) {
-    if (vec) sparse_adam_long_kernel<true><<<2 * num_sms(), 32 * kLongWarps, 0, cs>>>(p, m, v, (int)D, sorted_idx, perm, R, gs, s, scalars, state_dev, long_list);
-    else sparse_adam_long_kernel<false><<<2 * num_sms(), 32 * kLongWarps, 0, cs>>>(p, m, v, (int)D, sorted_idx, perm, R, gs, s, scalars, state_dev, long_list);
-    TTAM_LAUNCH_CHECK();
-  }
   return TTAM_OK;
 }
 
@@ -722,22 +816,21 @@ extern "C" int ttam_lazy_rows(int kind, float* p, float* m, float* v, int32_t* l
   if (R == 0) return TTAM_OK;
   AdamScalars s = make_scalars(lr, weight_decay, beta1, beta2, eps, momentum);
   GradSrc gs{grad_a, ld_a, n_a, grad_b, ld_b};
-  const int blocks = (int)ceil_div(R * 32, 256);
   cudaStream_t st = (cudaStream_t)stream;
-  const bool skip = long_list != nullptr;
   const bool vec = vec_ok(D, p, m, v, grad_a, ld_a, grad_b, ld_b);
-#define CALL(K, V) lazy_rows_kernel<K, V><<<blocks, 256, 0, st>>>(p, m, v, last_step, (int)D, sorted_idx, perm, R, gs, scalars, s, (int)step, state_dev, skip)
-  if (vec) TTAM_DISPATCH_KIND(kind, true, CALL);
-  else TTAM_DISPATCH_KIND(kind, false, CALL);
+  const int long_blocks = long_list ? num_sms() : 0;
+  const int stride = row_stride(long_list != nullptr);
+  const int blocks = long_blocks + (int)ceil_div(R, (int64_t)stride * kRowWarps);
+#define LZ_ARGS p, m, v, last_step, (int)D, sorted_idx, perm, R, gs, scalars, s, (int)step, state_dev, long_list, long_blocks, stride
+#define CALL(K, V) lazy_rows_kernel<K, V, 4><<<blocks, kRowThreads, 0, st>>>(LZ_ARGS)
+#define CALL2(K, V) lazy_rows_kernel<K, V, 2><<<blocks, kRowThreads, 0, st>>>(LZ_ARGS)
+  if (!vec) TTAM_DISPATCH_KIND(kind, false, CALL);
+  else if (rows_hb() == 2) TTAM_DISPATCH_KIND(kind, true, CALL2);
+  else TTAM_DISPATCH_KIND(kind, true, CALL);
 #undef CALL
+#undef CALL2
+#undef LZ_ARGS
   TTAM_LAUNCH_CHECK();
-  if (skip) {
-#define CALL(K, V) lazy_long_kernel<K, V><<<2 * num_sms(), 32 * kLongWarps, 0, st>>>(p, m, v, last_step, (int)D, sorted_idx, perm, R, gs, scalars, s, (int)step, state_dev, long_list)
-    if (vec) TTAM_DISPATCH_KIND(kind, true, CALL);
-    else TTAM_DISPATCH_KIND(kind, false, CALL);
-#undef CALL
-    TTAM_LAUNCH_CHECK();
-  }
   return TTAM_OK;
 }
 
@@ -752,11 +845,15 @@ extern "C" int ttam_lazy_catchup(int kind, float* p, float* m, float* v, int32_t
   TTAM_CHECK_ARG(kind != TTAM_OPT_SGD || momentum == 0.0 || m, "lazy_catchup: SGD momentum needs the buffer m");
   TTAM_CHECK_ARG(D > 0 && step >= 1 && step < (1ll << 30), "lazy_catchup: bad argument");
   AdamScalars s = make_scalars(lr, weight_decay, beta1, beta2, eps, momentum);
-  const int blocks = (int)ceil_div(R * 32, 256);
+  const int blocks = (int)ceil_div(R, kCatchStride * kRowWarps);
   cudaStream_t st = (cudaStream_t)stream;
-#define CALL(K, V) lazy_catchup_kernel<K, V><<<blocks, 256, 0, st>>>(p, m, v, last_step, (int)D, sorted_idx, R, scalars, s, (int)step, state_dev)
-  if (vec_ok(D, p, m, v, nullptr, 0, nullptr, 0)) TTAM_DISPATCH_KIND(kind, true, CALL);
-  else TTAM_DISPATCH_KIND(kind, false, CALL);
+#define CALL(K, NE) lazy_catchup_kernel<K, NE><<<blocks, kRowThreads, 0, st>>>(p, m, v, last_step, (int)D, sorted_idx, R, scalars, s, (int)step, state_dev)
+  // elements per lane: the whole row in one pass when D is 32, 64, 96 or 128; 128-column passes for wider rows
+  const int ne = D % 128 == 0 ? 4 : (D % 32 == 0 && D < 128) ? (int)(D / 32) : D > 64 ? 4 : D > 32 ? 2 : 1;
+  if (ne == 4) TTAM_DISPATCH_KIND(kind, 4, CALL);
+  else if (ne == 3) TTAM_DISPATCH_KIND(kind, 3, CALL);
+  else if (ne == 2) TTAM_DISPATCH_KIND(kind, 2, CALL);
+  else TTAM_DISPATCH_KIND(kind, 1, CALL);
 #undef CALL
   TTAM_LAUNCH_CHECK();
   return TTAM_OK;

@@ -9,37 +9,39 @@
 namespace ttam {
 
 // ------------------------------------------------------------------------------------------------
-// gather: one 16-byte chunk per thread-iteration, 4 independent loads in flight per thread
+// gather: a warp takes kGatherRows consecutive output rows; their indices are ONE coalesced load by the first lanes
+// (no per-chunk division, no per-chunk dependent index load), then lane = 16-byte chunk of the row with all kGatherRows
+// row loads issued before the first store (8 x 384 B in flight per warp at D = 96).
 // ------------------------------------------------------------------------------------------------
+constexpr int kGatherRows = 8;
+
 template <bool VEC>
 __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ table, int64_t ld_t,
                                                           int64_t num_rows, const int64_t* __restrict__ idx,
                                                           float* __restrict__ out, int64_t ld_o, int64_t R,
                                                           int64_t ncols) {
   if (VEC) {
-    const int64_t cpr = ncols >> 2;  // chunks per row
-    const int64_t total = R * cpr;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i + 3 * stride < total; i += 4 * stride) {
-      float4 v[4];
-      int64_t r[4], c[4];
+    const int lane = threadIdx.x & 31;
+    const int64_t r0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * kGatherRows;
+    if (r0 >= R) return;
+    int64_t mine = -1;
+    if (lane < kGatherRows && r0 + lane < R) {
+      mine = idx[r0 + lane];
+      if (mine < 0 || mine >= num_rows) mine = -1;   // rows outside the table come back as zeros
+    }
+    const int nrows = (int)((R - r0) < kGatherRows ? (R - r0) : kGatherRows);
+    const int cpr = (int)(ncols >> 2);  // 16-byte chunks per row
+    for (int c0 = 0; c0 < cpr; c0 += 32) {
+      const int c = c0 + lane;
+      float4 v[kGatherRows];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        int64_t j = i + u * stride;
-        r[u] = j / cpr;
-        c[u] = j - r[u] * cpr;
-        int64_t src = idx[r[u]];
-        v[u] = (src >= 0 && src < num_rows) ? ld_f4(table + src * ld_t + c[u] * 4) : make_float4(0, 0, 0, 0);
+      for (int u = 0; u < kGatherRows; ++u) {
+        const int64_t src = __shfl_sync(0xffffffffu, mine, u);
+        v[u] = (c < cpr && src >= 0) ? ld_f4(table + src * ld_t + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) st_f4(out + r[u] * ld_o + c[u] * 4, v[u]);
-    }
-    for (; i < total; i += stride) {
-      int64_t r = i / cpr, c = i - r * cpr;
-      int64_t src = idx[r];
-      float4 v = (src >= 0 && src < num_rows) ? ld_f4(table + src * ld_t + c * 4) : make_float4(0, 0, 0, 0);
-      st_f4(out + r * ld_o + c * 4, v);
+      for (int u = 0; u < kGatherRows; ++u)
+        if (c < cpr && u < nrows) st_f4(out + (r0 + u) * ld_o + c * 4, v[u]);
     }
   } else {
     const int64_t total = R * ncols;
@@ -521,8 +523,8 @@ extern "C" int ttam_gather_rows_f32(const float* table, int64_t ld_table, int64_
   bool vec = (ncols % 4 == 0) && (ld_table % 4 == 0) && (ld_out % 4 == 0) && (((uintptr_t)table & 15) == 0) &&
              (((uintptr_t)out & 15) == 0);
   if (vec)
-    gather_rows_kernel<true><<<grid_for(R * (ncols / 4), 256), 256, 0, s>>>(table, ld_table, num_rows, idx, out,
-                                                                           ld_out, R, ncols);
+    gather_rows_kernel<true><<<(unsigned)ceil_div(R, (int64_t)kGatherRows * 8), 256, 0, s>>>(table, ld_table, num_rows, idx, out,
+                                                                                             ld_out, R, ncols);
   else
     gather_rows_kernel<false><<<grid_for(R * ncols, 256), 256, 0, s>>>(table, ld_table, num_rows, idx, out, ld_out,
                                                                       R, ncols);
