@@ -200,13 +200,23 @@ def time_kernel_classes(eng, F, c, dev, users, pos, neg, user_x, item_x, nu_l, n
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
+    clean = os.environ.get("TTAM_FLUSH", "clean") != "dirty"
+    def flush_l2():
+        # a cold L2 that holds CLEAN lines: reading 256 MB evicts what the kernel left behind without leaving 126 MB of dirty
+        # lines whose write-backs the next kernel would pay for (a memset flush showed up as 90-130 MB of DRAM writes inside
+        # an 18 us kernel under ncu).  TTAM_FLUSH=dirty restores the memset.
+        if clean:
+            flush.view(torch.int64).max()
+        else:
+            flush.zero_()
+
     def alone(fn, reps=5, prep=None):
         fn()
         tot = 0.0
         for _ in range(reps):
             if prep is not None:
                 prep()
-            flush.zero_()
+            flush_l2()
             torch.cuda._sleep(400_000)      # the host enqueues fn() while the GPU spins: k0 -> k1 is device time only
             k0.record(); fn(); k1.record()
             torch.cuda.synchronize()

@@ -5,6 +5,7 @@ persistent kernel (gemm_tma.cu): CUDA events, cold L2.
     python scripts/time_gemm.py [--reps 5]
 """
 import argparse
+import os
 import sys
 from pathlib import Path
 
@@ -23,13 +24,22 @@ def main():
     dev = torch.device("cuda")
     R, D, H = a.rows, 96, 192
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    clean = os.environ.get("TTAM_FLUSH", "clean") != "dirty"
+
+    def flush_l2():
+        # a cold L2 of CLEAN lines (a 256 MB read); TTAM_FLUSH=dirty: the memset flush, whose write-backs land in the timed kernel
+        if clean:
+            flush.view(torch.int64).max()
+        else:
+            flush.zero_()
+
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def alone(fn):
         fn()
         tot = 0.0
         for _ in range(a.reps):
-            flush.zero_()
+            flush_l2()
             torch.cuda._sleep(400_000)      # the host enqueues fn() while the GPU spins: e0 -> e1 is device time only
             e0.record(); fn(); e1.record()
             torch.cuda.synchronize()

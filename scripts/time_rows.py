@@ -6,6 +6,7 @@ cold L2 and algorithmic bytes / time, for `ncu --set full` capture
     python scripts/time_rows.py [--reps 5] [--rows 2000000] [--gap 49]
 """
 import argparse
+import os
 import sys
 from pathlib import Path
 
@@ -47,6 +48,15 @@ def main():
     ll = F.find_long_segments(sidx)
     print(f"R={R} unique={uniq} long segments={int(ll[0])} longest={int(torch.bincount(idx).max())}", flush=True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    clean = os.environ.get("TTAM_FLUSH", "clean") != "dirty"
+
+    def flush_l2():
+        # a cold L2 of CLEAN lines (a 256 MB read); TTAM_FLUSH=dirty: the memset flush, whose write-backs land in the timed kernel
+        if clean:
+            flush.view(torch.int64).max()
+        else:
+            flush.zero_()
+
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
     def alone(fn, prep=None):
@@ -55,7 +65,7 @@ def main():
         for _ in range(a.reps):
             if prep is not None:
                 prep()
-            flush.zero_()
+            flush_l2()
             torch.cuda._sleep(400_000)      # the host enqueues fn() while the GPU spins: e0 -> e1 is device time only
             e0.record(); fn(); e1.record()
             torch.cuda.synchronize()
