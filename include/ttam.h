@@ -228,6 +228,18 @@ int ttam_loss_fwd_bwd(const float* o_u, const float* o_i, const float* t_u, cons
                       float* do_u, float* do_i, float* dq_u, float* dq_p, int64_t B, int64_t N, int64_t D,
                       float batch_fraction, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* The same loss with the augmentation add folded in (adaptive_mimic.py:88-95 + training.py:770-803 as ONE pass):
+ * t_u[B,D], t_i[(1+N)B,D] base tower outputs (positives first, then negatives [B,N] row-major); aug_u / aug_i the augmentation
+ * tables ([rows, D] fp32, rows D floats apart); users[B], items[(1+N)B] the step's row ids (ids outside the table add nothing).
+ * o = t + aug[idx] is formed in registers; loss, do_*, dq_* exactly as ttam_augment_fwd followed by ttam_loss_fwd_bwd
+ * (mimic != 0: the mimic terms are evaluated, q = the augmentation rows of the positive pairs).  N <= 8, D % 4 == 0, D <= 128
+ * (ttam_loss_aug_supported); otherwise use the two calls. */
+int ttam_loss_aug_supported(int64_t N, int64_t D);
+int ttam_loss_aug_fwd_bwd(const float* t_u, const float* t_i, const float* aug_u, int64_t aug_u_rows, const float* aug_i,
+                          int64_t aug_i_rows, const int64_t* users, const int64_t* items, int mimic, float lambda_u,
+                          float lambda_i, float* loss_out, float* do_u, float* do_i, float* dq_u, float* dq_p, int64_t B,
+                          int64_t N, int64_t D, float batch_fraction, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- in-batch softmax loss (EXTENSION: BASELINE.json configs[1] "in-batch negatives"; the reference has no such loss, its
  * training loss is the sampled-negative BCE above - definition and parity: oracle/model.py inbatch_loss_forward_backward) ----
  * S = o_u o_p^T [B,B]; L_ce = mean_b (logsumexp_j S[b,j] - S[b,b]); mimic terms as in ttam_loss_fwd_bwd.

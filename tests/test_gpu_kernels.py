@@ -282,6 +282,32 @@ def test_loss_fwd_bwd(F, B, N, D, mimic):
     assert float(l2[1]) == pytest.approx(float(ref["bce"]), rel=2e-6)
 
 
+@pytest.mark.parametrize("B,N,D", [(24, 3, 16), (8192, 5, 96), (100, 8, 128), (7, 1, 96)])
+def test_loss_with_augmentation_folded_in_equals_two_calls(F, B, N, D):
+    """ttam_loss_aug_fwd_bwd (o = t + A[idx] formed inside the loss kernel) against ttam_augment_fwd + ttam_loss_fwd_bwd:
+    the same fp32 operations in the same order, so every output is bit-identical (duplicate ids and an id that repeats
+    between positives and negatives included)."""
+    rng = np.random.default_rng(B + N + D)
+    NU, NI = 50, 40                                                # small tables: many duplicate ids
+    t_u = dev((rng.standard_normal((B, D)) * 0.3).astype(np.float32))
+    t_i = dev((rng.standard_normal((B * (1 + N), D)) * 0.3).astype(np.float32))
+    A_u = dev((rng.standard_normal((NU, D)) * 0.05).astype(np.float32))
+    A_i = dev((rng.standard_normal((NI, D)) * 0.05).astype(np.float32))
+    users = dev(rng.integers(0, NU, size=B).astype(np.int64))
+    items = dev(rng.integers(0, NI, size=B * (1 + N)).astype(np.int64))
+    o_u, q_u = torch.empty_like(t_u), torch.empty_like(t_u)
+    o_i, q_i = torch.empty_like(t_i), torch.empty_like(t_i)
+    F.augment_fwd(t_u, A_u, users, out=o_u, q_out=q_u)
+    F.augment_fwd(t_i, A_i, items, out=o_i, q_out=q_i)
+    ref = F.loss_fwd_bwd(o_u, o_i, t_u=t_u, t_p=t_i[:B], q_u=q_u, q_p=q_i[:B], lambda_u=0.15, lambda_i=0.25)
+    got = F.loss_aug_fwd_bwd(t_u, t_i, A_u, A_i, users, items, mimic=True, lambda_u=0.15, lambda_i=0.25)
+    for a, b, name in zip(ref, got, ("loss", "do_u", "do_i", "dq_u", "dq_p")):
+        assert torch.equal(a, b), name
+    # forward only
+    fwd = F.loss_aug_fwd_bwd(t_u, t_i, A_u, A_i, users, items, mimic=True, lambda_u=0.15, lambda_i=0.25, backward=False)
+    assert torch.equal(fwd[0], ref[0]) and fwd[1] is None
+
+
 def test_sort_and_unique_rows_bit_exact(F):
     rng = np.random.default_rng(2)
     idx = rng.integers(0, 2_000_000, size=57344).astype(np.int64)

@@ -572,7 +572,8 @@ int tma_gemm(const float* A, int64_t lda, const float* B, int64_t ldb, float* C,
 // Splits of the TMA weight gradient: about two CTAs per SM, at least 256 rows each.
 int tma_wgrad_splits(int64_t M, int64_t N, int64_t K) {
   const int64_t tiles = ceil_div(K, kBM) * ceil_div(N, 256);
-  int64_t s = (2 * (int64_t)num_sms()) / tiles;
+  static const int tenths = [] { const char* e = getenv("TTAM_WGRAD_CTAS_X10"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 20; }();
+  int64_t s = (tenths * (int64_t)num_sms() / 10) / tiles;   // CTAs per SM x 10 (default 2.0)
   const int64_t by_rows = ceil_div(M, 256);
   if (s > by_rows) s = by_rows;
   return (int)(s < 1 ? 1 : s);

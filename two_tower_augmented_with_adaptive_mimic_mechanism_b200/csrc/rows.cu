@@ -414,6 +414,105 @@ __global__ void __launch_bounds__(256) loss_vec_kernel(const float* __restrict__
   }
 }
 
+// The same loss with the augmentation add folded in (BASELINE north_star (2)): o = t + A[idx] is formed in registers from
+// the base tower rows t and the augmentation rows of the step's ids, so o and q never exist in HBM and the separate
+// augment launch (read t, gather A, write o and q) disappears from the step.  Indices of the pair's 2 + N rows are one
+// load by the first lanes; every row of the pair (2 + N base rows, 2 + N augmentation rows) is requested before the
+// first use.  Arithmetic identical to ttam_augment_fwd followed by loss_vec_kernel (o = t + q is the same fp32 add).
+template <int NMAX>
+__global__ void __launch_bounds__(256) loss_aug_vec_kernel(const float* __restrict__ t_u, const float* __restrict__ t_i,
+                                                           const float* __restrict__ A_u, int64_t rows_u,
+                                                           const float* __restrict__ A_i, int64_t rows_i,
+                                                           const int64_t* __restrict__ users, const int64_t* __restrict__ items,
+                                                           int mimic, float cu, float ci, float* __restrict__ partial,
+                                                           float* __restrict__ do_u, float* __restrict__ do_i,
+                                                           float* __restrict__ dq_u, float* __restrict__ dq_p, int B, int N,
+                                                           int D, float inv_M) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const int col = lane * 4;
+  const bool act = col < D;
+  const bool bwd = (do_u != nullptr);
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  int64_t my = -1;   // lane 0: the user, lane 1: the positive, lanes 2 .. 1+N: the negatives
+  if (lane == 0) my = users[b];
+  else if (lane == 1) my = items[b];
+  else if (lane < 2 + N) my = items[(int64_t)B + (int64_t)b * N + (lane - 2)];
+  if (my >= (lane == 0 ? rows_u : rows_i)) my = -1;
+  const int64_t rb = (int64_t)b * D + col;                                  // row b of a [B, D] block
+  const int64_t rn = ((int64_t)B + (int64_t)b * N) * D + col;               // first negative of b in t_i / do_i
+  const int64_t iu = __shfl_sync(0xffffffffu, my, 0), ip = __shfl_sync(0xffffffffu, my, 1);
+  int64_t in_[NMAX];
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n) in_[n] = __shfl_sync(0xffffffffu, my, 2 + n);
+  float4 tu = z4, tp = z4, qu = z4, qp = z4, tn[NMAX], qn[NMAX];
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n) tn[n] = qn[n] = z4;
+  if (act) {
+    tu = ld_f4(t_u + rb);
+    tp = ld_f4(t_i + rb);
+    if (iu >= 0) qu = ld_f4(A_u + iu * D + col);
+    if (ip >= 0) qp = ld_f4(A_i + ip * D + col);
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n)
+      if (n < N) {
+        tn[n] = ld_f4(t_i + rn + (int64_t)n * D);
+        if (in_[n] >= 0) qn[n] = ld_f4(A_i + in_[n] * D + col);
+      }
+  }
+  auto add4 = [](const float4& a, const float4& c) { return make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w); };
+  const float4 uu = add4(tu, qu), pp = add4(tp, qp);
+  float4 nn[NMAX];
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n) nn[n] = add4(tn[n], qn[n]);
+  auto dot4 = [](const float4& a, const float4& c) { return fmaf(a.w, c.w, fmaf(a.z, c.z, fmaf(a.y, c.y, a.x * c.x))); };
+  const float sp = warp_sum(dot4(uu, pp));
+  float bce = softplusf_(-sp);
+  const float dsp = (sigmoidf_(sp) - 1.f) * inv_M;
+  float ds[NMAX];
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n) {
+    ds[n] = 0.f;
+    if (n < N) {
+      const float sc = warp_sum(dot4(uu, nn[n]));
+      bce += softplusf_(sc);
+      ds[n] = sigmoidf_(sc) * inv_M;
+    }
+  }
+  float mu = 0.f, mi = 0.f;
+  float4 gu = make_float4(dsp * pp.x, dsp * pp.y, dsp * pp.z, dsp * pp.w);
+  const float4 gp = make_float4(dsp * uu.x, dsp * uu.y, dsp * uu.z, dsp * uu.w);
+  if (bwd) {
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n)
+      if (n < N) {
+        gu.x = fmaf(ds[n], nn[n].x, gu.x); gu.y = fmaf(ds[n], nn[n].y, gu.y);
+        gu.z = fmaf(ds[n], nn[n].z, gu.z); gu.w = fmaf(ds[n], nn[n].w, gu.w);
+        if (act) st_f4(do_i + rn + (int64_t)n * D, make_float4(ds[n] * uu.x, ds[n] * uu.y, ds[n] * uu.z, ds[n] * uu.w));
+      }
+    if (act) {
+      st_f4(do_u + rb, gu);
+      st_f4(do_i + rb, gp);
+    }
+  }
+  if (mimic) {
+    const float4 du = make_float4(qu.x - tp.x, qu.y - tp.y, qu.z - tp.z, qu.w - tp.w);
+    const float4 di = make_float4(qp.x - tu.x, qp.y - tu.y, qp.z - tu.z, qp.w - tu.w);
+    mu = warp_sum(dot4(du, du));
+    mi = warp_sum(dot4(di, di));
+    if (bwd && act) {
+      st_f4(dq_u + rb, make_float4(fmaf(cu, du.x, gu.x), fmaf(cu, du.y, gu.y), fmaf(cu, du.z, gu.z), fmaf(cu, du.w, gu.w)));
+      st_f4(dq_p + rb, make_float4(fmaf(ci, di.x, gp.x), fmaf(ci, di.y, gp.y), fmaf(ci, di.z, gp.z), fmaf(ci, di.w, gp.w)));
+    }
+  }
+  if (lane == 0) {
+    partial[(int64_t)b * 3 + 0] = bce;
+    partial[(int64_t)b * 3 + 1] = mu;
+    partial[(int64_t)b * 3 + 2] = mi;
+  }
+}
+
 // deterministic final reduction: one block, fixed-order strided partial sums + tree
 __global__ void __launch_bounds__(1024) loss_reduce_kernel(const float* __restrict__ partial, int B, float inv_M,
                                                            float inv_BD, float lambda_u, float lambda_i, int mimic,
@@ -646,6 +745,45 @@ extern "C" int ttam_loss_fwd_bwd(const float* o_u, const float* o_i, const float
   TTAM_LAUNCH_CHECK();
   loss_reduce_kernel<<<1, 1024, 0, s>>>((const float*)workspace, (int)B, inv_M, inv_BD, lambda_u, lambda_i,
                                         q_u != nullptr, loss_out);
+  TTAM_LAUNCH_CHECK();
+  return TTAM_OK;
+}
+
+extern "C" int ttam_loss_aug_supported(int64_t N, int64_t D) { return (D % 4 == 0 && D <= 128 && N >= 1 && N <= 8) ? 1 : 0; }
+
+extern "C" int ttam_loss_aug_fwd_bwd(const float* t_u, const float* t_i, const float* aug_u, int64_t aug_u_rows, const float* aug_i,
+                                     int64_t aug_i_rows, const int64_t* users, const int64_t* items, int mimic, float lambda_u,
+                                     float lambda_i, float* loss_out, float* do_u, float* do_i, float* dq_u, float* dq_p, int64_t B,
+                                     int64_t N, int64_t D, float batch_fraction, void* workspace, int64_t workspace_bytes,
+                                     void* stream) {
+  TTAM_CHECK_ARG(t_u && t_i && aug_u && aug_i && users && items && loss_out && workspace, "loss_aug: null pointer");
+  TTAM_CHECK_ARG(batch_fraction > 0.f && batch_fraction <= 1.f, "loss_aug: batch_fraction must be in (0, 1]");
+  TTAM_CHECK_ARG(B > 0 && ttam_loss_aug_supported(N, D), "loss_aug: need B > 0, 1 <= N <= 8, D %% 4 == 0, D <= 128 (use ttam_augment_fwd + ttam_loss_fwd_bwd)");
+  TTAM_CHECK_ARG((do_u == nullptr) == (do_i == nullptr), "loss_aug: do_u/do_i must both be set or both null");
+  TTAM_CHECK_ARG(!(do_u && mimic) || (dq_u && dq_p), "loss_aug: dq_u/dq_p required with mimic backward");
+  auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+  TTAM_CHECK_ARG(al16(t_u) && al16(t_i) && al16(aug_u) && al16(aug_i) && al16(do_u) && al16(do_i) && al16(dq_u) && al16(dq_p),
+                 "loss_aug: 16-byte aligned rows required");
+  if (workspace_bytes < ttam_loss_workspace_bytes(B)) {
+    set_error("loss_aug: workspace too small");
+    return TTAM_EWORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const double M = (double)B * (double)(1 + N);
+  const float inv_M = (float)((double)batch_fraction / M);
+  const float inv_BD = (float)((double)batch_fraction / ((double)B * (double)D));
+  const float cu = lambda_u > 0.f ? (float)(2.0 * (double)lambda_u * (double)batch_fraction / ((double)B * (double)D)) : 0.f;
+  const float ci = lambda_i > 0.f ? (float)(2.0 * (double)lambda_i * (double)batch_fraction / ((double)B * (double)D)) : 0.f;
+  const int threads = 256;
+  const int blocks = (int)ceil_div(B * 32, threads);
+  if (N <= 5)
+    loss_aug_vec_kernel<5><<<blocks, threads, 0, s>>>(t_u, t_i, aug_u, aug_u_rows, aug_i, aug_i_rows, users, items, mimic, cu, ci,
+                                                      (float*)workspace, do_u, do_i, dq_u, dq_p, (int)B, (int)N, (int)D, inv_M);
+  else
+    loss_aug_vec_kernel<8><<<blocks, threads, 0, s>>>(t_u, t_i, aug_u, aug_u_rows, aug_i, aug_i_rows, users, items, mimic, cu, ci,
+                                                      (float*)workspace, do_u, do_i, dq_u, dq_p, (int)B, (int)N, (int)D, inv_M);
+  TTAM_LAUNCH_CHECK();
+  loss_reduce_kernel<<<1, 1024, 0, s>>>((const float*)workspace, (int)B, inv_M, inv_BD, lambda_u, lambda_i, mimic, loss_out);
   TTAM_LAUNCH_CHECK();
   return TTAM_OK;
 }

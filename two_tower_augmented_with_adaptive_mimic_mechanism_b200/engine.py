@@ -126,6 +126,8 @@ class FusedEngine:
         prio = -1 if os.environ.get("TTAM_SORT_PRIORITY", "1") != "0" else 0
         self._sort_streams = {"u": torch.cuda.Stream(device=dev, priority=prio), "i": torch.cuda.Stream(device=dev, priority=prio)}
         self._overlap_sort = os.environ.get("TTAM_OVERLAP_SORT", "1") != "0"
+        # o = t + A[idx] formed inside the loss kernel (ttam_loss_aug_fwd_bwd) instead of by a separate augment launch per tower
+        self._fuse_aug_loss = os.environ.get("TTAM_FUSE_AUG_LOSS", "1") != "0"
         self._wgrad_streams = {"u": torch.cuda.Stream(device=dev), "i": torch.cuda.Stream(device=dev)}
         self._split_wgrad = os.environ.get("TTAM_WGRAD_STREAM", "1") != "0"
         self._use_aug_stream = os.environ.get("TTAM_AUG_STREAM", "1") != "0"
@@ -304,7 +306,7 @@ class FusedEngine:
     def _join(self, side) -> None:
         torch.cuda.current_stream(self.device).wait_stream(side)
 
-    def _tower_side(self, side: str, plan: TowerPlan, idx, X, bufs, rng_base):
+    def _tower_side(self, side: str, plan: TowerPlan, idx, X, bufs, rng_base, fused_loss: bool = False):
         """Sort + lazy catch-up + tower forward of one side, on the current stream.
         Only the augmentation add (o = t + A[idx]) reads a lazily-updated table when the ID table is a SparseAdam one, so
         the sort of the step's row ids and the catch-up of A run on their own stream NEXT TO the gather + MLP + gate of
@@ -328,6 +330,9 @@ class FusedEngine:
             self._catchup(a_tab, sort[0])
         c = tower_forward(plan, idx, X, augment=False, **kw)
         cur.wait_stream(ss)
+        if fused_loss:      # the loss kernel gathers A[idx] itself (after the catch-up joined just above)
+            c.o = c.q = None
+            return sort, c
         R = idx.numel()
         from .tower_ops import _buf
         o = _buf(bufs, "o", (R, plan.out_dim), self.device)
@@ -336,15 +341,16 @@ class FusedEngine:
         c.o, c.q = o, q
         return sort, c
 
-    def _forward_phase(self, users, items, Xu, Xi):
-        """Sort + lazy catch-up + both towers for the rows `users` / `items` (row ids of THIS engine's tables)."""
+    def _forward_phase(self, users, items, Xu, Xi, fused_loss: bool = False):
+        """Sort + lazy catch-up + both towers for the rows `users` / `items` (row ids of THIS engine's tables).
+        fused_loss: the caller's loss kernel adds the augmentation rows itself (cu.o / ci.o stay None)."""
         Xu, Xi = self._x(Xu), self._x(Xi)
         F.advance_step(self.state, rng_stride=1 << 36)
         side = self._fork()
         with torch.cuda.stream(side), F.ws_scope("user"):
-            sort_u, cu = self._tower_side("user", self.user, users, Xu, self.bufs_u, 0)
+            sort_u, cu = self._tower_side("user", self.user, users, Xu, self.bufs_u, 0, fused_loss)
         with F.ws_scope("item"):
-            sort_i, ci = self._tower_side("item", self.item, items, Xi, self.bufs_i, 1 << 35)
+            sort_i, ci = self._tower_side("item", self.item, items, Xi, self.bufs_i, 1 << 35, fused_loss)
         self._join(side)
         return dict(sort_u=sort_u, sort_i=sort_i, cu=cu, ci=ci)
 
@@ -367,6 +373,35 @@ class FusedEngine:
             cat, n_cat = self._categories()
             F.category_alignment(items, o_i, cat, n_cat, int(self.major), lambda_c=self.lambda_c, loss_out=loss,
                                  grad_a=do_i, grad_b=dq_p if self.mimic else None, B=B)
+        return loss, do_u, do_i, dq_u, dq_p
+
+    def _can_fuse_aug_loss(self, N: int) -> bool:
+        """The augmentation add can move into the loss kernel when both towers take the overlapped-sort branch of _tower_side
+        (their add is a separate launch there), the loss is the sampled-negative BCE without the category term (that one reads
+        o_i), and the shape is one the fused kernel covers."""
+        if not (self._fuse_aug_loss and self._overlap_sort and self.loss_kind != "inbatch" and self.mimic and N >= 1):
+            return False
+        if self.lambda_c > 0 and self.cat_tensor is not None and self.major is not None:
+            return False
+        T = self.tables
+        for side, plan in (("user", self.user), ("item", self.item)):
+            a_tab = T.get(f"adaptive_mimic.{side}_augmented.weight")
+            if a_tab is None or plan.aug is None or T[f"{side}_encoder.embedding.weight"].mode == "lazy" or plan.D != plan.out_dim:
+                return False
+            if not plan.aug.is_contiguous():
+                return False
+        return F.loss_aug_supported(N, self.user.out_dim)
+
+    def _loss_aug_phase(self, t_u, t_i, users, items, B, N):
+        """Loss forward + backward with o = t + A[idx] formed inside the kernel (no o / q buffers, no augment launches)."""
+        D = t_u.shape[1]
+        loss = self._misc("loss", (4,), torch.float32)
+        do_u = self._misc("do_u", (B, D), torch.float32)
+        do_i = self._misc("do_i", (B * (1 + N), D), torch.float32)
+        dq_u = self._misc("dq_u", (B, D), torch.float32)
+        dq_p = self._misc("dq_p", (B, D), torch.float32)
+        F.loss_aug_fwd_bwd(t_u, t_i, self.user.aug, self.item.aug, users, items, mimic=True, lambda_u=self.lambda_u,
+                           lambda_i=self.lambda_i, out=(loss, do_u, do_i, dq_u, dq_p))
         return loss, do_u, do_i, dq_u, dq_p
 
     def _inbatch_phase(self, o_u, o_p, t_u, t_p, q_u, q_p, B):
@@ -477,9 +512,13 @@ class FusedEngine:
 
     def _step_body(self, users, items, B, N, Xu, Xi):
         launches0 = F.lib().ttam_launch_count()
-        ctx = self._forward_phase(users, items, Xu, Xi)
+        fused = self._can_fuse_aug_loss(N)
+        ctx = self._forward_phase(users, items, Xu, Xi, fused_loss=fused)
         cu, ci = ctx["cu"], ctx["ci"]
-        if self.loss_kind == "inbatch":
+        if fused and cu.o is None and ci.o is None:
+            loss, do_u, do_i, dq_u, dq_p = self._loss_aug_phase(cu.t, ci.t, users, items, B, N)
+            self._backward_phase(ctx, do_u, do_i, dq_u, (dq_p, do_i[B:]) if self.mimic else None)
+        elif self.loss_kind == "inbatch":
             loss, do_u, do_i, dq_u, dq_p = self._inbatch_phase(cu.o, ci.o, cu.t, ci.t, cu.q, ci.q, B)
             self._backward_phase(ctx, do_u, do_i, dq_u, dq_p)
         else:

@@ -416,6 +416,38 @@ def loss_fwd_bwd(o_u, o_i, *, t_u=None, t_p=None, q_u=None, q_p=None, lambda_u=0
     return loss, do_u, do_i, dq_u, dq_p
 
 
+def loss_aug_supported(N: int, D: int) -> bool:
+    return bool(lib().ttam_loss_aug_supported(int(N), int(D)))
+
+
+def loss_aug_fwd_bwd(t_u, t_i, aug_u, aug_i, users, items, *, mimic=True, lambda_u=0.0, lambda_i=0.0, backward=True, out=None,
+                     batch_fraction=1.0):
+    """Augmentation add + loss in one pass: o = t + aug[idx] never leaves the registers (csrc/rows.cu loss_aug_vec_kernel).
+    t_i / items = [positives (B rows); negatives (B*N rows, [B,N] row-major)].  Returns (loss[4], do_u, do_i, dq_u, dq_p)."""
+    for t, n in ((t_u, "t_u"), (t_i, "t_i"), (aug_u, "aug_u"), (aug_i, "aug_i")):
+        _chk(t, torch.float32, n)
+    _chk(users, torch.int64, "users"); _chk(items, torch.int64, "items")
+    B, D = t_u.shape
+    N = t_i.shape[0] // B - 1
+    if not (t_u.is_contiguous() and t_i.is_contiguous() and aug_u.is_contiguous() and aug_i.is_contiguous()):
+        raise ValueError("loss_aug_fwd_bwd needs contiguous rows")
+    dev = t_u.device
+    if out is not None:
+        loss, do_u, do_i, dq_u, dq_p = out
+    else:
+        loss = torch.empty(4, dtype=torch.float32, device=dev)
+        do_u = torch.empty_like(t_u) if backward else None
+        do_i = torch.empty_like(t_i) if backward else None
+        dq_u = torch.empty_like(t_u) if (backward and mimic) else None
+        dq_p = torch.empty_like(t_u) if (backward and mimic) else None
+    ws = workspace(lib().ttam_loss_workspace_bytes(B), dev, "loss")
+    check(lib().ttam_loss_aug_fwd_bwd(t_u.data_ptr(), t_i.data_ptr(), aug_u.data_ptr(), aug_u.shape[0], aug_i.data_ptr(), aug_i.shape[0],
+                                      users.data_ptr(), items.data_ptr(), 1 if mimic else 0, float(lambda_u), float(lambda_i),
+                                      loss.data_ptr(), _ptr(do_u), _ptr(do_i), _ptr(dq_u), _ptr(dq_p), B, N, D, float(batch_fraction),
+                                      ws.data_ptr(), ws.numel(), _stream()), "loss_aug_fwd_bwd")
+    return loss, do_u, do_i, dq_u, dq_p
+
+
 def inbatch_loss_fwd_bwd(o_u, o_p, *, t_u=None, t_p=None, q_u=None, q_p=None, lambda_u=0.0, lambda_i=0.0, backward=True, out=None,
                          precision="fp32"):
     """In-batch softmax loss (extension; see ttam.h): o_u, o_p [B, D].  Returns (loss[4], do_u, do_p, dq_u, dq_p)."""
