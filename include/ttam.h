@@ -240,6 +240,20 @@ int ttam_loss_aug_fwd_bwd(const float* t_u, const float* t_i, const float* aug_u
                           float lambda_i, float* loss_out, float* do_u, float* do_i, float* dq_u, float* dq_p, int64_t B,
                           int64_t N, int64_t D, float batch_fraction, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* The loss of the row-sharded step with the row exchange folded in (SURVEY 8(e) all-to-all #2 / #3 as the loads and stores of ONE
+ * kernel; mimic on).  t_u[w] / q_u[w] / t_i[w] / q_i[w] (HOST arrays of `world` device pointers): base of the rows rank w
+ * computed for THIS requester's slots (its own buffers through NVLink peer mappings: what ttam_slot_unpack reads);
+ * a_*[w] / b_*[w]: base of THIS requester's section of rank w's receive buffers (what ttam_slot_pack writes; rows D floats
+ * apart).  slot_of_u[B], slot_of_i[(1+N)B] from ttam_slot_plan (positives first, then negatives [B,N] row-major).
+ * Every real slot receives a = do and b = dq (dq of a negative = its do); padding slots are NOT written: the owner zeroes
+ * its receive buffers before the step's first barrier.  Same arithmetic and loss_out[4] as ttam_loss_fwd_bwd on
+ * o = t + q. */
+int ttam_loss_slots_fwd_bwd(const float* const* t_u, const float* const* q_u, const float* const* t_i, const float* const* q_i,
+                            float* const* a_u, float* const* b_u, float* const* a_i, float* const* b_i, int64_t world,
+                            int64_t cap_u, int64_t cap_i, const int64_t* slot_of_u, const int64_t* slot_of_i, float lambda_u,
+                            float lambda_i, float* loss_out, int64_t B, int64_t N, int64_t D, float batch_fraction,
+                            void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- in-batch softmax loss (EXTENSION: BASELINE.json configs[1] "in-batch negatives"; the reference has no such loss, its
  * training loss is the sampled-negative BCE above - definition and parity: oracle/model.py inbatch_loss_forward_backward) ----
  * S = o_u o_p^T [B,B]; L_ce = mean_b (logsumexp_j S[b,j] - S[b,b]); mimic terms as in ttam_loss_fwd_bwd.

@@ -140,6 +140,7 @@ SIGNATURES = {
     "ttam_loss_fwd_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _i64, _i64, _i64, _f, _p, _i64, _p]),
     "ttam_loss_aug_supported": (C.c_int, [_i64, _i64]),
     "ttam_loss_aug_fwd_bwd": (C.c_int, [_p, _p, _p, _i64, _p, _i64, _p, _p, _i32, _f, _f, _p, _p, _p, _p, _p, _i64, _i64, _i64, _f, _p, _i64, _p]),
+    "ttam_loss_slots_fwd_bwd": (C.c_int, [_p] * 8 + [_i64, _i64, _i64, _p, _p, _f, _f, _p, _i64, _i64, _i64, _f, _p, _i64, _p]),
     "ttam_inbatch_loss_workspace_bytes": (C.c_int64, [_i64, _i64]),
     "ttam_inbatch_loss_fwd_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _i64, _i64, _i32, _p, _i64, _p]),
     "ttam_category_alignment_workspace_bytes": (C.c_int64, [_i64, _i64, _i64]),

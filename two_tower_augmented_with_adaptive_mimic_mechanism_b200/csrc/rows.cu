@@ -513,6 +513,111 @@ __global__ void __launch_bounds__(256) loss_aug_vec_kernel(const float* __restri
   }
 }
 
+// The loss of the row-sharded step with the row exchange folded in (SURVEY 8(e) all-to-all #2 and #3 as the loads and
+// stores of ONE kernel over NVLink peer mappings): a pair's base rows t and augmentation rows q are loaded straight from
+// the buffers of the ranks that OWN them (slot s of an index set = owner s / cap, position s % cap, as ttam_slot_plan
+// laid them out), o = t + q is formed in registers, and the gradient rows [do | dq] are stored straight into the
+// owners' receive buffers at the same slots.  Replaces ttam_slot_unpack -> ttam_loss_fwd_bwd -> ttam_slot_pack (three
+// passes over the rows, two of them only to move data); padding slots are never written - the owner zeroes its receive
+// buffers at the start of the step.
+constexpr int kSlotMaxW = 16;
+struct SlotLossPtrs {
+  const float* t_u[kSlotMaxW]; const float* q_u[kSlotMaxW]; const float* t_i[kSlotMaxW]; const float* q_i[kSlotMaxW];
+  float* a_u[kSlotMaxW]; float* b_u[kSlotMaxW]; float* a_i[kSlotMaxW]; float* b_i[kSlotMaxW];
+};
+
+template <int NMAX>
+__global__ void __launch_bounds__(256) loss_slots_vec_kernel(const SlotLossPtrs P, int W, int64_t cap_u, int64_t cap_i,
+                                                             const int64_t* __restrict__ slot_of_u,
+                                                             const int64_t* __restrict__ slot_of_i, float cu, float ci,
+                                                             float* __restrict__ partial, int B, int N, int D, float inv_M) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const int col = lane * 4;
+  const bool act = col < D;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  // lane 0: the user's slot, lane 1: the positive's, lanes 2 .. 1+N: the negatives'; owner and element offset per lane
+  int64_t slot = -1;
+  if (lane == 0) slot = slot_of_u[b];
+  else if (lane == 1) slot = slot_of_i[b];
+  else if (lane < 2 + N) slot = slot_of_i[(int64_t)B + (int64_t)b * N + (lane - 2)];
+  const int64_t cap = lane == 0 ? cap_u : cap_i;
+  int own = -1;
+  int64_t off = 0;
+  if (slot >= 0 && slot < (int64_t)W * cap) {   // (a slot of W * cap = "did not fit": the caller routes such steps elsewhere)
+    own = (int)(slot / cap);
+    off = (slot - (int64_t)own * cap) * D;
+  }
+  const int ou = __shfl_sync(0xffffffffu, own, 0), op = __shfl_sync(0xffffffffu, own, 1);
+  const int64_t eu_ = __shfl_sync(0xffffffffu, off, 0) + col, ep_ = __shfl_sync(0xffffffffu, off, 1) + col;
+  int on[NMAX];
+  int64_t en[NMAX];
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n) {
+    on[n] = __shfl_sync(0xffffffffu, own, 2 + n);
+    en[n] = __shfl_sync(0xffffffffu, off, 2 + n) + col;
+  }
+  float4 tu = z4, tp = z4, qu = z4, qp = z4, tn[NMAX], qn[NMAX];
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n) tn[n] = qn[n] = z4;
+  if (act) {
+    if (ou >= 0) { tu = ld_f4_stream(P.t_u[ou] + eu_); qu = ld_f4_stream(P.q_u[ou] + eu_); }
+    if (op >= 0) { tp = ld_f4_stream(P.t_i[op] + ep_); qp = ld_f4_stream(P.q_i[op] + ep_); }
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n)
+      if (n < N && on[n] >= 0) {
+        tn[n] = ld_f4_stream(P.t_i[on[n]] + en[n]);
+        qn[n] = ld_f4_stream(P.q_i[on[n]] + en[n]);
+      }
+  }
+  auto add4 = [](const float4& a, const float4& c) { return make_float4(a.x + c.x, a.y + c.y, a.z + c.z, a.w + c.w); };
+  const float4 uu = add4(tu, qu), pp = add4(tp, qp);
+  float4 nn[NMAX];
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n) nn[n] = add4(tn[n], qn[n]);
+  auto dot4 = [](const float4& a, const float4& c) { return fmaf(a.w, c.w, fmaf(a.z, c.z, fmaf(a.y, c.y, a.x * c.x))); };
+  const float sp = warp_sum(dot4(uu, pp));
+  float bce = softplusf_(-sp);
+  const float dsp = (sigmoidf_(sp) - 1.f) * inv_M;
+  float4 gu = make_float4(dsp * pp.x, dsp * pp.y, dsp * pp.z, dsp * pp.w);
+  const float4 gp = make_float4(dsp * uu.x, dsp * uu.y, dsp * uu.z, dsp * uu.w);
+#pragma unroll
+  for (int n = 0; n < NMAX; ++n) {
+    if (n < N) {
+      const float sc = warp_sum(dot4(uu, nn[n]));
+      bce += softplusf_(sc);
+      const float dsn = sigmoidf_(sc) * inv_M;
+      gu.x = fmaf(dsn, nn[n].x, gu.x); gu.y = fmaf(dsn, nn[n].y, gu.y);
+      gu.z = fmaf(dsn, nn[n].z, gu.z); gu.w = fmaf(dsn, nn[n].w, gu.w);
+      if (act && on[n] >= 0) {
+        const float4 g = make_float4(dsn * uu.x, dsn * uu.y, dsn * uu.z, dsn * uu.w);
+        st_f4(P.a_i[on[n]] + en[n], g);       // do of a negative ...
+        st_f4(P.b_i[on[n]] + en[n], g);       // ... is also the gradient of its augmentation row
+      }
+    }
+  }
+  const float4 du = make_float4(qu.x - tp.x, qu.y - tp.y, qu.z - tp.z, qu.w - tp.w);
+  const float4 di = make_float4(qp.x - tu.x, qp.y - tu.y, qp.z - tu.z, qp.w - tu.w);
+  const float mu = warp_sum(dot4(du, du));
+  const float mi = warp_sum(dot4(di, di));
+  if (act) {
+    if (ou >= 0) {
+      st_f4(P.a_u[ou] + eu_, gu);
+      st_f4(P.b_u[ou] + eu_, make_float4(fmaf(cu, du.x, gu.x), fmaf(cu, du.y, gu.y), fmaf(cu, du.z, gu.z), fmaf(cu, du.w, gu.w)));
+    }
+    if (op >= 0) {
+      st_f4(P.a_i[op] + ep_, gp);
+      st_f4(P.b_i[op] + ep_, make_float4(fmaf(ci, di.x, gp.x), fmaf(ci, di.y, gp.y), fmaf(ci, di.z, gp.z), fmaf(ci, di.w, gp.w)));
+    }
+  }
+  if (lane == 0) {
+    partial[(int64_t)b * 3 + 0] = bce;
+    partial[(int64_t)b * 3 + 1] = mu;
+    partial[(int64_t)b * 3 + 2] = mi;
+  }
+}
+
 // deterministic final reduction: one block, fixed-order strided partial sums + tree
 __global__ void __launch_bounds__(1024) loss_reduce_kernel(const float* __restrict__ partial, int B, float inv_M,
                                                            float inv_BD, float lambda_u, float lambda_i, int mimic,
@@ -784,6 +889,50 @@ extern "C" int ttam_loss_aug_fwd_bwd(const float* t_u, const float* t_i, const f
                                                       (float*)workspace, do_u, do_i, dq_u, dq_p, (int)B, (int)N, (int)D, inv_M);
   TTAM_LAUNCH_CHECK();
   loss_reduce_kernel<<<1, 1024, 0, s>>>((const float*)workspace, (int)B, inv_M, inv_BD, lambda_u, lambda_i, mimic, loss_out);
+  TTAM_LAUNCH_CHECK();
+  return TTAM_OK;
+}
+
+extern "C" int ttam_loss_slots_fwd_bwd(const float* const* t_u, const float* const* q_u, const float* const* t_i, const float* const* q_i,
+                                       float* const* a_u, float* const* b_u, float* const* a_i, float* const* b_i, int64_t world,
+                                       int64_t cap_u, int64_t cap_i, const int64_t* slot_of_u, const int64_t* slot_of_i, float lambda_u,
+                                       float lambda_i, float* loss_out, int64_t B, int64_t N, int64_t D, float batch_fraction,
+                                       void* workspace, int64_t workspace_bytes, void* stream) {
+  TTAM_CHECK_ARG(t_u && q_u && t_i && q_i && a_u && b_u && a_i && b_i && slot_of_u && slot_of_i && loss_out && workspace,
+                 "loss_slots: null pointer");
+  TTAM_CHECK_ARG(world >= 1 && world <= kSlotMaxW && cap_u >= 1 && cap_i >= 1, "loss_slots: world=%lld not in [1,%d] or empty slots",
+                 (long long)world, kSlotMaxW);
+  TTAM_CHECK_ARG(batch_fraction > 0.f && batch_fraction <= 1.f, "loss_slots: batch_fraction must be in (0, 1]");
+  TTAM_CHECK_ARG(B > 0 && ttam_loss_aug_supported(N, D), "loss_slots: need B > 0, 1 <= N <= 8, D %% 4 == 0, D <= 128");
+  SlotLossPtrs P{};
+  for (int w = 0; w < (int)world; ++w) {
+    P.t_u[w] = t_u[w]; P.q_u[w] = q_u[w]; P.t_i[w] = t_i[w]; P.q_i[w] = q_i[w];
+    P.a_u[w] = a_u[w]; P.b_u[w] = b_u[w]; P.a_i[w] = a_i[w]; P.b_i[w] = b_i[w];
+    const uintptr_t all = (uintptr_t)t_u[w] | (uintptr_t)q_u[w] | (uintptr_t)t_i[w] | (uintptr_t)q_i[w] | (uintptr_t)a_u[w] |
+                          (uintptr_t)b_u[w] | (uintptr_t)a_i[w] | (uintptr_t)b_i[w];
+    TTAM_CHECK_ARG(t_u[w] && q_u[w] && t_i[w] && q_i[w] && a_u[w] && b_u[w] && a_i[w] && b_i[w] && (all & 15) == 0,
+                   "loss_slots: buffer of rank %d null or not 16-byte aligned", w);
+  }
+  if (workspace_bytes < ttam_loss_workspace_bytes(B)) {
+    set_error("loss_slots: workspace too small");
+    return TTAM_EWORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const double M = (double)B * (double)(1 + N);
+  const float inv_M = (float)((double)batch_fraction / M);
+  const float inv_BD = (float)((double)batch_fraction / ((double)B * (double)D));
+  const float cu = lambda_u > 0.f ? (float)(2.0 * (double)lambda_u * (double)batch_fraction / ((double)B * (double)D)) : 0.f;
+  const float ci = lambda_i > 0.f ? (float)(2.0 * (double)lambda_i * (double)batch_fraction / ((double)B * (double)D)) : 0.f;
+  const int threads = 256;
+  const int blocks = (int)ceil_div(B * 32, threads);
+  if (N <= 5)
+    loss_slots_vec_kernel<5><<<blocks, threads, 0, s>>>(P, (int)world, cap_u, cap_i, slot_of_u, slot_of_i, cu, ci, (float*)workspace,
+                                                        (int)B, (int)N, (int)D, inv_M);
+  else
+    loss_slots_vec_kernel<8><<<blocks, threads, 0, s>>>(P, (int)world, cap_u, cap_i, slot_of_u, slot_of_i, cu, ci, (float*)workspace,
+                                                        (int)B, (int)N, (int)D, inv_M);
+  TTAM_LAUNCH_CHECK();
+  loss_reduce_kernel<<<1, 1024, 0, s>>>((const float*)workspace, (int)B, inv_M, inv_BD, lambda_u, lambda_i, 1, loss_out);
   TTAM_LAUNCH_CHECK();
   return TTAM_OK;
 }

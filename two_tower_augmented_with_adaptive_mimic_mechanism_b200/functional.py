@@ -448,6 +448,23 @@ def loss_aug_fwd_bwd(t_u, t_i, aug_u, aug_i, users, items, *, mimic=True, lambda
     return loss, do_u, do_i, dq_u, dq_p
 
 
+def loss_slots_fwd_bwd(t_u: list, q_u: list, t_i: list, q_i: list, a_u: list, b_u: list, a_i: list, b_i: list, cap_u: int, cap_i: int,
+                       slot_of_u, slot_of_i, B: int, N: int, D: int, *, lambda_u=0.0, lambda_i=0.0, loss=None, batch_fraction=1.0):
+    """The sharded step's loss with the row exchange folded in (csrc/rows.cu loss_slots_vec_kernel): the eight lists hold one
+    device address per rank (the owners' row buffers and receive buffers, local or NVLink peer mappings)."""
+    _chk(slot_of_u, torch.int64, "slot_of_u"); _chk(slot_of_i, torch.int64, "slot_of_i")
+    dev = slot_of_u.device
+    if loss is None:
+        loss = torch.empty(4, dtype=torch.float32, device=dev)
+    W = len(t_u)
+    ws = workspace(lib().ttam_loss_workspace_bytes(B), dev, "loss")
+    arrs = [_ptr_array(x) for x in (t_u, q_u, t_i, q_i, a_u, b_u, a_i, b_i)]
+    check(lib().ttam_loss_slots_fwd_bwd(*arrs, W, int(cap_u), int(cap_i), slot_of_u.data_ptr(), slot_of_i.data_ptr(), float(lambda_u),
+                                        float(lambda_i), loss.data_ptr(), int(B), int(N), int(D), float(batch_fraction), ws.data_ptr(),
+                                        ws.numel(), _stream()), "loss_slots_fwd_bwd")
+    return loss
+
+
 def inbatch_loss_fwd_bwd(o_u, o_p, *, t_u=None, t_p=None, q_u=None, q_p=None, lambda_u=0.0, lambda_i=0.0, backward=True, out=None,
                          precision="fp32"):
     """In-batch softmax loss (extension; see ttam.h): o_u, o_p [B, D].  Returns (loss[4], do_u, do_p, dq_u, dq_p)."""

@@ -21,11 +21,13 @@ with an oracle-backed engine: tests/test_sharding.py).
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
 import torch.distributed as dist
 
+from . import functional as F
 from . import sharding as S
 
 
@@ -82,8 +84,20 @@ class ShardedEngine:
         S.all_reduce_flat(grads, self.group)
 
     # ---- the step body, shared by both routes ---------------------------------------------------------------------
+    def _fused_slot_loss(self, N: int, D: int) -> bool:
+        eng = self.eng
+        if os.environ.get("TTAM_FUSE_SLOT_LOSS", "1") == "0" or getattr(eng, "loss_kind", "sampled") != "sampled":
+            return False
+        if eng.lambda_c > 0 and eng.cat_tensor is not None and eng.major is not None:
+            return False
+        return F.loss_aug_supported(N, D)
+
     def _body(self, ex_u, ex_i, items, B, N, user_x_shard, item_x_shard):
         eng, W = self.eng, self.world
+        if (isinstance(ex_u, S.SlotExchange) and ex_i.peer is not None and eng.mimic
+                and self._fused_slot_loss(N, eng.user.out_dim)):
+            for ex in (ex_u, ex_i):                # the fused loss writes real slots only: padding slots must read as zero rows
+                ex.recv_a.zero_(); ex.recv_b.zero_()
         ctx = eng._forward_phase(ex_u.local_rows.contiguous(), ex_i.local_rows.contiguous(), user_x_shard, item_x_shard)
         cu, ci = ctx["cu"], ctx["ci"]
         mimic = bool(eng.mimic)
@@ -96,6 +110,17 @@ class ShardedEngine:
                 ex_u.publish(cu.t, cu.q if mimic else None)
                 ex_i.publish(ci.t, ci.q if mimic else None)
                 ex_i.peer_barrier()               # every owner's rows are in place
+            if peer and mimic and self._fused_slot_loss(N, D):
+                # pull, loss and push as ONE kernel: the pair's rows are loaded from their owners and its gradient rows stored
+                # into the owners' receive buffers (zeroed at the start of the step: padding slots keep zero rows)
+                loss = eng._misc("loss", (4,), torch.float32)
+                F.loss_slots_fwd_bwd(ex_u._peer_bases(0), ex_u._peer_bases(1), ex_i._peer_bases(0), ex_i._peer_bases(1),
+                                     ex_u._peer_bases(2), ex_u._peer_bases(3), ex_i._peer_bases(2), ex_i._peer_bases(3),
+                                     ex_u.cap, ex_i.cap, ex_u.slot_of, ex_i.slot_of, B, N, D, lambda_u=eng.lambda_u,
+                                     lambda_i=eng.lambda_i, loss=loss, batch_fraction=bf)
+                ex_i.peer_barrier()               # every requester's gradient rows have landed
+                eng._backward_phase(ctx, ex_u.recv_a, ex_i.recv_a, ex_u.recv_b, ex_i.recv_b, dense_grad_hook=hook)
+                return loss
             if mimic:
                 t_u, q_u, o_u = ex_u.pull(cu.t, cu.q)
                 t_i, q_i, o_i = ex_i.pull(ci.t, ci.q)
