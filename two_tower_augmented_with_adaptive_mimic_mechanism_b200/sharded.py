@@ -94,10 +94,6 @@ class ShardedEngine:
 
     def _body(self, ex_u, ex_i, items, B, N, user_x_shard, item_x_shard):
         eng, W = self.eng, self.world
-        if (isinstance(ex_u, S.SlotExchange) and ex_i.peer is not None and eng.mimic
-                and self._fused_slot_loss(N, eng.user.out_dim)):
-            for ex in (ex_u, ex_i):                # the fused loss writes real slots only: padding slots must read as zero rows
-                ex.recv_a.zero_(); ex.recv_b.zero_()
         ctx = eng._forward_phase(ex_u.local_rows.contiguous(), ex_i.local_rows.contiguous(), user_x_shard, item_x_shard)
         cu, ci = ctx["cu"], ctx["ci"]
         mimic = bool(eng.mimic)
@@ -245,10 +241,17 @@ class ShardedEngine:
         if self.world > 1:                  # every rank takes the same route
             dist.all_reduce(st.flag, op=dist.ReduceOp.MAX, group=self.group)
         st.flag_host.copy_(st.flag, non_blocking=True)
-
-    def _main(self, st: _Static, user_x_shard, item_x_shard):
+        # Queued BEHIND the flag's copy, so that they run while the host reads the flag and launches the main half (the GPU
+        # would idle through that round trip otherwise): the id exchange (valid whatever the flag says - the all-reduce
+        # above has ordered every rank's plan before it) and the zeroing of the receive buffers of the fused loss.
         st.ex_u.exchange_ids()
         st.ex_i.exchange_ids()
+        eng = self.eng
+        if st.ex_i.peer is not None and eng.mimic and self._fused_slot_loss(st.N, eng.user.out_dim):
+            for ex in (st.ex_u, st.ex_i):          # the fused loss writes real slots only: padding slots must read as zero rows
+                ex.recv_a.zero_(); ex.recv_b.zero_()
+
+    def _main(self, st: _Static, user_x_shard, item_x_shard):
         return self._body(st.ex_u, st.ex_i, st.items, st.B, st.N, user_x_shard, item_x_shard)
 
     def _overflowed(self, st: _Static) -> bool:
