@@ -214,6 +214,15 @@ int ttam_bag_linear_wgrad(const int64_t* rowptr, const void* entries, const floa
                           float* db, int64_t H, int64_t F, int accumulate, void* workspace, int64_t workspace_bytes,
                           void* stream);
 
+/* The same weight gradient on the tensor cores (TF32 products, fp32 accumulation; exact fp32 bias gradient): the CSR rows of a
+ * 32-row chunk are expanded into a zeroed shared-memory operand tile and multiplied with tcgen05.mma like a dense x
+ * (csrc/gemm_tma.cu bag_wgrad_tc_kernel).  Returns +1 (not an error) when the shape is not covered - H % 32 != 0, F > 640,
+ * lddw != F - and the caller should use ttam_bag_linear_wgrad. */
+int64_t ttam_bag_linear_wgrad_tc_workspace_bytes(int64_t R, int64_t H, int64_t F);
+int ttam_bag_linear_wgrad_tc(const int64_t* rowptr, const void* entries, const float* tail, int64_t T, int64_t tail_start,
+                             const int64_t* gather, int64_t R, const float* dh, int64_t lddh, float* dw, int64_t lddw, float* db,
+                             int64_t H, int64_t F, int accumulate, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- fused loss forward+backward (training.py:770-803, adaptive_mimic.py:59-68) -------------------
  * o_u[B,D], o_i[(1+N)B,D] (positives first, then negatives row-major [B,N]); t_u,t_p[B,D] base tower
  * outputs, q_u,q_p[B,D] augmentation rows of the positive pairs (all four null when mimic is off).

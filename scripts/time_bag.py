@@ -62,7 +62,9 @@ def main():
         dw, db = torch.empty((H, Fd), device=dev), torch.empty(H, device=dev)
         t_f = alone(lambda: F.bag_linear_fwd(bag, idx, W, b, act="relu", out=hd, round_tf32_out=True))
         t_w = alone(lambda: F.bag_linear_wgrad(bag, idx, dh, dw=dw, db=db))
-        print(f"{side}: R={R} mean nnz {bag.mean_nnz:.1f} (max sparse {bag.max_nnz}, tail {bag.T})  fwd {t_f:.1f} us  wgrad {t_w:.1f} us", flush=True)
+        t_tc = alone(lambda: F.bag_linear_wgrad(bag, idx, dh, dw=dw, db=db, precision="tf32"))
+        print(f"{side}: R={R} mean nnz {bag.mean_nnz:.1f} (max sparse {bag.max_nnz}, tail {bag.T})  fwd {t_f:.1f} us  wgrad {t_w:.1f} us  "
+              f"wgrad on the tensor cores {t_tc:.1f} us", flush=True)
 
 
 if __name__ == "__main__":

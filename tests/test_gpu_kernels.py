@@ -660,6 +660,40 @@ def test_bag_linear_fwd_and_wgrad_match_dense_product(F, R, H, Fd, nnz, tail, ac
     assert torch.equal(dw3, dw) and torch.equal(db3, db)
 
 
+@pytest.mark.parametrize("R,H,Fd,nnz,tail", [(1000, 192, 605, (2, 5), 5), (49152, 192, 605, (2, 5), 5), (8192, 192, 605, (20, 45), 5),
+                                             (333, 96, 200, (0, 3), 0), (4097, 256, 1100, (1, 12), 8), (31, 32, 40, (1, 2), 3)])
+def test_bag_linear_wgrad_tensor_cores_match_dense_product(F, R, H, Fd, nnz, tail):
+    """bag_wgrad_tc_kernel (CSR rows expanded into the tcgen05 operand tile) against the fp64 product dh^T X[idx]: TF32 operand
+    rounding bound per element, exact (fp32) bias gradient, deterministic from run to run, duplicate and out-of-order ids."""
+    rng = np.random.default_rng(R + H)
+    NI = 3000
+    X = np.zeros((NI, Fd), np.float32)
+    for r in range(NI):
+        k = rng.integers(nnz[0], nnz[1] + 1)
+        cols = rng.choice(Fd - tail, size=min(k, Fd - tail), replace=False)
+        X[r, cols] = rng.choice([1.0, 0.5, 1.0 / 3.0, 0.25], size=cols.size).astype(np.float32)
+        if tail:
+            X[r, Fd - tail:] = rng.standard_normal(tail).astype(np.float32)
+    bag = F.BagMatrix.build(dev(X))
+    assert bag is not None
+    idx = dev(rng.integers(0, NI, size=R).astype(np.int64))
+    dh_np = (rng.standard_normal((R, H)) * 1e-2).astype(np.float32)
+    dh = dev(dh_np)
+    dw, db = F.bag_linear_wgrad(bag, idx, dh, precision="tf32")
+    dw2, db2 = F.bag_linear_wgrad(bag, idx, dh, precision="tf32")
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)
+    Xg = X[idx.cpu().numpy()].astype(np.float64)
+    ref = dh_np.astype(np.float64).T @ Xg
+    bound = 2.0 * 2.0 ** -11 * (np.abs(dh_np.astype(np.float64)).T @ np.abs(Xg)) + 1e-7
+    err = np.abs(dw.cpu().numpy().astype(np.float64) - ref)
+    assert (err <= bound).all(), (err.max(), bound[err > bound][:3] if (err > bound).any() else None)
+    np.testing.assert_allclose(db.cpu().numpy(), dh_np.astype(np.float64).sum(0), rtol=2e-5, atol=1e-6)
+    # accumulate into an existing gradient
+    base = torch.ones_like(dw)
+    dw3, _ = F.bag_linear_wgrad(bag, idx, dh, dw=base, db=torch.zeros_like(db), accumulate=True, precision="tf32")
+    np.testing.assert_allclose(dw3.cpu().numpy(), dw.cpu().numpy() + 1.0, rtol=0, atol=2e-7)
+
+
 def test_bag_linear_fwd_dropout_mask_equals_gemm_path(F):
     """Same Philox element numbering as ttam_linear_fwd: the two layer-1 paths drop the same elements for the same
     (seed, offset), so the backward mask (h > 0) of either is valid for both."""

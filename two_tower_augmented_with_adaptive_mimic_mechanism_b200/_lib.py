@@ -137,6 +137,8 @@ SIGNATURES = {
                                       _p, _i32, _p, _i64, _p]),
     "ttam_bag_linear_wgrad": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i32, _p, _i64, _p]),
     "ttam_loss_workspace_bytes": (C.c_int64, [_i64]),
+    "ttam_bag_linear_wgrad_tc_workspace_bytes": (C.c_int64, [_i64, _i64, _i64]),
+    "ttam_bag_linear_wgrad_tc": (C.c_int, [_p, _p, _p, _i64, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i32, _p, _i64, _p]),
     "ttam_loss_fwd_bwd": (C.c_int, [_p, _p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _i64, _i64, _i64, _f, _p, _i64, _p]),
     "ttam_loss_aug_supported": (C.c_int, [_i64, _i64]),
     "ttam_loss_aug_fwd_bwd": (C.c_int, [_p, _p, _p, _i64, _p, _i64, _p, _p, _i32, _f, _f, _p, _p, _p, _p, _p, _i64, _i64, _i64, _f, _p, _i64, _p]),

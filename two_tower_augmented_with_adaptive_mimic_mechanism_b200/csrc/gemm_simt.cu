@@ -333,3 +333,32 @@ extern "C" int ttam_linear_wgrad(const float* dy, int64_t lddy, const float* x, 
   }
   return TTAM_OK;
 }
+
+// ---- bag-form layer 1, weight gradient on the tensor cores (csrc/gemm_tma.cu bag_wgrad_tc_kernel) ---------------------------
+extern "C" int64_t ttam_bag_linear_wgrad_tc_workspace_bytes(int64_t R, int64_t H, int64_t F) {
+  const int64_t s = tma_bag_wgrad_splits(R > 0 ? R : 1, H, F);
+  return align_up((s * H * F + s * H) * (int64_t)sizeof(float), 256) + 256;
+}
+
+// Returns TTAM_OK, an error, or +1 when the shape is not covered (the caller then uses ttam_bag_linear_wgrad).
+extern "C" int ttam_bag_linear_wgrad_tc(const int64_t* rowptr, const void* entries, const float* tail, int64_t T, int64_t tail_start,
+                                        const int64_t* gather, int64_t R, const float* dh, int64_t lddh, float* dw, int64_t lddw,
+                                        float* db, int64_t H, int64_t F, int accumulate, void* workspace, int64_t workspace_bytes,
+                                        void* stream) {
+  TTAM_CHECK_ARG(rowptr && entries && dh && dw && workspace, "bag_linear_wgrad_tc: null pointer");
+  TTAM_CHECK_ARG(T >= 0 && T <= 8 && tail_start + T == F && (T == 0 || tail), "bag_linear_wgrad_tc: bad dense tail");
+  if (R <= 0 || lddw != F) return 1;
+  if (workspace_bytes < ttam_bag_linear_wgrad_tc_workspace_bytes(R, H, F)) {
+    set_error("bag_linear_wgrad_tc: workspace too small");
+    return TTAM_EWORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int splits = tma_bag_wgrad_splits(R, H, F);
+  float* partial_w = (float*)workspace;
+  float* partial_b = partial_w + (int64_t)splits * H * F;
+  int real = 0;
+  const int rc = tma_bag_wgrad_partials(rowptr, entries, tail, T, tail_start, gather, R, dh, lddh, partial_w, db ? partial_b : nullptr, H, F,
+                                        &real, s);
+  if (rc != TTAM_OK) return rc;
+  return launch_splitk_reduce(partial_w, H * F, dw, partial_b, db ? H : 0, db, real, accumulate, s);
+}

@@ -31,4 +31,12 @@ int tma_wgrad_splits(int64_t M, int64_t N, int64_t K);
 int tma_wgrad_partials(const float* dy, int64_t lddy, const float* x, int64_t ldx, float* partial, float* colsum_partial, int64_t M,
                        int64_t N, int64_t K, int* real_splits, int prerounded, cudaStream_t stream);
 
+
+// gemm_tma.cu: the weight gradient of the bag-form layer 1 on the tensor cores (CSR rows expanded into the A stage).  Same
+// partial layout; +1 when the shape is not covered.
+int tma_bag_wgrad_splits(int64_t R, int64_t H, int64_t F);
+int tma_bag_wgrad_partials(const int64_t* rowptr, const void* entries, const float* tail, int64_t T, int64_t tail_start,
+                           const int64_t* gather, int64_t R, const float* dh, int64_t lddh, float* partial, float* colsum_partial,
+                           int64_t H, int64_t F, int* real_splits, cudaStream_t stream);
+
 }  // namespace ttam

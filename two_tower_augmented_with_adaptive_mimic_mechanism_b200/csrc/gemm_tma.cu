@@ -514,6 +514,267 @@ gemm_tf32_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Weight gradient of the BAG-form layer 1 on the tensor cores:  dW1[H, F] = dh[R, H]^T . X[idx][R, F]  with X given as CSR rows
+// + a dense tail (csrc/bag.cu).  Same MMA, descriptors, epilogue and split-K reduce as gemm_tf32_tma_wgrad_kernel; what differs is
+// where the A operand comes from and how the work is cut:
+//   * instead of TMA boxes of a dense x, the four fill warps EXPAND the 32 CSR rows of a chunk into the shared-memory stage:
+//     the handful of entries (and tail values) of a row are scattered straight into the "MN-major, 128-byte swizzle, 32-byte
+//     atom" layout the UMMA descriptor expects (element (feature f, row r) of a 32 x 32 block at byte r*128 + c*16 + (f%4)*4
+//     with the 16-byte chunk c = (((f/4)>>1 ^ (r&3)) << 1) | ((f/4)&1): what TMA produces with SWIZZLE_128B_ATOM_32B).  The
+//     stages are zeroed once; when a stage comes round again each thread writes zeros back to exactly the words it scattered
+//     there, so a chunk costs a few dozen shared-memory stores instead of a pass over the tile.
+//   * a CTA owns ALL feature tiles (m_tiles x 128 features, one TMEM accumulator of bn columns each: m_tiles * bn <= 512) of one
+//     slice of bn hidden columns and one split of the rows: every dh element is fetched and rounded by exactly one CTA, every
+//     CSR row is read by H / bn CTAs.  One CTA per SM.
+//   * the index chain idx -> rowptr of the split's rows is resolved once into shared memory; the entries of chunk c+1 are
+//     fetched into registers while chunk c is scattered (4 threads per row: thread `sub` holds the entries sub, sub+4 and the
+//     tail values sub, sub+4; longer rows take a slow loop).  Values are rounded to TF32 like a dense x.
+// The SIMT kernel this replaces on the tensor-core path (bag_wgrad_kernel: per-entry read-modify-writes of a shared-memory
+// accumulator, 81 us for 49 152 rows) stays the fp32 path.
+struct BagWgP {
+  float* part;     // [splits][N][ldk]
+  float* colsum;   // [splits][N] or null
+  int R, N, K;     // rows, H, F
+  int bn, m_tiles, rows_per_split, stages, b_stages;
+  int ldk;         // row pitch of a partial (floats)
+  const int64_t* rowptr;
+  const int2* ent;
+  const float* tail;
+  int T, tail_start;
+  const int64_t* gather;
+};
+constexpr int kBagMaxRows = 4096;   // rows of a split whose (row, first entry, count) fit the shared-memory table
+constexpr int kBagMaxTiles = 5;     // feature tiles per CTA (F <= 640)
+
+__global__ void __launch_bounds__(kThreadsW, 1)
+bag_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, BagWgP p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nb_atoms = p.bn >> 5;
+  const uint32_t a_bytes = (uint32_t)p.m_tiles * kABytes;        // one A stage: every feature tile of the chunk
+  const uint32_t b_bytes = (uint32_t)nb_atoms * kAtomBytes;      // one B stage: the chunk's dh slice
+  // two rings: A (p.stages deep, big, filled by the fill warps) and B (p.b_stages deep, small, fed by TMA several chunks ahead)
+  uint8_t* ringB = smem + (uint32_t)p.stages * a_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ringB + (uint32_t)p.b_stages * b_bytes);
+  uint64_t* full = bars;                       // [b_stages] dh chunk landed
+  uint64_t* ready = bars + kMaxStages;         // [stages]   A expanded and B rounded: the MMAs of the chunk may go
+  uint64_t* empty = bars + 2 * kMaxStages;     // [stages]   the MMAs that read the A stage have completed
+  uint64_t* acc_full = bars + 3 * kMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * kMaxStages + 4);
+  uint64_t* emptyB = bars + 4 * kMaxStages;    // [b_stages] the MMAs that read the B stage have completed
+  float* tailbuf = reinterpret_cast<float*>(smem);   // epilogue tiles: alias the A ring (free once acc_full has fired)
+  int64_t* row_beg = reinterpret_cast<int64_t*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [rows_per_split] first entry of a row
+  int32_t* row_g = reinterpret_cast<int32_t*>(row_beg + p.rows_per_split);         // [rows_per_split] feature-matrix row
+  int32_t* row_n = row_g + p.rows_per_split;                                       // [rows_per_split] sparse entries of the row
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * p.bn;
+  const int r_lo = blockIdx.y * p.rows_per_split, r_hi = min(p.R, r_lo + p.rows_per_split);
+  const int nchunks = (r_hi - r_lo + kKC - 1) / kKC;
+  const bool want_colsum = p.colsum != nullptr;
+  const uint32_t need_cols = (uint32_t)(p.m_tiles * p.bn);
+  const uint32_t tmem_cols = need_cols <= 32 ? 32u : need_cols <= 64 ? 64u : need_cols <= 128 ? 128u : need_cols <= 256 ? 256u : 512u;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmDy);
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(ready + i, kRoundWarps);
+      mbar_init(empty + i, 1);
+    }
+    for (int i = 0; i < p.b_stages; ++i) {
+      mbar_init(full + i, 1);
+      mbar_init(emptyB + i, 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  // the split's index chain, two global latencies for the whole CTA: idx -> rowptr
+  for (int i = threadIdx.x; i < r_hi - r_lo; i += kThreadsW) {
+    const int64_t g = p.gather ? p.gather[r_lo + i] : (int64_t)(r_lo + i);
+    const int64_t b = p.rowptr[g];
+    row_g[i] = (int32_t)g;
+    row_beg[i] = b;
+    row_n[i] = (int32_t)(p.rowptr[g + 1] - b);
+  }
+  // the A halves of every stage start as zeros (the fill warps keep them so between chunks)
+  for (uint32_t i = threadIdx.x; i < (uint32_t)p.stages * a_bytes / 16; i += kThreadsW)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int c = 0; c < nchunks; ++c) {
+        const int bs = c % p.b_stages;
+        mbar_wait_relaxed(emptyB + bs, ((c / p.b_stages) & 1) ^ 1, 64);
+        uint8_t* sB = ringB + (uint32_t)bs * b_bytes;
+        mbar_expect_tx(full + bs, b_bytes);
+        const int r = r_lo + c * kKC;
+        for (int b = 0; b < nb_atoms; ++b) tma_load_2d(sB + b * kAtomBytes, &tmDy, full + bs, n0 + 32 * b, r);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(2 /*tf32*/, kBM, p.bn, 1, 1);
+      for (int c = 0; c < nchunks; ++c) {
+        const int stage = c % p.stages, bs = c % p.b_stages;
+        mbar_wait(ready + stage, (c / p.stages) & 1);
+        tc_fence_after();
+        const uint32_t sA = smem_u32(smem + (uint32_t)stage * a_bytes);
+        const uint32_t sB = smem_u32(ringB + (uint32_t)bs * b_bytes);
+        for (int tile = 0; tile < p.m_tiles; ++tile) {
+#pragma unroll
+          for (int ks = 0; ks < kKC / 8; ++ks)
+            umma_tf32(tmem_base + (uint32_t)(tile * p.bn), make_mnmajor_desc_tf32(sA + tile * kABytes + ks * 1024, kAtomBytes, 512),
+                      make_mnmajor_desc_tf32(sB + ks * 1024, kAtomBytes, 512), idesc, (c | ks) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty + stage);
+        umma_commit(emptyB + bs);
+      }
+      umma_commit(acc_full);
+    }
+  } else if (warp < 2 + kEpiWarpsW) {
+    // ===================== epilogue: transposed store  part[z][n][m]  through a [32][33] tile per warp =====================
+    const int quad = warp & 3;
+    float* stg = tailbuf + (warp - 2) * (32 * 33);
+    float* Cz = p.part + (int64_t)blockIdx.y * p.N * p.ldk;
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    for (int tile = 0; tile < p.m_tiles; ++tile) {
+      const int m = tile * kBM + quad * 32 + lane;
+      for (int col = 0; col < p.bn; col += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(tile * p.bn + col), r);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = __uint_as_float(r[i]);
+        __syncwarp();
+#pragma unroll 4
+        for (int i = 0; i < 32; ++i) {
+          const int n = n0 + col + i;
+          if (n < p.N && m < p.K) Cz[(int64_t)n * p.ldk + m] = stg[lane * 33 + i];   // lanes = 32 consecutive m: one 128-byte store
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== fill warps: expand the chunk's CSR rows into the A stage; round dh (+ exact column sums) ==========
+    const int t = threadIdx.x - 32 * (2 + kEpiWarpsW);   // 0 .. 127
+    const int crow = t >> 2, sub = t & 3;                 // row of the chunk, which quarter of its entries
+    float4 csum[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) csum[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // entries / tail values of THIS thread for one chunk (held one chunk ahead)
+    int2 e0 = make_int2(-1, 0), e1 = make_int2(-1, 0);
+    float tl0 = 0.f, tl1 = 0.f;
+    int n_row = 0;
+    int64_t beg_row = 0;
+    auto fetch = [&](int c) {
+      e0 = e1 = make_int2(-1, 0);
+      tl0 = tl1 = 0.f;
+      n_row = 0;
+      const int i = c * kKC + crow;
+      if (c < nchunks && r_lo + i < r_hi) {
+        n_row = row_n[i];
+        beg_row = row_beg[i];
+        if (sub < n_row) e0 = p.ent[beg_row + sub];
+        if (sub + 4 < n_row) e1 = p.ent[beg_row + sub + 4];
+        const float* ts = p.tail + (int64_t)row_g[i] * p.T;
+        if (sub < p.T) tl0 = ts[sub];
+        if (sub + 4 < p.T) tl1 = ts[sub + 4];
+      }
+    };
+    // byte offset of element (feature f, chunk row crow) inside the A part of a stage
+    auto where = [&](int f) -> uint32_t {
+      const int tile = f >> 7, fl = f & 127;
+      const int atom = fl >> 5, fi = fl & 31, L = fi >> 2;
+      const int ch = ((((L >> 1) ^ (crow & 3)) << 1) | (L & 1));
+      return (uint32_t)(tile * (int)kABytes + atom * (int)kAtomBytes + crow * 128 + ch * 16 + (fi & 3) * 4);
+    };
+    // what this thread scattered into each stage last time (to be zeroed when the stage comes round): 4 words + the slow rows
+    uint32_t mine[kMaxStages > 4 ? 4 : kMaxStages][4];
+    int slow_n[4];
+    int64_t slow_beg[4];
+#pragma unroll
+    for (int sidx = 0; sidx < 4; ++sidx) {
+      slow_n[sidx] = 0; slow_beg[sidx] = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) mine[sidx][k] = 0xFFFFFFFFu;
+    }
+    fetch(0);
+    for (int c = 0; c < nchunks; ++c) {
+      const int stage = c % p.stages;
+      // this chunk's values move out of the prefetch registers; the next chunk's loads go out before anything waits
+      const int2 a0 = e0, a1 = e1;
+      const float u0 = tl0, u1 = tl1;
+      const int n_cur = n_row;
+      const int64_t beg_cur = beg_row;
+      const bool row_ok = c * kKC + crow < r_hi - r_lo;
+      fetch(c + 1);
+      mbar_wait(empty + stage, ((c / p.stages) & 1) ^ 1);   // the MMAs that read this stage last time have completed
+      uint8_t* sA = smem + (uint32_t)stage * a_bytes;
+      // zeros back into the words this thread set in this stage p.stages chunks ago (nobody else touched them), then this chunk
+#pragma unroll
+      for (int sidx = 0; sidx < 4; ++sidx) {
+        if (sidx == stage) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (mine[sidx][k] != 0xFFFFFFFFu) *reinterpret_cast<uint32_t*>(sA + mine[sidx][k]) = 0u;
+            mine[sidx][k] = 0xFFFFFFFFu;
+          }
+          for (int k = sub + 8; k < slow_n[sidx]; k += 4) *reinterpret_cast<uint32_t*>(sA + where(p.ent[slow_beg[sidx] + k].x)) = 0u;
+          slow_n[sidx] = n_cur; slow_beg[sidx] = beg_cur;
+          if (a0.x >= 0 && a0.x < p.K) { mine[sidx][0] = where(a0.x); *reinterpret_cast<uint32_t*>(sA + mine[sidx][0]) = to_tf32(__int_as_float(a0.y)) & 0xFFFFE000u; }
+          if (a1.x >= 0 && a1.x < p.K) { mine[sidx][1] = where(a1.x); *reinterpret_cast<uint32_t*>(sA + mine[sidx][1]) = to_tf32(__int_as_float(a1.y)) & 0xFFFFE000u; }
+          if (row_ok && sub < p.T) { mine[sidx][2] = where(p.tail_start + sub); *reinterpret_cast<uint32_t*>(sA + mine[sidx][2]) = to_tf32(u0) & 0xFFFFE000u; }
+          if (row_ok && sub + 4 < p.T) { mine[sidx][3] = where(p.tail_start + sub + 4); *reinterpret_cast<uint32_t*>(sA + mine[sidx][3]) = to_tf32(u1) & 0xFFFFE000u; }
+        }
+      }
+      for (int k = sub + 8; k < n_cur; k += 4) {            // rows with more than 8 sparse entries (not on the fast path)
+        const int2 e = p.ent[beg_cur + k];
+        if (e.x >= 0 && e.x < p.K) *reinterpret_cast<uint32_t*>(sA + where(e.x)) = to_tf32(__int_as_float(e.y)) & 0xFFFFE000u;
+      }
+      // B: round dh to TF32 in place (+ exact column sums for the bias gradient), as in gemm_tf32_tma_wgrad_kernel
+      const int bs = c % p.b_stages;
+      mbar_wait(full + bs, (c / p.b_stages) & 1);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (i < 2 * nb_atoms) {
+          uint4* q = reinterpret_cast<uint4*>(ringB + (uint32_t)bs * b_bytes) + t + 128 * i;
+          const float4 v = *reinterpret_cast<float4*>(q);
+          if (want_colsum) { csum[i >> 1].x += v.x; csum[i >> 1].y += v.y; csum[i >> 1].z += v.z; csum[i >> 1].w += v.w; }
+          *q = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ready + stage);
+    }
+    if (want_colsum) {
+      mbar_wait(acc_full, 0);   // every MMA has read the stages: the ring memory is free
+      float4* red = reinterpret_cast<float4*>(ringB);   // [128 threads][8 blocks]: the B ring is free (the epilogue uses the A ring)
+#pragma unroll
+      for (int b = 0; b < 8; ++b) red[t * 8 + b] = csum[b];
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kRoundWarps) : "memory");
+      for (int n = t; n < p.bn; n += 32 * kRoundWarps) {
+        const int b = n >> 5, want = (n & 31) >> 2, comp = n & 3;
+        float sacc = 0.f;
+        for (int u = 0; u < 32 * kRoundWarps; ++u) {
+          const int cu = ((((u & 7) >> 1) ^ ((u >> 3) & 3)) << 1) | (u & 1);
+          if (cu == want) sacc += reinterpret_cast<const float*>(red + u * 8 + b)[comp];
+        }
+        if (n0 + n < p.N) p.colsum[(int64_t)blockIdx.y * p.N + n0 + n] = sacc;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 }  // namespace tma
@@ -616,6 +877,70 @@ int tma_wgrad_partials(const float* dy, int64_t lddy, const float* x, int64_t ld
   }
   dim3 grid((unsigned)(p.m_tiles * nt), (unsigned)*real_splits);
   gemm_tf32_tma_wgrad_kernel<<<grid, kThreadsW, smem, stream>>>(tmX, tmDy, p);
+  TTAM_LAUNCH_CHECK();
+  return TTAM_OK;
+}
+
+// Cut of the bag-form weight gradient: every CTA owns all feature tiles (m_tiles accumulators of bn TMEM columns), one slice of bn
+// hidden columns and one split of the rows; one CTA per SM.
+static bool bag_wgrad_cut(int64_t R, int64_t H, int64_t F, int* bn, int* n_tiles, int* splits) {
+  const int64_t m_tiles = ceil_div(F, kBM);
+  if (m_tiles > kBagMaxTiles || H % 32 || H <= 0) return false;
+  int64_t w = (512 / m_tiles) / 32 * 32;
+  if (w > 256) w = 256;
+  if (w > H) w = H;
+  if (w < 32) return false;
+  *bn = (int)w;
+  *n_tiles = (int)ceil_div(H, w);
+  int64_t s = num_sms() / *n_tiles;
+  const int64_t by_rows = ceil_div(R, 64);
+  if (s > by_rows) s = by_rows;
+  if (s < 1) s = 1;
+  while (align_up(ceil_div(R, s), kKC) > kBagMaxRows) ++s;
+  *splits = (int)s;
+  return true;
+}
+int tma_bag_wgrad_splits(int64_t R, int64_t H, int64_t F) {
+  int bn, nt, s;
+  return bag_wgrad_cut(R, H, F, &bn, &nt, &s) ? s : 1;
+}
+
+// part[z][H][F] (and colsum[z][H]) for z < *real_splits.  +1: shape not covered (the caller keeps the SIMT bag kernel).
+int tma_bag_wgrad_partials(const int64_t* rowptr, const void* entries, const float* tail, int64_t T, int64_t tail_start,
+                           const int64_t* gather, int64_t R, const float* dh, int64_t lddh, float* partial, float* colsum_partial,
+                           int64_t H, int64_t F, int* real_splits, cudaStream_t stream) {
+  if (!aligned16(dh) || lddh % 4 || R <= 0 || F <= 0 || T < 0 || T > 8) return 1;
+  if (getenv("TTAM_NO_TMA_GEMM") || getenv("TTAM_NO_BAG_TC")) return 1;
+  BagWgP p{};
+  int n_tiles = 1, splits = 1;
+  if (!bag_wgrad_cut(R, H, F, &p.bn, &n_tiles, &splits)) return 1;
+  p.part = partial; p.colsum = colsum_partial; p.R = (int)R; p.N = (int)H; p.K = (int)F;
+  p.m_tiles = (int)ceil_div(F, kBM);
+  p.ldk = (int)F;   // (a 32-float row pitch - aligned 128-byte stores - was measured: no faster, and it needs its own reduce kernel)
+  p.rows_per_split = (int)align_up(ceil_div(R, splits), kKC);
+  *real_splits = (int)ceil_div(R, p.rows_per_split);
+  p.rowptr = rowptr; p.ent = (const int2*)entries; p.tail = tail; p.T = (int)T; p.tail_start = (int)tail_start; p.gather = gather;
+  const size_t a_bytes = (size_t)p.m_tiles * kABytes, b_bytes = (size_t)(p.bn / 32) * kAtomBytes;
+  const size_t fixed = 1024 + 512 + (size_t)p.rows_per_split * 16;
+  p.stages = 2;
+  if (p.stages * a_bytes < (size_t)kEpiWarpsW * 32 * 33 * 4) return 1;   // the epilogue tiles alias the A ring
+  // the B ring takes what is left (dh chunks several chunks ahead of the MMAs; its 16 kB floor also holds the column-sum reduction)
+  int64_t bst = ((int64_t)220 * 1024 - (int64_t)fixed - (int64_t)(p.stages * a_bytes)) / (int64_t)b_bytes;
+  if (bst > kMaxStages) bst = kMaxStages;
+  if (bst < 2 || (size_t)bst * b_bytes < (size_t)128 * 8 * 16) return 1;
+  p.b_stages = (int)bst;
+  const size_t smem = (size_t)p.stages * a_bytes + (size_t)p.b_stages * b_bytes + fixed;
+  CUtensorMap tmDy;
+  int rc = make_tmap_2d(&tmDy, dh, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)R, (uint64_t)H, (uint64_t)lddh * 4, 32, 32,
+                        CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+  if (rc != TTAM_OK) return rc;
+  static bool attr_done = false;
+  if (!attr_done) {
+    TTAM_CUDA(cudaFuncSetAttribute(bag_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_done = true;
+  }
+  dim3 grid((unsigned)n_tiles, (unsigned)*real_splits);
+  bag_wgrad_tc_kernel<<<grid, kThreadsW, smem, stream>>>(tmDy, p);
   TTAM_LAUNCH_CHECK();
   return TTAM_OK;
 }

@@ -3,6 +3,7 @@
 // and their autograd).  Nothing new is computed here; the point is host-side: an eager step (the row-sharded N-GPU
 // step, the training hooks) makes ~10 C calls instead of ~85, so the CPU stays ahead of the GPU.
 #include "common.cuh"
+#include <algorithm>
 
 using namespace ttam;
 
@@ -61,7 +62,8 @@ extern "C" int64_t ttam_tower_bwd_workspace_bytes(const ttam_tower_desc* d, int6
   if (!d || R <= 0) return 256;
   int64_t m = ttam_linear_wgrad_workspace_bytes(R, d->D, d->Hg);
   const int64_t c[3] = {ttam_linear_wgrad_workspace_bytes(R, d->Hg, 2 * d->D), ttam_linear_wgrad_workspace_bytes(R, d->D, d->H),
-                        (d->bag_rowptr && d->bag_wgrad) ? ttam_bag_linear_workspace_bytes(R, d->H, d->F) : ttam_linear_wgrad_workspace_bytes(R, d->H, d->F)};
+                        (d->bag_rowptr && d->bag_wgrad) ? std::max(ttam_bag_linear_workspace_bytes(R, d->H, d->F), ttam_bag_linear_wgrad_tc_workspace_bytes(R, d->H, d->F))
+                                                        : ttam_linear_wgrad_workspace_bytes(R, d->H, d->F)};
   for (int i = 0; i < 3; ++i) m = c[i] > m ? c[i] : m;
   return m;
 }
@@ -110,6 +112,14 @@ extern "C" int ttam_tower_bwd(const ttam_tower_desc* d, const int64_t* idx, int6
                                           prec | ((bag && tc) ? TTAM_PREC_X_ROUNDED : 0), stream));
     if (!wg(3)) {
     } else if (bag && d->bag_wgrad) {
+      // tensor-core path: the CSR rows expanded into the MMA operand tile (TF32, like the other weight gradients of the step);
+      // +1 = shape not covered -> the fp32 SIMT scatter kernel
+      int rc = 1;
+      if (tc && workspace_bytes >= ttam_bag_linear_wgrad_tc_workspace_bytes(R, H, F))
+        rc = ttam_bag_linear_wgrad_tc(d->bag_rowptr, d->bag_entries, d->bag_tail, d->bag_T, d->bag_tail_start, idx, R, g->dhd, H, g->dW1, F,
+                                      g->db1, H, F, acc, workspace, workspace_bytes, stream);
+      if (rc < 0) return rc;
+      if (rc == 1)
       TTAM_TRY(ttam_bag_linear_wgrad(d->bag_rowptr, d->bag_entries, d->bag_tail, d->bag_T, d->bag_tail_start, d->bag_max_nnz, idx, R, g->dhd, H,
                                      g->dW1, F, g->db1, H, F, acc, workspace, workspace_bytes, stream));
     } else {

@@ -312,8 +312,10 @@ def bag_linear_fwd(bag: BagMatrix, gather, w, bias=None, *, act="none", out=None
     return out
 
 
-def bag_linear_wgrad(bag: BagMatrix, gather, dh, *, dw=None, db=None, accumulate=False, want_bias=True):
-    """dw[h, j] (+)= sum_r dh[r, h] X[gather[r], j];  db[h] (+)= sum_r dh[r, h].  Deterministic."""
+def bag_linear_wgrad(bag: BagMatrix, gather, dh, *, dw=None, db=None, accumulate=False, want_bias=True, precision="fp32"):
+    """dw[h, j] (+)= sum_r dh[r, h] X[gather[r], j];  db[h] (+)= sum_r dh[r, h].  Deterministic.
+    precision="tf32": the tensor-core kernel (CSR rows expanded into the MMA operand tile; TF32 products, exact fp32 bias
+    gradient) where the shape is covered, else - and for "fp32" - the fp32 scatter kernel."""
     _chk(dh, torch.float32, "dh")
     dp, lddh = _rows2d(dh, "dh")
     R, H = dh.shape
@@ -324,6 +326,15 @@ def bag_linear_wgrad(bag: BagMatrix, gather, dh, *, dw=None, db=None, accumulate
     if db is None and want_bias:
         db = torch.empty((H,), dtype=torch.float32, device=dh.device)
     L = lib()
+    if precision == "tf32" and R > 0:
+        ws = workspace(L.ttam_bag_linear_wgrad_tc_workspace_bytes(R, H, Fd), dh.device, "bag")
+        rc = L.ttam_bag_linear_wgrad_tc(bag.rowptr.data_ptr(), bag.entries.data_ptr(), _ptr(bag.tail), bag.T, bag.tail_start, _ptr(gather), R,
+                                        dp, lddh, dw.data_ptr(), dw.stride(0), _ptr(db), H, Fd, 1 if accumulate else 0, ws.data_ptr(),
+                                        ws.numel(), _stream())
+        if rc == 0:
+            return dw, db
+        if rc != 1:
+            check(rc, "bag_linear_wgrad_tc")
     ws = workspace(L.ttam_bag_linear_workspace_bytes(R, H, Fd), dh.device, "bag")
     check(L.ttam_bag_linear_wgrad(bag.rowptr.data_ptr(), bag.entries.data_ptr(), _ptr(bag.tail), bag.T, bag.tail_start, bag.max_nnz, _ptr(gather), R,
                                   dp, lddh, dw.data_ptr(), dw.stride(0), _ptr(db), H, Fd, 1 if accumulate else 0, ws.data_ptr(),
