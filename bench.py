@@ -203,7 +203,8 @@ def kernel_function(name: str, precision: str) -> str:
         return "gemm_tf32_kernel (gemm_tc.cu)" if tc else "gemm_f32_kernel (gemm_simt.cu)"
     if n.startswith("gemm"):
         return "gemm_tf32_tma_kernel (gemm_tma.cu)" if tc else "gemm_f32_kernel (gemm_simt.cu)"
-    for key, fn in (("bag_fwd", "bag_fwd_kernel (bag.cu)"), ("bag_wgrad", "bag_wgrad_kernel + reduce (bag.cu)"), ("gather_rows", "gather_rows_kernel (rows.cu)"),
+    for key, fn in (("bag_fwd", "bag_fwd_kernel (bag.cu)"), ("bag_wgrad_tc", "bag_wgrad_tc_kernel + splitk_reduce (gemm_tma.cu)"),
+                    ("bag_wgrad", "bag_wgrad_kernel + reduce (bag.cu)"), ("gather_rows", "gather_rows_kernel (rows.cu)"),
                     ("gate_fwd", "gate_fwd_vec_kernel (rows.cu)"), ("gate_bwd", "gate_bwd_vec_kernel (rows.cu)"), ("loss_aug", "loss_aug_vec_kernel (rows.cu)"),
                     ("loss_fwd", "loss_vec_kernel (rows.cu)"), ("inbatch", "inbatch loss (inbatch.cu + GEMMs)"), ("sort_rows", "cub::DeviceRadixSort + find_long_segments"),
                     ("sparse_adam", "sparse_adam_rows_kernel (optim.cu)"), ("lazy_catchup", "lazy_catchup_kernel (optim.cu)"), ("lazy_rows", "lazy_rows_kernel (optim.cu)")):
@@ -334,8 +335,12 @@ def time_kernel_classes(eng, F, c, dev, users, pos, neg, user_x, item_x, nu_l, n
     add("gemm gate 1 wgrad", lambda: F.linear_wgrad(dpre1, z, precision=precision), R * (Hg + 2 * D) * 4, 2.0 * R * 2 * D * Hg)
     add("gemm layer 2 wgrad", lambda: F.linear_wgrad(dz[:, D:], hd, precision=precision, x_rounded=tc and bag is not None), R * (D + H) * 4, 2.0 * R * H * D)
     if bag is not None:
-        add("bag_wgrad: layer 1 weight gradient (deterministic column-owner scatter)", lambda: F.bag_linear_wgrad(bag, idx, dhd),
-            R * (row_bytes + H * 4), 2.0 * R * (nnz + bag.T) * H, smem_operand_bytes=int(R * w_rows))
+        if tc:   # what ttam_tower_bwd launches on the tensor-core path: CSR rows expanded into the tcgen05 operand tile (+ split-K reduce)
+            add("bag_wgrad_tc: layer 1 weight gradient, CSR rows expanded into the MMA operand tile + split-K reduce",
+                lambda: F.bag_linear_wgrad(bag, idx, dhd, precision="tf32"), R * (row_bytes + H * 4), 2.0 * R * Fd * H)
+        else:
+            add("bag_wgrad: layer 1 weight gradient (deterministic column-owner scatter)", lambda: F.bag_linear_wgrad(bag, idx, dhd),
+                R * (row_bytes + H * 4), 2.0 * R * (nnz + bag.T) * H, smem_operand_bytes=int(R * w_rows))
     else:
         add("gemm layer 1 wgrad: dh^T . X[idx]", lambda: F.linear_wgrad(dhd, Xi, gather=idx, precision=precision, x_rounded=tc),
             R * (Fd * 4 + 8 + H * 4) + H * Fd * 4, 2.0 * R * Fd * H)

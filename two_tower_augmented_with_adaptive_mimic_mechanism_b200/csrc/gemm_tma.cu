@@ -444,11 +444,16 @@ gemm_tf32_tma_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid
 #pragma unroll
       for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = __uint_as_float(r[i]);
       __syncwarp();
+      // lanes = 32 consecutive m: one 128-byte store per output row n; address and bounds hoisted out of the row loop (with
+      // them inside, the loop body was ~70 instructions and the epilogue of a 128 x 96 tile took ~7 us of a ~20 us CTA)
       const int m = m0 + quad * 32 + lane;
-#pragma unroll 4
-      for (int i = 0; i < 32; ++i) {
-        const int n = n0 + col + i;
-        if (n < p.N && m < p.K) Cz[(int64_t)n * p.K + m] = stg[lane * 33 + i];   // lanes = 32 consecutive m: one 128-byte store
+      const int rows = min(32, p.N - (n0 + col));
+      if (m < p.K) {
+        float* dst = Cz + (int64_t)(n0 + col) * p.K + m;
+        const float* srow = stg + lane * 33;
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i)
+          if (i < rows) dst[(int64_t)i * p.K] = srow[i];
       }
       __syncwarp();
     }
@@ -651,10 +656,13 @@ bag_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, BagWgP p) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = __uint_as_float(r[i]);
         __syncwarp();
-#pragma unroll 4
-        for (int i = 0; i < 32; ++i) {
-          const int n = n0 + col + i;
-          if (n < p.N && m < p.K) Cz[(int64_t)n * p.ldk + m] = stg[lane * 33 + i];   // lanes = 32 consecutive m: one 128-byte store
+        const int rows = min(32, p.N - (n0 + col));
+        if (m < p.K) {   // lanes = 32 consecutive m: one 128-byte store per output row n
+          float* dst = Cz + (int64_t)(n0 + col) * p.ldk + m;
+          const float* srow = stg + lane * 33;
+#pragma unroll 8
+          for (int i = 0; i < 32; ++i)
+            if (i < rows) dst[(int64_t)i * p.ldk] = srow[i];
         }
         __syncwarp();
       }
@@ -703,16 +711,23 @@ bag_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, BagWgP p) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) mine[sidx][k] = 0xFFFFFFFFu;
     }
+    // two chunks ahead: the loads of chunk c+2 go out while chunk c is expanded (one chunk ahead the loop stalled ~0.5 us per
+    // chunk on them - globaltimer trace of the first version)
     fetch(0);
+    int2 n0e = e0, n1e = e1;
+    float nt0 = tl0, nt1 = tl1;
+    int nn_row = n_row;
+    int64_t nbeg_row = beg_row;
+    fetch(1);
     for (int c = 0; c < nchunks; ++c) {
       const int stage = c % p.stages;
-      // this chunk's values move out of the prefetch registers; the next chunk's loads go out before anything waits
-      const int2 a0 = e0, a1 = e1;
-      const float u0 = tl0, u1 = tl1;
-      const int n_cur = n_row;
-      const int64_t beg_cur = beg_row;
+      const int2 a0 = n0e, a1 = n1e;
+      const float u0 = nt0, u1 = nt1;
+      const int n_cur = nn_row;
+      const int64_t beg_cur = nbeg_row;
       const bool row_ok = c * kKC + crow < r_hi - r_lo;
-      fetch(c + 1);
+      n0e = e0; n1e = e1; nt0 = tl0; nt1 = tl1; nn_row = n_row; nbeg_row = beg_row;   // chunk c+1 (loaded during chunk c-1)
+      fetch(c + 2);
       mbar_wait(empty + stage, ((c / p.stages) & 1) ^ 1);   // the MMAs that read this stage last time have completed
       uint8_t* sA = smem + (uint32_t)stage * a_bytes;
       // zeros back into the words this thread set in this stage p.stages chunks ago (nobody else touched them), then this chunk
@@ -740,12 +755,20 @@ bag_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, BagWgP p) {
       const int bs = c % p.b_stages;
       mbar_wait(full + bs, (c / p.b_stages) & 1);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        if (i < 2 * nb_atoms) {
-          uint4* q = reinterpret_cast<uint4*>(ringB + (uint32_t)bs * b_bytes) + t + 128 * i;
-          const float4 v = *reinterpret_cast<float4*>(q);
-          if (want_colsum) { csum[i >> 1].x += v.x; csum[i >> 1].y += v.y; csum[i >> 1].z += v.z; csum[i >> 1].w += v.w; }
-          *q = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+      for (int i0 = 0; i0 < 16; i0 += 4) {      // four 16-byte pieces per round: the loads of a round go out together
+        if (i0 < 2 * nb_atoms) {
+          uint4* q = reinterpret_cast<uint4*>(ringB + (uint32_t)bs * b_bytes) + t + 128 * i0;
+          float4 v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            v[j] = (i0 + j < 2 * nb_atoms) ? *reinterpret_cast<float4*>(q + 128 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (i0 + j < 2 * nb_atoms) {
+              if (want_colsum) { csum[(i0 + j) >> 1].x += v[j].x; csum[(i0 + j) >> 1].y += v[j].y; csum[(i0 + j) >> 1].z += v[j].z; csum[(i0 + j) >> 1].w += v[j].w; }
+              q[128 * j] = make_uint4(to_tf32(v[j].x), to_tf32(v[j].y), to_tf32(v[j].z), to_tf32(v[j].w));
+            }
+          }
         }
       }
       fence_proxy_async_smem();
