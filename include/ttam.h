@@ -390,7 +390,7 @@ int ttam_slot_pack(const float* a, const float* b0, int64_t n0, const float* b1,
  * (descending score, ascending id on ties).  Scores returned are the canonical fp32 scores
  * (sequential accumulation over d).  id_offset is added to every returned id (item-sharded corpora).
  *   ttam_topk_f32 : fp32 operands, SIMT                       (drop-in for the fp32 FAISS path)
- *   ttam_topk_bf16: bf16 operands, TMA-fed tcgen05 GEMM with an in-kernel threshold top-K epilogue,
+ *   ttam_topk_bf16: bf16 operands (D <= 256, K <= 128), TMA-fed tcgen05 GEMM with an in-kernel threshold top-K epilogue,
  *                   followed by an exact re-score + (-score,+id) sort of the survivors
  *   ttam_topk_merge: merge `parts` partial lists per query (item shards) under the same order */
 int64_t ttam_topk_f32_workspace_bytes(int64_t Q, int64_t N, int64_t D, int64_t K);
@@ -412,6 +412,19 @@ int64_t ttam_topk_bf16_workspace_bytes(int64_t Q, int64_t N, int64_t D, int64_t 
 int ttam_topk_bf16(const uint16_t* q, const uint16_t* items, int64_t Q, int64_t N, int64_t D, int64_t K,
                    int64_t id_offset, int64_t* out_ids, float* out_scores, void* workspace,
                    int64_t workspace_bytes, void* stream);
+/* fp32 index on the tensor cores (faiss.IndexFlatIP over fp32 embeddings, training.py:646-679, 944-958; K <= 128,
+ * D <= 256): the candidate pass runs the bf16 tcgen05 kernel over a 3-way bf16 split of both operands
+ * (x = hi + lo + r; queries laid out [hi | lo | hi], items [hi | hi | lo], each part padded to a multiple of 16 columns,
+ * so one product over ttam_split_bf16x3_cols(D) columns is qh.xh + ql.xh + qh.xl), the survivors within the proven error
+ * bound of the K-th score are re-scored from the fp32 rows in the canonical order.  Ids and scores are bit-identical to
+ * ttam_topk_f32.  The caller keeps `items_split` next to the corpus (ttam_split_bf16x3 once per index build, item_layout = 1)
+ * and splits each query batch (item_layout = 0). */
+int64_t ttam_split_bf16x3_cols(int64_t D);
+int ttam_split_bf16x3(const float* x, int64_t R, int64_t D, int item_layout, uint16_t* out, void* stream);
+int64_t ttam_topk_f32_tc_workspace_bytes(int64_t Q, int64_t N, int64_t D, int64_t K);
+int ttam_topk_f32_tc(const float* q, const float* items, const uint16_t* q_split, const uint16_t* items_split,
+                     int64_t Q, int64_t N, int64_t D, int64_t K, int64_t id_offset, int64_t* out_ids,
+                     float* out_scores, void* workspace, int64_t workspace_bytes, void* stream);
 int ttam_topk_merge(const int64_t* ids, const float* scores, int64_t Q, int64_t parts, int64_t K_in,
                     int64_t K_out, int64_t* out_ids, float* out_scores, void* stream);
 

@@ -57,7 +57,8 @@ def test_topk_merge_equals_unsharded(tt):
 
 
 @pytest.mark.parametrize("name,cosine", [("train_gated_mlp", False), ("train_gated_mlp_cosine", True)])
-def test_eval_path_matches_reference_golden(tt, name, cosine):
+def test_eval_path_matches_reference_golden(tt, name, cosine, monkeypatch):
+    monkeypatch.setattr(tt.hooks.OPTIONS, "precision", "fp32")     # the goldens are fp32; the hooks' default engine is tf32
     d, meta, _ = load_case(name)
     state = state_after(d, meta["steps"] - 1)
     model = build_model(meta, TRAIN_CASES[name], state, "cuda")
@@ -197,3 +198,109 @@ def test_flat_ip_index_bf16(tt):
     ids, sc = idx.search(q, 10)
     ref = oracle.topk_canonical(oracle.canonical_scores(q.bfloat16().float().cpu().numpy(), emb.bfloat16().float().cpu().numpy()), 10)[0]
     assert np.array_equal(ids.cpu().numpy(), ref)
+
+
+# ---------------------------------------------------------------------------------------------
+# D up to 256 on the tcgen05 path (BASELINE config 4 is 256-dim): the box-ring variant of the kernel
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("Q,N,D,K", [(300, 5000, 256, 100), (130, 30001, 256, 100), (130, 9000, 192, 128), (33, 2000, 144, 50),
+                                     (140, 60000, 256, 100)])
+def test_topk_bf16_tensor_core_wide_rows(tt, Q, N, D, K):
+    q, items = _bf16_case(Q, N, D, N + D)
+    items[N // 2] = items[N // 3]
+    items[N - 1] = items[0]
+    ids, scores = tt.functional.topk(q.cuda(), items.cuda(), K, id_offset=7)
+    ref_s = oracle.canonical_scores(q.float().numpy(), items.float().numpy())
+    ref_i, ref_v = oracle.topk_canonical(ref_s, K)
+    assert np.array_equal(ids.cpu().numpy(), ref_i + 7)
+    assert np.array_equal(scores.cpu().numpy(), ref_v)
+
+
+def test_topk_bf16_box_ring_equals_tile_ring(tt, monkeypatch):
+    """The same D = 96 search through both shapes of the item ring (TTAM_TOPK_RING forces the box ring)."""
+    q, items = _bf16_case(700, 150000, 96, 5)
+    a_i, a_s = tt.functional.topk(q.cuda(), items.cuda(), 100)
+    monkeypatch.setenv("TTAM_TOPK_RING", "1")
+    b_i, b_s = tt.functional.topk(q.cuda(), items.cuda(), 100)
+    assert torch.equal(a_i, b_i) and torch.equal(a_s, b_s)
+
+
+# ---------------------------------------------------------------------------------------------
+# fp32 index with the candidate pass on the tensor cores (3-way bf16 split): bit-exact fp32 ids and scores
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("Q,N,D,K", [(300, 5000, 96, 100), (1, 300, 96, 100), (257, 70001, 96, 100), (64, 4096, 64, 10),
+                                     (130, 9000, 128, 128), (40, 3000, 40, 50), (33, 2000, 8, 100), (100, 30000, 256, 100),
+                                     (260, 100000, 96, 100)])
+def test_topk_f32_tensor_core_candidates_bit_exact(tt, Q, N, D, K):
+    rng = np.random.default_rng(N + D)
+    q = rng.standard_normal((Q, D)).astype(np.float32)
+    items = rng.standard_normal((N, D)).astype(np.float32)
+    items[N // 2] = items[N // 3]                      # exact duplicates -> ties broken by id
+    items[N - 1] = items[0]
+    dq, di = torch.from_numpy(q).cuda(), torch.from_numpy(items).cuda()
+    split = tt.functional.split_bf16x3(di, item_layout=True)
+    ids, scores = tt.functional.topk_f32_tc(dq, di, split, K, id_offset=1000)
+    ref_i, ref_v = oracle.topk_canonical(oracle.canonical_scores(q, items), K)
+    assert np.array_equal(ids.cpu().numpy(), ref_i + 1000)
+    assert np.array_equal(scores.cpu().numpy(), ref_v)
+
+
+def test_topk_f32_tensor_core_normalised_rows_and_near_ties(tt):
+    """Cosine-style corpus (unit rows, scores packed into [-1, 1]) with clusters of near-duplicates whose scores differ
+    only below bf16 resolution: the split keeps them apart or the re-score / exact fallback does."""
+    rng = np.random.default_rng(11)
+    Q, N, D, K = 200, 60000, 96, 100
+    items = rng.standard_normal((N, D)).astype(np.float32)
+    items[1000:1200] = items[999] + 1e-4 * rng.standard_normal((200, D)).astype(np.float32)
+    items /= np.linalg.norm(items, axis=1, keepdims=True)
+    q = rng.standard_normal((Q, D)).astype(np.float32)
+    q[:20] = items[999] + 0.05 * rng.standard_normal((20, D)).astype(np.float32)      # queries that land in the cluster
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    idx = tt.retrieval.FlatIPIndex(torch.from_numpy(items).cuda())
+    ids, scores = idx.search(torch.from_numpy(q).cuda(), K)
+    assert idx._items_split is not None                # the tensor-core path ran
+    ref_i, ref_v = oracle.topk_canonical(oracle.canonical_scores(q, items), K)
+    assert np.array_equal(ids.cpu().numpy(), ref_i)
+    assert np.array_equal(scores.cpu().numpy(), ref_v)
+    simt = tt.retrieval.FlatIPIndex(torch.from_numpy(items).cuda(), tensor_cores=False)
+    s_i, s_s = simt.search(torch.from_numpy(q).cuda(), K)
+    assert torch.equal(s_i, ids) and torch.equal(s_s, scores)
+
+
+def test_topk_f32_deep_and_paged(tt):
+    """K = 1024 in one call (pending-list select kernel) and a 2500-deep ranking walked page by page."""
+    rng = np.random.default_rng(5)
+    Q, N, D = 9, 30000, 32
+    q = rng.standard_normal((Q, D)).astype(np.float32)
+    items = np.round(rng.standard_normal((N, D)) * 4).astype(np.float32) / 4          # coarse values: exact ties
+    ref_i, ref_v = oracle.topk_canonical(oracle.canonical_scores(q, items), 2500)
+    idx = tt.retrieval.FlatIPIndex(torch.from_numpy(items).cuda())
+    ids, scores = idx.search(torch.from_numpy(q).cuda(), 1024)
+    assert np.array_equal(ids.cpu().numpy(), ref_i[:, :1024]) and np.array_equal(scores.cpu().numpy(), ref_v[:, :1024])
+    d_i, d_s = idx.search_deep(torch.from_numpy(q).cuda(), 2500)
+    assert np.array_equal(d_i, ref_i) and np.array_equal(d_s, ref_v)
+
+
+def test_evaluate_users_heavy_users_match_the_per_user_filter(tt):
+    """Users whose blocked set is far larger than one launch returns (search_k = max_k + |gt| + |blocked|,
+    training.py:956-958), next to ordinary ones: predictions equal the reference's filter applied to the full ranking."""
+    rng = np.random.default_rng(21)
+    NU, NI, D, max_k = 40, 6000, 32, 20
+    items = rng.standard_normal((NI, D)).astype(np.float32)
+    users = rng.standard_normal((NU, D)).astype(np.float32)
+    full = oracle.topk_canonical(oracle.canonical_scores(users, items), NI)[0]
+    gt, blocked = {}, {}
+    for u in range(NU):
+        gt[u] = set(rng.choice(NI, size=3, replace=False).tolist())
+        if u % 7 == 0:      # heavy: the top of the ranking is blocked
+            blocked[u] = set(full[u, :1500].tolist()) - gt[u]
+        elif u % 7 == 1:    # top-128 nearly all blocked: falls short of max_k after the tensor-core pass
+            blocked[u] = set(full[u, :120].tolist()) - gt[u]
+        else:
+            blocked[u] = set(rng.choice(NI, size=int(rng.integers(0, 60)), replace=False).tolist()) - gt[u]
+    idx = tt.retrieval.FlatIPIndex(torch.from_numpy(items).cuda())
+    preds = tt.retrieval.evaluate_users(idx, torch.from_numpy(users).cuda(), list(range(NU)), gt, blocked, [5, max_k])
+    for u in range(NU):
+        need = max(max_k + len(gt[u]), 1) + len(blocked[u])
+        want = tt.retrieval.filter_candidates(full[u, :need].tolist(), blocked[u], gt[u], max_k)
+        assert preds[u] == want, u

@@ -90,6 +90,31 @@ def test_filter_block_equals_per_user_filter():
     assert retrieval.filter_block(np.zeros((0, 4), np.int64), [], [], {}, {}, 3) == {}
 
 
+def test_filter_block_fetches_longer_lists_in_one_call():
+    """Rows whose K columns keep fewer than max_k candidates although the reference would have searched deeper
+    (need > K) are handed to `deeper` together, once; every row ends up with the reference's list."""
+    import numpy as np
+    rng = np.random.default_rng(3)
+    n, K, NI, max_k = 12, 16, 300, 10
+    full = np.stack([rng.permutation(NI) for _ in range(n)]).astype(np.int64)
+    users = list(range(100, 100 + n))
+    gt = {u: set(rng.integers(0, NI, size=2).tolist()) for u in users}
+    blocked, need = {}, []
+    for r, u in enumerate(users):
+        b = set(full[r, : (14 if r % 3 == 0 else 2)].tolist()) - gt[u]          # every third row: its top 14 are blocked
+        blocked[u] = b
+        need.append(max_k + len(gt[u]) + len(b))
+    calls = []
+
+    def deeper(rows, k):
+        calls.append((list(rows), k))
+        return {r: full[r, :k].tolist() for r in rows}
+    got = retrieval.filter_block(full[:, :K], need, users, gt, blocked, max_k, deeper=deeper)
+    assert len(calls) == 1 and calls[0][0] == [r for r in range(n) if r % 3 == 0]
+    for r, u in enumerate(users):
+        assert got[u] == retrieval.filter_candidates(full[r, : need[r]].tolist(), blocked[u], gt[u], max_k), r
+
+
 def test_bag_matrix_layout_roundtrip():
     """functional.BagMatrix (CSR over the sparse columns + dense tail) reproduces the dense matrix; a matrix with a row of more
     than 64 sparse non-zeros is refused (the engine keeps the dense GEMM path for it)."""

@@ -169,6 +169,10 @@ SIGNATURES = {
     "ttam_score_pairs": (C.c_int, [_p, _p, _p, _i64, _i64, _i64, _i64, _p, _p]),
     "ttam_topk_bf16_workspace_bytes": (C.c_int64, [_i64, _i64, _i64, _i64]),
     "ttam_topk_bf16": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _i64, _p]),
+    "ttam_split_bf16x3_cols": (C.c_int64, [_i64]),
+    "ttam_split_bf16x3": (C.c_int, [_p, _i64, _i64, C.c_int, _p, _p]),
+    "ttam_topk_f32_tc_workspace_bytes": (C.c_int64, [_i64, _i64, _i64, _i64]),
+    "ttam_topk_f32_tc": (C.c_int, [_p, _p, _p, _p, _i64, _i64, _i64, _i64, _i64, _p, _p, _p, _i64, _p]),
     "ttam_topk_merge": (C.c_int, [_p, _p, _i64, _i64, _i64, _i64, _p, _p, _p]),
 }
 

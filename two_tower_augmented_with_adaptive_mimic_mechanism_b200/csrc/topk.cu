@@ -30,35 +30,101 @@ constexpr int kSelThreads = 256;
 constexpr int kSelItems = 20;                       // 5120 keys per block
 constexpr int kSelCap = kSelThreads * kSelItems;
 
-// One block per query: new running top-K = best K of (running K keys  U  chunk scores).
-// scores: [Q, ld] fp32 for ids id0 .. id0+n-1.  running: [Q, K] keys (sorted ascending).
-// after: optional [Q] keys; a candidate is admitted only if it sorts strictly AFTER its query's key (paged search).
-__global__ void __launch_bounds__(kSelThreads) select_topk_kernel(const float* __restrict__ scores, int64_t ld, int n,
-                                                                  uint32_t id0, uint64_t* __restrict__ running, int K,
-                                                                  const uint64_t* __restrict__ after) {
+constexpr int kPend = kSelCap - 1024;               // pending candidates per query (>= one chunk of scores)
+
+// running <- best K of (running  U  pending[0, cnt)); blocked arrangement: thread t owns slots t*kSelItems .. +kSelItems-1
+__device__ __forceinline__ void merge_pending(uint64_t* __restrict__ running, const uint64_t* __restrict__ pend, int cnt,
+                                              int K, void* temp_storage) {
   using Sort = cub::BlockRadixSort<uint64_t, kSelThreads, kSelItems>;
-  __shared__ typename Sort::TempStorage temp;
-  const int q = blockIdx.x;
-  const uint64_t floor_key = after ? after[q] : 0ull;
   uint64_t keys[kSelItems];
-  // blocked arrangement: thread t owns slots t*kSelItems .. +kSelItems-1
 #pragma unroll
   for (int i = 0; i < kSelItems; ++i) {
     const int slot = threadIdx.x * kSelItems + i;
     uint64_t k = kWorstKey;
-    if (slot < K) k = running[(int64_t)q * K + slot];
-    else if (slot - K < n) {
-      k = make_key(scores[(int64_t)q * ld + (slot - K)], id0 + (uint32_t)(slot - K));
-      if (after && k <= floor_key) k = kWorstKey;
-    }
+    if (slot < K) k = running[slot];
+    else if (slot - K < cnt) k = pend[slot - K];
     keys[i] = k;
   }
-  Sort(temp).Sort(keys);
+  Sort(*reinterpret_cast<typename Sort::TempStorage*>(temp_storage)).Sort(keys);
 #pragma unroll
   for (int i = 0; i < kSelItems; ++i) {
     const int slot = threadIdx.x * kSelItems + i;
-    if (slot < K) running[(int64_t)q * K + slot] = keys[i];
+    if (slot < K) running[slot] = keys[i];
   }
+}
+
+// One block per query.  A chunk score becomes a candidate only if it beats the query's current K-th best (the last key
+// of `running`) - after the first chunks that is a handful of the 4096 - and candidates wait in `pending` until that
+// fills up; only then is the block-wide sort paid (K ln(N / K) candidates in all: two or three sorts per query over a
+// whole corpus instead of one per chunk).
+// scores: [Q, ld] fp32 for ids id0 .. id0+n-1.  running: [Q, K] keys (sorted ascending).  pending: [Q, kPend], cnt [Q].
+// after: optional [Q] keys; a candidate is admitted only if it sorts strictly AFTER its query's key (paged search).
+__global__ void __launch_bounds__(kSelThreads) select_topk_kernel(const float* __restrict__ scores, int64_t ld, int n,
+                                                                  uint32_t id0, uint64_t* __restrict__ running, int K,
+                                                                  uint64_t* __restrict__ pending, int32_t* __restrict__ pcnt,
+                                                                  const uint64_t* __restrict__ after) {
+  using Sort = cub::BlockRadixSort<uint64_t, kSelThreads, kSelItems>;
+  __shared__ typename Sort::TempStorage temp;
+  __shared__ int s_new, s_base;
+  const int q = blockIdx.x;
+  uint64_t* run = running + (int64_t)q * K;
+  uint64_t* pend = pending + (int64_t)q * kPend;
+  const uint64_t floor_key = after ? after[q] : 0ull;
+  constexpr int kPer = 4096 / kSelThreads;   // scores per thread (n <= 4096), strided: coalesced loads
+  uint64_t thr = run[K - 1];
+  if (threadIdx.x == 0) s_new = 0;
+  __syncthreads();
+  uint64_t keys[kPer];
+  int mine = 0;
+#pragma unroll
+  for (int i = 0; i < kPer; ++i) {
+    const int j = i * kSelThreads + threadIdx.x;
+    uint64_t k = kWorstKey;
+    if (j < n) {
+      k = make_key(scores[(int64_t)q * ld + j], id0 + (uint32_t)j);
+      if (k >= thr || (after && k <= floor_key)) k = kWorstKey;
+    }
+    keys[i] = k;
+    mine += k != kWorstKey;
+  }
+  int at = mine ? atomicAdd(&s_new, mine) : 0;
+  __syncthreads();
+  const int total = s_new;
+  if (total == 0) return;
+  int cnt = pcnt[q];
+  if (cnt + total > kPend) {   // block-uniform: fold the pending candidates into `running`, tighten the threshold, re-filter
+    __syncthreads();
+    merge_pending(run, pend, cnt, K, &temp);
+    if (threadIdx.x == 0) s_new = 0;
+    __syncthreads();
+    thr = run[K - 1];
+    mine = 0;
+#pragma unroll
+    for (int i = 0; i < kPer; ++i) {
+      if (keys[i] >= thr) keys[i] = kWorstKey;
+      mine += keys[i] != kWorstKey;
+    }
+    at = mine ? atomicAdd(&s_new, mine) : 0;
+    __syncthreads();
+    cnt = 0;
+  }
+#pragma unroll
+  for (int i = 0; i < kPer; ++i)
+    if (keys[i] != kWorstKey) pend[cnt + at++] = keys[i];
+  __syncthreads();
+  if (threadIdx.x == 0) pcnt[q] = cnt + s_new;
+}
+
+// end of the corpus: fold what is still pending
+__global__ void __launch_bounds__(kSelThreads) merge_pending_kernel(uint64_t* __restrict__ running, int K,
+                                                                    const uint64_t* __restrict__ pending,
+                                                                    const int32_t* __restrict__ pcnt) {
+  using Sort = cub::BlockRadixSort<uint64_t, kSelThreads, kSelItems>;
+  __shared__ typename Sort::TempStorage temp;
+  const int q = blockIdx.x;
+  const int cnt = pcnt[q];
+  if (cnt == 0) return;
+  merge_pending(running + (int64_t)q * K, pending + (int64_t)q * kPend, cnt, K, &temp);
 }
 
 // (score, returned id) of the last result of the previous page -> key; id < 0: no previous page (admit everything)
@@ -157,7 +223,7 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const int64_t* __r
 }
 
 constexpr int kQBlock = 2048;   // queries per scoring pass
-constexpr int kChunk = 4096;    // items per scoring pass (+K <= kSelCap)
+constexpr int kChunk = 4096;    // items per scoring pass (<= kPend; K + kPend <= kSelCap)
 
 }  // namespace ttam
 
@@ -166,7 +232,8 @@ using namespace ttam;
 extern "C" int64_t ttam_topk_f32_workspace_bytes(int64_t Q, int64_t N, int64_t D, int64_t K) {
   (void)N; (void)D;
   int64_t qb = Q < kQBlock ? Q : kQBlock;
-  return align_up(qb * kChunk * 4, 256) + align_up(Q * K * 8, 256) + align_up(Q * 8, 256) + 256;
+  return align_up(qb * kChunk * 4, 256) + align_up(Q * K * 8, 256) + align_up(Q * 8, 256) +
+         align_up(qb * (int64_t)kPend * 8, 256) + align_up(qb * 4, 256) + 256;
 }
 
 extern "C" int ttam_topk_f32(const float* q, const float* items, int64_t Q, int64_t N, int64_t D, int64_t K,
@@ -204,9 +271,12 @@ extern "C" int ttam_topk_f32_after(const float* q, const float* items, int64_t Q
   const int64_t qb = Q < kQBlock ? Q : kQBlock;
   float* scores = (float*)workspace;
   uint64_t* running = (uint64_t*)((char*)workspace + align_up(qb * kChunk * 4, 256));
+  uint64_t* after_buf = running + align_up(Q * K * 8, 256) / 8;
+  uint64_t* pending = after_buf + align_up(Q * 8, 256) / 8;
+  int32_t* pcnt = (int32_t*)(pending + align_up(qb * (int64_t)kPend * 8, 256) / 8);
   uint64_t* after = nullptr;
   if (after_ids) {
-    after = running + align_up(Q * K * 8, 256) / 8;
+    after = after_buf;
     after_keys_kernel<<<(unsigned)ceil_div(Q, 256), 256, 0, s>>>(after_scores, after_ids, id_offset, Q, after);
     TTAM_LAUNCH_CHECK();
   }
@@ -214,6 +284,7 @@ extern "C" int ttam_topk_f32_after(const float* q, const float* items, int64_t Q
   TTAM_LAUNCH_CHECK();
   for (int64_t q0 = 0; q0 < Q; q0 += qb) {
     const int64_t nq = std::min<int64_t>(qb, Q - q0);
+    TTAM_CUDA(cudaMemsetAsync(pcnt, 0, (size_t)nq * 4, s));
     for (int64_t c0 = 0; c0 < N; c0 += kChunk) {
       const int64_t nc = std::min<int64_t>(kChunk, N - c0);
       GemmP p{};
@@ -222,10 +293,12 @@ extern "C" int ttam_topk_f32_after(const float* q, const float* items, int64_t Q
       dim3 grid((unsigned)ceil_div(nc, BN), (unsigned)ceil_div(nq, BM), 1);
       gemm_f32_kernel<true, true, true><<<grid, 256, 0, s>>>(p);
       TTAM_LAUNCH_CHECK();
-      select_topk_kernel<<<(unsigned)nq, kSelThreads, 0, s>>>(scores, kChunk, (int)nc, (uint32_t)c0,
-                                                              running + q0 * K, (int)K, after ? after + q0 : nullptr);
+      select_topk_kernel<<<(unsigned)nq, kSelThreads, 0, s>>>(scores, kChunk, (int)nc, (uint32_t)c0, running + q0 * K,
+                                                              (int)K, pending, pcnt, after ? after + q0 : nullptr);
       TTAM_LAUNCH_CHECK();
     }
+    merge_pending_kernel<<<(unsigned)nq, kSelThreads, 0, s>>>(running + q0 * K, (int)K, pending, pcnt);
+    TTAM_LAUNCH_CHECK();
   }
   decode_keys_kernel<<<(int)std::min<int64_t>(ceil_div(Q * K, 256), 4096), 256, 0, s>>>(running, Q * K, id_offset,
                                                                                         out_ids, out_scores);

@@ -35,8 +35,8 @@ namespace tc {
 using namespace ttam::sm100;
 
 constexpr int kBM = 128;       // queries per A tile (UMMA M)
-constexpr int kATiles = 2;     // A tiles resident per CTA: 256 queries per work unit
-constexpr int kQBlock = kBM * kATiles;
+constexpr int kMaxStages = 8;  // ring slots of the item stream (barrier table size)
+constexpr uint32_t kMaxSmem = 227 * 1024;
 constexpr int kBN = 256;       // items per B tile (one TMA stage)
 constexpr int kHN = 128;       // items per MMA (UMMA N): two halves per B tile, one TMEM accumulator each
 constexpr int kBoxK = 64;      // bf16 per 128-byte swizzled smem row
@@ -52,10 +52,17 @@ constexpr int kMaxCand = 256;  // candidates re-scored per query in the finalize
 constexpr uint32_t kABoxBytes = kBM * 128;   // 16 KB: 128 rows x 128 B
 constexpr uint32_t kBBoxBytes = kBN * 128;   // 32 KB
 
+// Two shapes of the item ring:
+//  * KBOX = 1, 2 (D <= 128; the tuned config-3 path): a stage holds a whole 256-item tile (KBOX boxes of 64 columns), two
+//    query tiles (256 queries) per CTA.
+//  * KBOX = 0 ("box ring", D up to 768): a stage holds ONE 64-column box of a tile, the MMA thread accumulates over the
+//    boxes of a tile as they arrive; p.kbox boxes per tile, p.stages slots - whatever fits beside the resident query tiles.
+//    ATILES = 1 (128 queries per CTA, epilogue warpgroup 1 idle) once the query tiles alone would not leave a slot.
+//    This is what D = 256 (BASELINE config 4) and the fp32 index (3 x D split-bf16 columns, below) run on.
 template <int KBOX>
 struct Cfg {
   static constexpr int kStages = KBOX == 1 ? 4 : 2;
-  static constexpr uint32_t kABytes = kATiles * KBOX * kABoxBytes;
+  static constexpr uint32_t kABytes = 2 * KBOX * kABoxBytes;
   static constexpr uint32_t kBStage = KBOX * kBBoxBytes;
   static constexpr uint32_t kSmem = kABytes + kStages * kBStage + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
@@ -170,6 +177,7 @@ struct MainParams {
   int D, S;
   int qblocks, tiles_total, tiles_per_split;
   int sample_tiles;  // T0: tiles of a unit's range visited first in sampling mode (0 = none)
+  int kbox, stages;  // box-ring variant only: 64-column boxes per tile, ring slots
   uint2* lists;     // [Q][S][kCap] raw {score bits, id}
   int32_t* cnts;    // [Q][S]
   float* taus;      // [Q][S]
@@ -203,22 +211,27 @@ struct TileSeq {
   __device__ __forceinline__ int tile(int i) const { return i < T0 ? t0 + i * stride : t0 + (i - T0); }
 };
 
-template <int KBOX>
+template <int KBOX, int ATILES>
 __global__ void __launch_bounds__(kThreads, 1)
 score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_items, MainParams p) {
-  using C = Cfg<KBOX>;
+  constexpr bool kRing = KBOX == 0;
+  constexpr int kQBlock = kBM * ATILES;
+  const int kbox = kRing ? p.kbox : KBOX;
+  const int n_stages = kRing ? p.stages : (KBOX == 1 ? 4 : 2);
+  const uint32_t a_bytes = (uint32_t)(ATILES * kbox) * kABoxBytes;
+  const uint32_t stage_bytes = kRing ? kBBoxBytes : (uint32_t)KBOX * kBBoxBytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + C::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + C::kStages * C::kBStage);
+  uint8_t* smem_b = smem + a_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + (uint32_t)n_stages * stage_bytes);
   uint64_t* a_full = bars + 0;
   uint64_t* a_empty = bars + 1;
   uint64_t* acc_full = bars + 2;    // [2] (4 slots reserved): accumulator of query tile a
   uint64_t* acc_empty = bars + 6;   // [4]: half h of accumulator a at index a*2+h
-  uint64_t* b_full = bars + 10;     // [kStages]
-  uint64_t* b_empty = bars + 10 + C::kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * C::kStages);
+  uint64_t* b_full = bars + 10;     // [kMaxStages]
+  uint64_t* b_empty = bars + 10 + kMaxStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10 + 2 * kMaxStages);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -232,7 +245,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       mbar_init(acc_full + i, 1);
       mbar_init(acc_empty + i, kEpiWarps / 2);  // the 4 warps of the warpgroup that owns query tile a
     }
-    for (int i = 0; i < C::kStages; ++i) {
+    for (int i = 0; i < n_stages; ++i) {
       mbar_init(b_full + i, 1);
       mbar_init(b_empty + i, 1);
     }
@@ -254,22 +267,35 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       for (int u = blockIdx.x; u < units; u += gridDim.x, ++un) {
         const int qb = u % p.qblocks, s = u / p.qblocks;
         mbar_wait_relaxed(a_empty, (un & 1) ^ 1, 256);
-        mbar_expect_tx(a_full, C::kABytes);
-        for (int a = 0; a < kATiles; ++a)
-          for (int kb = 0; kb < KBOX; ++kb)
-            tma_load_2d(smem_a + (a * KBOX + kb) * kABoxBytes, &tmap_q, a_full, kb * kBoxK, qb * kQBlock + a * kBM);
+        mbar_expect_tx(a_full, a_bytes);
+        for (int a = 0; a < ATILES; ++a)
+          for (int kb = 0; kb < kbox; ++kb)
+            tma_load_2d(smem_a + (a * kbox + kb) * kABoxBytes, &tmap_q, a_full, kb * kBoxK, qb * kQBlock + a * kBM);
         const TileSeq seq(p, s);
-        for (int i = 0; i < seq.count(); ++i, ++it) {
-          const int t = seq.tile(i);
-          const int stage = it % C::kStages;
-          mbar_wait_relaxed(b_empty + stage, ((it / C::kStages) & 1) ^ 1, 256);
-          if ((p.debug & 4) && it >= (uint32_t)C::kStages) {  // timing experiment: the MMA re-reads stale tiles
-            mbar_arrive(b_full + stage);
-            continue;
+        if constexpr (kRing) {
+          // `it` counts boxes here: one ring slot per (tile, 64-column box)
+          for (int i = 0; i < seq.count(); ++i) {
+            const int t = seq.tile(i);
+            for (int kb = 0; kb < kbox; ++kb, ++it) {
+              const int stage = it % n_stages;
+              mbar_wait_relaxed(b_empty + stage, ((it / n_stages) & 1) ^ 1, 64);
+              mbar_expect_tx(b_full + stage, kBBoxBytes);
+              tma_load_2d(smem_b + stage * kBBoxBytes, &tmap_items, b_full + stage, kb * kBoxK, t * kBN);
+            }
           }
-          mbar_expect_tx(b_full + stage, C::kBStage);
-          for (int kb = 0; kb < KBOX; ++kb)
-            tma_load_2d(smem_b + stage * C::kBStage + kb * kBBoxBytes, &tmap_items, b_full + stage, kb * kBoxK, t * kBN);
+        } else {
+          for (int i = 0; i < seq.count(); ++i, ++it) {
+            const int t = seq.tile(i);
+            const int stage = it % n_stages;
+            mbar_wait_relaxed(b_empty + stage, ((it / n_stages) & 1) ^ 1, 256);
+            if ((p.debug & 4) && it >= (uint32_t)n_stages) {  // timing experiment: the MMA re-reads stale tiles
+              mbar_arrive(b_full + stage);
+              continue;
+            }
+            mbar_expect_tx(b_full + stage, stage_bytes);
+            for (int kb = 0; kb < KBOX; ++kb)
+              tma_load_2d(smem_b + stage * stage_bytes + kb * kBBoxBytes, &tmap_items, b_full + stage, kb * kBoxK, t * kBN);
+          }
         }
       }
     }
@@ -280,36 +306,61 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       // descriptors differ only in the 14-bit start-address field: precompute the bases once
       const uint64_t a_desc0 = make_kmajor_desc<128>(smem_u32(smem_a));
       const uint64_t b_desc0 = make_kmajor_desc<128>(smem_u32(smem_b));
-      uint32_t it = 0, un = 0;
+      uint32_t it = 0, un = 0, bx = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x, ++un) {
         const int s = u / p.qblocks;
         const TileSeq seq(p, s);
         mbar_wait(a_full, un & 1);
-        for (int i = 0; i < seq.count(); ++i, ++it) {
-          const int stage = it % C::kStages;
-          mbar_wait(b_full + stage, (it / C::kStages) & 1);
-          const uint64_t b_desc = b_desc0 + (uint64_t)((stage * C::kBStage) >> 4);
+        if constexpr (kRing) {
+          for (int i = 0; i < seq.count(); ++i, ++it) {
+            for (int kb = 0; kb < kbox; ++kb, ++bx) {
+              const int stage = bx % n_stages;
+              mbar_wait(b_full + stage, (bx / n_stages) & 1);
+              const uint64_t b_desc = b_desc0 + (uint64_t)((stage * kBBoxBytes) >> 4);
+              const int kin = min(4, ksteps - kb * 4);  // 16-column MMA steps inside this box
 #pragma unroll 1
-          for (int a = 0; a < kATiles; ++a) {
-            // one N=256 MMA group fills both 128-column halves of query tile a: both must have been drained
-            if (p.debug & 16) {    // (16: timing experiment, polls of the MMA thread back off with nanosleep)
-              mbar_wait_relaxed(acc_empty + a * 2, (it & 1) ^ 1, 32);
-              mbar_wait_relaxed(acc_empty + a * 2 + 1, (it & 1) ^ 1, 32);
-            } else if (!(p.debug & 8)) {  // (8: timing experiment, accumulators overwritten without waiting for the drain)
-              mbar_wait(acc_empty + a * 2, (it & 1) ^ 1);
-              mbar_wait(acc_empty + a * 2 + 1, (it & 1) ^ 1);
+              for (int a = 0; a < ATILES; ++a) {
+                if (kb == 0) {  // first box of the tile: both halves of accumulator a must have been drained
+                  mbar_wait(acc_empty + a * 2, (it & 1) ^ 1);
+                  mbar_wait(acc_empty + a * 2 + 1, (it & 1) ^ 1);
+                  tc_fence_after();
+                }
+                const uint32_t d_tmem = tmem_base + (uint32_t)(a * kBN);
+                const uint64_t a_desc = a_desc0 + (uint64_t)(((a * kbox + kb) * kABoxBytes) >> 4);
+                for (int k = 0; k < kin; ++k)
+                  umma_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                if (kb == kbox - 1) umma_commit(acc_full + a);
+              }
+              umma_commit(b_empty + stage);
             }
-            tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(a * kBN);
-            const uint64_t a_desc = a_desc0 + (uint64_t)((a * KBOX * kABoxBytes) >> 4);
-            for (int k = 0; k < ksteps; ++k) {
-              const uint32_t koff_a = (uint32_t)(((k >> 2) * kABoxBytes + (k & 3) * 32) >> 4);
-              const uint32_t koff_b = (uint32_t)(((k >> 2) * kBBoxBytes + (k & 3) * 32) >> 4);
-              umma_f16(d_tmem, a_desc + koff_a, b_desc + koff_b, idesc, k > 0 ? 1u : 0u);
-            }
-            umma_commit(acc_full + a);
           }
-          umma_commit(b_empty + stage);
+        } else {
+          for (int i = 0; i < seq.count(); ++i, ++it) {
+            const int stage = it % n_stages;
+            mbar_wait(b_full + stage, (it / n_stages) & 1);
+            const uint64_t b_desc = b_desc0 + (uint64_t)((stage * stage_bytes) >> 4);
+#pragma unroll 1
+            for (int a = 0; a < ATILES; ++a) {
+              // one N=256 MMA group fills both 128-column halves of query tile a: both must have been drained
+              if (p.debug & 16) {    // (16: timing experiment, polls of the MMA thread back off with nanosleep)
+                mbar_wait_relaxed(acc_empty + a * 2, (it & 1) ^ 1, 32);
+                mbar_wait_relaxed(acc_empty + a * 2 + 1, (it & 1) ^ 1, 32);
+              } else if (!(p.debug & 8)) {  // (8: timing experiment, accumulators overwritten without waiting for the drain)
+                mbar_wait(acc_empty + a * 2, (it & 1) ^ 1);
+                mbar_wait(acc_empty + a * 2 + 1, (it & 1) ^ 1);
+              }
+              tc_fence_after();
+              const uint32_t d_tmem = tmem_base + (uint32_t)(a * kBN);
+              const uint64_t a_desc = a_desc0 + (uint64_t)((a * KBOX * kABoxBytes) >> 4);
+              for (int k = 0; k < ksteps; ++k) {
+                const uint32_t koff_a = (uint32_t)(((k >> 2) * kABoxBytes + (k & 3) * 32) >> 4);
+                const uint32_t koff_b = (uint32_t)(((k >> 2) * kBBoxBytes + (k & 3) * 32) >> 4);
+                umma_f16(d_tmem, a_desc + koff_a, b_desc + koff_b, idesc, k > 0 ? 1u : 0u);
+              }
+              umma_commit(acc_full + a);
+            }
+            umma_commit(b_empty + stage);
+          }
         }
         umma_commit(a_empty);  // all MMAs of this unit have read the query tiles
       }
@@ -321,7 +372,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     const int a = ew >> 2;       // which query tile / pair of accumulators
     const int row_in_tile = quad * 32 + lane;
     uint32_t it = 0;
-    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    for (int u = blockIdx.x; u < (a < ATILES ? units : 0); u += gridDim.x) {
       const int qb = u % p.qblocks, s = u / p.qblocks;
       const TileSeq seq(p, s);
       const int64_t qrow = (int64_t)qb * kQBlock + a * kBM + row_in_tile;
@@ -463,7 +514,11 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 }
 
 // ---- max row norm of the corpus -------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) max_norm_kernel(const __nv_bfloat16* __restrict__ items, int64_t N, int D,
+__device__ __forceinline__ float to_f32(float x) { return x; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 x) { return __bfloat162float(x); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) max_norm_kernel(const T* __restrict__ items, int64_t N, int D,
                                                        uint32_t* __restrict__ out_bits) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -472,7 +527,7 @@ __global__ void __launch_bounds__(256) max_norm_kernel(const __nv_bfloat16* __re
   for (int64_t r = warp0; r < N; r += nwarps) {
     float s = 0.f;
     for (int d = lane; d < D; d += 32) {
-      const float x = __bfloat162float(items[r * D + d]);
+      const float x = to_f32(items[r * D + d]);
       s = fmaf(x, x, s);
     }
     s = warp_sum(s);
@@ -497,6 +552,43 @@ __device__ __forceinline__ float canonical_dot(const float* __restrict__ qf, con
   return acc;
 }
 
+__device__ __forceinline__ float canonical_dot(const float* __restrict__ qf, const float* __restrict__ row, int D) {
+  float acc = 0.f;
+  int d0 = 0;
+  if ((reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+    for (; d0 + 4 <= D; d0 += 4) {
+      const float4 x = *reinterpret_cast<const float4*>(row + d0);
+      acc = __fadd_rn(acc, __fmul_rn(qf[d0], x.x));
+      acc = __fadd_rn(acc, __fmul_rn(qf[d0 + 1], x.y));
+      acc = __fadd_rn(acc, __fmul_rn(qf[d0 + 2], x.z));
+      acc = __fadd_rn(acc, __fmul_rn(qf[d0 + 3], x.w));
+    }
+  }
+  for (; d0 < D; ++d0) acc = __fadd_rn(acc, __fmul_rn(qf[d0], row[d0]));
+  return acc;
+}
+
+// ---- fp32 index on the tensor cores: x = hi + lo + r with hi = bf16(x), lo = bf16(x - hi), |r| <= 2^-16 |x| ------------
+// Queries are laid out as [hi | lo | hi], items as [hi | hi | lo] (each part padded to Dp = 16-multiple columns), so one
+// bf16 tensor-core product over 3 Dp columns is  qh.xh + ql.xh + qh.xl = q.x - (ql.xl + residuals):
+// |tensor-core score - canonical fp32 score| <= (3.1 * 2^-16 + accumulation terms) * |q| |x|.  The candidate pass is the
+// bf16 kernel unchanged; the finalize kernel re-scores with the fp32 rows.
+__global__ void split_bf16x3_kernel(const float* __restrict__ x, int64_t R, int D, int Dp, int item_layout,
+                                    __nv_bfloat16* __restrict__ out) {
+  const int64_t total = R * Dp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / Dp;
+    const int d = (int)(i - r * Dp);
+    const float v = d < D ? x[r * D + d] : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    __nv_bfloat16* o = out + r * (3 * Dp) + d;
+    o[0] = hi;
+    o[Dp] = item_layout ? hi : lo;
+    o[2 * Dp] = item_layout ? lo : hi;
+  }
+}
+
 // ascending radix-sort key == (descending score, ascending id)
 __device__ __forceinline__ uint64_t final_key(float score, uint32_t id) {
   return ((uint64_t)(~ordered_bits(score)) << 32) | (uint64_t)id;
@@ -504,8 +596,11 @@ __device__ __forceinline__ uint64_t final_key(float score, uint32_t id) {
 constexpr uint64_t kWorst = ~0ull;
 
 struct FinalParams {
-  const __nv_bfloat16* q;
+  const __nv_bfloat16* q;      // bf16 index: the operands the tensor cores saw ARE the canonical ones
   const __nv_bfloat16* items;
+  const float* qf32;           // fp32 index: canonical operands (the tensor cores saw their 3-way bf16 split)
+  const float* itemsf32;
+  float delta_rel;             // |tensor-core score - canonical score| <= delta_rel * |q| * max|item|
   int64_t Q, N, id_offset;
   int D, S, K;
   const uint2* lists;
@@ -526,14 +621,14 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalParams p) {
     typename SortA::TempStorage a;
     typename SortB::TempStorage b;
   } temp;
-  __shared__ float qf[128];
+  __shared__ float qf[256];
   __shared__ uint32_t cand[kMaxCand];
   __shared__ float s_tk, s_qnorm2, s_tq;
   __shared__ int s_total, s_P;
   const int q = blockIdx.x;
   const int tid = threadIdx.x;
   const int L = p.S;
-  if (tid < p.D) qf[tid] = __bfloat162float(p.q[(int64_t)q * p.D + tid]);
+  if (tid < p.D) qf[tid] = p.qf32 ? p.qf32[(int64_t)q * p.D + tid] : __bfloat162float(p.q[(int64_t)q * p.D + tid]);
   if (tid == 0) {
     int tot = 0;
     float tq = -INFINITY;
@@ -572,9 +667,9 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalParams p) {
   for (int i = 0; i < ITEMS; ++i)
     if (tid * ITEMS + i == kth) s_tk = key_score(~keys[i]);
   __syncthreads();
-  // |tc - canonical| <= delta: both are fp32 accumulations of D exact products bounded by |q||item|
+  // |tc - canonical| <= delta (bf16 index: both are fp32 accumulations of D exact products bounded by |q||item|)
   const float max_norm = __uint_as_float(*p.max_norm_bits);
-  const float delta = 4.f * (float)p.D * 5.9604645e-8f * sqrtf(s_qnorm2) * max_norm;
+  const float delta = p.delta_rel * sqrtf(s_qnorm2) * max_norm + 1e-30f;
   const float thr = s_tk - 2.f * delta;
   int mine = 0;
 #pragma unroll
@@ -600,7 +695,9 @@ __global__ void __launch_bounds__(256) finalize_kernel(FinalParams p) {
   fk[0] = kWorst;
   if (tid < P) {
     const uint32_t id = cand[tid];
-    fk[0] = final_key(canonical_dot(qf, p.items + (int64_t)id * p.D, p.D), id);
+    const float sc = p.itemsf32 ? canonical_dot(qf, p.itemsf32 + (int64_t)id * p.D, p.D)
+                                : canonical_dot(qf, p.items + (int64_t)id * p.D, p.D);
+    fk[0] = final_key(sc, id);
   }
   SortB(temp.b).Sort(fk);
   if (tid < p.K) {
@@ -618,13 +715,13 @@ constexpr int kExactChunk = 4096;
 __global__ void __launch_bounds__(256) exact_rows_kernel(FinalParams p) {
   using Sort = cub::BlockRadixSort<uint64_t, 256, kExactItems>;
   __shared__ typename Sort::TempStorage temp;
-  __shared__ float qf[128];
+  __shared__ float qf[256];
   const int tid = threadIdx.x;
   const int nf = *p.n_flagged;
   for (int f = blockIdx.x; f < nf; f += gridDim.x) {
     const int q = p.flagged[f];
     __syncthreads();
-    if (tid < p.D) qf[tid] = __bfloat162float(p.q[(int64_t)q * p.D + tid]);
+    if (tid < p.D) qf[tid] = p.qf32 ? p.qf32[(int64_t)q * p.D + tid] : __bfloat162float(p.q[(int64_t)q * p.D + tid]);
     __syncthreads();
     uint64_t keys[kExactItems];
 #pragma unroll
@@ -636,7 +733,10 @@ __global__ void __launch_bounds__(256) exact_rows_kernel(FinalParams p) {
         const int slot = tid * kExactItems + i;
         if (slot >= p.K) {
           const int64_t id = c0 + (slot - p.K);
-          keys[i] = (slot - p.K < kExactChunk && id < p.N) ? final_key(canonical_dot(qf, p.items + id * p.D, p.D), (uint32_t)id) : kWorst;
+          keys[i] = kWorst;
+          if (slot - p.K < kExactChunk && id < p.N)
+            keys[i] = final_key(p.itemsf32 ? canonical_dot(qf, p.itemsf32 + id * p.D, p.D) : canonical_dot(qf, p.items + id * p.D, p.D),
+                                (uint32_t)id);
         }
       }
       __syncthreads();
@@ -659,8 +759,8 @@ __global__ void __launch_bounds__(256) exact_rows_kernel(FinalParams p) {
 // split runs its own threshold warm-up (the expensive early part of a stream, where most scores still beat the row's
 // threshold) and adds a list to merge.  Measured at Q = 100 k x 2 M (391 query blocks, 148 SMs): S = 1: 76.9 ms,
 // S = 2: 96.6 ms, S = 3: 106.0 ms, S = 4: 120.0 ms.  Splits therefore only exist to occupy SMs that would otherwise idle.
-static int choose_splits(int64_t Q, int64_t N) {
-  const int64_t qblocks = ceil_div(Q, kQBlock), tiles = ceil_div(N, kBN);
+static int choose_splits(int64_t Q, int64_t N, int qblock) {
+  const int64_t qblocks = ceil_div(Q, qblock), tiles = ceil_div(N, kBN);
   const int64_t sms = num_sms();
   int64_t best = 1;
   if (qblocks < sms) {
@@ -705,57 +805,80 @@ static Workspace carve(void* base, int64_t Q, int S) {
   return w;
 }
 
-}  // namespace tc
-}  // namespace ttam
-
-using namespace ttam;
-using namespace ttam::tc;
-
-extern "C" int64_t ttam_topk_bf16_workspace_bytes(int64_t Q, int64_t N, int64_t D, int64_t K) {
-  (void)D; (void)K;
-  if (Q <= 0 || N <= 0) return 256;
-  return carve(nullptr, Q, choose_splits(Q, N)).bytes;
+// Kernel shape for an MMA depth of Dm bf16 columns (see Cfg): kbox = 0 -> the whole-tile ring (KBOX = 1 or 2).
+struct Shape {
+  int kbox_t;   // template KBOX (0 = box ring)
+  int kbox;     // 64-column boxes per tile
+  int atiles;   // query tiles per CTA
+  int stages;   // ring slots
+  uint32_t smem;
+};
+static Shape shape_for(int64_t Dm) {
+  Shape sh{};
+  sh.kbox = (int)ceil_div(Dm, (int64_t)kBoxK);
+  const bool force_ring = getenv("TTAM_TOPK_RING") != nullptr;   // A/B switch: small D through the box ring
+  if (sh.kbox <= 2 && !force_ring) {
+    sh.kbox_t = sh.kbox; sh.atiles = 2;
+    sh.stages = sh.kbox == 1 ? 4 : 2;
+    sh.smem = sh.kbox == 1 ? Cfg<1>::kSmem : Cfg<2>::kSmem;
+    return sh;
+  }
+  sh.kbox_t = 0;
+  sh.atiles = sh.kbox <= 5 ? 2 : 1;
+  const int64_t a_bytes = (int64_t)sh.atiles * sh.kbox * kABoxBytes;
+  int64_t st = ((int64_t)kMaxSmem - 1024 - 256 - a_bytes) / kBBoxBytes;
+  if (st > kMaxStages) st = kMaxStages;
+  if (st > 2 * sh.kbox && sh.kbox >= 3) st = 2 * sh.kbox;   // two whole tiles in flight are enough
+  sh.stages = (int)st;
+  sh.smem = (uint32_t)(a_bytes + st * kBBoxBytes + 1024 + 256);
+  return sh;
 }
 
-extern "C" int ttam_topk_bf16(const uint16_t* q, const uint16_t* items, int64_t Q, int64_t N, int64_t D, int64_t K,
-                              int64_t id_offset, int64_t* out_ids, float* out_scores, void* workspace,
-                              int64_t workspace_bytes, void* stream) {
-  TTAM_CHECK_ARG(Q >= 0 && N > 0 && D > 0 && K > 0, "topk_bf16: bad shape");
-  if (Q == 0) return TTAM_OK;
-  TTAM_CHECK_ARG(q && items && out_ids && out_scores && workspace, "topk_bf16: null pointer");
-  if (D % 16 != 0 || D > 128 || K > kKeep) {
-    set_error("topk_bf16: the tcgen05 path needs D %% 16 == 0, D <= 128 and K <= %d (got D=%lld, K=%lld)", kKeep,
-              (long long)D, (long long)K);
+template <int KBOX, int ATILES>
+static int launch_main(const CUtensorMap& tq, const CUtensorMap& ti, const MainParams& mp, int grid, uint32_t smem, cudaStream_t st) {
+  TTAM_CUDA(cudaFuncSetAttribute(score_topk_kernel<KBOX, ATILES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  score_topk_kernel<KBOX, ATILES><<<grid, kThreads, smem, st>>>(tq, ti, mp);
+  TTAM_LAUNCH_CHECK();
+  return TTAM_OK;
+}
+
+// The launch sequence shared by the bf16 index (qm / im are the canonical operands) and the fp32 index (qm / im are the
+// 3-way bf16 splits of qf / itf, which stay the canonical operands of the re-score).
+static int run_topk(const uint16_t* qm, const uint16_t* im, int64_t Dm, const float* qf, const float* itf, int64_t Q,
+                    int64_t N, int64_t D, int64_t K, int64_t id_offset, int64_t* out_ids, float* out_scores,
+                    void* workspace, int64_t workspace_bytes, cudaStream_t st) {
+  const Shape sh = shape_for(Dm);
+  if (sh.stages < 1) {
+    set_error("topk: %lld operand columns do not fit the shared-memory ring", (long long)Dm);
     return TTAM_EUNSUPPORTED;
   }
-  TTAM_CHECK_ARG(N < (1ll << 32) - 1 && Q < (1ll << 31), "topk_bf16: corpus too large for 32-bit local ids");
-  TTAM_CHECK_ARG(((uintptr_t)q & 15) == 0 && ((uintptr_t)items & 15) == 0, "topk_bf16: operands must be 16-byte aligned");
-  const int S = choose_splits(Q, N);
+  const int qblock = kBM * sh.atiles;
+  const int S = choose_splits(Q, N, qblock);
   Workspace w = carve(workspace, Q, S);
   if (workspace_bytes < w.bytes) {
-    set_error("topk_bf16: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)w.bytes);
+    set_error("topk: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)w.bytes);
     return TTAM_EWORKSPACE;
   }
-  cudaStream_t st = (cudaStream_t)stream;
-  const int KBOX = D <= 64 ? 1 : 2;
   CUtensorMap tq, ti;
-  int rc = make_tmap_2d(&tq, q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)Q, (uint64_t)D, (uint64_t)D * 2, kBoxK, kBM,
+  int rc = make_tmap_2d(&tq, qm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)Q, (uint64_t)Dm, (uint64_t)Dm * 2, kBoxK, kBM,
                         CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != TTAM_OK) return rc;
-  rc = make_tmap_2d(&ti, items, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)N, (uint64_t)D, (uint64_t)D * 2, kBoxK, kBN,
+  rc = make_tmap_2d(&ti, im, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)N, (uint64_t)Dm, (uint64_t)Dm * 2, kBoxK, kBN,
                     CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != TTAM_OK) return rc;
 
   TTAM_CUDA(cudaMemsetAsync(w.max_norm_bits, 0, 256, st));  // max norm and the flagged counter
-  max_norm_kernel<<<num_sms() * 4, 256, 0, st>>>((const __nv_bfloat16*)items, N, (int)D, w.max_norm_bits);
+  if (itf) max_norm_kernel<float><<<num_sms() * 4, 256, 0, st>>>(itf, N, (int)D, w.max_norm_bits);
+  else max_norm_kernel<__nv_bfloat16><<<num_sms() * 4, 256, 0, st>>>((const __nv_bfloat16*)im, N, (int)D, w.max_norm_bits);
   TTAM_LAUNCH_CHECK();
 
   MainParams mp{};
-  mp.Q = Q; mp.N = N; mp.D = (int)D; mp.S = S;
-  mp.qblocks = (int)ceil_div(Q, kQBlock);
+  mp.Q = Q; mp.N = N; mp.D = (int)Dm; mp.S = S;
+  mp.qblocks = (int)ceil_div(Q, qblock);
   mp.tiles_total = (int)ceil_div(N, kBN);
   mp.tiles_per_split = (int)ceil_div(mp.tiles_total, S);
   mp.lists = w.lists; mp.cnts = w.cnts; mp.taus = w.taus;
+  mp.kbox = sh.kbox; mp.stages = sh.stages;
   mp.sample_tiles = 64;
   if (const char* e = getenv("TTAM_TOPK_SAMPLE_TILES")) mp.sample_tiles = atoi(e);
   {
@@ -764,18 +887,20 @@ extern "C" int ttam_topk_bf16(const uint16_t* q, const uint16_t* items, int64_t 
   }
   const int units = mp.qblocks * S;
   const int grid = units < num_sms() ? units : num_sms();
-  if (KBOX == 1) {
-    TTAM_CUDA(cudaFuncSetAttribute(score_topk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<1>::kSmem));
-    score_topk_kernel<1><<<grid, kThreads, Cfg<1>::kSmem, st>>>(tq, ti, mp);
-  } else {
-    TTAM_CUDA(cudaFuncSetAttribute(score_topk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<2>::kSmem));
-    score_topk_kernel<2><<<grid, kThreads, Cfg<2>::kSmem, st>>>(tq, ti, mp);
-  }
-  TTAM_LAUNCH_CHECK();
+  if (sh.kbox_t == 1) rc = launch_main<1, 2>(tq, ti, mp, grid, sh.smem, st);
+  else if (sh.kbox_t == 2) rc = launch_main<2, 2>(tq, ti, mp, grid, sh.smem, st);
+  else if (sh.atiles == 2) rc = launch_main<0, 2>(tq, ti, mp, grid, sh.smem, st);
+  else rc = launch_main<0, 1>(tq, ti, mp, grid, sh.smem, st);
+  if (rc != TTAM_OK) return rc;
   if (mp.debug) return TTAM_OK;  // timing experiments: the lists are meaningless, skip the merge
 
   FinalParams fp{};
-  fp.q = (const __nv_bfloat16*)q; fp.items = (const __nv_bfloat16*)items;
+  fp.q = (const __nv_bfloat16*)qm; fp.items = (const __nv_bfloat16*)im;
+  fp.qf32 = qf; fp.itemsf32 = itf;
+  // fp32 accumulation of Dm exact bf16 products on either side (factor 4: alignment truncation inside the tensor core);
+  // fp32 index: + the dropped lo.lo products and split residuals (3.1 * 2^-16) + the canonical fp32 sum's own rounding
+  fp.delta_rel = 4.f * (float)Dm * 5.9604645e-8f;
+  if (itf) fp.delta_rel = 1.01f * (fp.delta_rel + 3.1f * 1.52587890625e-5f + 2.f * (float)D * 5.9604645e-8f);
   fp.Q = Q; fp.N = N; fp.id_offset = id_offset; fp.D = (int)D; fp.S = S; fp.K = (int)K;
   fp.lists = w.lists; fp.cnts = w.cnts; fp.taus = w.taus; fp.max_norm_bits = w.max_norm_bits;
   fp.out_ids = out_ids; fp.out_scores = out_scores; fp.flagged = w.flagged; fp.n_flagged = w.n_flagged;
@@ -788,4 +913,74 @@ extern "C" int ttam_topk_bf16(const uint16_t* q, const uint16_t* items, int64_t 
   exact_rows_kernel<<<num_sms(), 256, 0, st>>>(fp);
   TTAM_LAUNCH_CHECK();
   return TTAM_OK;
+}
+
+}  // namespace tc
+}  // namespace ttam
+
+using namespace ttam;
+using namespace ttam::tc;
+
+constexpr int64_t kMaxD = 256;   // canonical depth (query row held in shared memory by the finalize kernels)
+
+extern "C" int64_t ttam_topk_bf16_workspace_bytes(int64_t Q, int64_t N, int64_t D, int64_t K) {
+  (void)K;
+  if (Q <= 0 || N <= 0 || D <= 0) return 256;
+  return carve(nullptr, Q, choose_splits(Q, N, kBM * shape_for(D).atiles)).bytes;
+}
+
+extern "C" int ttam_topk_bf16(const uint16_t* q, const uint16_t* items, int64_t Q, int64_t N, int64_t D, int64_t K,
+                              int64_t id_offset, int64_t* out_ids, float* out_scores, void* workspace,
+                              int64_t workspace_bytes, void* stream) {
+  TTAM_CHECK_ARG(Q >= 0 && N > 0 && D > 0 && K > 0, "topk_bf16: bad shape");
+  if (Q == 0) return TTAM_OK;
+  TTAM_CHECK_ARG(q && items && out_ids && out_scores && workspace, "topk_bf16: null pointer");
+  if (D % 16 != 0 || D > kMaxD || K > kKeep) {
+    set_error("topk_bf16: the tcgen05 path needs D %% 16 == 0, D <= %lld and K <= %d (got D=%lld, K=%lld)", (long long)kMaxD,
+              kKeep, (long long)D, (long long)K);
+    return TTAM_EUNSUPPORTED;
+  }
+  TTAM_CHECK_ARG(N < (1ll << 32) - 1 && Q < (1ll << 31), "topk_bf16: corpus too large for 32-bit local ids");
+  TTAM_CHECK_ARG(((uintptr_t)q & 15) == 0 && ((uintptr_t)items & 15) == 0, "topk_bf16: operands must be 16-byte aligned");
+  return run_topk(q, items, D, nullptr, nullptr, Q, N, D, K, id_offset, out_ids, out_scores, workspace, workspace_bytes,
+                  (cudaStream_t)stream);
+}
+
+// ---- fp32 index on the tensor cores ------------------------------------------------------------------------------------
+extern "C" int64_t ttam_split_bf16x3_cols(int64_t D) { return 3 * align_up(D, 16); }
+
+extern "C" int ttam_split_bf16x3(const float* x, int64_t R, int64_t D, int item_layout, uint16_t* out, void* stream) {
+  TTAM_CHECK_ARG(R >= 0 && D > 0, "split_bf16x3: bad shape");
+  if (R == 0) return TTAM_OK;
+  TTAM_CHECK_ARG(x && out, "split_bf16x3: null pointer");
+  const int64_t Dp = align_up(D, 16);
+  const int64_t blocks = std::min<int64_t>(ceil_div(R * Dp, 256), (int64_t)num_sms() * 16);
+  split_bf16x3_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, R, (int)D, (int)Dp, item_layout,
+                                                                         (__nv_bfloat16*)out);
+  TTAM_LAUNCH_CHECK();
+  return TTAM_OK;
+}
+
+extern "C" int64_t ttam_topk_f32_tc_workspace_bytes(int64_t Q, int64_t N, int64_t D, int64_t K) {
+  (void)K;
+  if (Q <= 0 || N <= 0 || D <= 0) return 256;
+  return carve(nullptr, Q, choose_splits(Q, N, kBM * shape_for(ttam_split_bf16x3_cols(D)).atiles)).bytes;
+}
+
+extern "C" int ttam_topk_f32_tc(const float* q, const float* items, const uint16_t* q_split, const uint16_t* items_split,
+                                int64_t Q, int64_t N, int64_t D, int64_t K, int64_t id_offset, int64_t* out_ids,
+                                float* out_scores, void* workspace, int64_t workspace_bytes, void* stream) {
+  TTAM_CHECK_ARG(Q >= 0 && N > 0 && D > 0 && K > 0, "topk_f32_tc: bad shape");
+  if (Q == 0) return TTAM_OK;
+  TTAM_CHECK_ARG(q && items && q_split && items_split && out_ids && out_scores && workspace, "topk_f32_tc: null pointer");
+  if (D > kMaxD || K > kKeep) {
+    set_error("topk_f32_tc: needs D <= %lld and K <= %d (got D=%lld, K=%lld); use ttam_topk_f32", (long long)kMaxD, kKeep,
+              (long long)D, (long long)K);
+    return TTAM_EUNSUPPORTED;
+  }
+  TTAM_CHECK_ARG(N < (1ll << 32) - 1 && Q < (1ll << 31), "topk_f32_tc: corpus too large for 32-bit local ids");
+  TTAM_CHECK_ARG(((uintptr_t)q_split & 15) == 0 && ((uintptr_t)items_split & 15) == 0,
+                 "topk_f32_tc: split operands must be 16-byte aligned");
+  return run_topk(q_split, items_split, ttam_split_bf16x3_cols(D), q, items, Q, N, D, K, id_offset, out_ids, out_scores,
+                  workspace, workspace_bytes, (cudaStream_t)stream);
 }

@@ -685,6 +685,39 @@ def topk(q: torch.Tensor, items: torch.Tensor, k: int, *, id_offset: int = 0, af
     return ids, scores
 
 
+TOPK_TC_MAX_D = 256       # csrc/topk_tc.cu: kMaxD (both tensor-core paths)
+
+
+def split_bf16x3(x: torch.Tensor, *, item_layout: bool) -> torch.Tensor:
+    """fp32 [R, D] -> bf16 [R, 3*ceil16(D)]: the 3-way split operand of `topk_f32_tc` (items: [hi|hi|lo], queries: [hi|lo|hi])."""
+    _chk(x, torch.float32, "x")
+    x = x.contiguous()
+    R, D = x.shape
+    out = torch.empty((R, int(lib().ttam_split_bf16x3_cols(D))), dtype=torch.bfloat16, device=x.device)
+    check(lib().ttam_split_bf16x3(x.data_ptr(), R, D, 1 if item_layout else 0, out.data_ptr(), _stream()), "split_bf16x3")
+    return out
+
+
+def topk_f32_tc(q: torch.Tensor, items: torch.Tensor, items_split: torch.Tensor, k: int, *, id_offset: int = 0):
+    """`topk` for fp32 operands with the candidate pass on the tensor cores (k <= 128, D <= 256): same ids and scores,
+    bit for bit, as the SIMT path.  items_split = split_bf16x3(items, item_layout=True), kept by the index."""
+    _chk(q, torch.float32, "q"); _chk(items, torch.float32, "items"); _chk(items_split, torch.bfloat16, "items_split")
+    if not (q.is_cuda and items.is_cuda):
+        raise _lib.TtamError("topk needs CUDA tensors; there is no CPU path")
+    q = q.contiguous(); items = items.contiguous()
+    Q, D = q.shape
+    N = items.shape[0]
+    k_eff = min(k, N)
+    q_split = split_bf16x3(q, item_layout=False)
+    ids = torch.empty((Q, k_eff), dtype=torch.int64, device=q.device)
+    scores = torch.empty((Q, k_eff), dtype=torch.float32, device=q.device)
+    L = lib()
+    ws = workspace(L.ttam_topk_f32_tc_workspace_bytes(Q, N, D, k_eff), q.device, "topk")
+    check(L.ttam_topk_f32_tc(q.data_ptr(), items.data_ptr(), q_split.data_ptr(), items_split.data_ptr(), Q, N, D, k_eff,
+                             id_offset, ids.data_ptr(), scores.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "topk_f32_tc")
+    return ids, scores
+
+
 def topk_merge(ids: torch.Tensor, scores: torch.Tensor, k_out: int):
     """ids/scores [Q, parts, K_in] -> best k_out per query under (-score,+id)."""
     Q, parts, k_in = ids.shape

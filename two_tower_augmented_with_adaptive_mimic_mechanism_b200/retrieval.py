@@ -23,11 +23,14 @@ def l2_normalize(x: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
 class FlatIPIndex:
     """Exact inner-product index over an item corpus resident in HBM (the IndexFlatIP stand-in).
 
-    `dtype=torch.float32` keeps the reference's fp32 scores (SIMT kernel); `torch.bfloat16` rounds corpus and
-    queries to bf16 and scores them on the tcgen05 tensor cores (BASELINE config 3)."""
+    `dtype=torch.float32` keeps the reference's fp32 scores: searches with k <= 128 run their candidate pass on the
+    tcgen05 tensor cores over a 3-way bf16 split of the corpus (kept beside it, built on first use: 6 x D bytes per item)
+    and re-score the survivors from the fp32 rows - ids and scores are bit-identical to the SIMT kernel, which deeper
+    or paged searches still use (`tensor_cores=False` forces it everywhere).  `torch.bfloat16` rounds corpus and queries
+    to bf16 and scores them on the tensor cores directly (BASELINE config 3)."""
 
     def __init__(self, item_embeddings: torch.Tensor, *, normalize: bool = False, dtype=torch.float32,
-                 id_offset: int = 0) -> None:
+                 id_offset: int = 0, tensor_cores: bool = True) -> None:
         if not item_embeddings.is_cuda:
             raise F._lib.TtamError("FlatIPIndex needs a CUDA corpus; there is no CPU path")
         x = item_embeddings.float()
@@ -38,6 +41,8 @@ class FlatIPIndex:
         self.id_offset = int(id_offset)
         self.items = x.contiguous() if dtype == torch.float32 else F.cast_bf16(x.contiguous())
         self.ntotal, self.d = self.items.shape
+        self.tensor_cores = bool(tensor_cores) and dtype == torch.float32 and self.d <= F.TOPK_TC_MAX_D
+        self._items_split = None
 
     @property
     def max_k(self) -> int:
@@ -55,7 +60,12 @@ class FlatIPIndex:
         after = (scores [Q], ids [Q]): only results ranked strictly after that pair (fp32 index)."""
         q = self._prepare(queries)
         k_eff = min(int(k), self.ntotal)
-        ids, scores = F.topk(q, self.items, k_eff, id_offset=self.id_offset, after=after)
+        if self.tensor_cores and after is None and k_eff <= F.TOPK_BF16_MAX_K:
+            if self._items_split is None:
+                self._items_split = F.split_bf16x3(self.items, item_layout=True)
+            ids, scores = F.topk_f32_tc(q, self.items, self._items_split, k_eff, id_offset=self.id_offset)
+        else:
+            ids, scores = F.topk(q, self.items, k_eff, id_offset=self.id_offset, after=after)
         if k_eff < k:
             pad_i = torch.full((q.shape[0], k - k_eff), -1, dtype=torch.int64, device=q.device)
             pad_s = torch.full((q.shape[0], k - k_eff), float("-inf"), dtype=torch.float32, device=q.device)
@@ -117,8 +127,8 @@ def filter_block(ids: np.ndarray, need: Sequence[int], users: Sequence[int], gro
     membership is one searchsorted over (row, item) keys, the survivors' first max_k columns one stable argsort.  Rows
     that keep fewer (their ground truth gets appended) or repeat an id go through `filter_candidates` itself, so the
     result is the reference's for every row.
-    deeper(r, k) -> list of row r's first k candidates: called for the rare row that keeps fewer than max_k of its K
-    columns although the reference would have asked for more than K results (a user with more training positives than
+    deeper(rows, k) -> {row: its first k candidates}: called once, for the rare rows that keep fewer than max_k of their
+    K columns although the reference would have asked for more than K results (a user with more training positives than
     one launch returns)."""
     ids = np.asarray(ids, dtype=np.int64)
     n, K = ids.shape
@@ -145,12 +155,15 @@ def filter_block(ids: np.ndarray, need: Sequence[int], users: Sequence[int], gro
     if take > 1:
         srt = np.sort(sel, axis=1)
         fast &= ~(srt[:, 1:] == srt[:, :-1]).any(axis=1)                 # a repeated id: the reference drops it, go slow
+    # rows that need a longer candidate list than the K columns given: fetched in ONE call, deeper(rows, k) -> {row: list}
+    short = [r for r in range(n) if not fast[r] and int(need[r, 0]) > K] if deeper is not None else []
+    longer = deeper(short, max(int(need[r, 0]) for r in short)) if short else {}
     for r, u in enumerate(users):
         if fast[r]:
             out[u] = sel[r].tolist()
         else:
             k_r = int(need[r, 0])
-            row = ids[r, :k_r].tolist() if (k_r <= K or deeper is None) else deeper(r, k_r)
+            row = longer[r][:k_r] if r in longer else ids[r, :k_r].tolist()
             out[u] = filter_candidates(row, set(train_positive_map.get(u, ())), ground_truth[u], max_k)
     return out
 
@@ -169,9 +182,15 @@ def evaluate_users(index: FlatIPIndex, user_embeddings: torch.Tensor, user_ids: 
         # one launch returns at most index.max_k results per query; search_k grows with a user's number of training
         # positives (training.py:956-958), so a heavy user can ask for more: such a row is only walked further down
         # (search_deep) when its first max_k columns do not already hold max_k unblocked items
-        k_blk = min(max(need), index.ntotal, index.max_k)
+        # (an fp32 index first asks for at most the 128 results its tensor-core pass returns; the rows that fall short go
+        # through the SIMT kernel together)
+        k_blk = min(max(need), index.ntotal, F.TOPK_BF16_MAX_K if getattr(index, "tensor_cores", False) else index.max_k)
         q_blk = user_embeddings[s:s + len(blk)]
         ids, _ = index.search(q_blk, k_blk)
-        deeper = lambda r, k, q_blk=q_blk: index.search_deep(q_blk[r:r + 1], k)[0][0].tolist()
+
+        def deeper(rows, k, q_blk=q_blk):
+            sel = torch.as_tensor(rows, dtype=torch.int64, device=q_blk.device)
+            got = index.search_deep(q_blk.index_select(0, sel), k)[0]
+            return {r: got[j].tolist() for j, r in enumerate(rows)}
         preds.update(filter_block(ids.cpu().numpy(), need, blk, ground_truth, train_positive_map, max_k, deeper=deeper))
     return preds
