@@ -661,11 +661,9 @@ def main():
         line["gpu_launches"] = (int(sh.launches_per_step) * K if args.route != "dynamic" and not args.no_graph else
                                 int((F.lib().ttam_launch_count() - launches0) * K / steps_launched))
 
-    if not args.no_retrieval and c["D"] > 128:
-        if rank == 0:
-            line["retrieval"] = {"skipped": f"the bf16 tensor-core top-K takes D <= 128 (this config has D = {c['D']}); FlatIPIndex(dtype=float32) covers it"}
-    elif not args.no_retrieval:
-        r = bench_retrieval(tt, c, dev, pk, world=world, rank=rank)
+    if not args.no_retrieval:
+        # config 4 searches its own corpus (50M x 256, item-sharded); config 2 the 2M x 96 corpus of BASELINE configs[2]
+        r = bench_retrieval(tt, c, dev, pk, NI=c["NI"] if args.config == 4 else 2_000_000, world=world, rank=rank)
         if rank == 0:
             line["retrieval"] = r
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -695,15 +693,15 @@ def bench_retrieval(tt, c, dev, pk, Q=100_000, NI=2_000_000, K=100, world=1, ran
     lists of its own query block after an all-to-all."""
     from two_tower_augmented_with_adaptive_mimic_mechanism_b200 import functional as F
     import torch.distributed as dist
-    g = torch.Generator(device=dev).manual_seed(7)              # same corpus / queries on every rank
-    items = (torch.randn((NI, c["D"]), device=dev, generator=g) * 0.3)
+    g = torch.Generator(device=dev).manual_seed(7)              # same queries on every rank
     q = (torch.randn((Q - Q % world, c["D"]), device=dev, generator=g) * 0.3)
     out = {}
     if world > 1:
         per = (NI + world - 1) // world
         lo, hi = rank * per, min(NI, (rank + 1) * per)
-        index = tt.ShardedFlatIPIndex(items[lo:hi].contiguous(), dtype=torch.bfloat16, contiguous_offset=lo)
-        del items
+        gs = torch.Generator(device=dev).manual_seed(70 + rank)  # each rank draws its own shard of the corpus
+        index = tt.ShardedFlatIPIndex(torch.randn((hi - lo, c["D"]), device=dev, generator=gs) * 0.3, dtype=torch.bfloat16,
+                                      contiguous_offset=lo)
         index.search(q, K)
         dist.barrier(); torch.cuda.synchronize()
         best = float("inf")
@@ -719,15 +717,23 @@ def bench_retrieval(tt, c, dev, pk, Q=100_000, NI=2_000_000, K=100, world=1, ran
                        "items_per_gpu": hi - lo, "tflops": flops / (best * 1e-3) / 1e12,
                        "frac_of_bf16_peak": flops / (best * 1e-3) / 1e12 / (pk["tf"] * world)}
         return out
-    for name, (qi, it) in {"bf16": (q.bfloat16(), items.bfloat16()), "f32": (q[:1024], items)}.items():
+    items = (torch.randn((NI, c["D"]), device=dev, generator=g) * 0.3)
+    # bf16: BASELINE configs[2] (bf16 corpus).  f32: the fp32 index the drop-in evaluation hooks build (FlatIPIndex default):
+    # candidate pass on the tensor cores over a 3-way bf16 split (3x the MMA work), canonical fp32 re-score - bit-identical
+    # to f32_simt, the SIMT kernel that deeper (k > 128) and paged searches use.
+    items_split = F.split_bf16x3(items, item_layout=True)
+    paths = {"bf16": (q.bfloat16(), items.bfloat16(), lambda a, b: F.topk(a, b, K), 1.0),
+             "f32": (q, items, lambda a, b: F.topk_f32_tc(a, b, items_split, K), 3.0),
+             "f32_simt": (q[:4096], items, lambda a, b: F.topk(a, b, K), 1.0)}
+    for name, (qi, it, fn, mma_mult) in paths.items():
         try:
-            F.topk(qi, it, K)                          # warm-up at the timed shape (sizes the workspace)
+            fn(qi, it)                                 # warm-up at the timed shape (sizes the workspace)
             torch.cuda.synchronize()
             msr = float("inf")
             for _ in range(3):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                F.topk(qi, it, K)
+                fn(qi, it)
                 e1.record()
                 torch.cuda.synchronize()
                 msr = min(msr, e0.elapsed_time(e1))
@@ -735,9 +741,14 @@ def bench_retrieval(tt, c, dev, pk, Q=100_000, NI=2_000_000, K=100, world=1, ran
             tf = flops / (msr * 1e-3) / 1e12
             out[name] = {"queries_per_s": qi.shape[0] / (msr * 1e-3), "ms": msr, "queries": qi.shape[0], "items": NI,
                          "tflops": tf, "frac_of_bf16_peak": tf / pk["tf"],
-                         "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["tf"], "unit": "TFLOP/s", "frac": tf / pk["tf"],
+                         "roofline": {"bound": "tensor", "achieved": tf * mma_mult, "peak": pk["tf"], "unit": "TFLOP/s",
+                                      "frac": tf * mma_mult / pk["tf"],
                                       "traffic": None, "peak_source": pk["source"] + " (sustained bf16)",
-                                      "algorithmic_flops": flops, "kernel": "score_topk_kernel + finalize (whole ttam_topk call)"}}
+                                      "algorithmic_flops": flops, "tensor_core_flops": flops * mma_mult,
+                                      "kernel": "score_topk_kernel + finalize (whole ttam_topk call)"}}
+            if name == "f32_simt":
+                out[name]["roofline"].update(bound="fp32 SIMT (canonical mul + add per product, no FMA)",
+                                             kernel="gemm_f32_kernel + select_topk_kernel per 4096-item chunk")
             # end to end through the public API: HOST queries (pinned) -> H2D -> search -> ids + scores D2H
             hq = qi.cpu().pin_memory()
             dq = torch.empty_like(qi)
@@ -748,7 +759,7 @@ def bench_retrieval(tt, c, dev, pk, Q=100_000, NI=2_000_000, K=100, world=1, ran
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 dq.copy_(hq, non_blocking=True)
-                ids, sc = F.topk(dq, it, K)
+                ids, sc = fn(dq, it)
                 h_ids.copy_(ids, non_blocking=True); h_sc.copy_(sc, non_blocking=True)
                 e1.record()
                 torch.cuda.synchronize()

@@ -104,7 +104,9 @@ __global__ void __launch_bounds__(SLOT_BLOCK) slot_place_kernel(const int64_t* _
         slot_of[i] = s;
         if (j == 0) first[o] = id;
       } else {
-        slot_of[i] = n_slots;                               // does not fit: the step takes the dynamic route (flag)
+        // does not fit: the step takes the dynamic route (flag).  The forward half of the step may already be running when
+        // the host learns that (ShardedEngine: speculative replay); every consumer of slot_of skips this marker.
+        slot_of[i] = n_slots;
       }
     }
     __syncthreads();
@@ -130,7 +132,8 @@ __global__ void __launch_bounds__(256) slot_pad_kernel(int W, int64_t cap, const
       // padding repeats REAL ids of the bucket (zero gradient rows: the owner's touched-row sets stay exact), cycling through
       // them: repeating only the first one handed the owner one segment of ~cap - count duplicates, which the long-segment
       // kernels of the row-wise optimisers then summed serially (85-96 us per table at N = 2)
-      send_idx[s] = cnt > 0 ? send_idx[(int64_t)o * cap + (j - cnt) % (cnt < cap ? cnt : cap)] : first[o];
+      // (an EMPTY bucket raises the flag too; until the host has seen it the slots must hold a row its owner has: row o)
+      send_idx[s] = cnt > 0 ? send_idx[(int64_t)o * cap + (j - cnt) % (cnt < cap ? cnt : cap)] : (int64_t)o;
       req_of[s] = -1;
     }
   }

@@ -45,6 +45,8 @@ class _Static:
         if torch.device(device).type == "cuda":
             self.flag_host = self.flag_host.pin_memory()
         self.graph_plan = self.graph_main = None
+        self.graph_bwd = None               # speculative replay: graph_main holds the forward + loss half, this the rest
+        self.flag_event = torch.cuda.Event() if torch.device(device).type == "cuda" else None
         self.loss = None
         self.x_key = None
         self.calib_left = 0                 # calibration steps still to run on this shape (see ShardedEngine._calibrate)
@@ -92,11 +94,46 @@ class ShardedEngine:
             return False
         return F.loss_aug_supported(N, D)
 
-    def _body(self, ex_u, ex_i, items, B, N, user_x_shard, item_x_shard):
-        eng, W = self.eng, self.world
+    def _speculative(self, st: "_Static") -> bool:
+        """Can the forward + loss half of the step be launched before the host has read the overflow flag?  It must not
+        change anything a discarded step would have to undo: that holds for the peer route with the fused pull + loss + push
+        kernel (buffers only; the lazy catch-up it runs is value-preserving; the device step counter is rewound)."""
+        eng = self.eng
+        return (os.environ.get("TTAM_SPECULATE", "1") != "0" and st.ex_i.peer is not None and bool(eng.mimic)
+                and self._fused_slot_loss(st.N, eng.user.out_dim))
+
+    def _body_fwd(self, ex_u, ex_i, B, N, user_x_shard, item_x_shard):
+        """Owner-side forward, then pull, loss and push as ONE kernel: the pair's rows are loaded from their owners and its
+        gradient rows stored into the owners' receive buffers (zeroed at the start of the step: padding slots keep zero
+        rows).  Writes buffers only (see _speculative)."""
+        eng = self.eng
         ctx = eng._forward_phase(ex_u.local_rows.contiguous(), ex_i.local_rows.contiguous(), user_x_shard, item_x_shard)
         cu, ci = ctx["cu"], ctx["ci"]
+        ex_u.publish(cu.t, cu.q)
+        ex_i.publish(ci.t, ci.q)
+        ex_i.peer_barrier()               # every owner's rows are in place
+        loss = eng._misc("loss", (4,), torch.float32)
+        F.loss_slots_fwd_bwd(ex_u._peer_bases(0), ex_u._peer_bases(1), ex_i._peer_bases(0), ex_i._peer_bases(1),
+                             ex_u._peer_bases(2), ex_u._peer_bases(3), ex_i._peer_bases(2), ex_i._peer_bases(3),
+                             ex_u.cap, ex_i.cap, ex_u.slot_of, ex_i.slot_of, B, N, cu.t.shape[1], lambda_u=eng.lambda_u,
+                             lambda_i=eng.lambda_i, loss=loss, batch_fraction=1.0 / self.world)
+        ex_i.peer_barrier()               # every requester's gradient rows have landed
+        return ctx, loss
+
+    def _body_bwd(self, ctx, ex_u, ex_i) -> None:
+        self.eng._backward_phase(ctx, ex_u.recv_a, ex_i.recv_a, ex_u.recv_b, ex_i.recv_b,
+                                 dense_grad_hook=self._hook if self.world > 1 else None)
+
+    def _body(self, ex_u, ex_i, items, B, N, user_x_shard, item_x_shard):
+        eng, W = self.eng, self.world
         mimic = bool(eng.mimic)
+        if (isinstance(ex_u, S.SlotExchange) and ex_i.peer is not None and mimic
+                and self._fused_slot_loss(N, eng.user.out_dim)):
+            ctx, loss = self._body_fwd(ex_u, ex_i, B, N, user_x_shard, item_x_shard)
+            self._body_bwd(ctx, ex_u, ex_i)
+            return loss
+        ctx = eng._forward_phase(ex_u.local_rows.contiguous(), ex_i.local_rows.contiguous(), user_x_shard, item_x_shard)
+        cu, ci = ctx["cu"], ctx["ci"]
         D = cu.t.shape[1]
         hook = self._hook if W > 1 else None
         bf = 1.0 / W
@@ -106,17 +143,6 @@ class ShardedEngine:
                 ex_u.publish(cu.t, cu.q if mimic else None)
                 ex_i.publish(ci.t, ci.q if mimic else None)
                 ex_i.peer_barrier()               # every owner's rows are in place
-            if peer and mimic and self._fused_slot_loss(N, D):
-                # pull, loss and push as ONE kernel: the pair's rows are loaded from their owners and its gradient rows stored
-                # into the owners' receive buffers (zeroed at the start of the step: padding slots keep zero rows)
-                loss = eng._misc("loss", (4,), torch.float32)
-                F.loss_slots_fwd_bwd(ex_u._peer_bases(0), ex_u._peer_bases(1), ex_i._peer_bases(0), ex_i._peer_bases(1),
-                                     ex_u._peer_bases(2), ex_u._peer_bases(3), ex_i._peer_bases(2), ex_i._peer_bases(3),
-                                     ex_u.cap, ex_i.cap, ex_u.slot_of, ex_i.slot_of, B, N, D, lambda_u=eng.lambda_u,
-                                     lambda_i=eng.lambda_i, loss=loss, batch_fraction=bf)
-                ex_i.peer_barrier()               # every requester's gradient rows have landed
-                eng._backward_phase(ctx, ex_u.recv_a, ex_i.recv_a, ex_u.recv_b, ex_i.recv_b, dense_grad_hook=hook)
-                return loss
             if mimic:
                 t_u, q_u, o_u = ex_u.pull(cu.t, cu.q)
                 t_i, q_i, o_i = ex_i.pull(ci.t, ci.q)
@@ -270,7 +296,7 @@ class ShardedEngine:
         cap_u = st.ex_u.cap if big_u <= st.ex_u.cap else S.grown_slot_capacity(big_u, B)
         cap_i = st.ex_i.cap if big_i <= st.ex_i.cap else S.grown_slot_capacity(big_i, B * (1 + N))
         # the dynamic step may have re-allocated engine buffers the recorded graphs point into: never replay them again
-        st.graph_plan = st.graph_main = None
+        st.graph_plan = st.graph_main = st.graph_bwd = None
         if (cap_u, cap_i) != (st.ex_u.cap, st.ex_i.cap):       # (an EMPTY bucket also raises the flag: nothing to grow then)
             self.capacity = (cap_u, cap_i)
             del self._static[(B, N)]
@@ -285,11 +311,25 @@ class ShardedEngine:
         x_key = (None if user_x_shard is None else user_x_shard.data_ptr(), None if item_x_shard is None else item_x_shard.data_ptr())
         # no graph is recorded before the calibration steps of the shape are over: the slots may still be re-sized
         use_graph = graph and users.is_cuda and st.calib_left == 0
-        if use_graph and st.graph_main is not None and st.x_key == x_key:
+        replay = use_graph and st.graph_main is not None and st.x_key == x_key
+        speculated = False
+        if replay:
             st.graph_plan.replay()
+            if st.graph_bwd is not None:
+                # Forward + loss go out BEFORE the host looks at the flag: its copy lands while they run, so the host round
+                # trip (read the flag, launch the rest) no longer leaves the GPU idle.  A step that overflowed throws the
+                # speculative half away: it wrote buffers only, the device step counter is rewound below.
+                st.flag_event.record()
+                eng.begin_step()
+                st.graph_main.replay()
+                st.flag_event.synchronize()
+                speculated = True
         else:
             self._plan(st)
-        if self._overflowed(st):
+        if (bool(int(st.flag_host[0])) if speculated else self._overflowed(st)):
+            if speculated:
+                eng.t -= 1
+                eng.state.sub_(torch.tensor([1, 1 << 36], dtype=torch.int64, device=eng.state.device))
             self.fallback_steps += 1
             loss = self._dynamic_step(users, pos, neg, user_x_shard, item_x_shard)
             self._calibrated.add((B, N))         # the slots are about to be sized from a real overflow
@@ -297,8 +337,11 @@ class ShardedEngine:
             return loss
         calibrating = st.calib_left > 0
         self.last_exchange_rows = (st.ex_u.n_slots, st.ex_i.n_slots)
+        if speculated:
+            st.graph_bwd.replay()
+            return st.loss
         eng.begin_step()
-        if use_graph and st.graph_main is not None and st.x_key == x_key:
+        if replay:
             st.graph_main.replay()
             return st.loss
         count = getattr(eng, "launch_count", None)
@@ -313,8 +356,16 @@ class ShardedEngine:
             gp, gm = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(gp, capture_error_mode="thread_local"):
                 self._plan(st)
-            with torch.cuda.graph(gm, capture_error_mode="thread_local"):
-                st.loss = self._main(st, user_x_shard, item_x_shard)
+            if self._speculative(st):
+                gb = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gm, capture_error_mode="thread_local"):
+                    ctx, st.loss = self._body_fwd(st.ex_u, st.ex_i, st.B, st.N, user_x_shard, item_x_shard)
+                with torch.cuda.graph(gb, pool=gm.pool(), capture_error_mode="thread_local"):
+                    self._body_bwd(ctx, st.ex_u, st.ex_i)
+                st.graph_bwd = gb
+            else:
+                with torch.cuda.graph(gm, capture_error_mode="thread_local"):
+                    st.loss = self._main(st, user_x_shard, item_x_shard)
             st.graph_plan, st.graph_main, st.x_key = gp, gm, x_key
         if calibrating:
             self._calibrate(st)
