@@ -178,6 +178,7 @@ struct MainParams {
   int qblocks, tiles_total, tiles_per_split;
   int sample_tiles;  // T0: tiles of a unit's range visited first in sampling mode (0 = none)
   int kbox, stages;  // box-ring variant only: 64-column boxes per tile, ring slots
+  int trig;          // a row's list is compacted to its best kKeep .. kKeep + kSlack once it holds more than this
   uint2* lists;     // [Q][S][kCap] raw {score bits, id}
   int32_t* cnts;    // [Q][S]
   float* taus;      // [Q][S]
@@ -379,6 +380,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
       const bool valid = qrow < p.Q;
       float tau = valid ? -INFINITY : INFINITY;  // rows past the end never collect anything
       int cnt = 0;
+      const int trig = p.trig;   // list length that triggers a compaction (<= kCap - 64: room for a chunk pair of appends)
       const int64_t slot = (valid ? qrow : 0) * p.S + s;
       uint2* buf = p.lists + slot * kCap;
       // A pair of 32-column chunks of this thread's row per iteration (two tcgen05.ld in flight, two independent max
@@ -404,15 +406,23 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         for (int q4 = 0; q4 < 4; ++q4) m4[q4] = fmaxf(fmaxf(m[4 * q4], m[4 * q4 + 1]), fmaxf(m[4 * q4 + 2], m[4 * q4 + 3]));
         const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
         if (__any_sync(0xffffffffu, mx > tau) && !(p.debug & 2)) {
-          // usually one or two of the warp's 2048 scores beat their row's threshold: descend with warp votes (uniform
-          // branches) into the 16-column quarters and 4-column groups that hold them, append with predicated stores
+          // usually one or two of the warp's 2048 scores beat their row's threshold.  Descend into the 16-column quarters
+          // and 4-column groups that hold them; the votes of a level are issued back to back BEFORE the first branch on
+          // them (a branch between two votes serialises their latencies: the nested any-per-branch form of this descent
+          // cost ~40 % of the kernel), the branches are warp-uniform, the appends predicated stores.
+          unsigned qv[4];
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) qv[q4] = __ballot_sync(0xffffffffu, m4[q4] > tau);
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
-            if (__any_sync(0xffffffffu, m4[q4] > tau)) {
+            if (qv[q4]) {
+              unsigned gv[4];
+#pragma unroll
+              for (int gg = 0; gg < 4; ++gg) gv[gg] = __ballot_sync(0xffffffffu, m[4 * q4 + gg] > tau);
 #pragma unroll
               for (int gg = 0; gg < 4; ++gg) {
                 const int g = 4 * q4 + gg;
-                if (__any_sync(0xffffffffu, m[g] > tau)) {
+                if (gv[gg]) {
 #pragma unroll
                   for (int i = 0; i < 4; ++i) {
                     const uint32_t bits = g < 8 ? v0[4 * (g & 7) + i] : v1[4 * (g & 7) + i];
@@ -428,7 +438,7 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         }
       };
       auto make_room = [&]() {
-        unsigned need = __ballot_sync(0xffffffffu, cnt > kCap - 64);
+        unsigned need = __ballot_sync(0xffffffffu, cnt > trig);
         while (need) {
           const int r = __ffs(need) - 1;
           need &= need - 1;
@@ -881,6 +891,11 @@ static int run_topk(const uint16_t* qm, const uint16_t* im, int64_t Dm, const fl
   mp.kbox = sh.kbox; mp.stages = sh.stages;
   mp.sample_tiles = 64;
   if (const char* e = getenv("TTAM_TOPK_SAMPLE_TILES")) mp.sample_tiles = atoi(e);
+  mp.trig = kCap - 64;
+  if (const char* e = getenv("TTAM_TOPK_TRIG")) {   // A/B switch
+    const int v = atoi(e);
+    if (v >= kKeep + kSlack && v <= kCap - 64) mp.trig = v;
+  }
   {
     const char* dbg = getenv("TTAM_TOPK_DEBUG");
     mp.debug = dbg ? atoi(dbg) : 0;
