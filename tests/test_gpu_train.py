@@ -290,3 +290,40 @@ def test_static_slot_route_overflow_falls_back_and_grows():
     got, ref = model_state_np(model), state_after(d, meta["steps"] - 1)
     for k in ref:
         np.testing.assert_allclose(got[k], ref[k], rtol=RTOL, atol=ATOL, err_msg=f"{name} {k}")
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_resume_from_optimizer_state_continues_bit_identically(graph):
+    """FusedEngine.load_optimizer_state: an engine rebuilt from the parameters and moments after step 1 (what a checkpoint
+    holds) takes step 2 exactly as the engine that never stopped - bias corrections, lazily-updated rows and the SparseAdam
+    moments continue where they were."""
+    name = "train_gated_mlp"
+    d, meta, init = load_case(name)
+    kw = TRAIN_CASES[name]
+    ux, ix = torch.from_numpy(d["user_x"]).cuda(), torch.from_numpy(d["item_x"]).cuda()
+    batches = [tuple(torch.from_numpy(d[f"step{s}/{k}"]).cuda() for k in ("users", "pos", "neg")) for s in range(meta["steps"])]
+    model_a = build_model(meta, kw, init, "cuda")
+    eng_a = _engine(model_a, meta, kw)
+    for s in range(2):
+        eng_a.train_step(*batches[s], ux, ix, graph=graph)
+    eng_a.flush()                                                                          # what a checkpoint does first
+    saved_params = {k: v.clone() for k, v in model_a.state_dict().items()}
+    saved_opt = {k: {kk: (vv.clone() if torch.is_tensor(vv) else vv) for kk, vv in ent.items()} for k, ent in eng_a.optimizer_state().items()}
+    loss_a = eng_a.train_step(*batches[2], ux, ix, graph=graph).clone()
+    eng_a.flush()
+    model_b = build_model(meta, kw, {k: v.cpu().numpy() for k, v in saved_params.items()}, "cuda")
+    eng_b = _engine(model_b, meta, kw)
+    eng_b.load_optimizer_state(saved_opt, 2)
+    loss_b = eng_b.train_step(*batches[2], ux, ix, graph=graph).clone()
+    eng_b.flush()
+    torch.cuda.synchronize()
+    assert torch.equal(loss_a, loss_b)
+    sa, sb = model_a.state_dict(), model_b.state_dict()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    oa, ob = eng_a.optimizer_state(), eng_b.optimizer_state()
+    for k in oa:
+        for slot in ("exp_avg", "exp_avg_sq"):
+            if oa[k][slot] is not None:
+                assert torch.equal(oa[k][slot], ob[k][slot]), (k, slot)
+    assert float(loss_b[0]) == pytest.approx(float(d["losses"][2]), rel=5e-6, abs=1e-7)

@@ -261,9 +261,9 @@ class _TinyModel(torch.nn.Module):
 
     def __init__(self, nu, ni, d):
         super().__init__()
-        mk = lambda n: torch.nn.Embedding(n, d)
-        self.user_encoder = torch.nn.Module(); self.user_encoder.embedding = mk(nu)
-        self.item_encoder = torch.nn.Module(); self.item_encoder.embedding = mk(ni)
+        mk = lambda n, sparse=False: torch.nn.Embedding(n, d, sparse=sparse)
+        self.user_encoder = torch.nn.Module(); self.user_encoder.embedding = mk(nu, True)
+        self.item_encoder = torch.nn.Module(); self.item_encoder.embedding = mk(ni, True)
         self.item_encoder.dense = torch.nn.Linear(d, d)
         self.adaptive_mimic = torch.nn.Module()
         self.adaptive_mimic.user_augmented = mk(nu); self.adaptive_mimic.item_augmented = mk(ni)
@@ -277,7 +277,10 @@ class _TinyEngine:
         self.flushed += 1
 
     def optimizer_state(self):
-        return {n: {"step": 3, "exp_avg": p.detach() * 2, "exp_avg_sq": None} for n, p in self.model.named_parameters()}
+        return {n: {"step": 3, "exp_avg": p.detach() * 2, "exp_avg_sq": p.detach() ** 2} for n, p in self.model.named_parameters()}
+
+    def load_optimizer_state(self, state, step):
+        self.loaded = (state, step)
 
 
 def _checkpoint_worker(rank, world, out_dir):
@@ -301,8 +304,27 @@ def _checkpoint_worker(rank, world, out_dir):
     ck = torch.load(path, weights_only=False)
     assert set(ck) == {"epoch", "model_state_dict", "optimizer_state_dicts", "metric_name", "metric_value", "timestamp"}
     assert ck["epoch"] == 4 and all(torch.equal(ck["model_state_dict"][k], ref[k]) for k in ref)
-    opt = ck["optimizer_state_dicts"][0]
-    assert torch.equal(opt["adaptive_mimic.item_augmented.weight"]["exp_avg"], 2 * ref["adaptive_mimic.item_augmented.weight"])
+    # optimizer_state_dicts = [dense optimiser, SparseAdam] in torch's own layout, parameters in the reference's order
+    # (training.py:276-309, 1315-1346): the reference's optimisers load them as they are
+    dense_p = list(full.item_encoder.dense.parameters()) + [full.adaptive_mimic.user_augmented.weight, full.adaptive_mimic.item_augmented.weight]
+    sparse_p = [full.user_encoder.embedding.weight, full.item_encoder.embedding.weight]
+    adamw, sadam = torch.optim.AdamW(dense_p), torch.optim.SparseAdam(sparse_p)
+    adamw.load_state_dict(ck["optimizer_state_dicts"][0])
+    sadam.load_state_dict(ck["optimizer_state_dicts"][1])
+    assert torch.equal(adamw.state[full.adaptive_mimic.item_augmented.weight]["exp_avg"], 2 * ref["adaptive_mimic.item_augmented.weight"])
+    assert torch.equal(sadam.state[full.user_encoder.embedding.weight]["exp_avg_sq"], ref["user_encoder.embedding.weight"] ** 2)
+    assert float(adamw.state[dense_p[0]]["step"]) == 3.0 and sadam.state[sparse_p[1]]["step"] == 3
+    # ... and back: tables and moments return to the ranks that own their rows
+    with torch.no_grad():
+        for prm in sh.eng.model.parameters():
+            prm.zero_()
+    meta_back = sh.load_checkpoint(path)
+    assert meta_back == {"epoch": 4, "metric_name": "recall@10", "metric_value": 0.5}
+    assert torch.equal(sh.eng.model.state_dict()["item_encoder.embedding.weight"], ref["item_encoder.embedding.weight"][rank::world])
+    state, step = sh.eng.loaded
+    assert step == 3 and set(state) == set(ref)
+    assert torch.equal(state["adaptive_mimic.user_augmented.weight"]["exp_avg"], 2 * ref["adaptive_mimic.user_augmented.weight"][rank::world])
+    assert torch.equal(state["item_encoder.dense.weight"]["exp_avg_sq"], ref["item_encoder.dense.weight"] ** 2)
     with pytest.raises(ValueError):
         S.gather_rows_from_shards(torch.zeros(1, D), NU, None)                     # wrong shard length for this rank
 

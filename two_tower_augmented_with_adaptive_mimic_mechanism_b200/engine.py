@@ -674,6 +674,33 @@ class FusedEngine:
         return loss
 
     # --------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def load_optimizer_state(self, state: dict, step: int) -> None:
+        """Inverse of `optimizer_state`: {name: {exp_avg, exp_avg_sq}} (this engine's shapes; missing entries stay zero) and
+        the number of optimiser steps taken.  Every row of a lazily-updated table counts as up to date at `step` (what
+        `optimizer_state` exported was flushed).  Resuming continues the bias corrections and the dropout counters from there."""
+        step = int(step)
+        self._ensure_steps(step + 1)
+        names = {id(p): n for n, p in self.model.named_parameters()}
+        slots = {name: (tab.m, tab.v) for name, tab in self.tables.items()}
+        for j, p in enumerate(self.dense):
+            slots[names.get(id(p), f"dense{j}")] = (None if self.dense_m is None else self.dense_m[j],
+                                                    None if self.dense_v is None else self.dense_v[j])
+        for name, ent in state.items():
+            if name not in slots:
+                raise KeyError(f"optimizer state for an unknown parameter: {name}")
+            for dst, key in zip(slots[name], ("exp_avg", "exp_avg_sq")):
+                src = ent.get(key)
+                if dst is not None and src is not None:
+                    dst.copy_(torch.as_tensor(src).to(dst.device, dst.dtype).view_as(dst))
+        for tab in self.tables.values():
+            if tab.last_step is not None:
+                tab.last_step.fill_(step)
+        self.t = step
+        self.dirty = False
+        self.state.copy_(F.new_step_state(self.device, step, step << 36))      # _forward_phase advances the counter by 1 << 36 a step
+        self._graphs.clear()
+
     def optimizer_state(self) -> dict:
         """Per-parameter optimiser state in torch.optim layout ({name: {step, exp_avg, exp_avg_sq}})."""
         self.flush()

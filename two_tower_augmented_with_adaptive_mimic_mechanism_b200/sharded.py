@@ -413,29 +413,110 @@ class ShardedEngine:
             mine[name] = S.shard_rows(t, self.rank, self.world) if self._is_row_sharded(name) else t
         self.eng.model.load_state_dict(mine)
 
+    def _reference_param_groups(self):
+        """(dense names, sparse names) in the order the reference hands the parameters to its two optimisers
+        (`_collect_parameter_groups`, training.py:276-309): per encoder the embedding weight first (SparseAdam when the
+        embedding is sparse), then its other parameters, then whatever the model has left (the augmentation tables)."""
+        model = self.eng.model
+        names = {id(p): n for n, p in model.named_parameters()}
+        dense, sparse, seen = [], [], set()
+
+        def add(p, coll):
+            if id(p) not in seen:
+                seen.add(id(p))
+                coll.append(names[id(p)])
+        for enc in (model.user_encoder, model.item_encoder):
+            emb = getattr(enc, "embedding", None)
+            if isinstance(emb, torch.nn.Embedding):
+                add(emb.weight, sparse if getattr(emb, "sparse", False) else dense)
+            for n, p in enc.named_parameters():
+                if n != "embedding.weight":
+                    add(p, dense)
+        for p in model.parameters():
+            add(p, dense)
+        return dense, sparse
+
+    def _torch_optimizers(self, dense, sparse):
+        """Empty stand-ins of the reference's optimisers (training.py:1315-1346): they only supply `param_groups` in the
+        layout of the installed torch version."""
+        eng = self.eng
+        mk = lambda names: [torch.nn.Parameter(torch.empty(0)) for _ in names]
+        hp = lambda k, d: getattr(eng, k, d)
+        opts = []
+        if dense:
+            kind = hp("kind", "adamw")
+            if kind == "sgd":
+                opts.append(torch.optim.SGD(mk(dense), lr=hp("lr", 1e-3), weight_decay=hp("wd", 0.0), momentum=hp("momentum", 0.0)))
+            else:
+                cls = torch.optim.AdamW if kind == "adamw" else torch.optim.Adam
+                opts.append(cls(mk(dense), lr=hp("lr", 1e-3), weight_decay=hp("wd", 0.0), betas=hp("dense_betas", (0.9, 0.999)),
+                                eps=hp("eps", 1e-8)))
+        if sparse:
+            opts.append(torch.optim.SparseAdam(mk(sparse), lr=hp("lr", 1e-3), betas=hp("sparse_betas", (0.9, 0.999)), eps=hp("eps", 1e-8)))
+        return opts
+
     @torch.no_grad()
     def save_checkpoint(self, path, num_users: int, num_items: int, *, epoch: int = 0, metric_name=None, metric_value=None):
-        """Rank 0 writes a `torch.save` dict with the reference's keys (training.py:173-181); every rank takes part in the
-        gather.  `optimizer_state_dicts` holds the engine's per-parameter moments under the same names (row-sharded ones
-        gathered likewise)."""
+        """Rank 0 writes the reference's checkpoint (training.py:150-182): `model_state_dict` un-sharded, and
+        `optimizer_state_dicts` = one `optimizer.state_dict()` per reference optimiser - the dense one, then SparseAdam - in
+        torch's own layout ({'state': {index: {step, exp_avg, exp_avg_sq}}, 'param_groups': [...]}, parameters in the order
+        the reference passes them), so `optimizer.load_state_dict` of a reference run accepts it.  Row-sharded moments are
+        gathered like the tables.  COLLECTIVE."""
         import time
         model_state = self.full_state_dict(num_users, num_items)
-        opt = {}
-        if hasattr(self.eng, "optimizer_state"):
-            for name, st in self.eng.optimizer_state().items():
-                ent = {"step": st["step"]}
+        dense, sparse = self._reference_param_groups()
+        opts = self._torch_optimizers(dense, sparse)
+        st = self.eng.optimizer_state() if hasattr(self.eng, "optimizer_state") else {}
+        dicts = []
+        for names, opt in zip([g for g in (dense, sparse) if g], opts):
+            sd = opt.state_dict()
+            is_sparse = isinstance(opt, torch.optim.SparseAdam)
+            for j, name in enumerate(names):            # every rank walks the same names: the gathers are collective
+                ent = st.get(name)
+                if ent is None:
+                    continue
+                slot = {"step": int(ent["step"]) if is_sparse else torch.tensor(float(ent["step"]))}
                 for k in ("exp_avg", "exp_avg_sq"):
-                    v = st.get(k)
-                    if v is not None and self._is_row_sharded(name):
+                    v = ent.get(k)
+                    if v is None:
+                        continue
+                    if self._is_row_sharded(name):
                         n = num_users if ("user_encoder" in name or "user_augmented" in name) else num_items
                         v = S.gather_rows_from_shards(v, n, self.group)
-                    ent[k] = None if v is None else v.detach().cpu().clone()
-                opt[name] = ent
+                    key = "momentum_buffer" if (k == "exp_avg" and isinstance(opt, torch.optim.SGD)) else k
+                    slot[key] = v.detach().cpu().clone()
+                if int(ent["step"]) > 0:
+                    sd["state"][j] = slot
+            dicts.append(sd)
         if self.rank == 0:
-            torch.save({"epoch": epoch, "model_state_dict": model_state, "optimizer_state_dicts": [opt],
+            torch.save({"epoch": epoch, "model_state_dict": model_state, "optimizer_state_dicts": dicts,
                         "metric_name": metric_name, "metric_value": metric_value, "timestamp": time.time()}, path)
         if self.world > 1:
             dist.barrier(group=self.group)
+
+    @torch.no_grad()
+    def load_checkpoint(self, path) -> dict:
+        """Resume from a checkpoint in the reference's layout (one written by `save_checkpoint`, by the one-GPU hooks, or by
+        the reference itself): every rank reads the file and keeps its rows of the tables and of their moments.  Returns
+        the checkpoint's metadata (epoch, metric_name, metric_value)."""
+        ck = torch.load(path, map_location="cpu", weights_only=False)
+        self.load_full_state_dict(ck["model_state_dict"])
+        dense, sparse = self._reference_param_groups()
+        state, step = {}, 0
+        for names, sd in zip([g for g in (dense, sparse) if g], ck.get("optimizer_state_dicts", [])):
+            for j, slot in sd.get("state", {}).items():
+                name = names[int(j)]
+                step = max(step, int(float(slot.get("step", 0))))
+                ent = {}
+                for k_src, k_dst in (("exp_avg", "exp_avg"), ("momentum_buffer", "exp_avg"), ("exp_avg_sq", "exp_avg_sq")):
+                    v = slot.get(k_src)
+                    if v is not None:
+                        ent[k_dst] = S.shard_rows(v, self.rank, self.world) if self._is_row_sharded(name) else v
+                state[name] = ent
+        if hasattr(self.eng, "load_optimizer_state"):
+            self.eng.load_optimizer_state(state, step)
+        self._static.clear()            # recorded graphs address the old step state
+        return {k: ck.get(k) for k in ("epoch", "metric_name", "metric_value")}
 
     @torch.no_grad()
     def export_item_embeddings(self, path, item_x_shard, num_items: int):
