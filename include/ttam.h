@@ -413,12 +413,13 @@ int ttam_topk_bf16(const uint16_t* q, const uint16_t* items, int64_t Q, int64_t 
                    int64_t id_offset, int64_t* out_ids, float* out_scores, void* workspace,
                    int64_t workspace_bytes, void* stream);
 /* fp32 index on the tensor cores (faiss.IndexFlatIP over fp32 embeddings, training.py:646-679, 944-958; K <= 128,
- * D <= 256): the candidate pass runs the bf16 tcgen05 kernel over a 3-way bf16 split of both operands
- * (x = hi + lo + r; queries laid out [hi | lo | hi], items [hi | hi | lo], each part padded to a multiple of 16 columns,
- * so one product over ttam_split_bf16x3_cols(D) columns is qh.xh + ql.xh + qh.xl), the survivors within the proven error
- * bound of the K-th score are re-scored from the fp32 rows in the canonical order.  Ids and scores are bit-identical to
- * ttam_topk_f32.  The caller keeps `items_split` next to the corpus (ttam_split_bf16x3 once per index build, item_layout = 1)
- * and splits each query batch (item_layout = 0). */
+ * D <= 256): every fp32 operand is split as x = hi + lo + r, hi = bf16(x), lo = bf16(x - hi), |r| <= 2^-16 |x|, and laid
+ * out as [hi | lo] (each part padded to a multiple of 16 columns: ttam_split_bf16x3_cols(D) = 2 * ceil16(D) columns).  The
+ * candidate pass runs the bf16 tcgen05 kernel with THREE products per column from those two copies,
+ * qh.xh + ql.xh + qh.xl (hence the name), the survivors within the proven error bound of the K-th score are re-scored from
+ * the fp32 rows in the canonical order.  Ids and scores are bit-identical to ttam_topk_f32.  The caller keeps
+ * `items_split` next to the corpus (ttam_split_bf16x3 once per index build) and splits each query batch; `item_layout`
+ * is ignored (both operands share one layout). */
 int64_t ttam_split_bf16x3_cols(int64_t D);
 int ttam_split_bf16x3(const float* x, int64_t R, int64_t D, int item_layout, uint16_t* out, void* stream);
 int64_t ttam_topk_f32_tc_workspace_bytes(int64_t Q, int64_t N, int64_t D, int64_t K);

@@ -32,7 +32,7 @@ for D in (96, 256):
     del ib, qb
     split = F.split_bf16x3(items, item_layout=True)
     ms = timed(lambda: F.topk_f32_tc(q, items, split, K))
-    print(json.dumps({"path": "fp32 index, tcgen05 candidates (3 x bf16 split)", "Q": Q, "N": N, "D": D, "ms": ms,
+    print(json.dumps({"path": "fp32 index, tcgen05 candidates (hi|lo split, 3 products)", "Q": Q, "N": N, "D": D, "ms": ms,
                       "qps": Q / ms * 1e3, "tflops_mma": 6.0 * Q * N * D / ms / 1e9}), flush=True)
     del split
     Qs = min(Q, 4096)

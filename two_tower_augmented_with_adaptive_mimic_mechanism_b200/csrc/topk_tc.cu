@@ -178,6 +178,7 @@ struct MainParams {
   int qblocks, tiles_total, tiles_per_split;
   int sample_tiles;  // T0: tiles of a unit's range visited first in sampling mode (0 = none)
   int kbox, stages;  // box-ring variant only: 64-column boxes per tile, ring slots
+  int split_ks;      // box-ring variant, fp32 index: 16-column steps per part of the [hi | lo] operands (0 = plain bf16 operands)
   int trig;          // a row's list is compacted to its best kKeep .. kKeep + kSlack once it holds more than this
   uint2* lists;     // [Q][S][kCap] raw {score bits, id}
   int32_t* cnts;    // [Q][S]
@@ -327,9 +328,28 @@ score_topk_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                   tc_fence_after();
                 }
                 const uint32_t d_tmem = tmem_base + (uint32_t)(a * kBN);
-                const uint64_t a_desc = a_desc0 + (uint64_t)(((a * kbox + kb) * kABoxBytes) >> 4);
-                for (int k = 0; k < kin; ++k)
-                  umma_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                if (p.split_ks == 0) {
+                  const uint64_t a_desc = a_desc0 + (uint64_t)(((a * kbox + kb) * kABoxBytes) >> 4);
+                  for (int k = 0; k < kin; ++k)
+                    umma_f16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                } else {
+                  // fp32 index: both operands are [hi | lo], split_ks 16-column steps each.  Item step bk of the hi part meets
+                  // the query's hi step bk AND its lo step (qh.xh + ql.xh), a step of the lo part the query's hi step
+                  // (qh.xl): three products from two resident copies - the query tiles are addressable at any step.
+                  auto a_at = [&](int ak) {
+                    return a_desc0 + (uint64_t)((((a * kbox + (ak >> 2)) * kABoxBytes) >> 4) + (uint32_t)((ak & 3) * 2));
+                  };
+                  for (int k = 0; k < kin; ++k) {
+                    const int bk = kb * 4 + k;
+                    const uint64_t bd = b_desc + (uint64_t)(k * 2);
+                    if (bk < p.split_ks) {
+                      umma_f16(d_tmem, a_at(bk), bd, idesc, bk ? 1u : 0u);
+                      umma_f16(d_tmem, a_at(p.split_ks + bk), bd, idesc, 1u);
+                    } else {
+                      umma_f16(d_tmem, a_at(bk - p.split_ks), bd, idesc, 1u);
+                    }
+                  }
+                }
                 if (kb == kbox - 1) umma_commit(acc_full + a);
               }
               umma_commit(b_empty + stage);
@@ -579,12 +599,11 @@ __device__ __forceinline__ float canonical_dot(const float* __restrict__ qf, con
 }
 
 // ---- fp32 index on the tensor cores: x = hi + lo + r with hi = bf16(x), lo = bf16(x - hi), |r| <= 2^-16 |x| ------------
-// Queries are laid out as [hi | lo | hi], items as [hi | hi | lo] (each part padded to Dp = 16-multiple columns), so one
-// bf16 tensor-core product over 3 Dp columns is  qh.xh + ql.xh + qh.xl = q.x - (ql.xl + residuals):
-// |tensor-core score - canonical fp32 score| <= (3.1 * 2^-16 + accumulation terms) * |q| |x|.  The candidate pass is the
-// bf16 kernel unchanged; the finalize kernel re-scores with the fp32 rows.
-__global__ void split_bf16x3_kernel(const float* __restrict__ x, int64_t R, int D, int Dp, int item_layout,
-                                    __nv_bfloat16* __restrict__ out) {
+// Queries and items are both laid out as [hi | lo] (each part padded to Dp = 16-multiple columns).  The MMA thread forms
+// qh.xh + ql.xh + qh.xl = q.x - (ql.xl + residuals) from those two copies (see the split_ks branch of the box-ring issuer):
+// |tensor-core score - canonical fp32 score| <= (3.1 * 2^-16 + accumulation terms) * |q| |x|.  The epilogue is the bf16
+// kernel's; the finalize kernel re-scores with the fp32 rows.
+__global__ void split_bf16_hi_lo_kernel(const float* __restrict__ x, int64_t R, int D, int Dp, __nv_bfloat16* __restrict__ out) {
   const int64_t total = R * Dp;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / Dp;
@@ -592,10 +611,9 @@ __global__ void split_bf16x3_kernel(const float* __restrict__ x, int64_t R, int 
     const float v = d < D ? x[r * D + d] : 0.f;
     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
     const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-    __nv_bfloat16* o = out + r * (3 * Dp) + d;
+    __nv_bfloat16* o = out + r * (2 * Dp) + d;
     o[0] = hi;
-    o[Dp] = item_layout ? hi : lo;
-    o[2 * Dp] = item_layout ? lo : hi;
+    o[Dp] = lo;
   }
 }
 
@@ -608,7 +626,7 @@ constexpr uint64_t kWorst = ~0ull;
 struct FinalParams {
   const __nv_bfloat16* q;      // bf16 index: the operands the tensor cores saw ARE the canonical ones
   const __nv_bfloat16* items;
-  const float* qf32;           // fp32 index: canonical operands (the tensor cores saw their 3-way bf16 split)
+  const float* qf32;           // fp32 index: canonical operands (the tensor cores saw their [hi | lo] bf16 split)
   const float* itemsf32;
   float delta_rel;             // |tensor-core score - canonical score| <= delta_rel * |q| * max|item|
   int64_t Q, N, id_offset;
@@ -823,10 +841,10 @@ struct Shape {
   int stages;   // ring slots
   uint32_t smem;
 };
-static Shape shape_for(int64_t Dm) {
+static Shape shape_for(int64_t Dm, bool split = false) {
   Shape sh{};
   sh.kbox = (int)ceil_div(Dm, (int64_t)kBoxK);
-  const bool force_ring = getenv("TTAM_TOPK_RING") != nullptr;   // A/B switch: small D through the box ring
+  const bool force_ring = split || getenv("TTAM_TOPK_RING") != nullptr;   // (env: A/B switch, small D through the box ring)
   if (sh.kbox <= 2 && !force_ring) {
     sh.kbox_t = sh.kbox; sh.atiles = 2;
     sh.stages = sh.kbox == 1 ? 4 : 2;
@@ -853,11 +871,11 @@ static int launch_main(const CUtensorMap& tq, const CUtensorMap& ti, const MainP
 }
 
 // The launch sequence shared by the bf16 index (qm / im are the canonical operands) and the fp32 index (qm / im are the
-// 3-way bf16 splits of qf / itf, which stay the canonical operands of the re-score).
+// [hi | lo] bf16 splits of qf / itf, which stay the canonical operands of the re-score).
 static int run_topk(const uint16_t* qm, const uint16_t* im, int64_t Dm, const float* qf, const float* itf, int64_t Q,
                     int64_t N, int64_t D, int64_t K, int64_t id_offset, int64_t* out_ids, float* out_scores,
                     void* workspace, int64_t workspace_bytes, cudaStream_t st) {
-  const Shape sh = shape_for(Dm);
+  const Shape sh = shape_for(Dm, itf != nullptr);
   if (sh.stages < 1) {
     set_error("topk: %lld operand columns do not fit the shared-memory ring", (long long)Dm);
     return TTAM_EUNSUPPORTED;
@@ -889,6 +907,7 @@ static int run_topk(const uint16_t* qm, const uint16_t* im, int64_t Dm, const fl
   mp.tiles_per_split = (int)ceil_div(mp.tiles_total, S);
   mp.lists = w.lists; mp.cnts = w.cnts; mp.taus = w.taus;
   mp.kbox = sh.kbox; mp.stages = sh.stages;
+  mp.split_ks = itf ? (int)(Dm / 32) : 0;     // Dm = 2 Dp columns = 2 * split_ks steps of 16
   mp.sample_tiles = 64;
   if (const char* e = getenv("TTAM_TOPK_SAMPLE_TILES")) mp.sample_tiles = atoi(e);
   mp.trig = kCap - 64;
@@ -915,7 +934,8 @@ static int run_topk(const uint16_t* qm, const uint16_t* im, int64_t Dm, const fl
   // fp32 accumulation of Dm exact bf16 products on either side (factor 4: alignment truncation inside the tensor core);
   // fp32 index: + the dropped lo.lo products and split residuals (3.1 * 2^-16) + the canonical fp32 sum's own rounding
   fp.delta_rel = 4.f * (float)Dm * 5.9604645e-8f;
-  if (itf) fp.delta_rel = 1.01f * (fp.delta_rel + 3.1f * 1.52587890625e-5f + 2.f * (float)D * 5.9604645e-8f);
+  if (itf)   // three products per column: 1.5 * Dm terms in the tensor-core sum
+    fp.delta_rel = 1.01f * (1.5f * fp.delta_rel + 3.1f * 1.52587890625e-5f + 2.f * (float)D * 5.9604645e-8f);
   fp.Q = Q; fp.N = N; fp.id_offset = id_offset; fp.D = (int)D; fp.S = S; fp.K = (int)K;
   fp.lists = w.lists; fp.cnts = w.cnts; fp.taus = w.taus; fp.max_norm_bits = w.max_norm_bits;
   fp.out_ids = out_ids; fp.out_scores = out_scores; fp.flagged = w.flagged; fp.n_flagged = w.n_flagged;
@@ -962,7 +982,7 @@ extern "C" int ttam_topk_bf16(const uint16_t* q, const uint16_t* items, int64_t 
 }
 
 // ---- fp32 index on the tensor cores ------------------------------------------------------------------------------------
-extern "C" int64_t ttam_split_bf16x3_cols(int64_t D) { return 3 * align_up(D, 16); }
+extern "C" int64_t ttam_split_bf16x3_cols(int64_t D) { return 2 * align_up(D, 16); }
 
 extern "C" int ttam_split_bf16x3(const float* x, int64_t R, int64_t D, int item_layout, uint16_t* out, void* stream) {
   TTAM_CHECK_ARG(R >= 0 && D > 0, "split_bf16x3: bad shape");
@@ -970,8 +990,8 @@ extern "C" int ttam_split_bf16x3(const float* x, int64_t R, int64_t D, int item_
   TTAM_CHECK_ARG(x && out, "split_bf16x3: null pointer");
   const int64_t Dp = align_up(D, 16);
   const int64_t blocks = std::min<int64_t>(ceil_div(R * Dp, 256), (int64_t)num_sms() * 16);
-  split_bf16x3_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, R, (int)D, (int)Dp, item_layout,
-                                                                         (__nv_bfloat16*)out);
+  (void)item_layout;   // both operands share the [hi | lo] layout (the argument is kept for ABI stability)
+  split_bf16_hi_lo_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, R, (int)D, (int)Dp, (__nv_bfloat16*)out);
   TTAM_LAUNCH_CHECK();
   return TTAM_OK;
 }
@@ -979,7 +999,7 @@ extern "C" int ttam_split_bf16x3(const float* x, int64_t R, int64_t D, int item_
 extern "C" int64_t ttam_topk_f32_tc_workspace_bytes(int64_t Q, int64_t N, int64_t D, int64_t K) {
   (void)K;
   if (Q <= 0 || N <= 0 || D <= 0) return 256;
-  return carve(nullptr, Q, choose_splits(Q, N, kBM * shape_for(ttam_split_bf16x3_cols(D)).atiles)).bytes;
+  return carve(nullptr, Q, choose_splits(Q, N, kBM * shape_for(ttam_split_bf16x3_cols(D), true).atiles)).bytes;
 }
 
 extern "C" int ttam_topk_f32_tc(const float* q, const float* items, const uint16_t* q_split, const uint16_t* items_split,

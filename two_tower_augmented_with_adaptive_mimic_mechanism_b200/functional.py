@@ -689,7 +689,8 @@ TOPK_TC_MAX_D = 256       # csrc/topk_tc.cu: kMaxD (both tensor-core paths)
 
 
 def split_bf16x3(x: torch.Tensor, *, item_layout: bool) -> torch.Tensor:
-    """fp32 [R, D] -> bf16 [R, 3*ceil16(D)]: the 3-way split operand of `topk_f32_tc` (items: [hi|hi|lo], queries: [hi|lo|hi])."""
+    """fp32 [R, D] -> bf16 [R, 2*ceil16(D)] = [hi | lo], hi = bf16(x), lo = bf16(x - hi): the operand of `topk_f32_tc`, whose
+    MMA schedule forms the three products qh.xh + ql.xh + qh.xl from the two copies (same layout for items and queries)."""
     _chk(x, torch.float32, "x")
     x = x.contiguous()
     R, D = x.shape

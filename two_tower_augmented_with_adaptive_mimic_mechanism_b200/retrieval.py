@@ -24,7 +24,7 @@ class FlatIPIndex:
     """Exact inner-product index over an item corpus resident in HBM (the IndexFlatIP stand-in).
 
     `dtype=torch.float32` keeps the reference's fp32 scores: searches with k <= 128 run their candidate pass on the
-    tcgen05 tensor cores over a 3-way bf16 split of the corpus (kept beside it, built on first use: 6 x D bytes per item)
+    tcgen05 tensor cores over a [hi | lo] bf16 split of the corpus (kept beside it, built on first use: 4 x D bytes per item)
     and re-score the survivors from the fp32 rows - ids and scores are bit-identical to the SIMT kernel, which deeper
     or paged searches still use (`tensor_cores=False` forces it everywhere).  `torch.bfloat16` rounds corpus and queries
     to bf16 and scores them on the tensor cores directly (BASELINE config 3)."""
