@@ -8,13 +8,12 @@ Q, N, K, D = 100_000, 2_000_000, 100, int(sys.argv[1]) if len(sys.argv) > 1 else
 g = torch.Generator(device="cuda").manual_seed(3)
 ib = (torch.randn((N, D), device="cuda", generator=g) * 0.3).bfloat16()
 qb = (torch.randn((Q, D), device="cuda", generator=g) * 0.3).bfloat16()
-for pipe in ("0", "1"):
-    for dbg in ("0", "2", "1", "9"):
-        os.environ["TTAM_TOPK_PIPE"], os.environ["TTAM_TOPK_DEBUG"] = pipe, dbg
-        F.topk(qb, ib, K); torch.cuda.synchronize()
-        best = 1e9
-        for _ in range(2):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); F.topk(qb, ib, K); e1.record(); torch.cuda.synchronize()
-            best = min(best, e0.elapsed_time(e1))
-        print(json.dumps({"D": D, "pipe": pipe, "debug": dbg, "ms": best, "tflops": 2.0 * Q * N * D / best / 1e9}), flush=True)
+for dbg in ("0", "2", "1", "9"):
+    os.environ["TTAM_TOPK_DEBUG"] = dbg
+    F.topk(qb, ib, K); torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); F.topk(qb, ib, K); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    print(json.dumps({"D": D, "debug": dbg, "ms": best, "tflops": 2.0 * Q * N * D / best / 1e9}), flush=True)
