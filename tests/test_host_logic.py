@@ -115,6 +115,44 @@ def test_filter_block_fetches_longer_lists_in_one_call():
         assert got[u] == retrieval.filter_candidates(full[r, : need[r]].tolist(), blocked[u], gt[u], max_k), r
 
 
+def test_evaluate_users_asks_a_tensor_core_index_for_128_first():
+    """evaluate_users against a stand-in index (no GPU): an fp32 index with tensor-core candidates is asked for at most 128
+    results per user, the users whose blocked items leave fewer than max_k of those get longer lists through ONE
+    search_deep call per block, and every prediction equals the reference's per-user filter over the full ranking."""
+    import numpy as np
+    import torch
+    rng = np.random.default_rng(9)
+    NU, NI, max_k = 30, 900, 10
+    full = np.stack([rng.permutation(NI) for _ in range(NU)]).astype(np.int64)
+
+    class Index:
+        tensor_cores, ntotal, max_k = True, NI, 1024
+        calls = []
+
+        def search(self, q, k):
+            self.calls.append(("search", int(q.shape[0]), int(k)))
+            rows = q[:, 0].long().numpy()
+            return torch.from_numpy(full[rows, :k]), None
+
+        def search_deep(self, q, k):
+            self.calls.append(("deep", int(q.shape[0]), int(k)))
+            rows = q[:, 0].long().numpy()
+            return full[rows, :k], None
+    gt = {u: set(rng.integers(0, NI, size=2).tolist()) for u in range(NU)}
+    blocked = {}
+    for u in range(NU):
+        n_top = 125 if u % 5 == 0 else int(rng.integers(0, 40))           # every fifth user: nearly all of the top 128 blocked
+        blocked[u] = set(full[u, :n_top].tolist()) - gt[u]
+    idx = Index()
+    q = torch.arange(NU, dtype=torch.float32).view(-1, 1)                 # query r "is" user r
+    preds = retrieval.evaluate_users(idx, q, list(range(NU)), gt, blocked, [5, max_k], query_block=16)
+    assert [c for c in idx.calls if c[0] == "search"] == [("search", 16, 128), ("search", 14, 128)]
+    assert len([c for c in idx.calls if c[0] == "deep"]) == 2             # one batched call per block
+    for u in range(NU):
+        need = max(max_k + len(gt[u]), 1) + len(blocked[u])
+        assert preds[u] == retrieval.filter_candidates(full[u, :need].tolist(), blocked[u], gt[u], max_k), u
+
+
 def test_bag_matrix_layout_roundtrip():
     """functional.BagMatrix (CSR over the sparse columns + dense tail) reproduces the dense matrix; a matrix with a row of more
     than 64 sparse non-zeros is refused (the engine keeps the dense GEMM path for it)."""
