@@ -30,7 +30,9 @@ constexpr int kSelThreads = 256;
 constexpr int kSelItems = 20;                       // 5120 keys per block
 constexpr int kSelCap = kSelThreads * kSelItems;
 
-constexpr int kPend = kSelCap - 1024;               // pending candidates per query (>= one chunk of scores)
+constexpr int kChunk = 4096;                        // items per scoring pass
+constexpr int kPend = kSelCap - 1024;               // pending candidates per query (>= kChunk; K + kPend <= kSelCap)
+static_assert(kPend >= kChunk && kChunk % kSelThreads == 0, "a chunk of survivors must fit the pending list");
 
 // running <- best K of (running  U  pending[0, cnt)); blocked arrangement: thread t owns slots t*kSelItems .. +kSelItems-1
 __device__ __forceinline__ void merge_pending(uint64_t* __restrict__ running, const uint64_t* __restrict__ pend, int cnt,
@@ -70,7 +72,7 @@ __global__ void __launch_bounds__(kSelThreads) select_topk_kernel(const float* _
   uint64_t* run = running + (int64_t)q * K;
   uint64_t* pend = pending + (int64_t)q * kPend;
   const uint64_t floor_key = after ? after[q] : 0ull;
-  constexpr int kPer = 4096 / kSelThreads;   // scores per thread (n <= 4096), strided: coalesced loads
+  constexpr int kPer = kChunk / kSelThreads;   // scores per thread (n <= kChunk), strided: coalesced loads
   uint64_t thr = run[K - 1];
   if (threadIdx.x == 0) s_new = 0;
   __syncthreads();
@@ -223,7 +225,6 @@ __global__ void __launch_bounds__(kMergeThreads) merge_kernel(const int64_t* __r
 }
 
 constexpr int kQBlock = 2048;   // queries per scoring pass
-constexpr int kChunk = 4096;    // items per scoring pass (<= kPend; K + kPend <= kSelCap)
 
 }  // namespace ttam
 
